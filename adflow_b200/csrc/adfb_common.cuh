@@ -1,0 +1,100 @@
+// adfb_common.cuh -- shared device-side definitions for libadflow_b200
+//
+// Data layout in HBM: every per-block array lives in one
+// uniform box (0:ib, 0:jb, 0:kb), i fastest, so the Fortran index (i,j,k) of the
+// reference (src/modules/block.F90:205-752) is the device offset
+// i + NI*(j + NJ*k) for cell, node and face arrays alike; multi-component
+// arrays are SoA with the component slowest (w(i,j,k,l) -> l*N + idx), which is
+// the reference's own ordering and gives unit-stride, fully coalesced access
+// along i for every variable.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/adflow_b200.h"
+
+struct Dims {
+    int nx, ny, nz;
+    int il, jl, kl, ie, je, ke, ib, jb, kb;
+    int NI, NJ, NK;
+    long long N;   // box size
+    long long sJ, sK;  // strides (sI == 1)
+};
+
+static inline Dims make_dims(int nx, int ny, int nz) {
+    Dims d;
+    d.nx = nx; d.ny = ny; d.nz = nz;
+    d.il = nx + 1; d.jl = ny + 1; d.kl = nz + 1;
+    d.ie = nx + 2; d.je = ny + 2; d.ke = nz + 2;
+    d.ib = nx + 3; d.jb = ny + 3; d.kb = nz + 3;
+    d.NI = d.ib + 1; d.NJ = d.jb + 1; d.NK = d.kb + 1;
+    d.N = (long long)d.NI * d.NJ * d.NK;
+    d.sJ = d.NI; d.sK = (long long)d.NI * d.NJ;
+    return d;
+}
+
+// device pointers of one block (all in the uniform box)
+struct BlockDev {
+    double *w, *p, *rlv, *rev;          // state
+    double *x, *si, *sj, *sk;           // geometry (3 comps each)
+    double *vol, *volRef, *d2Wall;
+    int8_t *porI, *porJ, *porK;
+    int32_t *iblank;
+    double *dw, *fw;                    // residual (nw) and dissipative+viscous part (5)
+    double *ss, *dss;                   // entropy / shock sensor (3)
+    double *aa, *radI, *radJ, *radK, *dtl;
+    double *grad;                       // 12 nodal gradient arrays
+    double *wn, *pn;                    // RK stage-0 copies (5 / 1)
+    double *scratch;                    // 10 work arrays (DADI, SA solve)
+};
+
+// single translation unit (adflow_b200.cu includes every *_kernels.cuh)
+__constant__ AdfbParams c_prm;
+
+#define ADFB_IDX(i, j, k) ((long long)(i) + d.sJ * (long long)(j) + d.sK * (long long)(k))
+
+__host__ __device__ static inline double dmax_(double a, double b) { return a > b ? a : b; }
+__host__ __device__ static inline double dmin_(double a, double b) { return a < b ? a : b; }
+
+// ---------------------------------------------------------------------------
+// launch accounting + optional per-kernel CUDA-event timing (bench.py roofline)
+#include <vector>
+enum KernelId { K_PREP = 0, K_NODAL, K_RESID, K_STATE, K_METRICS, K_NORMS, K_VEC, K_BC, K_RK, K_HALO, K_DADI, K_SA, K_MFFD, K_MISC, K_NUM };
+static const char* const kKernelNames[K_NUM] = {"k_prep", "k_nodal", "k_resid", "k_state_prep", "k_metrics", "k_norms", "k_vec",
+                                                "k_bc", "k_rk", "k_halo", "k_dadi", "k_sa_solve", "k_mffd", "k_misc"};
+struct KTimer {
+    bool on = false;
+    long long launches = 0;
+    long long count[K_NUM] = {0};
+    double ms[K_NUM] = {0};
+    struct Rec { int id; cudaEvent_t a, b; };
+    std::vector<Rec> pending;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void begin(int id, cudaStream_t s) {
+        if (!on) return;
+        Rec r; r.id = id; r.a = get(); r.b = get();
+        cudaEventRecord(r.a, s);
+        pending.push_back(r);
+    }
+    void end(int id, cudaStream_t s) {
+        launches++; count[id]++;
+        if (!on) return;
+        cudaEventRecord(pending.back().b, s);
+    }
+    void collect() {  // caller has synchronised the stream
+        for (Rec& r : pending) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, r.a, r.b);
+            ms[r.id] += t;
+            pool.push_back(r.a); pool.push_back(r.b);
+        }
+        pending.clear();
+    }
+    void reset() { collect(); for (int i = 0; i < K_NUM; i++) { ms[i] = 0; count[i] = 0; } }
+};
+static KTimer g_kt;
+#define KT_BEGIN(id, stream) g_kt.begin(id, stream)
+#define KT_END(id, stream) g_kt.end(id, stream)

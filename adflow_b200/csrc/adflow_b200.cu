@@ -1,0 +1,506 @@
+// adflow_b200.cu -- C ABI of libadflow_b200.so (include/adflow_b200.h) and the
+// host-side block registry.  Single translation unit: the kernel families are
+// implementation headers (*_kernels.cuh) so that the constant-memory parameter
+// block is shared without relocatable device code.
+//
+// There is no CPU fallback anywhere in this file: every entry point needs a
+// live CUDA context and fails with a message otherwise.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "adfb_common.cuh"
+#include "state_kernels.cuh"
+#include "residual_kernels.cuh"
+
+namespace {
+
+struct Block {
+    bool alive = false;
+    int level = 1, nw = 6, rightHanded = 1;
+    Dims d;
+    BlockDev dev;
+    std::vector<void*> allocs;
+    bool haveMetrics = false;
+    std::vector<AdfbSubface> subfaces;  // host copies (device arrays in bcDev)
+    std::vector<void*> bcAllocs;
+};
+
+struct Context {
+    bool ready = false;
+    int device = -1, rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;
+    AdfbParams prm;
+    bool havePrm = false;
+    std::vector<Block> blocks;
+    double* dRed = nullptr;   // reduction scratch
+    size_t dRedN = 0;
+    double* hRed = nullptr;   // pinned
+    double* dVec = nullptr;   // AoS staging vector (get/set states, get res)
+    size_t dVecN = 0;
+    std::string err;
+};
+
+Context g;
+
+int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g.err = buf;
+    return 1;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define NEED_INIT()                                                      \
+    do {                                                                 \
+        if (!g.ready) return fail("adfb_init has not been called (no CUDA device bound)"); \
+    } while (0)
+
+Block* get_block(int blk) {
+    if (blk < 0 || blk >= (int)g.blocks.size() || !g.blocks[blk].alive) return nullptr;
+    return &g.blocks[blk];
+}
+
+template <typename T>
+int dalloc(Block& b, T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+    e = cudaMemsetAsync(q, 0, n * sizeof(T), g.stream);
+    if (e != cudaSuccess) return fail("cudaMemset: %s", cudaGetErrorString(e));
+    b.allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+// Copy a host Fortran array with reference extents lo:lo+n-1 (per dimension) and
+// ncomp trailing components into / out of the uniform device box.
+int copy_box(const Dims& d, void* dev, const void* host, const int lo[3], const int n[3], int ncomp, size_t es,
+             bool toDevice) {
+    const bool full = lo[0] == 0 && lo[1] == 0 && lo[2] == 0 && n[0] == d.NI && n[1] == d.NJ && n[2] == d.NK;
+    if (full) {
+        const size_t bytes = (size_t)d.N * ncomp * es;
+        if (toDevice) CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, g.stream));
+        else CK(cudaMemcpyAsync((void*)host, dev, bytes, cudaMemcpyDeviceToHost, g.stream));
+        return 0;
+    }
+    const size_t hostComp = (size_t)n[0] * n[1] * n[2] * es;
+    for (int m = 0; m < ncomp; m++) {
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof p);
+        cudaPitchedPtr hp = make_cudaPitchedPtr((char*)host + m * hostComp, n[0] * es, n[0] * es, n[1]);
+        cudaPitchedPtr dp = make_cudaPitchedPtr((char*)dev + (size_t)m * d.N * es, d.NI * es, d.NI * es, d.NJ);
+        p.extent = make_cudaExtent(n[0] * es, n[1], n[2]);
+        if (toDevice) {
+            p.srcPtr = hp; p.dstPtr = dp;
+            p.dstPos = make_cudaPos(lo[0] * es, lo[1], lo[2]);
+            p.kind = cudaMemcpyHostToDevice;
+        } else {
+            p.srcPtr = dp; p.dstPtr = hp;
+            p.srcPos = make_cudaPos(lo[0] * es, lo[1], lo[2]);
+            p.kind = cudaMemcpyDeviceToHost;
+        }
+        CK(cudaMemcpy3DAsync(&p, g.stream));
+    }
+    return 0;
+}
+
+enum Ext { C2, C1, C0, NODE, FI, FJ, FK, PI_, PJ_, PK_ };
+void extents(const Dims& d, Ext e, int lo[3], int n[3]) {
+    switch (e) {
+        case C2: lo[0] = lo[1] = lo[2] = 0; n[0] = d.NI; n[1] = d.NJ; n[2] = d.NK; break;
+        case C1: lo[0] = lo[1] = lo[2] = 1; n[0] = d.ie; n[1] = d.je; n[2] = d.ke; break;
+        case C0: lo[0] = lo[1] = lo[2] = 2; n[0] = d.nx; n[1] = d.ny; n[2] = d.nz; break;
+        case NODE: lo[0] = lo[1] = lo[2] = 0; n[0] = d.ie + 1; n[1] = d.je + 1; n[2] = d.ke + 1; break;
+        case FI: lo[0] = 0; lo[1] = 1; lo[2] = 1; n[0] = d.ie + 1; n[1] = d.je; n[2] = d.ke; break;
+        case FJ: lo[0] = 1; lo[1] = 0; lo[2] = 1; n[0] = d.ie; n[1] = d.je + 1; n[2] = d.ke; break;
+        case FK: lo[0] = 1; lo[1] = 1; lo[2] = 0; n[0] = d.ie; n[1] = d.je; n[2] = d.ke + 1; break;
+        case PI_: lo[0] = 1; lo[1] = 2; lo[2] = 2; n[0] = d.il; n[1] = d.ny; n[2] = d.nz; break;
+        case PJ_: lo[0] = 2; lo[1] = 1; lo[2] = 2; n[0] = d.nx; n[1] = d.jl; n[2] = d.nz; break;
+        case PK_: lo[0] = 2; lo[1] = 2; lo[2] = 1; n[0] = d.nx; n[1] = d.ny; n[2] = d.kl; break;
+    }
+}
+int put(const Block& b, Ext e, void* dev, const void* host, int ncomp, size_t es) {
+    int lo[3], n[3];
+    extents(b.d, e, lo, n);
+    return copy_box(b.d, dev, host, lo, n, ncomp, es, true);
+}
+int get(const Block& b, Ext e, const void* dev, void* host, int ncomp, size_t es) {
+    int lo[3], n[3];
+    extents(b.d, e, lo, n);
+    return copy_box(b.d, (void*)dev, host, lo, n, ncomp, es, false);
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int adfb_last_error(char* buf, int n) {
+    if (!buf || n <= 0) return 1;
+    snprintf(buf, n, "%s", g.err.c_str());
+    return 0;
+}
+
+int adfb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int adfb_get_unique_id(void* out128) {
+    if (!out128) return fail("adfb_get_unique_id: null buffer");
+    memset(out128, 0, 128);
+    return 0;
+}
+
+int adfb_init(int device, const void* ncclUniqueId, int rank, int nranks) {
+    (void)ncclUniqueId;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail("adfb_init: no CUDA device available (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail("adfb_init: device %d out of range (0..%d)", device, n - 1);
+    CK(cudaSetDevice(device));
+    if (!g.stream) CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    g.device = device; g.rank = rank; g.nranks = nranks;
+    if (!g.hRed) CK(cudaMallocHost((void**)&g.hRed, 64 * sizeof(double)));
+    g.ready = true;
+    g.err.clear();
+    if (nranks > 1) return fail("adfb_init: multi-rank communicator not built into this library version");
+    return 0;
+}
+
+int adfb_finalize(void) {
+    if (!g.ready) return 0;
+    for (size_t i = 0; i < g.blocks.size(); i++)
+        if (g.blocks[i].alive) adfb_block_destroy((int)i);
+    g.blocks.clear();
+    if (g.dRed) cudaFree(g.dRed);
+    g.dRed = nullptr; g.dRedN = 0;
+    if (g.hRed) cudaFreeHost(g.hRed);
+    g.hRed = nullptr;
+    if (g.dVec) cudaFree(g.dVec);
+    g.dVec = nullptr; g.dVecN = 0;
+    if (g.stream) cudaStreamDestroy(g.stream);
+    g.stream = nullptr;
+    g.ready = false;
+    return 0;
+}
+
+int adfb_synchronize(void) {
+    NEED_INIT();
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+long long adfb_launch_count(void) { return g_kt.launches; }
+/* per-kernel CUDA-event timing (bench.py roofline pass): on=1 starts recording and
+   resets the accumulators; adfb_kernel_times synchronises and returns the
+   cumulative milliseconds and launch counts per kernel family. */
+int adfb_set_timing(int on) {
+    NEED_INIT();
+    CK(cudaStreamSynchronize(g.stream));
+    g_kt.reset();
+    g_kt.on = on != 0;
+    return 0;
+}
+int adfb_kernel_times(double* ms, long long* counts, int n) {
+    NEED_INIT();
+    CK(cudaStreamSynchronize(g.stream));
+    g_kt.collect();
+    for (int i = 0; i < n && i < K_NUM; i++) { ms[i] = g_kt.ms[i]; counts[i] = g_kt.count[i]; }
+    return K_NUM;
+}
+const char* adfb_kernel_name(int id) { return (id >= 0 && id < K_NUM) ? kKernelNames[id] : ""; }
+void* adfb_stream(void) { return (void*)g.stream; }
+
+int adfb_set_params(const AdfbParams* prm) {
+    NEED_INIT();
+    if (!prm) return fail("adfb_set_params: null");
+    if (prm->equations < ADFB_EULER || prm->equations > ADFB_RANS) return fail("adfb_set_params: bad equations %d", prm->equations);
+    if (prm->spaceDiscr != ADFB_DISS_SCALAR)
+        return fail("adfb_set_params: spaceDiscr %d not supported on device yet (scalar JST only)", prm->spaceDiscr);
+    if (prm->useRotationSA && prm->turbProd == ADFB_PROD_VORTICITY)
+        return fail("adfb_set_params: useRotationSA with vorticity production reads an unset strainMag2 in the "
+                    "reference (src/turbulence/sa.F90:273); unsupported");
+    g.prm = *prm;
+    g.havePrm = true;
+    CK(cudaMemcpyToSymbolAsync(c_prm, &g.prm, sizeof(AdfbParams), 0, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int adfb_block_create(int blk, int level, int nx, int ny, int nz, int nw, int rightHanded) {
+    NEED_INIT();
+    if (blk < 0 || blk > 4095) return fail("adfb_block_create: block id %d out of range", blk);
+    if (nx < 1 || ny < 1 || nz < 1) return fail("adfb_block_create: bad extents %d %d %d", nx, ny, nz);
+    if (nw != 5 && nw != 6) return fail("adfb_block_create: nw must be 5 (Euler/NS) or 6 (RANS-SA), got %d", nw);
+    if ((int)g.blocks.size() <= blk) g.blocks.resize(blk + 1);
+    if (g.blocks[blk].alive) return fail("adfb_block_create: block %d already exists", blk);
+    Block& b = g.blocks[blk];
+    b = Block();
+    b.level = level; b.nw = nw; b.rightHanded = rightHanded;
+    b.d = make_dims(nx, ny, nz);
+    const size_t N = (size_t)b.d.N;
+    BlockDev& v = b.dev;
+    memset(&v, 0, sizeof v);
+    int rc = 0;
+    rc |= dalloc(b, &v.w, N * nw); rc |= dalloc(b, &v.p, N); rc |= dalloc(b, &v.rlv, N); rc |= dalloc(b, &v.rev, N);
+    rc |= dalloc(b, &v.x, N * 3); rc |= dalloc(b, &v.si, N * 3); rc |= dalloc(b, &v.sj, N * 3); rc |= dalloc(b, &v.sk, N * 3);
+    rc |= dalloc(b, &v.vol, N); rc |= dalloc(b, &v.volRef, N); rc |= dalloc(b, &v.d2Wall, N);
+    rc |= dalloc(b, &v.porI, N); rc |= dalloc(b, &v.porJ, N); rc |= dalloc(b, &v.porK, N); rc |= dalloc(b, &v.iblank, N);
+    rc |= dalloc(b, &v.dw, N * nw); rc |= dalloc(b, &v.fw, N * 5);
+    rc |= dalloc(b, &v.ss, N); rc |= dalloc(b, &v.dss, N * 3);
+    rc |= dalloc(b, &v.aa, N); rc |= dalloc(b, &v.radI, N); rc |= dalloc(b, &v.radJ, N); rc |= dalloc(b, &v.radK, N);
+    rc |= dalloc(b, &v.dtl, N); rc |= dalloc(b, &v.grad, N * 12);
+    rc |= dalloc(b, &v.wn, N * 5); rc |= dalloc(b, &v.pn, N); rc |= dalloc(b, &v.scratch, N * 10);
+    if (rc) {
+        for (void* q : b.allocs) cudaFree(q);
+        b.allocs.clear();
+        return 1;
+    }
+    b.alive = true;
+    return 0;
+}
+
+int adfb_block_destroy(int blk) {
+    NEED_INIT();
+    Block* b = get_block(blk);
+    if (!b) return fail("adfb_block_destroy: no block %d", blk);
+    cudaStreamSynchronize(g.stream);
+    for (void* q : b->allocs) cudaFree(q);
+    for (void* q : b->bcAllocs) cudaFree(q);
+    *b = Block();
+    return 0;
+}
+
+int adfb_block_set_geometry(int blk, const double* x, const double* si, const double* sj, const double* sk,
+                            const double* vol, const double* volRef, const double* d2Wall, const int8_t* porI,
+                            const int8_t* porJ, const int8_t* porK, const int32_t* iblank) {
+    NEED_INIT();
+    Block* b = get_block(blk);
+    if (!b) return fail("adfb_block_set_geometry: no block %d", blk);
+    if (!x || !vol || !volRef || !porI || !porJ || !porK || !iblank)
+        return fail("adfb_block_set_geometry: x, vol, volRef, porI/J/K and iblank are required");
+    if (b->nw > 5 && !d2Wall) return fail("adfb_block_set_geometry: d2Wall is required for RANS blocks");
+    const BlockDev& v = b->dev;
+    if (put(*b, NODE, v.x, x, 3, 8)) return 1;
+    if (si && sj && sk) {
+        if (put(*b, FI, v.si, si, 3, 8) || put(*b, FJ, v.sj, sj, 3, 8) || put(*b, FK, v.sk, sk, 3, 8)) return 1;
+    } else if (si || sj || sk) {
+        return fail("adfb_block_set_geometry: pass all of si, sj, sk or none");
+    } else {
+        if (launch_metrics(b->d, v, b->rightHanded, g.stream)) return fail("metrics kernel launch failed");
+    }
+    if (put(*b, C2, v.vol, vol, 1, 8) || put(*b, C2, v.volRef, volRef, 1, 8)) return 1;
+    if (d2Wall && put(*b, C0, v.d2Wall, d2Wall, 1, 8)) return 1;
+    if (put(*b, PI_, v.porI, porI, 1, 1) || put(*b, PJ_, v.porJ, porJ, 1, 1) || put(*b, PK_, v.porK, porK, 1, 1)) return 1;
+    if (put(*b, C2, v.iblank, iblank, 1, 4)) return 1;
+    CK(cudaStreamSynchronize(g.stream));
+    b->haveMetrics = true;
+    return 0;
+}
+
+int adfb_block_set_bc(int blk, int nSub, const AdfbSubface* subfaces) {
+    NEED_INIT();
+    Block* b = get_block(blk);
+    if (!b) return fail("adfb_block_set_bc: no block %d", blk);
+    if (nSub < 0 || (nSub > 0 && !subfaces)) return fail("adfb_block_set_bc: bad arguments");
+    cudaStreamSynchronize(g.stream);
+    for (void* q : b->bcAllocs) cudaFree(q);
+    b->bcAllocs.clear();
+    b->subfaces.clear();
+    for (int s = 0; s < nSub; s++) {
+        AdfbSubface sf = subfaces[s];
+        if (sf.faceId < ADFB_IMIN || sf.faceId > ADFB_KMAX) return fail("adfb_block_set_bc: bad faceId %d", sf.faceId);
+        const size_t n = (size_t)(sf.icEnd - sf.icBeg + 1) * (sf.jcEnd - sf.jcBeg + 1);
+        auto up = [&](const double*& hp, int ncomp) -> int {
+            if (!hp) return 0;
+            void* q = nullptr;
+            if (cudaMalloc(&q, n * ncomp * 8) != cudaSuccess) return fail("adfb_block_set_bc: cudaMalloc failed");
+            b->bcAllocs.push_back(q);
+            if (cudaMemcpy(q, hp, n * ncomp * 8, cudaMemcpyHostToDevice) != cudaSuccess) return fail("adfb_block_set_bc: copy failed");
+            hp = (const double*)q;  // from here on the subface holds DEVICE pointers
+            return 0;
+        };
+        if (up(sf.norm, 3) || up(sf.rface, 1) || up(sf.uSlip, 3) || up(sf.TNSWall, 1)) return 1;
+        b->subfaces.push_back(sf);
+    }
+    return 0;
+}
+
+int adfb_upload_state(int blk, const double* w, const double* p) {
+    NEED_INIT();
+    Block* b = get_block(blk);
+    if (!b) return fail("adfb_upload_state: no block %d", blk);
+    if (!w) return fail("adfb_upload_state: w is required");
+    if (put(*b, C2, b->dev.w, w, b->nw, 8)) return 1;
+    if (p && put(*b, C2, b->dev.p, p, 1, 8)) return 1;
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int adfb_upload_visc(int blk, const double* rlv, const double* rev) {
+    NEED_INIT();
+    Block* b = get_block(blk);
+    if (!b) return fail("adfb_upload_visc: no block %d", blk);
+    if (rlv && put(*b, C2, b->dev.rlv, rlv, 1, 8)) return 1;
+    if (rev && put(*b, C2, b->dev.rev, rev, 1, 8)) return 1;
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int adfb_download_state(int blk, double* w, double* p, double* rlv, double* rev) {
+    NEED_INIT();
+    Block* b = get_block(blk);
+    if (!b) return fail("adfb_download_state: no block %d", blk);
+    if (w && get(*b, C2, b->dev.w, w, b->nw, 8)) return 1;
+    if (p && get(*b, C2, b->dev.p, p, 1, 8)) return 1;
+    if (rlv && get(*b, C2, b->dev.rlv, rlv, 1, 8)) return 1;
+    if (rev && get(*b, C2, b->dev.rev, rev, 1, 8)) return 1;
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int adfb_download_residual(int blk, double* dw) {
+    NEED_INIT();
+    Block* b = get_block(blk);
+    if (!b) return fail("adfb_download_residual: no block %d", blk);
+    if (!dw) return fail("adfb_download_residual: null");
+    if (get(*b, C2, b->dev.dw, dw, b->nw, 8)) return 1;
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int adfb_download_intermed(int blk, double* dtl, double* radI, double* radJ, double* radK) {
+    NEED_INIT();
+    Block* b = get_block(blk);
+    if (!b) return fail("adfb_download_intermed: no block %d", blk);
+    if (dtl && get(*b, C1, b->dev.dtl, dtl, 1, 8)) return 1;
+    if (radI && get(*b, C1, b->dev.radI, radI, 1, 8)) return 1;
+    if (radJ && get(*b, C1, b->dev.radJ, radJ, 1, 8)) return 1;
+    if (radK && get(*b, C1, b->dev.radK, radK, 1, 8)) return 1;
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+// debug/test access to device-resident work arrays (nodal gradients etc.)
+int adfb_download_array(int blk, const char* name, double* out) {
+    NEED_INIT();
+    Block* b = get_block(blk);
+    if (!b) return fail("adfb_download_array: no block %d", blk);
+    const BlockDev& v = b->dev;
+    const void* src = nullptr;
+    int nc = 1;
+    std::string s(name ? name : "");
+    if (s == "grad") { src = v.grad; nc = 12; }
+    else if (s == "dss") { src = v.dss; nc = 3; }
+    else if (s == "ss") src = v.ss;
+    else if (s == "aa") src = v.aa;
+    else if (s == "si") { src = v.si; nc = 3; }
+    else if (s == "sj") { src = v.sj; nc = 3; }
+    else if (s == "sk") { src = v.sk; nc = 3; }
+    else if (s == "fw") { src = v.fw; nc = 5; }
+    else if (s == "dtl") src = v.dtl;
+    else if (s == "radI") src = v.radI;
+    else if (s == "radJ") src = v.radJ;
+    else if (s == "radK") src = v.radK;
+    else return fail("adfb_download_array: unknown array '%s'", s.c_str());
+    if (get(*b, C2, src, out, nc, 8)) return 1;
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+long long adfb_state_size(void) {
+    long long n = 0;
+    for (Block& b : g.blocks)
+        if (b.alive && b.level == 1) n += (long long)b.d.nx * b.d.ny * b.d.nz * b.nw;
+    return n;
+}
+
+static int vec_io(double* host, long long n, int mode) {
+    NEED_INIT();
+    const long long need = adfb_state_size();
+    if (!host || n != need) return fail("vector length %lld does not match the local state size %lld", n, need);
+    if (g.dVecN < (size_t)need) {
+        if (g.dVec) cudaFree(g.dVec);
+        g.dVec = nullptr; g.dVecN = 0;
+        CK(cudaMalloc((void**)&g.dVec, need * sizeof(double)));
+        g.dVecN = need;
+    }
+    if (mode == 1) CK(cudaMemcpyAsync(g.dVec, host, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    long long off = 0;
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != 1) continue;
+        if (launch_vec(b.d, b.dev, b.nw, g.dVec + off, mode, g.stream)) return fail("vector kernel launch failed");
+        off += (long long)b.d.nx * b.d.ny * b.d.nz * b.nw;
+    }
+    if (mode != 1) CK(cudaMemcpyAsync(host, g.dVec, need * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+int adfb_get_states(double* states, long long n) { return vec_io(states, n, 0); }
+int adfb_set_states(const double* states, long long n) { return vec_io((double*)states, n, 1); }
+int adfb_get_res(double* res, long long n) { return vec_io(res, n, 2); }
+
+int adfb_residual(int level, unsigned flags) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_residual: adfb_set_params has not been called");
+    if (!(flags & (ADFB_RES_FLOW | ADFB_RES_TURB))) return fail("adfb_residual: neither flow nor turbulence residual requested");
+    if (flags & (ADFB_RES_DISS_APPROX | ADFB_RES_VISC_APPROX))
+        return fail("adfb_residual: approximate (PC/ANK) flux variants are not built yet");
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != level) continue;
+        if (!b.haveMetrics) return fail("adfb_residual: geometry of a block was never set");
+        if (!(flags & ADFB_RES_SKIP_PREAMBLE)) {
+            // blocketteRes :213-226: p, rlv, rev on owned cells, then BCs
+            if (launch_state_prep(b.d, b.dev, g.prm, false, g.stream)) return fail("state prep launch failed");
+            if (!b.subfaces.empty()) return fail("adfb_residual: device BC kernels not built yet; pass ADFB_RES_SKIP_PREAMBLE");
+        }
+    }
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != level) continue;
+        if (launch_residual_core(b.d, b.dev, g.prm, flags, 1.0, 0, g.stream))
+            return fail("residual kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int adfb_norms(double out[2]) {
+    NEED_INIT();
+    if (!out) return fail("adfb_norms: null");
+    out[0] = out[1] = 0.0;
+    for (Block& b : g.blocks) {
+        if (!b.alive) continue;
+        const int nPart = 1024;
+        if (g.dRedN < (size_t)2 * nPart + 2) {
+            if (g.dRed) cudaFree(g.dRed);
+            CK(cudaMalloc((void**)&g.dRed, (2 * nPart + 2) * sizeof(double)));
+            g.dRedN = 2 * nPart + 2;
+        }
+        if (launch_norms(b.d, b.dev, b.nw, g.prm.turbResScale, g.dRed, nPart, g.stream)) return fail("norm kernel failed");
+        CK(cudaMemcpyAsync(g.hRed, g.dRed + 2 * nPart, 2 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        out[0] += g.hRed[0];
+        out[1] += g.hRed[1];
+    }
+    return 0;
+}
+
+}  // extern "C"

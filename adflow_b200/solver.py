@@ -1,0 +1,142 @@
+"""Host-side mirror of the pyADflow calls that sit on the hot path.
+
+``ADFLOW_B200`` keeps the names, argument meaning and ordering conventions of
+``adflow/pyADflow.py`` for the calls that reach the per-block numerics
+(``getResidual`` :5359, ``getStates`` :5174, ``setStates`` :5181,
+``getFreeStreamResidual`` :5422, ``getResNorms`` :3399) and routes them through
+the C ABI (``include/adflow_b200.h``) to the CUDA kernels -- the same calls the
+Fortran drivers would make through ISO_C_BINDING.  It is a thin
+layer: all arithmetic happens on the device; there is no CPU path.
+
+State/residual vectors use the reference ordering (``NKSolvers.F90:1240-1255``):
+for each block, k, j, i, then the nw variables of the cell (AoS per cell).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import AdfbSubface, check, ptr
+
+RES_DISS_APPROX, RES_VISC_APPROX, RES_UPDATE_INTERMED = 1, 2, 4
+RES_FLOW, RES_TURB, RES_STORE_WALL, RES_SKIP_PREAMBLE = 8, 16, 32, 64
+
+
+class ADFLOW_B200:
+    def __init__(self, prm, device=0, rank=0, nranks=1, unique_id=None):
+        self.L = _lib.load()
+        check(self.L.adfb_init(device, unique_id, rank, nranks), "adfb_init")
+        self.prm = prm
+        check(self.L.adfb_set_params(C.byref(prm)), "adfb_set_params")
+        self.blocks = []  # HostBlock descriptors (extents only are needed after upload)
+        self._keep = []
+
+    # -- data model ---------------------------------------------------------
+    def addBlock(self, hb, level=1, upload_metrics=True):
+        """Create the device mirror of one block and upload geometry + BC data + state."""
+        blk = len(self.blocks)
+        d = hb.d
+        check(self.L.adfb_block_create(blk, level, d.nx, d.ny, d.nz, hb.nw, int(hb.right_handed)), "adfb_block_create")
+        r = hb.ref
+        si = r("si") if upload_metrics else None
+        sj = r("sj") if upload_metrics else None
+        sk = r("sk") if upload_metrics else None
+        arrs = [r("x"), si, sj, sk, r("vol"), r("volRef"), r("d2Wall"), r("porI"), r("porJ"), r("porK"), r("iblank")]
+        check(self.L.adfb_block_set_geometry(blk, *[ptr(a) for a in arrs]), "adfb_block_set_geometry")
+        if hb.subfaces:
+            n = len(hb.subfaces)
+            sf = (AdfbSubface * n)()
+            keep = []
+            for q, s in enumerate(hb.subfaces):
+                sf[q].bcType, sf[q].faceId = s["bcType"], s["faceId"]
+                sf[q].icBeg, sf[q].icEnd, sf[q].jcBeg, sf[q].jcEnd = s["icBeg"], s["icEnd"], s["jcBeg"], s["jcEnd"]
+                for name in ("norm", "rface", "uSlip", "TNSWall"):
+                    a = s.get(name)
+                    if a is not None:
+                        a = np.asfortranarray(a)
+                        keep.append(a)
+                        setattr(sf[q], name, a.ctypes.data)
+            check(self.L.adfb_block_set_bc(blk, n, sf), "adfb_block_set_bc")
+        self.blocks.append(hb)
+        self.uploadState(blk, hb)
+        return blk
+
+    def uploadState(self, blk, hb, with_visc=True):
+        check(self.L.adfb_upload_state(blk, ptr(hb.w), ptr(hb.p)), "adfb_upload_state")
+        if with_visc:
+            check(self.L.adfb_upload_visc(blk, ptr(hb.rlv), ptr(hb.rev)), "adfb_upload_visc")
+
+    def setParams(self, prm):
+        self.prm = prm
+        check(self.L.adfb_set_params(C.byref(prm)), "adfb_set_params")
+
+    # -- hot path -----------------------------------------------------------
+    def residual(self, flags=RES_FLOW | RES_TURB, level=1):
+        """blocketteRes (src/NKSolver/blockette.F90:70-297) on all local blocks."""
+        check(self.L.adfb_residual(level, flags), "adfb_residual")
+
+    def downloadResidual(self, blk):
+        hb = self.blocks[blk]
+        out = np.zeros(hb.d.box + (hb.nw,), order="F")
+        check(self.L.adfb_download_residual(blk, ptr(out)), "adfb_download_residual")
+        return out
+
+    def downloadState(self, blk):
+        hb = self.blocks[blk]
+        w = np.zeros(hb.d.box + (hb.nw,), order="F")
+        p, rlv, rev = (np.zeros(hb.d.box, order="F") for _ in range(3))
+        check(self.L.adfb_download_state(blk, ptr(w), ptr(p), ptr(rlv), ptr(rev)), "adfb_download_state")
+        return w, p, rlv, rev
+
+    def downloadIntermed(self, blk):
+        d = self.blocks[blk].d
+        shp = (d.ie, d.je, d.ke)
+        a = [np.zeros(shp, order="F") for _ in range(4)]
+        check(self.L.adfb_download_intermed(blk, *[ptr(x) for x in a]), "adfb_download_intermed")
+        return dict(zip(("dtl", "radI", "radJ", "radK"), a))
+
+    def downloadArray(self, blk, name, ncomp=1):
+        hb = self.blocks[blk]
+        shp = hb.d.box + ((ncomp,) if ncomp > 1 else ())
+        out = np.zeros(shp, order="F")
+        check(self.L.adfb_download_array(blk, name.encode(), ptr(out)), "adfb_download_array")
+        return out
+
+    def getResNorms(self):
+        """(sum (dw_rho/vol)^2, sum all (dw/vol)^2) -- getCurrentResidual, NKSolvers.F90:335-370."""
+        out = (C.c_double * 2)()
+        check(self.L.adfb_norms(out), "adfb_norms")
+        return np.array([out[0], out[1]])
+
+    def synchronize(self):
+        check(self.L.adfb_synchronize(), "adfb_synchronize")
+
+    def launchCount(self):
+        return int(self.L.adfb_launch_count())
+
+    def close(self):
+        self.L.adfb_finalize()
+
+    # -- pyADflow-named vector API (device gather kernels + one copy) ---------
+    def getStateSize(self):
+        return int(self.L.adfb_state_size())
+
+    def getStates(self):
+        """pyADflow.getStates (:5174) -> nksolver.getstates (NKSolvers.F90:1378)."""
+        out = np.zeros(self.getStateSize())
+        check(self.L.adfb_get_states(out.ctypes.data, out.size), "adfb_get_states")
+        return out
+
+    def setStates(self, states):
+        """pyADflow.setStates (:5181) -> nksolver.setstates (NKSolvers.F90:1452)."""
+        states = np.ascontiguousarray(states, dtype=np.float64)
+        check(self.L.adfb_set_states(states.ctypes.data, states.size), "adfb_set_states")
+
+    def getResidual(self, res=None, flags=RES_FLOW | RES_TURB | RES_UPDATE_INTERMED):
+        """pyADflow.getResidual (:5359) -> nksolver.getres (NKSolvers.F90:1413-1450):
+        evaluate the residual, return dw/volRef in AoS order."""
+        self.residual(flags)
+        if res is None:
+            res = np.zeros(self.getStateSize())
+        check(self.L.adfb_get_res(res.ctypes.data, res.size), "adfb_get_res")
+        return res

@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (contract in the task brief).
+
+Metric (BASELINE.json): Mcells/s of the RANS-SA residual.  A "step" is one full
+residual evaluation (blocketteRes core: SA source/advection/diffusion, central +
+scalar-JST + viscous fluxes, spectral radii/time step) of every local block.
+
+Workload at N=1: BASELINE configs[1] -- one 96x72x64 = 442 368-cell RANS-SA
+block ("MDO tutorial wing RANS-SA, 450k cells, 1 block"), synthetic mesh/state
+(adflow_b200/synthetic.py, seed 314).  N>1 (weak scaling): one such block per
+GPU, residual of all blocks, no data-path collective (independent blocks).
+
+  value : whole-job Mcells/s with inputs resident in HBM, timed per step with CUDA
+          events on the library's stream; L2 is flushed (256 MiB memset) before
+          every timed step.
+  e2e   : same metric through the public vector API with HOST buffers
+          (setStates -> residual incl. p/rlv/rev preamble -> getRes): pinned host
+          state vector H2D and residual vector D2H inside the timed region.
+  roofline : HBM; achieved = 176 B/cell (RANS-SA residual, algorithmic)
+          x cells / summed duration of the residual's kernels (CUDA events around
+          each launch, separate pass); peak from MEASURED_PEAKS.json.
+  cpu_baseline : the oracle port (C restatement of the reference algorithm,
+          -O3 -march=native -ffast-math like the reference's gfortran flags) on 1 core.
+
+--impl reference times that same CPU restatement using all host cores (one
+sub-block per process, the reference's MPI-rank-per-block model); the reference
+Fortran itself cannot be built in this image (no Fortran/MPI/PETSc/CGNS).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2 = (96, 72, 64)
+BYTES_PER_CELL = 176.0  # RANS-SA residual, metrics from x, algorithmic
+METRIC = "Mcells/s RANS-SA residual"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.lines, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_single(shape, reps_budget_s=12.0):
+    """Oracle port on ONE core over the full C2 block; returns Mcells/s."""
+    from adflow_b200 import make_params
+    from adflow_b200 import synthetic as syn
+    from oracle.pyoracle import Oracle
+
+    prm = make_params()
+    hb = syn.make_block(*shape, prm)
+    o = Oracle(hb, prm, fast=True)
+    o.residual_core(8 | 16)  # warm-up
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        o.residual_core(8 | 16)
+        reps += 1
+        if time.perf_counter() - t0 > reps_budget_s or reps >= 20:
+            break
+    dt = time.perf_counter() - t0
+    return hb.d.ncells * reps / dt / 1e6, reps
+
+
+def _ref_worker(args):
+    shape, origin, gshape, reps, tag = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from adflow_b200 import make_params
+    from adflow_b200 import synthetic as syn
+    from oracle.pyoracle import Oracle
+
+    prm = make_params()
+    hb = syn.make_block(*shape, prm, origin=origin, global_n=gshape, origin_tag=tag)
+    o = Oracle(hb, prm, fast=True)
+    o.residual_core(8 | 16)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        o.residual_core(8 | 16)
+    return time.perf_counter() - t0, hb.d.ncells
+
+
+def run_reference(args):
+    """--impl reference: CPU restatement of the reference algorithm on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+
+    ncores = len(os.sched_getaffinity(0))
+    nx, ny, nz = C2
+    # split the C2 block along k (and j if needed) into one sub-block per core, like
+    # the reference's load balancer splits a block over MPI ranks (loadBalance.F90:2790)
+    parts = min(ncores, nz // 4)
+    ks = [nz * q // parts for q in range(parts + 1)]
+    reps = 3
+    jobs = [((nx, ny, ks[q + 1] - ks[q]), (0, 0, ks[q]), C2, reps, q) for q in range(parts)]
+    ctx = mp.get_context("spawn")
+    step_ms = []
+    with ctx.Pool(parts) as pool:
+        for _ in range(args.warmup):
+            pool.map(_ref_worker, jobs)
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            out = pool.map(_ref_worker, jobs)
+            wall = max(o[0] for o in out)  # slowest rank, like an MPI barrier
+            step_ms.append(wall * 1e3 / reps)
+            _ = time.perf_counter() - t0
+    cells = nx * ny * nz
+    ms = sum(step_ms) / len(step_ms)
+    val = cells / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mcells/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 96x72x64 RANS-SA residual, block split over host cores"},
+        "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": parts, "kind": "port",
+                         "sample": "%d residual evaluations of the C2 block per step, %d sub-blocks (1 per core), "
+                                   "oracle port -O3 -march=native -ffast-math" % (reps, parts)},
+        "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shape", type=int, nargs=3, default=list(C2))
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    from adflow_b200 import make_params
+    from adflow_b200 import synthetic as syn
+    from adflow_b200.solver import ADFLOW_B200, RES_FLOW, RES_SKIP_PREAMBLE, RES_TURB
+    import ctypes as C
+
+    shape = tuple(args.shape)
+    prm = make_params()
+    hb = syn.make_block(*shape, prm, origin_tag=rank)
+    hb.subfaces = []
+    s = ADFLOW_B200(prm, device=local)
+    s.addBlock(hb)
+    cells = hb.d.ncells
+    stream = torch.cuda.ExternalStream(s.L.adfb_stream(), device=local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flags_core = RES_FLOW | RES_TURB | RES_SKIP_PREAMBLE
+    flags_full = RES_FLOW | RES_TURB
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(fn, n):
+        """n steps, each bracketed by CUDA events on the library stream, L2 flushed before each."""
+        tot = 0.0
+        with torch.cuda.stream(stream):
+            for _ in range(n):
+                flush.zero_()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                e1.synchronize()
+                tot += e0.elapsed_time(e1)
+        return tot
+
+    # ---- device-resident value ------------------------------------------------
+    step = lambda: s.residual(flags_core)  # noqa: E731
+    timed_steps(step, args.warmup)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    n0 = s.launchCount()
+    ms_total = timed_steps(step, args.steps)
+    launches = s.launchCount() - n0
+    barrier()
+    # ---- e2e through the vector API with pinned host buffers -------------------
+    nvec = s.getStateSize()
+    h_state = torch.empty(nvec, dtype=torch.float64).pin_memory()
+    h_res = torch.empty(nvec, dtype=torch.float64).pin_memory()
+    h_state.numpy()[:] = s.getStates()
+
+    def e2e_step():
+        s.L.adfb_set_states(C.c_void_p(h_state.data_ptr()), nvec)
+        s.L.adfb_residual(1, flags_full)
+        s.L.adfb_get_res(C.c_void_p(h_res.data_ptr()), nvec)
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel timing pass (roofline) --------------------------------------
+    s.L.adfb_set_timing(1)
+    for _ in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        s.residual(flags_core)
+    ms_k = (C.c_double * 16)(); cnt_k = (C.c_longlong * 16)()
+    s.L.adfb_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    s.L.adfb_kernel_name.restype = C.c_char_p
+    nk = s.L.adfb_kernel_times(ms_k, cnt_k, 16)
+    s.L.adfb_set_timing(0)
+    kernels = {s.L.adfb_kernel_name(i).decode(): {"ms_per_launch": ms_k[i] / cnt_k[i], "launches": int(cnt_k[i])}
+               for i in range(nk) if cnt_k[i] > 0}
+    res_ms = sum(ms_k[i] for i in range(3)) / args.steps  # k_prep + k_nodal + k_resid per step
+
+    # max over ranks
+    ms_step = ms_total / args.steps
+    if world > 1:
+        t = torch.tensor([ms_step, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms = float(t[0]), float(t[1])
+    value = cells * world / (ms_step * 1e-3) / 1e6
+    e2e_val = cells * world / (e2e_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = BYTES_PER_CELL * cells / (res_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2 %dx%dx%d RANS-SA residual (flow+SA rows, exact fluxes), 1 block per GPU" % shape,
+                       "cells_per_gpu": cells, "l2": "flushed before every timed step (256 MiB memset)",
+                       "timing": "CUDA events on the library stream around each step"},
+            "e2e": {"value": e2e_val, "unit": "Mcells/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(nvec * 8), "d2h_bytes_per_step": int(nvec * 8),
+                    "path": "adfb_set_states(pinned host) -> adfb_residual(p/rlv/rev preamble + core) -> adfb_get_res(pinned host)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "residual pipeline k_prep+k_nodal+k_resid (all three launches charged)",
+                         "algorithmic_bytes_per_cell": BYTES_PER_CELL, "kernels": kernels},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            v, reps = cpu_baseline_single(shape)
+            line["cpu_baseline"] = {"value": v, "unit": "Mcells/s", "cores": 1, "kind": "port",
+                                    "sample": "%d full residual evaluations of the same block, oracle port "
+                                              "(-O3 -march=native -ffast-math), 1 core" % reps}
+        print(json.dumps(line))
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,195 @@
+/*
+ * adflow_b200.h -- C ABI of libadflow_b200.so
+ *
+ * B200-native (sm_100a) implementation of the per-block residual / smoother /
+ * matrix-free Jacobian-vector hot path of mdolab/adflow.  The reference has no
+ * FFI seam around this path: its L2 routines are
+ * argument-less Fortran module procedures acting on module-global block
+ * pointers.  Each entry point below names the reference routine (file:line,
+ * relative to the reference tree) whose body it replaces; INTEGRATION.md shows
+ * the ISO_C_BINDING interface block a maintainer adds on the Fortran side.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; the message is
+ *    available from adfb_last_error().  The Fortran caller maps non-zero to
+ *    `call terminate(routine, msg)` (src/utils/utils.F90:501).
+ *  - all reals are IEEE double (src/modules/precision.F90:74-81 realType),
+ *    ints are 32 bit (intType), porosities are int8 (porType).
+ *  - host arrays are Fortran column-major with the reference's own extents and
+ *    lower bounds; they are only read/written during the call (no retained
+ *    pointers).  Extents for a block of nx*ny*nz owned cells
+ *    (il=nx+1, ie=nx+2, ib=nx+3; idem j,k; src/modules/block.F90:209-223):
+ *       w(0:ib,0:jb,0:kb,1:nw) p,rlv,rev,vol,volRef,dw(0:ib,0:jb,0:kb[,1:nw])
+ *       iblank(0:ib,0:jb,0:kb) int32
+ *       x(0:ie,0:je,0:ke,3)
+ *       sI(0:ie,1:je,1:ke,3) sJ(1:ie,0:je,1:ke,3) sK(1:ie,1:je,0:ke,3)
+ *       porI(1:il,2:jl,2:kl) porJ(2:il,1:jl,2:kl) porK(2:il,2:jl,1:kl) int8
+ *       d2Wall(2:il,2:jl,2:kl)
+ *       dtl,radI,radJ,radK(1:ie,1:je,1:ke)
+ *  - not re-entrant; called from the rank's only thread (the reference is
+ *    single threaded per MPI rank).  One process <-> one GPU.
+ *  - the library has NO CPU fallback: every entry point fails with an error if
+ *    no CUDA device is usable.
+ */
+#ifndef ADFLOW_B200_H
+#define ADFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* variable slots, src/modules/constants.F90:34-40 (1-based in Fortran) */
+enum { ADFB_IRHO = 0, ADFB_IVX = 1, ADFB_IVY = 2, ADFB_IVZ = 3, ADFB_IRHOE = 4, ADFB_ITU1 = 5 };
+
+/* equations, src/modules/constants.F90 (EulerEquations/NSEquations/RANSEquations) */
+enum { ADFB_EULER = 1, ADFB_NS = 2, ADFB_RANS = 3 };
+/* spaceDiscr */
+enum { ADFB_DISS_SCALAR = 1, ADFB_DISS_MATRIX = 2, ADFB_UPWIND = 4 };
+/* turbProd */
+enum { ADFB_PROD_STRAIN = 1, ADFB_PROD_VORTICITY = 2 };
+/* limiter for the upwind scheme (inputDiscretization%limiter) */
+enum { ADFB_LIM_NONE = 1, ADFB_LIM_VANALBADA = 2, ADFB_LIM_MINMOD = 3 };
+/* porosity codes, src/modules/constants.F90:28-30 */
+enum { ADFB_NOFLUX = -1, ADFB_BOUNDFLUX = 0, ADFB_NORMALFLUX = 1 };
+/* BC types handled on device (subset of src/modules/constants.F90:257-282) */
+enum {
+    ADFB_BC_SYMM = 1,
+    ADFB_BC_NSWALL_ADIABATIC = 2,
+    ADFB_BC_FARFIELD = 3,
+    ADFB_BC_EULERWALL = 4,
+    ADFB_BC_EXTRAP = 5,
+    ADFB_BC_NSWALL_ISOTHERMAL = 6
+};
+/* block faces, reference order iMin..kMax (src/modules/constants.F90 iMin=1..kMax=6) */
+enum { ADFB_IMIN = 1, ADFB_IMAX = 2, ADFB_JMIN = 3, ADFB_JMAX = 4, ADFB_KMIN = 5, ADFB_KMAX = 6 };
+
+/* residual flags == blocketteRes optional logicals, src/NKSolver/blockette.F90:70-164 */
+enum {
+    ADFB_RES_DISS_APPROX = 1,     /* useDissApprox   */
+    ADFB_RES_VISC_APPROX = 2,     /* useViscApprox   */
+    ADFB_RES_UPDATE_INTERMED = 4, /* useUpdateIntermed: also store dtl, radI/J/K */
+    ADFB_RES_FLOW = 8,            /* useFlowRes      */
+    ADFB_RES_TURB = 16,           /* useTurbRes      */
+    ADFB_RES_STORE_WALL = 32,     /* useStoreWall    */
+    ADFB_RES_SKIP_PREAMBLE = 64   /* core only: skip p/rlv/rev + BCs + halo exchange
+                                     (== calling blocketteResCore directly) */
+};
+
+/*
+ * All scalar module globals the hot path reads, passed by value
+ * (replaces inputDiscretization, inputPhysics, flowVarRefState, paramTurb,
+ * inputIteration module state; SURVEY.md section 5 "Config / flags").
+ */
+typedef struct AdfbParams {
+    /* reference state, src/initFlow/initializeFlow.F90:10-182 (referenceState) */
+    double gammaInf;   /* == gammaConstant (cpConstant model only) */
+    double RGas;
+    double pInfCorr;
+    double rhoInf;
+    double wInf[6];    /* rho, u, v, w, rhoE, nuTilde of the free stream */
+    double pInf;
+    /* Sutherland, non-dimensional: muSuthDim/muRef, TSuthDim/Tref, SSuthDim/Tref
+       (src/utils/flowUtils.F90:1241-1243) */
+    double muSuth, TSuth, SSuth;
+    double prandtl, prandtlTurb;
+    /* JST, src/inputParam/inputParamRoutines.F90:3823-3833 + pyADflow defaults */
+    double vis2, vis4, adis, acousticScaleFactor;
+    double kappaCoef;  /* MUSCL kappa for the upwind scheme */
+    /* SA model, src/modules/paramTurb.F90:8-20 */
+    double rsaK, rsaCb1, rsaCb2, rsaCb3, rsaCv1, rsaCw1, rsaCw2, rsaCw3, rsaCt3, rsaCt4, rsaCrot;
+    /* smoothers, src/inputParam/inputParamRoutines.F90:3576-3633 */
+    double cfl, cflCoarse;
+    double etaRK[6], cdisRK[6];
+    double alfaTurb;      /* DD-ADI under-relaxation, inputParamRoutines.F90:3908 */
+    double turbResScale;  /* NKSolvers.F90:1295-1307 */
+    double cflLimit, smoop; /* residual averaging, residuals.F90:1850-1893 */
+    /* integer switches */
+    int32_t equations;    /* ADFB_EULER / NS / RANS */
+    int32_t spaceDiscr;   /* ADFB_DISS_SCALAR ... */
+    int32_t nRKStages;
+    int32_t turbProd;
+    int32_t useQCR;
+    int32_t useft2SA;
+    int32_t useRotationSA;
+    int32_t approxSA;
+    int32_t secondOrdTurb; /* turbMod%secondOrd, turbUtils.F90:828 ff. */
+    int32_t limiter;
+    int32_t resAveraging;  /* 0 never, 1 always, 2 alternate */
+    int32_t nSubiterTurb;
+    int32_t wallBCConstantPressure; /* viscWallBCTreatment == constantPressure */
+    int32_t reserved;
+} AdfbParams;
+
+/* One boundary subface of a block, mirroring BCDataType (src/modules/block.F90:52-156)
+   for the BC classes handled on device.  Ranges are the *cell* ranges icBeg:icEnd,
+   jcBeg:jcEnd of BCData(nn) in the two in-plane directions (utils.F90:895-900). */
+typedef struct AdfbSubface {
+    int32_t bcType;   /* ADFB_BC_* */
+    int32_t faceId;   /* ADFB_IMIN .. ADFB_KMAX */
+    int32_t icBeg, icEnd, jcBeg, jcEnd;
+    /* optional per-face arrays, NULL for defaults; extents (icBeg:icEnd, jcBeg:jcEnd[,3]) */
+    const double* norm;   /* unit outward normal BCData%norm, required for symm / wall / farfield */
+    const double* rface;  /* BCData%rface (grid normal velocity), NULL == 0 */
+    const double* uSlip;  /* BCData%uSlip(:,:,3), NULL == 0 */
+    const double* TNSWall; /* isothermal walls only */
+} AdfbSubface;
+
+/* ---- life cycle ---------------------------------------------------------- */
+/* one MPI rank <-> one GPU <-> one NCCL rank.  ncclUniqueId may be NULL when
+   nranks == 1.  Replaces nothing in the reference (no device exists there);
+   called after partitionAndReadGrid (adflow/pyADflow.py:236). */
+int adfb_init(int device, const void* ncclUniqueId, int rank, int nranks);
+int adfb_finalize(void);
+/* rank 0 calls this and broadcasts the 128 bytes over its own transport (MPI_Bcast
+   in the Fortran host, torch.distributed in the Python harness). */
+int adfb_get_unique_id(void* out128);
+int adfb_last_error(char* buf, int n);
+int adfb_device_count(void);
+
+/* ---- data model (src/modules/block.F90:205-752 blockType) ----------------- */
+/* after allocMemFlovarPart2 (src/initFlow/initializeFlow.F90:686-722) */
+int adfb_block_create(int blk, int level, int nx, int ny, int nz, int nw, int rightHanded);
+int adfb_block_destroy(int blk);
+/* after preprocessing / each mesh warp (updateGeometryInfo).  si/sj/sk may be NULL:
+   they are then computed on the device from x with the blockette `metrics`
+   formula (src/NKSolver/blockette.F90:854-960).  d2Wall may be NULL for Euler/NS. */
+int adfb_block_set_geometry(int blk, const double* x, const double* si, const double* sj,
+                            const double* sk, const double* vol, const double* volRef,
+                            const double* d2Wall, const int8_t* porI, const int8_t* porJ,
+                            const int8_t* porK, const int32_t* iblank);
+/* after updateBCDataAllLevels */
+int adfb_block_set_bc(int blk, int nSub, const AdfbSubface* subfaces);
+/* whenever options / AeroProblem change (setOption, _setAeroProblemData) */
+int adfb_set_params(const AdfbParams* prm);
+
+/* ---- explicit sync points (NKSolvers.F90:1378-1485 getStates/setStates/getRes) */
+int adfb_upload_state(int blk, const double* w, const double* p);
+int adfb_download_state(int blk, double* w, double* p, double* rlv, double* rev);
+int adfb_upload_visc(int blk, const double* rlv, const double* rev);
+int adfb_download_residual(int blk, double* dw);
+int adfb_download_intermed(int blk, double* dtl, double* radI, double* radJ, double* radK);
+
+/* Vector forms used by the Python layer and PETSc (NKSolvers.F90:1378-1485):
+   ordering = for block, for k, for j, for i, for l=1..nw (AoS per owned cell).
+   adfb_get_states <- getStates, adfb_set_states <- setStates (no clipping),
+   adfb_get_res <- the gather loop of getRes (dw/volRef, :1432-1448; it does not
+   evaluate the residual: call adfb_residual first). n = total vector length. */
+int adfb_get_states(double* states, long long n);
+int adfb_set_states(const double* states, long long n);
+int adfb_get_res(double* res, long long n);
+long long adfb_state_size(void);
+
+/* ---- the hot path --------------------------------------------------------- */
+/* replaces blocketteRes body, src/NKSolver/blockette.F90:199-283 */
+int adfb_residual(int level, unsigned flags);
+/* Sum of (dw(irho)/vol)^2 and of all (dw/vol)^2 over owned cells of all local
+   blocks, all-reduced (getCurrentResidual, NKSolvers.F90:335-370). out[0]=rho, out[1]=total */
+int adfb_norms(double out[2]);
+int adfb_synchronize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADFLOW_B200_H */

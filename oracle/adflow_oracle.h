@@ -1,0 +1,74 @@
+/*
+ * adflow_oracle.h -- CPU restatement of the ADflow hot path (TEST INFRASTRUCTURE ONLY).
+ *
+ * This is the parity oracle of SURVEY.md section 8c.  It is never linked into
+ * or called from the product library (adflow_b200/csrc); only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load it.
+ *
+ * PARITY UNPINNED: the reference (Fortran + MPI + PETSc + CGNS) cannot be built
+ * or imported in this environment and its regression meshes are not in the
+ * tree, so this restatement cannot be checked against reference output or the
+ * golden JSONs (tests/reg_tests/refs/, 36 json files).  It is pinned only by the
+ * mesh-independent invariants the reference itself relies on (free-stream
+ * preservation, discrete conservation, FD consistency, tridiagonal
+ * multiply-back) -- see tests/test_oracle_invariants.py.
+ *
+ * Layout: every array lives in one uniform box (0:ib,0:jb,0:kb) (column-major,
+ * i fastest) so that the Fortran index (i,j,k) IS the C offset
+ * i + NI*(j + NJ*k); arrays that the reference allocates with tighter bounds
+ * (1:ie, 2:il, node and face arrays) simply leave the unused entries untouched.
+ * Multi-component arrays put the component slowest: w(i,j,k,l) -> (l-1)*N + idx.
+ */
+#ifndef ADFLOW_ORACLE_H
+#define ADFLOW_ORACLE_H
+#include <stdint.h>
+#include "../include/adflow_b200.h"
+
+typedef struct OrcBlock {
+    int32_t nx, ny, nz, nw, rightHanded, pad_;
+    /* state (cell, 2 halos) */
+    double *w, *p, *rlv, *rev;
+    /* geometry */
+    double *x;              /* nodes (0:ie,0:je,0:ke,3) */
+    double *si, *sj, *sk;   /* face normals, 3 comps each */
+    double *vol, *volRef, *d2Wall;
+    int8_t *porI, *porJ, *porK;
+    int32_t *iblank;
+    /* residual + work */
+    double *dw, *fw;        /* nw and 5 comps */
+    double *ss, *dss;       /* entropy, sensor (3 comps) */
+    double *aa, *radI, *radJ, *radK, *dtl;
+    double *grad;           /* 12 nodal gradient arrays ux,uy,uz,vx,..,qz */
+    /* smoother storage */
+    double *wn, *pn;        /* 5 comps / 1 */
+    double *scratch;        /* 10 comps: DADI work, SA qq etc. */
+} OrcBlock;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+void orc_metrics(const OrcBlock* b);
+void orc_volume(const OrcBlock* b);
+void orc_pressure(const OrcBlock* b, const AdfbParams* prm, int includeHalos);
+void orc_lam_viscosity(const OrcBlock* b, const AdfbParams* prm, int includeHalos);
+void orc_eddy_viscosity(const OrcBlock* b, const AdfbParams* prm, int includeHalos);
+void orc_etot(const OrcBlock* b, const AdfbParams* prm, int i0, int i1, int j0, int j1, int k0, int k1);
+void orc_residual_core(const OrcBlock* b, const AdfbParams* prm, unsigned flags, double rFil);
+/* individual operators, exposed for per-term tests */
+void orc_time_step(const OrcBlock* b, const AdfbParams* prm, int updateDtl);
+void orc_central_flux(const OrcBlock* b, const AdfbParams* prm);
+void orc_diss_scalar(const OrcBlock* b, const AdfbParams* prm, double rFil);
+void orc_speed_of_sound(const OrcBlock* b, const AdfbParams* prm);
+void orc_nodal_gradients(const OrcBlock* b);
+void orc_viscous_flux(const OrcBlock* b, const AdfbParams* prm, double rFil);
+void orc_sa_source(const OrcBlock* b, const AdfbParams* prm);
+void orc_sa_advection(const OrcBlock* b, const AdfbParams* prm);
+void orc_sa_viscous(const OrcBlock* b, const AdfbParams* prm);
+void orc_sa_res_scale(const OrcBlock* b);
+void orc_sum_dw_fw(const OrcBlock* b);
+void orc_norms(const OrcBlock* b, const AdfbParams* prm, double out[2]);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,103 @@
+"""ctypes binding of the CPU oracle (oracle/adflow_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py; never by the product package.
+PARITY UNPINNED (see oracle/adflow_oracle.h).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "adflow_oracle.c")
+    stale = (not os.path.exists(so)) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(so)
+        for f in ("adflow_oracle.c", "adflow_oracle.h", "../include/adflow_b200.h")
+    )
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+    assert os.path.exists(src)
+    return so
+
+
+class OrcBlock(C.Structure):
+    _fields_ = (
+        [(n, C.c_int32) for n in ("nx", "ny", "nz", "nw", "rightHanded", "pad_")]
+        + [(n, C.c_void_p) for n in (
+            "w", "p", "rlv", "rev", "x", "si", "sj", "sk", "vol", "volRef", "d2Wall",
+            "porI", "porJ", "porK", "iblank", "dw", "fw", "ss", "dss",
+            "aa", "radI", "radJ", "radK", "dtl", "grad", "wn", "pn", "scratch")]
+    )
+
+
+_lib = {}
+
+
+def lib(fast=False):
+    key = "fast" if fast else "strict"
+    if key not in _lib:
+        build()
+        name = "liboracle_fast.so" if fast else "liboracle.so"
+        L = C.CDLL(os.path.join(_HERE, name))
+        for fn in ("orc_metrics", "orc_volume", "orc_nodal_gradients", "orc_sa_res_scale", "orc_sum_dw_fw"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+            getattr(L, fn).restype = None
+        _lib[key] = L
+    return _lib[key]
+
+
+def orc_block(hb):
+    """OrcBlock view of a HostBlock (no copies; arrays must stay alive)."""
+    ob = OrcBlock()
+    ob.nx, ob.ny, ob.nz, ob.nw = hb.d.nx, hb.d.ny, hb.d.nz, hb.nw
+    ob.rightHanded = int(hb.right_handed)
+    for n, _t in OrcBlock._fields_[6:]:
+        a = getattr(hb, n)
+        assert a.flags.f_contiguous, n
+        setattr(ob, n, a.ctypes.data)
+    return ob
+
+
+def _p(x):
+    return C.byref(x)
+
+
+class Oracle:
+    """Thin convenience wrapper: Oracle(hb, prm).residual(flags)."""
+
+    def __init__(self, hb, prm, fast=False):
+        self.hb, self.prm = hb, prm
+        self.L = lib(fast)
+        self.ob = orc_block(hb)
+
+    def metrics(self):
+        self.L.orc_metrics(_p(self.ob))
+
+    def volume(self):
+        self.L.orc_volume(_p(self.ob))
+
+    def pressure(self, include_halos=False):
+        self.L.orc_pressure(_p(self.ob), _p(self.prm), C.c_int(int(include_halos)))
+
+    def lam_viscosity(self, include_halos=False):
+        self.L.orc_lam_viscosity(_p(self.ob), _p(self.prm), C.c_int(int(include_halos)))
+
+    def eddy_viscosity(self, include_halos=False):
+        self.L.orc_eddy_viscosity(_p(self.ob), _p(self.prm), C.c_int(int(include_halos)))
+
+    def residual_core(self, flags, rfil=1.0):
+        self.L.orc_residual_core(_p(self.ob), _p(self.prm), C.c_uint(flags), C.c_double(rfil))
+
+    def norms(self):
+        out = (C.c_double * 2)()
+        self.L.orc_norms(_p(self.ob), _p(self.prm), out)
+        return np.array([out[0], out[1]])
+
+    def call(self, name, *args):
+        getattr(self.L, name)(_p(self.ob), *args)

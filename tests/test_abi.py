@@ -1,0 +1,55 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every
+symbol include/adflow_b200.h declares, and fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from adflow_b200 import _lib, make_params
+from adflow_b200.params import AdfbParams
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "adflow_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(adfb_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported():
+    L = _lib.load()
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), "libadflow_b200.so does not export %s" % s
+    assert set(_lib.ABI_SYMBOLS) == set(syms)
+
+
+def test_params_struct_size_matches_header():
+    # 64 doubles? count from the header: keep the ctypes twin in sync with the C struct
+    txt = open(os.path.join(ROOT, "include", "adflow_b200.h")).read()
+    body = txt[txt.index("typedef struct AdfbParams {"):txt.index("} AdfbParams;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    nd = 0
+    for decl in re.findall(r"double\s+([^;]+);", body):
+        for name in decl.split(","):
+            m = re.search(r"\[(\d+)\]", name)
+            nd += int(m.group(1)) if m else 1
+    ni = len(re.findall(r"int32_t\s+\w+\s*;", body))
+    assert C.sizeof(AdfbParams) == 8 * nd + 4 * ni
+
+
+def test_fails_loudly_without_gpu():
+    L = _lib.load()
+    if L.adfb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    rc = L.adfb_init(0, None, 0, 1)
+    assert rc != 0
+    buf = C.create_string_buffer(512)
+    L.adfb_last_error(buf, 512)
+    assert b"no CUDA device" in buf.value
+    prm = make_params()
+    assert L.adfb_set_params(C.byref(prm)) != 0  # not initialised -> error, never a CPU path
+    assert L.adfb_residual(1, 8 | 16) != 0
