@@ -19,6 +19,7 @@ ABI_SYMBOLS = [
     "adfb_set_params", "adfb_upload_state", "adfb_download_state", "adfb_upload_visc",
     "adfb_download_residual", "adfb_download_intermed", "adfb_residual", "adfb_norms", "adfb_synchronize",
     "adfb_get_states", "adfb_set_states", "adfb_get_res", "adfb_state_size",
+    "adfb_apply_bcs", "adfb_timestep", "adfb_smoother_residual", "adfb_rk_stage", "adfb_rk_cycle",
 ]
 
 
@@ -68,6 +69,11 @@ def load():
     for fn in (L.adfb_get_states, L.adfb_set_states, L.adfb_get_res):
         fn.argtypes = [vp, C.c_longlong]
     L.adfb_state_size.restype = C.c_longlong
+    L.adfb_apply_bcs.argtypes = [ci, ci, ci]
+    L.adfb_timestep.argtypes = [ci, ci]
+    L.adfb_smoother_residual.argtypes = [ci, ci]
+    L.adfb_rk_stage.argtypes = [ci, ci]
+    L.adfb_rk_cycle.argtypes = [ci]
     L.adfb_launch_count.restype = C.c_longlong
     L.adfb_stream.restype = C.c_void_p
     _lib = L

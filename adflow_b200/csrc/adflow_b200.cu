@@ -17,6 +17,7 @@
 #include "adfb_common.cuh"
 #include "state_kernels.cuh"
 #include "residual_kernels.cuh"
+#include "smoother_kernels.cuh"
 
 namespace {
 
@@ -468,18 +469,96 @@ int adfb_residual(int level, unsigned flags) {
         if (!b.alive || b.level != level) continue;
         if (!b.haveMetrics) return fail("adfb_residual: geometry of a block was never set");
         if (!(flags & ADFB_RES_SKIP_PREAMBLE)) {
-            // blocketteRes :213-226: p, rlv, rev on owned cells, then BCs
+            // blocketteRes :213-226: p, rlv, rev on owned cells, then turbulence and flow BCs
             if (launch_state_prep(b.d, b.dev, g.prm, false, g.stream)) return fail("state prep launch failed");
-            if (!b.subfaces.empty()) return fail("adfb_residual: device BC kernels not built yet; pass ADFB_RES_SKIP_PREAMBLE");
+            if (g.prm.equations == ADFB_RANS && (flags & ADFB_RES_TURB))
+                if (launch_bc_turb(b.d, b.dev, b.subfaces, 1, g.stream)) return fail("turbulence BC launch failed");
+            if (launch_bc_flow(b.d, b.dev, b.subfaces, 1, g.stream)) return fail("flow BC launch failed");
         }
     }
+    // whalo2(1, lStart, lEnd, T, T, T), blockette.F90:246 (single-rank: nothing to exchange)
     for (Block& b : g.blocks) {
         if (!b.alive || b.level != level) continue;
-        if (launch_residual_core(b.d, b.dev, g.prm, flags, 1.0, 0, g.stream))
+        if (launch_residual_core(b.d, b.dev, g.prm, flags, 1.0, 0, 1, g.stream))
             return fail("residual kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     CK(cudaGetLastError());
     return 0;
+}
+
+// applyAllBC (+ turbulence halos), src/solver/BCRoutines.F90:57, turbBCRoutines.F90:49
+int adfb_apply_bcs(int level, int secondHalo, int withTurb) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_apply_bcs: adfb_set_params has not been called");
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != level) continue;
+        if (withTurb && g.prm.equations == ADFB_RANS)
+            if (launch_bc_turb(b.d, b.dev, b.subfaces, secondHalo, g.stream)) return fail("turbulence BC launch failed");
+        if (launch_bc_flow(b.d, b.dev, b.subfaces, secondHalo, g.stream)) return fail("flow BC launch failed");
+    }
+    return 0;
+}
+
+// timeStep(onlyRadii), src/solver/solverUtils.F90:43-355 (fine level, directional scaling)
+int adfb_timestep(int level, int onlyRadii) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_timestep: adfb_set_params has not been called");
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != level) continue;
+        dim3 tb(32, 4, 2);
+        dim3 gr((b.d.NI + 31) / 32, (b.d.NJ + 3) / 4, (b.d.NK + 1) / 2);
+        KT_BEGIN(K_PREP, g.stream);
+        k_prep<<<gr, tb, 0, g.stream>>>(b.d, b.dev, onlyRadii ? 0 : 1, 1);
+        KT_END(K_PREP, g.stream);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// `initres(1,nwf); sourceTerms; residual` of the smoother loops (smoothers.F90:73-75,
+// multiGrid.F90:883-888): mean-flow residual with rFil = cdisRK(rkStage+1), fw persistent.
+int adfb_smoother_residual(int level, int rkStage) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_smoother_residual: adfb_set_params has not been called");
+    if (rkStage < 0 || rkStage > 5) return fail("adfb_smoother_residual: rkStage %d out of range", rkStage);
+    const double rFil = g.prm.cdisRK[rkStage];
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != level) continue;
+        if (launch_residual_core(b.d, b.dev, g.prm, ADFB_RES_FLOW, rFil, 1, 0, g.stream)) return fail("residual launch failed");
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// executeRkStage, src/solver/smoothers.F90:90-382
+int adfb_rk_stage(int level, int rkStage) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_rk_stage: adfb_set_params has not been called");
+    if (rkStage < 1 || rkStage > g.prm.nRKStages) return fail("adfb_rk_stage: stage %d out of 1..%d", rkStage, g.prm.nRKStages);
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != level) continue;
+        if (launch_rk_update(b.d, b.dev, g.prm, rkStage, g.stream)) return fail("RK update launch failed");
+        if (launch_bc_flow(b.d, b.dev, b.subfaces, 1, g.stream)) return fail("flow BC launch failed");
+    }
+    // whalo2(level, 1, nwf, T, T, T) (single-rank: nothing to exchange)
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// RungeKuttaSmoother, src/solver/smoothers.F90:4-86
+int adfb_rk_cycle(int level) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_rk_cycle: adfb_set_params has not been called");
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != level) continue;
+        CK(cudaMemcpyAsync(b.dev.wn, b.dev.w, (size_t)b.d.N * 5 * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+        CK(cudaMemcpyAsync(b.dev.pn, b.dev.p, (size_t)b.d.N * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+    }
+    for (int st = 1; st <= g.prm.nRKStages - 1; st++) {
+        if (adfb_rk_stage(level, st)) return 1;
+        if (adfb_smoother_residual(level, st)) return 1;
+    }
+    return adfb_rk_stage(level, g.prm.nRKStages);
 }
 
 int adfb_norms(double out[2]) {

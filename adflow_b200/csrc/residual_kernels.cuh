@@ -39,7 +39,7 @@ __device__ __forceinline__ bool cell_index(const Dims& d, int& i, int& j, int& k
 // k_prep: entropy (inviscidDissFluxScalar, blockette.F90:3055-3089), speed of
 // sound squared (:5168-5203), spectral radii and local time step (timeStep,
 // :1899-2148).  One pass over the box; radii/aa only on cells 1:ie, dtl on owned.
-__global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt) {
+__global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, int doRad) {
     int i, j, k;
     cell_index(d, i, j, k, 0, 0, 0);
     if (i > d.ib || j > d.jb || k > d.kb) return;
@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt) 
     if (i < 1 || i > d.ie || j < 1 || j > d.je || k < 1 || k > d.ke) return;
     const bool viscous = c_prm.equations != ADFB_EULER;
     if (viscous) b.aa[c] = gam * p / rho;
+    if (!doRad) return;  // smoother path: radii/dtl are frozen between timeStep calls
 
     const double clim2 = 0.000001 * gam * c_prm.pInfCorr / c_prm.rhoInf;
     const double adis = c_prm.adis, asf = c_prm.acousticScaleFactor;
@@ -413,7 +414,7 @@ __device__ __forceinline__ double sa_source(const BlockDev& b, const Dims& d, lo
 //   fluxes.F90:1193); for blocketteRes rFil == 1 and fw is never stored.
 template <bool VISCOUS>
 __global__ void __launch_bounds__(128) k_resid(Dims d, BlockDev b, int flowRes, int turbRes, double rFil, int persistFw,
-                                               int doVisc) {
+                                               int doVisc, int doDiss) {
     int i, j, k;
     cell_index(d, i, j, k, 2, 2, 2);
     if (i > d.il || j > d.jl || k > d.kl) return;
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(128) k_resid(Dims d, BlockDev b, int flowRes, 
     const double sfil = 1.0 - rFil;
 #pragma unroll
     for (int l = 0; l < 5; l++) fw[l] = persistFw ? sfil * b.fw[l * N + c] : 0.0;
-    if (c_prm.spaceDiscr == ADFB_DISS_SCALAR) {
+    if (doDiss && c_prm.spaceDiscr == ADFB_DISS_SCALAR) {
         const double fis2 = rFil * c_prm.vis2, fis4 = rFil * c_prm.vis4;
         jst_face(b, N, c - 1, 1, b.radI, b.dss, b.porI[c - 1], fis2, fis4, f);
 #pragma unroll
@@ -521,21 +522,23 @@ __global__ void __launch_bounds__(128) k_resid(Dims d, BlockDev b, int flowRes, 
 
 // ---------------------------------------------------------------------------
 // host-side launcher (called from adfb_api.cu)
+// doRad: 1 = recompute spectral radii + dtl (blockette order), 0 = keep them (block/smoother path)
 static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbParams& prm, unsigned flags, double rFil,
-                                int persistFw, cudaStream_t stream) {
+                                int persistFw, int doRad, cudaStream_t stream) {
     const int flowRes = (flags & ADFB_RES_FLOW) != 0;
     const int turbRes = ((flags & ADFB_RES_TURB) != 0) && prm.equations == ADFB_RANS;
     const int updateDt = 1;  // blockette timeStep always computes dtl (blockette.F90:1929-1932)
     const bool viscous = prm.equations != ADFB_EULER;
-    const int doVisc = viscous && fabs(rFil) > 1.e-10;
+    const int doDiss = fabs(rFil) >= 1.e-10;  // fluxes.F90:1082 early return
+    const int doVisc = viscous && doDiss;
     dim3 tb(32, 4, 2);
-    {
+    if (doRad || doDiss) {
         dim3 g((d.NI + tb.x - 1) / tb.x, (d.NJ + tb.y - 1) / tb.y, (d.NK + tb.z - 1) / tb.z);
         KT_BEGIN(K_PREP, stream);
-        k_prep<<<g, tb, 0, stream>>>(d, b, updateDt);
+        k_prep<<<g, tb, 0, stream>>>(d, b, updateDt, doRad);
         KT_END(K_PREP, stream);
     }
-    if (flowRes) {
+    if (flowRes && doDiss) {
         dim3 g((d.ie + tb.x - 1) / tb.x, (d.je + tb.y - 1) / tb.y, (d.ke + tb.z - 1) / tb.z);
         KT_BEGIN(K_NODAL, stream);
         k_nodal<<<g, tb, 0, stream>>>(d, b, doVisc);
@@ -546,9 +549,9 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         dim3 g((d.nx + tr.x - 1) / tr.x, (d.ny + tr.y - 1) / tr.y, (d.nz + tr.z - 1) / tr.z);
         KT_BEGIN(K_RESID, stream);
         if (viscous)
-            k_resid<true><<<g, tr, 0, stream>>>(d, b, flowRes, turbRes, rFil, persistFw, doVisc);
+            k_resid<true><<<g, tr, 0, stream>>>(d, b, flowRes, turbRes, rFil, persistFw, doVisc, doDiss);
         else
-            k_resid<false><<<g, tr, 0, stream>>>(d, b, flowRes, turbRes, rFil, persistFw, doVisc);
+            k_resid<false><<<g, tr, 0, stream>>>(d, b, flowRes, turbRes, rFil, persistFw, doVisc, doDiss);
         KT_END(K_RESID, stream);
     }
     return (int)cudaGetLastError();

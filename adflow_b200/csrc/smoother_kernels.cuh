@@ -1,0 +1,381 @@
+// smoother_kernels.cuh -- boundary-condition, Runge-Kutta and residual-averaging kernels
+//
+//   k_bc_turb / k_bc_flow : applyAllTurbBCThisBlock (src/turbulence/turbBCRoutines.F90:49-236)
+//                           and applyAllBC_block (src/solver/BCRoutines.F90:57-222) for the BC
+//                           classes of the BASELINE configs: symmetry, adiabatic NS wall,
+//                           far field, Euler wall.  One launch per subface and phase, issued
+//                           in the reference's order (edge/corner halos depend on it).
+//   k_rk_scale / k_rk_update : executeRkStage (src/solver/smoothers.F90:90-382)
+//   k_resavg_line            : residualAveraging (src/solver/residuals.F90:1785-2080)
+#pragma once
+#include "adfb_common.cuh"
+#include <math.h>
+
+struct FaceDev {
+    long long off[4];  // plane 0 (2nd halo) .. 3 (2nd interior), setBCPointers utils.F90:881
+    long long sa, sb;  // in-plane strides
+    int icBeg, icEnd, jcBeg, jcEnd;
+    int bcType;
+    const double *norm, *rface, *uSlip;
+};
+
+static FaceDev make_face(const Dims& d, const AdfbSubface& sf) {
+    FaceDev f;
+    switch (sf.faceId) {
+        case ADFB_IMIN: f.off[0] = 0; f.off[1] = 1; f.off[2] = 2; f.off[3] = 3; f.sa = d.sJ; f.sb = d.sK; break;
+        case ADFB_IMAX: f.off[0] = d.ib; f.off[1] = d.ie; f.off[2] = d.il; f.off[3] = d.nx; f.sa = d.sJ; f.sb = d.sK; break;
+        case ADFB_JMIN: f.off[0] = 0; f.off[1] = d.sJ; f.off[2] = 2 * d.sJ; f.off[3] = 3 * d.sJ; f.sa = 1; f.sb = d.sK; break;
+        case ADFB_JMAX: f.off[0] = d.jb * d.sJ; f.off[1] = d.je * d.sJ; f.off[2] = d.jl * d.sJ; f.off[3] = d.ny * d.sJ; f.sa = 1; f.sb = d.sK; break;
+        case ADFB_KMIN: f.off[0] = 0; f.off[1] = d.sK; f.off[2] = 2 * d.sK; f.off[3] = 3 * d.sK; f.sa = 1; f.sb = d.sJ; break;
+        default: f.off[0] = d.kb * d.sK; f.off[1] = d.ke * d.sK; f.off[2] = d.kl * d.sK; f.off[3] = d.nz * d.sK; f.sa = 1; f.sb = d.sJ; break;
+    }
+    f.icBeg = sf.icBeg; f.icEnd = sf.icEnd; f.jcBeg = sf.jcBeg; f.jcEnd = sf.jcEnd;
+    f.bcType = sf.bcType;
+    f.norm = sf.norm; f.rface = sf.rface; f.uSlip = sf.uSlip;
+    return f;
+}
+
+namespace {
+
+__device__ __forceinline__ void bc_etot(const BlockDev& b, long long N, long long c) {
+    const double ovgm1 = 1.0 / (c_prm.gammaInf - 1.0);
+    const double r = b.w[c], u = b.w[N + c], v = b.w[2 * N + c], w = b.w[3 * N + c];
+    b.w[4 * N + c] = ovgm1 * b.p[c] + 0.5 * r * (u * u + v * v + w * w);
+}
+// extrapolate2ndHalo, src/solver/BCRoutines.F90:1870-1918
+__device__ __forceinline__ void bc_extrap2(const BlockDev& b, long long N, long long c0, long long c1, long long c2) {
+    double r0 = 2.0 * b.w[c1] - b.w[c2];
+    r0 = dmax_(0.5 * b.w[c1], r0);
+    b.w[c0] = r0;
+    b.w[N + c0] = 2.0 * b.w[N + c1] - b.w[N + c2];
+    b.w[2 * N + c0] = 2.0 * b.w[2 * N + c1] - b.w[2 * N + c2];
+    b.w[3 * N + c0] = 2.0 * b.w[3 * N + c1] - b.w[3 * N + c2];
+    b.p[c0] = dmax_(0.5 * b.p[c1], 2.0 * b.p[c1] - b.p[c2]);
+    if (c_prm.equations != ADFB_EULER) b.rlv[c0] = b.rlv[c1];
+    if (c_prm.equations == ADFB_RANS) b.rev[c0] = b.rev[c1];
+    bc_etot(b, N, c0);
+}
+
+__global__ void __launch_bounds__(128) k_bc_turb(Dims d, BlockDev b, FaceDev f, int secondHalo) {
+    const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
+    const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
+    if (ia > f.icEnd || jb > f.jcEnd) return;
+    const long long N = d.N;
+    const long long q = ia * f.sa + jb * f.sb;
+    const long long c0 = f.off[0] + q, c1 = f.off[1] + q, c2 = f.off[2] + q;
+    const long long na = f.icEnd - f.icBeg + 1, nb = f.jcEnd - f.jcBeg + 1;
+    const long long o = (ia - f.icBeg) + na * (jb - f.jcBeg);
+    double bmt = 0.0, bvt = 0.0;
+    const bool wall = f.bcType == ADFB_BC_NSWALL_ADIABATIC || f.bcType == ADFB_BC_NSWALL_ISOTHERMAL;
+    if (wall) bmt = 1.0;
+    else if (f.bcType == ADFB_BC_FARFIELD) {
+        const double dot = f.norm[o] * c_prm.wInf[1] + f.norm[o + na * nb] * c_prm.wInf[2] + f.norm[o + 2 * na * nb] * c_prm.wInf[3] -
+                           (f.rface ? f.rface[o] : 0.0);
+        if (dot > 0.0) bmt = -1.0; else bvt = c_prm.wInf[5];
+    } else bmt = -1.0;  // symm, Euler wall, extrapolation: zero gradient
+    double* nt = b.w + 5 * N;
+    double v1 = bvt;
+    v1 = v1 - bmt * nt[c2];
+    nt[c1] = v1;
+    const double r1 = wall ? -b.rev[c2] : b.rev[c2];
+    b.rev[c1] = r1;
+    if (secondHalo) { nt[c0] = v1; b.rev[c0] = r1; }
+}
+
+// phase: 1 = symmetry first halo, 2 = symmetry second halo, 0 = everything else
+__global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, int secondHalo, int phase) {
+    const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
+    const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
+    if (ia > f.icEnd || jb > f.jcEnd) return;
+    const long long N = d.N;
+    const long long q = ia * f.sa + jb * f.sb;
+    const long long c0 = f.off[0] + q, c1 = f.off[1] + q, c2 = f.off[2] + q, c3 = f.off[3] + q;
+    const long long na = f.icEnd - f.icBeg + 1, nb = f.jcEnd - f.jcBeg + 1;
+    const long long o = (ia - f.icBeg) + na * (jb - f.jcBeg);
+    const double n1 = f.norm ? f.norm[o] : 0.0, n2 = f.norm ? f.norm[o + na * nb] : 0.0, n3 = f.norm ? f.norm[o + 2 * na * nb] : 0.0;
+    const double rface = f.rface ? f.rface[o] : 0.0;
+    const bool viscous = c_prm.equations != ADFB_EULER, eddy = c_prm.equations == ADFB_RANS;
+    const double gam = c_prm.gammaInf;
+    double* w = b.w;
+    switch (f.bcType) {
+        case ADFB_BC_SYMM: {  // bcSymm1stHalo / bcSymm2ndHalo, BCRoutines.F90:223-340
+            const long long ch = phase == 1 ? c1 : c0, ci = phase == 1 ? c2 : c3;
+            const double u = w[N + ci], v = w[2 * N + ci], ww = w[3 * N + ci];
+            const double vn = 2.0 * (u * n1 + v * n2 + ww * n3);
+            w[ch] = w[ci];
+            w[N + ch] = u - vn * n1;
+            w[2 * N + ch] = v - vn * n2;
+            w[3 * N + ch] = ww - vn * n3;
+            w[4 * N + ch] = w[4 * N + ci];
+            b.p[ch] = b.p[ci];
+            if (viscous) b.rlv[ch] = b.rlv[ci];
+            if (eddy) b.rev[ch] = b.rev[ci];
+            break;
+        }
+        case ADFB_BC_NSWALL_ADIABATIC: {  // bcNSWallAdiabatic, BCRoutines.F90:489-578
+            double us1 = 0.0, us2 = 0.0, us3 = 0.0;
+            if (f.uSlip) { us1 = f.uSlip[o]; us2 = f.uSlip[o + na * nb]; us3 = f.uSlip[o + 2 * na * nb]; }
+            w[c1] = w[c2];
+            w[N + c1] = -w[N + c2] + 2.0 * us1;
+            w[2 * N + c1] = -w[2 * N + c2] + 2.0 * us2;
+            w[3 * N + c1] = -w[3 * N + c2] + 2.0 * us3;
+            b.rlv[c1] = b.rlv[c2];
+            if (eddy) b.rev[c1] = -b.rev[c2];
+            if (c_prm.wallBCConstantPressure) {
+                b.p[c1] = b.p[c2];
+            } else {
+                double p1 = 2.0 * b.p[c2] - b.p[c3];
+                if (p1 <= 0.0) p1 = b.p[c2];
+                b.p[c1] = p1;
+            }
+            bc_etot(b, N, c1);
+            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            break;
+        }
+        case ADFB_BC_FARFIELD: {  // bcFarfield, BCRoutines.F90:1282-1396
+            const double gm1 = gam - 1.0, ovgm1 = 1.0 / gm1;
+            const double r0 = 1.0 / c_prm.wInf[0], u0 = c_prm.wInf[1], v0 = c_prm.wInf[2], w0 = c_prm.wInf[3];
+            const double c0s = sqrt(gam * c_prm.pInfCorr * r0);
+            const double s0 = pow(c_prm.wInf[0], gam) / c_prm.pInfCorr;
+            const double qn0 = u0 * n1 + v0 * n2 + w0 * n3;
+            const double vn0 = qn0 - rface;
+            const double rho2 = w[c2];
+            const double re = 1.0 / rho2, ue = w[N + c2], ve = w[2 * N + c2], we = w[3 * N + c2];
+            const double qne = ue * n1 + ve * n2 + we * n3;
+            const double p2 = b.p[c2];
+            const double ce = sqrt(gam * p2 * re);
+            double ac1, ac2;
+            if (vn0 > -c0s) ac1 = qne + 2.0 * ovgm1 * ce; else ac1 = qn0 + 2.0 * ovgm1 * c0s;
+            if (vn0 > c0s) ac2 = qne - 2.0 * ovgm1 * ce; else ac2 = qn0 - 2.0 * ovgm1 * c0s;
+            const double qnf = 0.5 * (ac1 + ac2);
+            const double cf = 0.25 * (ac1 - ac2) * gm1;
+            double uf, vf, wf, sfv;
+            if (vn0 > 0.0) {
+                uf = ue + (qnf - qne) * n1; vf = ve + (qnf - qne) * n2; wf = we + (qnf - qne) * n3;
+                sfv = pow(rho2, gam) / p2;
+            } else {
+                uf = u0 + (qnf - qn0) * n1; vf = v0 + (qnf - qn0) * n2; wf = w0 + (qnf - qn0) * n3;
+                sfv = s0;
+            }
+            const double cc = cf * cf / gam;
+            const double r1 = pow(sfv * cc, ovgm1);
+            w[c1] = r1; w[N + c1] = uf; w[2 * N + c1] = vf; w[3 * N + c1] = wf;
+            b.p[c1] = r1 * cc;
+            if (viscous) b.rlv[c1] = b.rlv[c2];
+            if (eddy) b.rev[c1] = b.rev[c2];
+            bc_etot(b, N, c1);
+            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            break;
+        }
+        case ADFB_BC_EULERWALL: {  // bcEulerWall, BCRoutines.F90:1063-1280 (constant / linear pressure)
+            const double grad = c_prm.reserved ? 0.0 : b.p[c3] - b.p[c2];
+            b.p[c1] = dmax_(b.p[c2] - grad, 0.0);
+            const double u = w[N + c2], v = w[2 * N + c2], ww = w[3 * N + c2];
+            const double vn = 2.0 * (rface - u * n1 - v * n2 - ww * n3);
+            w[c1] = w[c2];
+            w[N + c1] = u + vn * n1; w[2 * N + c1] = v + vn * n2; w[3 * N + c1] = ww + vn * n3;
+            if (viscous) b.rlv[c1] = b.rlv[c2];
+            if (eddy) b.rev[c1] = b.rev[c2];
+            bc_etot(b, N, c1);
+            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            break;
+        }
+        default: break;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// executeRkStage part 1: dw *= cfl*etaRK(stage)*dtl, smoothers.F90:196-218
+__global__ void __launch_bounds__(256) k_rk_scale(Dims d, BlockDev b, double tmp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
+    if (i > d.il || j > d.jl || k > d.kl) return;
+    const long long c = ADFB_IDX(i, j, k), N = d.N;
+    const double dt = tmp * b.dtl[c];
+#pragma unroll
+    for (int l = 0; l < 5; l++) b.dw[l * N + c] = b.dw[l * N + c] * dt;
+}
+
+// executeRkStage part 2 (smoothers.F90:298-354): conservative update -> primitive,
+// clips, then computeEtotBlock + computeLamViscosity + computeEddyViscosity fused.
+// scaleDt != 0 folds part 1 in (used when no residual averaging runs in between).
+__global__ void __launch_bounds__(256) k_rk_update(Dims d, BlockDev b, int scaleDt, double tmp, int nw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
+    if (i > d.il || j > d.jl || k > d.kl) return;
+    const long long c = ADFB_IDX(i, j, k), N = d.N;
+    double dw[5];
+#pragma unroll
+    for (int l = 0; l < 5; l++) dw[l] = b.dw[l * N + c];
+    if (scaleDt) {
+        const double dt = tmp * b.dtl[c];
+#pragma unroll
+        for (int l = 0; l < 5; l++) { dw[l] = dw[l] * dt; b.dw[l * N + c] = dw[l]; }
+    }
+    const double gm1 = c_prm.gammaInf - 1.0;
+    const double rho = b.w[c], u = b.w[N + c], v = b.w[2 * N + c], w = b.w[3 * N + c], e = b.w[4 * N + c];
+    double ovr = 1.0 / rho;
+    const double v2 = u * u + v * v + w * w;
+    const double dp = (ovr * b.p[c] + 0.0 - gm1 * (ovr * e - v2)) * dw[0] + gm1 * (dw[4] - u * dw[1] - v * dw[2] - w * dw[3]);
+    const double rn = b.wn[c];
+    double rnew = rn - dw[0];
+    rnew = dmax_(rnew, 1.e-4 * c_prm.rhoInf);
+    const double ru = rn * b.wn[N + c] - dw[1];
+    const double rv = rn * b.wn[2 * N + c] - dw[2];
+    const double rw = rn * b.wn[3 * N + c] - dw[3];
+    ovr = 1.0 / rnew;
+    const double un = ovr * ru, vn = ovr * rv, wn_ = ovr * rw;
+    double pnew = b.pn[c] - dp;
+    pnew = dmax_(pnew, 1.e-4 * c_prm.pInfCorr);
+    b.w[c] = rnew; b.w[N + c] = un; b.w[2 * N + c] = vn; b.w[3 * N + c] = wn_;
+    b.p[c] = pnew;
+    b.w[4 * N + c] = (1.0 / gm1) * pnew + 0.5 * rnew * (un * un + vn * vn + wn_ * wn_);
+    if (c_prm.equations == ADFB_EULER) return;
+    const double T = pnew / (c_prm.RGas * rnew);
+    const double rlv = c_prm.muSuth * ((c_prm.TSuth + c_prm.SSuth) / (T + c_prm.SSuth)) * pow(T / c_prm.TSuth, 1.5);
+    b.rlv[c] = rlv;
+    if (c_prm.equations != ADFB_RANS || nw < 6) return;
+    const double rnuSA = b.w[5 * N + c] * rnew;
+    const double chi = rnuSA / rlv;
+    const double chi3 = chi * chi * chi;
+    const double cv13 = c_prm.rsaCv1 * c_prm.rsaCv1 * c_prm.rsaCv1;
+    b.rev[c] = chi3 / (chi3 + cv13) * rnuSA;
+}
+
+// ---------------------------------------------------------------------------
+// residualAveraging, one direction (residuals.F90:1850-1927 i, :1929-1993 j, :1995-2078 k).
+// One thread per grid line; n owned cells along the line (stride sd); the two other
+// owned index ranges are spanned by the grid (q1 fastest).  epz/d/t live in scratch
+// slots 0..2 of the block (same box indexing).
+__device__ __forceinline__ double ra_rfl(const BlockDev& b, const Dims& d, long long c, double plim) {
+    const double* p = b.p;
+    const double p0 = p[c];
+    const double dpi = fabs(p[c + 1] - 2.0 * p0 + p[c - 1]) / (p[c + 1] + 2.0 * p0 + p[c - 1] + plim);
+    const double dpj = fabs(p[c + d.sJ] - 2.0 * p0 + p[c - d.sJ]) / (p[c + d.sJ] + 2.0 * p0 + p[c - d.sJ] + plim);
+    const double dpk = fabs(p[c + d.sK] - 2.0 * p0 + p[c - d.sK]) / (p[c + d.sK] + 2.0 * p0 + p[c - d.sK] + plim);
+    return 1.0 / (1.0 + 2.0 * (dpi + dpj + dpk));
+}
+__global__ void __launch_bounds__(128) k_resavg_line(Dims d, BlockDev b, long long sd, int n, long long s1, int n1, long long s2,
+                                                     int n2, double rfl0) {
+    const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int q2 = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    if (q1 > n1 + 1 || q2 > n2 + 1) return;
+    const long long N = d.N;
+    const long long base = q1 * s1 + q2 * s2;
+    const double plim = 0.001 * c_prm.pInfCorr, smoop = c_prm.smoop;
+    double* epzA = b.scratch;       // epz(i)
+    double* dA = b.scratch + N;     // d(i)
+    const int l = n + 1;
+    // forward sweep fused with the coefficient recurrences
+    double epzm = 0.0, dm = 0.0;    // epz(i-1), d(i-1) ; epz(1) = d(1) = 0
+    double rflc = ra_rfl(b, d, base + 2 * sd, plim);
+    double dwm[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // dw(i-1) after the forward update (multiplied by epz(1)=0 at i=2)
+    for (int i = 2; i <= l; i++) {
+        const long long c = base + i * sd;
+        double epz = 0.0;
+        if (i <= n) {
+            const double rfln = ra_rfl(b, d, c + sd, plim);
+            const double r = rfl0 * (rflc + rfln);
+            epz = 0.25 * smoop * dmax_(r * r - 1.0, 0.0) * dmax_((double)b.iblank[c], 0.0);
+            rflc = rfln;
+        }
+        const double t = 1.0 / (1.0 + epz + epzm - epzm * dm);
+        const double dd = t * epz;
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+            const double v = t * (b.dw[m * N + c] + epzm * dwm[m]);
+            b.dw[m * N + c] = v;
+            dwm[m] = v;
+        }
+        dA[c] = dd;
+        epzA[c] = epz;
+        epzm = epz; dm = dd;
+    }
+    // backward substitution i = n .. 2
+    for (int m = 0; m < 5; m++) dwm[m] = b.dw[m * N + base + l * sd];
+    for (int i = n; i >= 2; i--) {
+        const long long c = base + i * sd;
+        const double dd = dA[c];
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+            const double v = b.dw[m * N + c] + dd * dwm[m];
+            b.dw[m * N + c] = v;
+            dwm[m] = v;
+        }
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+static int launch_bc_turb(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, int secondHalo, cudaStream_t s) {
+    for (const AdfbSubface& sf : subs) {
+        FaceDev f = make_face(d, sf);
+        dim3 tb(32, 4);
+        dim3 g((f.icEnd - f.icBeg + 1 + 31) / 32, (f.jcEnd - f.jcBeg + 1 + 3) / 4);
+        KT_BEGIN(K_BC, s);
+        k_bc_turb<<<g, tb, 0, s>>>(d, b, f, secondHalo);
+        KT_END(K_BC, s);
+    }
+    return (int)cudaGetLastError();
+}
+
+static void launch_bc_one(const Dims& d, const BlockDev& b, const AdfbSubface& sf, int secondHalo, int phase, cudaStream_t s) {
+    FaceDev f = make_face(d, sf);
+    dim3 tb(32, 4);
+    dim3 g((f.icEnd - f.icBeg + 1 + 31) / 32, (f.jcEnd - f.jcBeg + 1 + 3) / 4);
+    KT_BEGIN(K_BC, s);
+    k_bc_flow<<<g, tb, 0, s>>>(d, b, f, secondHalo, phase);
+    KT_END(K_BC, s);
+}
+
+// applyAllBC_block order, src/solver/BCRoutines.F90:81-216
+static int launch_bc_flow(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, int secondHalo, cudaStream_t s) {
+    for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SYMM) launch_bc_one(d, b, sf, secondHalo, 1, s);
+    if (secondHalo)
+        for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SYMM) launch_bc_one(d, b, sf, secondHalo, 2, s);
+    for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_NSWALL_ADIABATIC) launch_bc_one(d, b, sf, secondHalo, 0, s);
+    for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_FARFIELD) launch_bc_one(d, b, sf, secondHalo, 0, s);
+    for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_EULERWALL) launch_bc_one(d, b, sf, secondHalo, 0, s);
+    return (int)cudaGetLastError();
+}
+
+static int launch_residual_averaging(const Dims& d, const BlockDev& b, const AdfbParams& prm, cudaStream_t s) {
+    const double rfl0 = 0.5 * prm.cfl / prm.cflLimit;
+    dim3 tb(32, 4);
+    auto run = [&](long long sd, int n, long long s1, int n1, long long s2, int n2) {
+        if (n <= 1) return;
+        dim3 g((n1 + 31) / 32, (n2 + 3) / 4);
+        KT_BEGIN(K_RK, s);
+        k_resavg_line<<<g, tb, 0, s>>>(d, b, sd, n, s1, n1, s2, n2, rfl0);
+        KT_END(K_RK, s);
+    };
+    run(1, d.nx, d.sJ, d.ny, d.sK, d.nz);
+    run(d.sJ, d.ny, 1, d.nx, d.sK, d.nz);
+    run(d.sK, d.nz, 1, d.nx, d.sJ, d.ny);
+    return (int)cudaGetLastError();
+}
+
+static int launch_rk_update(const Dims& d, const BlockDev& b, const AdfbParams& prm, int rkStage, cudaStream_t s) {
+    const double tmp = prm.cfl * prm.etaRK[rkStage - 1];
+    const bool smooth = prm.resAveraging == 1 || (prm.resAveraging == 2 && (rkStage % 2) == 1);
+    dim3 tb(32, 4, 2);
+    dim3 g((d.nx + 31) / 32, (d.ny + 3) / 4, (d.nz + 1) / 2);
+    const int nw = prm.equations == ADFB_RANS ? 6 : 5;
+    if (smooth) {
+        KT_BEGIN(K_RK, s);
+        k_rk_scale<<<g, tb, 0, s>>>(d, b, tmp);
+        KT_END(K_RK, s);
+        if (launch_residual_averaging(d, b, prm, s)) return 1;
+        KT_BEGIN(K_RK, s);
+        k_rk_update<<<g, tb, 0, s>>>(d, b, 0, tmp, nw);
+        KT_END(K_RK, s);
+    } else {
+        KT_BEGIN(K_RK, s);
+        k_rk_update<<<g, tb, 0, s>>>(d, b, 1, tmp, nw);
+        KT_END(K_RK, s);
+    }
+    return (int)cudaGetLastError();
+}

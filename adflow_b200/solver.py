@@ -75,6 +75,24 @@ class ADFLOW_B200:
         """blocketteRes (src/NKSolver/blockette.F90:70-297) on all local blocks."""
         check(self.L.adfb_residual(level, flags), "adfb_residual")
 
+    def applyBCs(self, second_halo=True, with_turb=True, level=1):
+        """applyAllBC (+ turbulence halo treatment) on all local blocks."""
+        check(self.L.adfb_apply_bcs(level, int(second_halo), int(with_turb)), "adfb_apply_bcs")
+
+    def timeStep(self, only_radii=False, level=1):
+        check(self.L.adfb_timestep(level, int(only_radii)), "adfb_timestep")
+
+    def smootherResidual(self, rk_stage=0, level=1):
+        """initres + residual of the smoother loops; rFil = cdisRK(rk_stage+1)."""
+        check(self.L.adfb_smoother_residual(level, rk_stage), "adfb_smoother_residual")
+
+    def rkStage(self, stage, level=1):
+        check(self.L.adfb_rk_stage(level, stage), "adfb_rk_stage")
+
+    def rkCycle(self, level=1):
+        """RungeKuttaSmoother (src/solver/smoothers.F90:4)."""
+        check(self.L.adfb_rk_cycle(level), "adfb_rk_cycle")
+
     def downloadResidual(self, blk):
         hb = self.blocks[blk]
         out = np.zeros(hb.d.box + (hb.nw,), order="F")

@@ -189,6 +189,23 @@ int adfb_residual(int level, unsigned flags);
 int adfb_norms(double out[2]);
 int adfb_synchronize(void);
 
+/* ---- smoothers ------------------------------------------------------------- */
+/* applyAllBC(secondHalo) (src/solver/BCRoutines.F90:57-222); withTurb != 0 first runs
+   bcTurbTreatment + applyAllTurbBCThisBlock (src/turbulence/turbBCRoutines.F90:49,662) */
+int adfb_apply_bcs(int level, int secondHalo, int withTurb);
+/* timeStep(onlyRadii): spectral radii radI/J/K and local time step dtl
+   (src/solver/solverUtils.F90:43-355) */
+int adfb_timestep(int level, int onlyRadii);
+/* `initres(1,nwf); sourceTerms; residual` as called by the smoothers
+   (src/solver/smoothers.F90:73-75, src/solver/multiGrid.F90:883-888): block-path
+   mean-flow residual_block (src/solver/residuals.F90:4-346) with
+   rFil = cdisRK(rkStage+1); the dissipative+viscous part fw persists on the device. */
+int adfb_smoother_residual(int level, int rkStage);
+/* executeRkStage (src/solver/smoothers.F90:90-382), rkStage = 1..nRKStages */
+int adfb_rk_stage(int level, int rkStage);
+/* RungeKuttaSmoother (src/solver/smoothers.F90:4-86); residual and dtl must be current */
+int adfb_rk_cycle(int level);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,13 @@ void orc_sa_viscous(const OrcBlock* b, const AdfbParams* prm);
 void orc_sa_res_scale(const OrcBlock* b);
 void orc_sum_dw_fw(const OrcBlock* b);
 void orc_norms(const OrcBlock* b, const AdfbParams* prm, double out[2]);
+/* adflow_oracle_smooth.c : BCs + Runge-Kutta smoother (subface arrays are HOST pointers) */
+void orc_apply_turb_bc(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf, int secondHalo);
+void orc_apply_flow_bc(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf, int secondHalo);
+void orc_residual_averaging(const OrcBlock* b, const AdfbParams* prm);
+void orc_residual_block(const OrcBlock* b, const AdfbParams* prm, double rFil);
+void orc_rk_stage(const OrcBlock* b, const AdfbParams* prm, int rkStage, int nSub, const AdfbSubface* sf);
+void orc_rk_smoother(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf);
 #ifdef __cplusplus
 }
 #endif

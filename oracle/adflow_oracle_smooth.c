@@ -1,0 +1,318 @@
+/*
+ * adflow_oracle_smooth.c -- CPU restatement of the boundary conditions and the
+ * Runge-Kutta smoother of the ADflow hot path.  TEST INFRASTRUCTURE ONLY
+ * (PARITY UNPINNED, see adflow_oracle.h).
+ */
+#include "orc_internal.h"
+
+/* ------------------------------------------------------------------------ */
+/* BC plane addressing == setBCPointers, src/utils/utils.F90:881-1174:
+   plane 0 = 2nd halo, 1 = 1st halo, 2 = first interior, 3 = second interior;
+   (a,b) are the two in-plane indices in the reference's order. */
+typedef struct Face {
+    long off[4];
+    long sa, sb;
+} Face;
+
+static Face face_of(Dims d, int faceId) {
+    Face f;
+    switch (faceId) {
+        case ADFB_IMIN: f.off[0] = 0; f.off[1] = 1; f.off[2] = 2; f.off[3] = 3; f.sa = d.sJ; f.sb = d.sK; break;
+        case ADFB_IMAX: f.off[0] = d.ib; f.off[1] = d.ie; f.off[2] = d.il; f.off[3] = d.nx; f.sa = d.sJ; f.sb = d.sK; break;
+        case ADFB_JMIN: f.off[0] = 0; f.off[1] = d.sJ; f.off[2] = 2 * d.sJ; f.off[3] = 3 * d.sJ; f.sa = 1; f.sb = d.sK; break;
+        case ADFB_JMAX: f.off[0] = d.jb * d.sJ; f.off[1] = d.je * d.sJ; f.off[2] = d.jl * d.sJ; f.off[3] = d.ny * d.sJ; f.sa = 1; f.sb = d.sK; break;
+        case ADFB_KMIN: f.off[0] = 0; f.off[1] = d.sK; f.off[2] = 2 * d.sK; f.off[3] = 3 * d.sK; f.sa = 1; f.sb = d.sJ; break;
+        default: f.off[0] = d.kb * d.sK; f.off[1] = d.ke * d.sK; f.off[2] = d.kl * d.sK; f.off[3] = d.nz * d.sK; f.sa = 1; f.sb = d.sJ; break;
+    }
+    return f;
+}
+#define NRM(sf, a, b, m) ((sf)->norm[((a) - (sf)->icBeg) + na * (((b) - (sf)->jcBeg) + nb * (long)(m))])
+
+/* computeEtot on one halo plane: src/solver/BCRoutines.F90:1816-1868 (cpConstant, no k) */
+static void bc_etot(const OrcBlock* b, Dims d, double gam, long c) {
+    double ovgm1 = one / (gam - one);
+    W(c, IRHOE) = ovgm1 * b->p[c] + half * W(c, IRHO) * (W(c, IVX) * W(c, IVX) + W(c, IVY) * W(c, IVY) + W(c, IVZ) * W(c, IVZ));
+}
+/* extrapolate2ndHalo: src/solver/BCRoutines.F90:1870-1918 */
+static void bc_extrap2(const OrcBlock* b, Dims d, const AdfbParams* prm, long c0, long c1, long c2) {
+    const double factor = 0.5;
+    W(c0, IRHO) = two * W(c1, IRHO) - W(c2, IRHO);
+    W(c0, IRHO) = dmax(factor * W(c1, IRHO), W(c0, IRHO));
+    W(c0, IVX) = two * W(c1, IVX) - W(c2, IVX);
+    W(c0, IVY) = two * W(c1, IVY) - W(c2, IVY);
+    W(c0, IVZ) = two * W(c1, IVZ) - W(c2, IVZ);
+    b->p[c0] = dmax(factor * b->p[c1], two * b->p[c1] - b->p[c2]);
+    if (prm->equations != ADFB_EULER) b->rlv[c0] = b->rlv[c1];
+    if (prm->equations == ADFB_RANS) b->rev[c0] = b->rev[c1];
+    bc_etot(b, d, prm->gammaInf, c0);
+}
+
+/* turbulence halo treatment of one subface: bcTurbTreatment + applyAllTurbBCThisBlock,
+   src/turbulence/turbBCRoutines.F90:49-236,662-797 specialised to the scalar SA
+   variable (bmt is 1x1): wall bmt=1 (:835-870), symm bmt=-1 (:614-660), far field
+   bmt=-1 on outflow else bvt=wInf (:373-459); bcEddyWall/NoWall :238-372;
+   turb2ndHalo :1132-1231. */
+static void bc_turb_subface(const OrcBlock* b, const AdfbParams* prm, const AdfbSubface* sf, int secondHalo) {
+    Dims d = dims_of(b);
+    Face f = face_of(d, sf->faceId);
+    long na = sf->icEnd - sf->icBeg + 1, nb = sf->jcEnd - sf->jcBeg + 1;
+    for (int jb_ = sf->jcBeg; jb_ <= sf->jcEnd; jb_++) for (int ia = sf->icBeg; ia <= sf->icEnd; ia++) {
+        long q = ia * f.sa + jb_ * f.sb;
+        long c0 = f.off[0] + q, c1 = f.off[1] + q, c2 = f.off[2] + q;
+        double bmt = zero, bvt = zero;
+        int wall = sf->bcType == ADFB_BC_NSWALL_ADIABATIC || sf->bcType == ADFB_BC_NSWALL_ISOTHERMAL;
+        if (wall) bmt = one;
+        else if (sf->bcType == ADFB_BC_SYMM) bmt = -one;
+        else if (sf->bcType == ADFB_BC_FARFIELD) {
+            double dot = NRM(sf, ia, jb_, 0) * prm->wInf[IVX] + NRM(sf, ia, jb_, 1) * prm->wInf[IVY] +
+                         NRM(sf, ia, jb_, 2) * prm->wInf[IVZ] - (sf->rface ? sf->rface[(ia - sf->icBeg) + na * (jb_ - sf->jcBeg)] : zero);
+            if (dot > zero) bmt = -one; else bvt = prm->wInf[ITU1];
+        } else if (sf->bcType == ADFB_BC_EULERWALL) bmt = -one; /* bcTurbSymm is used for Euler walls (:706) */
+        else if (sf->bcType == ADFB_BC_EXTRAP) bmt = -one;     /* bcTurbOutflow: zero gradient (:564-613) */
+        W(c1, ITU1) = bvt;
+        W(c1, ITU1) = W(c1, ITU1) - bmt * W(c2, ITU1);
+        if (wall) b->rev[c1] = -b->rev[c2]; else b->rev[c1] = b->rev[c2];
+        if (secondHalo) { W(c0, ITU1) = W(c1, ITU1); b->rev[c0] = b->rev[c1]; }
+    }
+}
+
+/* flow BC of one subface; phase selects symm 1st (1) / 2nd (2) halo, else the
+   whole routine.  src/solver/BCRoutines.F90: bcSymm1stHalo :223, bcSymm2ndHalo :282,
+   bcNSWallAdiabatic :489, bcFarfield :1282, bcEulerWall :1063, bcExtrap :1690. */
+static void bc_flow_subface(const OrcBlock* b, const AdfbParams* prm, const AdfbSubface* sf, int secondHalo, int phase) {
+    Dims d = dims_of(b);
+    Face f = face_of(d, sf->faceId);
+    long na = sf->icEnd - sf->icBeg + 1, nb = sf->jcEnd - sf->jcBeg + 1;
+    int viscous = prm->equations != ADFB_EULER, eddy = prm->equations == ADFB_RANS;
+    double gam = prm->gammaInf;
+    for (int jb_ = sf->jcBeg; jb_ <= sf->jcEnd; jb_++) for (int ia = sf->icBeg; ia <= sf->icEnd; ia++) {
+        long q = ia * f.sa + jb_ * f.sb;
+        long c0 = f.off[0] + q, c1 = f.off[1] + q, c2 = f.off[2] + q, c3 = f.off[3] + q;
+        double n1 = sf->norm ? NRM(sf, ia, jb_, 0) : zero, n2 = sf->norm ? NRM(sf, ia, jb_, 1) : zero,
+               n3 = sf->norm ? NRM(sf, ia, jb_, 2) : zero;
+        double rface = sf->rface ? sf->rface[(ia - sf->icBeg) + na * (jb_ - sf->jcBeg)] : zero;
+        switch (sf->bcType) {
+            case ADFB_BC_SYMM: {
+                long ch = phase == 1 ? c1 : c0, ci = phase == 1 ? c2 : c3;
+                double vn = two * (W(ci, IVX) * n1 + W(ci, IVY) * n2 + W(ci, IVZ) * n3);
+                W(ch, IRHO) = W(ci, IRHO);
+                W(ch, IVX) = W(ci, IVX) - vn * n1;
+                W(ch, IVY) = W(ci, IVY) - vn * n2;
+                W(ch, IVZ) = W(ci, IVZ) - vn * n3;
+                W(ch, IRHOE) = W(ci, IRHOE);
+                b->p[ch] = b->p[ci];
+                if (viscous) b->rlv[ch] = b->rlv[ci];
+                if (eddy) b->rev[ch] = b->rev[ci];
+                break;
+            }
+            case ADFB_BC_NSWALL_ADIABATIC: {
+                double us1 = zero, us2 = zero, us3 = zero;
+                if (sf->uSlip) {
+                    long o = (ia - sf->icBeg) + na * (jb_ - sf->jcBeg);
+                    us1 = sf->uSlip[o]; us2 = sf->uSlip[o + na * nb]; us3 = sf->uSlip[o + 2 * na * nb];
+                }
+                W(c1, IRHO) = W(c2, IRHO);
+                W(c1, IVX) = -W(c2, IVX) + two * us1;
+                W(c1, IVY) = -W(c2, IVY) + two * us2;
+                W(c1, IVZ) = -W(c2, IVZ) + two * us3;
+                b->rlv[c1] = b->rlv[c2];
+                if (eddy) b->rev[c1] = -b->rev[c2];
+                if (prm->wallBCConstantPressure) {
+                    b->p[c1] = b->p[c2] - four * third * zero;
+                } else {
+                    b->p[c1] = 2 * b->p[c2] - b->p[c3];
+                    if (b->p[c1] <= zero) b->p[c1] = b->p[c2];
+                }
+                bc_etot(b, d, gam, c1);
+                if (secondHalo) bc_extrap2(b, d, prm, c0, c1, c2);
+                break;
+            }
+            case ADFB_BC_FARFIELD: {
+                double gm1 = gam - one, ovgm1 = one / gm1;
+                double r0 = one / prm->wInf[IRHO], u0 = prm->wInf[IVX], v0 = prm->wInf[IVY], w0 = prm->wInf[IVZ];
+                double c0s = sqrt(gam * prm->pInfCorr * r0);
+                double s0 = pow(prm->wInf[IRHO], gam) / prm->pInfCorr;
+                double qn0 = u0 * n1 + v0 * n2 + w0 * n3;
+                double vn0 = qn0 - rface;
+                double re = one / W(c2, IRHO), ue = W(c2, IVX), ve = W(c2, IVY), we = W(c2, IVZ);
+                double qne = ue * n1 + ve * n2 + we * n3;
+                double ce = sqrt(gam * b->p[c2] * re);
+                double ac1, ac2;
+                if (vn0 > -c0s) ac1 = qne + two * ovgm1 * ce; else ac1 = qn0 + two * ovgm1 * c0s;
+                if (vn0 > c0s) ac2 = qne - two * ovgm1 * ce; else ac2 = qn0 - two * ovgm1 * c0s;
+                double qnf = half * (ac1 + ac2);
+                double cf = fourth * (ac1 - ac2) * gm1;
+                double uf, vf, wf, sfv;
+                if (vn0 > zero) {
+                    uf = ue + (qnf - qne) * n1; vf = ve + (qnf - qne) * n2; wf = we + (qnf - qne) * n3;
+                    sfv = pow(W(c2, IRHO), gam) / b->p[c2];
+                } else {
+                    uf = u0 + (qnf - qn0) * n1; vf = v0 + (qnf - qn0) * n2; wf = w0 + (qnf - qn0) * n3;
+                    sfv = s0;
+                }
+                double cc = cf * cf / gam;
+                W(c1, IRHO) = pow(sfv * cc, ovgm1);
+                W(c1, IVX) = uf; W(c1, IVY) = vf; W(c1, IVZ) = wf;
+                b->p[c1] = W(c1, IRHO) * cc;
+                if (viscous) b->rlv[c1] = b->rlv[c2];
+                if (eddy) b->rev[c1] = b->rev[c2];
+                bc_etot(b, d, gam, c1);
+                if (secondHalo) bc_extrap2(b, d, prm, c0, c1, c2);
+                break;
+            }
+            case ADFB_BC_EULERWALL: {
+                /* eulerWallBCTreatment: linear pressure extrapolation (pyADflow default) or
+                   constant pressure; the normal-momentum variant is not restated */
+                double grad = prm->reserved ? zero : b->p[c3] - b->p[c2];
+                b->p[c1] = fdim_(b->p[c2], grad);
+                double vn = two * (rface - W(c2, IVX) * n1 - W(c2, IVY) * n2 - W(c2, IVZ) * n3);
+                W(c1, IRHO) = W(c2, IRHO);
+                W(c1, IVX) = W(c2, IVX) + vn * n1;
+                W(c1, IVY) = W(c2, IVY) + vn * n2;
+                W(c1, IVZ) = W(c2, IVZ) + vn * n3;
+                if (viscous) b->rlv[c1] = b->rlv[c2];
+                if (eddy) b->rev[c1] = b->rev[c2];
+                bc_etot(b, d, gam, c1);
+                if (secondHalo) bc_extrap2(b, d, prm, c0, c1, c2);
+                break;
+            }
+            default: break;
+        }
+    }
+}
+
+/* applyAllTurbBCThisBlock order: subfaces in nBocos order */
+void orc_apply_turb_bc(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf, int secondHalo) {
+    if (prm->equations != ADFB_RANS) return;
+    for (int n = 0; n < nSub; n++) bc_turb_subface(b, prm, &sf[n], secondHalo);
+}
+/* applyAllBC_block order, src/solver/BCRoutines.F90:81-216: symm 1st halo, symm 2nd
+   halo, (polar), adiabatic walls, isothermal walls, far field, (outflow, inflow),
+   extrapolation, Euler walls, (supersonic inflow) */
+void orc_apply_flow_bc(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf, int secondHalo) {
+    int n;
+    for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SYMM) bc_flow_subface(b, prm, &sf[n], secondHalo, 1);
+    if (secondHalo) for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SYMM) bc_flow_subface(b, prm, &sf[n], secondHalo, 2);
+    for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_NSWALL_ADIABATIC) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
+    for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_FARFIELD) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
+    for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_EULERWALL) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
+}
+
+/* ------------------------------------------------------------------------ */
+/* residualAveraging: src/solver/residuals.F90:1785-2080 (fine level: cfl) */
+static double ra_rfl(const OrcBlock* b, Dims d, long c, double plim) {
+    const double* p = b->p;
+    double dpi = fabs(p[c + 1] - two * p[c] + p[c - 1]) / (p[c + 1] + two * p[c] + p[c - 1] + plim);
+    double dpj = fabs(p[c + d.sJ] - two * p[c] + p[c - d.sJ]) / (p[c + d.sJ] + two * p[c] + p[c - d.sJ] + plim);
+    double dpk = fabs(p[c + d.sK] - two * p[c] + p[c - d.sK]) / (p[c + d.sK] + two * p[c] + p[c - d.sK] + plim);
+    return one / (one + 2.0 * (dpi + dpj + dpk));
+}
+/* one direction: lines of n owned cells with stride sd; other two owned ranges looped */
+static void ra_dir(const OrcBlock* b, const AdfbParams* prm, Dims d, long sd, int n, long s1, int n1, long s2, int n2) {
+    if (n <= 1) return;
+    double rfl0 = half * prm->cfl / prm->cflLimit, plim = 0.001 * prm->pInfCorr;
+    int l = n + 1; /* il-equivalent along the line: owned 2..l */
+    double* epz = (double*)malloc(sizeof(double) * (l + 2));
+    double* dd = (double*)malloc(sizeof(double) * (l + 2));
+    double* t = (double*)malloc(sizeof(double) * (l + 2));
+    for (int q2 = 2; q2 <= n2 + 1; q2++) for (int q1 = 2; q1 <= n1 + 1; q1++) {
+        long base = q1 * s1 + q2 * s2;
+        for (int i = 2; i <= n; i++) {
+            long c = base + i * sd;
+            double r = rfl0 * (ra_rfl(b, d, c, plim) + ra_rfl(b, d, c + sd, plim));
+            epz[i] = fourth * prm->smoop * fdim_(r * r, one) * dmax((double)b->iblank[c], zero);
+        }
+        epz[1] = zero; epz[l] = zero; dd[1] = zero;
+        for (int i = 2; i <= l; i++) {
+            t[i] = one / (one + epz[i] + epz[i - 1] - epz[i - 1] * dd[i - 1]);
+            dd[i] = t[i] * epz[i];
+        }
+        for (int i = 2; i <= l; i++) {
+            long c = base + i * sd;
+            for (int m = 0; m < 5; m++) DW(c, m) = t[i] * (DW(c, m) + epz[i - 1] * DW(c - sd, m));
+        }
+        for (int i = n; i >= 2; i--) {
+            long c = base + i * sd;
+            for (int m = 0; m < 5; m++) DW(c, m) = DW(c, m) + dd[i] * DW(c + sd, m);
+        }
+    }
+    free(epz); free(dd); free(t);
+}
+void orc_residual_averaging(const OrcBlock* b, const AdfbParams* prm) {
+    Dims d = dims_of(b);
+    ra_dir(b, prm, d, d.sI, d.nx, d.sJ, d.ny, d.sK, d.nz);
+    ra_dir(b, prm, d, d.sJ, d.ny, d.sI, d.nx, d.sK, d.nz);
+    ra_dir(b, prm, d, d.sK, d.nz, d.sI, d.nx, d.sJ, d.ny);
+}
+
+/* ------------------------------------------------------------------------ */
+/* block-path mean-flow residual used by the smoothers:
+   initres (fine grid steady: dw = 0, src/solver/residuals.F90:427-497) +
+   residual_block (:4-346) with rFil = cdisRK(rkStage+1) for the RK smoother.
+   Radii are NOT recomputed (timeStep is a separate call in executeMGCycle). */
+void orc_residual_block(const OrcBlock* b, const AdfbParams* prm, double rFil) {
+    Dims d = dims_of(b);
+    int viscous = prm->equations != ADFB_EULER;
+    memset(b->dw, 0, sizeof(double) * 5 * d.N);
+    orc_central_flux(b, prm);
+    if (fabs(rFil) >= thresholdReal) {
+        /* orc_diss_scalar recomputes ss/dss and scales fw by (1-rFil) like fluxes.F90:1193 */
+        orc_diss_scalar(b, prm, rFil);
+        if (viscous) {
+            orc_speed_of_sound(b, prm);
+            orc_nodal_gradients(b);
+            orc_viscous_flux(b, prm, rFil);
+        }
+    }
+    orc_sum_dw_fw(b);
+}
+
+/* executeRkStage: src/solver/smoothers.F90:90-382 (steady, fine level, no precond);
+   BCs and halo exchange are the caller's (single block: BCs only). */
+void orc_rk_stage(const OrcBlock* b, const AdfbParams* prm, int rkStage, int nSub, const AdfbSubface* sf) {
+    Dims d = dims_of(b);
+    double tmp = prm->cfl * prm->etaRK[rkStage - 1];
+    int smooth = prm->resAveraging == 1 || (prm->resAveraging == 2 && (rkStage % 2) == 1);
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
+        long c = IDX(i, j, k);
+        double dt = tmp * b->dtl[c];
+        for (int l = 0; l < 5; l++) DW(c, l) = DW(c, l) * dt;
+    }
+    if (smooth) orc_residual_averaging(b, prm);
+    double gm1 = prm->gammaInf - one;
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
+        long c = IDX(i, j, k);
+        double ovr = one / W(c, IRHO);
+        double v2 = W(c, IVX) * W(c, IVX) + W(c, IVY) * W(c, IVY) + W(c, IVZ) * W(c, IVZ);
+        double factK = zero;
+        double dp = (ovr * b->p[c] + factK - gm1 * (ovr * W(c, IRHOE) - v2)) * DW(c, IRHO) +
+                    gm1 * (DW(c, IRHOE) - W(c, IVX) * DW(c, IMX) - W(c, IVY) * DW(c, IMY) - W(c, IVZ) * DW(c, IMZ));
+        const double* wn = b->wn;
+        W(c, IRHO) = wn[c] - DW(c, IRHO);
+        W(c, IRHO) = dmax(W(c, IRHO), 1.e-4 * prm->rhoInf);
+        double ru = wn[c] * wn[d.N + c] - DW(c, IMX);
+        double rv = wn[c] * wn[2 * d.N + c] - DW(c, IMY);
+        double rw = wn[c] * wn[3 * d.N + c] - DW(c, IMZ);
+        ovr = one / W(c, IRHO);
+        W(c, IVX) = ovr * ru; W(c, IVY) = ovr * rv; W(c, IVZ) = ovr * rw;
+        b->p[c] = b->pn[c] - dp;
+        b->p[c] = dmax(b->p[c], 1.e-4 * prm->pInfCorr);
+    }
+    orc_etot(b, prm, 2, d.il, 2, d.jl, 2, d.kl);
+    orc_lam_viscosity(b, prm, 0);
+    orc_eddy_viscosity(b, prm, 0);
+    orc_apply_flow_bc(b, prm, nSub, sf, 1);
+}
+
+/* RungeKuttaSmoother: src/solver/smoothers.F90:4-86.  On entry residual (rFil =
+   cdisRK(1)) and dtl are assumed computed, like the reference. */
+void orc_rk_smoother(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf) {
+    Dims d = dims_of(b);
+    for (int l = 0; l < 5; l++) memcpy(b->wn + (long)l * d.N, b->w + (long)l * d.N, sizeof(double) * d.N);
+    memcpy(b->pn, b->p, sizeof(double) * d.N);
+    for (int st = 1; st <= prm->nRKStages - 1; st++) {
+        orc_rk_stage(b, prm, st, nSub, sf);
+        orc_residual_block(b, prm, prm->cdisRK[st]);
+    }
+    orc_rk_stage(b, prm, prm->nRKStages, nSub, sf);
+}

@@ -99,5 +99,47 @@ class Oracle:
         self.L.orc_norms(_p(self.ob), _p(self.prm), out)
         return np.array([out[0], out[1]])
 
+    # -- BCs + smoothers (adflow_oracle_smooth.c) ------------------------------
+    def _subfaces(self):
+        from adflow_b200._lib import AdfbSubface
+        subs = self.hb.subfaces
+        arr = (AdfbSubface * max(1, len(subs)))()
+        self._keep = []
+        for q, s in enumerate(subs):
+            arr[q].bcType, arr[q].faceId = s["bcType"], s["faceId"]
+            arr[q].icBeg, arr[q].icEnd, arr[q].jcBeg, arr[q].jcEnd = s["icBeg"], s["icEnd"], s["jcBeg"], s["jcEnd"]
+            for name in ("norm", "rface", "uSlip", "TNSWall"):
+                a = s.get(name)
+                if a is not None:
+                    a = np.asfortranarray(a, dtype=np.float64)
+                    self._keep.append(a)
+                    setattr(arr[q], name, a.ctypes.data)
+        return len(subs), arr
+
+    def apply_turb_bc(self, second_halo=True):
+        n, arr = self._subfaces()
+        self.L.orc_apply_turb_bc(_p(self.ob), _p(self.prm), C.c_int(n), arr, C.c_int(int(second_halo)))
+
+    def apply_flow_bc(self, second_halo=True):
+        n, arr = self._subfaces()
+        self.L.orc_apply_flow_bc(_p(self.ob), _p(self.prm), C.c_int(n), arr, C.c_int(int(second_halo)))
+
+    def residual_averaging(self):
+        self.L.orc_residual_averaging(_p(self.ob), _p(self.prm))
+
+    def residual_block(self, rfil=1.0):
+        self.L.orc_residual_block(_p(self.ob), _p(self.prm), C.c_double(rfil))
+
+    def time_step(self, update_dt=True):
+        self.L.orc_time_step(_p(self.ob), _p(self.prm), C.c_int(int(update_dt)))
+
+    def rk_stage(self, stage):
+        n, arr = self._subfaces()
+        self.L.orc_rk_stage(_p(self.ob), _p(self.prm), C.c_int(stage), C.c_int(n), arr)
+
+    def rk_smoother(self):
+        n, arr = self._subfaces()
+        self.L.orc_rk_smoother(_p(self.ob), _p(self.prm), C.c_int(n), arr)
+
     def call(self, name, *args):
         getattr(self.L, name)(_p(self.ob), *args)
