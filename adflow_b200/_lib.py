@@ -19,6 +19,7 @@ ABI_SYMBOLS = [
     "adfb_set_params", "adfb_upload_state", "adfb_download_state", "adfb_upload_visc",
     "adfb_download_residual", "adfb_download_intermed", "adfb_residual", "adfb_norms", "adfb_synchronize",
     "adfb_get_states", "adfb_set_states", "adfb_get_res", "adfb_state_size",
+    "adfb_comm_set_pattern", "adfb_halo_exchange",
     "adfb_apply_bcs", "adfb_timestep", "adfb_smoother_residual", "adfb_rk_stage", "adfb_rk_cycle",
 ]
 
@@ -69,6 +70,8 @@ def load():
     for fn in (L.adfb_get_states, L.adfb_set_states, L.adfb_get_res):
         fn.argtypes = [vp, C.c_longlong]
     L.adfb_state_size.restype = C.c_longlong
+    L.adfb_comm_set_pattern.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, vp, vp]
+    L.adfb_halo_exchange.argtypes = [ci] * 6
     L.adfb_apply_bcs.argtypes = [ci, ci, ci]
     L.adfb_timestep.argtypes = [ci, ci]
     L.adfb_smoother_residual.argtypes = [ci, ci]

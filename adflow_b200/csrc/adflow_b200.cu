@@ -18,6 +18,7 @@
 #include "state_kernels.cuh"
 #include "residual_kernels.cuh"
 #include "smoother_kernels.cuh"
+#include "halo_kernels.cuh"
 
 namespace {
 
@@ -45,6 +46,23 @@ struct Context {
     double* dVec = nullptr;   // AoS staging vector (get/set states, get res)
     size_t dVecN = 0;
     std::string err;
+    // multi-rank
+    NcclApi nccl;
+    ncclComm_t_ comm = nullptr;
+    // 1-to-1 communication pattern (commPatternCell_2nd + internalCell_2nd,
+    // src/modules/communication.F90:85-168), device resident
+    struct Pattern {
+        bool set = false;
+        std::vector<int> nbrRank, sendCount, recvCount;
+        long long nSend = 0, nRecv = 0, nInt = 0;
+        int *sBlk = nullptr, *sLocal = nullptr, *sCount = nullptr; long long *sOff = nullptr, *sCum = nullptr;
+        int *rBlk = nullptr, *rLocal = nullptr, *rCount = nullptr; long long *rOff = nullptr, *rCum = nullptr;
+        int *iSrcBlk = nullptr, *iDstBlk = nullptr; long long *iSrcOff = nullptr, *iDstOff = nullptr;
+        double *sendBuf = nullptr, *recvBuf = nullptr;
+        CommVarTable* dTab = nullptr;
+        int tabBlocks = 0;
+        std::vector<void*> allocs;
+    } pat;
 };
 
 Context g;
@@ -164,7 +182,10 @@ int adfb_device_count(void) {
 
 int adfb_get_unique_id(void* out128) {
     if (!out128) return fail("adfb_get_unique_id: null buffer");
-    memset(out128, 0, 128);
+    std::string e;
+    if (!g.nccl.load(e)) return fail("adfb_get_unique_id: %s", e.c_str());
+    const int rc = g.nccl.GetUniqueId(out128);
+    if (rc != 0) return fail("ncclGetUniqueId: %s", g.nccl.GetErrorString(rc));
     return 0;
 }
 
@@ -182,7 +203,15 @@ int adfb_init(int device, const void* ncclUniqueId, int rank, int nranks) {
     if (!g.hRed) CK(cudaMallocHost((void**)&g.hRed, 64 * sizeof(double)));
     g.ready = true;
     g.err.clear();
-    if (nranks > 1) return fail("adfb_init: multi-rank communicator not built into this library version");
+    if (nranks > 1) {
+        if (!ncclUniqueId) return fail("adfb_init: nranks > 1 needs the 128-byte NCCL unique id of rank 0");
+        std::string e;
+        if (!g.nccl.load(e)) return fail("adfb_init: %s", e.c_str());
+        Id128 id;
+        memcpy(id.b, ncclUniqueId, 128);
+        const int rc = g.nccl.CommInitRank(&g.comm, nranks, id, rank);
+        if (rc != 0) return fail("ncclCommInitRank: %s", g.nccl.GetErrorString(rc));
+    }
     return 0;
 }
 
@@ -197,6 +226,9 @@ int adfb_finalize(void) {
     g.hRed = nullptr;
     if (g.dVec) cudaFree(g.dVec);
     g.dVec = nullptr; g.dVecN = 0;
+    for (void* q : g.pat.allocs) cudaFree(q);
+    g.pat = Context::Pattern();
+    if (g.comm) { g.nccl.CommDestroy(g.comm); g.comm = nullptr; }
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
     g.ready = false;
@@ -459,6 +491,160 @@ int adfb_get_states(double* states, long long n) { return vec_io(states, n, 0); 
 int adfb_set_states(const double* states, long long n) { return vec_io((double*)states, n, 1); }
 int adfb_get_res(double* res, long long n) { return vec_io(res, n, 2); }
 
+// ---------------------------------------------------------------------------
+// halo exchange
+}  // extern "C" (templates need C++ linkage)
+template <typename T>
+static int pat_upload(T** dst, const std::vector<T>& src) {
+    *dst = nullptr;
+    if (src.empty()) return 0;
+    void* q = nullptr;
+    if (cudaMalloc(&q, src.size() * sizeof(T)) != cudaSuccess) return fail("comm pattern: cudaMalloc failed");
+    g.pat.allocs.push_back(q);
+    if (cudaMemcpy(q, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return fail("comm pattern: copy failed");
+    *dst = (T*)q;
+    return 0;
+}
+
+static int list_to_offsets(const int* list, long long n, std::vector<int>& blk, std::vector<long long>& off, const char* what) {
+    blk.resize(n); off.resize(n);
+    for (long long e = 0; e < n; e++) {
+        const int bId = list[4 * e], i = list[4 * e + 1], j = list[4 * e + 2], k = list[4 * e + 3];
+        Block* b = get_block(bId);
+        if (!b) return fail("adfb_comm_set_pattern: %s entry %lld names unknown block %d", what, e, bId);
+        const Dims& d = b->d;
+        if (i < 0 || i > d.ib || j < 0 || j > d.jb || k < 0 || k > d.kb)
+            return fail("adfb_comm_set_pattern: %s entry %lld index (%d,%d,%d) outside block %d", what, e, i, j, k, bId);
+        blk[e] = bId;
+        off[e] = ADFB_IDX(i, j, k);
+    }
+    return 0;
+}
+
+extern "C" {
+int adfb_comm_set_pattern(int level, int nNbr, const int* nbrRank, const int* sendCount, const int* recvCount,
+                          const int* sendList, const int* recvList, int nInternal, const int* donorList,
+                          const int* haloList) {
+    NEED_INIT();
+    (void)level;
+    if (nNbr < 0 || nInternal < 0) return fail("adfb_comm_set_pattern: negative counts");
+    if (nNbr > 0 && g.nranks == 1) return fail("adfb_comm_set_pattern: neighbour ranks given but adfb_init was called with nranks = 1");
+    CK(cudaStreamSynchronize(g.stream));
+    for (void* q : g.pat.allocs) cudaFree(q);
+    g.pat = Context::Pattern();
+    Context::Pattern& P = g.pat;
+    std::vector<long long> cumS, cumR;
+    std::vector<int> locS, locR, cntS, cntR;
+    for (int m = 0; m < nNbr; m++) {
+        if (nbrRank[m] < 0 || nbrRank[m] >= g.nranks || nbrRank[m] == g.rank) return fail("adfb_comm_set_pattern: bad neighbour rank %d", nbrRank[m]);
+        P.nbrRank.push_back(nbrRank[m]); P.sendCount.push_back(sendCount[m]); P.recvCount.push_back(recvCount[m]);
+        for (int e = 0; e < sendCount[m]; e++) { cumS.push_back(P.nSend); locS.push_back(e); cntS.push_back(sendCount[m]); }
+        for (int e = 0; e < recvCount[m]; e++) { cumR.push_back(P.nRecv); locR.push_back(e); cntR.push_back(recvCount[m]); }
+        P.nSend += sendCount[m]; P.nRecv += recvCount[m];
+    }
+    P.nInt = nInternal;
+    std::vector<int> blk; std::vector<long long> off;
+    if (P.nSend) {
+        if (list_to_offsets(sendList, P.nSend, blk, off, "send")) return 1;
+        if (pat_upload(&P.sBlk, blk) || pat_upload(&P.sOff, off) || pat_upload(&P.sCum, cumS) || pat_upload(&P.sLocal, locS) || pat_upload(&P.sCount, cntS)) return 1;
+    }
+    if (P.nRecv) {
+        if (list_to_offsets(recvList, P.nRecv, blk, off, "recv")) return 1;
+        if (pat_upload(&P.rBlk, blk) || pat_upload(&P.rOff, off) || pat_upload(&P.rCum, cumR) || pat_upload(&P.rLocal, locR) || pat_upload(&P.rCount, cntR)) return 1;
+    }
+    if (P.nInt) {
+        if (list_to_offsets(donorList, P.nInt, blk, off, "donor")) return 1;
+        if (pat_upload(&P.iSrcBlk, blk) || pat_upload(&P.iSrcOff, off)) return 1;
+        if (list_to_offsets(haloList, P.nInt, blk, off, "halo")) return 1;
+        if (pat_upload(&P.iDstBlk, blk) || pat_upload(&P.iDstOff, off)) return 1;
+    }
+    void* q = nullptr;
+    if (P.nSend) { CK(cudaMalloc(&q, (size_t)P.nSend * ADFB_MAX_COMM_VARS * 8)); P.allocs.push_back(q); P.sendBuf = (double*)q; }
+    if (P.nRecv) { CK(cudaMalloc(&q, (size_t)P.nRecv * ADFB_MAX_COMM_VARS * 8)); P.allocs.push_back(q); P.recvBuf = (double*)q; }
+    P.tabBlocks = (int)g.blocks.size();
+    CK(cudaMalloc(&q, sizeof(CommVarTable) * (P.tabBlocks > 0 ? P.tabBlocks : 1)));
+    P.allocs.push_back(q); P.dTab = (CommVarTable*)q;
+    P.set = true;
+    return 0;
+}
+
+// whalo1to1 part of whalo2/whalo1 for the variable selection of setCommPointers
+// (src/utils/haloExchange.F90:356-470)
+static int halo_exchange_impl(int level, int start, int end, int commPressure, int commViscous, bool etotOwned) {
+    Context::Pattern& P = g.pat;
+    const bool viscous = g.prm.equations != ADFB_EULER, eddy = g.prm.equations == ADFB_RANS;
+    if (P.set && (P.nSend || P.nRecv || P.nInt)) {
+        if ((int)g.blocks.size() != P.tabBlocks) return fail("halo exchange: blocks changed after adfb_comm_set_pattern");
+        std::vector<CommVarTable> tab(P.tabBlocks);
+        int nVar = 0;
+        for (int bId = 0; bId < P.tabBlocks; bId++) {
+            Block& b = g.blocks[bId];
+            memset(&tab[bId], 0, sizeof(CommVarTable));
+            if (!b.alive) continue;
+            int v = 0;
+            for (int l = start; l <= end && l <= b.nw; l++) tab[bId].ptr[v++] = b.dev.w + (size_t)(l - 1) * b.d.N;
+            if (commPressure) tab[bId].ptr[v++] = b.dev.p;
+            if (viscous && commViscous) tab[bId].ptr[v++] = b.dev.rlv;
+            if (eddy && commViscous) tab[bId].ptr[v++] = b.dev.rev;
+            nVar = v;
+        }
+        if (nVar == 0) return 0;
+        if (nVar > ADFB_MAX_COMM_VARS) return fail("halo exchange: too many variables");
+        CK(cudaMemcpyAsync(P.dTab, tab.data(), sizeof(CommVarTable) * P.tabBlocks, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaStreamSynchronize(g.stream));  // tab is a stack vector
+        if (P.nSend) {
+            const long long n = P.nSend * nVar;
+            KT_BEGIN(K_HALO, g.stream);
+            k_halo_pack<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.sBlk, P.sOff, P.sCum, P.sLocal, P.sCount, P.dTab, nVar, P.nSend, P.sendBuf);
+            KT_END(K_HALO, g.stream);
+        }
+        if (!P.nbrRank.empty()) {
+            int rc = g.nccl.GroupStart();
+            long long so = 0, ro = 0;
+            for (size_t m = 0; m < P.nbrRank.size() && rc == 0; m++) {
+                if (P.sendCount[m]) rc = g.nccl.Send(P.sendBuf + so * nVar, (size_t)P.sendCount[m] * nVar, kNcclDouble, P.nbrRank[m], g.comm, g.stream);
+                if (rc == 0 && P.recvCount[m]) rc = g.nccl.Recv(P.recvBuf + ro * nVar, (size_t)P.recvCount[m] * nVar, kNcclDouble, P.nbrRank[m], g.comm, g.stream);
+                so += P.sendCount[m]; ro += P.recvCount[m];
+            }
+            const int rc2 = g.nccl.GroupEnd();
+            if (rc != 0 || rc2 != 0) return fail("NCCL halo exchange: %s", g.nccl.GetErrorString(rc ? rc : rc2));
+        }
+        if (P.nInt) {
+            const long long n = P.nInt * nVar;
+            KT_BEGIN(K_HALO, g.stream);
+            k_halo_internal<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.iSrcBlk, P.iSrcOff, P.iDstBlk, P.iDstOff, P.dTab, nVar, P.nInt);
+            KT_END(K_HALO, g.stream);
+        }
+        if (P.nRecv) {
+            const long long n = P.nRecv * nVar;
+            KT_BEGIN(K_HALO, g.stream);
+            k_halo_unpack<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.rBlk, P.rOff, P.rCum, P.rLocal, P.rCount, P.dTab, nVar, P.nRecv, P.recvBuf);
+            KT_END(K_HALO, g.stream);
+        }
+    }
+    // bothPAndE: computeEtotBlock(2, il, 2, jl, 2, kl) on every block (haloExchange.F90:174-197)
+    if (etotOwned && commPressure && start <= 5 && end >= 5) {
+        for (Block& b : g.blocks) {
+            if (!b.alive || b.level != level) continue;
+            dim3 tb(32, 4, 2);
+            dim3 gr((b.d.nx + 31) / 32, (b.d.ny + 3) / 4, (b.d.nz + 1) / 2);
+            KT_BEGIN(K_HALO, g.stream);
+            k_etot_owned<<<gr, tb, 0, g.stream>>>(b.d, b.dev);
+            KT_END(K_HALO, g.stream);
+        }
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int adfb_halo_exchange(int level, int start, int end, int commPressure, int commGamma, int commViscous) {
+    NEED_INIT();
+    (void)commGamma;  // gamma is constant (cpConstant): commVarGamma is always false, haloExchange.F90:146
+    if (!g.havePrm) return fail("adfb_halo_exchange: adfb_set_params has not been called");
+    if (start < 1 || end > 6 || (end >= start && false)) return fail("adfb_halo_exchange: bad variable range %d:%d", start, end);
+    return halo_exchange_impl(level, start, end, commPressure, commViscous, true);
+}
+
 int adfb_residual(int level, unsigned flags) {
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_residual: adfb_set_params has not been called");
@@ -470,13 +656,20 @@ int adfb_residual(int level, unsigned flags) {
         if (!b.haveMetrics) return fail("adfb_residual: geometry of a block was never set");
         if (!(flags & ADFB_RES_SKIP_PREAMBLE)) {
             // blocketteRes :213-226: p, rlv, rev on owned cells, then turbulence and flow BCs
-            if (launch_state_prep(b.d, b.dev, g.prm, false, g.stream)) return fail("state prep launch failed");
+            if (launch_state_prep(b.d, b.dev, g.prm, false, (flags & ADFB_RES_FLOW) != 0, g.stream)) return fail("state prep launch failed");
             if (g.prm.equations == ADFB_RANS && (flags & ADFB_RES_TURB))
                 if (launch_bc_turb(b.d, b.dev, b.subfaces, 1, g.stream)) return fail("turbulence BC launch failed");
             if (launch_bc_flow(b.d, b.dev, b.subfaces, 1, g.stream)) return fail("flow BC launch failed");
         }
     }
-    // whalo2(1, lStart, lEnd, T, T, T), blockette.F90:246 (single-rank: nothing to exchange)
+    if (!(flags & ADFB_RES_SKIP_PREAMBLE)) {
+        // whalo2(1, lStart, lEnd, T, T, T), blockette.F90:231-246; the owned-cell
+        // computeEtotBlock of whalo2 is fused into k_state_prep
+        const int nwLoc = g.prm.equations == ADFB_RANS ? 6 : 5;
+        const bool fr = flags & ADFB_RES_FLOW, tr = (flags & ADFB_RES_TURB) && nwLoc == 6;
+        const int lStart = fr ? 1 : 6, lEnd = tr ? 6 : 5;
+        if (halo_exchange_impl(level, lStart, lEnd, 1, 1, false)) return 1;
+    }
     for (Block& b : g.blocks) {
         if (!b.alive || b.level != level) continue;
         if (launch_residual_core(b.d, b.dev, g.prm, flags, 1.0, 0, 1, g.stream))
@@ -540,7 +733,8 @@ int adfb_rk_stage(int level, int rkStage) {
         if (launch_rk_update(b.d, b.dev, g.prm, rkStage, g.stream)) return fail("RK update launch failed");
         if (launch_bc_flow(b.d, b.dev, b.subfaces, 1, g.stream)) return fail("flow BC launch failed");
     }
-    // whalo2(level, 1, nwf, T, T, T) (single-rank: nothing to exchange)
+    // whalo2(level, 1, nwf, T, T, T): the trailing computeEtotBlock is idempotent here
+    if (halo_exchange_impl(level, 1, 5, 1, 1, false)) return 1;
     CK(cudaGetLastError());
     return 0;
 }
@@ -578,6 +772,15 @@ int adfb_norms(double out[2]) {
         CK(cudaStreamSynchronize(g.stream));
         out[0] += g.hRed[0];
         out[1] += g.hRed[1];
+    }
+    if (g.nranks > 1) {  // mpi_allreduce(monLoc, monGlob, ...), NKSolvers.F90:364
+        g.hRed[0] = out[0]; g.hRed[1] = out[1];
+        CK(cudaMemcpyAsync(g.dRed, g.hRed, 2 * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+        const int rc = g.nccl.AllReduce(g.dRed, g.dRed, 2, kNcclDouble, kNcclSum, g.comm, g.stream);
+        if (rc != 0) return fail("ncclAllReduce: %s", g.nccl.GetErrorString(rc));
+        CK(cudaMemcpyAsync(g.hRed, g.dRed, 2 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        out[0] = g.hRed[0]; out[1] = g.hRed[1];
     }
     return 0;
 }

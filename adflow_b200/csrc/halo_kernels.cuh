@@ -1,0 +1,98 @@
+// halo_kernels.cuh -- device side of whalo1 / whalo2
+// (src/utils/haloExchange.F90:5-199, whalo1to1RealGeneric :553-719)
+//
+// The reference packs `nVar` values per list entry into a host send buffer, posts
+// MPI_Isend/Irecv per neighbour rank, copies same-rank donor->halo pairs directly and
+// scatters the receive buffers.  Here the generic (block,i,j,k) index lists live on the
+// device as (block, box offset) pairs; one gather kernel packs all neighbours' messages
+// (SoA inside a message: value[var*count + entry], coalesced writes), NCCL moves them
+// GPU to GPU over NVLink (grouped ncclSend/ncclRecv on the compute stream), one scatter
+// kernel unpacks, one kernel does the same-rank copies.
+#pragma once
+#include "adfb_common.cuh"
+#include <dlfcn.h>
+
+#define ADFB_MAX_COMM_VARS 12
+
+struct CommVarTable {
+    // [block][var] -> device base pointer of that variable's box (nullptr beyond nVar)
+    double* ptr[ADFB_MAX_COMM_VARS];
+};
+
+namespace {
+
+// entries [0,n): gather var v of entry e into buf[msgBase[e's message] + v*msgCount + local e]
+// message layout: message m (entries cum_m .. cum_m+count_m-1) starts at nVar*cum_m doubles;
+// inside it value[v*count_m + local]
+__global__ void __launch_bounds__(256) k_halo_pack(const int* __restrict__ entBlk, const long long* __restrict__ entOff,
+                                                   const long long* __restrict__ entCum, const int* __restrict__ entLocal,
+                                                   const int* __restrict__ entCount,
+                                                   const CommVarTable* __restrict__ tab, int nVar, long long n,
+                                                   double* __restrict__ buf) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n * nVar) return;
+    const long long e = q % n;
+    const int v = (int)(q / n);
+    buf[(long long)nVar * entCum[e] + (long long)v * entCount[e] + entLocal[e]] = tab[entBlk[e]].ptr[v][entOff[e]];
+}
+__global__ void __launch_bounds__(256) k_halo_unpack(const int* __restrict__ entBlk, const long long* __restrict__ entOff,
+                                                     const long long* __restrict__ entCum, const int* __restrict__ entLocal,
+                                                     const int* __restrict__ entCount,
+                                                     const CommVarTable* __restrict__ tab, int nVar, long long n,
+                                                     const double* __restrict__ buf) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n * nVar) return;
+    const long long e = q % n;
+    const int v = (int)(q / n);
+    tab[entBlk[e]].ptr[v][entOff[e]] = buf[(long long)nVar * entCum[e] + (long long)v * entCount[e] + entLocal[e]];
+}
+// same-rank donor -> halo copies (haloExchange.F90:654-676)
+__global__ void __launch_bounds__(256) k_halo_internal(const int* __restrict__ srcBlk, const long long* __restrict__ srcOff,
+                                                       const int* __restrict__ dstBlk, const long long* __restrict__ dstOff,
+                                                       const CommVarTable* __restrict__ tab, int nVar, long long n) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n * nVar) return;
+    const long long e = q % n;
+    const int v = (int)(q / n);
+    tab[dstBlk[e]].ptr[v][dstOff[e]] = tab[srcBlk[e]].ptr[v][srcOff[e]];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// NCCL, resolved at run time (dlopen) so that the library also loads where no NCCL is
+// installed; only multi-rank runs need it.
+typedef struct ncclComm* ncclComm_t_;
+struct Id128 { char b[128]; };  // ncclUniqueId is passed BY VALUE to ncclCommInitRank
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(ncclComm_t_*, int, Id128, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t_) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (h) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define ADFB_SYM(field, name) *(void**)(&field) = dlsym(h, name); if (!field) { err = std::string("missing NCCL symbol ") + name; return false; }
+        ADFB_SYM(GetUniqueId, "ncclGetUniqueId");
+        ADFB_SYM(CommInitRank, "ncclCommInitRank");
+        ADFB_SYM(CommDestroy, "ncclCommDestroy");
+        ADFB_SYM(Send, "ncclSend");
+        ADFB_SYM(Recv, "ncclRecv");
+        ADFB_SYM(AllReduce, "ncclAllReduce");
+        ADFB_SYM(GroupStart, "ncclGroupStart");
+        ADFB_SYM(GroupEnd, "ncclGroupEnd");
+        ADFB_SYM(GetErrorString, "ncclGetErrorString");
+#undef ADFB_SYM
+        return true;
+    }
+};
+static const int kNcclDouble = 8;  // ncclFloat64 (nccl.h ncclDataType_t)
+static const int kNcclSum = 0;     // ncclSum

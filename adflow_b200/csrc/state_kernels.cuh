@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_metrics(Dims d, BlockDev b, double fact
 }
 
 // p on [pLo,pHi] (owned, or 0:ib with halos), rlv/rev on [vLo,vHi] (owned, or 1:ie with halos)
-__global__ void __launch_bounds__(256) k_state_prep(Dims d, BlockDev b, int includeHalos, int nw) {
+__global__ void __launch_bounds__(256) k_state_prep(Dims d, BlockDev b, int includeHalos, int nw, int etot) {
     const int lo = includeHalos ? 0 : 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x + lo;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + lo;
@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(256) k_state_prep(Dims d, BlockDev b, int incl
     double p = (c_prm.gammaInf - 1.0) * (b.w[4 * N + c] - 0.5 * rho * v2);
     p = dmax_(p, 1.e-4 * c_prm.pInfCorr);
     b.p[c] = p;
+    // whalo2's computeEtotBlock on owned cells (haloExchange.F90:174-197), fused here
+    if (etot) b.w[4 * N + c] = (1.0 / (c_prm.gammaInf - 1.0)) * p + 0.5 * rho * v2;
     if (c_prm.equations == ADFB_EULER) return;
     if (includeHalos && (i < 1 || i > d.ie || j < 1 || j > d.je || k < 1 || k > d.ke)) return;
     const double T = p / (c_prm.RGas * rho);
@@ -76,6 +78,17 @@ __global__ void __launch_bounds__(256) k_state_prep(Dims d, BlockDev b, int incl
     const double chi3 = chi * chi * chi;
     const double cv13 = c_prm.rsaCv1 * c_prm.rsaCv1 * c_prm.rsaCv1;
     b.rev[c] = chi3 / (chi3 + cv13) * rnuSA;
+}
+
+// computeEtotBlock(2,il,2,jl,2,kl) (src/utils/flowUtils.F90:551-672, cpConstant)
+__global__ void __launch_bounds__(256) k_etot_owned(Dims d, BlockDev b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
+    if (i > d.il || j > d.jl || k > d.kl) return;
+    const long long N = d.N, c = ADFB_IDX(i, j, k);
+    const double r = b.w[c], u = b.w[N + c], v = b.w[2 * N + c], w = b.w[3 * N + c];
+    b.w[4 * N + c] = (1.0 / (c_prm.gammaInf - 1.0)) * b.p[c] + 0.5 * r * (u * u + v * v + w * w);
 }
 
 // two-pass deterministic reduction: pass 1 -> nPart partial pairs, pass 2 -> final pair
@@ -154,13 +167,13 @@ static int launch_metrics(const Dims& d, const BlockDev& b, int rightHanded, cud
     return (int)cudaGetLastError();
 }
 
-static int launch_state_prep(const Dims& d, const BlockDev& b, const AdfbParams& prm, bool includeHalos, cudaStream_t stream) {
+static int launch_state_prep(const Dims& d, const BlockDev& b, const AdfbParams& prm, bool includeHalos, bool etot, cudaStream_t stream) {
     (void)prm;
     dim3 tb(32, 4, 2);
     const int ni = includeHalos ? d.NI : d.nx, nj = includeHalos ? d.NJ : d.ny, nk = includeHalos ? d.NK : d.nz;
     dim3 g((ni + tb.x - 1) / tb.x, (nj + tb.y - 1) / tb.y, (nk + tb.z - 1) / tb.z);
     KT_BEGIN(K_STATE, stream);
-    k_state_prep<<<g, tb, 0, stream>>>(d, b, includeHalos ? 1 : 0, prm.equations == ADFB_RANS ? 6 : 5);
+    k_state_prep<<<g, tb, 0, stream>>>(d, b, includeHalos ? 1 : 0, prm.equations == ADFB_RANS ? 6 : 5, etot ? 1 : 0);
     KT_END(K_STATE, stream);
     return (int)cudaGetLastError();
 }

@@ -75,6 +75,22 @@ class ADFLOW_B200:
         """blocketteRes (src/NKSolver/blockette.F90:70-297) on all local blocks."""
         check(self.L.adfb_residual(level, flags), "adfb_residual")
 
+    def setCommPattern(self, pat, level=1):
+        """Upload a 1-to-1 communication pattern (adflow_b200.halo.build_cartesian_pattern)."""
+        a = {k: np.ascontiguousarray(v, dtype=np.int32) for k, v in pat.items()}
+        self._keep.append(a)
+        p = lambda x: x.ctypes.data if x.size else None  # noqa: E731
+        check(self.L.adfb_comm_set_pattern(level, len(a["nbrRank"]), p(a["nbrRank"]), p(a["sendCount"]), p(a["recvCount"]),
+                                           p(a["sendList"]), p(a["recvList"]), len(a["donorList"]), p(a["donorList"]),
+                                           p(a["haloList"])), "adfb_comm_set_pattern")
+
+    def haloExchange(self, start=1, end=None, comm_pressure=True, comm_gamma=True, comm_viscous=True, level=1):
+        """whalo2(level, start, end, commPressure, commGamma, commViscous)."""
+        if end is None:
+            end = self.blocks[0].nw
+        check(self.L.adfb_halo_exchange(level, start, end, int(comm_pressure), int(comm_gamma), int(comm_viscous)),
+              "adfb_halo_exchange")
+
     def applyBCs(self, second_halo=True, with_turb=True, level=1):
         """applyAllBC (+ turbulence halo treatment) on all local blocks."""
         check(self.L.adfb_apply_bcs(level, int(second_halo), int(with_turb)), "adfb_apply_bcs")

@@ -189,6 +189,24 @@ int adfb_residual(int level, unsigned flags);
 int adfb_norms(double out[2]);
 int adfb_synchronize(void);
 
+/* ---- halo exchange (src/utils/haloExchange.F90) ---------------------------- */
+/* Device copy of the 1-to-1 communication pattern commPatternCell_2nd /
+   internalCell_2nd (src/modules/communication.F90:85-168, built by
+   src/preprocessing/pointMatchedCommPattern.F90).  Lists are (block, i, j, k) int32
+   quadruples with the reference's cell indices (0:ib ...), concatenated over the
+   neighbour ranks in the order of nbrRank; the send list of rank A towards B must
+   enumerate cells in the same order as B's receive list from A (as the reference's
+   sendList/recvList do).  donorList/haloList are the same-rank copies
+   (internal%donorBlock/donorIndices -> haloBlock/haloIndices). */
+int adfb_comm_set_pattern(int level, int nNbr, const int* nbrRank, const int* sendCount, const int* recvCount,
+                          const int* sendList, const int* recvList, int nInternal, const int* donorList,
+                          const int* haloList);
+/* whalo2(level, start, end, commPressure, commGamma, commViscous)
+   (src/utils/haloExchange.F90:109-199): w(start:end) [1-based], p, rlv, rev of all
+   listed halo cells; grouped ncclSend/ncclRecv over NVLink; then computeEtotBlock on
+   the owned cells when both p and rhoE were exchanged (:174-197). */
+int adfb_halo_exchange(int level, int start, int end, int commPressure, int commGamma, int commViscous);
+
 /* ---- smoothers ------------------------------------------------------------- */
 /* applyAllBC(secondHalo) (src/solver/BCRoutines.F90:57-222); withTurb != 0 first runs
    bcTurbTreatment + applyAllTurbBCThisBlock (src/turbulence/turbBCRoutines.F90:49,662) */
