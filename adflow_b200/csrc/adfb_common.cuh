@@ -45,6 +45,12 @@ struct BlockDev {
     double *grad;                       // 12 nodal gradient arrays
     double *wn, *pn;                    // RK stage-0 copies (5 / 1)
     double *scratch;                    // 10 work arrays (DADI, SA solve)
+    // geometry-derived static arrays (k_geom) and the face-flux store
+    double *ssum;                       // 9: s(c-sd)+s(c) per direction
+    double *sv;                         // 9: dual-face normal sums per direction
+    double *ovol;                       // 1: 1/(8-cell volume sum) at nodes
+    double *vn;                         // 12: cell-centre unit vector + 1/length per face direction
+    double *flux;                       // 30: face fluxes (15 used in merged mode)
 };
 
 // single translation unit (adflow_b200.cu includes every *_kernels.cuh)
@@ -58,9 +64,9 @@ __host__ __device__ static inline double dmin_(double a, double b) { return a < 
 // ---------------------------------------------------------------------------
 // launch accounting + optional per-kernel CUDA-event timing (bench.py roofline)
 #include <vector>
-enum KernelId { K_PREP = 0, K_NODAL, K_RESID, K_STATE, K_METRICS, K_NORMS, K_VEC, K_BC, K_RK, K_HALO, K_DADI, K_SA, K_MFFD, K_MISC, K_NUM };
-static const char* const kKernelNames[K_NUM] = {"k_prep", "k_nodal", "k_resid", "k_state_prep", "k_metrics", "k_norms", "k_vec",
-                                                "k_bc", "k_rk", "k_halo", "k_dadi", "k_sa_solve", "k_mffd", "k_misc"};
+enum KernelId { K_PREP = 0, K_NODAL, K_RESID, K_DIV, K_SA, K_STATE, K_METRICS, K_NORMS, K_VEC, K_BC, K_RK, K_HALO, K_DADI, K_SASOLVE, K_MFFD, K_MISC, K_NUM };
+static const char* const kKernelNames[K_NUM] = {"k_prep", "k_nodal", "k_faces", "k_div", "k_sa", "k_state_prep", "k_metrics", "k_norms",
+                                                "k_vec", "k_bc", "k_rk", "k_halo", "k_dadi", "k_sa_solve", "k_mffd", "k_misc"};
 struct KTimer {
     bool on = false;
     long long launches = 0;

@@ -302,6 +302,8 @@ int adfb_block_create(int blk, int level, int nx, int ny, int nz, int nw, int ri
     rc |= dalloc(b, &v.aa, N); rc |= dalloc(b, &v.radI, N); rc |= dalloc(b, &v.radJ, N); rc |= dalloc(b, &v.radK, N);
     rc |= dalloc(b, &v.dtl, N); rc |= dalloc(b, &v.grad, N * 12);
     rc |= dalloc(b, &v.wn, N * 5); rc |= dalloc(b, &v.pn, N); rc |= dalloc(b, &v.scratch, N * 10);
+    rc |= dalloc(b, &v.ssum, N * 9); rc |= dalloc(b, &v.sv, N * 9); rc |= dalloc(b, &v.ovol, N);
+    rc |= dalloc(b, &v.vn, N * 12); rc |= dalloc(b, &v.flux, N * 30);
     if (rc) {
         for (void* q : b.allocs) cudaFree(q);
         b.allocs.clear();
@@ -344,6 +346,7 @@ int adfb_block_set_geometry(int blk, const double* x, const double* si, const do
     if (d2Wall && put(*b, C0, v.d2Wall, d2Wall, 1, 8)) return 1;
     if (put(*b, PI_, v.porI, porI, 1, 1) || put(*b, PJ_, v.porJ, porJ, 1, 1) || put(*b, PK_, v.porK, porK, 1, 1)) return 1;
     if (put(*b, C2, v.iblank, iblank, 1, 4)) return 1;
+    if (launch_geom(b->d, v, g.stream)) return fail("geometry kernel launch failed");
     CK(cudaStreamSynchronize(g.stream));
     b->haveMetrics = true;
     return 0;

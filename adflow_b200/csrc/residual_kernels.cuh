@@ -1,20 +1,23 @@
-// residual_kernels.cuh -- fused residual kernels (gather form) for sm_100a
+// residual_kernels.cuh -- residual kernels (face-flux form) for sm_100a
 //
 // Replaces the per-block residual core of the reference
-// (blocketteResCore, src/NKSolver/blockette.F90:299-753 and its operator twins
-// in src/solver/fluxes.F90, src/turbulence/sa.F90, src/utils/flowUtils.F90).
+// (blocketteResCore, src/NKSolver/blockette.F90:299-753 and its operator twins in
+// src/solver/fluxes.F90, src/turbulence/sa.F90, src/utils/flowUtils.F90).
 //
-// The reference scatters every face flux to its two cells
-// (`dw(i+1) -= fs; dw(i) += fs`); here every thread owns one cell and GATHERS
-// its six faces, adding them in exactly the order in which the reference's
-// i/j/k sweeps would have touched that cell, so no atomics and no halo writes
-// are needed and results agree with the scatter form to round-off.
+// The reference scatters every face flux to its two cells (`dw(i+1) -= fs; dw(i) += fs`).
+// Here each face flux is computed exactly ONCE by the thread that owns the cell on the
+// low side of the face (k_faces: the i+, j+ and k+ faces of cell c), stored in a face
+// array, and k_div gathers the six faces of every owned cell in the order in which the
+// reference's i/j/k sweeps touch that cell.  No atomics, no halo writes, results
+// independent of launch geometry.
 //
 // Launch plan per residual evaluation:
-//   k_prep   : box cells     -> ss (entropy), aa, radI/J/K, [dtl]
-//   k_nodal  : cells 1:ie    -> dss(3) and the 12 nodal gradients at nodes 1:il
-//   k_resid  : owned cells   -> SA source/advection/diffusion, central + JST
-//                               + viscous fluxes, epilogue -> dw(1:nw)
+//   k_prep   : box cells  -> ss (entropy), aa, radI/J/K, [dtl]
+//   k_nodal  : cells 1:ie -> dss(3); nodes 1:il -> 12 nodal gradients
+//   k_faces  : cells 1:il x 1:jl x 1:kl -> central - JST - viscous flux of the 3 plus faces
+//   k_div    : owned cells -> SA source/advection/diffusion row + flux divergence -> dw
+//
+// All index arithmetic is 32 bit (a block box times 30 components stays far below 2^31).
 #pragma once
 #include "adfb_common.cuh"
 #include <math.h>
@@ -28,23 +31,85 @@
 
 namespace {
 
-__device__ __forceinline__ bool cell_index(const Dims& d, int& i, int& j, int& k, int i0, int j0, int k0) {
-    i = blockIdx.x * blockDim.x + threadIdx.x + i0;
-    j = blockIdx.y * blockDim.y + threadIdx.y + j0;
-    k = blockIdx.z * blockDim.z + threadIdx.z + k0;
-    return true;
+// ---------------------------------------------------------------------------
+// k_geom: geometry-derived static arrays, once per mesh (adfb_block_set_geometry).
+//   ssum[dir] = s(c-sd) + s(c)          (timeStep sx/sy/sz, blockette.F90:1976-2006; saAdvection/saViscous xa)
+//   sv[dir]   = 8-face normal sum of the dual face at cell layer c (allNodalGradients, :5247-5258)
+//   ovol      = 1 / (8-cell volume sum) at node c (:5489-5492)
+//   vn[dir]   = unit vector + inverse length between cell centres across face c (viscousFlux, :5638-5657)
+__global__ void __launch_bounds__(256) k_geom(Dims d, BlockDev b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i < 1 || i > d.ie || j < 1 || j > d.je || k < 1 || k > d.ke) return;
+    const int N = (int)d.N, sJ = (int)d.sJ, sK = (int)d.sK;
+    const int c = i + sJ * j + sK * k;
+    const double *si = b.si, *sj = b.sj, *sk = b.sk;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        b.ssum[m * N + c] = si[m * N + c - 1] + si[m * N + c];
+        b.ssum[(3 + m) * N + c] = sj[m * N + c - sJ] + sj[m * N + c];
+        b.ssum[(6 + m) * N + c] = sk[m * N + c - sK] + sk[m * N + c];
+    }
+    // dual-face sums; reference order: layer c-sd: (0, t1, t2, t1+t2), then layer c
+    if (i <= d.il && j <= d.jl) {  // K sweep: i 1:il, j 1:jl, k 1:ke ; t1 = I, t2 = J
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const double* s = sk + m * N;
+            b.sv[(6 + m) * N + c] = s[c - sK] + s[c - sK + 1] + s[c - sK + sJ] + s[c - sK + 1 + sJ] + s[c] + s[c + 1] + s[c + sJ] + s[c + 1 + sJ];
+        }
+    }
+    if (i <= d.il && k <= d.kl) {  // J sweep: t1 = I, t2 = K
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const double* s = sj + m * N;
+            b.sv[(3 + m) * N + c] = s[c - sJ] + s[c - sJ + 1] + s[c - sJ + sK] + s[c - sJ + 1 + sK] + s[c] + s[c + 1] + s[c + sK] + s[c + 1 + sK];
+        }
+    }
+    if (j <= d.jl && k <= d.kl) {  // I sweep: t1 = J, t2 = K
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const double* s = si + m * N;
+            b.sv[m * N + c] = s[c - 1] + s[c - 1 + sJ] + s[c - 1 + sK] + s[c - 1 + sJ + sK] + s[c] + s[c + sJ] + s[c + sK] + s[c + sJ + sK];
+        }
+    }
+    if (i <= d.il && j <= d.jl && k <= d.kl) {
+        const double* vol = b.vol;
+        b.ovol[c] = 1.0 / (vol[c] + vol[c + sK] + vol[c + 1] + vol[c + 1 + sK] + vol[c + sJ] + vol[c + sJ + sK] + vol[c + 1 + sJ] + vol[c + 1 + sJ + sK]);
+        // face-normal unit vectors for the viscous gradient correction; node n = c
+        const double* x = b.x;
+        const int sd[3] = {1, sJ, sK}, t1[3] = {sJ, 1, 1}, t2[3] = {sK, sK, sJ};
+#pragma unroll
+        for (int dir = 0; dir < 3; dir++) {
+            // faces exist for the two transverse indices >= 2
+            const bool ok = (dir == 0) ? (j >= 2 && k >= 2) : (dir == 1) ? (i >= 2 && k >= 2) : (i >= 2 && j >= 2);
+            if (!ok) continue;
+            const int n = c, n1 = c - t1[dir] - t2[dir], n2 = c - t2[dir], n3 = c - t1[dir], s = sd[dir];
+            double v[3];
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                const double* xm = x + m * N;
+                v[m] = 0.125 * (xm[n1 + s] - xm[n1 - s] + xm[n3 + s] - xm[n3 - s] + xm[n2 + s] - xm[n2 - s] + xm[n + s] - xm[n - s]);
+            }
+            const double snrm = 1.0 / sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            b.vn[(4 * dir + 0) * N + c] = snrm * v[0];
+            b.vn[(4 * dir + 1) * N + c] = snrm * v[1];
+            b.vn[(4 * dir + 2) * N + c] = snrm * v[2];
+            b.vn[(4 * dir + 3) * N + c] = snrm;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
-// k_prep: entropy (inviscidDissFluxScalar, blockette.F90:3055-3089), speed of
-// sound squared (:5168-5203), spectral radii and local time step (timeStep,
-// :1899-2148).  One pass over the box; radii/aa only on cells 1:ie, dtl on owned.
+// k_prep: entropy (inviscidDissFluxScalar, blockette.F90:3055-3089), speed of sound squared
+// (:5168-5203), spectral radii and local time step (timeStep, :1899-2148).
 __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, int doRad) {
-    int i, j, k;
-    cell_index(d, i, j, k, 0, 0, 0);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z;
     if (i > d.ib || j > d.jb || k > d.kb) return;
-    const long long c = ADFB_IDX(i, j, k);
-    const long long N = d.N;
+    const int N = (int)d.N, sJ = (int)d.sJ, sK = (int)d.sK;
+    const int c = i + sJ * j + sK * k;
     const double gam = c_prm.gammaInf;
     const double rho = b.w[c], p = b.p[c];
     b.ss[c] = (c_prm.equations == ADFB_EULER) ? p : p / pow(rho, gam);
@@ -58,18 +123,16 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
     const double ux = b.w[N + c], uy = b.w[2 * N + c], uz = b.w[3 * N + c];
     double cc2 = gam * p / rho;
     cc2 = dmax_(cc2, clim2);
-    double sx, sy, sz, q;
-    sx = b.si[c - 1] + b.si[c]; sy = b.si[N + c - 1] + b.si[N + c]; sz = b.si[2 * N + c - 1] + b.si[2 * N + c];
-    const double sxi = sx, syi = sy, szi = sz;
-    q = ux * sx + uy * sy + uz * sz;
-    double ri = 0.5 * (fabs(q) + asf * sqrt(cc2 * (sx * sx + sy * sy + sz * sz)));
-    sx = b.sj[c - d.sJ] + b.sj[c]; sy = b.sj[N + c - d.sJ] + b.sj[N + c]; sz = b.sj[2 * N + c - d.sJ] + b.sj[2 * N + c];
-    const double sxj = sx, syj = sy, szj = sz;
-    q = ux * sx + uy * sy + uz * sz;
-    double rj = 0.5 * (fabs(q) + asf * sqrt(cc2 * (sx * sx + sy * sy + sz * sz)));
-    sx = b.sk[c - d.sK] + b.sk[c]; sy = b.sk[N + c - d.sK] + b.sk[N + c]; sz = b.sk[2 * N + c - d.sK] + b.sk[2 * N + c];
-    q = ux * sx + uy * sy + uz * sz;
-    double rk = 0.5 * (fabs(q) + asf * sqrt(cc2 * (sx * sx + sy * sy + sz * sz)));
+    const double* ss = b.ssum;
+    const double sxi = ss[c], syi = ss[N + c], szi = ss[2 * N + c];
+    const double sxj = ss[3 * N + c], syj = ss[4 * N + c], szj = ss[5 * N + c];
+    const double sxk = ss[6 * N + c], syk = ss[7 * N + c], szk = ss[8 * N + c];
+    const double s2i = sxi * sxi + syi * syi + szi * szi;
+    const double s2j = sxj * sxj + syj * syj + szj * szj;
+    const double s2k = sxk * sxk + syk * syk + szk * szk;
+    double ri = 0.5 * (fabs(ux * sxi + uy * syi + uz * szi) + asf * sqrt(cc2 * s2i));
+    double rj = 0.5 * (fabs(ux * sxj + uy * syj + uz * szj) + asf * sqrt(cc2 * s2j));
+    double rk = 0.5 * (fabs(ux * sxk + uy * syk + uz * szk) + asf * sqrt(cc2 * s2k));
     double dt = ri + rj + rk;
     ri = dmax_(ri, 1.e-25); rj = dmax_(rj, 1.e-25); rk = dmax_(rk, 1.e-25);
     const double rij = pow(ri / rj, adis), rjk = pow(rj / rk, adis), rki = pow(rk / ri, adis);
@@ -83,212 +146,242 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
         double rmu = b.rlv[c];
         rmu = rmu + b.rev[c];
         rmu = 0.5 * rmu / (rho * b.vol[c]);
-        dt = dt + rmu * (sxi * sxi + syi * syi + szi * szi);
-        dt = dt + rmu * (sxj * sxj + syj * syj + szj * szj);
-        dt = dt + rmu * (sx * sx + sy * sy + sz * sz);
+        dt = dt + rmu * s2i;
+        dt = dt + rmu * s2j;
+        dt = dt + rmu * s2k;
     }
     const double plim = 0.001 * c_prm.pInfCorr;
     const double* pp = b.p;
     const double dpi = fabs(pp[c + 1] - 2.0 * p + pp[c - 1]) / (pp[c + 1] + 2.0 * p + pp[c - 1] + plim);
-    const double dpj = fabs(pp[c + d.sJ] - 2.0 * p + pp[c - d.sJ]) / (pp[c + d.sJ] + 2.0 * p + pp[c - d.sJ] + plim);
-    const double dpk = fabs(pp[c + d.sK] - 2.0 * p + pp[c - d.sK]) / (pp[c + d.sK] + 2.0 * p + pp[c - d.sK] + plim);
+    const double dpj = fabs(pp[c + sJ] - 2.0 * p + pp[c - sJ]) / (pp[c + sJ] + 2.0 * p + pp[c - sJ] + plim);
+    const double dpk = fabs(pp[c + sK] - 2.0 * p + pp[c - sK]) / (pp[c + sK] + 2.0 * p + pp[c - sK] + plim);
     const double rfl = 1.0 / (1.0 + 2.0 * (dpi + dpj + dpk));
     b.dtl[c] = rfl / dt;
 }
 
 // ---------------------------------------------------------------------------
-// nodal gradient contribution of one sweep direction (allNodalGradients,
-// blockette.F90:5235-5479): dual-face "upper" (cell layer c+sd, added) and
-// "lower" (cell layer c, subtracted); the reference's scatter order for a node
-// is: subtract lower first, then add upper.
-__device__ __forceinline__ void nodal_face(const BlockDev& b, long long N, long long c, long long sd, long long t1,
-                                           long long t2, const double* __restrict__ s, double sv[3], double& ubar,
-                                           double& vbar, double& wbar, double& a2) {
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-        const double* sm = s + m * N;
-        sv[m] = sm[c - sd] + sm[c - sd + t1] + sm[c - sd + t2] + sm[c - sd + t1 + t2] + sm[c] + sm[c + t1] +
-                sm[c + t2] + sm[c + t1 + t2];
-    }
-    const double* w = b.w;
-    ubar = 0.25 * (w[N + c] + w[N + c + t1] + w[N + c + t2] + w[N + c + t1 + t2]);
-    vbar = 0.25 * (w[2 * N + c] + w[2 * N + c + t1] + w[2 * N + c + t2] + w[2 * N + c + t1 + t2]);
-    wbar = 0.25 * (w[3 * N + c] + w[3 * N + c + t1] + w[3 * N + c + t2] + w[3 * N + c + t1 + t2]);
-    a2 = 0.25 * (b.aa[c] + b.aa[c + t1] + b.aa[c + t2] + b.aa[c + t1 + t2]);
-}
-
-__device__ __forceinline__ void nodal_dir(const BlockDev& b, long long N, long long c, long long sd, long long t1,
-                                          long long t2, const double* __restrict__ s, double g[12]) {
-    double sv[3], ub, vb, wb, a2;
-    nodal_face(b, N, c, sd, t1, t2, s, sv, ub, vb, wb, a2);
-#pragma unroll
-    for (int m = 0; m < 3; m++) { g[m] -= ub * sv[m]; g[3 + m] -= vb * sv[m]; g[6 + m] -= wb * sv[m]; g[9 + m] += a2 * sv[m]; }
-    nodal_face(b, N, c + sd, sd, t1, t2, s, sv, ub, vb, wb, a2);
-#pragma unroll
-    for (int m = 0; m < 3; m++) { g[m] += ub * sv[m]; g[3 + m] += vb * sv[m]; g[6 + m] += wb * sv[m]; g[9 + m] -= a2 * sv[m]; }
-}
-
-// k_nodal: shock sensor dss (blockette.F90:3091-3105) on cells 1:ie and the
-// nodal gradients (:5205-5515) on nodes 1:il.
+// k_nodal: shock sensor dss (blockette.F90:3091-3105) on cells 1:ie and the nodal gradients
+// (allNodalGradients, :5205-5515) on nodes 1:il in gather form.  For node n (= cell index c)
+// the reference's three scatter sweeps add, in this order:  -K(layer k) +K(layer k+1)
+// -J(layer j) +J(layer j+1) -I(layer i) +I(layer i+1), then scale by 1/(8 vol).
 __global__ void __launch_bounds__(256) k_nodal(Dims d, BlockDev b, int doGrad) {
-    int i, j, k;
-    cell_index(d, i, j, k, 1, 1, 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 1;
     if (i > d.ie || j > d.je || k > d.ke) return;
-    const long long c = ADFB_IDX(i, j, k);
-    const long long N = d.N;
+    const int N = (int)d.N, sJ = (int)d.sJ, sK = (int)d.sK;
+    const int c = i + sJ * j + sK * k;
     {
         const double sslim = (c_prm.equations == ADFB_EULER) ? 0.001 * c_prm.pInfCorr
                                                             : 0.001 * c_prm.pInfCorr / pow(c_prm.rhoInf, c_prm.gammaInf);
         const double* ss = b.ss;
         const double s0 = ss[c];
         b.dss[c] = fabs((ss[c + 1] - 2.0 * s0 + ss[c - 1]) / (ss[c + 1] + 2.0 * s0 + ss[c - 1] + sslim));
-        b.dss[N + c] = fabs((ss[c + d.sJ] - 2.0 * s0 + ss[c - d.sJ]) / (ss[c + d.sJ] + 2.0 * s0 + ss[c - d.sJ] + sslim));
-        b.dss[2 * N + c] = fabs((ss[c + d.sK] - 2.0 * s0 + ss[c - d.sK]) / (ss[c + d.sK] + 2.0 * s0 + ss[c - d.sK] + sslim));
+        b.dss[N + c] = fabs((ss[c + sJ] - 2.0 * s0 + ss[c - sJ]) / (ss[c + sJ] + 2.0 * s0 + ss[c - sJ] + sslim));
+        b.dss[2 * N + c] = fabs((ss[c + sK] - 2.0 * s0 + ss[c - sK]) / (ss[c + sK] + 2.0 * s0 + ss[c - sK] + sslim));
     }
     if (!doGrad || i > d.il || j > d.jl || k > d.kl) return;
+    // the 8 cells around the node: bit0 = +i, bit1 = +j, bit2 = +k
+    double q[8][4];
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        const int cc = c + (m & 1) + ((m >> 1) & 1) * sJ + ((m >> 2) & 1) * sK;
+        q[m][0] = b.w[N + cc]; q[m][1] = b.w[2 * N + cc]; q[m][2] = b.w[3 * N + cc]; q[m][3] = b.aa[cc];
+    }
     double g[12];
 #pragma unroll
     for (int m = 0; m < 12; m++) g[m] = 0.0;
-    nodal_dir(b, N, c, d.sK, 1, d.sJ, b.sk, g);
-    nodal_dir(b, N, c, d.sJ, 1, d.sK, b.sj, g);
-    nodal_dir(b, N, c, 1, d.sJ, d.sK, b.si, g);
-    const double* vol = b.vol;
-    const double oVol = 1.0 / (vol[c] + vol[c + d.sK] + vol[c + 1] + vol[c + 1 + d.sK] + vol[c + d.sJ] +
-                               vol[c + d.sJ + d.sK] + vol[c + 1 + d.sJ] + vol[c + 1 + d.sJ + d.sK]);
+    // dir K: layers c (cells 0,1,2,3) and c+sK (4,5,6,7); J: (0,1,4,5) and (2,3,6,7); I: (0,2,4,6) and (1,3,5,7)
+    const int lo[3][4] = {{0, 2, 4, 6}, {0, 1, 4, 5}, {0, 1, 2, 3}};
+    const int hi[3][4] = {{1, 3, 5, 7}, {2, 3, 6, 7}, {4, 5, 6, 7}};
+    const int sd[3] = {1, sJ, sK};
+#pragma unroll
+    for (int dd = 2; dd >= 0; dd--) {  // K, J, I
+        const double* sv = b.sv + (3 * dd) * N;
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const int* sel = side ? hi[dd] : lo[dd];
+            const int cs = side ? c + sd[dd] : c;
+            const double s1 = sv[cs], s2 = sv[N + cs], s3 = sv[2 * N + cs];
+            double bar[4];
+#pragma unroll
+            for (int v = 0; v < 4; v++) bar[v] = 0.25 * (q[sel[0]][v] + q[sel[1]][v] + q[sel[2]][v] + q[sel[3]][v]);
+            const double sg = side ? 1.0 : -1.0;
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+                g[3 * v + 0] += sg * (bar[v] * s1);
+                g[3 * v + 1] += sg * (bar[v] * s2);
+                g[3 * v + 2] += sg * (bar[v] * s3);
+            }
+            g[9] -= sg * (bar[3] * s1);
+            g[10] -= sg * (bar[3] * s2);
+            g[11] -= sg * (bar[3] * s3);
+        }
+    }
+    const double oVol = b.ovol[c];
 #pragma unroll
     for (int m = 0; m < 12; m++) b.grad[m * N + c] = g[m] * oVol;
 }
 
 // ---------------------------------------------------------------------------
-// face fluxes.  `c` is the cell on the low side of the face, cp = c + sd.
+// one face of direction sd: central (inviscidCentralFlux, blockette.F90:2150-2428), scalar
+// JST (inviscidDissFluxScalar, :3133-3338) and viscous (viscousFlux, :5576-6400) fluxes.
+// c is the low-side cell, cp = c + sd.  Outputs fc[5] (central: dw(cp) -= fc, dw(c) += fc) and
+// fd[5] = JST + viscous flux (the part the reference accumulates in fw with the same sign
+// pattern for both: fw(cp) += f, fw(c) -= f).
+struct CellState { double r, u, v, w, e, p; };
 
-// inviscidCentralFlux, blockette.F90:2150-2428
-__device__ __forceinline__ void central_face(const BlockDev& b, long long N, long long c, long long cp,
-                                             const double* __restrict__ s, int8_t por, double f[5]) {
-    const double* w = b.w;
-    const double s1 = s[c], s2 = s[N + c], s3 = s[2 * N + c];
-    const double rp = w[cp], up = w[N + cp], vp = w[2 * N + cp], wp = w[3 * N + cp], ep = w[4 * N + cp];
-    const double rm = w[c], um = w[N + c], vm = w[2 * N + c], wm = w[3 * N + c], em = w[4 * N + c];
-    const double pp = b.p[cp], pm = b.p[c];
-    double vnp = up * s1 + vp * s2 + wp * s3;
-    double vnm = um * s1 + vm * s2 + wm * s3;
-    double porVel = 1.0, porFlux = 0.5;
-    if (por == ADFB_NOFLUX) porFlux = 0.0;
-    if (por == ADFB_BOUNDFLUX) { porVel = 0.0; vnp = 0.0; vnm = 0.0; }
-    porVel = porVel * porFlux;
-    const double qsp = vnp * porVel, qsm = vnm * porVel;
-    const double rqsp = qsp * rp, rqsm = qsm * rm;
-    const double pa = porFlux * (pp + pm);
-    f[0] = rqsp + rqsm;
-    f[1] = rqsp * up + rqsm * um + pa * s1;
-    f[2] = rqsp * vp + rqsm * vm + pa * s2;
-    f[3] = rqsp * wp + rqsm * wm + pa * s3;
-    f[4] = qsp * ep + qsm * em + porFlux * (vnp * pp + vnm * pm);
+__device__ __forceinline__ CellState load_cell(const BlockDev& b, int N, int c) {
+    CellState s;
+    s.r = b.w[c]; s.u = b.w[N + c]; s.v = b.w[2 * N + c]; s.w = b.w[3 * N + c]; s.e = b.w[4 * N + c]; s.p = b.p[c];
+    return s;
 }
 
-// inviscidDissFluxScalar, blockette.F90:3133-3338
-__device__ __forceinline__ void jst_face(const BlockDev& b, long long N, long long c, long long sd,
-                                         const double* __restrict__ rad, const double* __restrict__ dss, int8_t por,
-                                         double fis2, double fis4, double f[5]) {
-    const double* w = b.w;
-    const double* p = b.p;
-    const long long cp = c + sd, cpp = c + 2 * sd, cm = c - sd;
-    const double ppor = (por == ADFB_NORMALFLUX) ? 0.5 : 0.0;
-    const double rrad = ppor * (rad[c] + rad[cp]);
-    const double dis2 = fis2 * rrad * dmin_(0.25, dmax_(dss[c], dss[cp]));
-    const double dis4 = dmax_(fis4 * rrad - dis2, 0.0);
-    const double r0 = w[c], r1 = w[cp], r2 = w[cpp], rm = w[cm];
-    double ddw = r1 - r0;
-    f[0] = dis2 * ddw - dis4 * (r2 - rm - 3.0 * ddw);
-#pragma unroll
-    for (int l = 1; l <= 3; l++) {
-        ddw = w[l * N + cp] * r1 - w[l * N + c] * r0;
-        f[l] = dis2 * ddw - dis4 * (w[l * N + cpp] * r2 - w[l * N + cm] * rm - 3.0 * ddw);
+template <bool VISCOUS>
+__device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int sd, int t1, int t2, int dir,
+                                          const double* __restrict__ s, int8_t por, const double* __restrict__ rad,
+                                          const double* __restrict__ dss, const CellState& m, double rFil, int doDiss,
+                                          int doVisc, double fc[5], double fd[5]) {
+    const int cp = c + sd;
+    const CellState q = load_cell(b, N, cp);
+    const double s1 = s[c], s2 = s[N + c], s3 = s[2 * N + c];
+    {   // central
+        double vnp = q.u * s1 + q.v * s2 + q.w * s3;
+        double vnm = m.u * s1 + m.v * s2 + m.w * s3;
+        double porVel = 1.0, porFlux = 0.5;
+        if (por == ADFB_NOFLUX) porFlux = 0.0;
+        if (por == ADFB_BOUNDFLUX) { porVel = 0.0; vnp = 0.0; vnm = 0.0; }
+        porVel = porVel * porFlux;
+        const double qsp = vnp * porVel, qsm = vnm * porVel;
+        const double rqsp = qsp * q.r, rqsm = qsm * m.r;
+        const double pa = porFlux * (q.p + m.p);
+        fc[0] = rqsp + rqsm;
+        fc[1] = rqsp * q.u + rqsm * m.u + pa * s1;
+        fc[2] = rqsp * q.v + rqsm * m.v + pa * s2;
+        fc[3] = rqsp * q.w + rqsm * m.w + pa * s3;
+        fc[4] = qsp * q.e + qsm * m.e + porFlux * (vnp * q.p + vnm * m.p);
     }
-    ddw = (w[4 * N + cp] + p[cp]) - (w[4 * N + c] + p[c]);
-    f[4] = dis2 * ddw - dis4 * ((w[4 * N + cpp] + p[cpp]) - (w[4 * N + cm] + p[cm]) - 3.0 * ddw);
+#pragma unroll
+    for (int l = 0; l < 5; l++) fd[l] = 0.0;
+    if (doDiss && c_prm.spaceDiscr == ADFB_DISS_SCALAR) {  // scalar JST
+        const CellState mm = load_cell(b, N, c - sd), qq = load_cell(b, N, cp + sd);
+        const double fis2 = rFil * c_prm.vis2, fis4 = rFil * c_prm.vis4;
+        const double ppor = (por == ADFB_NORMALFLUX) ? 0.5 : 0.0;
+        const double rrad = ppor * (rad[c] + rad[cp]);
+        const double dis2 = fis2 * rrad * dmin_(0.25, dmax_(dss[c], dss[cp]));
+        const double dis4 = dmax_(fis4 * rrad - dis2, 0.0);
+        double ddw = q.r - m.r;
+        fd[0] = dis2 * ddw - dis4 * (qq.r - mm.r - 3.0 * ddw);
+        ddw = q.u * q.r - m.u * m.r;
+        fd[1] = dis2 * ddw - dis4 * (qq.u * qq.r - mm.u * mm.r - 3.0 * ddw);
+        ddw = q.v * q.r - m.v * m.r;
+        fd[2] = dis2 * ddw - dis4 * (qq.v * qq.r - mm.v * mm.r - 3.0 * ddw);
+        ddw = q.w * q.r - m.w * m.r;
+        fd[3] = dis2 * ddw - dis4 * (qq.w * qq.r - mm.w * mm.r - 3.0 * ddw);
+        ddw = (q.e + q.p) - (m.e + m.p);
+        fd[4] = dis2 * ddw - dis4 * ((qq.e + qq.p) - (mm.e + mm.p) - 3.0 * ddw);
+    }
+    if (VISCOUS && doVisc) {
+        double porv = 0.5 * rFil;
+        if (por == ADFB_NOFLUX) porv = 0.0;
+        const double mul = porv * (b.rlv[c] + b.rlv[cp]);
+        const double mue = porv * (b.rev[c] + b.rev[cp]);
+        const double mut = mul + mue;
+        const double gm1 = c_prm.gammaInf - 1.0;
+        const double heatCoef = mul * (1.0 / (c_prm.prandtl * gm1)) + mue * (1.0 / (c_prm.prandtlTurb * gm1));
+        const int n = c, n1 = c - t1 - t2, n2 = c - t2, n3 = c - t1;
+        double g[12];
+#pragma unroll
+        for (int l = 0; l < 12; l++) {
+            const double* gm = b.grad + l * N;
+            g[l] = 0.25 * (gm[n1] + gm[n2] + gm[n3] + gm[n]);
+        }
+        const double* vn = b.vn + (4 * dir) * N;
+        const double ssx = vn[c], ssy = vn[N + c], ssz = vn[2 * N + c], snrm = vn[3 * N + c];
+        double corr;
+        corr = g[0] * ssx + g[1] * ssy + g[2] * ssz - (q.u - m.u) * snrm;
+        const double u_x = g[0] - corr * ssx, u_y = g[1] - corr * ssy, u_z = g[2] - corr * ssz;
+        corr = g[3] * ssx + g[4] * ssy + g[5] * ssz - (q.v - m.v) * snrm;
+        const double v_x = g[3] - corr * ssx, v_y = g[4] - corr * ssy, v_z = g[5] - corr * ssz;
+        corr = g[6] * ssx + g[7] * ssy + g[8] * ssz - (q.w - m.w) * snrm;
+        const double w_x = g[6] - corr * ssx, w_y = g[7] - corr * ssy, w_z = g[8] - corr * ssz;
+        corr = g[9] * ssx + g[10] * ssy + g[11] * ssz + (b.aa[cp] - b.aa[c]) * snrm;
+        double q_x = g[9] - corr * ssx, q_y = g[10] - corr * ssy, q_z = g[11] - corr * ssz;
+        const double fracDiv = (2.0 * (1.0 / 3.0)) * (u_x + v_y + w_z);
+        const double tauxxS = 2.0 * u_x - fracDiv, tauyyS = 2.0 * v_y - fracDiv, tauzzS = 2.0 * w_z - fracDiv;
+        const double tauxyS = u_y + v_x, tauxzS = u_z + w_x, tauyzS = v_z + w_y;
+        q_x = heatCoef * q_x; q_y = heatCoef * q_y; q_z = heatCoef * q_z;
+        double tauxx = mut * tauxxS, tauyy = mut * tauyyS, tauzz = mut * tauzzS;
+        double tauxy = mut * tauxyS, tauxz = mut * tauxzS, tauyz = mut * tauyzS;
+        if (c_prm.useQCR) {
+            double den = sqrt(u_x * u_x + u_y * u_y + u_z * u_z + v_x * v_x + v_y * v_y + v_z * v_z + w_x * w_x + w_y * w_y + w_z * w_z);
+            den = dmax_(den, 1.e-10);
+            const double fact = mue * 0.3 / den;
+            const double Wxy = u_y - v_x, Wxz = u_z - w_x, Wyz = v_z - w_y;
+            const double Wyx = -Wxy, Wzx = -Wxz, Wzy = -Wyz;
+            tauxx -= fact * (Wxy * tauxyS + Wxz * tauxzS) * 2.0;
+            tauyy -= fact * (Wyx * tauxyS + Wyz * tauyzS) * 2.0;
+            tauzz -= fact * (Wzx * tauxzS + Wzy * tauyzS) * 2.0;
+            tauxy -= fact * (Wxy * tauyyS + Wxz * tauyzS + Wyx * tauxxS + Wyz * tauxzS);
+            tauxz -= fact * (Wxy * tauyzS + Wxz * tauzzS + Wzx * tauxxS + Wzy * tauxyS);
+            tauyz -= fact * (Wyx * tauxzS + Wyz * tauzzS + Wzx * tauxyS + Wzy * tauyyS);
+        }
+        const double ubar = 0.5 * (m.u + q.u), vbar = 0.5 * (m.v + q.v), wbar = 0.5 * (m.w + q.w);
+        fd[1] += tauxx * s1 + tauxy * s2 + tauxz * s3;
+        fd[2] += tauxy * s1 + tauyy * s2 + tauyz * s3;
+        fd[3] += tauxz * s1 + tauyz * s2 + tauzz * s3;
+        fd[4] += (ubar * tauxx + vbar * tauxy + wbar * tauxz) * s1 + (ubar * tauxy + vbar * tauyy + wbar * tauyz) * s2 +
+                 (ubar * tauxz + vbar * tauyz + wbar * tauzz) * s3 - q_x * s1 - q_y * s2 - q_z * s3;
+    }
 }
 
-// viscousFlux, one face: blockette.F90:5576-5808 (k), :5876-6110 (j), :6172-6400 (i).
-// n is the node at the (+,+,+) corner of cell c; the face's four nodes are
-// n-t1-t2, n-t2, n-t1, n (reference order of the 4-node average).
-__device__ __forceinline__ void visc_face(const BlockDev& b, long long N, long long c, long long sd, long long t1,
-                                          long long t2, const double* __restrict__ s, int8_t por, double rFilv,
-                                          double f[4]) {
-    const long long cp = c + sd;
-    const double* w = b.w;
-    double porv = 0.5 * rFilv;
-    if (por == ADFB_NOFLUX) porv = 0.0;
-    const double mul = porv * (b.rlv[c] + b.rlv[cp]);
-    const double mue = porv * (b.rev[c] + b.rev[cp]);
-    const double mut = mul + mue;
-    const double gm1 = c_prm.gammaInf - 1.0;
-    const double heatCoef = mul * (1.0 / (c_prm.prandtl * gm1)) + mue * (1.0 / (c_prm.prandtlTurb * gm1));
-    const long long n = c, n1 = c - t1 - t2, n2 = c - t2, n3 = c - t1;
-    double g[12];
+// k_faces: plus faces of cell (i,j,k), i 1:il, j 1:jl, k 1:kl.  MERGED: one array G = fc - fd per
+// face (net outflow of the low cell) -> flux[dir*5 + l]; otherwise fc -> flux[dir*10 + l],
+// fd -> flux[dir*10 + 5 + l] (smoother path: fw persists between RK stages).
+template <bool VISCOUS, bool MERGED>
+__global__ void __launch_bounds__(128) k_faces(Dims d, BlockDev b, double rFil, int doVisc, int doDiss) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 1;
+    if (i > d.il || j > d.jl || k > d.kl) return;
+    const int N = (int)d.N, sJ = (int)d.sJ, sK = (int)d.sK;
+    const int c = i + sJ * j + sK * k;
+    const CellState m = load_cell(b, N, c);
+    double fc[5], fd[5];
+    const bool oi = i >= 2, oj = j >= 2, ok = k >= 2;
+    if (oj && ok) {
+        face_flux<VISCOUS>(b, N, c, 1, sJ, sK, 0, b.si, b.porI[c], b.radI, b.dss, m, rFil, doDiss, doVisc, fc, fd);
 #pragma unroll
-    for (int m = 0; m < 12; m++) {
-        const double* gm = b.grad + m * N;
-        g[m] = 0.25 * (gm[n1] + gm[n2] + gm[n3] + gm[n]);
+        for (int l = 0; l < 5; l++) {
+            if (MERGED) b.flux[l * N + c] = fc[l] - fd[l];
+            else { b.flux[l * N + c] = fc[l]; b.flux[(5 + l) * N + c] = fd[l]; }
+        }
     }
-    double ss3[3];
+    if (oi && ok) {
+        face_flux<VISCOUS>(b, N, c, sJ, 1, sK, 1, b.sj, b.porJ[c], b.radJ, b.dss + N, m, rFil, doDiss, doVisc, fc, fd);
 #pragma unroll
-    for (int m = 0; m < 3; m++) {
-        const double* xm = b.x + m * N;
-        ss3[m] = 0.125 * (xm[n1 + sd] - xm[n1 - sd] + xm[n3 + sd] - xm[n3 - sd] + xm[n2 + sd] - xm[n2 - sd] +
-                          xm[n + sd] - xm[n - sd]);
+        for (int l = 0; l < 5; l++) {
+            if (MERGED) b.flux[(5 + l) * N + c] = fc[l] - fd[l];
+            else { b.flux[(10 + l) * N + c] = fc[l]; b.flux[(15 + l) * N + c] = fd[l]; }
+        }
     }
-    const double snrm = 1.0 / sqrt(ss3[0] * ss3[0] + ss3[1] * ss3[1] + ss3[2] * ss3[2]);
-    const double ssx = snrm * ss3[0], ssy = snrm * ss3[1], ssz = snrm * ss3[2];
-    const double u0 = w[N + c], v0 = w[2 * N + c], w0 = w[3 * N + c];
-    const double u1 = w[N + cp], v1 = w[2 * N + cp], w1 = w[3 * N + cp];
-    double corr;
-    corr = g[0] * ssx + g[1] * ssy + g[2] * ssz - (u1 - u0) * snrm;
-    const double u_x = g[0] - corr * ssx, u_y = g[1] - corr * ssy, u_z = g[2] - corr * ssz;
-    corr = g[3] * ssx + g[4] * ssy + g[5] * ssz - (v1 - v0) * snrm;
-    const double v_x = g[3] - corr * ssx, v_y = g[4] - corr * ssy, v_z = g[5] - corr * ssz;
-    corr = g[6] * ssx + g[7] * ssy + g[8] * ssz - (w1 - w0) * snrm;
-    const double w_x = g[6] - corr * ssx, w_y = g[7] - corr * ssy, w_z = g[8] - corr * ssz;
-    corr = g[9] * ssx + g[10] * ssy + g[11] * ssz + (b.aa[cp] - b.aa[c]) * snrm;
-    double q_x = g[9] - corr * ssx, q_y = g[10] - corr * ssy, q_z = g[11] - corr * ssz;
-    const double fracDiv = (2.0 * (1.0 / 3.0)) * (u_x + v_y + w_z);
-    const double tauxxS = 2.0 * u_x - fracDiv, tauyyS = 2.0 * v_y - fracDiv, tauzzS = 2.0 * w_z - fracDiv;
-    const double tauxyS = u_y + v_x, tauxzS = u_z + w_x, tauyzS = v_z + w_y;
-    q_x = heatCoef * q_x; q_y = heatCoef * q_y; q_z = heatCoef * q_z;
-    double tauxx = mut * tauxxS, tauyy = mut * tauyyS, tauzz = mut * tauzzS;
-    double tauxy = mut * tauxyS, tauxz = mut * tauxzS, tauyz = mut * tauyzS;
-    if (c_prm.useQCR) {
-        double den = sqrt(u_x * u_x + u_y * u_y + u_z * u_z + v_x * v_x + v_y * v_y + v_z * v_z + w_x * w_x +
-                          w_y * w_y + w_z * w_z);
-        den = dmax_(den, 1.e-10);
-        const double fact = mue * 0.3 / den;
-        const double Wxy = u_y - v_x, Wxz = u_z - w_x, Wyz = v_z - w_y;
-        const double Wyx = -Wxy, Wzx = -Wxz, Wzy = -Wyz;
-        tauxx -= fact * (Wxy * tauxyS + Wxz * tauxzS) * 2.0;
-        tauyy -= fact * (Wyx * tauxyS + Wyz * tauyzS) * 2.0;
-        tauzz -= fact * (Wzx * tauxzS + Wzy * tauyzS) * 2.0;
-        tauxy -= fact * (Wxy * tauyyS + Wxz * tauyzS + Wyx * tauxxS + Wyz * tauxzS);
-        tauxz -= fact * (Wxy * tauyzS + Wxz * tauzzS + Wzx * tauxxS + Wzy * tauxyS);
-        tauyz -= fact * (Wyx * tauxzS + Wyz * tauzzS + Wzx * tauxyS + Wzy * tauyyS);
+    if (oi && oj) {
+        face_flux<VISCOUS>(b, N, c, sK, 1, sJ, 2, b.sk, b.porK[c], b.radK, b.dss + 2 * N, m, rFil, doDiss, doVisc, fc, fd);
+#pragma unroll
+        for (int l = 0; l < 5; l++) {
+            if (MERGED) b.flux[(10 + l) * N + c] = fc[l] - fd[l];
+            else { b.flux[(20 + l) * N + c] = fc[l]; b.flux[(25 + l) * N + c] = fd[l]; }
+        }
     }
-    const double ubar = 0.5 * (u0 + u1), vbar = 0.5 * (v0 + v1), wbar = 0.5 * (w0 + w1);
-    const double s1 = s[c], s2 = s[N + c], s3 = s[2 * N + c];
-    f[0] = tauxx * s1 + tauxy * s2 + tauxz * s3;
-    f[1] = tauxy * s1 + tauyy * s2 + tauyz * s3;
-    f[2] = tauxz * s1 + tauyz * s2 + tauzz * s3;
-    f[3] = (ubar * tauxx + vbar * tauxy + wbar * tauxz) * s1 + (ubar * tauxy + vbar * tauyy + wbar * tauyz) * s2 +
-           (ubar * tauxz + vbar * tauyz + wbar * tauzz) * s3 - q_x * s1 - q_y * s2 - q_z * s3;
 }
 
 // ---------------------------------------------------------------------------
 // SA residual pieces for one cell.
 // saAdvection, one direction: blockette.F90:1415-1560 (k), j, i analogous
-__device__ __forceinline__ double sa_adv_dir(const BlockDev& b, long long N, long long c, long long sd,
-                                             const double* __restrict__ s, double voli2, double ux, double uy, double uz) {
+__device__ __forceinline__ double sa_adv_dir(const BlockDev& b, int N, int c, int sd, const double* __restrict__ ssum,
+                                             double voli2, double ux, double uy, double uz) {
     const double* nt = b.w + ITU1 * N;
-    const double xa = (s[c] + s[c - sd]) * voli2;
-    const double ya = (s[N + c] + s[N + c - sd]) * voli2;
-    const double za = (s[2 * N + c] + s[2 * N + c - sd]) * voli2;
+    const double xa = ssum[c] * voli2, ya = ssum[N + c] * voli2, za = ssum[2 * N + c] * voli2;
     const double uu = xa * ux + ya * uy + za * uz;
     double dwtx;
     if (uu > 0.0) {
@@ -318,28 +411,25 @@ __device__ __forceinline__ double sa_adv_dir(const BlockDev& b, long long N, lon
 }
 
 // saViscous, one direction: blockette.F90:1197-1258 (k), j, i analogous.
-// returns c1m*nu(m) - c10*nu + c1p*nu(p) added left-to-right onto `acc`.
-__device__ __forceinline__ double sa_visc_dir(const BlockDev& b, long long N, long long c, long long sd,
-                                              const double* __restrict__ s, double acc) {
+__device__ __forceinline__ double sa_visc_dir(const BlockDev& b, int N, int c, int sd, const double* __restrict__ s,
+                                              const double* __restrict__ ssum, double nu, double acc) {
     const double* w = b.w;
     const double* vol = b.vol;
-    const long long cm = c - sd, cp = c + sd;
+    const int cm = c - sd, cp = c + sd;
     const double cb3Inv = 1.0 / c_prm.rsaCb3, cb2 = c_prm.rsaCb2;
-    const double voli = 1.0 / vol[c];
-    const double volmi = 2.0 / (vol[c] + vol[cm]);
-    const double volpi = 2.0 / (vol[c] + vol[cp]);
+    const double vc = vol[c];
+    const double voli = 1.0 / vc;
+    const double volmi = 2.0 / (vc + vol[cm]);
+    const double volpi = 2.0 / (vc + vol[cp]);
     const double xm = s[cm] * volmi, ym = s[N + cm] * volmi, zm = s[2 * N + cm] * volmi;
     const double xp = s[c] * volpi, yp = s[N + c] * volpi, zp = s[2 * N + c] * volpi;
-    const double xa = 0.5 * (s[c] + s[cm]) * voli;
-    const double ya = 0.5 * (s[N + c] + s[N + cm]) * voli;
-    const double za = 0.5 * (s[2 * N + c] + s[2 * N + cm]) * voli;
+    const double xa = 0.5 * ssum[c] * voli, ya = 0.5 * ssum[N + c] * voli, za = 0.5 * ssum[2 * N + c] * voli;
     const double ttm = xm * xa + ym * ya + zm * za;
     const double ttp = xp * xa + yp * ya + zp * za;
     const double nt0 = w[ITU1 * N + c], ntm = w[ITU1 * N + cm], ntp = w[ITU1 * N + cp];
     const double cnud = -cb2 * nt0 * cb3Inv;
     const double cam = ttm * cnud, cap = ttp * cnud;
     const double nutm = 0.5 * (ntm + nt0), nutp = 0.5 * (ntp + nt0);
-    const double nu = b.rlv[c] / w[c];
     const double num = 0.5 * (b.rlv[cm] / w[cm] + nu);
     const double nup = 0.5 * (b.rlv[cp] / w[cp] + nu);
     const double cdm = (num + (1.0 + cb2) * nutm) * ttm * cb3Inv;
@@ -350,19 +440,18 @@ __device__ __forceinline__ double sa_visc_dir(const BlockDev& b, long long N, lo
 }
 
 // saSource: blockette.F90:976-1168
-__device__ __forceinline__ double sa_source(const BlockDev& b, const Dims& d, long long c) {
-    const long long N = d.N;
+__device__ __forceinline__ double sa_source(const BlockDev& b, int N, int sJ, int sK, int c, double nu) {
     const double* w = b.w;
     double gv[3][3];
 #pragma unroll
     for (int v = 0; v < 3; v++) {
         const double* q = w + (IVX + v) * N;
-        const double qip = q[c + 1], qim = q[c - 1], qjp = q[c + d.sJ], qjm = q[c - d.sJ], qkp = q[c + d.sK], qkm = q[c - d.sK];
+        const double qip = q[c + 1], qim = q[c - 1], qjp = q[c + sJ], qjm = q[c - sJ], qkp = q[c + sK], qkm = q[c - sK];
 #pragma unroll
         for (int m = 0; m < 3; m++) {
-            const long long o = m * N;
-            gv[v][m] = qip * b.si[o + c] - qim * b.si[o + c - 1] + qjp * b.sj[o + c] - qjm * b.sj[o + c - d.sJ] +
-                       qkp * b.sk[o + c] - qkm * b.sk[o + c - d.sK];
+            const int o = m * N;
+            gv[v][m] = qip * b.si[o + c] - qim * b.si[o + c - 1] + qjp * b.sj[o + c] - qjm * b.sj[o + c - sJ] +
+                       qkp * b.sk[o + c] - qkm * b.sk[o + c - sK];
         }
     }
     const double fact = 0.25 / b.vol[c];
@@ -384,7 +473,6 @@ __device__ __forceinline__ double sa_source(const BlockDev& b, const Dims& d, lo
     const double cw3 = c_prm.rsaCw3;
     const double cw36 = (cw3 * cw3 * cw3) * (cw3 * cw3 * cw3);
     const double nt = w[ITU1 * N + c];
-    const double nu = b.rlv[c] / w[c];
     const double dw_ = b.d2Wall[c];
     const double dist2Inv = 1.0 / (dw_ * dw_);
     const double chi = nt / nu, chi2 = chi * chi, chi3 = chi * chi2;
@@ -407,121 +495,90 @@ __device__ __forceinline__ double sa_source(const BlockDev& b, const Dims& d, lo
     return (term1 + term2 * nt) * nt;
 }
 
-// ---------------------------------------------------------------------------
-// k_resid: the fused residual for one owned cell.
-//   flowRes / turbRes select rows; rFil and persistFw implement the RK
-//   dissipation blending (fw = sfil*fw_old + ..., src/solver/residuals.F90:61-65,
-//   fluxes.F90:1193); for blocketteRes rFil == 1 and fw is never stored.
-template <bool VISCOUS>
-__global__ void __launch_bounds__(128) k_resid(Dims d, BlockDev b, int flowRes, int turbRes, double rFil, int persistFw,
-                                               int doVisc, int doDiss) {
-    int i, j, k;
-    cell_index(d, i, j, k, 2, 2, 2);
+// k_sa: SA row of one owned cell: source, advection k/j/i, diffusion k/j/i, scaling
+// (blockette.F90:623-627, :1872-1897)
+__global__ void __launch_bounds__(128) k_sa(Dims d, BlockDev b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
     if (i > d.il || j > d.jl || k > d.kl) return;
-    const long long c = ADFB_IDX(i, j, k);
-    const long long N = d.N;
+    const int N = (int)d.N, sJ = (int)d.sJ, sK = (int)d.sK;
+    const int c = i + sJ * j + sK * k;
     const double rblank = dmax_((double)b.iblank[c], 0.0);
+    const double nu = b.rlv[c] / b.w[c];
+    double r = 0.0;
+    r = r + sa_source(b, N, sJ, sK, c, nu);
+    const double voli2 = 0.5 / b.vol[c];
+    const double ux = b.w[N + c], uy = b.w[2 * N + c], uz = b.w[3 * N + c];
+    r = r - sa_adv_dir(b, N, c, sK, b.ssum + 6 * N, voli2, ux, uy, uz);
+    r = r - sa_adv_dir(b, N, c, sJ, b.ssum + 3 * N, voli2, ux, uy, uz);
+    r = r - sa_adv_dir(b, N, c, 1, b.ssum, voli2, ux, uy, uz);
+    r = sa_visc_dir(b, N, c, sK, b.sk, b.ssum + 6 * N, nu, r);
+    r = sa_visc_dir(b, N, c, sJ, b.sj, b.ssum + 3 * N, nu, r);
+    r = sa_visc_dir(b, N, c, 1, b.si, b.ssum, nu, r);
+    b.dw[ITU1 * N + c] = -b.volRef[c] * r * rblank;
+}
 
-    if (turbRes) {
-        // order of accumulation: source, advection k/j/i, diffusion k/j/i (blockette.F90:623-627)
-        double r = 0.0;
-        r = r + sa_source(b, d, c);
-        const double voli2 = 0.5 / b.vol[c];
-        const double ux = b.w[N + c], uy = b.w[2 * N + c], uz = b.w[3 * N + c];
-        r = r - sa_adv_dir(b, N, c, d.sK, b.sk, voli2, ux, uy, uz);
-        r = r - sa_adv_dir(b, N, c, d.sJ, b.sj, voli2, ux, uy, uz);
-        r = r - sa_adv_dir(b, N, c, 1, b.si, voli2, ux, uy, uz);
-        r = sa_visc_dir(b, N, c, d.sK, b.sk, r);
-        r = sa_visc_dir(b, N, c, d.sJ, b.sj, r);
-        r = sa_visc_dir(b, N, c, 1, b.si, r);
-        b.dw[ITU1 * N + c] = -b.volRef[c] * r * rblank;  // saResScale, :1872-1897
+// k_div: flux divergence + sumDwandFw epilogue (blockette.F90:6839-6864) for one owned cell.
+// Order per variable: -Fi(c-1) +Fi(c) -Fj(c-sJ) +Fj(c) -Fk(c-sK) +Fk(c), like the reference's sweeps.
+template <bool MERGED>
+__global__ void __launch_bounds__(256) k_div(Dims d, BlockDev b, double rFil, int persistFw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
+    if (i > d.il || j > d.jl || k > d.kl) return;
+    const int N = (int)d.N, sJ = (int)d.sJ, sK = (int)d.sK;
+    const int c = i + sJ * j + sK * k;
+    const double rblank = dmax_((double)b.iblank[c], 0.0);
+    const double* F = b.flux;
+    if (MERGED) {
+#pragma unroll
+        for (int l = 0; l < 5; l++) {
+            double a = 0.0;
+            a -= F[l * N + c - 1];
+            a += F[l * N + c];
+            a -= F[(5 + l) * N + c - sJ];
+            a += F[(5 + l) * N + c];
+            a -= F[(10 + l) * N + c - sK];
+            a += F[(10 + l) * N + c];
+            b.dw[l * N + c] = a * rblank;
+        }
+    } else {
+        const double sfil = 1.0 - rFil;
+#pragma unroll
+        for (int l = 0; l < 5; l++) {
+            double a = 0.0;
+            a -= F[l * N + c - 1];
+            a += F[l * N + c];
+            a -= F[(10 + l) * N + c - sJ];
+            a += F[(10 + l) * N + c];
+            a -= F[(20 + l) * N + c - sK];
+            a += F[(20 + l) * N + c];
+            double fw = persistFw ? sfil * b.fw[l * N + c] : 0.0;
+            fw += F[(5 + l) * N + c - 1];
+            fw -= F[(5 + l) * N + c];
+            fw += F[(15 + l) * N + c - sJ];
+            fw -= F[(15 + l) * N + c];
+            fw += F[(25 + l) * N + c - sK];
+            fw -= F[(25 + l) * N + c];
+            if (persistFw) b.fw[l * N + c] = fw;
+            b.dw[l * N + c] = (a + fw) * rblank;
+        }
     }
-    if (!flowRes) return;
-
-    double dw[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    double f[5];
-    // central: i, j, k ; minus face first (dw(i+1) -= fs at loop i-1), then plus face
-    central_face(b, N, c - 1, c, b.si, b.porI[c - 1], f);
-#pragma unroll
-    for (int l = 0; l < 5; l++) dw[l] -= f[l];
-    central_face(b, N, c, c + 1, b.si, b.porI[c], f);
-#pragma unroll
-    for (int l = 0; l < 5; l++) dw[l] += f[l];
-    central_face(b, N, c - d.sJ, c, b.sj, b.porJ[c - d.sJ], f);
-#pragma unroll
-    for (int l = 0; l < 5; l++) dw[l] -= f[l];
-    central_face(b, N, c, c + d.sJ, b.sj, b.porJ[c], f);
-#pragma unroll
-    for (int l = 0; l < 5; l++) dw[l] += f[l];
-    central_face(b, N, c - d.sK, c, b.sk, b.porK[c - d.sK], f);
-#pragma unroll
-    for (int l = 0; l < 5; l++) dw[l] -= f[l];
-    central_face(b, N, c, c + d.sK, b.sk, b.porK[c], f);
-#pragma unroll
-    for (int l = 0; l < 5; l++) dw[l] += f[l];
-
-    // dissipation (scalar JST): fw = sfil*fw ; i, j, k ; fw(i+1) += fs ; fw(i) -= fs
-    double fw[5];
-    const double sfil = 1.0 - rFil;
-#pragma unroll
-    for (int l = 0; l < 5; l++) fw[l] = persistFw ? sfil * b.fw[l * N + c] : 0.0;
-    if (doDiss && c_prm.spaceDiscr == ADFB_DISS_SCALAR) {
-        const double fis2 = rFil * c_prm.vis2, fis4 = rFil * c_prm.vis4;
-        jst_face(b, N, c - 1, 1, b.radI, b.dss, b.porI[c - 1], fis2, fis4, f);
-#pragma unroll
-        for (int l = 0; l < 5; l++) fw[l] += f[l];
-        jst_face(b, N, c, 1, b.radI, b.dss, b.porI[c], fis2, fis4, f);
-#pragma unroll
-        for (int l = 0; l < 5; l++) fw[l] -= f[l];
-        jst_face(b, N, c - d.sJ, d.sJ, b.radJ, b.dss + N, b.porJ[c - d.sJ], fis2, fis4, f);
-#pragma unroll
-        for (int l = 0; l < 5; l++) fw[l] += f[l];
-        jst_face(b, N, c, d.sJ, b.radJ, b.dss + N, b.porJ[c], fis2, fis4, f);
-#pragma unroll
-        for (int l = 0; l < 5; l++) fw[l] -= f[l];
-        jst_face(b, N, c - d.sK, d.sK, b.radK, b.dss + 2 * N, b.porK[c - d.sK], fis2, fis4, f);
-#pragma unroll
-        for (int l = 0; l < 5; l++) fw[l] += f[l];
-        jst_face(b, N, c, d.sK, b.radK, b.dss + 2 * N, b.porK[c], fis2, fis4, f);
-#pragma unroll
-        for (int l = 0; l < 5; l++) fw[l] -= f[l];
-    }
-
-    if (VISCOUS && doVisc) {
-        // viscous: k, j, i ; fw(k+1) += f at loop k-1 (minus face), fw(k) -= f (plus face)
-        double v[4];
-        visc_face(b, N, c - d.sK, d.sK, 1, d.sJ, b.sk, b.porK[c - d.sK], rFil, v);
-#pragma unroll
-        for (int l = 0; l < 4; l++) fw[l + 1] += v[l];
-        visc_face(b, N, c, d.sK, 1, d.sJ, b.sk, b.porK[c], rFil, v);
-#pragma unroll
-        for (int l = 0; l < 4; l++) fw[l + 1] -= v[l];
-        visc_face(b, N, c - d.sJ, d.sJ, 1, d.sK, b.sj, b.porJ[c - d.sJ], rFil, v);
-#pragma unroll
-        for (int l = 0; l < 4; l++) fw[l + 1] += v[l];
-        visc_face(b, N, c, d.sJ, 1, d.sK, b.sj, b.porJ[c], rFil, v);
-#pragma unroll
-        for (int l = 0; l < 4; l++) fw[l + 1] -= v[l];
-        visc_face(b, N, c - 1, 1, d.sJ, d.sK, b.si, b.porI[c - 1], rFil, v);
-#pragma unroll
-        for (int l = 0; l < 4; l++) fw[l + 1] += v[l];
-        visc_face(b, N, c, 1, d.sJ, d.sK, b.si, b.porI[c], rFil, v);
-#pragma unroll
-        for (int l = 0; l < 4; l++) fw[l + 1] -= v[l];
-    }
-    if (persistFw) {
-#pragma unroll
-        for (int l = 0; l < 5; l++) b.fw[l * N + c] = fw[l];
-    }
-    // sumDwandFw, blockette.F90:6839-6864
-#pragma unroll
-    for (int l = 0; l < 5; l++) b.dw[l * N + c] = (dw[l] + fw[l]) * rblank;
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------
-// host-side launcher (called from adfb_api.cu)
+static int launch_geom(const Dims& d, const BlockDev& b, cudaStream_t stream) {
+    dim3 tb(32, 4, 2);
+    dim3 g((d.NI + tb.x - 1) / tb.x, (d.NJ + tb.y - 1) / tb.y, (d.NK + tb.z - 1) / tb.z);
+    KT_BEGIN(K_METRICS, stream);
+    k_geom<<<g, tb, 0, stream>>>(d, b);
+    KT_END(K_METRICS, stream);
+    return (int)cudaGetLastError();
+}
+
 // doRad: 1 = recompute spectral radii + dtl (blockette order), 0 = keep them (block/smoother path)
 static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbParams& prm, unsigned flags, double rFil,
                                 int persistFw, int doRad, cudaStream_t stream) {
@@ -532,7 +589,7 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
     const int doDiss = fabs(rFil) >= 1.e-10;  // fluxes.F90:1082 early return
     const int doVisc = viscous && doDiss;
     dim3 tb(32, 4, 2);
-    if (doRad || doDiss) {
+    if (doRad || (flowRes && doDiss)) {
         dim3 g((d.NI + tb.x - 1) / tb.x, (d.NJ + tb.y - 1) / tb.y, (d.NK + tb.z - 1) / tb.z);
         KT_BEGIN(K_PREP, stream);
         k_prep<<<g, tb, 0, stream>>>(d, b, updateDt, doRad);
@@ -544,16 +601,31 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         k_nodal<<<g, tb, 0, stream>>>(d, b, doVisc);
         KT_END(K_NODAL, stream);
     }
-    {
+    if (turbRes) {
         dim3 tr(32, 4, 1);
         dim3 g((d.nx + tr.x - 1) / tr.x, (d.ny + tr.y - 1) / tr.y, (d.nz + tr.z - 1) / tr.z);
+        KT_BEGIN(K_SA, stream);
+        k_sa<<<g, tr, 0, stream>>>(d, b);
+        KT_END(K_SA, stream);
+    }
+    if (flowRes) {
+        dim3 tr(32, 4, 1);
+        dim3 g((d.il + tr.x - 1) / tr.x, (d.jl + tr.y - 1) / tr.y, (d.kl + tr.z - 1) / tr.z);
+        const bool merged = !persistFw;
         KT_BEGIN(K_RESID, stream);
-        if (viscous)
-            k_resid<true><<<g, tr, 0, stream>>>(d, b, flowRes, turbRes, rFil, persistFw, doVisc, doDiss);
-        else
-            k_resid<false><<<g, tr, 0, stream>>>(d, b, flowRes, turbRes, rFil, persistFw, doVisc, doDiss);
+        if (viscous) {
+            if (merged) k_faces<true, true><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
+            else k_faces<true, false><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
+        } else {
+            if (merged) k_faces<false, true><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
+            else k_faces<false, false><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
+        }
         KT_END(K_RESID, stream);
+        dim3 g2((d.nx + tb.x - 1) / tb.x, (d.ny + tb.y - 1) / tb.y, (d.nz + tb.z - 1) / tb.z);
+        KT_BEGIN(K_DIV, stream);
+        if (merged) k_div<true><<<g2, tb, 0, stream>>>(d, b, rFil, persistFw);
+        else k_div<false><<<g2, tb, 0, stream>>>(d, b, rFil, persistFw);
+        KT_END(K_DIV, stream);
     }
     return (int)cudaGetLastError();
 }
-
