@@ -10,7 +10,7 @@ import os
 from .params import AdfbParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadflow_b200.so")
+LIB_PATH = os.environ.get("ADFLOW_B200_LIB", os.path.join(_HERE, "libadflow_b200.so"))  # override: tuning experiments only
 
 # every symbol include/adflow_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [

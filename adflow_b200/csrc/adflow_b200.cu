@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -59,10 +60,15 @@ struct Context {
         int *rBlk = nullptr, *rLocal = nullptr, *rCount = nullptr; long long *rOff = nullptr, *rCum = nullptr;
         int *iSrcBlk = nullptr, *iDstBlk = nullptr; long long *iSrcOff = nullptr, *iDstOff = nullptr;
         double *sendBuf = nullptr, *recvBuf = nullptr;
-        CommVarTable* dTab = nullptr;
+        CommVarTable* dTab = nullptr;   // unused (kept for layout); tables are cached per selection
         int tabBlocks = 0;
+        std::map<int, CommVarTable*> tabs;  // key: start | end<<4 | commP<<8 | commV<<9
         std::vector<void*> allocs;
     } pat;
+    // CUDA graphs of whole entry points (launch-latency bound sequences of small kernels)
+    std::map<unsigned long long, cudaGraphExec_t> graphs;
+    std::map<unsigned long long, long long> graphLaunches;
+    bool useGraphs = true;
 };
 
 Context g;
@@ -163,6 +169,53 @@ int get(const Block& b, Ext e, const void* dev, void* host, int ncomp, size_t es
     return copy_box(b.d, (void*)dev, host, lo, n, ncomp, es, false);
 }
 
+// Run `body` through a cached CUDA graph: the entry points are sequences of 10-25 small
+// kernels (BC subfaces, halo pack/unpack ...) whose launch latency would otherwise dominate.
+// Graphs are bypassed while per-kernel event timing is on and for multi-rank runs unless
+// ADFB_GRAPH_NCCL=1 (NCCL send/recv inside stream capture).
+template <typename F>
+int run_graphed(unsigned long long key, F body) {
+    static int ncclOk = -1;
+    if (ncclOk < 0) {
+        const char* e = getenv("ADFB_GRAPH_NCCL"); ncclOk = (e && e[0] == '1') ? 1 : 0;
+        const char* n = getenv("ADFB_NO_GRAPH"); if (n && n[0] == '1') g.useGraphs = false;
+    }
+    if (!g.useGraphs || g_kt.on || (g.nranks > 1 && !ncclOk)) return body();
+    auto it = g.graphs.find(key);
+    if (it == g.graphs.end()) {
+        // relaxed mode: the lazily built halo variable tables may cudaMalloc/cudaMemcpy (on the
+        // legacy stream, which does not synchronise with the non-blocking compute stream)
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeRelaxed));
+        const long long l0 = g_kt.launches;
+        const int rc = body();
+        const long long nl = g_kt.launches - l0;
+        cudaError_t e = cudaStreamEndCapture(g.stream, &graph);
+        if (rc != 0 || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            g.useGraphs = false;  // fall back to direct launches for the rest of the run
+            if (rc != 0) return rc;
+            return body();
+        }
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { g.useGraphs = false; cudaGetLastError(); return body(); }
+        g.graphs[key] = exec;
+        g.graphLaunches[key] = nl;
+        it = g.graphs.find(key);
+    }
+    CK(cudaGraphLaunch(it->second, g.stream));
+    g_kt.launches += g.graphLaunches[key];
+    return 0;
+}
+void drop_graphs() {
+    for (auto& kv : g.graphs) cudaGraphExecDestroy(kv.second);
+    g.graphs.clear();
+    g.graphLaunches.clear();
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -226,6 +279,7 @@ int adfb_finalize(void) {
     g.hRed = nullptr;
     if (g.dVec) cudaFree(g.dVec);
     g.dVec = nullptr; g.dVecN = 0;
+    drop_graphs();
     for (void* q : g.pat.allocs) cudaFree(q);
     g.pat = Context::Pattern();
     if (g.comm) { g.nccl.CommDestroy(g.comm); g.comm = nullptr; }
@@ -242,6 +296,7 @@ int adfb_synchronize(void) {
 }
 
 long long adfb_launch_count(void) { return g_kt.launches; }
+int adfb_graph_count(void) { return g.useGraphs ? (int)g.graphs.size() : -1; }
 /* per-kernel CUDA-event timing (bench.py roofline pass): on=1 starts recording and
    resets the accumulators; adfb_kernel_times synchronises and returns the
    cumulative milliseconds and launch counts per kernel family. */
@@ -264,6 +319,7 @@ void* adfb_stream(void) { return (void*)g.stream; }
 
 int adfb_set_params(const AdfbParams* prm) {
     NEED_INIT();
+    drop_graphs();
     if (!prm) return fail("adfb_set_params: null");
     if (prm->equations < ADFB_EULER || prm->equations > ADFB_RANS) return fail("adfb_set_params: bad equations %d", prm->equations);
     if (prm->spaceDiscr != ADFB_DISS_SCALAR)
@@ -280,6 +336,7 @@ int adfb_set_params(const AdfbParams* prm) {
 
 int adfb_block_create(int blk, int level, int nx, int ny, int nz, int nw, int rightHanded) {
     NEED_INIT();
+    drop_graphs();
     if (blk < 0 || blk > 4095) return fail("adfb_block_create: block id %d out of range", blk);
     if (nx < 1 || ny < 1 || nz < 1) return fail("adfb_block_create: bad extents %d %d %d", nx, ny, nz);
     if (nw != 5 && nw != 6) return fail("adfb_block_create: nw must be 5 (Euler/NS) or 6 (RANS-SA), got %d", nw);
@@ -315,6 +372,7 @@ int adfb_block_create(int blk, int level, int nx, int ny, int nz, int nw, int ri
 
 int adfb_block_destroy(int blk) {
     NEED_INIT();
+    drop_graphs();
     Block* b = get_block(blk);
     if (!b) return fail("adfb_block_destroy: no block %d", blk);
     cudaStreamSynchronize(g.stream);
@@ -356,6 +414,7 @@ int adfb_block_set_bc(int blk, int nSub, const AdfbSubface* subfaces) {
     NEED_INIT();
     Block* b = get_block(blk);
     if (!b) return fail("adfb_block_set_bc: no block %d", blk);
+    drop_graphs();
     if (nSub < 0 || (nSub > 0 && !subfaces)) return fail("adfb_block_set_bc: bad arguments");
     cudaStreamSynchronize(g.stream);
     for (void* q : b->bcAllocs) cudaFree(q);
@@ -531,6 +590,7 @@ int adfb_comm_set_pattern(int level, int nNbr, const int* nbrRank, const int* se
     NEED_INIT();
     (void)level;
     if (nNbr < 0 || nInternal < 0) return fail("adfb_comm_set_pattern: negative counts");
+    drop_graphs();
     if (nNbr > 0 && g.nranks == 1) return fail("adfb_comm_set_pattern: neighbour ranks given but adfb_init was called with nranks = 1");
     CK(cudaStreamSynchronize(g.stream));
     for (void* q : g.pat.allocs) cudaFree(q);
@@ -578,27 +638,45 @@ static int halo_exchange_impl(int level, int start, int end, int commPressure, i
     const bool viscous = g.prm.equations != ADFB_EULER, eddy = g.prm.equations == ADFB_RANS;
     if (P.set && (P.nSend || P.nRecv || P.nInt)) {
         if ((int)g.blocks.size() != P.tabBlocks) return fail("halo exchange: blocks changed after adfb_comm_set_pattern");
-        std::vector<CommVarTable> tab(P.tabBlocks);
+        const int key = start | (end << 4) | ((commPressure ? 1 : 0) << 8) | ((commViscous ? 1 : 0) << 9);
         int nVar = 0;
-        for (int bId = 0; bId < P.tabBlocks; bId++) {
-            Block& b = g.blocks[bId];
-            memset(&tab[bId], 0, sizeof(CommVarTable));
-            if (!b.alive) continue;
-            int v = 0;
-            for (int l = start; l <= end && l <= b.nw; l++) tab[bId].ptr[v++] = b.dev.w + (size_t)(l - 1) * b.d.N;
-            if (commPressure) tab[bId].ptr[v++] = b.dev.p;
-            if (viscous && commViscous) tab[bId].ptr[v++] = b.dev.rlv;
-            if (eddy && commViscous) tab[bId].ptr[v++] = b.dev.rev;
-            nVar = v;
+        {
+            Block* b0 = nullptr;
+            for (Block& b : g.blocks) if (b.alive) { b0 = &b; break; }
+            if (!b0) return 0;
+            for (int l = start; l <= end && l <= b0->nw; l++) nVar++;
+            if (commPressure) nVar++;
+            if (viscous && commViscous) nVar++;
+            if (eddy && commViscous) nVar++;
         }
         if (nVar == 0) return 0;
         if (nVar > ADFB_MAX_COMM_VARS) return fail("halo exchange: too many variables");
-        CK(cudaMemcpyAsync(P.dTab, tab.data(), sizeof(CommVarTable) * P.tabBlocks, cudaMemcpyHostToDevice, g.stream));
-        CK(cudaStreamSynchronize(g.stream));  // tab is a stack vector
+        CommVarTable* dTab = nullptr;
+        auto it = P.tabs.find(key);
+        if (it != P.tabs.end()) dTab = it->second;
+        else {
+            std::vector<CommVarTable> tab(P.tabBlocks);
+            for (int bId = 0; bId < P.tabBlocks; bId++) {
+                Block& b = g.blocks[bId];
+                memset(&tab[bId], 0, sizeof(CommVarTable));
+                if (!b.alive) continue;
+                int v = 0;
+                for (int l = start; l <= end && l <= b.nw; l++) tab[bId].ptr[v++] = b.dev.w + (size_t)(l - 1) * b.d.N;
+                if (commPressure) tab[bId].ptr[v++] = b.dev.p;
+                if (viscous && commViscous) tab[bId].ptr[v++] = b.dev.rlv;
+                if (eddy && commViscous) tab[bId].ptr[v++] = b.dev.rev;
+            }
+            void* q = nullptr;
+            CK(cudaMalloc(&q, sizeof(CommVarTable) * P.tabBlocks));
+            P.allocs.push_back(q);
+            CK(cudaMemcpy(q, tab.data(), sizeof(CommVarTable) * P.tabBlocks, cudaMemcpyHostToDevice));
+            dTab = (CommVarTable*)q;
+            P.tabs[key] = dTab;
+        }
         if (P.nSend) {
             const long long n = P.nSend * nVar;
             KT_BEGIN(K_HALO, g.stream);
-            k_halo_pack<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.sBlk, P.sOff, P.sCum, P.sLocal, P.sCount, P.dTab, nVar, P.nSend, P.sendBuf);
+            k_halo_pack<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.sBlk, P.sOff, P.sCum, P.sLocal, P.sCount, dTab, nVar, P.nSend, P.sendBuf);
             KT_END(K_HALO, g.stream);
         }
         if (!P.nbrRank.empty()) {
@@ -615,13 +693,13 @@ static int halo_exchange_impl(int level, int start, int end, int commPressure, i
         if (P.nInt) {
             const long long n = P.nInt * nVar;
             KT_BEGIN(K_HALO, g.stream);
-            k_halo_internal<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.iSrcBlk, P.iSrcOff, P.iDstBlk, P.iDstOff, P.dTab, nVar, P.nInt);
+            k_halo_internal<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.iSrcBlk, P.iSrcOff, P.iDstBlk, P.iDstOff, dTab, nVar, P.nInt);
             KT_END(K_HALO, g.stream);
         }
         if (P.nRecv) {
             const long long n = P.nRecv * nVar;
             KT_BEGIN(K_HALO, g.stream);
-            k_halo_unpack<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.rBlk, P.rOff, P.rCum, P.rLocal, P.rCount, P.dTab, nVar, P.nRecv, P.recvBuf);
+            k_halo_unpack<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.rBlk, P.rOff, P.rCum, P.rLocal, P.rCount, dTab, nVar, P.nRecv, P.recvBuf);
             KT_END(K_HALO, g.stream);
         }
     }
@@ -648,15 +726,22 @@ int adfb_halo_exchange(int level, int start, int end, int commPressure, int comm
     return halo_exchange_impl(level, start, end, commPressure, commViscous, true);
 }
 
+static int residual_body(int level, unsigned flags);
 int adfb_residual(int level, unsigned flags) {
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_residual: adfb_set_params has not been called");
     if (!(flags & (ADFB_RES_FLOW | ADFB_RES_TURB))) return fail("adfb_residual: neither flow nor turbulence residual requested");
     if (flags & (ADFB_RES_DISS_APPROX | ADFB_RES_VISC_APPROX))
         return fail("adfb_residual: approximate (PC/ANK) flux variants are not built yet");
+    for (Block& b : g.blocks)
+        if (b.alive && b.level == level && !b.haveMetrics) return fail("adfb_residual: geometry of a block was never set");
+    const unsigned long long key = (1ull << 40) | ((unsigned long long)level << 32) | flags;
+    return run_graphed(key, [&]() { return residual_body(level, flags); });
+}
+
+static int residual_body(int level, unsigned flags) {
     for (Block& b : g.blocks) {
         if (!b.alive || b.level != level) continue;
-        if (!b.haveMetrics) return fail("adfb_residual: geometry of a block was never set");
         if (!(flags & ADFB_RES_SKIP_PREAMBLE)) {
             // blocketteRes :213-226: p, rlv, rev on owned cells, then turbulence and flow BCs
             if (launch_state_prep(b.d, b.dev, g.prm, false, (flags & ADFB_RES_FLOW) != 0, g.stream)) return fail("state prep launch failed");
