@@ -46,6 +46,11 @@ struct Context {
     double* hRed = nullptr;   // pinned
     double* dVec = nullptr;   // AoS staging vector (get/set states, get res)
     size_t dVecN = 0;
+    // NK / MFFD device vectors: direction a, base state U, base residual F(U), result y
+    double *nkA = nullptr, *nkU = nullptr, *nkF0 = nullptr, *nkY = nullptr;
+    size_t nkN = 0;
+    bool nkHaveBase = false;
+    double nkUnorm = 0.0, nkLastH = 0.0;
     std::string err;
     // multi-rank
     NcclApi nccl;
@@ -279,6 +284,8 @@ int adfb_finalize(void) {
     g.hRed = nullptr;
     if (g.dVec) cudaFree(g.dVec);
     g.dVec = nullptr; g.dVecN = 0;
+    for (double** p : {&g.nkA, &g.nkU, &g.nkF0, &g.nkY}) { if (*p) cudaFree(*p); *p = nullptr; }
+    g.nkN = 0; g.nkHaveBase = false;
     drop_graphs();
     for (void* q : g.pat.allocs) cudaFree(q);
     g.pat = Context::Pattern();
@@ -766,6 +773,115 @@ static int residual_body(int level, unsigned flags) {
     CK(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+// NK matrix-free residual-Jacobian product (src/NKSolver/NKSolvers.F90:437-461, :1331-1376,
+// :1262-1329; PETSc MatMFFD y = (F(U + h a) - F(U)) / h)
+static int nk_buffers(long long need) {
+    if (g.nkN >= (size_t)need) return 0;
+    for (double** p : {&g.nkA, &g.nkU, &g.nkF0, &g.nkY}) { if (*p) cudaFree(*p); *p = nullptr; }
+    g.nkN = 0;
+    for (double** p : {&g.nkA, &g.nkU, &g.nkF0, &g.nkY}) CK(cudaMalloc((void**)p, need * sizeof(double)));
+    if (!g.dRed) { CK(cudaMalloc((void**)&g.dRed, (2 * 1024 + 2) * sizeof(double))); g.dRedN = 2 * 1024 + 2; }
+    g.nkN = need;
+    return 0;
+}
+static int nk_vec_kernel(const double* vec, const double* base, double* out, double h, int mode) {
+    long long off = 0;
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != 1) continue;
+        const long long n = (long long)b.d.nx * b.d.ny * b.d.nz * b.nw;
+        KT_BEGIN(K_MFFD, g.stream);
+        k_nkvec<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(b.d, b.dev, b.nw, vec ? vec + off : nullptr, base ? base + off : nullptr,
+                                                                   out ? out + off : nullptr, h, mode);
+        KT_END(K_MFFD, g.stream);
+        off += n;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+// sum of squares of a device vector, all-reduced; result in *out
+static int nk_sumsq(const double* v, long long n, double* out) {
+    const int nPart = 512;
+    KT_BEGIN(K_MFFD, g.stream);
+    k_sumsq_partial<<<nPart, 256, 0, g.stream>>>(v, n, g.dRed);
+    KT_END(K_MFFD, g.stream);
+    KT_BEGIN(K_MFFD, g.stream);
+    k_sum_final<<<1, 256, 0, g.stream>>>(g.dRed, nPart);
+    KT_END(K_MFFD, g.stream);
+    if (g.nranks > 1) {
+        const int rc = g.nccl.AllReduce(g.dRed + nPart, g.dRed + nPart, 1, kNcclDouble, kNcclSum, g.comm, g.stream);
+        if (rc != 0) return fail("ncclAllReduce: %s", g.nccl.GetErrorString(rc));
+    }
+    CK(cudaMemcpyAsync(g.hRed, g.dRed + nPart, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    *out = g.hRed[0];
+    return 0;
+}
+static const unsigned kNkFlags = ADFB_RES_FLOW | ADFB_RES_TURB;
+
+// FormFunction_mf (NKSolvers.F90:437-461): setW(wVec); computeResidualNK; setRVec(rVec)
+int adfb_form_function(const double* wVec, double* rVec, long long n) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_form_function: adfb_set_params has not been called");
+    const long long need = adfb_state_size();
+    if (!wVec || !rVec || n != need) return fail("adfb_form_function: vector length %lld != local state size %lld", n, need);
+    if (nk_buffers(need)) return 1;
+    CK(cudaMemcpyAsync(g.nkA, wVec, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    if (nk_vec_kernel(g.nkA, nullptr, nullptr, 0.0, 0)) return 1;
+    if (adfb_residual(1, kNkFlags)) return 1;
+    if (nk_vec_kernel(nullptr, nullptr, g.nkY, 1.0, 2)) return 1;
+    CK(cudaMemcpyAsync(rVec, g.nkY, need * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+// MatMFFDSetBase(dRdw, wVec, baseRes) (NKSolvers.F90:628-630): U <- wVec, F0 <- F(U) on the device
+int adfb_mffd_set_base(const double* U, long long n) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_mffd_set_base: adfb_set_params has not been called");
+    const long long need = adfb_state_size();
+    if (!U || n != need) return fail("adfb_mffd_set_base: vector length %lld != local state size %lld", n, need);
+    if (nk_buffers(need)) return 1;
+    CK(cudaMemcpyAsync(g.nkU, U, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    if (nk_vec_kernel(g.nkU, nullptr, nullptr, 0.0, 0)) return 1;
+    if (adfb_residual(1, kNkFlags)) return 1;
+    if (nk_vec_kernel(nullptr, nullptr, g.nkF0, 1.0, 2)) return 1;
+    double uu = 0.0;
+    if (nk_sumsq(g.nkU, need, &uu)) return 1;
+    g.nkUnorm = sqrt(uu);
+    g.nkHaveBase = true;
+    return 0;
+}
+
+// MatMult of the MFFD shell: y = (F(U + h a) - F(U)) / h.  h > 0: use it as given;
+// h <= 0: PETSc's default Walker-Pernice choice h = error_rel * sqrt(1 + ||U||) / ||a||
+// with error_rel = sqrt(machine epsilon) (PARITY UNPINNED at this boundary).
+int adfb_mffd_apply(const double* a, double* y, long long n, double h) {
+    NEED_INIT();
+    if (!g.nkHaveBase) return fail("adfb_mffd_apply: adfb_mffd_set_base has not been called");
+    const long long need = adfb_state_size();
+    if (!a || !y || n != need || (size_t)need > g.nkN) return fail("adfb_mffd_apply: vector length %lld != local state size %lld", n, need);
+    CK(cudaMemcpyAsync(g.nkA, a, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    if (h <= 0.0) {
+        double aa = 0.0;
+        if (nk_sumsq(g.nkA, need, &aa)) return 1;
+        if (aa == 0.0) {
+            memset(y, 0, need * sizeof(double));
+            g.nkLastH = 0.0;
+            return 0;
+        }
+        h = 1.4901161193847656e-08 * sqrt(1.0 + g.nkUnorm) / sqrt(aa);
+    }
+    g.nkLastH = h;
+    if (nk_vec_kernel(g.nkA, g.nkU, nullptr, h, 1)) return 1;
+    if (adfb_residual(1, kNkFlags)) return 1;
+    if (nk_vec_kernel(nullptr, g.nkF0, g.nkY, h, 3)) return 1;
+    CK(cudaMemcpyAsync(y, g.nkY, need * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+double adfb_mffd_last_h(void) { return g.nkLastH; }
 
 // applyAllBC (+ turbulence halos), src/solver/BCRoutines.F90:57, turbBCRoutines.F90:49
 int adfb_apply_bcs(int level, int secondHalo, int withTurb) {

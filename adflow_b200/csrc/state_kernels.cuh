@@ -148,6 +148,60 @@ __global__ void __launch_bounds__(256) k_vec(Dims d, BlockDev b, int nw, double*
     else vec[q] = b.dw[l * d.N + c] * (1.0 / b.volRef[c]);
 }
 
+// NK / MFFD vector kernels (src/NKSolver/NKSolvers.F90):
+//  mode 0: setW (:1331-1376)            w <- vec, turbulence clipped at 1e-6*wInf
+//  mode 1: perturbed setW               w <- max-clip(base + h*vec)   (MFFD: F(U + h a))
+//  mode 2: setRVec (:1262-1329)         out <- dw/volRef (* turbResScale on turbulence rows)
+//  mode 3: MFFD difference              out <- (dw/volRef*scale - base) / h
+__global__ void __launch_bounds__(256) k_nkvec(Dims d, BlockDev b, int nw, const double* __restrict__ vec,
+                                               const double* __restrict__ base, double* __restrict__ out, double h, int mode) {
+    const long long nOwned = (long long)d.nx * d.ny * d.nz;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nOwned * nw) return;
+    const int l = (int)(q % nw);
+    const long long cell = q / nw;
+    const int i = (int)(cell % d.nx) + 2;
+    const int j = (int)((cell / d.nx) % d.ny) + 2;
+    const int k = (int)(cell / ((long long)d.nx * d.ny)) + 2;
+    const long long c = ADFB_IDX(i, j, k);
+    if (mode <= 1) {
+        double v = mode == 0 ? vec[q] : base[q] + h * vec[q];
+        if (l >= 5) v = dmax_(1e-6 * c_prm.wInf[l], v);
+        b.w[l * d.N + c] = v;
+    } else {
+        const double ovv = 1.0 / b.volRef[c];
+        double r = b.dw[l * d.N + c] * ovv;
+        if (l >= 5) r = b.dw[l * d.N + c] * ovv * c_prm.turbResScale;
+        out[q] = mode == 2 ? r : (r - base[q]) / h;
+    }
+}
+
+// sum of squares of a device vector (two-pass, deterministic): part[0..nPart) then part[nPart]
+__global__ void __launch_bounds__(256) k_sumsq_partial(const double* __restrict__ v, long long n, double* part) {
+    __shared__ double s[256];
+    double a = 0.0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) a += v[q] * v[q];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) s[threadIdx.x] += s[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = s[0];
+}
+__global__ void __launch_bounds__(256) k_sum_final(double* part, int nPart) {
+    __shared__ double s[256];
+    double a = 0.0;
+    for (int q = threadIdx.x; q < nPart; q += 256) a += part[q];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) s[threadIdx.x] += s[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[nPart] = s[0];
+}
+
 }  // namespace
 
 static int launch_vec(const Dims& d, const BlockDev& b, int nw, double* vec, int mode, cudaStream_t stream) {

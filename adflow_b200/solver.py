@@ -174,3 +174,24 @@ class ADFLOW_B200:
             res = np.zeros(self.getStateSize())
         check(self.L.adfb_get_res(res.ctypes.data, res.size), "adfb_get_res")
         return res
+
+    # -- NK matrix-free product (FormFunction_mf / MatMFFD, NKSolvers.F90:437, :167) ----
+    def formFunction(self, wvec):
+        wvec = np.ascontiguousarray(wvec, dtype=np.float64)
+        r = np.zeros_like(wvec)
+        check(self.L.adfb_form_function(wvec.ctypes.data, r.ctypes.data, wvec.size), "adfb_form_function")
+        return r
+
+    def mffdSetBase(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        check(self.L.adfb_mffd_set_base(U.ctypes.data, U.size), "adfb_mffd_set_base")
+
+    def mffdApply(self, a, h=-1.0, out=None):
+        """y = (F(U + h a) - F(U)) / h ; h <= 0 -> Walker-Pernice h computed on the device."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        y = np.zeros_like(a) if out is None else out
+        check(self.L.adfb_mffd_apply(a.ctypes.data, y.ctypes.data, a.size, float(h)), "adfb_mffd_apply")
+        return y
+
+    def mffdLastH(self):
+        return float(self.L.adfb_mffd_last_h())

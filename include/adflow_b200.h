@@ -189,6 +189,20 @@ int adfb_residual(int level, unsigned flags);
 int adfb_norms(double out[2]);
 int adfb_synchronize(void);
 
+/* ---- NK matrix-free residual-Jacobian product ------------------------------ */
+/* FormFunction_mf (src/NKSolver/NKSolvers.F90:437-461): setW(wVec) with the turbulence
+   clip max(1e-6*wInf, .) (:1331-1376), full residual (blocketteRes), setRVec
+   (dw/volRef, turbulence rows * turbResScale, :1262-1329).  Host vectors, AoS ordering. */
+int adfb_form_function(const double* wVec, double* rVec, long long n);
+/* MatMFFDSetBase (NKSolvers.F90:630): keep U and F(U) on the device */
+int adfb_mffd_set_base(const double* U, long long n);
+/* MatMult of the MFFD shell that replaces MatCreateMFFD (NKSolvers.F90:167):
+   y = (F(U + h a) - F(U)) / h, perturbation, residual and difference all on the device.
+   h > 0 is used as given; h <= 0 selects PETSc's default Walker-Pernice
+   h = sqrt(eps) * sqrt(1 + ||U||) / ||a|| (norms reduced on the device, all-reduced). */
+int adfb_mffd_apply(const double* a, double* y, long long n, double h);
+double adfb_mffd_last_h(void);
+
 /* ---- halo exchange (src/utils/haloExchange.F90) ---------------------------- */
 /* Device copy of the 1-to-1 communication pattern commPatternCell_2nd /
    internalCell_2nd (src/modules/communication.F90:85-168, built by

@@ -30,3 +30,28 @@ def oracle_residual(prm, hb, flags=FLOW | TURB, rfil=1.0):
     ho = hb.copy()
     Oracle(ho, prm).residual_core(flags, rfil)
     return ho
+
+
+def oracle_form_function(prm, hb, wvec):
+    """FormFunction_mf on one block with the oracle: setW (turbulence clip), blocketteRes
+    (p/rlv/rev, BCs, whalo2's owned-cell etot, core), setRVec."""
+    import ctypes as C
+
+    from oracle.pyoracle import Oracle
+
+    d = hb.d
+    ow = d.owned()
+    h2 = hb.copy()
+    v = np.asarray(wvec).reshape(d.nz, d.ny, d.nx, hb.nw).transpose(2, 1, 0, 3).copy()
+    if hb.nw > 5:
+        v[..., 5] = np.maximum(1e-6 * prm.wInf[5], v[..., 5])
+    h2.w[ow] = v
+    o = Oracle(h2, prm)
+    o.pressure(False); o.lam_viscosity(False); o.eddy_viscosity(False)
+    o.apply_turb_bc(True); o.apply_flow_bc(True)
+    o.L.orc_etot(C.byref(o.ob), C.byref(prm), 2, d.il, 2, d.jl, 2, d.kl)
+    o.residual_core(FLOW | TURB)
+    r = h2.dw[ow] / h2.volRef[ow][..., None]
+    if hb.nw > 5:
+        r[..., 5] *= prm.turbResScale
+    return np.transpose(r, (2, 1, 0, 3)).reshape(-1)
