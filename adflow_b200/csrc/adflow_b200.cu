@@ -20,6 +20,7 @@
 #include "residual_kernels.cuh"
 #include "smoother_kernels.cuh"
 #include "halo_kernels.cuh"
+#include "dadi_kernels.cuh"
 
 namespace {
 
@@ -941,6 +942,32 @@ int adfb_rk_stage(int level, int rkStage) {
     if (halo_exchange_impl(level, 1, 5, 1, 1, false)) return 1;
     CK(cudaGetLastError());
     return 0;
+}
+
+// executeDADIStep, src/solver/smoothers.F90:425-693
+int adfb_dadi_step(int level) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_dadi_step: adfb_set_params has not been called");
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != level) continue;
+        if (launch_dadi(b.d, b.dev, g.prm, g.stream)) return fail("DADI launch failed");
+        if (launch_dadi_update(b.d, b.dev, g.prm, g.stream)) return fail("DADI update launch failed");
+        if (launch_bc_flow(b.d, b.dev, b.subfaces, 1, g.stream)) return fail("flow BC launch failed");
+    }
+    if (halo_exchange_impl(level, 1, 5, 1, 1, false)) return 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// DADISmoother, src/solver/smoothers.F90:383-421
+int adfb_dadi_cycle(int level, int nSubiterations) {
+    NEED_INIT();
+    if (nSubiterations < 1) return fail("adfb_dadi_cycle: nSubiterations must be >= 1");
+    for (int sub = 1; sub <= nSubiterations - 1; sub++) {
+        if (adfb_dadi_step(level)) return 1;
+        if (adfb_smoother_residual(level, 0)) return 1;
+    }
+    return adfb_dadi_step(level);
 }
 
 // RungeKuttaSmoother, src/solver/smoothers.F90:4-86

@@ -1,0 +1,268 @@
+// dadi_kernels.cuh -- diagonalised ADI smoother (computedwDADI, src/solver/residuals.F90:1062-1748;
+// executeDADIStep, src/solver/smoothers.F90:425-693)
+//
+// The reference makes 3 sweeps (j, i, k); each solves, for every grid line, 5 scalar
+// tridiagonal systems (3 distinct coefficient sets: u+-0, u+c, u-c) with the Thomas
+// algorithm (tridiagsolve, :1750-1783), and wraps the sweeps in cell-local changes of
+// basis (T_eta^-1 :1277-1327, T_xi^-1 T_eta :1407-1448, T_zeta^-1 T_xi :1543-1583,
+// T_zeta :1679-1731).  Here ONE kernel per sweep does everything for its direction:
+// the thread that owns a line applies the incoming change of basis while it reads dw,
+// builds the tridiagonal coefficients on the fly from w, p, rlv, rev and the metrics
+// (no qq/cc/dual_dt scratch arrays), eliminates forward, substitutes backward, and (k
+// sweep) applies T_zeta and the -1/vol scaling while it writes the result.
+// j and k lines are walked with threads adjacent in i (coalesced); i lines are walked
+// one thread per line.
+//
+// Reference quirks kept: the spectral_* terms are multiplied by zero (:1269-1271) and
+// vanish; the k sweep's eps2 metric uses sj for the lower face (:1625-1627).
+#pragma once
+#include "adfb_common.cuh"
+#include <math.h>
+
+namespace {
+
+struct DadiCoef {      // per cell, per direction
+    double dP[3], dM[3];   // diagPlus / diagMinus for (u), (u+c), (u-c)
+    double vt1, vt3;       // viscTerm1, viscTerm3
+    double dtrb;           // dual_dt * max(iblank,0)
+};
+
+// cell-local coefficients of cell c for the sweep along sd (residuals.F90:1345-1372 etc.)
+__device__ __forceinline__ void dadi_cell(const BlockDev& b, int N, int c, int sd, const double* __restrict__ s,
+                                          const double* __restrict__ slow, double cfl, bool viscous, bool eddy, DadiCoef& A) {
+    const double epsval = 0.08, fac = 1.05;
+    const double cInf2 = c_prm.gammaInf * c_prm.pInf / c_prm.rhoInf;
+    const double rho = b.w[c], vol = b.vol[c];
+    const double volhalf = 0.5 / vol;
+    // metterm(m) (face c|c+sd) and metterm(m-1) (face c-sd|c)
+    double mp = 0.0, mm = 0.0;
+    {
+        double mut = 0.0;
+        if (viscous) mut = b.rlv[c] + b.rlv[c + sd];
+        if (eddy) mut = mut + b.rev[c] + b.rev[c + sd];
+        const double volfact = 1.0 / (vol + b.vol[c + sd]);
+        const double mt = s[c] * s[c] + s[N + c] * s[N + c] + s[2 * N + c] * s[2 * N + c];
+        mp = mt * mut * volfact;
+        const int cm = c - sd;
+        mut = 0.0;
+        if (viscous) mut = b.rlv[cm] + b.rlv[c];
+        if (eddy) mut = mut + b.rev[cm] + b.rev[c];
+        const double volfactm = 1.0 / (b.vol[cm] + vol);
+        const double mtm = s[cm] * s[cm] + s[N + cm] * s[N + cm] + s[2 * N + cm] * s[2 * N + cm];
+        mm = mtm * mut * volfactm;
+    }
+    A.vt1 = mp / vol / rho;
+    A.vt3 = mm / vol / rho;
+    // qq, cc (:1169-1211) use the true face sum; eps2 uses (s[c] + slow[c-sd]) (quirk in the k sweep)
+    const double q1 = volhalf * (s[c] + s[c - sd]), q2 = volhalf * (s[N + c] + s[N + c - sd]), q3 = volhalf * (s[2 * N + c] + s[2 * N + c - sd]);
+    const double u = b.w[N + c], v = b.w[2 * N + c], w = b.w[3 * N + c];
+    const double q = q1 * u + q2 * v + q3 * w - 0.0;
+    const double cijk = sqrt(c_prm.gammaInf * b.p[c] / rho);
+    const double cs = cijk * sqrt(q1 * q1 + q2 * q2 + q3 * q3);
+    const double r1 = volhalf * (s[c] + slow[c - sd]), r2 = volhalf * (s[N + c] + slow[N + c - sd]), r3 = volhalf * (s[2 * N + c] + slow[2 * N + c - sd]);
+    const double eps2 = epsval * epsval * cInf2 * (r1 * r1 + r2 * r2 + r3 * r3);
+    const double t0 = fac * sqrt(q * q + eps2), t1 = fac * sqrt((q + cs) * (q + cs) + eps2), t2 = fac * sqrt((q - cs) * (q - cs) + eps2);
+    A.dP[0] = 0.5 * (q + t0); A.dP[1] = 0.5 * (q + cs + t1); A.dP[2] = 0.5 * (q - cs + t2);
+    A.dM[0] = 0.5 * (q - t0); A.dM[1] = 0.5 * (q + cs - t1); A.dM[2] = 0.5 * (q - cs - t2);
+    A.dtrb = (cfl * b.dtl[c] * vol) * dmax_((double)b.iblank[c], 0.0);
+}
+
+__device__ __forceinline__ void unit_half_sum(const double* __restrict__ ssum, int N, int c, double r[3], double& len) {
+    r[0] = 0.5 * ssum[c]; r[1] = 0.5 * ssum[N + c]; r[2] = 0.5 * ssum[2 * N + c];
+    len = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+}
+
+// incoming change of basis for cell c.  DIR 0 (j sweep): scale by -cfl*dtl*vol (smoothers.F90:520)
+// and T_eta^-1; DIR 1 (i sweep): rotation (ri, rj); DIR 2 (k sweep): rotation (ri, rk).
+template <int DIR>
+__device__ __forceinline__ void dadi_pre(const BlockDev& b, int N, int c, double cfl, double f[5]) {
+    double dw1 = f[0], dw2 = f[1], dw3 = f[2], dw4 = f[3], dw5 = f[4];
+    if (DIR == 0) {
+        const double dt = -cfl * b.dtl[c] * b.vol[c];
+        dw1 *= dt; dw2 *= dt; dw3 *= dt; dw4 *= dt; dw5 *= dt;
+        const double gam = c_prm.gammaInf, gm1 = gam - 1.0;
+        const double rho = b.w[c], uvel = b.w[N + c], vvel = b.w[2 * N + c], wvel = b.w[3 * N + c];
+        const double cijk = sqrt(gam * b.p[c] / rho);
+        const double c2inv = 1.0 / (cijk * cijk);
+        const double xfact = 2.0 * cijk;
+        const double alphinv = sqrt(2.0) * cijk / rho;
+        const double uvw = 0.5 * (uvel * uvel + vvel * vvel + wvel * wvel);
+        double rj[3], len;
+        unit_half_sum(b.ssum + 3 * N, N, c, rj, len);
+        const double uu = uvel * rj[0] + vvel * rj[1] + wvel * rj[2];
+        const double rj1 = rj[0] / len, rj2 = rj[1] / len, rj3 = rj[2] / len;
+        double a1 = dw2 * uvel + dw3 * vvel + dw4 * wvel - dw5;
+        a1 = a1 * gm1 * c2inv + dw1 * (1.0 - uvw * gm1 * c2inv);
+        const double a2 = (rj2 * wvel - rj3 * vvel) * dw1 + rj3 * dw3 - rj2 * dw4;
+        const double a3 = (rj3 * uvel - rj1 * wvel) * dw1 + rj1 * dw4 - rj3 * dw2;
+        const double a4 = (rj1 * vvel - rj2 * uvel) * dw1 + rj2 * dw2 - rj1 * dw3;
+        double a5 = uvw * dw1 - uvel * dw2 - vvel * dw3 - wvel * dw4 + dw5;
+        a5 = a5 * gm1 * c2inv;
+        const double a6 = uu * dw1 / len - rj1 * dw2 - rj2 * dw3 - rj3 * dw4;
+        f[0] = a1 * rj1 + a2 / rho;
+        f[1] = a1 * rj2 + a3 / rho;
+        f[2] = a1 * rj3 + a4 / rho;
+        f[3] = (0.5 * a5 - a6 / xfact) * alphinv;
+        f[4] = (0.5 * a5 + a6 / xfact) * alphinv;
+    } else {
+        double ri[3], rx[3], li, lx;
+        unit_half_sum(b.ssum, N, c, ri, li);
+        unit_half_sum(b.ssum + (DIR == 1 ? 3 : 6) * N, N, c, rx, lx);
+        ri[0] /= li; ri[1] /= li; ri[2] /= li;
+        rx[0] /= lx; rx[1] /= lx; rx[2] /= lx;
+        const double sqrt2inv = 1.0 / sqrt(2.0);
+        const double a1 = ri[0] * rx[0] + ri[1] * rx[1] + ri[2] * rx[2];
+        double a2, a3, a4;
+        if (DIR == 1) {
+            a2 = ri[0] * rx[1] - rx[0] * ri[1];
+            a3 = ri[2] * rx[1] - rx[2] * ri[1];
+            a4 = ri[0] * rx[2] - rx[0] * ri[2];
+        } else {
+            a2 = rx[0] * ri[1] - ri[0] * rx[1];
+            a3 = rx[2] * ri[1] - ri[2] * rx[1];
+            a4 = rx[0] * ri[2] - ri[0] * rx[2];
+        }
+        const double a5 = (dw4 - dw5) * sqrt2inv;
+        const double a6 = (dw4 + dw5) * 0.5;
+        const double a7 = (a3 * dw1 + a4 * dw2 - a2 * dw3 - a5 * a1) * sqrt2inv;
+        f[0] = a1 * dw1 + a2 * dw2 + a4 * dw3 + a5 * a3;
+        f[1] = -a2 * dw1 + a1 * dw2 - a3 * dw3 + a5 * a4;
+        f[2] = -a4 * dw1 + a3 * dw2 + a1 * dw3 - a5 * a2;
+        f[3] = -a7 + a6;
+        f[4] = a7 + a6;
+    }
+}
+
+// T_zeta back to conservative variables and the -1/vol scaling (residuals.F90:1679-1746)
+__device__ __forceinline__ void dadi_post(const BlockDev& b, int N, int c, double f[5]) {
+    const double gam = c_prm.gammaInf;
+    const double rho = b.w[c], uvel = b.w[N + c], vvel = b.w[2 * N + c], wvel = b.w[3 * N + c];
+    double rk[3], len;
+    unit_half_sum(b.ssum + 6 * N, N, c, rk, len);
+    const double uu = uvel * rk[0] + vvel * rk[1] + wvel * rk[2];
+    const double rk1 = rk[0] / len, rk2 = rk[1] / len, rk3 = rk[2] / len;
+    const double uvw = 0.5 * (uvel * uvel + vvel * vvel + wvel * wvel);
+    const double cijkinv = sqrt(rho / gam / b.p[c]);
+    const double alph = rho * cijkinv * (1.0 / sqrt(2.0));
+    const double xfact = 2.0 / cijkinv;
+    const double ge = gam * b.w[4 * N + c] / rho - (gam - 1.0) * uvw;
+    const double dw1 = f[0], dw2 = f[1], dw3 = f[2], dw4 = f[3] * alph, dw5 = f[4] * alph;
+    const double a1 = dw1 * rk1 + dw2 * rk2 + dw3 * rk3 + dw4 + dw5;
+    const double a2 = 0.5 * xfact * (dw4 - dw5);
+    const double a3 = uvw * (rk1 * dw1 + rk2 * dw2 + rk3 * dw3);
+    const double volfact = -1.0 / b.vol[c];
+    f[0] = a1 * volfact;
+    f[1] = (a1 * uvel - rho * (rk3 * dw2 - rk2 * dw3) + a2 * rk1) * volfact;
+    f[2] = (a1 * vvel - rho * (rk1 * dw3 - rk3 * dw1) + a2 * rk2) * volfact;
+    f[3] = (a1 * wvel - rho * (rk2 * dw1 - rk1 * dw2) + a2 * rk3) * volfact;
+    f[4] = (a3 + rho * ((vvel * rk3 - wvel * rk2) * dw1 + (wvel * rk1 - uvel * rk3) * dw2 + (uvel * rk2 - vvel * rk1) * dw3) +
+            (ge + 0.5 * xfact * uu / len) * dw4 + (ge - 0.5 * xfact * uu / len) * dw5) * volfact;
+}
+
+// one thread = one grid line of nl owned cells along sd.  dd (3 coefficient sets) is kept in
+// scratch slots 0..2; ff lives in dw.
+template <int DIR>
+__global__ void __launch_bounds__(64) k_dadi_line(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2, double cfl) {
+    const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int q2 = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    if (q1 > n1 + 1 || q2 > n2 + 1) return;
+    const int N = (int)d.N;
+    const int base = q1 * s1 + q2 * s2;
+    const bool viscous = c_prm.equations != ADFB_EULER, eddy = c_prm.equations == ADFB_RANS;
+    const double* s = DIR == 0 ? b.sj : (DIR == 1 ? b.si : b.sk);
+    const double* slow = DIR == 2 ? b.sj : s;  // reference quirk, residuals.F90:1625-1627
+    double* ddA = b.scratch;
+    const int l = nl + 1;
+    const int typ[5] = {0, 0, 0, 1, 2};
+    if (nl <= 1) {  // `if (jl > 2)` guards: no implicit solve, but the changes of basis still apply
+        const int c = base + 2 * sd;
+        double f[5];
+#pragma unroll
+        for (int n = 0; n < 5; n++) f[n] = b.dw[n * N + c];
+        dadi_pre<DIR>(b, N, c, cfl, f);
+        if (DIR == 2) dadi_post(b, N, c, f);
+#pragma unroll
+        for (int n = 0; n < 5; n++) b.dw[n * N + c] = f[n];
+        return;
+    }
+    DadiCoef Am, A0, Ap;   // cells m-1, m, m+1
+    dadi_cell(b, N, base + 2 * sd, sd, s, slow, cfl, viscous, eddy, A0);
+    Am = A0;
+    double ddp[3] = {0.0, 0.0, 0.0}, ffp[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int m = 2; m <= l; m++) {
+        const int c = base + m * sd;
+        if (m < l) dadi_cell(b, N, c + sd, sd, s, slow, cfl, viscous, eddy, Ap);
+        double f[5];
+#pragma unroll
+        for (int n = 0; n < 5; n++) f[n] = b.dw[n * N + c];
+        dadi_pre<DIR>(b, N, c, cfl, f);
+        const double vt2 = A0.vt1 + A0.vt3;
+        double d0[3], bbm[3], ddm[3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const double cc = 1.0 + (vt2 + A0.dP[t] - A0.dM[t]) * A0.dtrb;
+            bbm[t] = (m > 2) ? (-Am.vt1 - Am.dP[t]) * A0.dtrb : 0.0;
+            const double dsup = (m < l) ? (-Ap.vt3 + Ap.dM[t]) * A0.dtrb : 0.0;
+            d0[t] = (m == 2) ? 1.0 / cc : 1.0 / (cc - bbm[t] * ddp[t]);
+            ddm[t] = dsup * d0[t];
+            ddA[t * N + c] = ddm[t];
+        }
+#pragma unroll
+        for (int n = 0; n < 5; n++) {
+            const int t = typ[n];
+            f[n] = (m == 2) ? f[n] * d0[t] : (f[n] - bbm[t] * ffp[n]) * d0[t];
+            ffp[n] = f[n];
+        }
+#pragma unroll
+        for (int t = 0; t < 3; t++) ddp[t] = ddm[t];
+        if (m < l) {
+#pragma unroll
+            for (int n = 0; n < 5; n++) b.dw[n * N + c] = f[n];
+        } else {  // last cell is final after the forward sweep
+            if (DIR == 2) dadi_post(b, N, c, f);
+#pragma unroll
+            for (int n = 0; n < 5; n++) b.dw[n * N + c] = f[n];
+        }
+        Am = A0; A0 = Ap;
+    }
+    // back substitution; ffp holds ff(l) in the sweep basis
+    for (int m = l - 1; m >= 2; m--) {
+        const int c = base + m * sd;
+        double f[5];
+#pragma unroll
+        for (int n = 0; n < 5; n++) {
+            f[n] = b.dw[n * N + c] - ddA[typ[n] * N + c] * ffp[n];
+            ffp[n] = f[n];
+        }
+        if (DIR == 2) dadi_post(b, N, c, f);
+#pragma unroll
+        for (int n = 0; n < 5; n++) b.dw[n * N + c] = f[n];
+    }
+}
+
+}  // namespace
+
+// computedwDADI including the -cfl*dtl*vol scaling of executeDADIStep (smoothers.F90:515-528)
+static int launch_dadi(const Dims& d, const BlockDev& b, const AdfbParams& prm, cudaStream_t s) {
+    const int sJ = (int)d.sJ, sK = (int)d.sK;
+    dim3 tb(32, 1);
+    {
+        dim3 g((d.nx + 31) / 32, d.nz);
+        KT_BEGIN(K_DADI, s);
+        k_dadi_line<0><<<g, tb, 0, s>>>(d, b, sJ, d.ny, 1, d.nx, sK, d.nz, prm.cfl);
+        KT_END(K_DADI, s);
+    }
+    {
+        dim3 g((d.ny + 31) / 32, d.nz);
+        KT_BEGIN(K_DADI, s);
+        k_dadi_line<1><<<g, tb, 0, s>>>(d, b, 1, d.nx, sJ, d.ny, sK, d.nz, prm.cfl);
+        KT_END(K_DADI, s);
+    }
+    {
+        dim3 g((d.nx + 31) / 32, d.ny);
+        KT_BEGIN(K_DADI, s);
+        k_dadi_line<2><<<g, tb, 0, s>>>(d, b, sK, d.nz, 1, d.nx, sJ, d.ny, prm.cfl);
+        KT_END(K_DADI, s);
+    }
+    return (int)cudaGetLastError();
+}

@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(256) k_rk_scale(Dims d, BlockDev b, double tmp
 // executeRkStage part 2 (smoothers.F90:298-354): conservative update -> primitive,
 // clips, then computeEtotBlock + computeLamViscosity + computeEddyViscosity fused.
 // scaleDt != 0 folds part 1 in (used when no residual averaging runs in between).
-__global__ void __launch_bounds__(256) k_rk_update(Dims d, BlockDev b, int scaleDt, double tmp, int nw) {
+// fromCurrent != 0: the DADI update, which starts from the current w, p instead of wn, pn (smoothers.F90:614-640)
+__global__ void __launch_bounds__(256) k_rk_update(Dims d, BlockDev b, int scaleDt, double tmp, int nw, int fromCurrent) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -219,15 +220,15 @@ __global__ void __launch_bounds__(256) k_rk_update(Dims d, BlockDev b, int scale
     double ovr = 1.0 / rho;
     const double v2 = u * u + v * v + w * w;
     const double dp = (ovr * b.p[c] + 0.0 - gm1 * (ovr * e - v2)) * dw[0] + gm1 * (dw[4] - u * dw[1] - v * dw[2] - w * dw[3]);
-    const double rn = b.wn[c];
+    const double rn = fromCurrent ? rho : b.wn[c];
     double rnew = rn - dw[0];
     rnew = dmax_(rnew, 1.e-4 * c_prm.rhoInf);
-    const double ru = rn * b.wn[N + c] - dw[1];
-    const double rv = rn * b.wn[2 * N + c] - dw[2];
-    const double rw = rn * b.wn[3 * N + c] - dw[3];
+    const double ru = rn * (fromCurrent ? u : b.wn[N + c]) - dw[1];
+    const double rv = rn * (fromCurrent ? v : b.wn[2 * N + c]) - dw[2];
+    const double rw = rn * (fromCurrent ? w : b.wn[3 * N + c]) - dw[3];
     ovr = 1.0 / rnew;
     const double un = ovr * ru, vn = ovr * rv, wn_ = ovr * rw;
-    double pnew = b.pn[c] - dp;
+    double pnew = (fromCurrent ? b.p[c] : b.pn[c]) - dp;
     pnew = dmax_(pnew, 1.e-4 * c_prm.pInfCorr);
     b.w[c] = rnew; b.w[N + c] = un; b.w[2 * N + c] = vn; b.w[3 * N + c] = wn_;
     b.p[c] = pnew;
@@ -370,12 +371,24 @@ static int launch_rk_update(const Dims& d, const BlockDev& b, const AdfbParams& 
         KT_END(K_RK, s);
         if (launch_residual_averaging(d, b, prm, s)) return 1;
         KT_BEGIN(K_RK, s);
-        k_rk_update<<<g, tb, 0, s>>>(d, b, 0, tmp, nw);
+        k_rk_update<<<g, tb, 0, s>>>(d, b, 0, tmp, nw, 0);
         KT_END(K_RK, s);
     } else {
         KT_BEGIN(K_RK, s);
-        k_rk_update<<<g, tb, 0, s>>>(d, b, 1, tmp, nw);
+        k_rk_update<<<g, tb, 0, s>>>(d, b, 1, tmp, nw, 0);
         KT_END(K_RK, s);
     }
+    return (int)cudaGetLastError();
+}
+
+// state update of executeDADIStep (smoothers.F90:595-650) after computedwDADI
+static int launch_dadi_update(const Dims& d, const BlockDev& b, const AdfbParams& prm, cudaStream_t s) {
+    if (prm.resAveraging == 1)  // rkStage == 0 in the DADI smoother: `alternate` never smooths (smoothers.F90:461-469)
+        if (launch_residual_averaging(d, b, prm, s)) return 1;
+    dim3 tb(32, 4, 2);
+    dim3 g((d.nx + 31) / 32, (d.ny + 3) / 4, (d.nz + 1) / 2);
+    KT_BEGIN(K_RK, s);
+    k_rk_update<<<g, tb, 0, s>>>(d, b, 0, 0.0, prm.equations == ADFB_RANS ? 6 : 5, 1);
+    KT_END(K_RK, s);
     return (int)cudaGetLastError();
 }

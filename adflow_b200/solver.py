@@ -109,6 +109,14 @@ class ADFLOW_B200:
         """RungeKuttaSmoother (src/solver/smoothers.F90:4)."""
         check(self.L.adfb_rk_cycle(level), "adfb_rk_cycle")
 
+    def dadiStep(self, level=1):
+        """executeDADIStep (src/solver/smoothers.F90:425)."""
+        check(self.L.adfb_dadi_step(level), "adfb_dadi_step")
+
+    def dadiCycle(self, n_subiterations=1, level=1):
+        """DADISmoother (src/solver/smoothers.F90:383)."""
+        check(self.L.adfb_dadi_cycle(level, n_subiterations), "adfb_dadi_cycle")
+
     def downloadResidual(self, blk):
         hb = self.blocks[blk]
         out = np.zeros(hb.d.box + (hb.nw,), order="F")

@@ -237,6 +237,12 @@ int adfb_smoother_residual(int level, int rkStage);
 int adfb_rk_stage(int level, int rkStage);
 /* RungeKuttaSmoother (src/solver/smoothers.F90:4-86); residual and dtl must be current */
 int adfb_rk_cycle(int level);
+/* executeDADIStep (src/solver/smoothers.F90:425-693): dw *= -cfl*dtl*vol, computedwDADI
+   (src/solver/residuals.F90:1062-1748: three line-implicit sweeps of 5 scalar tridiagonal
+   systems), primitive update, BCs, halo exchange */
+int adfb_dadi_step(int level);
+/* DADISmoother (src/solver/smoothers.F90:383-421) */
+int adfb_dadi_cycle(int level, int nSubiterations);
 
 #ifdef __cplusplus
 }

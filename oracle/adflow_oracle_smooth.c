@@ -316,3 +316,254 @@ void orc_rk_smoother(const OrcBlock* b, const AdfbParams* prm, int nSub, const A
     }
     orc_rk_stage(b, prm, prm->nRKStages, nSub, sf);
 }
+
+/* ------------------------------------------------------------------------ */
+/* tridiagsolve: src/solver/residuals.F90:1750-1783 (5 systems, rows 2..nn) */
+static void tridiagsolve(double* bb, double* cc, double* dd, double* ff, int nn, int ld) {
+    for (int n = 0; n < 5; n++) {
+        double* b = bb + n * ld; double* c = cc + n * ld; double* d = dd + n * ld; double* f = ff + n * ld;
+        int m = 2;
+        double d0 = 1. / c[m];
+        d[m] = d[m] * d0;
+        f[m] = f[m] * d0;
+        for (m = 3; m <= nn; m++) {
+            double d2 = b[m];
+            d0 = 1. / (c[m] - d2 * d[m - 1]);
+            f[m] = (f[m] - d2 * f[m - 1]) * d0;
+            d[m] = d[m] * d0;
+        }
+        for (m = nn - 1; m >= 2; m--) f[m] = f[m] - d[m] * f[m + 1];
+    }
+}
+
+/* one implicit sweep of computedwDADI along direction `sd` (j :1333-1405, i :1470-1538,
+   k :1605-1674).  s = face normals of the sweep direction; s2 = the array used in the
+   metric average of eps2: the k sweep uses sj for the lower face (reference quirk,
+   residuals.F90:1625-1627).  qq/cc are the scratch slots of the direction. */
+static void dadi_sweep(const OrcBlock* b, const AdfbParams* prm, Dims d, long sd, int nl, const double* s, const double* slow,
+                       const double* qq, const double* cc, const double* dual_dt, long s1, int n1, long s2, int n2) {
+    const double epsval = 0.08, fac = 1.05;
+    double cInf2 = prm->gammaInf * prm->pInf / prm->rhoInf;
+    int viscous = prm->equations != ADFB_EULER, eddy = prm->equations == ADFB_RANS;
+    int l = nl + 1, e = nl + 2; /* il, ie along the line */
+    if (l <= 2) return;
+    int ld = e + 2;
+    double* bb = (double*)calloc(5 * ld, sizeof(double)); double* ccv = (double*)calloc(5 * ld, sizeof(double));
+    double* dd = (double*)calloc(5 * ld, sizeof(double)); double* ff = (double*)calloc(5 * ld, sizeof(double));
+    double* metterm = (double*)calloc(ld, sizeof(double));
+    for (int q2 = 2; q2 <= n2 + 1; q2++) for (int q1 = 2; q1 <= n1 + 1; q1++) {
+        long base = q1 * s1 + q2 * s2;
+        for (int m = 1; m <= l; m++) {
+            long c = base + m * sd;
+            double mut = zero;
+            if (viscous) mut = b->rlv[c] + b->rlv[c + sd];
+            if (eddy) mut = mut + b->rev[c] + b->rev[c + sd];
+            double volfact = one / (b->vol[c] + b->vol[c + sd]);
+            double mt = s[c] * s[c] + s[d.N + c] * s[d.N + c] + s[2 * d.N + c] * s[2 * d.N + c];
+            metterm[m] = mt * mut * volfact;
+        }
+        for (int m = 2; m <= l; m++) {
+            long c = base + m * sd;
+            double viscTerm1 = metterm[m] / b->vol[c] / W(c, IRHO);
+            double viscTerm3 = metterm[m - 1] / b->vol[c] / W(c, IRHO);
+            double viscTerm2 = viscTerm1 + viscTerm3;
+            double volhalf = half / b->vol[c];
+            double r1 = volhalf * (s[c] + slow[c - sd]);
+            double r2 = volhalf * (s[d.N + c] + slow[d.N + c - sd]);
+            double r3 = volhalf * (s[2 * d.N + c] + slow[2 * d.N + c - sd]);
+            double mt = r1 * r1 + r2 * r2 + r3 * r3;
+            double eps2 = epsval * epsval * cInf2 * mt;
+            double q = qq[c], cs = cc[c];
+            double dP[5], dM[5];
+            dP[0] = half * (q + fac * sqrt(q * q + eps2)); dP[1] = dP[0]; dP[2] = dP[0];
+            dP[3] = half * (q + cs + fac * sqrt((q + cs) * (q + cs) + eps2));
+            dP[4] = half * (q - cs + fac * sqrt((q - cs) * (q - cs) + eps2));
+            dM[0] = half * (q - fac * sqrt(q * q + eps2)); dM[1] = dM[0]; dM[2] = dM[0];
+            dM[3] = half * (q + cs - fac * sqrt((q + cs) * (q + cs) + eps2));
+            dM[4] = half * (q - cs - fac * sqrt((q - cs) * (q - cs) + eps2));
+            for (int n = 0; n < 5; n++) {
+                bb[n * ld + m + 1] = -viscTerm1 - dP[n];
+                dd[n * ld + m - 1] = -viscTerm3 + dM[n];
+                ccv[n * ld + m] = viscTerm2 + dP[n] - dM[n];
+            }
+        }
+        for (int n = 0; n < 5; n++) {
+            bb[n * ld + e] = zero;
+            dd[n * ld + 1] = zero;
+            dd[n * ld + l] = zero; /* never set by the reference (read but unused) */
+            for (int m = 2; m <= l; m++) {
+                long c = base + m * sd;
+                double rb = dmax((double)b->iblank[c], zero);
+                bb[n * ld + m] = bb[n * ld + m] * dual_dt[c] * rb;
+                dd[n * ld + m] = dd[n * ld + m] * dual_dt[c] * rb;
+                ccv[n * ld + m] = one + ccv[n * ld + m] * dual_dt[c] * rb + zero + zero;
+                ff[n * ld + m] = DW(c, n);
+            }
+        }
+        tridiagsolve(bb, ccv, dd, ff, l, ld);
+        for (int n = 0; n < 5; n++) for (int m = 2; m <= l; m++) DW(base + m * sd, n) = ff[n * ld + m];
+    }
+    free(bb); free(ccv); free(dd); free(ff); free(metterm);
+}
+
+/* rotation between two characteristic bases (residuals.F90:1407-1448 with (ri,rj), :1543-1583 with (ri,rk)) */
+static void dadi_rotate(const OrcBlock* b, Dims d, const double* sa, long sda, const double* sb, long sdb, int second) {
+    const double sqrt2inv = one / sqrt(two);
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
+        long c = IDX(i, j, k);
+        double a_[3], b_[3];
+        for (int m = 0; m < 3; m++) { a_[m] = half * (sa[m * d.N + c] + sa[m * d.N + c - sda]); b_[m] = half * (sb[m * d.N + c] + sb[m * d.N + c - sdb]); }
+        double ra = sqrt(a_[0] * a_[0] + a_[1] * a_[1] + a_[2] * a_[2]);
+        a_[0] /= ra; a_[1] /= ra; a_[2] /= ra;
+        double rb = sqrt(b_[0] * b_[0] + b_[1] * b_[1] + b_[2] * b_[2]);
+        b_[0] /= rb; b_[1] /= rb; b_[2] /= rb;
+        double dw1 = DW(c, 0), dw2 = DW(c, 1), dw3 = DW(c, 2), dw4 = DW(c, 3), dw5 = DW(c, 4);
+        double a1, a2, a3, a4;
+        const double *ri = a_, *rx = b_;
+        a1 = ri[0] * rx[0] + ri[1] * rx[1] + ri[2] * rx[2];
+        if (!second) { /* (ri, rj) */
+            a2 = ri[0] * rx[1] - rx[0] * ri[1];
+            a3 = ri[2] * rx[1] - rx[2] * ri[1];
+            a4 = ri[0] * rx[2] - rx[0] * ri[2];
+        } else {       /* (ri, rk): a2 = rk1*ri2 - ri1*rk2 ... */
+            a2 = rx[0] * ri[1] - ri[0] * rx[1];
+            a3 = rx[2] * ri[1] - ri[2] * rx[1];
+            a4 = rx[0] * ri[2] - ri[0] * rx[2];
+        }
+        double a5 = (dw4 - dw5) * sqrt2inv;
+        double a6 = (dw4 + dw5) * half;
+        double a7 = (a3 * dw1 + a4 * dw2 - a2 * dw3 - a5 * a1) * sqrt2inv;
+        DW(c, 0) = a1 * dw1 + a2 * dw2 + a4 * dw3 + a5 * a3;
+        DW(c, 1) = -a2 * dw1 + a1 * dw2 - a3 * dw3 + a5 * a4;
+        DW(c, 2) = -a4 * dw1 + a3 * dw2 + a1 * dw3 - a5 * a2;
+        DW(c, 3) = -a7 + a6;
+        DW(c, 4) = a7 + a6;
+    }
+}
+
+/* computedwDADI: src/solver/residuals.F90:1062-1748 (steady; spectral_* are multiplied by
+   zero in the reference (:1269-1271) and therefore omitted) */
+void orc_compute_dw_dadi(const OrcBlock* b, const AdfbParams* prm) {
+    Dims d = dims_of(b);
+    double* qq_i = b->scratch, *qq_j = b->scratch + d.N, *qq_k = b->scratch + 2 * d.N;
+    double* cc_i = b->scratch + 3 * d.N, *cc_j = b->scratch + 4 * d.N, *cc_k = b->scratch + 5 * d.N;
+    double* dual_dt = b->scratch + 9 * d.N;
+    const double sqrt2 = sqrt(two);
+    double gam = prm->gammaInf;
+    const double *si = b->si, *sj = b->sj, *sk = b->sk;
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
+        long c = IDX(i, j, k);
+        dual_dt[c] = prm->cfl * b->dtl[c] * b->vol[c];
+    }
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
+        long c = IDX(i, j, k);
+        double volhalf = half / b->vol[c];
+        double cijk = sqrt(gam * b->p[c] / W(c, IRHO));
+        double ri1 = volhalf * (si[c] + si[c - 1]), ri2 = volhalf * (si[d.N + c] + si[d.N + c - 1]), ri3 = volhalf * (si[2 * d.N + c] + si[2 * d.N + c - 1]);
+        double rj1 = volhalf * (sj[c] + sj[c - d.sJ]), rj2 = volhalf * (sj[d.N + c] + sj[d.N + c - d.sJ]), rj3 = volhalf * (sj[2 * d.N + c] + sj[2 * d.N + c - d.sJ]);
+        double rk1 = volhalf * (sk[c] + sk[c - d.sK]), rk2 = volhalf * (sk[d.N + c] + sk[d.N + c - d.sK]), rk3 = volhalf * (sk[2 * d.N + c] + sk[2 * d.N + c - d.sK]);
+        qq_i[c] = ri1 * W(c, IVX) + ri2 * W(c, IVY) + ri3 * W(c, IVZ) - zero;
+        qq_j[c] = rj1 * W(c, IVX) + rj2 * W(c, IVY) + rj3 * W(c, IVZ) - zero;
+        qq_k[c] = rk1 * W(c, IVX) + rk2 * W(c, IVY) + rk3 * W(c, IVZ) - zero;
+        cc_i[c] = cijk * sqrt(ri1 * ri1 + ri2 * ri2 + ri3 * ri3);
+        cc_j[c] = cijk * sqrt(rj1 * rj1 + rj2 * rj2 + rj3 * rj3);
+        cc_k[c] = cijk * sqrt(rk1 * rk1 + rk2 * rk2 + rk3 * rk3);
+    }
+    /* T_eta^-1: conservative -> characteristic variables of the j direction (:1277-1327) */
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
+        long c = IDX(i, j, k);
+        double gm1 = gam - one;
+        double cijk = sqrt(gam * b->p[c] / W(c, IRHO));
+        double c2inv = one / (cijk * cijk);
+        double xfact = two * cijk;
+        double alphinv = sqrt2 * cijk / W(c, IRHO);
+        double uvel = W(c, IVX), vvel = W(c, IVY), wvel = W(c, IVZ);
+        double uvw = half * (uvel * uvel + vvel * vvel + wvel * wvel);
+        double rj1 = half * (sj[c] + sj[c - d.sJ]), rj2 = half * (sj[d.N + c] + sj[d.N + c - d.sJ]), rj3 = half * (sj[2 * d.N + c] + sj[2 * d.N + c - d.sJ]);
+        double rj = sqrt(rj1 * rj1 + rj2 * rj2 + rj3 * rj3);
+        double uu = uvel * rj1 + vvel * rj2 + wvel * rj3;
+        rj1 = rj1 / rj; rj2 = rj2 / rj; rj3 = rj3 / rj;
+        double dw1 = DW(c, 0), dw2 = DW(c, 1), dw3 = DW(c, 2), dw4 = DW(c, 3), dw5 = DW(c, 4);
+        double a1 = dw2 * uvel + dw3 * vvel + dw4 * wvel - dw5;
+        a1 = a1 * gm1 * c2inv + dw1 * (one - uvw * gm1 * c2inv);
+        double a2 = (rj2 * wvel - rj3 * vvel) * dw1 + rj3 * dw3 - rj2 * dw4;
+        double a3 = (rj3 * uvel - rj1 * wvel) * dw1 + rj1 * dw4 - rj3 * dw2;
+        double a4 = (rj1 * vvel - rj2 * uvel) * dw1 + rj2 * dw2 - rj1 * dw3;
+        double a5 = uvw * dw1 - uvel * dw2 - vvel * dw3 - wvel * dw4 + dw5;
+        a5 = a5 * gm1 * c2inv;
+        double a6 = uu * dw1 / rj - rj1 * dw2 - rj2 * dw3 - rj3 * dw4;
+        DW(c, 0) = a1 * rj1 + a2 / W(c, IRHO);
+        DW(c, 1) = a1 * rj2 + a3 / W(c, IRHO);
+        DW(c, 2) = a1 * rj3 + a4 / W(c, IRHO);
+        DW(c, 3) = (half * a5 - a6 / xfact) * alphinv;
+        DW(c, 4) = (half * a5 + a6 / xfact) * alphinv;
+    }
+    dadi_sweep(b, prm, d, d.sJ, d.ny, sj, sj, qq_j, cc_j, dual_dt, d.sI, d.nx, d.sK, d.nz);
+    dadi_rotate(b, d, si, d.sI, sj, d.sJ, 0);
+    dadi_sweep(b, prm, d, d.sI, d.nx, si, si, qq_i, cc_i, dual_dt, d.sJ, d.ny, d.sK, d.nz);
+    dadi_rotate(b, d, si, d.sI, sk, d.sK, 1);
+    dadi_sweep(b, prm, d, d.sK, d.nz, sk, sj, qq_k, cc_k, dual_dt, d.sI, d.nx, d.sJ, d.ny);
+    /* T_zeta: back to conservative variables (:1679-1731) and the -1/vol scaling (:1735-1746) */
+    const double sqrt2inv = one / sqrt2;
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
+        long c = IDX(i, j, k);
+        double uvel = W(c, IVX), vvel = W(c, IVY), wvel = W(c, IVZ);
+        double rk1 = half * (sk[c] + sk[c - d.sK]), rk2 = half * (sk[d.N + c] + sk[d.N + c - d.sK]), rk3 = half * (sk[2 * d.N + c] + sk[2 * d.N + c - d.sK]);
+        double rk = sqrt(rk1 * rk1 + rk2 * rk2 + rk3 * rk3);
+        double uu = uvel * rk1 + vvel * rk2 + wvel * rk3;
+        rk1 = rk1 / rk; rk2 = rk2 / rk; rk3 = rk3 / rk;
+        double uvw = half * (uvel * uvel + vvel * vvel + wvel * wvel);
+        double cijkinv = sqrt(W(c, IRHO) / gam / b->p[c]);
+        double alph = W(c, IRHO) * cijkinv * sqrt2inv;
+        double xfact = two / cijkinv;
+        double ge = gam * W(c, IRHOE) / W(c, IRHO) - (gam - one) * uvw;
+        double dw1 = DW(c, 0), dw2 = DW(c, 1), dw3 = DW(c, 2), dw4 = DW(c, 3) * alph, dw5 = DW(c, 4) * alph;
+        double a1 = dw1 * rk1 + dw2 * rk2 + dw3 * rk3 + dw4 + dw5;
+        double a2 = half * xfact * (dw4 - dw5);
+        double a3 = uvw * (rk1 * dw1 + rk2 * dw2 + rk3 * dw3);
+        DW(c, 0) = a1;
+        DW(c, 1) = a1 * uvel - W(c, IRHO) * (rk3 * dw2 - rk2 * dw3) + a2 * rk1;
+        DW(c, 2) = a1 * vvel - W(c, IRHO) * (rk1 * dw3 - rk3 * dw1) + a2 * rk2;
+        DW(c, 3) = a1 * wvel - W(c, IRHO) * (rk2 * dw1 - rk1 * dw2) + a2 * rk3;
+        DW(c, 4) = a3 + W(c, IRHO) * ((vvel * rk3 - wvel * rk2) * dw1 + (wvel * rk1 - uvel * rk3) * dw2 + (uvel * rk2 - vvel * rk1) * dw3) +
+                   (ge + half * xfact * uu / rk) * dw4 + (ge - half * xfact * uu / rk) * dw5;
+    }
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
+        long c = IDX(i, j, k);
+        double volfact = -one / b->vol[c];
+        for (int l = 0; l < 5; l++) DW(c, l) = DW(c, l) * volfact;
+    }
+}
+
+/* executeDADIStep: src/solver/smoothers.F90:425-693 (steady, fine level) */
+void orc_dadi_step(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf) {
+    Dims d = dims_of(b);
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
+        long c = IDX(i, j, k);
+        double dt = -prm->cfl * b->dtl[c] * b->vol[c];
+        for (int l = 0; l < 5; l++) DW(c, l) = DW(c, l) * dt;
+    }
+    orc_compute_dw_dadi(b, prm);
+    if (prm->resAveraging == 1) orc_residual_averaging(b, prm); /* rkStage = 0: `alternate` never smooths */
+    double gm1 = prm->gammaInf - one;
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
+        long c = IDX(i, j, k);
+        double ovr = one / W(c, IRHO);
+        double v2 = W(c, IVX) * W(c, IVX) + W(c, IVY) * W(c, IVY) + W(c, IVZ) * W(c, IVZ);
+        double dp = (ovr * b->p[c] + zero - gm1 * (ovr * W(c, IRHOE) - v2)) * DW(c, IRHO) +
+                    gm1 * (DW(c, IRHOE) - W(c, IVX) * DW(c, IMX) - W(c, IVY) * DW(c, IMY) - W(c, IVZ) * DW(c, IMZ));
+        double ru = W(c, IRHO) * W(c, IVX) - DW(c, IMX);
+        double rv = W(c, IRHO) * W(c, IVY) - DW(c, IMY);
+        double rw = W(c, IRHO) * W(c, IVZ) - DW(c, IMZ);
+        W(c, IRHO) = W(c, IRHO) - DW(c, IRHO);
+        W(c, IRHO) = dmax(W(c, IRHO), 1.e-4 * prm->rhoInf);
+        ovr = one / W(c, IRHO);
+        W(c, IVX) = ovr * ru; W(c, IVY) = ovr * rv; W(c, IVZ) = ovr * rw;
+        b->p[c] = b->p[c] - dp;
+        b->p[c] = dmax(b->p[c], 1.e-4 * prm->pInfCorr);
+    }
+    orc_etot(b, prm, 2, d.il, 2, d.jl, 2, d.kl);
+    orc_lam_viscosity(b, prm, 0);
+    orc_eddy_viscosity(b, prm, 0);
+    orc_apply_flow_bc(b, prm, nSub, sf, 1);
+}

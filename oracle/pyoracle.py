@@ -141,5 +141,12 @@ class Oracle:
         n, arr = self._subfaces()
         self.L.orc_rk_smoother(_p(self.ob), _p(self.prm), C.c_int(n), arr)
 
+    def dadi_step(self):
+        n, arr = self._subfaces()
+        self.L.orc_dadi_step(_p(self.ob), _p(self.prm), C.c_int(n), arr)
+
+    def compute_dw_dadi(self):
+        self.L.orc_compute_dw_dadi(_p(self.ob), _p(self.prm))
+
     def call(self, name, *args):
         getattr(self.L, name)(_p(self.ob), *args)
