@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "adfb_get_states", "adfb_set_states", "adfb_get_res", "adfb_state_size",
     "adfb_comm_set_pattern", "adfb_halo_exchange",
     "adfb_form_function", "adfb_mffd_set_base", "adfb_mffd_apply", "adfb_mffd_last_h",
-    "adfb_apply_bcs", "adfb_timestep", "adfb_smoother_residual", "adfb_rk_stage", "adfb_rk_cycle", "adfb_dadi_step", "adfb_dadi_cycle",
+    "adfb_apply_bcs", "adfb_timestep", "adfb_smoother_residual", "adfb_rk_stage", "adfb_rk_cycle", "adfb_dadi_step", "adfb_dadi_cycle", "adfb_sa_ddadi",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
     L.adfb_rk_cycle.argtypes = [ci]
     L.adfb_dadi_step.argtypes = [ci]
     L.adfb_dadi_cycle.argtypes = [ci, ci]
+    L.adfb_sa_ddadi.argtypes = [ci, ci]
     L.adfb_launch_count.restype = C.c_longlong
     L.adfb_stream.restype = C.c_void_p
     _lib = L

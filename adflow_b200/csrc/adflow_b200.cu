@@ -21,6 +21,7 @@
 #include "smoother_kernels.cuh"
 #include "halo_kernels.cuh"
 #include "dadi_kernels.cuh"
+#include "sa_kernels.cuh"
 
 namespace {
 
@@ -968,6 +969,24 @@ int adfb_dadi_cycle(int level, int nSubiterations) {
         if (adfb_smoother_residual(level, 0)) return 1;
     }
     return adfb_dadi_step(level);
+}
+
+// turbSolveDDADI, src/turbulence/turbAPI.F90:4-95 (Spalart-Allmaras)
+int adfb_sa_ddadi(int level, int nSubIterTurb) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_sa_ddadi: adfb_set_params has not been called");
+    if (g.prm.equations != ADFB_RANS) return fail("adfb_sa_ddadi: equations are not RANS");
+    if (nSubIterTurb < 1) return fail("adfb_sa_ddadi: nSubIterTurb must be >= 1");
+    for (int iter = 0; iter < nSubIterTurb; iter++) {
+        for (Block& b : g.blocks) {
+            if (!b.alive || b.level != level) continue;
+            if (launch_sa_block(b.d, b.dev, g.prm, b.subfaces, g.stream)) return fail("SA DD-ADI launch failed");
+        }
+        // whalo2(groundLevel, nt1, nt2, .false., .false., .true.), turbAPI.F90:91
+        if (halo_exchange_impl(level, 6, 6, 0, 1, false)) return 1;
+    }
+    CK(cudaGetLastError());
+    return 0;
 }
 
 // RungeKuttaSmoother, src/solver/smoothers.F90:4-86

@@ -117,6 +117,11 @@ class ADFLOW_B200:
         """DADISmoother (src/solver/smoothers.F90:383)."""
         check(self.L.adfb_dadi_cycle(level, n_subiterations), "adfb_dadi_cycle")
 
+    def turbSolveDDADI(self, n_sub_iter_turb=None, level=1):
+        """turbSolveDDADI (src/turbulence/turbAPI.F90:4)."""
+        n = self.prm.nSubiterTurb if n_sub_iter_turb is None else n_sub_iter_turb
+        check(self.L.adfb_sa_ddadi(level, n), "adfb_sa_ddadi")
+
     def downloadResidual(self, blk):
         hb = self.blocks[blk]
         out = np.zeros(hb.d.box + (hb.nw,), order="F")

@@ -241,6 +241,11 @@ int adfb_rk_cycle(int level);
    (src/solver/residuals.F90:1062-1748: three line-implicit sweeps of 5 scalar tridiagonal
    systems), primitive update, BCs, halo exchange */
 int adfb_dadi_step(int level);
+/* turbSolveDDADI (src/turbulence/turbAPI.F90:4-95): nSubIterTurb x { sa_block(.false.) on every
+   block = SA residual with its implicit diagonal, three diagonally dominant ADI sweeps
+   (saSolve, src/turbulence/sa.F90:717-1267), nuTilde update + clip, eddy viscosity,
+   turbulence BCs; whalo2(nt1, nt2, F, F, T) } */
+int adfb_sa_ddadi(int level, int nSubIterTurb);
 /* DADISmoother (src/solver/smoothers.F90:383-421) */
 int adfb_dadi_cycle(int level, int nSubiterations);
 

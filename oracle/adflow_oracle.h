@@ -76,6 +76,8 @@ void orc_residual_block(const OrcBlock* b, const AdfbParams* prm, double rFil);
 void orc_rk_stage(const OrcBlock* b, const AdfbParams* prm, int rkStage, int nSub, const AdfbSubface* sf);
 void orc_compute_dw_dadi(const OrcBlock* b, const AdfbParams* prm);
 void orc_dadi_step(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf);
+/* adflow_oracle_sa.c: one sa_block(resOnly=.false.) = residual + DD-ADI solve + rev + turbulence BCs */
+void orc_sa_block(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf);
 void orc_rk_smoother(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf);
 #ifdef __cplusplus
 }

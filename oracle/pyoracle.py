@@ -18,7 +18,8 @@ def build(force=False):
     src = os.path.join(_HERE, "adflow_oracle.c")
     stale = (not os.path.exists(so)) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(so)
-        for f in ("adflow_oracle.c", "adflow_oracle.h", "../include/adflow_b200.h")
+        for f in ("adflow_oracle.c", "adflow_oracle_smooth.c", "adflow_oracle_sa.c", "adflow_oracle.h", "orc_internal.h",
+                  "../include/adflow_b200.h")
     )
     if force or stale:
         subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
@@ -147,6 +148,10 @@ class Oracle:
 
     def compute_dw_dadi(self):
         self.L.orc_compute_dw_dadi(_p(self.ob), _p(self.prm))
+
+    def sa_block(self):
+        n, arr = self._subfaces()
+        self.L.orc_sa_block(_p(self.ob), _p(self.prm), C.c_int(n), arr)
 
     def call(self, name, *args):
         getattr(self.L, name)(_p(self.ob), *args)
