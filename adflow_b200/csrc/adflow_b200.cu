@@ -331,8 +331,8 @@ int adfb_set_params(const AdfbParams* prm) {
     drop_graphs();
     if (!prm) return fail("adfb_set_params: null");
     if (prm->equations < ADFB_EULER || prm->equations > ADFB_RANS) return fail("adfb_set_params: bad equations %d", prm->equations);
-    if (prm->spaceDiscr != ADFB_DISS_SCALAR)
-        return fail("adfb_set_params: spaceDiscr %d not supported on device yet (scalar JST only)", prm->spaceDiscr);
+    if (prm->spaceDiscr != ADFB_DISS_SCALAR && prm->spaceDiscr != ADFB_DISS_MATRIX && prm->spaceDiscr != ADFB_UPWIND)
+        return fail("adfb_set_params: unknown spaceDiscr %d", prm->spaceDiscr);
     if (prm->useRotationSA && prm->turbProd == ADFB_PROD_VORTICITY)
         return fail("adfb_set_params: useRotationSA with vorticity production reads an unset strainMag2 in the "
                     "reference (src/turbulence/sa.F90:273); unsupported");

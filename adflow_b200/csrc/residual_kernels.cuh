@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
     const double rho = b.w[c], p = b.p[c];
     // p / rho**gamma as p*exp(-gamma*log(rho)): |gamma*log(rho)| = O(1), so the result agrees
     // with pow() to a few ulp at less than half the FP64 instructions
-    b.ss[c] = (c_prm.equations == ADFB_EULER) ? p : p * exp(-gam * log(rho));
+    if (c_prm.spaceDiscr == ADFB_DISS_SCALAR) b.ss[c] = (c_prm.equations == ADFB_EULER) ? p : p * exp(-gam * log(rho));
     if (i < 1 || i > d.ie || j < 1 || j > d.je || k < 1 || k > d.ke) return;
     const bool viscous = c_prm.equations != ADFB_EULER;
     if (viscous) b.aa[c] = gam * p / rho;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(NODAL_TPB, NODAL_MINB) k_nodal(Dims d, BlockDe
     if (i > d.ie || j > d.je || k > d.ke) return;
     const int N = (int)d.N, sJ = (int)d.sJ, sK = (int)d.sK;
     const int c = i + sJ * j + sK * k;
-    {
+    if (c_prm.spaceDiscr == ADFB_DISS_SCALAR) {
         const double sslim = (c_prm.equations == ADFB_EULER) ? 0.001 * c_prm.pInfCorr
                                                             : 0.001 * c_prm.pInfCorr / pow(c_prm.rhoInf, c_prm.gammaInf);
         const double* ss = b.ss;
@@ -212,6 +212,17 @@ __global__ void __launch_bounds__(NODAL_TPB, NODAL_MINB) k_nodal(Dims d, BlockDe
         b.dss[c] = fabs((ss[c + 1] - 2.0 * s0 + ss[c - 1]) / (ss[c + 1] + 2.0 * s0 + ss[c - 1] + sslim));
         b.dss[N + c] = fabs((ss[c + sJ] - 2.0 * s0 + ss[c - sJ]) / (ss[c + sJ] + 2.0 * s0 + ss[c - sJ] + sslim));
         b.dss[2 * N + c] = fabs((ss[c + sK] - 2.0 * s0 + ss[c - sK]) / (ss[c + sK] + 2.0 * s0 + ss[c - sK] + sslim));
+    } else if (c_prm.spaceDiscr == ADFB_DISS_MATRIX) {
+        // pressure sensor with the omega blend, inviscidDissFluxMatrix blockette.F90:2495-2512
+        const double plim = 0.001 * c_prm.pInfCorr;
+        const double* p = b.p;
+        const double p0 = p[c];
+        const int sdv[3] = {1, sJ, sK};
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const double pp = p[c + sdv[m]], pm = p[c - sdv[m]];
+            b.dss[m * N + c] = fabs((pp - 2.0 * p0 + pm) / (0.5 * (pp + 2.0 * p0 + pm) + 0.5 * (fabs(pp - p0) + fabs(p0 - pm)) + plim));
+        }
     }
     if (!doGrad || i > d.il || j > d.jl || k > d.kl) return;
     // the 8 cells around the node: bit0 = +i, bit1 = +j, bit2 = +k
@@ -270,7 +281,7 @@ __device__ __forceinline__ CellState load_cell(const BlockDev& b, int N, int c) 
     return s;
 }
 
-template <bool VISCOUS>
+template <bool VISCOUS, int DISC>
 __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int sd, int t1, int t2, int dir,
                                           const double* __restrict__ s, int8_t por, const double* __restrict__ rad,
                                           const double* __restrict__ dss, const CellState& m, double rFil, int doDiss,
@@ -296,7 +307,7 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
     }
 #pragma unroll
     for (int l = 0; l < 5; l++) fd[l] = 0.0;
-    if (doDiss && c_prm.spaceDiscr == ADFB_DISS_SCALAR) {  // scalar JST
+    if (DISC == ADFB_DISS_SCALAR && doDiss) {  // scalar JST
         const CellState mm = load_cell(b, N, c - sd), qq = load_cell(b, N, cp + sd);
         const double fis2 = rFil * c_prm.vis2, fis4 = rFil * c_prm.vis4;
         const double ppor = (por == ADFB_NORMALFLUX) ? 0.5 : 0.0;
@@ -313,6 +324,132 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
         fd[3] = dis2 * ddw - dis4 * (qq.w * qq.r - mm.w * mm.r - 3.0 * ddw);
         ddw = (q.e + q.p) - (m.e + m.p);
         fd[4] = dis2 * ddw - dis4 * ((qq.e + qq.p) - (mm.e + mm.p) - 3.0 * ddw);
+    }
+    if (DISC == ADFB_DISS_MATRIX && doDiss) {  // matrix dissipation, blockette.F90:2515-2680
+        const CellState mm = load_cell(b, N, c - sd), qq = load_cell(b, N, cp + sd);
+        const double gam = c_prm.gammaInf;
+        const double fis2 = rFil * c_prm.vis2, fis4 = rFil * c_prm.vis4;
+        const double ppor = (por == ADFB_NORMALFLUX) ? 1.0 : 0.0;
+        const double dis2 = ppor * fis2 * dmin_(0.25, dmax_(dss[c], dss[cp]));
+        const double dis4 = dmax_(ppor * fis4 - dis2, 0.0);
+        double ddw = q.r - m.r;
+        const double dr = dis2 * ddw - dis4 * (qq.r - mm.r - 3.0 * ddw);
+        ddw = q.r * q.u - m.r * m.u;
+        const double dru = dis2 * ddw - dis4 * (qq.r * qq.u - mm.r * mm.u - 3.0 * ddw);
+        ddw = q.r * q.v - m.r * m.v;
+        const double drv = dis2 * ddw - dis4 * (qq.r * qq.v - mm.r * mm.v - 3.0 * ddw);
+        ddw = q.r * q.w - m.r * m.w;
+        const double drw = dis2 * ddw - dis4 * (qq.r * qq.w - mm.r * mm.w - 3.0 * ddw);
+        ddw = q.e - m.e;
+        const double dre = dis2 * ddw - dis4 * (qq.e - mm.e - 3.0 * ddw);
+        const double gm1 = gam - 1.0, ovgm1 = 1.0 / gm1;
+        const double uAvg = 0.5 * (q.u + m.u), vAvg = 0.5 * (q.v + m.v), wAvg = 0.5 * (q.w + m.w);
+        const double a2Avg = 0.5 * (gam * q.p / q.r + gam * m.p / m.r);
+        const double area = sqrt(s1 * s1 + s2 * s2 + s3 * s3);
+        const double tmp = 1.0 / dmax_(1.e-25, area);
+        const double sx = s1 * tmp, sy = s2 * tmp, sz = s3 * tmp;
+        const double alphaAvg = 0.5 * (uAvg * uAvg + vAvg * vAvg + wAvg * wAvg);
+        const double hAvg = alphaAvg + ovgm1 * a2Avg;
+        const double aAvg = sqrt(a2Avg);
+        const double unAvg = uAvg * sx + vAvg * sy + wAvg * sz;
+        const double ovaAvg = 1.0 / aAvg, ova2Avg = 1.0 / a2Avg;
+        double lam1 = fabs(unAvg + aAvg), lam2 = fabs(unAvg - aAvg), lam3 = fabs(unAvg);
+        const double rrad = lam3 + aAvg;
+        lam1 = dmax_(lam1, 0.25 * rrad) * area;
+        lam2 = dmax_(lam2, 0.25 * rrad) * area;
+        lam3 = dmax_(lam3, 0.025 * rrad) * area;
+        const double abv1 = 0.5 * (lam1 + lam2), abv2 = 0.5 * (lam1 - lam2), abv3 = abv1 - lam3;
+        const double abv4 = gm1 * (alphaAvg * dr - uAvg * dru - vAvg * drv - wAvg * drw + dre);
+        const double abv5 = sx * dru + sy * drv + sz * drw - unAvg * dr;
+        const double abv6 = abv3 * abv4 * ova2Avg + abv2 * abv5 * ovaAvg;
+        const double abv7 = abv2 * abv4 * ovaAvg + abv3 * abv5;
+        fd[0] = lam3 * dr + abv6;
+        fd[1] = lam3 * dru + uAvg * abv6 + sx * abv7;
+        fd[2] = lam3 * drv + vAvg * abv6 + sy * abv7;
+        fd[3] = lam3 * drw + wAvg * abv6 + sz * abv7;
+        fd[4] = lam3 * dre + hAvg * abv6 + unAvg * abv7;
+    }
+    if (DISC == ADFB_UPWIND && doDiss) {  // Roe / MUSCL, blockette.F90:3341-4363
+        const CellState mm = load_cell(b, N, c - sd), qq = load_cell(b, N, cp + sd);
+        const double gam = c_prm.gammaInf;
+        double left[5] = {m.r, m.u, m.v, m.w, m.p}, right[5] = {q.r, q.u, q.v, q.w, q.p};
+        if (c_prm.limiter != ADFB_LIM_FIRSTORDER) {
+            const double du1[5] = {m.r - mm.r, m.u - mm.u, m.v - mm.v, m.w - mm.w, m.p - mm.p};
+            const double du2[5] = {q.r - m.r, q.u - m.u, q.v - m.v, q.w - m.w, q.p - m.p};
+            const double du3[5] = {qq.r - q.r, qq.u - q.u, qq.v - q.v, qq.w - q.w, qq.p - q.p};
+            const double kappa = c_prm.kappaCoef;
+            const double omk = 0.25 * (1.0 - kappa), opk = 0.25 * (1.0 + kappa);
+            const double factMinmod = (3.0 - kappa) / dmax_(1.e-10, 1.0 - kappa);
+#pragma unroll
+            for (int l = 0; l < 5; l++) {
+                double dl, dr_;
+                if (c_prm.limiter == ADFB_LIM_NONE) {
+                    dl = omk * du1[l] + opk * du2[l];
+                    dr_ = -omk * du3[l] - opk * du2[l];
+                } else {
+                    const double tmp = 1.0 / copysign(dmax_(fabs(du2[l]), 1.e-10), du2[l]);
+                    double rl1 = dmax_(0.0, du2[l] / copysign(dmax_(fabs(du1[l]), 1.e-10), du1[l]));
+                    double rl2 = dmax_(0.0, du1[l] * tmp);
+                    double rr1 = dmax_(0.0, du3[l] * tmp);
+                    double rr2 = dmax_(0.0, du2[l] / copysign(dmax_(fabs(du3[l]), 1.e-10), du3[l]));
+                    if (c_prm.limiter == ADFB_LIM_VANALBADA) {
+                        rl1 = rl1 * (rl1 + 1.0) / (rl1 * rl1 + 1.0); rl2 = rl2 * (rl2 + 1.0) / (rl2 * rl2 + 1.0);
+                        rr1 = rr1 * (rr1 + 1.0) / (rr1 * rr1 + 1.0); rr2 = rr2 * (rr2 + 1.0) / (rr2 * rr2 + 1.0);
+                    } else {
+                        rl1 = dmin_(1.0, factMinmod * rl1); rl2 = dmin_(1.0, factMinmod * rl2);
+                        rr1 = dmin_(1.0, factMinmod * rr1); rr2 = dmin_(1.0, factMinmod * rr2);
+                    }
+                    dl = omk * rl1 * du1[l] + opk * rl2 * du2[l];
+                    dr_ = -opk * rr1 * du2[l] - omk * rr2 * du3[l];
+                }
+                left[l] = dl + left[l];
+                right[l] = dr_ + right[l];
+            }
+        }
+        double porFlux = 0.5 * rFil;
+        if (por == ADFB_NOFLUX || por == ADFB_BOUNDFLUX) porFlux = 0.0;
+        const double gm1 = gam - 1.0, ovgm1 = 1.0 / gm1;
+        const double z1l = sqrt(left[0]), z1r = sqrt(right[0]);
+        double tmp = 1.0 / (z1l + z1r);
+        const double Etl = left[0] * (ovgm1 * left[4] / left[0] + 0.5 * (left[1] * left[1] + left[2] * left[2] + left[3] * left[3]));
+        const double Etr = right[0] * (ovgm1 * right[4] / right[0] + 0.5 * (right[1] * right[1] + right[2] * right[2] + right[3] * right[3]));
+        const double dr = right[0] - left[0];
+        const double dru = right[0] * right[1] - left[0] * left[1];
+        const double drv = right[0] * right[2] - left[0] * left[2];
+        const double drw = right[0] * right[3] - left[0] * left[3];
+        const double drE = Etr - Etl;
+        const double uAvg = tmp * (z1l * left[1] + z1r * right[1]);
+        const double vAvg = tmp * (z1l * left[2] + z1r * right[2]);
+        const double wAvg = tmp * (z1l * left[3] + z1r * right[3]);
+        const double hAvg = tmp * ((Etl + left[4]) / z1l + (Etr + right[4]) / z1r);
+        const double area = sqrt(s1 * s1 + s2 * s2 + s3 * s3);
+        tmp = 1.0 / dmax_(1.e-25, area);
+        const double sx = s1 * tmp, sy = s2 * tmp, sz = s3 * tmp;
+        const double alphaAvg = 0.5 * (uAvg * uAvg + vAvg * vAvg + wAvg * wAvg);
+        const double a2Avg = fabs(gm1 * (hAvg - alphaAvg));
+        const double aAvg = sqrt(a2Avg);
+        double unAvg = uAvg * sx + vAvg * sy + wAvg * sz;
+        const double ovaAvg = 1.0 / aAvg, ova2Avg = 1.0 / a2Avg;
+        if (por == ADFB_BOUNDFLUX) unAvg = 0.0;
+        const double eta = 0.5 * (fabs((left[1] - right[1]) * sx + (left[2] - right[2]) * sy + (left[3] - right[3]) * sz) +
+                                  fabs(sqrt(gam * left[4] / left[0]) - sqrt(gam * right[4] / right[0])));
+        double lam1 = fabs(unAvg + aAvg), lam2 = fabs(unAvg - aAvg), lam3 = fabs(unAvg);
+        tmp = 2.0 * eta;
+        if (lam1 < tmp) lam1 = eta + 0.25 * lam1 * lam1 / eta;
+        if (lam2 < tmp) lam2 = eta + 0.25 * lam2 * lam2 / eta;
+        if (lam3 < tmp) lam3 = eta + 0.25 * lam3 * lam3 / eta;
+        lam1 = lam1 * area; lam2 = lam2 * area; lam3 = lam3 * area;
+        const double abv1 = 0.5 * (lam1 + lam2), abv2 = 0.5 * (lam1 - lam2), abv3 = abv1 - lam3;
+        const double abv4 = gm1 * (alphaAvg * dr - uAvg * dru - vAvg * drv - wAvg * drw + drE);
+        const double abv5 = sx * dru + sy * drv + sz * drw - unAvg * dr;
+        const double abv6 = abv3 * abv4 * ova2Avg + abv2 * abv5 * ovaAvg;
+        const double abv7 = abv2 * abv4 * ovaAvg + abv3 * abv5;
+        // reference: flux = -porFlux*(...); fw(c) += flux; fw(cp) -= flux  ==  fd = +porFlux*(...)
+        fd[0] = porFlux * (lam3 * dr + abv6);
+        fd[1] = porFlux * (lam3 * dru + uAvg * abv6 + sx * abv7);
+        fd[2] = porFlux * (lam3 * drv + vAvg * abv6 + sy * abv7);
+        fd[3] = porFlux * (lam3 * drw + wAvg * abv6 + sz * abv7);
+        fd[4] = porFlux * (lam3 * drE + hAvg * abv6 + unAvg * abv7);
     }
     if (VISCOUS && doVisc) {
         double porv = 0.5 * rFil;
@@ -371,7 +508,7 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
 // k_faces: plus faces of cell (i,j,k), i 1:il, j 1:jl, k 1:kl.  MERGED: one array G = fc - fd per
 // face (net outflow of the low cell) -> flux[dir*5 + l]; otherwise fc -> flux[dir*10 + l],
 // fd -> flux[dir*10 + 5 + l] (smoother path: fw persists between RK stages).
-template <bool VISCOUS, bool MERGED>
+template <bool VISCOUS, bool MERGED, int DISC>
 __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDev b, double rFil, int doVisc, int doDiss) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
@@ -383,7 +520,7 @@ __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDe
     double fc[5], fd[5];
     const bool oi = i >= 2, oj = j >= 2, ok = k >= 2;
     if (oj && ok) {
-        face_flux<VISCOUS>(b, N, c, 1, sJ, sK, 0, b.si, b.porI[c], b.radI, b.dss, m, rFil, doDiss, doVisc, fc, fd);
+        face_flux<VISCOUS, DISC>(b, N, c, 1, sJ, sK, 0, b.si, b.porI[c], b.radI, b.dss, m, rFil, doDiss, doVisc, fc, fd);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
             if (MERGED) b.flux[l * N + c] = fc[l] - fd[l];
@@ -391,7 +528,7 @@ __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDe
         }
     }
     if (oi && ok) {
-        face_flux<VISCOUS>(b, N, c, sJ, 1, sK, 1, b.sj, b.porJ[c], b.radJ, b.dss + N, m, rFil, doDiss, doVisc, fc, fd);
+        face_flux<VISCOUS, DISC>(b, N, c, sJ, 1, sK, 1, b.sj, b.porJ[c], b.radJ, b.dss + N, m, rFil, doDiss, doVisc, fc, fd);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
             if (MERGED) b.flux[(5 + l) * N + c] = fc[l] - fd[l];
@@ -399,7 +536,7 @@ __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDe
         }
     }
     if (oi && oj) {
-        face_flux<VISCOUS>(b, N, c, sK, 1, sJ, 2, b.sk, b.porK[c], b.radK, b.dss + 2 * N, m, rFil, doDiss, doVisc, fc, fd);
+        face_flux<VISCOUS, DISC>(b, N, c, sK, 1, sJ, 2, b.sk, b.porK[c], b.radK, b.dss + 2 * N, m, rFil, doDiss, doVisc, fc, fd);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
             if (MERGED) b.flux[(10 + l) * N + c] = fc[l] - fd[l];
@@ -647,13 +784,17 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         dim3 g((d.il + tr.x - 1) / tr.x, (d.jl + tr.y - 1) / tr.y, (d.kl + tr.z - 1) / tr.z);
         const bool merged = !persistFw;
         KT_BEGIN(K_RESID, stream);
-        if (viscous) {
-            if (merged) k_faces<true, true><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
-            else k_faces<true, false><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
-        } else {
-            if (merged) k_faces<false, true><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
-            else k_faces<false, false><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
-        }
+#define ADFB_LAUNCH_FACES(V, M, D) k_faces<V, M, D><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss)
+#define ADFB_FACES_DISC(V, M)                                              \
+    do {                                                                   \
+        if (prm.spaceDiscr == ADFB_DISS_SCALAR) ADFB_LAUNCH_FACES(V, M, ADFB_DISS_SCALAR); \
+        else if (prm.spaceDiscr == ADFB_DISS_MATRIX) ADFB_LAUNCH_FACES(V, M, ADFB_DISS_MATRIX); \
+        else ADFB_LAUNCH_FACES(V, M, ADFB_UPWIND);                          \
+    } while (0)
+        if (viscous) { if (merged) ADFB_FACES_DISC(true, true); else ADFB_FACES_DISC(true, false); }
+        else { if (merged) ADFB_FACES_DISC(false, true); else ADFB_FACES_DISC(false, false); }
+#undef ADFB_FACES_DISC
+#undef ADFB_LAUNCH_FACES
         KT_END(K_RESID, stream);
         dim3 g2((d.nx + tb.x - 1) / tb.x, (d.ny + tb.y - 1) / tb.y, (d.nz + tb.z - 1) / tb.z);
         KT_BEGIN(K_DIV, stream);

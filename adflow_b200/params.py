@@ -213,7 +213,7 @@ def make_params(options=None, mach=0.8, alpha_deg=1.8, P=20000.0, T=220.0, R=287
     prm.useRotationSA = int(opt["useRotationSA"])
     prm.approxSA = int(opt["useApproxSA"])
     prm.secondOrdTurb = int(opt["turbulenceOrder"] == "second order")
-    prm.limiter = {"no limiter": 1, "van Albada": 2, "minmod": 3}[opt["limiter"]]
+    prm.limiter = {"first order": 0, "no limiter": 1, "van Albada": 2, "minmod": 3}[opt["limiter"]]
     prm.resAveraging = {"never": 0, "always": 1, "alternate": 2}[opt["resAveraging"]]
     prm.nSubiterTurb = opt["nSubiterTurb"]
     prm.wallBCConstantPressure = int(opt["viscWallTreatment"] == "constant pressure extrapolation")

@@ -50,7 +50,7 @@ enum { ADFB_DISS_SCALAR = 1, ADFB_DISS_MATRIX = 2, ADFB_UPWIND = 4 };
 /* turbProd */
 enum { ADFB_PROD_STRAIN = 1, ADFB_PROD_VORTICITY = 2 };
 /* limiter for the upwind scheme (inputDiscretization%limiter) */
-enum { ADFB_LIM_NONE = 1, ADFB_LIM_VANALBADA = 2, ADFB_LIM_MINMOD = 3 };
+enum { ADFB_LIM_FIRSTORDER = 0, ADFB_LIM_NONE = 1, ADFB_LIM_VANALBADA = 2, ADFB_LIM_MINMOD = 3 };
 /* porosity codes, src/modules/constants.F90:28-30 */
 enum { ADFB_NOFLUX = -1, ADFB_BOUNDFLUX = 0, ADFB_NORMALFLUX = 1 };
 /* BC types handled on device (subset of src/modules/constants.F90:257-282) */

@@ -653,6 +653,8 @@ void orc_residual_core(const OrcBlock* b, const AdfbParams* prm, unsigned flags,
     if (flowRes) {
         orc_central_flux(b, prm);
         if (prm->spaceDiscr == ADFB_DISS_SCALAR) orc_diss_scalar(b, prm, rFil);
+        else if (prm->spaceDiscr == ADFB_DISS_MATRIX) orc_diss_matrix(b, prm, rFil);
+        else if (prm->spaceDiscr == ADFB_UPWIND) orc_upwind_flux(b, prm, rFil);
         if (viscous && fabs(rFil) > thresholdReal) {
             orc_speed_of_sound(b, prm);
             orc_nodal_gradients(b);

@@ -76,6 +76,9 @@ void orc_residual_block(const OrcBlock* b, const AdfbParams* prm, double rFil);
 void orc_rk_stage(const OrcBlock* b, const AdfbParams* prm, int rkStage, int nSub, const AdfbSubface* sf);
 void orc_compute_dw_dadi(const OrcBlock* b, const AdfbParams* prm);
 void orc_dadi_step(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf);
+/* adflow_oracle_fluxes.c: alternative dissipation schemes (same calling convention as orc_diss_scalar) */
+void orc_diss_matrix(const OrcBlock* b, const AdfbParams* prm, double rFil);
+void orc_upwind_flux(const OrcBlock* b, const AdfbParams* prm, double rFil);
 /* adflow_oracle_sa.c: one sa_block(resOnly=.false.) = residual + DD-ADI solve + rev + turbulence BCs */
 void orc_sa_block(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf);
 void orc_rk_smoother(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf);

@@ -257,7 +257,9 @@ void orc_residual_block(const OrcBlock* b, const AdfbParams* prm, double rFil) {
     orc_central_flux(b, prm);
     if (fabs(rFil) >= thresholdReal) {
         /* orc_diss_scalar recomputes ss/dss and scales fw by (1-rFil) like fluxes.F90:1193 */
-        orc_diss_scalar(b, prm, rFil);
+        if (prm->spaceDiscr == ADFB_DISS_SCALAR) orc_diss_scalar(b, prm, rFil);
+        else if (prm->spaceDiscr == ADFB_DISS_MATRIX) orc_diss_matrix(b, prm, rFil);
+        else orc_upwind_flux(b, prm, rFil);
         if (viscous) {
             orc_speed_of_sound(b, prm);
             orc_nodal_gradients(b);

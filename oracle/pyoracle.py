@@ -18,7 +18,7 @@ def build(force=False):
     src = os.path.join(_HERE, "adflow_oracle.c")
     stale = (not os.path.exists(so)) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(so)
-        for f in ("adflow_oracle.c", "adflow_oracle_smooth.c", "adflow_oracle_sa.c", "adflow_oracle.h", "orc_internal.h",
+        for f in ("adflow_oracle.c", "adflow_oracle_smooth.c", "adflow_oracle_sa.c", "adflow_oracle_fluxes.c", "adflow_oracle.h", "orc_internal.h",
                   "../include/adflow_b200.h")
     )
     if force or stale:

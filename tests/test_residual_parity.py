@@ -80,6 +80,12 @@ def test_flow_only_and_turb_only(cuda_lib):
     {"turbulenceProduction": "vorticity"},
     {"useft2SA": False},
     {"vis2": 0.5, "vis4": 1.0 / 64, "dissipationScalingExponent": 2.0 / 3.0},
+    {"discretization": "central plus matrix dissipation"},
+    {"discretization": "central plus matrix dissipation", "equationType": "Euler"},
+    {"discretization": "upwind"},
+    {"discretization": "upwind", "limiter": "minmod"},
+    {"discretization": "upwind", "limiter": "no limiter", "equationType": "laminar NS"},
+    {"discretization": "upwind", "limiter": "first order", "equationType": "Euler"},
 ])
 def test_option_variants(cuda_lib, options):
     prm, hb = case(14, 11, 10, options)
