@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "adfb_download_residual", "adfb_download_intermed", "adfb_residual", "adfb_norms", "adfb_synchronize",
     "adfb_get_states", "adfb_set_states", "adfb_get_res", "adfb_state_size",
     "adfb_comm_set_pattern", "adfb_halo_exchange",
-    "adfb_form_function", "adfb_mffd_set_base", "adfb_mffd_apply", "adfb_mffd_last_h",
+    "adfb_reference_shock_sensor", "adfb_form_function", "adfb_mffd_set_base", "adfb_mffd_apply", "adfb_mffd_last_h",
     "adfb_apply_bcs", "adfb_timestep", "adfb_smoother_residual", "adfb_rk_stage", "adfb_rk_cycle", "adfb_dadi_step", "adfb_dadi_cycle", "adfb_sa_ddadi",
 ]
 
@@ -71,6 +71,7 @@ def load():
     for fn in (L.adfb_get_states, L.adfb_set_states, L.adfb_get_res):
         fn.argtypes = [vp, C.c_longlong]
     L.adfb_state_size.restype = C.c_longlong
+    L.adfb_reference_shock_sensor.argtypes = [ci]
     L.adfb_form_function.argtypes = [vp, vp, C.c_longlong]
     L.adfb_mffd_set_base.argtypes = [vp, C.c_longlong]
     L.adfb_mffd_apply.argtypes = [vp, vp, C.c_longlong, C.c_double]

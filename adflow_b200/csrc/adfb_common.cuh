@@ -51,6 +51,7 @@ struct BlockDev {
     double *ovol;                       // 1: 1/(8-cell volume sum) at nodes
     double *vn;                         // 12: cell-centre unit vector + 1/length per face direction
     double *flux;                       // 30: face fluxes (15 used in merged mode)
+    double *shock;                      // frozen shock sensor (referenceShockSensor)
 };
 
 // single translation unit (adflow_b200.cu includes every *_kernels.cuh)

@@ -369,7 +369,7 @@ int adfb_block_create(int blk, int level, int nx, int ny, int nz, int nw, int ri
     rc |= dalloc(b, &v.dtl, N); rc |= dalloc(b, &v.grad, N * 12);
     rc |= dalloc(b, &v.wn, N * 5); rc |= dalloc(b, &v.pn, N); rc |= dalloc(b, &v.scratch, N * 10);
     rc |= dalloc(b, &v.ssum, N * 9); rc |= dalloc(b, &v.sv, N * 9); rc |= dalloc(b, &v.ovol, N);
-    rc |= dalloc(b, &v.vn, N * 12); rc |= dalloc(b, &v.flux, N * 30);
+    rc |= dalloc(b, &v.vn, N * 12); rc |= dalloc(b, &v.flux, N * 30); rc |= dalloc(b, &v.shock, N);
     if (rc) {
         for (void* q : b.allocs) cudaFree(q);
         b.allocs.clear();
@@ -520,6 +520,7 @@ int adfb_download_array(int blk, const char* name, double* out) {
     else if (s == "sj") { src = v.sj; nc = 3; }
     else if (s == "sk") { src = v.sk; nc = 3; }
     else if (s == "fw") { src = v.fw; nc = 5; }
+    else if (s == "shock") src = v.shock;
     else if (s == "dtl") src = v.dtl;
     else if (s == "radI") src = v.radI;
     else if (s == "radJ") src = v.radJ;
@@ -740,8 +741,6 @@ int adfb_residual(int level, unsigned flags) {
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_residual: adfb_set_params has not been called");
     if (!(flags & (ADFB_RES_FLOW | ADFB_RES_TURB))) return fail("adfb_residual: neither flow nor turbulence residual requested");
-    if (flags & (ADFB_RES_DISS_APPROX | ADFB_RES_VISC_APPROX))
-        return fail("adfb_residual: approximate (PC/ANK) flux variants are not built yet");
     for (Block& b : g.blocks)
         if (b.alive && b.level == level && !b.haveMetrics) return fail("adfb_residual: geometry of a block was never set");
     const unsigned long long key = (1ull << 40) | ((unsigned long long)level << 32) | flags;
@@ -884,6 +883,20 @@ int adfb_mffd_apply(const double* a, double* y, long long n, double h) {
     return 0;
 }
 double adfb_mffd_last_h(void) { return g.nkLastH; }
+
+// referenceShockSensor, src/adjoint/adjointUtils.F90:1900-1950
+int adfb_reference_shock_sensor(int level) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_reference_shock_sensor: adfb_set_params has not been called");
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != level) continue;
+        KT_BEGIN(K_MISC, g.stream);
+        k_shock<<<(unsigned)((b.d.N + 255) / 256), 256, 0, g.stream>>>(b.d, b.dev);
+        KT_END(K_MISC, g.stream);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
 
 // applyAllBC (+ turbulence halos), src/solver/BCRoutines.F90:57, turbBCRoutines.F90:49
 int adfb_apply_bcs(int level, int secondHalo, int withTurb) {

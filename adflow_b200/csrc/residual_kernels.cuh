@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
 // (allNodalGradients, :5205-5515) on nodes 1:il in gather form.  For node n (= cell index c)
 // the reference's three scatter sweeps add, in this order:  -K(layer k) +K(layer k+1)
 // -J(layer j) +J(layer j+1) -I(layer i) +I(layer i+1), then scale by 1/(8 vol).
-__global__ void __launch_bounds__(NODAL_TPB, NODAL_MINB) k_nodal(Dims d, BlockDev b, int doGrad) {
+__global__ void __launch_bounds__(NODAL_TPB, NODAL_MINB) k_nodal(Dims d, BlockDev b, int doGrad, int dissApprox) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 1;
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(NODAL_TPB, NODAL_MINB) k_nodal(Dims d, BlockDe
     if (c_prm.spaceDiscr == ADFB_DISS_SCALAR) {
         const double sslim = (c_prm.equations == ADFB_EULER) ? 0.001 * c_prm.pInfCorr
                                                             : 0.001 * c_prm.pInfCorr / pow(c_prm.rhoInf, c_prm.gammaInf);
-        const double* ss = b.ss;
+        const double* ss = dissApprox ? b.shock : b.ss;  // *Approx: frozen sensor field (blockette.F90:4385-4396)
         const double s0 = ss[c];
         b.dss[c] = fabs((ss[c + 1] - 2.0 * s0 + ss[c - 1]) / (ss[c + 1] + 2.0 * s0 + ss[c - 1] + sslim));
         b.dss[N + c] = fabs((ss[c + sJ] - 2.0 * s0 + ss[c - sJ]) / (ss[c + sJ] + 2.0 * s0 + ss[c - sJ] + sslim));
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(NODAL_TPB, NODAL_MINB) k_nodal(Dims d, BlockDe
     } else if (c_prm.spaceDiscr == ADFB_DISS_MATRIX) {
         // pressure sensor with the omega blend, inviscidDissFluxMatrix blockette.F90:2495-2512
         const double plim = 0.001 * c_prm.pInfCorr;
-        const double* p = b.p;
+        const double* p = dissApprox ? b.shock : b.p;  // matrix *Approx uses the frozen sensor (blockette.F90:4655-4670)
         const double p0 = p[c];
         const int sdv[3] = {1, sJ, sK};
 #pragma unroll
@@ -281,7 +281,8 @@ __device__ __forceinline__ CellState load_cell(const BlockDev& b, int N, int c) 
     return s;
 }
 
-template <bool VISCOUS, int DISC>
+// APPROX bit 0: first-order/lumped dissipation (*Approx routines), bit 1: thin-layer viscous flux
+template <bool VISCOUS, int DISC, int APPROX>
 __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int sd, int t1, int t2, int dir,
                                           const double* __restrict__ s, int8_t por, const double* __restrict__ rad,
                                           const double* __restrict__ dss, const CellState& m, double rFil, int doDiss,
@@ -307,7 +308,7 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
     }
 #pragma unroll
     for (int l = 0; l < 5; l++) fd[l] = 0.0;
-    if (DISC == ADFB_DISS_SCALAR && doDiss) {  // scalar JST
+    if (DISC == ADFB_DISS_SCALAR && !(APPROX & 1) && doDiss) {  // scalar JST
         const CellState mm = load_cell(b, N, c - sd), qq = load_cell(b, N, cp + sd);
         const double fis2 = rFil * c_prm.vis2, fis4 = rFil * c_prm.vis4;
         const double ppor = (por == ADFB_NORMALFLUX) ? 0.5 : 0.0;
@@ -325,23 +326,43 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
         ddw = (q.e + q.p) - (m.e + m.p);
         fd[4] = dis2 * ddw - dis4 * ((qq.e + qq.p) - (mm.e + mm.p) - 3.0 * ddw);
     }
-    if (DISC == ADFB_DISS_MATRIX && doDiss) {  // matrix dissipation, blockette.F90:2515-2680
-        const CellState mm = load_cell(b, N, c - sd), qq = load_cell(b, N, cp + sd);
+    if (DISC == ADFB_DISS_SCALAR && (APPROX & 1) && doDiss) {  // inviscidDissFluxScalarApprox, blockette.F90:4367-4617
+        const double ppor = (por == ADFB_NORMALFLUX) ? 0.5 : 0.0;
+        const double rrad = ppor * (rad[c] + rad[cp]);
+        const double dis2 = c_prm.vis2 * rrad * dmin_(0.25, dmax_(dss[c], dss[cp])) + c_prm.sigma * c_prm.vis4 * rrad;
+        fd[0] = dis2 * (q.r - m.r);
+        fd[1] = dis2 * (q.u * q.r - m.u * m.r);
+        fd[2] = dis2 * (q.v * q.r - m.v * m.r);
+        fd[3] = dis2 * (q.w * q.r - m.w * m.r);
+        fd[4] = dis2 * ((q.e + q.p) - (m.e + m.p));
+    }
+    if (DISC == ADFB_DISS_MATRIX && doDiss) {  // matrix dissipation (exact and *Approx), blockette.F90:2515-2680
         const double gam = c_prm.gammaInf;
         const double fis2 = rFil * c_prm.vis2, fis4 = rFil * c_prm.vis4;
         const double ppor = (por == ADFB_NORMALFLUX) ? 1.0 : 0.0;
-        const double dis2 = ppor * fis2 * dmin_(0.25, dmax_(dss[c], dss[cp]));
-        const double dis4 = dmax_(ppor * fis4 - dis2, 0.0);
-        double ddw = q.r - m.r;
-        const double dr = dis2 * ddw - dis4 * (qq.r - mm.r - 3.0 * ddw);
-        ddw = q.r * q.u - m.r * m.u;
-        const double dru = dis2 * ddw - dis4 * (qq.r * qq.u - mm.r * mm.u - 3.0 * ddw);
-        ddw = q.r * q.v - m.r * m.v;
-        const double drv = dis2 * ddw - dis4 * (qq.r * qq.v - mm.r * mm.v - 3.0 * ddw);
-        ddw = q.r * q.w - m.r * m.w;
-        const double drw = dis2 * ddw - dis4 * (qq.r * qq.w - mm.r * mm.w - 3.0 * ddw);
-        ddw = q.e - m.e;
-        const double dre = dis2 * ddw - dis4 * (qq.e - mm.e - 3.0 * ddw);
+        double dr, dru, drv, drw, dre;
+        if (APPROX & 1) {  // inviscidDissFluxMatrixApprox, blockette.F90:4672-4690
+            const double dis2 = fis2 * ppor * dmin_(0.25, dmax_(dss[c], dss[cp])) + c_prm.sigma * fis4 * ppor;
+            dr = dis2 * (q.r - m.r);
+            dru = dis2 * (q.r * q.u - m.r * m.u);
+            drv = dis2 * (q.r * q.v - m.r * m.v);
+            drw = dis2 * (q.r * q.w - m.r * m.w);
+            dre = dis2 * (q.e - m.e);
+        } else {
+            const CellState mm = load_cell(b, N, c - sd), qq = load_cell(b, N, cp + sd);
+            const double dis2 = ppor * fis2 * dmin_(0.25, dmax_(dss[c], dss[cp]));
+            const double dis4 = dmax_(ppor * fis4 - dis2, 0.0);
+            double ddw = q.r - m.r;
+            dr = dis2 * ddw - dis4 * (qq.r - mm.r - 3.0 * ddw);
+            ddw = q.r * q.u - m.r * m.u;
+            dru = dis2 * ddw - dis4 * (qq.r * qq.u - mm.r * mm.u - 3.0 * ddw);
+            ddw = q.r * q.v - m.r * m.v;
+            drv = dis2 * ddw - dis4 * (qq.r * qq.v - mm.r * mm.v - 3.0 * ddw);
+            ddw = q.r * q.w - m.r * m.w;
+            drw = dis2 * ddw - dis4 * (qq.r * qq.w - mm.r * mm.w - 3.0 * ddw);
+            ddw = q.e - m.e;
+            dre = dis2 * ddw - dis4 * (qq.e - mm.e - 3.0 * ddw);
+        }
         const double gm1 = gam - 1.0, ovgm1 = 1.0 / gm1;
         const double uAvg = 0.5 * (q.u + m.u), vAvg = 0.5 * (q.v + m.v), wAvg = 0.5 * (q.w + m.w);
         const double a2Avg = 0.5 * (gam * q.p / q.r + gam * m.p / m.r);
@@ -373,7 +394,7 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
         const CellState mm = load_cell(b, N, c - sd), qq = load_cell(b, N, cp + sd);
         const double gam = c_prm.gammaInf;
         double left[5] = {m.r, m.u, m.v, m.w, m.p}, right[5] = {q.r, q.u, q.v, q.w, q.p};
-        if (c_prm.limiter != ADFB_LIM_FIRSTORDER) {
+        if (!(APPROX & 1) && c_prm.limiter != ADFB_LIM_FIRSTORDER) {  // inviscidUpwindFlux(.False.) is first order
             const double du1[5] = {m.r - mm.r, m.u - mm.u, m.v - mm.v, m.w - mm.w, m.p - mm.p};
             const double du2[5] = {q.r - m.r, q.u - m.u, q.v - m.v, q.w - m.w, q.p - m.p};
             const double du3[5] = {qq.r - q.r, qq.u - q.u, qq.v - q.v, qq.w - q.w, qq.p - q.p};
@@ -451,7 +472,37 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
         fd[3] = porFlux * (lam3 * drw + wAvg * abv6 + sz * abv7);
         fd[4] = porFlux * (lam3 * drE + hAvg * abv6 + unAvg * abv7);
     }
-    if (VISCOUS && doVisc) {
+    if (VISCOUS && doVisc && (APPROX & 2)) {  // viscousFluxApprox (thin layer), blockette.F90:6467-6837
+        double porv = 0.5 * rFil;
+        if (por == ADFB_NOFLUX) porv = 0.0;
+        const double* vn = b.vn + (4 * dir) * N;
+        const double snrm = vn[3 * N + c];
+        const double ssx = vn[c] * snrm, ssy = vn[N + c] * snrm, ssz = vn[2 * N + c] * snrm;  // d/|d|^2
+        double dd = q.u - m.u;
+        const double u_x = dd * ssx, u_y = dd * ssy, u_z = dd * ssz;
+        dd = q.v - m.v;
+        const double v_x = dd * ssx, v_y = dd * ssy, v_z = dd * ssz;
+        dd = q.w - m.w;
+        const double w_x = dd * ssx, w_y = dd * ssy, w_z = dd * ssz;
+        dd = b.aa[cp] - b.aa[c];
+        double q_x = -dd * ssx, q_y = -dd * ssy, q_z = -dd * ssz;
+        const double mul = porv * (b.rlv[c] + b.rlv[cp]);
+        const double mue = porv * (b.rev[c] + b.rev[cp]);
+        const double mut = mul + mue;
+        const double gm1 = c_prm.gammaInf - 1.0;
+        const double heatCoef = mul * (1.0 / (c_prm.prandtl * gm1)) + mue * (1.0 / (c_prm.prandtlTurb * gm1));
+        const double fracDiv = (2.0 * (1.0 / 3.0)) * (u_x + v_y + w_z);
+        const double tauxx = mut * (2.0 * u_x - fracDiv), tauyy = mut * (2.0 * v_y - fracDiv), tauzz = mut * (2.0 * w_z - fracDiv);
+        const double tauxy = mut * (u_y + v_x), tauxz = mut * (u_z + w_x), tauyz = mut * (v_z + w_y);
+        q_x = heatCoef * q_x; q_y = heatCoef * q_y; q_z = heatCoef * q_z;
+        const double ubar = 0.5 * (m.u + q.u), vbar = 0.5 * (m.v + q.v), wbar = 0.5 * (m.w + q.w);
+        fd[1] += tauxx * s1 + tauxy * s2 + tauxz * s3;
+        fd[2] += tauxy * s1 + tauyy * s2 + tauyz * s3;
+        fd[3] += tauxz * s1 + tauyz * s2 + tauzz * s3;
+        fd[4] += (ubar * tauxx + vbar * tauxy + wbar * tauxz) * s1 + (ubar * tauxy + vbar * tauyy + wbar * tauyz) * s2 +
+                 (ubar * tauxz + vbar * tauyz + wbar * tauzz) * s3 - q_x * s1 - q_y * s2 - q_z * s3;
+    }
+    if (VISCOUS && doVisc && !(APPROX & 2)) {
         double porv = 0.5 * rFil;
         if (por == ADFB_NOFLUX) porv = 0.0;
         const double mul = porv * (b.rlv[c] + b.rlv[cp]);
@@ -508,7 +559,7 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
 // k_faces: plus faces of cell (i,j,k), i 1:il, j 1:jl, k 1:kl.  MERGED: one array G = fc - fd per
 // face (net outflow of the low cell) -> flux[dir*5 + l]; otherwise fc -> flux[dir*10 + l],
 // fd -> flux[dir*10 + 5 + l] (smoother path: fw persists between RK stages).
-template <bool VISCOUS, bool MERGED, int DISC>
+template <bool VISCOUS, bool MERGED, int DISC, int APPROX>
 __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDev b, double rFil, int doVisc, int doDiss) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
@@ -520,7 +571,7 @@ __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDe
     double fc[5], fd[5];
     const bool oi = i >= 2, oj = j >= 2, ok = k >= 2;
     if (oj && ok) {
-        face_flux<VISCOUS, DISC>(b, N, c, 1, sJ, sK, 0, b.si, b.porI[c], b.radI, b.dss, m, rFil, doDiss, doVisc, fc, fd);
+        face_flux<VISCOUS, DISC, APPROX>(b, N, c, 1, sJ, sK, 0, b.si, b.porI[c], b.radI, b.dss, m, rFil, doDiss, doVisc, fc, fd);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
             if (MERGED) b.flux[l * N + c] = fc[l] - fd[l];
@@ -528,7 +579,7 @@ __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDe
         }
     }
     if (oi && ok) {
-        face_flux<VISCOUS, DISC>(b, N, c, sJ, 1, sK, 1, b.sj, b.porJ[c], b.radJ, b.dss + N, m, rFil, doDiss, doVisc, fc, fd);
+        face_flux<VISCOUS, DISC, APPROX>(b, N, c, sJ, 1, sK, 1, b.sj, b.porJ[c], b.radJ, b.dss + N, m, rFil, doDiss, doVisc, fc, fd);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
             if (MERGED) b.flux[(5 + l) * N + c] = fc[l] - fd[l];
@@ -536,7 +587,7 @@ __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDe
         }
     }
     if (oi && oj) {
-        face_flux<VISCOUS, DISC>(b, N, c, sK, 1, sJ, 2, b.sk, b.porK[c], b.radK, b.dss + 2 * N, m, rFil, doDiss, doVisc, fc, fd);
+        face_flux<VISCOUS, DISC, APPROX>(b, N, c, sK, 1, sJ, 2, b.sk, b.porK[c], b.radK, b.dss + 2 * N, m, rFil, doDiss, doVisc, fc, fd);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
             if (MERGED) b.flux[(10 + l) * N + c] = fc[l] - fd[l];
@@ -758,6 +809,8 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
     const bool viscous = prm.equations != ADFB_EULER;
     const int doDiss = fabs(rFil) >= 1.e-10;  // fluxes.F90:1082 early return
     const int doVisc = viscous && doDiss;
+    const int dissApprox = (flags & ADFB_RES_DISS_APPROX) ? 1 : 0, viscApprox = (flags & ADFB_RES_VISC_APPROX) ? 1 : 0;
+    if ((dissApprox || viscApprox) && persistFw) return 1;  // approximate variants exist on the blockette path only
     dim3 tb(32, 4, 2);
     if (doRad || (flowRes && doDiss)) {
         dim3 g((d.NI + tb.x - 1) / tb.x, (d.NJ + tb.y - 1) / tb.y, (d.NK + tb.z - 1) / tb.z);
@@ -769,7 +822,7 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         dim3 tn = tune_block("ADFB_NODAL_BLOCK", dim3(32, 4, 2));
         dim3 g((d.ie + tn.x - 1) / tn.x, (d.je + tn.y - 1) / tn.y, (d.ke + tn.z - 1) / tn.z);
         KT_BEGIN(K_NODAL, stream);
-        k_nodal<<<g, tn, 0, stream>>>(d, b, doVisc);
+        k_nodal<<<g, tn, 0, stream>>>(d, b, doVisc && !viscApprox, dissApprox);
         KT_END(K_NODAL, stream);
     }
     if (turbRes) {
@@ -784,15 +837,24 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         dim3 g((d.il + tr.x - 1) / tr.x, (d.jl + tr.y - 1) / tr.y, (d.kl + tr.z - 1) / tr.z);
         const bool merged = !persistFw;
         KT_BEGIN(K_RESID, stream);
-#define ADFB_LAUNCH_FACES(V, M, D) k_faces<V, M, D><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss)
-#define ADFB_FACES_DISC(V, M)                                              \
+#define ADFB_LAUNCH_FACES(V, M, D, A) k_faces<V, M, D, A><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss)
+#define ADFB_FACES_DISC(V, M, A)                                           \
     do {                                                                   \
-        if (prm.spaceDiscr == ADFB_DISS_SCALAR) ADFB_LAUNCH_FACES(V, M, ADFB_DISS_SCALAR); \
-        else if (prm.spaceDiscr == ADFB_DISS_MATRIX) ADFB_LAUNCH_FACES(V, M, ADFB_DISS_MATRIX); \
-        else ADFB_LAUNCH_FACES(V, M, ADFB_UPWIND);                          \
+        if (prm.spaceDiscr == ADFB_DISS_SCALAR) ADFB_LAUNCH_FACES(V, M, ADFB_DISS_SCALAR, A); \
+        else if (prm.spaceDiscr == ADFB_DISS_MATRIX) ADFB_LAUNCH_FACES(V, M, ADFB_DISS_MATRIX, A); \
+        else ADFB_LAUNCH_FACES(V, M, ADFB_UPWIND, A);                       \
     } while (0)
-        if (viscous) { if (merged) ADFB_FACES_DISC(true, true); else ADFB_FACES_DISC(true, false); }
-        else { if (merged) ADFB_FACES_DISC(false, true); else ADFB_FACES_DISC(false, false); }
+        const int approx = dissApprox | (viscApprox << 1);
+        if (approx == 0) {
+            if (viscous) { if (merged) ADFB_FACES_DISC(true, true, 0); else ADFB_FACES_DISC(true, false, 0); }
+            else { if (merged) ADFB_FACES_DISC(false, true, 0); else ADFB_FACES_DISC(false, false, 0); }
+        } else if (viscous) {
+            if (approx == 1) ADFB_FACES_DISC(true, true, 1);
+            else if (approx == 2) ADFB_FACES_DISC(true, true, 2);
+            else ADFB_FACES_DISC(true, true, 3);
+        } else {
+            ADFB_FACES_DISC(false, true, 1);
+        }
 #undef ADFB_FACES_DISC
 #undef ADFB_LAUNCH_FACES
         KT_END(K_RESID, stream);

@@ -80,6 +80,14 @@ __global__ void __launch_bounds__(256) k_state_prep(Dims d, BlockDev b, int incl
     b.rev[c] = chi3 / (chi3 + cv13) * rnuSA;
 }
 
+// referenceShockSensor (src/adjoint/adjointUtils.F90:1900-1950)
+__global__ void __launch_bounds__(256) k_shock(Dims d, BlockDev b) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.N) return;
+    const double p = b.p[c];
+    b.shock[c] = (c_prm.equations == ADFB_EULER) ? p : p / pow(b.w[c], c_prm.gammaInf);
+}
+
 // computeEtotBlock(2,il,2,jl,2,kl) (src/utils/flowUtils.F90:551-672, cpConstant)
 __global__ void __launch_bounds__(256) k_etot_owned(Dims d, BlockDev b) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;

@@ -59,7 +59,7 @@ NCOMP = {"x": 3, "si": 3, "sj": 3, "sk": 3, "fw": 5, "wn": 5, "dss": 3, "grad": 
 class HostBlock:
     """All per-block host arrays in uniform boxes (numpy, Fortran order)."""
 
-    REAL = ["p", "rlv", "rev", "vol", "volRef", "d2Wall", "ss", "aa", "radI", "radJ", "radK", "dtl", "pn"]
+    REAL = ["p", "rlv", "rev", "vol", "volRef", "d2Wall", "ss", "aa", "radI", "radJ", "radK", "dtl", "pn", "shock"]
     VEC = ["x", "si", "sj", "sk", "fw", "wn", "dss", "grad", "scratch"]
 
     def __init__(self, nx, ny, nz, nw=6, right_handed=True):

@@ -34,7 +34,7 @@ class AdfbParams(C.Structure):
         ("cfl", C.c_double), ("cflCoarse", C.c_double),
         ("etaRK", C.c_double * 6), ("cdisRK", C.c_double * 6),
         ("alfaTurb", C.c_double), ("turbResScale", C.c_double),
-        ("cflLimit", C.c_double), ("smoop", C.c_double),
+        ("cflLimit", C.c_double), ("smoop", C.c_double), ("sigma", C.c_double),
         ("equations", C.c_int32), ("spaceDiscr", C.c_int32), ("nRKStages", C.c_int32), ("turbProd", C.c_int32),
         ("useQCR", C.c_int32), ("useft2SA", C.c_int32), ("useRotationSA", C.c_int32), ("approxSA", C.c_int32),
         ("secondOrdTurb", C.c_int32), ("limiter", C.c_int32), ("resAveraging", C.c_int32),
@@ -70,6 +70,7 @@ DEFAULT_OPTIONS = {
     "nSubiter": 1,
     "resAveraging": "alternate",
     "smoothParameter": 1.5,
+    "dissipationLumpingParameter": 6.0,
     "useBlockettes": True,
     "liftIndex": 2,
     "viscWallTreatment": "constant pressure extrapolation",
@@ -207,6 +208,7 @@ def make_params(options=None, mach=0.8, alpha_deg=1.8, P=20000.0, T=220.0, R=287
     prm.turbResScale = opt["turbResScale"]
     prm.cflLimit = opt["CFLLimit"]
     prm.smoop = opt["smoothParameter"]
+    prm.sigma = opt["dissipationLumpingParameter"]
     prm.turbProd = {"strain": PROD_STRAIN, "vorticity": PROD_VORTICITY}[opt["turbulenceProduction"]]
     prm.useQCR = int(opt["useQCR"])
     prm.useft2SA = int(opt["useft2SA"])

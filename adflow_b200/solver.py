@@ -122,6 +122,10 @@ class ADFLOW_B200:
         n = self.prm.nSubiterTurb if n_sub_iter_turb is None else n_sub_iter_turb
         check(self.L.adfb_sa_ddadi(level, n), "adfb_sa_ddadi")
 
+    def referenceShockSensor(self, level=1):
+        """referenceShockSensor (src/adjoint/adjointUtils.F90:1900): freeze the sensor field."""
+        check(self.L.adfb_reference_shock_sensor(level), "adfb_reference_shock_sensor")
+
     def downloadResidual(self, blk):
         hb = self.blocks[blk]
         out = np.zeros(hb.d.box + (hb.nw,), order="F")

@@ -105,6 +105,7 @@ typedef struct AdfbParams {
     double alfaTurb;      /* DD-ADI under-relaxation, inputParamRoutines.F90:3908 */
     double turbResScale;  /* NKSolvers.F90:1295-1307 */
     double cflLimit, smoop; /* residual averaging, residuals.F90:1850-1893 */
+    double sigma;           /* dissipationLumpingParameter of the *Approx dissipation (blockette.F90:4416) */
     /* integer switches */
     int32_t equations;    /* ADFB_EULER / NS / RANS */
     int32_t spaceDiscr;   /* ADFB_DISS_SCALAR ... */
@@ -188,6 +189,10 @@ int adfb_residual(int level, unsigned flags);
    blocks, all-reduced (getCurrentResidual, NKSolvers.F90:335-370). out[0]=rho, out[1]=total */
 int adfb_norms(double out[2]);
 int adfb_synchronize(void);
+
+/* referenceShockSensor (src/adjoint/adjointUtils.F90:1900-1950): freeze the shock sensor
+   field (p for Euler, p/rho**gamma otherwise) used by the ADFB_RES_DISS_APPROX variants */
+int adfb_reference_shock_sensor(int level);
 
 /* ---- NK matrix-free residual-Jacobian product ------------------------------ */
 /* FormFunction_mf (src/NKSolver/NKSolvers.F90:437-461): setW(wVec) with the turbulence

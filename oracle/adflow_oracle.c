@@ -652,13 +652,26 @@ void orc_residual_core(const OrcBlock* b, const AdfbParams* prm, unsigned flags,
     orc_time_step(b, prm, 1);
     if (flowRes) {
         orc_central_flux(b, prm);
-        if (prm->spaceDiscr == ADFB_DISS_SCALAR) orc_diss_scalar(b, prm, rFil);
-        else if (prm->spaceDiscr == ADFB_DISS_MATRIX) orc_diss_matrix(b, prm, rFil);
-        else if (prm->spaceDiscr == ADFB_UPWIND) orc_upwind_flux(b, prm, rFil);
+        if (flags & ADFB_RES_DISS_APPROX) { /* blockette.F90:636-644 */
+            if (prm->spaceDiscr == ADFB_DISS_SCALAR) orc_diss_scalar_approx(b, prm);
+            else if (prm->spaceDiscr == ADFB_DISS_MATRIX) orc_diss_matrix_approx(b, prm, rFil);
+            else {
+                AdfbParams p1 = *prm;
+                p1.limiter = ADFB_LIM_FIRSTORDER; /* inviscidUpwindFlux(.False.): first order */
+                orc_upwind_flux(b, &p1, rFil);
+            }
+        } else {
+            if (prm->spaceDiscr == ADFB_DISS_SCALAR) orc_diss_scalar(b, prm, rFil);
+            else if (prm->spaceDiscr == ADFB_DISS_MATRIX) orc_diss_matrix(b, prm, rFil);
+            else if (prm->spaceDiscr == ADFB_UPWIND) orc_upwind_flux(b, prm, rFil);
+        }
         if (viscous && fabs(rFil) > thresholdReal) {
             orc_speed_of_sound(b, prm);
-            orc_nodal_gradients(b);
-            orc_viscous_flux(b, prm, rFil);
+            if (flags & ADFB_RES_VISC_APPROX) orc_viscous_flux_approx(b, prm, rFil);
+            else {
+                orc_nodal_gradients(b);
+                orc_viscous_flux(b, prm, rFil);
+            }
         }
         orc_sum_dw_fw(b);
     }

@@ -43,6 +43,7 @@ typedef struct OrcBlock {
     /* smoother storage */
     double *wn, *pn;        /* 5 comps / 1 */
     double *scratch;        /* 10 comps: DADI work, SA qq etc. */
+    double *shock;          /* frozen shock sensor (referenceShockSensor) */
 } OrcBlock;
 
 #ifdef __cplusplus
@@ -79,6 +80,10 @@ void orc_dadi_step(const OrcBlock* b, const AdfbParams* prm, int nSub, const Adf
 /* adflow_oracle_fluxes.c: alternative dissipation schemes (same calling convention as orc_diss_scalar) */
 void orc_diss_matrix(const OrcBlock* b, const AdfbParams* prm, double rFil);
 void orc_upwind_flux(const OrcBlock* b, const AdfbParams* prm, double rFil);
+void orc_reference_shock_sensor(const OrcBlock* b, const AdfbParams* prm);
+void orc_diss_scalar_approx(const OrcBlock* b, const AdfbParams* prm);
+void orc_diss_matrix_approx(const OrcBlock* b, const AdfbParams* prm, double rFil);
+void orc_viscous_flux_approx(const OrcBlock* b, const AdfbParams* prm, double rFil);
 /* adflow_oracle_sa.c: one sa_block(resOnly=.false.) = residual + DD-ADI solve + rev + turbulence BCs */
 void orc_sa_block(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf);
 void orc_rk_smoother(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf);

@@ -33,7 +33,7 @@ class OrcBlock(C.Structure):
         + [(n, C.c_void_p) for n in (
             "w", "p", "rlv", "rev", "x", "si", "sj", "sk", "vol", "volRef", "d2Wall",
             "porI", "porJ", "porK", "iblank", "dw", "fw", "ss", "dss",
-            "aa", "radI", "radJ", "radK", "dtl", "grad", "wn", "pn", "scratch")]
+            "aa", "radI", "radJ", "radK", "dtl", "grad", "wn", "pn", "scratch", "shock")]
     )
 
 
@@ -152,6 +152,9 @@ class Oracle:
     def sa_block(self):
         n, arr = self._subfaces()
         self.L.orc_sa_block(_p(self.ob), _p(self.prm), C.c_int(n), arr)
+
+    def reference_shock_sensor(self):
+        self.L.orc_reference_shock_sensor(_p(self.ob), _p(self.prm))
 
     def call(self, name, *args):
         getattr(self.L, name)(_p(self.ob), *args)
