@@ -178,13 +178,13 @@ int get(const Block& b, Ext e, const void* dev, void* host, int ncomp, size_t es
 
 // Run `body` through a cached CUDA graph: the entry points are sequences of 10-25 small
 // kernels (BC subfaces, halo pack/unpack ...) whose launch latency would otherwise dominate.
-// Graphs are bypassed while per-kernel event timing is on and for multi-rank runs unless
-// ADFB_GRAPH_NCCL=1 (NCCL send/recv inside stream capture).
+// Graphs are bypassed while per-kernel event timing is on (and for multi-rank runs when
+// ADFB_GRAPH_NCCL=0 disables capturing NCCL send/recv).
 template <typename F>
 int run_graphed(unsigned long long key, F body) {
     static int ncclOk = -1;
     if (ncclOk < 0) {
-        const char* e = getenv("ADFB_GRAPH_NCCL"); ncclOk = (e && e[0] == '1') ? 1 : 0;
+        const char* e = getenv("ADFB_GRAPH_NCCL"); ncclOk = (e && e[0] == '0') ? 0 : 1;  // NCCL send/recv capture fine with NCCL >= 2.9
         const char* n = getenv("ADFB_NO_GRAPH"); if (n && n[0] == '1') g.useGraphs = false;
     }
     if (!g.useGraphs || g_kt.on || (g.nranks > 1 && !ncclOk)) return body();
