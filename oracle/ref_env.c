@@ -1,0 +1,50 @@
+/* ref_env.c -- TEST INFRASTRUCTURE ONLY.  Definitions for ref_env.h: the module variables the
+ * translated reference routines (oracle/_ref/blockette_ref.c) read, plus the three tiny
+ * utility procedures they call.  The test harness sets the variables by symbol name through
+ * ctypes (tests/refblockette.py). */
+#include <stdio.h>
+#include <stdlib.h>
+#include "ref_env.h"
+
+int nw = 6, nwf = 5, nt1 = 6, nt2 = 6, viscous = 1, kpresent = 0, eddymodel = 1;
+double pinfcorr, rhoinf, gammainf, timeref = 1.0, rgas, tref;
+int equations, equationmode, turbmodel, turbprod, useqcr, useft2sa, userotationsa;
+double prandtl, prandtlturb;
+int spacediscr, orderturb, limiter, precond, riemann, riemanncoarse, approxsa;
+double vis2, vis4, sigma, adis, acousticscalefactor, kappacoef;
+int usedisscontinuation = 0;
+double disscontmagnitude, disscontmidpoint, disscontsharpness;
+double turbresscale[4];
+int currentlevel = 1, groundlevel = 1;
+double rfil = 1.0, totalr0 = 1.0, totalr = 1.0;
+int ntimeintervalsspectral = 1, oversetpresent = 0, secondord = 0;
+double rsak, rsacb1, rsacb2, rsacb3, rsacv1, rsacw1, rsacw2, rsacw3, rsact1, rsact2, rsact3, rsact4, rsacrot;
+double cv13, kar2inv, cw36, cb3inv;
+int bp_nx, bp_ny, bp_nz, bp_il, bp_jl, bp_kl, bp_ie, bp_je, bp_ke, bp_ib, bp_jb, bp_kb;
+int bp_addgridvelocities = 0, bp_righthanded = 1, bp_sectionid = 1, bp_blockismoving = 0, bp_nbkglobal = 1;
+double *bp_w, *bp_p, *bp_gamma, *bp_rlv, *bp_rev, *bp_vol, *bp_volref, *bp_d2wall, *bp_shocksensor;
+double *bp_x, *bp_si, *bp_sj, *bp_sk, *bp_sfacei, *bp_sfacej, *bp_sfacek;
+double *bp_dw, *bp_fw, *bp_dtl, *bp_aa, *bp_radi, *bp_radj, *bp_radk;
+double *bp_ux, *bp_uy, *bp_uz, *bp_vx, *bp_vy, *bp_vz, *bp_wx, *bp_wy, *bp_wz, *bp_qx, *bp_qy, *bp_qz;
+int *bp_iblank, *bp_pori, *bp_porj, *bp_pork;
+double *bp_rotmatrixi = NULL, *bp_rotmatrixj = NULL, *bp_rotmatrixk = NULL;
+
+/* src/utils/utils.F90:486-500 */
+int getcorrectfork(void) { return kpresent && currentlevel <= groundlevel; }
+
+/* src/utils/utils.F90:501 -- fatal error */
+void terminate(const char* routine, const char* msg) {
+    fprintf(stderr, "reference terminate() in %s: %s\n", routine, msg);
+    abort();
+}
+
+/* src/utils/flowUtils.F90:674-703 with eint's cpConstant branch (:742-761); gammaConstant == gammaInf here */
+void etot(double* rho, double* u, double* v, double* w, double* p, double* k, double* etotal, int* correctfork) {
+    double ovgm1 = one / (gammainf - one);
+    double eint = ovgm1 * (*p) / (*rho);
+    if (*correctfork) {
+        double factk = ovgm1 * (five * third - gammainf);
+        eint = eint - factk * (*k);
+    }
+    *etotal = (*rho) * (eint + half * ((*u) * (*u) + (*v) * (*v) + (*w) * (*w)));
+}

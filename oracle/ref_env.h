@@ -1,0 +1,55 @@
+/* ref_env.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Environment for oracle/_ref/blockette_ref.c, the C translation (oracle/f90toc.py) of the
+ * reference's src/NKSolver/blockette.F90.  The translated routines reference module variables
+ * of OTHER reference modules (inputPhysics, inputDiscretization, flowVarRefState, iteration,
+ * paramTurb, sa, blockPointers ...).  Those modules are not translated; this header declares
+ * the variables as C globals (lower-cased Fortran names; blockPointers names carry the prefix
+ * bp_) and ref_env.c defines them and fills them from the test harness.
+ *
+ * `parameter` constants of src/modules/constants.F90 are NOT restated here: they are generated
+ * from the reference file into oracle/_ref/ref_constants.h.
+ */
+#ifndef ADFB_REF_ENV_H
+#define ADFB_REF_ENV_H
+#include <stddef.h>
+#include "ref_constants.h"
+
+/* flowVarRefState */
+extern int nw, nwf, nt1, nt2, viscous, kpresent, eddymodel;
+extern double pinfcorr, rhoinf, gammainf, timeref, rgas, tref;
+/* inputPhysics */
+extern int equations, equationmode, turbmodel, turbprod, useqcr, useft2sa, userotationsa;
+extern double prandtl, prandtlturb;
+/* inputDiscretization */
+extern int spacediscr, orderturb, limiter, precond, riemann, riemanncoarse, approxsa;
+extern double vis2, vis4, sigma, adis, acousticscalefactor, kappacoef;
+/* inputIteration */
+extern int usedisscontinuation;
+extern double disscontmagnitude, disscontmidpoint, disscontsharpness;
+extern double turbresscale[4];
+/* iteration */
+extern int currentlevel, groundlevel;
+extern double rfil, totalr0, totalr;
+/* inputTimeSpectral, oversetData, turbMod */
+extern int ntimeintervalsspectral, oversetpresent, secondord;
+/* paramTurb (SA constants) and module sa (derived constants set in sa_block) */
+extern double rsak, rsacb1, rsacb2, rsacb3, rsacv1, rsacw1, rsacw2, rsacw3, rsact1, rsact2, rsact3, rsact4, rsacrot;
+extern double cv13, kar2inv, cw36, cb3inv;
+/* blockPointers: extents and arrays of the current block, uniform box (0:ib,0:jb,0:kb) */
+extern int bp_nx, bp_ny, bp_nz, bp_il, bp_jl, bp_kl, bp_ie, bp_je, bp_ke, bp_ib, bp_jb, bp_kb;
+extern int bp_addgridvelocities, bp_righthanded, bp_sectionid, bp_blockismoving, bp_nbkglobal;
+extern double *bp_w, *bp_p, *bp_gamma, *bp_rlv, *bp_rev, *bp_vol, *bp_volref, *bp_d2wall, *bp_shocksensor;
+extern double *bp_x, *bp_si, *bp_sj, *bp_sk, *bp_sfacei, *bp_sfacej, *bp_sfacek;
+extern double *bp_dw, *bp_fw, *bp_dtl, *bp_aa, *bp_radi, *bp_radj, *bp_radk;
+extern double *bp_ux, *bp_uy, *bp_uz, *bp_vx, *bp_vy, *bp_vz, *bp_wx, *bp_wy, *bp_wz, *bp_qx, *bp_qy, *bp_qz;
+extern int *bp_iblank, *bp_pori, *bp_porj, *bp_pork;
+extern double *bp_rotmatrixi, *bp_rotmatrixj, *bp_rotmatrixk;
+
+/* utils / flowUtils procedures the translated code calls */
+int getcorrectfork(void);                           /* src/utils/utils.F90 getCorrectForK */
+void terminate(const char* routine, const char* msg); /* src/utils/utils.F90 terminate */
+void etot(double* rho, double* u, double* v, double* w, double* p, double* k, double* etotal,
+          int* correctfork);                        /* src/utils/flowUtils.F90 eTot (cpConstant) */
+
+#endif

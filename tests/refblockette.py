@@ -1,0 +1,126 @@
+"""Harness around oracle/_ref/libblockette_ref.so -- the reference's OWN blockette routines
+(`/root/reference/src/NKSolver/blockette.F90`), machine-translated Fortran -> C by
+oracle/f90toc.py and compiled with gcc (oracle/Makefile target `ref`).
+
+Test infrastructure only.  The library exists only where /root/reference was present at build
+time (this container); on the GPU box the prebuilt .so travels with the snapshot.  `available()`
+says whether it can be used; tests that need it skip otherwise.
+
+The translated routines read the module variables of other reference modules; those are plain
+C globals in the library (oracle/ref_env.h) and are set here by symbol name.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "..", "oracle", "_ref", "libblockette_ref.so")
+
+FLAG_DISS_APPROX, FLAG_VISC_APPROX, FLAG_UPDATE_INTERMED, FLAG_FLOW, FLAG_TURB, FLAG_STORE_WALL = 1, 2, 4, 8, 16, 32
+
+
+def available():
+    return os.path.exists(_SO)
+
+
+_L = None
+
+
+def lib():
+    global _L
+    if _L is None:
+        _L = C.CDLL(os.path.abspath(_SO))
+    return _L
+
+
+def _seti(name, v):
+    C.c_int.in_dll(lib(), name).value = int(v)
+
+
+def _setd(name, v):
+    C.c_double.in_dll(lib(), name).value = float(v)
+
+
+def _setp(name, arr):
+    C.c_void_p.in_dll(lib(), name).value = arr.ctypes.data
+
+
+# reference enumerations (src/modules/constants.F90) for the values AdfbParams encodes differently
+_REF_SPACEDISCR = {1: 1, 2: 2, 4: 9}            # dissScalar, dissMatrix, upwind
+_REF_LIMITER = {0: 1, 1: 2, 2: 3, 3: 4}         # firstOrder, noLimiter, vanAlbeda, minmod
+
+
+def set_params(prm, nw, rfil=1.0):
+    """inputPhysics / inputDiscretization / flowVarRefState / paramTurb / iteration from AdfbParams."""
+    _seti("nw", nw); _seti("nwf", 5); _seti("nt1", 6); _seti("nt2", nw)
+    _seti("viscous", prm.equations != 1); _seti("kpresent", 0); _seti("eddymodel", prm.equations == 3)
+    _seti("equations", prm.equations); _seti("equationmode", 1); _seti("turbmodel", 2)
+    _seti("turbprod", prm.turbProd); _seti("useqcr", prm.useQCR); _seti("useft2sa", prm.useft2SA)
+    _seti("userotationsa", prm.useRotationSA)
+    _seti("spacediscr", _REF_SPACEDISCR[prm.spaceDiscr]); _seti("limiter", _REF_LIMITER[prm.limiter])
+    _seti("orderturb", 2 if prm.secondOrdTurb else 1); _seti("precond", 1); _seti("riemann", 1)
+    _seti("riemanncoarse", 1); _seti("approxsa", prm.approxSA)
+    _seti("usedisscontinuation", 0); _seti("currentlevel", 1); _seti("groundlevel", 1)
+    _seti("ntimeintervalsspectral", 1); _seti("oversetpresent", 0)
+    for n in ("pInfCorr", "rhoInf", "gammaInf", "RGas", "prandtl", "prandtlTurb", "vis2", "vis4", "sigma", "adis",
+              "acousticScaleFactor", "kappaCoef", "rsaK", "rsaCb1", "rsaCb2", "rsaCb3", "rsaCv1", "rsaCw1", "rsaCw2",
+              "rsaCw3", "rsaCt3", "rsaCt4", "rsaCrot"):
+        _setd(n.lower(), getattr(prm, n))
+    _setd("timeref", 1.0); _setd("tref", 1.0); _setd("rfil", rfil); _setd("totalr", 1.0); _setd("totalr0", 1.0)
+    # module sa derived constants, src/turbulence/sa.F90:123-126
+    _setd("cv13", prm.rsaCv1 ** 3); _setd("kar2inv", 1.0 / (prm.rsaK ** 2))
+    _setd("cw36", prm.rsaCw3 ** 6); _setd("cb3inv", 1.0 / prm.rsaCb3)
+    trs = (C.c_double * 4).in_dll(lib(), "turbresscale")
+    trs[0] = prm.turbResScale
+
+
+class RefBlock:
+    """blockPointers view of a HostBlock: every array in the uniform box (0:ib,0:jb,0:kb)."""
+
+    OUT = ["dw", "dtl", "aa", "radi", "radj", "radk", "ux", "uy", "uz", "vx", "vy", "vz", "wx", "wy", "wz", "qx",
+           "qy", "qz"]
+
+    def __init__(self, hb, prm):
+        d = hb.d
+        self.hb = hb
+        box = d.box
+        self.a = {}
+        f = np.asfortranarray
+        for ref, mine in (("w", "w"), ("p", "p"), ("rlv", "rlv"), ("rev", "rev"), ("vol", "vol"),
+                          ("volref", "volRef"), ("d2wall", "d2Wall"), ("shocksensor", "shock"), ("x", "x"),
+                          ("si", "si"), ("sj", "sj"), ("sk", "sk")):
+            self.a[ref] = f(getattr(hb, mine).astype(np.float64).copy(order="F"))
+        self.a["gamma"] = np.full(box, prm.gammaInf, order="F")
+        for n in ("sfacei", "sfacej", "sfacek"):
+            self.a[n] = np.zeros(box, order="F")
+        self.a["dw"] = np.zeros(box + (hb.nw,), order="F")
+        self.a["fw"] = np.zeros(box + (5,), order="F")
+        for n in self.OUT[1:]:
+            self.a[n] = np.zeros(box, order="F")
+        self.a["iblank"] = f(hb.iblank.astype(np.int32).copy(order="F"))
+        for ref, mine in (("pori", "porI"), ("porj", "porJ"), ("pork", "porK")):
+            self.a[ref] = f(getattr(hb, mine).astype(np.int32).copy(order="F"))
+
+    def bind(self):
+        d = self.hb.d
+        for n, v in (("nx", d.nx), ("ny", d.ny), ("nz", d.nz), ("il", d.il), ("jl", d.jl), ("kl", d.kl),
+                     ("ie", d.ie), ("je", d.je), ("ke", d.ke), ("ib", d.ib), ("jb", d.jb), ("kb", d.kb)):
+            _seti("bp_" + n, v)
+        _seti("bp_addgridvelocities", 0); _seti("bp_righthanded", int(self.hb.right_handed))
+        _seti("bp_sectionid", 1); _seti("bp_blockismoving", 0); _seti("bp_nbkglobal", 1)
+        for n, arr in self.a.items():
+            assert arr.flags.f_contiguous
+            _setp("bp_" + n, arr)
+
+
+def residual_core(hb, prm, flags=FLAG_FLOW | FLAG_TURB, rfil=1.0):
+    """blocketteResCore (src/NKSolver/blockette.F90:299-753) on one block; returns the RefBlock
+    whose arrays hold dw (and, with FLAG_UPDATE_INTERMED, dtl/rad*/aa/nodal gradients)."""
+    set_params(prm, hb.nw, rfil)
+    rb = RefBlock(hb, prm)
+    rb.bind()
+    args = [C.byref(C.c_int(1 if flags & m else 0)) for m in
+            (FLAG_DISS_APPROX, FLAG_VISC_APPROX, FLAG_UPDATE_INTERMED, FLAG_FLOW, FLAG_TURB, FLAG_STORE_WALL)]
+    lib().blocketterescore(*args)
+    return rb
