@@ -103,25 +103,46 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+KIND_NOTE = {
+    "reference": "oracle/_ref: the reference's src/NKSolver/blockette.F90 translated to C, gcc -O3 -ffast-math",
+    "port": "oracle port (C restatement), gcc -O3 -march=native -ffast-math",
+}
+
+
+def _cpu_core_runner(hb, prm):
+    """callable running the reference's blocketteResCore once on `hb`, and its kind:
+    "reference" = oracle/_ref (the reference's own blockette.F90 translated to C and built with
+    -O3 -ffast-math like config.LINUX_GFORTRAN.mk), else "port" = the oracle restatement."""
+    from oracle import refblockette as rb
+
+    if rb.available(fast=True):
+        rb.use_fast(True)
+        rb.residual_core(hb, prm, 8 | 16)
+        return (lambda: rb.call_core(8 | 16)), "reference"
+    from oracle.pyoracle import Oracle
+
+    o = Oracle(hb, prm, fast=True)
+    return (lambda: o.residual_core(8 | 16)), "port"
+
+
 def cpu_baseline_single(shape, reps_budget_s=12.0):
-    """Oracle port on ONE core over the full C2 block; returns Mcells/s."""
+    """Reference CPU path on ONE core over the full C2 block; returns (Mcells/s, reps, kind)."""
     from adflow_b200 import make_params
     from adflow_b200 import synthetic as syn
-    from oracle.pyoracle import Oracle
 
     prm = make_params()
     hb = syn.make_block(*shape, prm)
-    o = Oracle(hb, prm, fast=True)
-    o.residual_core(8 | 16)  # warm-up
+    run, kind = _cpu_core_runner(hb, prm)
+    run()  # warm-up
     t0 = time.perf_counter()
     reps = 0
     while True:
-        o.residual_core(8 | 16)
+        run()
         reps += 1
         if time.perf_counter() - t0 > reps_budget_s or reps >= 20:
             break
     dt = time.perf_counter() - t0
-    return hb.d.ncells * reps / dt / 1e6, reps
+    return hb.d.ncells * reps / dt / 1e6, reps, kind
 
 
 def _ref_worker(args):
@@ -129,16 +150,15 @@ def _ref_worker(args):
     os.environ["OMP_NUM_THREADS"] = "1"
     from adflow_b200 import make_params
     from adflow_b200 import synthetic as syn
-    from oracle.pyoracle import Oracle
 
     prm = make_params()
     hb = syn.make_block(*shape, prm, origin=origin, global_n=gshape, origin_tag=tag)
-    o = Oracle(hb, prm, fast=True)
-    o.residual_core(8 | 16)
+    run, kind = _cpu_core_runner(hb, prm)
+    run()
     t0 = time.perf_counter()
     for _ in range(reps):
-        o.residual_core(8 | 16)
-    return time.perf_counter() - t0, hb.d.ncells
+        run()
+    return time.perf_counter() - t0, hb.d.ncells, kind
 
 
 def run_reference(args):
@@ -175,9 +195,9 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C2 96x72x64 RANS-SA residual, block split over host cores"},
-        "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": parts, "kind": "port",
-                         "sample": "%d residual evaluations of the C2 block per step, %d sub-blocks (1 per core), "
-                                   "oracle port -O3 -march=native -ffast-math" % (reps, parts)},
+        "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": parts, "kind": out[0][2],
+                         "sample": "%d residual evaluations (blocketteResCore) of the C2 block per step, %d sub-blocks "
+                                   "(1 per core, one process each), %s" % (reps, parts, KIND_NOTE[out[0][2]])},
         "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -345,10 +365,10 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:
-            v, reps = cpu_baseline_single(shape)
-            line["cpu_baseline"] = {"value": v, "unit": "Mcells/s", "cores": 1, "kind": "port",
-                                    "sample": "%d full residual evaluations of the same block, oracle port "
-                                              "(-O3 -march=native -ffast-math), 1 core" % reps}
+            v, reps, kind = cpu_baseline_single(shape)
+            line["cpu_baseline"] = {"value": v, "unit": "Mcells/s", "cores": 1, "kind": kind,
+                                    "sample": "%d residual evaluations (blocketteResCore) of the same block, 1 core, %s"
+                                              % (reps, KIND_NOTE[kind])}
         print(json.dumps(line))
     s.close()
     if world > 1:

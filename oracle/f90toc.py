@@ -266,8 +266,24 @@ def parse_expr(s):
 
 # ----------------------------------------------------------------------------- symbols
 class Array:
-    def __init__(self, cname, ctype, bounds, pointer=False):
+    def __init__(self, cname, ctype, bounds, pointer=False, strides=None):
         self.cname, self.ctype, self.bounds, self.pointer = cname, ctype, bounds, pointer  # bounds: list of (lo_c, ext_c)
+        self.strides = strides  # explicit per-dimension strides (Fortran pointer arrays with run-time descriptors)
+
+    def stride_list(self):
+        if self.strides:
+            return list(self.strides)
+        out, st = [], "1"
+        for lo, ext in self.bounds:
+            out.append(st)
+            st = "%s * (%s)" % (st, ext)
+        return out
+
+    @staticmethod
+    def descriptor(name, ctype, rank):
+        """Fortran pointer array: C pointer + run-time lower bounds, extents, strides"""
+        return Array(name, ctype, [("%s_lb[%d]" % (name, d), "%s_n[%d]" % (name, d)) for d in range(rank)],
+                     pointer=True, strides=["%s_s[%d]" % (name, d) for d in range(rank)])
 
 
 class Scope:
@@ -327,6 +343,9 @@ class Translator:
         self.env = env
         self.rename_modules = rename_modules  # module -> prefix for imported names
         self.signatures = {}                  # subroutine -> list of (name, ctype, isarray)
+        self.prefix = ""                      # C-name prefix of the current module's procedures
+        self.toplevel = set()                 # module procedures (not contained ones) of the current module
+        self.all_protos = []                  # prototypes of every translated module procedure
         self.tmp = 0
 
     # ---- types
@@ -395,15 +414,13 @@ class Translator:
         """C index expression of arr(subs); `range` subscripts are replaced through loopmap."""
         if len(subs) != len(arr.bounds):
             raise SyntaxError("rank mismatch for %s: %d subscripts, rank %d" % (arr.cname, len(subs), len(arr.bounds)))
-        idx, stride = None, "1"
         terms = []
-        for (lo, ext), s in zip(arr.bounds, subs):
+        for (lo, ext), s, stride in zip(arr.bounds, subs, arr.stride_list()):
             if s[0] == "range":
                 s_c = loopmap.pop(0)
             else:
                 s_c = self.ex(s, sc)
             terms.append("((%s) - (%s)) * (%s)" % (s_c, lo, stride))
-            stride = "%s * (%s)" % (stride, ext)
         idx = " + ".join(terms)
         return "%s[%s]" % (arr.cname, idx)
 
@@ -563,16 +580,50 @@ class Translator:
         return out
 
     def index_c(self, arr, subs, sc):
-        terms, stride = [], "1"
-        for (lo, ext), s in zip(arr.bounds, subs):
+        terms = []
+        for (lo, ext), s, stride in zip(arr.bounds, subs, arr.stride_list()):
             s_c = s[1] if s[0] == "cexpr" else self.ex(s, sc)
             terms.append("((%s) - (%s)) * (%s)" % (s_c, lo, stride))
-            stride = "%s * (%s)" % (stride, ext)
         return "%s[%s]" % (arr.cname, " + ".join(terms))
+
+    # ---- pointer association  p => target(section)
+    def associate(self, lhs, rhs, sc, ind):
+        P = sc.lookup_array(lhs[1]) or self.env.arrays.get(sc.rename(lhs[1]))
+        if not P or not P.strides:
+            raise SyntaxError("pointer association to a non-descriptor array %r" % (lhs,))
+        p = P.cname
+        if rhs[0] == "name":
+            T = sc.lookup_array(rhs[1]) or self.env.arrays.get(sc.rename(rhs[1]))
+            subs = [("range", None, None)] * len(T.bounds)
+            whole = True
+        else:
+            T = sc.lookup_array(rhs[1][1]) or self.env.arrays.get(sc.rename(rhs[1][1]))
+            subs = rhs[2]
+            whole = False
+        if T is None:
+            raise SyntaxError("unknown pointer target %r" % (rhs,))
+        out, off, k = [], [], 0
+        for d, ((lo, ext), st, sb) in enumerate(zip(T.bounds, T.stride_list(), subs)):
+            if sb[0] == "range":
+                lo_r = self.ex(sb[1], sc) if sb[1] is not None else lo
+                hi_r = self.ex(sb[2], sc) if sb[2] is not None else "(%s) + (%s) - 1" % (lo, ext)
+                # a pointer to a SECTION has lower bound 1; to a whole array it inherits the bounds
+                out.append(ind + "%s_lb[%d] = %s; %s_n[%d] = (%s) - (%s) + 1; %s_s[%d] = %s;" % (
+                    p, k, lo if whole else "1", p, k, hi_r, lo_r, p, k, st))
+                off.append("((%s) - (%s)) * (%s)" % (lo_r, lo, st))
+                k += 1
+            else:
+                off.append("((%s) - (%s)) * (%s)" % (self.ex(sb, sc), lo, st))
+        if k != len(P.bounds):
+            raise SyntaxError("rank mismatch in pointer association of %s" % p)
+        out.append(ind + "%s = &%s[%s];" % (p, T.cname, " + ".join(off)))
+        return out
 
     # ---- call statements
     def call_stmt(self, name, args, sc):
         name2 = sc.rename(name)
+        if name in self.toplevel and name2 == name:
+            name2 = self.prefix + name
         sig = self.signatures.get(name) or self.env.subs.get(name2)
         cargs = []
         for q, a in enumerate(args):
@@ -724,9 +775,12 @@ class UnitTranslator:
         self.collect_signatures()
         subs = self.find_subroutines()
         top = [s for s in subs if s[4] == 0 and (self.only is None or s[0] in self.only)]
+        self.tr.toplevel = set(s[0] for s in subs if s[4] == 0)
         protos = []
         for name, a, b, args, depth in top:
             protos.append(self.proto(name) + ";")
+            self.tr.env.subs[self.tr.prefix + name] = self.tr.signatures[name]
+        self.tr.all_protos += protos
         self.out += protos + [""]
         for name, a, b, args, depth in top:
             self.out += self.subroutine(name, a, b, self.msc, nested=False)
@@ -736,7 +790,8 @@ class UnitTranslator:
     def proto(self, name, nested=False):
         sig = self.tr.signatures[name]
         ps = ", ".join("%s* %s" % (t, n) for n, t, _ in sig) or "void"
-        return "%svoid %s(%s)" % ("auto " if nested else "", name, ps)
+        cname = name if (nested or name not in self.tr.toplevel) else self.tr.prefix + name
+        return "%svoid %s(%s)" % ("auto " if nested else "", cname, ps)
 
     def subroutine(self, name, a, b, parent_scope, nested):
         tr = self.tr
@@ -782,6 +837,11 @@ class UnitTranslator:
                                 sc.renames[loc] = pref + ext
                             elif loc != ext:
                                 sc.renames[loc] = ext
+                    elif pref is not None:
+                        # whole-module import: every name ref_env.h provides under this prefix
+                        for en in list(tr.env.ints) + list(tr.env.arrays) + list(tr.env.subs):
+                            if en.startswith(pref):
+                                sc.renames[en[len(pref):]] = en
                     continue
                 if l.startswith("implicit"):
                     continue
@@ -804,7 +864,12 @@ class UnitTranslator:
                                 sc.ptr_scalars.add(en)
                                 sc.types[en] = ctype
                             continue
-                        if spec is not None:
+                        if spec is not None and "pointer" in attrs:
+                            rank = len(split_top(spec, ","))
+                            decls.append(ind + "%s* %s = 0; long %s_lb[%d] = {0}, %s_n[%d] = {0}, %s_s[%d] = {0};" % (
+                                ctype, en, en, rank, en, rank, en, rank))
+                            sc.arrays[en] = Array.descriptor(en, ctype, rank)
+                        elif spec is not None:
                             dims = dims_from_spec(spec, tr, sc)
                             total = " * ".join("(%s)" % x[1] for x in dims)
                             decls.append(ind + "%s %s_[%s];" % (ctype, en, total))
@@ -935,6 +1000,14 @@ class UnitTranslator:
                 depth += 1
             elif v == ")":
                 depth -= 1
+            elif v == "=>" and depth == 0:
+                return tr.associate(Parser(toks[:q]).expr(), Parser(toks[q + 1:]).expr(), sc, ind)
+        depth = 0
+        for q, (k, v) in enumerate(toks):
+            if v == "(":
+                depth += 1
+            elif v == ")":
+                depth -= 1
             elif v == "=" and depth == 0:
                 lhs = Parser(toks[:q]).expr()
                 rhs = Parser(toks[q + 1:]).expr()
@@ -947,6 +1020,7 @@ C_PRELUDE = r"""/* GENERATED by oracle/f90toc.py from %(src)s -- do not edit, do
 #include <stdlib.h>
 #include <stdio.h>
 #include "ref_env.h"
+#include "ref_protos.h"
 static inline double f90_dmax(double a, double b) { return a > b ? a : b; }
 static inline double f90_dmin(double a, double b) { return a < b ? a : b; }
 static inline int f90_imax(int a, int b) { return a > b ? a : b; }
@@ -964,13 +1038,15 @@ static inline int f90_ipow(int x, int n) { int r = 1; for (int q = 0; q < n; q++
 """
 
 
-def translate_module(src_path, only, env, rename_modules, patches=(), defined=()):
+def translate_module(src_path, only, env, rename_modules, patches=(), defined=(), tr=None, prefix=""):
     text = open(src_path).read()
     lines = preprocess(text, defined)
     for pat, rep in patches:
         lines = [re.sub(pat, rep, l) for l in lines]
     lines = [l for l in lines if l is not None and l.strip() != ""]
-    tr = Translator(env, rename_modules)
+    if tr is None:
+        tr = Translator(env, rename_modules)
+    tr.signatures, tr.prefix, tr.toplevel = {}, prefix, set()
     # module-level declarations
     msc = Scope()
     mdecl = []
@@ -992,6 +1068,8 @@ def translate_module(src_path, only, env, rename_modules, patches=(), defined=()
             spec = dspec or (dimattr[dimattr.index("(") + 1:-1] if dimattr else None)
             if spec is not None:
                 dims = dims_from_spec(spec, tr, msc)
+                if any(x is None for x in dims):
+                    continue  # allocatable / pointer module array: must come from ref_env.h
                 total = " * ".join("(%s)" % x[1] for x in dims)
                 mdecl.append("static %s %s_[%s];" % (ctype, en, total))
                 msc.arrays[en] = Array(en + "_", ctype, dims)
@@ -1008,7 +1086,7 @@ def translate_module(src_path, only, env, rename_modules, patches=(), defined=()
     body = [l for l in body if not l.startswith("end module")]
     ut = UnitTranslator(tr, body, msc, only)
     code = ut.translate()
-    return C_PRELUDE % {"src": src_path} + "\n".join(mdecl) + "\n\n" + code + "\n", msc
+    return C_PRELUDE % {"src": src_path} + "\n".join(mdecl) + "\n\n" + code + "\n", tr
 
 
 def translate_parameters(src_path, defined=()):

@@ -49,7 +49,8 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  firstorder secondorder nolimiter vanalbeda minmod noprecond turkel choimerkle roe vanleer ausmdv
  strain vorticity katolaunder kpresent eddymodel rotationalperiodic correctfork righthanded
  usedisscontinuation nbkglobal sectionid ntimeintervalsspectral normalflux boundflux internalflux
- lumpeddiss fullturb
+ lumpeddiss fullturb cpmodel rkstage resaveraging ndom exchangepressureearly lowspeedpreconditioner
+ noresaveraging alwaysresaveraging alternateresaveraging
  bp_nx bp_ny bp_nz bp_il bp_jl bp_kl bp_ie bp_je bp_ke bp_ib bp_jb bp_kb bp_addgridvelocities
  bp_righthanded bp_sectionid bp_blockismoving bp_nbkglobal""".split()
 
@@ -69,6 +70,12 @@ def env_arrays():
     arrs["bp_w"] = A("bp_w", "double", box("nw"))
     arrs["bp_dw"] = A("bp_dw", "double", box("nw"))
     arrs["bp_fw"] = A("bp_fw", "double", box("nwf"))
+    arrs["bp_wn"] = A("bp_wn", "double", box("nwf"))
+    arrs["bp_pn"] = A("bp_pn", "double", box())
+    arrs["bp_scratch"] = A("bp_scratch", "double", box(10))
+    arrs["etark"] = A("etark", "double", [("1", "6")])
+    arrs["cdisrk"] = A("cdisrk", "double", [("1", "6")])
+    arrs["coeftime"] = A("coeftime", "double", [("0", "8")])
     for n in ["x", "si", "sj", "sk"]:
         arrs["bp_" + n] = A("bp_" + n, "double", box(3))
     arrs["bp_iblank"] = A("bp_iblank", "int", box())
@@ -82,28 +89,51 @@ def env_arrays():
 
 ENV_SUBS = {
     # name -> [(argname, ctype, isarray)] for external subroutines called by reference
-    "etot": [("rho", "double", False), ("u", "double", False), ("v", "double", False), ("w", "double", False),
-             ("p", "double", False), ("k", "double", False), ("etotal", "double", False), ("correctfork", "int", False)],
     "terminate": [("routine", "str", False), ("msg", "str", False)],
+    # driver-level procedures outside the translated set: no-op stubs in ref_env.c (single block, BCs and
+    # halo exchange are applied by the test harness around the translated routine)
+    "setpointers": [("nn", "int", False), ("level", "int", False), ("sps", "int", False)],
+    "whalo1": [(n, "int", False) for n in ("level", "start", "end", "commpressure", "commgamma", "commviscous")],
+    "whalo2": [(n, "int", False) for n in ("level", "start", "end", "commpressure", "commgamma", "commviscous")],
+    "applyallbc": [("secondhalo", "int", False)],
 }
+
+
+# (source file relative to <ref>/src, C prefix of its procedures, routines to translate)
+UNITS = [
+    # USE_TAPENADE (the reference's own switch for its AD-differentiable subset) drops the cp-curve-fit
+    # branches of eint/computeEtotBlock, which need tables outside the path (cpModel == cpConstant here)
+    ("utils/flowUtils.F90", "flowutils_", ["computeetotblock", "computelamviscosity", "computepressuresimple",
+                                           "etot", "eint"], ("USE_TAPENADE",)),
+    ("NKSolver/blockette.F90", "", ROUTINES, ()),
+    ("turbulence/turbUtils.F90", "turbutils_", ["computeeddyviscosity", "saeddyviscosity"], ()),
+    ("solver/residuals.F90", "residuals_", ["residualaveraging", "computedwdadi", "tridiagsolve"], ()),
+    ("solver/smoothers.F90", "smoothers_", ["executerkstage", "executedadistep"], ()),
+]
+RENAME_MODULES = {"blockpointers": "bp_", "flowutils": "flowutils_", "turbutils": "turbutils_",
+                  "residuals": "residuals_", "smoothers": "smoothers_"}
 
 
 def main():
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
-    src = os.path.join(ref, "src", "NKSolver", "blockette.F90")
-    if not os.path.exists(src):
-        print("make_ref: %s not found -- reference not present, nothing generated" % src)
+    if not os.path.exists(os.path.join(ref, "src", "NKSolver", "blockette.F90")):
+        print("make_ref: %s/src not found -- reference not present, nothing generated" % ref)
         return 0
-    env = f90toc.Env(ENV_INTS, env_arrays(), ["getcorrectfork"], ENV_SUBS)
-    code, _ = f90toc.translate_module(
-        src, only=set(ROUTINES), env=env,
-        rename_modules={"blockpointers": "bp_"}, patches=PATCHES, defined=())
+    env = f90toc.Env(ENV_INTS, env_arrays(), ["getcorrectfork"], dict(ENV_SUBS))
     outdir = os.path.join(HERE, "_ref")
     os.makedirs(outdir, exist_ok=True)
-    out = os.path.join(outdir, "blockette_ref.c")
-    with open(out, "w") as f:
-        f.write(code)
-    print("make_ref: wrote %s (%d lines)" % (out, code.count("\n")))
+    tr = None
+    for rel, prefix, routines, defined in UNITS:
+        src = os.path.join(ref, "src", rel)
+        code, tr = f90toc.translate_module(src, only=set(routines), env=env, rename_modules=RENAME_MODULES,
+                                           patches=PATCHES, defined=defined, tr=tr, prefix=prefix)
+        out = os.path.join(outdir, os.path.basename(rel).replace(".F90", "").lower() + "_ref.c")
+        with open(out, "w") as f:
+            f.write(code)
+        print("make_ref: wrote %s (%d lines)" % (out, code.count("\n")))
+    with open(os.path.join(outdir, "ref_protos.h"), "w") as f:
+        f.write("/* GENERATED by oracle/make_ref.py -- prototypes of the translated reference procedures */\n")
+        f.write("\n".join(tr.all_protos) + "\n")
     consts = f90toc.translate_parameters(os.path.join(ref, "src", "modules", "constants.F90"))
     with open(os.path.join(outdir, "ref_constants.h"), "w") as f:
         f.write(consts)

@@ -29,6 +29,29 @@ double *bp_ux, *bp_uy, *bp_uz, *bp_vx, *bp_vy, *bp_vz, *bp_wx, *bp_wy, *bp_wz, *
 int *bp_iblank, *bp_pori, *bp_porj, *bp_pork;
 double *bp_rotmatrixi = NULL, *bp_rotmatrixj = NULL, *bp_rotmatrixk = NULL;
 
+int cpmodel = 1 /* cpConstant */, rkstage = 1, resaveraging = 0, ndom = 1, exchangepressureearly = 0;
+int lowspeedpreconditioner = 0;
+double gammaconstant, musuthdim, tsuthdim, ssuthdim, muref = 1.0, pinf;
+double cfl, cflcoarse, cfllimit, smoop, deltat = 1.0;
+double etark[6], cdisrk[6], coeftime[8];
+double *bp_wn, *bp_pn, *bp_scratch;
+
+/* Driver-level procedures that are NOT part of the translated set.  One block, pointers bound by
+   the harness, boundary conditions and halo exchange applied by the harness around the call. */
+void setpointers(int* nn, int* level, int* sps) { (void)nn; (void)level; (void)sps; }
+void whalo1(int* a, int* b, int* c, int* d, int* e, int* f) { (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; }
+void whalo2(int* a, int* b, int* c, int* d, int* e, int* f) { (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; }
+void applyallbc(int* secondhalo) { (void)secondhalo; }
+
+/* branches of other physical models (cp curve fits, k-omega, SST, k-tau, v2-f): never taken on the
+   path (cpConstant, Spalart-Allmaras); reaching one is a harness error */
+#define UNREACHABLE(name) void name() { terminate(#name, "model outside the translated hot path"); }
+UNREACHABLE(flowutils_computeetotcellcpfit)
+UNREACHABLE(turbutils_kweddyviscosity)
+UNREACHABLE(turbutils_ssteddyviscosity)
+UNREACHABLE(turbutils_kteddyviscosity)
+UNREACHABLE(turbutils_vfeddyviscosity)
+
 /* src/utils/utils.F90:486-500 */
 int getcorrectfork(void) { return kpresent && currentlevel <= groundlevel; }
 
@@ -36,15 +59,4 @@ int getcorrectfork(void) { return kpresent && currentlevel <= groundlevel; }
 void terminate(const char* routine, const char* msg) {
     fprintf(stderr, "reference terminate() in %s: %s\n", routine, msg);
     abort();
-}
-
-/* src/utils/flowUtils.F90:674-703 with eint's cpConstant branch (:742-761); gammaConstant == gammaInf here */
-void etot(double* rho, double* u, double* v, double* w, double* p, double* k, double* etotal, int* correctfork) {
-    double ovgm1 = one / (gammainf - one);
-    double eint = ovgm1 * (*p) / (*rho);
-    if (*correctfork) {
-        double factk = ovgm1 * (five * third - gammainf);
-        eint = eint - factk * (*k);
-    }
-    *etotal = (*rho) * (eint + half * ((*u) * (*u) + (*v) * (*v) + (*w) * (*w)));
 }

@@ -31,6 +31,12 @@ extern double turbresscale[4];
 /* iteration */
 extern int currentlevel, groundlevel;
 extern double rfil, totalr0, totalr;
+/* more of inputPhysics / inputIteration / inputUnsteady / iteration / block used by the smoothers */
+extern int cpmodel, rkstage, resaveraging, ndom, exchangepressureearly, lowspeedpreconditioner;
+extern double gammaconstant, musuthdim, tsuthdim, ssuthdim, muref, pinf;
+extern double cfl, cflcoarse, cfllimit, smoop, deltat;
+extern double etark[6], cdisrk[6], coeftime[8];
+extern double *bp_wn, *bp_pn, *bp_scratch;
 /* inputTimeSpectral, oversetData, turbMod */
 extern int ntimeintervalsspectral, oversetpresent, secondord;
 /* paramTurb (SA constants) and module sa (derived constants set in sa_block) */
@@ -46,10 +52,14 @@ extern double *bp_ux, *bp_uy, *bp_uz, *bp_vx, *bp_vy, *bp_vz, *bp_wx, *bp_wy, *b
 extern int *bp_iblank, *bp_pori, *bp_porj, *bp_pork;
 extern double *bp_rotmatrixi, *bp_rotmatrixj, *bp_rotmatrixk;
 
-/* utils / flowUtils procedures the translated code calls */
+/* utils procedures the translated code calls */
 int getcorrectfork(void);                           /* src/utils/utils.F90 getCorrectForK */
 void terminate(const char* routine, const char* msg); /* src/utils/utils.F90 terminate */
-void etot(double* rho, double* u, double* v, double* w, double* p, double* k, double* etotal,
-          int* correctfork);                        /* src/utils/flowUtils.F90 eTot (cpConstant) */
+
+/* driver-level procedures outside the translated set (no-op stubs, see ref_env.c) */
+void setpointers(int* nn, int* level, int* sps);
+void whalo1(int* level, int* start, int* end, int* commpressure, int* commgamma, int* commviscous);
+void whalo2(int* level, int* start, int* end, int* commpressure, int* commgamma, int* commviscous);
+void applyallbc(int* secondhalo);
 
 #endif

@@ -15,16 +15,24 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "..", "oracle", "_ref", "libblockette_ref.so")
+_SO = os.path.join(_HERE, "_ref", "libblockette_ref.so")
+_SO_FAST = os.path.join(_HERE, "_ref", "libblockette_ref_fast.so")
 
 FLAG_DISS_APPROX, FLAG_VISC_APPROX, FLAG_UPDATE_INTERMED, FLAG_FLOW, FLAG_TURB, FLAG_STORE_WALL = 1, 2, 4, 8, 16, 32
 
 
-def available():
-    return os.path.exists(_SO)
+def available(fast=False):
+    return os.path.exists(_SO_FAST if fast else _SO)
 
 
 _L = None
+_BOUND = None
+
+
+def use_fast(flag=True):
+    """select the -O3 -ffast-math build (timing only; the strict build is the one tests compare with)"""
+    global _L
+    _L = C.CDLL(os.path.abspath(_SO_FAST if flag else _SO))
 
 
 def lib():
@@ -48,6 +56,7 @@ def _setp(name, arr):
 
 # reference enumerations (src/modules/constants.F90) for the values AdfbParams encodes differently
 _REF_SPACEDISCR = {1: 1, 2: 2, 4: 9}            # dissScalar, dissMatrix, upwind
+_REF_RESAVG = {0: 0, 1: 1, 2: 2}                # noResAveraging, alwaysResAveraging, alternateResAveraging
 _REF_LIMITER = {0: 1, 1: 2, 2: 3, 3: 4}         # firstOrder, noLimiter, vanAlbeda, minmod
 
 
@@ -67,6 +76,17 @@ def set_params(prm, nw, rfil=1.0):
               "acousticScaleFactor", "kappaCoef", "rsaK", "rsaCb1", "rsaCb2", "rsaCb3", "rsaCv1", "rsaCw1", "rsaCw2",
               "rsaCw3", "rsaCt3", "rsaCt4", "rsaCrot"):
         _setd(n.lower(), getattr(prm, n))
+    # cpConstant gas; Sutherland constants are stored non-dimensional in AdfbParams (muRef = Tref = 1)
+    _seti("cpmodel", 1); _setd("gammaconstant", prm.gammaInf); _setd("pinf", prm.pInf)
+    _setd("musuthdim", prm.muSuth); _setd("tsuthdim", prm.TSuth); _setd("ssuthdim", prm.SSuth); _setd("muref", 1.0)
+    # smoothers (inputIteration)
+    _setd("cfl", prm.cfl); _setd("cflcoarse", prm.cflCoarse); _setd("cfllimit", prm.cflLimit)
+    _setd("smoop", prm.smoop); _seti("resaveraging", _REF_RESAVG[prm.resAveraging]); _seti("ndom", 1)
+    _seti("exchangepressureearly", 0); _seti("lowspeedpreconditioner", 0)
+    eta = (C.c_double * 6).in_dll(lib(), "etark")
+    cdis = (C.c_double * 6).in_dll(lib(), "cdisrk")
+    for q in range(6):
+        eta[q], cdis[q] = prm.etaRK[q], prm.cdisRK[q]
     _setd("timeref", 1.0); _setd("tref", 1.0); _setd("rfil", rfil); _setd("totalr", 1.0); _setd("totalr0", 1.0)
     # module sa derived constants, src/turbulence/sa.F90:123-126
     _setd("cv13", prm.rsaCv1 ** 3); _setd("kar2inv", 1.0 / (prm.rsaK ** 2))
@@ -94,9 +114,13 @@ class RefBlock:
         self.a["gamma"] = np.full(box, prm.gammaInf, order="F")
         for n in ("sfacei", "sfacej", "sfacek"):
             self.a[n] = np.zeros(box, order="F")
-        self.a["dw"] = np.zeros(box + (hb.nw,), order="F")
+        self.a["dw"] = f(hb.dw.copy(order="F"))
         self.a["fw"] = np.zeros(box + (5,), order="F")
-        for n in self.OUT[1:]:
+        self.a["wn"] = f(hb.wn.copy(order="F"))
+        self.a["pn"] = f(hb.pn.copy(order="F"))
+        self.a["scratch"] = f(hb.scratch.copy(order="F"))
+        self.a["dtl"] = f(hb.dtl.copy(order="F"))
+        for n in self.OUT[2:]:
             self.a[n] = np.zeros(box, order="F")
         self.a["iblank"] = f(hb.iblank.astype(np.int32).copy(order="F"))
         for ref, mine in (("pori", "porI"), ("porj", "porJ"), ("pork", "porK")):
@@ -118,9 +142,33 @@ def residual_core(hb, prm, flags=FLAG_FLOW | FLAG_TURB, rfil=1.0):
     """blocketteResCore (src/NKSolver/blockette.F90:299-753) on one block; returns the RefBlock
     whose arrays hold dw (and, with FLAG_UPDATE_INTERMED, dtl/rad*/aa/nodal gradients)."""
     set_params(prm, hb.nw, rfil)
+    global _BOUND
     rb = RefBlock(hb, prm)
     rb.bind()
+    _BOUND = rb  # the library holds raw pointers into rb's arrays: keep them alive for call_core()
     args = [C.byref(C.c_int(1 if flags & m else 0)) for m in
             (FLAG_DISS_APPROX, FLAG_VISC_APPROX, FLAG_UPDATE_INTERMED, FLAG_FLOW, FLAG_TURB, FLAG_STORE_WALL)]
     lib().blocketterescore(*args)
     return rb
+
+
+def call(hb, prm, routine, *int_args, rkstage=1, rfil=1.0):
+    """bind `hb` as the current block (blockPointers) and call one translated reference procedure
+    whose dummies are all integer/logical by reference, e.g.
+    call(hb, prm, "smoothers_executerkstage", rkstage=3) or
+    call(hb, prm, "flowutils_computelamviscosity", 1).  Returns the RefBlock (arrays in .a)."""
+    global _BOUND
+    set_params(prm, hb.nw, rfil)
+    _seti("rkstage", rkstage)
+    rb = RefBlock(hb, prm)
+    rb.bind()
+    _BOUND = rb
+    getattr(lib(), routine)(*[C.byref(C.c_int(int(v))) for v in int_args])
+    return rb
+
+
+def call_core(flags=FLAG_FLOW | FLAG_TURB):
+    """re-run blocketteResCore on the block bound by the last residual_core() (timing loops)"""
+    args = [C.byref(C.c_int(1 if flags & m else 0)) for m in
+            (FLAG_DISS_APPROX, FLAG_VISC_APPROX, FLAG_UPDATE_INTERMED, FLAG_FLOW, FLAG_TURB, FLAG_STORE_WALL)]
+    lib().blocketterescore(*args)

@@ -11,7 +11,7 @@ Runs without a GPU.  Skips when the library was not built (no /root/reference at
 import numpy as np
 import pytest
 
-import refblockette as rb
+from oracle import refblockette as rb
 from util import case
 
 pytestmark = pytest.mark.skipif(not rb.available(), reason="oracle/_ref/libblockette_ref.so not built")

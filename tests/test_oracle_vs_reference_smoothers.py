@@ -1,0 +1,118 @@
+"""Pins the oracle's state preparation and smoother stages against the reference's own routines
+(translated Fortran -> C, oracle/_ref, see test_oracle_vs_reference.py):
+
+  flowUtils.F90   computePressureSimple, computeLamViscosity, computeEtotBlock
+  turbUtils.F90   computeEddyViscosity / saEddyViscosity
+  residuals.F90   residualAveraging :1785-2080, computeDwDADI :1038-1755 (+ tridiagSolve)
+  smoothers.F90   executeRkStage :90-382, executeDADIStep :425-693
+
+The driver-level calls inside those routines (setPointers, applyAllBC, whalo1/2) are no-op stubs
+(oracle/ref_env.c): one block, and the oracle side is run with zero BC subfaces, so both sides
+execute exactly the interior update.  Comparison is bit-exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import refblockette as rb
+from util import case
+
+pytestmark = pytest.mark.skipif(not rb.available(), reason="oracle/_ref/libblockette_ref.so not built")
+
+
+def _oracle(hb, prm):
+    from oracle.pyoracle import Oracle
+
+    ho = hb.copy()
+    ho.subfaces = []  # BCs are applied outside the translated routines
+    return ho, Oracle(ho, prm)
+
+
+def _eq(a, b, what):
+    assert np.array_equal(a, b), "%s differs: max abs %.3e" % (what, np.abs(a - b).max())
+
+
+def _residual_state(shape, options, seed=314):
+    """block with a freshly computed residual, time step and spectral radii (what the smoothers see)"""
+    from oracle.pyoracle import Oracle
+
+    prm, hb = case(*shape, options, seed=seed)
+    o = Oracle(hb, prm)
+    o.time_step(True)
+    o.residual_block(1.0)
+    hb.wn[...] = hb.w[..., :5]
+    hb.pn[...] = hb.p
+    return prm, hb
+
+
+@pytest.mark.parametrize("eq", ["Euler", "laminar NS", "RANS"])
+@pytest.mark.parametrize("halos", [0, 1])
+def test_state_preparation(eq, halos):
+    prm, hb = case(11, 9, 10, {"equationType": eq})
+    d = hb.d
+    ho, o = _oracle(hb, prm)
+    o.pressure(bool(halos)); o.lam_viscosity(bool(halos)); o.eddy_viscosity(bool(halos))
+    r = rb.call(hb, prm, "flowutils_computepressuresimple", halos)
+    _eq(r.a["p"], ho.p, "p")
+    hb2 = hb.copy(); hb2.p[...] = ho.p
+    r = rb.call(hb2, prm, "flowutils_computelamviscosity", halos)
+    _eq(r.a["rlv"], ho.rlv, "rlv")
+    hb2.rlv[...] = ho.rlv
+    r = rb.call(hb2, prm, "turbutils_computeeddyviscosity", halos)
+    _eq(r.a["rev"], ho.rev, "rev")
+    # computeEtotBlock over the owned range
+    import ctypes as C
+    o.L.orc_etot(C.byref(o.ob), C.byref(prm), 2, d.il, 2, d.jl, 2, d.kl)
+    r = rb.call(hb2, prm, "flowutils_computeetotblock", 2, d.il, 2, d.jl, 2, d.kl, 0)
+    _eq(r.a["w"][..., 4], ho.w[..., 4], "rhoE")
+
+
+@pytest.mark.parametrize("shape", [(12, 9, 10), (5, 17, 6), (3, 3, 3)])
+def test_residual_averaging(shape):
+    prm, hb = _residual_state(shape, {"equationType": "RANS", "resAveraging": "always"})
+    ho, o = _oracle(hb, prm)
+    o.residual_averaging()
+    r = rb.call(hb, prm, "residuals_residualaveraging")
+    ow = hb.d.owned()
+    _eq(r.a["dw"][ow][..., :5], ho.dw[ow][..., :5], "dw")
+
+
+@pytest.mark.parametrize("eq", ["Euler", "RANS"])
+@pytest.mark.parametrize("stage", [1, 2, 5])
+@pytest.mark.parametrize("avg", ["never", "alternate"])
+def test_rk_stage(eq, stage, avg):
+    prm, hb = _residual_state((12, 9, 10), {"equationType": eq, "resAveraging": avg})
+    ho, o = _oracle(hb, prm)
+    o.rk_stage(stage)
+    r = rb.call(hb, prm, "smoothers_executerkstage", rkstage=stage)
+    ow = hb.d.owned()
+    for l in range(5):
+        _eq(r.a["w"][ow][..., l], ho.w[ow][..., l], "w[%d]" % l)
+    _eq(r.a["p"][ow], ho.p[ow], "p")
+    _eq(r.a["rlv"][ow], ho.rlv[ow], "rlv")
+    _eq(r.a["rev"][ow], ho.rev[ow], "rev")
+
+
+@pytest.mark.parametrize("eq", ["Euler", "laminar NS", "RANS"])
+def test_compute_dw_dadi(eq):
+    prm, hb = _residual_state((11, 10, 9), {"equationType": eq})
+    ow = hb.d.owned()
+    # executeDADIStep scales the residual by -cfl*dtl*vol before computeDwDADI
+    hb.dw[ow + (slice(0, 5),)] *= (-prm.cfl * hb.dtl[ow] * hb.vol[ow])[..., None]
+    ho, o = _oracle(hb, prm)
+    o.compute_dw_dadi()
+    r = rb.call(hb, prm, "residuals_computedwdadi")
+    for l in range(5):
+        _eq(r.a["dw"][ow][..., l], ho.dw[ow][..., l], "dw[%d]" % l)
+
+
+@pytest.mark.parametrize("eq", ["Euler", "RANS"])
+@pytest.mark.parametrize("avg", ["never", "always"])
+def test_dadi_step(eq, avg):
+    prm, hb = _residual_state((10, 12, 9), {"equationType": eq, "resAveraging": avg, "smoother": "DADI"})
+    ho, o = _oracle(hb, prm)
+    o.dadi_step()
+    r = rb.call(hb, prm, "smoothers_executedadistep", rkstage=0)
+    ow = hb.d.owned()
+    for l in range(5):
+        _eq(r.a["w"][ow][..., l], ho.w[ow][..., l], "w[%d]" % l)
+    _eq(r.a["p"][ow], ho.p[ow], "p")
