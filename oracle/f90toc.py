@@ -290,6 +290,15 @@ class Scope:
     def __init__(self, parent=None):
         self.parent = parent
         self.arrays, self.types, self.renames, self.ptr_scalars, self.consts = {}, {}, {}, set(), {}
+        self.cnames = {}  # scalar name -> C identifier when they differ (exported module variables)
+
+    def cname_of(self, n):
+        s = self
+        while s:
+            if n in s.types:
+                return s.cnames.get(n, n)
+            s = s.parent
+        return n
 
     def lookup_array(self, n):
         s = self
@@ -463,7 +472,7 @@ class Translator:
             if sc.is_ptr_scalar(n):
                 return "(*%s)" % n
             if sc.lookup_type(n):
-                return n
+                return sc.cname_of(n)
             n2 = sc.rename(n)
             if n2 in self.env.arrays:
                 arr = self.env.arrays[n2]
@@ -985,6 +994,26 @@ class UnitTranslator:
             return [ind + "return;"]
         if l == "continue":
             return [ind + ";"]
+        if re.match(r"^(print|write)\b", l):  # diagnostics only
+            return [ind + "/* %s */;" % l.replace("*/", "* /")]
+        if l == "stop" or l.startswith("stop "):
+            return [ind + "abort();"]
+        m = re.match(r"^allocate\s*\((.*)\)$", l)
+        if m:
+            node = Parser(tokenize(m.group(1))).expr()
+            arr = sc.lookup_array(node[1][1])
+            p, out, total, st = arr.cname, [], [], "1"
+            for dd, sub in enumerate(node[2]):
+                lo = tr.ex(sub[1], sc) if sub[0] == "range" else "1"
+                hi = tr.ex(sub[2], sc) if sub[0] == "range" else tr.ex(sub, sc)
+                out.append(ind + "%s_lb[%d] = %s; %s_n[%d] = (%s) - (%s) + 1; %s_s[%d] = %s;" % (p, dd, lo, p, dd, hi, lo, p, dd, st))
+                st = "%s * %s_n[%d]" % (st, p, dd)
+            out.append(ind + "%s = (%s*)malloc(sizeof(%s) * (%s));" % (p, arr.ctype, arr.ctype, st))
+            return out
+        m = re.match(r"^deallocate\s*\((\w+)\)$", l)
+        if m:
+            arr = sc.lookup_array(m.group(1))
+            return [ind + "free(%s); %s = 0;" % (arr.cname, arr.cname)]
         m = re.match(r"^call\s+(\w+)\s*(\((.*)\))?$", l)
         if m:
             args = []
@@ -1041,8 +1070,19 @@ static inline int f90_ipow(int x, int n) { int r = 1; for (int q = 0; q < n; q++
 def translate_module(src_path, only, env, rename_modules, patches=(), defined=(), tr=None, prefix=""):
     text = open(src_path).read()
     lines = preprocess(text, defined)
-    for pat, rep in patches:
-        lines = [re.sub(pat, rep, l) for l in lines]
+    for patch in patches:
+        if patch[0] == "block":  # ("block", first-line regex, last-line regex): drop the lines in between, inclusive
+            out, skipping = [], False
+            for l in lines:
+                if not skipping and re.search(patch[1], l):
+                    skipping = True
+                if not skipping:
+                    out.append(l)
+                elif re.search(patch[2], l):
+                    skipping = False
+            lines = out
+        else:
+            lines = [re.sub(patch[0], patch[1], l) for l in lines]
     lines = [l for l in lines if l is not None and l.strip() != ""]
     if tr is None:
         tr = Translator(env, rename_modules)
@@ -1069,7 +1109,12 @@ def translate_module(src_path, only, env, rename_modules, patches=(), defined=()
             if spec is not None:
                 dims = dims_from_spec(spec, tr, msc)
                 if any(x is None for x in dims):
-                    continue  # allocatable / pointer module array: must come from ref_env.h
+                    if "allocatable" in attrs:  # allocate()/deallocate() manage it at run time
+                        rank = len(dims)
+                        mdecl.append("static %s* %s = 0; static long %s_lb[%d], %s_n[%d], %s_s[%d];" % (
+                            ctype, en, en, rank, en, rank, en, rank))
+                        msc.arrays[en] = Array.descriptor(en, ctype, rank)
+                    continue  # pointer module array: only usable if ref_env.h provides it
                 total = " * ".join("(%s)" % x[1] for x in dims)
                 mdecl.append("static %s %s_[%s];" % (ctype, en, total))
                 msc.arrays[en] = Array(en + "_", ctype, dims)
@@ -1079,6 +1124,13 @@ def translate_module(src_path, only, env, rename_modules, patches=(), defined=()
                     msc.consts[en] = True
                     mdecl.append("enum { %s = %s };" % (en, tr.ex(parse_expr(init), msc)) if ctype == "int" else
                                  "static const %s %s = %s;" % (ctype, en, tr.ex(parse_expr(init), msc)))
+                elif prefix:
+                    # module variable of a named module: exported, other modules import it by `use`
+                    msc.cnames[en] = prefix + en
+                    mdecl.append("%s %s = 0;" % (ctype, prefix + en))
+                    tr.all_protos.append("extern %s %s;" % (ctype, prefix + en))
+                    if ctype == "int":
+                        tr.env.ints.add(prefix + en)
                 else:
                     mdecl.append("static %s %s = 0;" % (ctype, en))
     body = lines[q + 1:]

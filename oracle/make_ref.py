@@ -38,6 +38,13 @@ PATCHES = [
     # wall stress tensor storage into viscSubface (storeWallTensor): surface-force path, out of scope
     (r"^viscsubface\(.*$", "continue"),
     (r"visc[ijk]m(in|ax)pointer\([^()]*\)", "0"),
+    # sa_block: the turbulence BC treatment (bmt matrices in, halo values out) is done by the harness;
+    # steady flow, so the unsteady term is identically absent (turbUtils.F90:456-460 returns at once)
+    (r"^call bcturbtreatment$", "continue"),
+    (r"^call applyallturbbcthisblock\(.*$", "continue"),
+    (r"^call unsteadyturbterm\(.*$", "continue"),
+    # saSolve: wall-function branch (wallFunctions = .false. on the path) uses BCData/viscSubface
+    ("block", r"^testwallfunctions: if", r"^end if testwallfunctions"),
     # module-wide `use X` without only-list inside routines: names resolve through ref_env.h
 ]
 
@@ -50,7 +57,7 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  strain vorticity katolaunder kpresent eddymodel rotationalperiodic correctfork righthanded
  usedisscontinuation nbkglobal sectionid ntimeintervalsspectral normalflux boundflux internalflux
  lumpeddiss fullturb cpmodel rkstage resaveraging ndom exchangepressureearly lowspeedpreconditioner
- noresaveraging alwaysresaveraging alternateresaveraging
+ noresaveraging alwaysresaveraging alternateresaveraging turbrelax turbrelaximplicit turbrelaxexplicit
  bp_nx bp_ny bp_nz bp_il bp_jl bp_kl bp_ie bp_je bp_ke bp_ib bp_jb bp_kb bp_addgridvelocities
  bp_righthanded bp_sectionid bp_blockismoving bp_nbkglobal""".split()
 
@@ -72,6 +79,10 @@ def env_arrays():
     arrs["bp_fw"] = A("bp_fw", "double", box("nwf"))
     arrs["bp_wn"] = A("bp_wn", "double", box("nwf"))
     arrs["bp_pn"] = A("bp_pn", "double", box())
+    # turbulence BC matrices of the six block faces (block.F90: bmti1(je,ke,nt1:nt2,nt1:nt2) ...)
+    for n, (a, b) in {"bmti1": ("bp_je", "bp_ke"), "bmti2": ("bp_je", "bp_ke"), "bmtj1": ("bp_ie", "bp_ke"),
+                      "bmtj2": ("bp_ie", "bp_ke"), "bmtk1": ("bp_ie", "bp_je"), "bmtk2": ("bp_ie", "bp_je")}.items():
+        arrs["bp_" + n] = A("bp_" + n, "double", [("1", a), ("1", b), ("nt1", "1"), ("nt1", "1")])
     arrs["bp_scratch"] = A("bp_scratch", "double", box(10))
     arrs["etark"] = A("etark", "double", [("1", "6")])
     arrs["cdisrk"] = A("cdisrk", "double", [("1", "6")])
@@ -106,12 +117,13 @@ UNITS = [
     ("utils/flowUtils.F90", "flowutils_", ["computeetotblock", "computelamviscosity", "computepressuresimple",
                                            "etot", "eint"], ("USE_TAPENADE",)),
     ("NKSolver/blockette.F90", "", ROUTINES, ()),
-    ("turbulence/turbUtils.F90", "turbutils_", ["computeeddyviscosity", "saeddyviscosity"], ()),
+    ("turbulence/turbUtils.F90", "turbutils_", ["computeeddyviscosity", "saeddyviscosity", "turbadvection"], ()),
+    ("turbulence/sa.F90", "sa_", ["sa_block", "sasource", "saviscous", "saresscale", "sasolve"], ()),
     ("solver/residuals.F90", "residuals_", ["residualaveraging", "computedwdadi", "tridiagsolve"], ()),
     ("solver/smoothers.F90", "smoothers_", ["executerkstage", "executedadistep"], ()),
 ]
 RENAME_MODULES = {"blockpointers": "bp_", "flowutils": "flowutils_", "turbutils": "turbutils_",
-                  "residuals": "residuals_", "smoothers": "smoothers_"}
+                  "residuals": "residuals_", "smoothers": "smoothers_", "sa": "sa_"}
 
 
 def main():

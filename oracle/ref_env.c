@@ -19,7 +19,6 @@ int currentlevel = 1, groundlevel = 1;
 double rfil = 1.0, totalr0 = 1.0, totalr = 1.0;
 int ntimeintervalsspectral = 1, oversetpresent = 0, secondord = 0;
 double rsak, rsacb1, rsacb2, rsacb3, rsacv1, rsacw1, rsacw2, rsacw3, rsact1, rsact2, rsact3, rsact4, rsacrot;
-double cv13, kar2inv, cw36, cb3inv;
 int bp_nx, bp_ny, bp_nz, bp_il, bp_jl, bp_kl, bp_ie, bp_je, bp_ke, bp_ib, bp_jb, bp_kb;
 int bp_addgridvelocities = 0, bp_righthanded = 1, bp_sectionid = 1, bp_blockismoving = 0, bp_nbkglobal = 1;
 double *bp_w, *bp_p, *bp_gamma, *bp_rlv, *bp_rev, *bp_vol, *bp_volref, *bp_d2wall, *bp_shocksensor;
@@ -35,6 +34,9 @@ double gammaconstant, musuthdim, tsuthdim, ssuthdim, muref = 1.0, pinf;
 double cfl, cflcoarse, cfllimit, smoop, deltat = 1.0;
 double etark[6], cdisrk[6], coeftime[8];
 double *bp_wn, *bp_pn, *bp_scratch;
+double *bp_bmti1, *bp_bmti2, *bp_bmtj1, *bp_bmtj2, *bp_bmtk1, *bp_bmtk2;
+int turbrelax = 2 /* turbRelaxImplicit */;
+double alfaturb;
 
 /* Driver-level procedures that are NOT part of the translated set.  One block, pointers bound by
    the harness, boundary conditions and halo exchange applied by the harness around the call. */

@@ -37,11 +37,13 @@ extern double gammaconstant, musuthdim, tsuthdim, ssuthdim, muref, pinf;
 extern double cfl, cflcoarse, cfllimit, smoop, deltat;
 extern double etark[6], cdisrk[6], coeftime[8];
 extern double *bp_wn, *bp_pn, *bp_scratch;
+extern double *bp_bmti1, *bp_bmti2, *bp_bmtj1, *bp_bmtj2, *bp_bmtk1, *bp_bmtk2;
+extern int turbrelax;
+extern double alfaturb;
 /* inputTimeSpectral, oversetData, turbMod */
 extern int ntimeintervalsspectral, oversetpresent, secondord;
-/* paramTurb (SA constants) and module sa (derived constants set in sa_block) */
+/* paramTurb (SA constants) */
 extern double rsak, rsacb1, rsacb2, rsacb3, rsacv1, rsacw1, rsacw2, rsacw3, rsact1, rsact2, rsact3, rsact4, rsacrot;
-extern double cv13, kar2inv, cw36, cb3inv;
 /* blockPointers: extents and arrays of the current block, uniform box (0:ib,0:jb,0:kb) */
 extern int bp_nx, bp_ny, bp_nz, bp_il, bp_jl, bp_kl, bp_ie, bp_je, bp_ke, bp_ib, bp_jb, bp_kb;
 extern int bp_addgridvelocities, bp_righthanded, bp_sectionid, bp_blockismoving, bp_nbkglobal;

@@ -89,8 +89,9 @@ def set_params(prm, nw, rfil=1.0):
         eta[q], cdis[q] = prm.etaRK[q], prm.cdisRK[q]
     _setd("timeref", 1.0); _setd("tref", 1.0); _setd("rfil", rfil); _setd("totalr", 1.0); _setd("totalr0", 1.0)
     # module sa derived constants, src/turbulence/sa.F90:123-126
-    _setd("cv13", prm.rsaCv1 ** 3); _setd("kar2inv", 1.0 / (prm.rsaK ** 2))
-    _setd("cw36", prm.rsaCw3 ** 6); _setd("cb3inv", 1.0 / prm.rsaCb3)
+    _setd("sa_cv13", prm.rsaCv1 ** 3); _setd("sa_kar2inv", 1.0 / (prm.rsaK ** 2))
+    _setd("sa_cw36", prm.rsaCw3 ** 6); _setd("sa_cb3inv", 1.0 / prm.rsaCb3)
+    _setd("alfaturb", prm.alfaTurb); _seti("turbrelax", 2)  # turbRelaxImplicit
     trs = (C.c_double * 4).in_dll(lib(), "turbresscale")
     trs[0] = prm.turbResScale
 
@@ -101,7 +102,7 @@ class RefBlock:
     OUT = ["dw", "dtl", "aa", "radi", "radj", "radk", "ux", "uy", "uz", "vx", "vy", "vz", "wx", "wy", "wz", "qx",
            "qy", "qz"]
 
-    def __init__(self, hb, prm):
+    def __init__(self, hb, prm, bmt=None):
         d = hb.d
         self.hb = hb
         box = d.box
@@ -122,6 +123,15 @@ class RefBlock:
         self.a["dtl"] = f(hb.dtl.copy(order="F"))
         for n in self.OUT[2:]:
             self.a[n] = np.zeros(box, order="F")
+        # turbulence BC matrices per block face (block.F90 bmti1(je,ke,nt1:nt2,nt1:nt2) ...); `bmt` is a box
+        # array holding the scalar SA value of each boundary face at its first-halo cell
+        if bmt is None:
+            bmt = np.zeros(box, order="F")
+        sl = {"bmti1": bmt[1, 1:d.je + 1, 1:d.ke + 1], "bmti2": bmt[d.ie, 1:d.je + 1, 1:d.ke + 1],
+              "bmtj1": bmt[1:d.ie + 1, 1, 1:d.ke + 1], "bmtj2": bmt[1:d.ie + 1, d.je, 1:d.ke + 1],
+              "bmtk1": bmt[1:d.ie + 1, 1:d.je + 1, 1], "bmtk2": bmt[1:d.ie + 1, 1:d.je + 1, d.ke]}
+        for n, v in sl.items():
+            self.a[n] = f(np.array(v, dtype=np.float64, order="F"))
         self.a["iblank"] = f(hb.iblank.astype(np.int32).copy(order="F"))
         for ref, mine in (("pori", "porI"), ("porj", "porJ"), ("pork", "porK")):
             self.a[ref] = f(getattr(hb, mine).astype(np.int32).copy(order="F"))
@@ -152,7 +162,7 @@ def residual_core(hb, prm, flags=FLAG_FLOW | FLAG_TURB, rfil=1.0):
     return rb
 
 
-def call(hb, prm, routine, *int_args, rkstage=1, rfil=1.0):
+def call(hb, prm, routine, *int_args, rkstage=1, rfil=1.0, bmt=None):
     """bind `hb` as the current block (blockPointers) and call one translated reference procedure
     whose dummies are all integer/logical by reference, e.g.
     call(hb, prm, "smoothers_executerkstage", rkstage=3) or
@@ -160,7 +170,7 @@ def call(hb, prm, routine, *int_args, rkstage=1, rfil=1.0):
     global _BOUND
     set_params(prm, hb.nw, rfil)
     _seti("rkstage", rkstage)
-    rb = RefBlock(hb, prm)
+    rb = RefBlock(hb, prm, bmt)
     rb.bind()
     _BOUND = rb
     getattr(lib(), routine)(*[C.byref(C.c_int(int(v))) for v in int_args])

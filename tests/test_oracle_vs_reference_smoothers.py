@@ -116,3 +116,27 @@ def test_dadi_step(eq, avg):
     for l in range(5):
         _eq(r.a["w"][ow][..., l], ho.w[ow][..., l], "w[%d]" % l)
     _eq(r.a["p"][ow], ho.p[ow], "p")
+
+
+@pytest.mark.parametrize("shape", [(12, 9, 10), (4, 15, 7)])
+@pytest.mark.parametrize("opt", [{}, {"turbulenceOrder": "second order"}, {"turbulenceProduction": "vorticity"},
+                                 {"useApproxSA": True}, {"useRotationSA": True}])
+def test_sa_block_ddadi(shape, opt):
+    """sa_block (src/turbulence/sa.F90:16-86): saSource, turbAdvection (turbUtils.F90:828-1553), saViscous,
+    saResScale, saSolve (DD-ADI, :717-1267), saEddyViscosity.  The turbulence BC matrices bmt* are an input
+    (bcTurbTreatment is outside the translated set): taken from the oracle's own treatment."""
+    o_ = {"equationType": "RANS"}
+    o_.update(opt)
+    prm, hb = case(*shape, o_)
+    from oracle.pyoracle import Oracle
+
+    ho = hb.copy()
+    Oracle(ho, prm).sa_block()
+    bmt = ho.scratch[..., 2].copy(order="F")
+    assert np.abs(bmt).max() == 1.0
+    r = rb.call(hb, prm, "sa_sa_block", 0, bmt=bmt)
+    ow = hb.d.owned()
+    _eq(r.a["dw"][ow][..., 5], ho.dw[ow][..., 5], "dw(itu1) after saResScale")
+    _eq(r.a["w"][ow][..., 5], ho.w[ow][..., 5], "nuTilde after the DD-ADI update")
+    _eq(r.a["rev"][ow], ho.rev[ow], "rev")
+    assert np.abs(ho.w[ow][..., 5] - hb.w[ow][..., 5]).max() > 0.0
