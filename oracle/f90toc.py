@@ -266,9 +266,16 @@ def parse_expr(s):
 
 # ----------------------------------------------------------------------------- symbols
 class Array:
-    def __init__(self, cname, ctype, bounds, pointer=False, strides=None):
+    def __init__(self, cname, ctype, bounds, pointer=False, strides=None, base=None):
         self.cname, self.ctype, self.bounds, self.pointer = cname, ctype, bounds, pointer  # bounds: list of (lo_c, ext_c)
         self.strides = strides  # explicit per-dimension strides (Fortran pointer arrays with run-time descriptors)
+        # index origin per dimension: the subscript value that maps to offset 0 of `cname`.  Normally the declared
+        # lower bound; different for the blockPointers arrays, which ref_env.h stores in one uniform box (0:ib,..)
+        # while their DECLARED bounds (needed for `:` sections) are the reference's
+        self.base = base
+
+    def origin(self):
+        return list(self.base) if self.base else [lo for lo, _ in self.bounds]
 
     def stride_list(self):
         if self.strides:
@@ -424,7 +431,7 @@ class Translator:
         if len(subs) != len(arr.bounds):
             raise SyntaxError("rank mismatch for %s: %d subscripts, rank %d" % (arr.cname, len(subs), len(arr.bounds)))
         terms = []
-        for (lo, ext), s, stride in zip(arr.bounds, subs, arr.stride_list()):
+        for lo, s, stride in zip(arr.origin(), subs, arr.stride_list()):
             if s[0] == "range":
                 s_c = loopmap.pop(0)
             else:
@@ -590,7 +597,7 @@ class Translator:
 
     def index_c(self, arr, subs, sc):
         terms = []
-        for (lo, ext), s, stride in zip(arr.bounds, subs, arr.stride_list()):
+        for lo, s, stride in zip(arr.origin(), subs, arr.stride_list()):
             s_c = s[1] if s[0] == "cexpr" else self.ex(s, sc)
             terms.append("((%s) - (%s)) * (%s)" % (s_c, lo, stride))
         return "%s[%s]" % (arr.cname, " + ".join(terms))
@@ -612,17 +619,17 @@ class Translator:
         if T is None:
             raise SyntaxError("unknown pointer target %r" % (rhs,))
         out, off, k = [], [], 0
-        for d, ((lo, ext), st, sb) in enumerate(zip(T.bounds, T.stride_list(), subs)):
+        for d, ((lo, ext), st, sb, org) in enumerate(zip(T.bounds, T.stride_list(), subs, T.origin())):
             if sb[0] == "range":
                 lo_r = self.ex(sb[1], sc) if sb[1] is not None else lo
                 hi_r = self.ex(sb[2], sc) if sb[2] is not None else "(%s) + (%s) - 1" % (lo, ext)
                 # a pointer to a SECTION has lower bound 1; to a whole array it inherits the bounds
                 out.append(ind + "%s_lb[%d] = %s; %s_n[%d] = (%s) - (%s) + 1; %s_s[%d] = %s;" % (
                     p, k, lo if whole else "1", p, k, hi_r, lo_r, p, k, st))
-                off.append("((%s) - (%s)) * (%s)" % (lo_r, lo, st))
+                off.append("((%s) - (%s)) * (%s)" % (lo_r, org, st))
                 k += 1
             else:
-                off.append("((%s) - (%s)) * (%s)" % (self.ex(sb, sc), lo, st))
+                off.append("((%s) - (%s)) * (%s)" % (self.ex(sb, sc), org, st))
         if k != len(P.bounds):
             raise SyntaxError("rank mismatch in pointer association of %s" % p)
         out.append(ind + "%s = &%s[%s];" % (p, T.cname, " + ".join(off)))
@@ -645,6 +652,9 @@ class Translator:
                 arr = sc.lookup_array(n) or self.env.arrays.get(sc.rename(n))
                 if arr:
                     cargs.append(arr.cname)
+                    if sig and q < len(sig) and isinstance(sig[q][2], tuple):
+                        cargs.append("(long[]){%s}" % ", ".join(ext for _, ext in arr.bounds))
+                        cargs.append("(long[]){%s}" % ", ".join(arr.stride_list()))
                     continue
                 if sc.is_ptr_scalar(n):
                     cargs.append(n)
@@ -657,7 +667,8 @@ class Translator:
                 continue
             cargs.append(self.by_value(a, sc, want))
         if sig:
-            cargs += ["NULL"] * (len(sig) - len(cargs))
+            want_n = sum(3 if isinstance(k, tuple) else 1 for _, _, k in sig)
+            cargs += ["NULL"] * (want_n - len(cargs))
         return "%s(%s);" % (name2, ", ".join(cargs))
 
     def by_value(self, a, sc, want):
@@ -774,10 +785,15 @@ class UnitTranslator:
                         break
                     continue
                 ctype, attrs, ents = d
-                isarr = any(x.startswith("dimension") for x in attrs)
+                dimattr = next((x for x in attrs if x.startswith("dimension")), None)
                 for en, dspec, _ in ents:
                     if en in argn:
-                        types[en] = (ctype, isarr or dspec is not None)
+                        spec = dspec or (dimattr[dimattr.index("(") + 1:-1] if dimattr else None)
+                        kind = False
+                        if spec is not None:
+                            parts = [x.strip() for x in split_top(spec, ",")]
+                            kind = ("desc", len(parts)) if (len(parts) >= 2 and all(x == ":" for x in parts)) else True
+                        types[en] = (ctype, kind)
             self.tr.signatures[name] = [(n, types.get(n, ("double", False))[0], types.get(n, ("double", False))[1]) for n in argn]
 
     def translate(self):
@@ -798,7 +814,8 @@ class UnitTranslator:
 
     def proto(self, name, nested=False):
         sig = self.tr.signatures[name]
-        ps = ", ".join("%s* %s" % (t, n) for n, t, _ in sig) or "void"
+        ps = ", ".join(("%s* %s, long* %s_n, long* %s_s" % (t, n, n, n)) if isinstance(k, tuple) else ("%s* %s" % (t, n))
+                       for n, t, k in sig) or "void"
         cname = name if (nested or name not in self.tr.toplevel) else self.tr.prefix + name
         return "%svoid %s(%s)" % ("auto " if nested else "", cname, ps)
 
@@ -862,7 +879,11 @@ class UnitTranslator:
                     for en, dspec, init in ents:
                         spec = dspec or (dimattr[dimattr.index("(") + 1:-1] if dimattr else None)
                         if en in argnames:
-                            if spec is not None:
+                            kind = next(k for n_, t_, k in sig if n_ == en)
+                            if isinstance(kind, tuple):  # assumed shape, rank >= 2: lower bound 1, caller's strides
+                                sc.arrays[en] = Array(en, ctype, [("1", "%s_n[%d]" % (en, q_)) for q_ in range(kind[1])],
+                                                      pointer=True, strides=["%s_s[%d]" % (en, q_) for q_ in range(kind[1])])
+                            elif spec is not None:
                                 dims = dims_from_spec(spec, tr, sc)
                                 if len(dims) == 1:
                                     lo = dims[0][0] if dims[0] else "1"
@@ -1093,7 +1114,7 @@ def translate_module(src_path, only, env, rename_modules, patches=(), defined=()
     q = 0
     assert lines[0].startswith("module ")
     q = 1
-    while lines[q] != "contains":
+    while q < len(lines) and lines[q] != "contains" and not lines[q].startswith("end module"):
         l = lines[q]
         q += 1
         if l.startswith("use ") or l.startswith("implicit"):
@@ -1109,7 +1130,14 @@ def translate_module(src_path, only, env, rename_modules, patches=(), defined=()
             if spec is not None:
                 dims = dims_from_spec(spec, tr, msc)
                 if any(x is None for x in dims):
-                    if "allocatable" in attrs:  # allocate()/deallocate() manage it at run time
+                    if "pointer" in attrs and prefix:  # exported pointer array: global run-time descriptor
+                        rank, cn = len(dims), prefix + en
+                        mdecl.append("%s* %s = 0; long %s_lb[%d], %s_n[%d], %s_s[%d];" % (ctype, cn, cn, rank, cn, rank, cn, rank))
+                        tr.all_protos.append("extern %s* %s; extern long %s_lb[%d], %s_n[%d], %s_s[%d];" % (
+                            ctype, cn, cn, rank, cn, rank, cn, rank))
+                        tr.env.arrays[cn] = Array.descriptor(cn, ctype, rank)
+                        msc.arrays[en] = tr.env.arrays[cn]
+                    elif "allocatable" in attrs:  # allocate()/deallocate() manage it at run time
                         rank = len(dims)
                         mdecl.append("static %s* %s = 0; static long %s_lb[%d], %s_n[%d], %s_s[%d];" % (
                             ctype, en, en, rank, en, rank, en, rank))
@@ -1133,9 +1161,12 @@ def translate_module(src_path, only, env, rename_modules, patches=(), defined=()
                         tr.env.ints.add(prefix + en)
                 else:
                     mdecl.append("static %s %s = 0;" % (ctype, en))
-    body = lines[q + 1:]
-    # drop the trailing 'end module'
-    body = [l for l in body if not l.startswith("end module")]
+    body = lines[q + 1:] if (q < len(lines) and lines[q] == "contains") else []
+    # drop the trailing 'end module' (and anything after it: further small modules in the same file)
+    for q2, l in enumerate(body):
+        if l.startswith("end module"):
+            body = body[:q2]
+            break
     ut = UnitTranslator(tr, body, msc, only)
     code = ut.translate()
     return C_PRELUDE % {"src": src_path} + "\n".join(mdecl) + "\n\n" + code + "\n", tr

@@ -45,6 +45,12 @@ PATCHES = [
     (r"^call unsteadyturbterm\(.*$", "continue"),
     # saSolve: wall-function branch (wallFunctions = .false. on the path) uses BCData/viscSubface
     ("block", r"^testwallfunctions: if", r"^end if testwallfunctions"),
+    # ALE (deforming-mesh unsteady) hooks of applyAllBC: steady path, both return at once in the reference
+    (r"^call interplevelalebc_block$", "continue"),
+    (r"^call recoverlevelalebc_block$", "continue"),
+    # BCData(nn)%comp(...) -> accessor functions over the harness' subface table (oracle/ref_env.h)
+    (r"bcdata\((\w+)\)%(\w+)\(", r"bcd_\2(\1, "),
+    (r"bcdata\((\w+)\)%(\w+)", r"bcd_\2(\1)"),
     # module-wide `use X` without only-list inside routines: names resolve through ref_env.h
 ]
 
@@ -56,45 +62,79 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  firstorder secondorder nolimiter vanalbeda minmod noprecond turkel choimerkle roe vanleer ausmdv
  strain vorticity katolaunder kpresent eddymodel rotationalperiodic correctfork righthanded
  usedisscontinuation nbkglobal sectionid ntimeintervalsspectral normalflux boundflux internalflux
- lumpeddiss fullturb cpmodel rkstage resaveraging ndom exchangepressureearly lowspeedpreconditioner
+ lumpeddiss fullturb cpmodel rkstage resaveraging bp_ndom exchangepressureearly lowspeedpreconditioner
  noresaveraging alwaysresaveraging alternateresaveraging turbrelax turbrelaximplicit turbrelaxexplicit
  bp_nx bp_ny bp_nz bp_il bp_jl bp_kl bp_ie bp_je bp_ke bp_ib bp_jb bp_kb bp_addgridvelocities
- bp_righthanded bp_sectionid bp_blockismoving bp_nbkglobal""".split()
+ bp_righthanded bp_sectionid bp_blockismoving bp_nbkglobal bp_nbocos bp_nviscbocos
+ viscwallbctreatment eulerwallbctreatment outflowtreatment
+ symm symmpolar nswalladiabatic nswallisothermal farfield eulerwall extrap supersonicinflow supersonicoutflow
+ subsonicinflow subsonicoutflow massbleedoutflow imin imax jmin jmax kmin kmax
+ constantpressure linextrapolpressure quadextrapolpressure normalmomentum""".split()
 
-BOX3 = [("0", "(bp_ib + 1)"), ("0", "(bp_jb + 1)"), ("0", "(bp_kb + 1)")]
+BOX_STRIDES = ["1", "(bp_ib + 1)", "(bp_ib + 1) * (bp_jb + 1)", "(bp_ib + 1) * (bp_jb + 1) * (bp_kb + 1)"]
 
 
-def box(ncomp=None):
-    return BOX3 + ([("1", str(ncomp))] if ncomp else [])
+def refarr(name, ctype, lo, hi, ncomp=None, comp_lo="1"):
+    """blockPointers array: DECLARED bounds are the reference's (src/modules/block.F90, allocation in
+    src/initFlow/initializeFlow.F90:457-530,686-722 -- they decide what `a(:, j, k)` means), STORAGE is
+    the uniform box (0:ib,0:jb,0:kb[,ncomp]) that ref_env.h exposes, hence explicit strides and origin 0."""
+    bounds = [(l, "(%s) - (%s) + 1" % (h, l)) for l, h in zip(lo, hi)]
+    base = ["0", "0", "0"]
+    strides = BOX_STRIDES[:3]
+    if ncomp is not None:
+        bounds.append((comp_lo, str(ncomp)))
+        base.append(comp_lo)
+        strides = BOX_STRIDES[:4]
+    return f90toc.Array("bp_" + name, ctype, bounds, strides=strides, base=base)
 
 
 def env_arrays():
     A = f90toc.Array
+    c2 = (("0", "0", "0"), ("bp_ib", "bp_jb", "bp_kb"))      # double halo
+    c1 = (("1", "1", "1"), ("bp_ie", "bp_je", "bp_ke"))      # single halo
+    c0 = (("2", "2", "2"), ("bp_il", "bp_jl", "bp_kl"))      # owned cells
+    nd = (("1", "1", "1"), ("bp_il", "bp_jl", "bp_kl"))      # nodes 1:il
     arrs = {}
-    for n in ["p", "gamma", "radi", "radj", "radk", "ux", "uy", "uz", "vx", "vy", "vz", "wx", "wy", "wz", "qx", "qy",
-              "qz", "rlv", "rev", "vol", "volref", "d2wall", "shocksensor", "sfacei", "sfacej", "sfacek", "dtl", "aa"]:
-        arrs["bp_" + n] = A("bp_" + n, "double", box())
-    arrs["bp_w"] = A("bp_w", "double", box("nw"))
-    arrs["bp_dw"] = A("bp_dw", "double", box("nw"))
-    arrs["bp_fw"] = A("bp_fw", "double", box("nwf"))
-    arrs["bp_wn"] = A("bp_wn", "double", box("nwf"))
-    arrs["bp_pn"] = A("bp_pn", "double", box())
+    for n in ["p", "gamma", "rlv", "rev", "vol", "volref", "aa", "shocksensor"]:
+        arrs["bp_" + n] = refarr(n, "double", *c2)
+    for n in ["radi", "radj", "radk", "dtl"]:
+        arrs["bp_" + n] = refarr(n, "double", *c1)
+    for n in ["ux", "uy", "uz", "vx", "vy", "vz", "wx", "wy", "wz", "qx", "qy", "qz"]:
+        arrs["bp_" + n] = refarr(n, "double", *nd)
+    arrs["bp_d2wall"] = refarr("d2wall", "double", *c0)
+    arrs["bp_pn"] = refarr("pn", "double", *c0)
+    arrs["bp_wn"] = refarr("wn", "double", *c0, ncomp="nwf")
+    arrs["bp_w"] = refarr("w", "double", *c2, ncomp="nw")
+    arrs["bp_dw"] = refarr("dw", "double", *c2, ncomp="nw")
+    arrs["bp_fw"] = refarr("fw", "double", *c2, ncomp="nwf")
+    arrs["bp_scratch"] = refarr("scratch", "double", *c2, ncomp=10)
+    arrs["bp_x"] = refarr("x", "double", ("0", "0", "0"), ("bp_ie", "bp_je", "bp_ke"), ncomp=3)
+    arrs["bp_si"] = refarr("si", "double", ("0", "1", "1"), ("bp_ie", "bp_je", "bp_ke"), ncomp=3)
+    arrs["bp_sj"] = refarr("sj", "double", ("1", "0", "1"), ("bp_ie", "bp_je", "bp_ke"), ncomp=3)
+    arrs["bp_sk"] = refarr("sk", "double", ("1", "1", "0"), ("bp_ie", "bp_je", "bp_ke"), ncomp=3)
+    arrs["bp_s"] = refarr("s", "double", *c1, ncomp=3)
+    arrs["bp_sfacei"] = refarr("sfacei", "double", ("0", "1", "1"), ("bp_ie", "bp_je", "bp_ke"))
+    arrs["bp_sfacej"] = refarr("sfacej", "double", ("1", "0", "1"), ("bp_ie", "bp_je", "bp_ke"))
+    arrs["bp_sfacek"] = refarr("sfacek", "double", ("1", "1", "0"), ("bp_ie", "bp_je", "bp_ke"))
+    arrs["bp_iblank"] = refarr("iblank", "int", *c2)
+    arrs["bp_globalcell"] = refarr("globalcell", "int", *c2)
+    arrs["bp_pori"] = refarr("pori", "int", ("1", "2", "2"), ("bp_il", "bp_jl", "bp_kl"))
+    arrs["bp_porj"] = refarr("porj", "int", ("2", "1", "2"), ("bp_il", "bp_jl", "bp_kl"))
+    arrs["bp_pork"] = refarr("pork", "int", ("2", "2", "1"), ("bp_il", "bp_jl", "bp_kl"))
     # turbulence BC matrices of the six block faces (block.F90: bmti1(je,ke,nt1:nt2,nt1:nt2) ...)
     for n, (a, b) in {"bmti1": ("bp_je", "bp_ke"), "bmti2": ("bp_je", "bp_ke"), "bmtj1": ("bp_ie", "bp_ke"),
                       "bmtj2": ("bp_ie", "bp_ke"), "bmtk1": ("bp_ie", "bp_je"), "bmtk2": ("bp_ie", "bp_je")}.items():
         arrs["bp_" + n] = A("bp_" + n, "double", [("1", a), ("1", b), ("nt1", "1"), ("nt1", "1")])
-    arrs["bp_scratch"] = A("bp_scratch", "double", box(10))
+        arrs["bp_" + n.replace("bmt", "bvt")] = A("bp_" + n.replace("bmt", "bvt"), "double", [("1", a), ("1", b), ("nt1", "1")])
+    for n in ["rotmatrixi", "rotmatrixj", "rotmatrixk"]:
+        arrs["bp_" + n] = A("bp_" + n, "double", [("1", "1")])
+    arrs["bp_bctype"] = A("bp_bctype", "int", [("1", "64")])
+    arrs["bp_bcfaceid"] = A("bp_bcfaceid", "int", [("1", "64")])
+    arrs["winf"] = A("winf", "double", [("1", "10")])
+    arrs["turbresscale"] = A("turbresscale", "double", [("1", "4")])
     arrs["etark"] = A("etark", "double", [("1", "6")])
     arrs["cdisrk"] = A("cdisrk", "double", [("1", "6")])
     arrs["coeftime"] = A("coeftime", "double", [("0", "8")])
-    for n in ["x", "si", "sj", "sk"]:
-        arrs["bp_" + n] = A("bp_" + n, "double", box(3))
-    arrs["bp_iblank"] = A("bp_iblank", "int", box())
-    for n in ["pori", "porj", "pork"]:
-        arrs["bp_" + n] = A("bp_" + n, "int", box())
-    for n in ["rotmatrixi", "rotmatrixj", "rotmatrixk"]:
-        arrs["bp_" + n] = A("bp_" + n, "double", [("1", "1")])
-    arrs["turbresscale"] = A("turbresscale", "double", [("1", "4")])
     return arrs
 
 
@@ -106,7 +146,6 @@ ENV_SUBS = {
     "setpointers": [("nn", "int", False), ("level", "int", False), ("sps", "int", False)],
     "whalo1": [(n, "int", False) for n in ("level", "start", "end", "commpressure", "commgamma", "commviscous")],
     "whalo2": [(n, "int", False) for n in ("level", "start", "end", "commpressure", "commgamma", "commviscous")],
-    "applyallbc": [("secondhalo", "int", False)],
 }
 
 
@@ -117,13 +156,19 @@ UNITS = [
     ("utils/flowUtils.F90", "flowutils_", ["computeetotblock", "computelamviscosity", "computepressuresimple",
                                            "etot", "eint"], ("USE_TAPENADE",)),
     ("NKSolver/blockette.F90", "", ROUTINES, ()),
+    ("modules/BCPointers.F90", "bcpointers_", [], ("USE_TAPENADE",)),
+    ("utils/utils.F90", "", ["setbcpointers"], ()),
+    ("solver/BCRoutines.F90", "bcroutines_", ["applyallbc", "applyallbc_block", "bcsymm1sthalo", "bcsymm2ndhalo", "bcnswalladiabatic",
+                                              "bcnswallisothermal", "bcfarfield", "bceulerwall", "bcextrap",
+                                              "computeetot", "extrapolate2ndhalo"], ()),
     ("turbulence/turbUtils.F90", "turbutils_", ["computeeddyviscosity", "saeddyviscosity", "turbadvection"], ()),
     ("turbulence/sa.F90", "sa_", ["sa_block", "sasource", "saviscous", "saresscale", "sasolve"], ()),
     ("solver/residuals.F90", "residuals_", ["residualaveraging", "computedwdadi", "tridiagsolve"], ()),
     ("solver/smoothers.F90", "smoothers_", ["executerkstage", "executedadistep"], ()),
 ]
 RENAME_MODULES = {"blockpointers": "bp_", "flowutils": "flowutils_", "turbutils": "turbutils_",
-                  "residuals": "residuals_", "smoothers": "smoothers_", "sa": "sa_"}
+                  "residuals": "residuals_", "smoothers": "smoothers_", "sa": "sa_",
+                  "bcpointers": "bcpointers_", "bcroutines": "bcroutines_"}
 
 
 def main():
@@ -131,7 +176,8 @@ def main():
     if not os.path.exists(os.path.join(ref, "src", "NKSolver", "blockette.F90")):
         print("make_ref: %s/src not found -- reference not present, nothing generated" % ref)
         return 0
-    env = f90toc.Env(ENV_INTS, env_arrays(), ["getcorrectfork"], dict(ENV_SUBS))
+    env = f90toc.Env(ENV_INTS, env_arrays(), ["getcorrectfork", "bcd_icbeg", "bcd_icend", "bcd_jcbeg", "bcd_jcend",
+                                              "bcd_inbeg", "bcd_inend", "bcd_jnbeg", "bcd_jnend"], dict(ENV_SUBS))
     outdir = os.path.join(HERE, "_ref")
     os.makedirs(outdir, exist_ok=True)
     tr = None

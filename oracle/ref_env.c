@@ -28,7 +28,7 @@ double *bp_ux, *bp_uy, *bp_uz, *bp_vx, *bp_vy, *bp_vz, *bp_wx, *bp_wy, *bp_wz, *
 int *bp_iblank, *bp_pori, *bp_porj, *bp_pork;
 double *bp_rotmatrixi = NULL, *bp_rotmatrixj = NULL, *bp_rotmatrixk = NULL;
 
-int cpmodel = 1 /* cpConstant */, rkstage = 1, resaveraging = 0, ndom = 1, exchangepressureearly = 0;
+int cpmodel = 1 /* cpConstant */, rkstage = 1, resaveraging = 0, bp_ndom = 1, exchangepressureearly = 0;
 int lowspeedpreconditioner = 0;
 double gammaconstant, musuthdim, tsuthdim, ssuthdim, muref = 1.0, pinf;
 double cfl, cflcoarse, cfllimit, smoop, deltat = 1.0;
@@ -38,12 +38,19 @@ double *bp_bmti1, *bp_bmti2, *bp_bmtj1, *bp_bmtj2, *bp_bmtk1, *bp_bmtk2;
 int turbrelax = 2 /* turbRelaxImplicit */;
 double alfaturb;
 
+int bp_nbocos = 0, bp_nviscbocos = 0, bp_bctype[64], bp_bcfaceid[64];
+int viscwallbctreatment = 1, eulerwallbctreatment = 1, outflowtreatment = 1;
+double winf[10];
+double *bp_s;
+int *bp_globalcell;
+double *bp_bvti1, *bp_bvti2, *bp_bvtj1, *bp_bvtj2, *bp_bvtk1, *bp_bvtk2;
+RefSubface bcd[64];
+
 /* Driver-level procedures that are NOT part of the translated set.  One block, pointers bound by
-   the harness, boundary conditions and halo exchange applied by the harness around the call. */
+   the harness; halo exchange (no neighbours) is a no-op. */
 void setpointers(int* nn, int* level, int* sps) { (void)nn; (void)level; (void)sps; }
 void whalo1(int* a, int* b, int* c, int* d, int* e, int* f) { (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; }
 void whalo2(int* a, int* b, int* c, int* d, int* e, int* f) { (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; }
-void applyallbc(int* secondhalo) { (void)secondhalo; }
 
 /* branches of other physical models (cp curve fits, k-omega, SST, k-tau, v2-f): never taken on the
    path (cpConstant, Spalart-Allmaras); reaching one is a harness error */
@@ -53,6 +60,12 @@ UNREACHABLE(turbutils_kweddyviscosity)
 UNREACHABLE(turbutils_ssteddyviscosity)
 UNREACHABLE(turbutils_kteddyviscosity)
 UNREACHABLE(turbutils_vfeddyviscosity)
+/* boundary-condition types outside section 8 (polar symmetry, in/outflow) */
+UNREACHABLE(bcroutines_bcsymmpolar1sthalo)
+UNREACHABLE(bcroutines_bcsymmpolar2ndhalo)
+UNREACHABLE(bcroutines_bcsubsonicoutflow)
+UNREACHABLE(bcroutines_bcsubsonicinflow)
+UNREACHABLE(bcroutines_bcsupersonicinflow)
 
 /* src/utils/utils.F90:486-500 */
 int getcorrectfork(void) { return kpresent && currentlevel <= groundlevel; }

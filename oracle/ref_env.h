@@ -32,7 +32,7 @@ extern double turbresscale[4];
 extern int currentlevel, groundlevel;
 extern double rfil, totalr0, totalr;
 /* more of inputPhysics / inputIteration / inputUnsteady / iteration / block used by the smoothers */
-extern int cpmodel, rkstage, resaveraging, ndom, exchangepressureearly, lowspeedpreconditioner;
+extern int cpmodel, rkstage, resaveraging, bp_ndom, exchangepressureearly, lowspeedpreconditioner;
 extern double gammaconstant, musuthdim, tsuthdim, ssuthdim, muref, pinf;
 extern double cfl, cflcoarse, cfllimit, smoop, deltat;
 extern double etark[6], cdisrk[6], coeftime[8];
@@ -58,10 +58,39 @@ extern double *bp_rotmatrixi, *bp_rotmatrixj, *bp_rotmatrixk;
 int getcorrectfork(void);                           /* src/utils/utils.F90 getCorrectForK */
 void terminate(const char* routine, const char* msg); /* src/utils/utils.F90 terminate */
 
+/* boundary-condition bookkeeping of the current block (blockPointers nBocos, BCType, BCFaceID, BCData) */
+extern int bp_nbocos, bp_nviscbocos, bp_bctype[64], bp_bcfaceid[64];
+extern int viscwallbctreatment, eulerwallbctreatment, outflowtreatment;
+extern double winf[10];
+extern double *bp_s;
+extern int *bp_globalcell;
+extern double *bp_bvti1, *bp_bvti2, *bp_bvtj1, *bp_bvtj2, *bp_bvtk1, *bp_bvtk2;
+/* BCData(nn): cell range of the subface and its per-face data, Fortran order (icBeg:icEnd, jcBeg:jcEnd[, 3]) */
+typedef struct {
+    int icbeg, icend, jcbeg, jcend;
+    double *norm, *rface, *uslip, *tns_wall;
+} RefSubface;
+extern RefSubface bcd[64];
+static inline int bcd_icbeg(int nn) { return bcd[nn - 1].icbeg; }
+static inline int bcd_icend(int nn) { return bcd[nn - 1].icend; }
+static inline int bcd_jcbeg(int nn) { return bcd[nn - 1].jcbeg; }
+static inline int bcd_jcend(int nn) { return bcd[nn - 1].jcend; }
+static inline long bcd_off(int nn, int i, int j) {
+    const RefSubface* s = &bcd[nn - 1];
+    return (i - s->icbeg) + (long)(s->icend - s->icbeg + 1) * (j - s->jcbeg);
+}
+static inline long bcd_size(int nn) {
+    const RefSubface* s = &bcd[nn - 1];
+    return (long)(s->icend - s->icbeg + 1) * (s->jcend - s->jcbeg + 1);
+}
+static inline double bcd_norm(int nn, int i, int j, int l) { return bcd[nn - 1].norm[bcd_off(nn, i, j) + (l - 1) * bcd_size(nn)]; }
+static inline double bcd_uslip(int nn, int i, int j, int l) { return bcd[nn - 1].uslip[bcd_off(nn, i, j) + (l - 1) * bcd_size(nn)]; }
+static inline double bcd_rface(int nn, int i, int j) { return bcd[nn - 1].rface[bcd_off(nn, i, j)]; }
+static inline double bcd_tns_wall(int nn, int i, int j) { return bcd[nn - 1].tns_wall[bcd_off(nn, i, j)]; }
+
 /* driver-level procedures outside the translated set (no-op stubs, see ref_env.c) */
 void setpointers(int* nn, int* level, int* sps);
 void whalo1(int* level, int* start, int* end, int* commpressure, int* commgamma, int* commviscous);
 void whalo2(int* level, int* start, int* end, int* commpressure, int* commgamma, int* commviscous);
-void applyallbc(int* secondhalo);
 
 #endif

@@ -81,7 +81,7 @@ def set_params(prm, nw, rfil=1.0):
     _setd("musuthdim", prm.muSuth); _setd("tsuthdim", prm.TSuth); _setd("ssuthdim", prm.SSuth); _setd("muref", 1.0)
     # smoothers (inputIteration)
     _setd("cfl", prm.cfl); _setd("cflcoarse", prm.cflCoarse); _setd("cfllimit", prm.cflLimit)
-    _setd("smoop", prm.smoop); _seti("resaveraging", _REF_RESAVG[prm.resAveraging]); _seti("ndom", 1)
+    _setd("smoop", prm.smoop); _seti("resaveraging", _REF_RESAVG[prm.resAveraging]); _seti("bp_ndom", 1)
     _seti("exchangepressureearly", 0); _seti("lowspeedpreconditioner", 0)
     eta = (C.c_double * 6).in_dll(lib(), "etark")
     cdis = (C.c_double * 6).in_dll(lib(), "cdisrk")
@@ -94,6 +94,58 @@ def set_params(prm, nw, rfil=1.0):
     _setd("alfaturb", prm.alfaTurb); _seti("turbrelax", 2)  # turbRelaxImplicit
     trs = (C.c_double * 4).in_dll(lib(), "turbresscale")
     trs[0] = prm.turbResScale
+
+
+def ref_constants():
+    """integer `parameter`s of the reference's constants.F90, read from the generated header"""
+    import re
+
+    out = {}
+    with open(os.path.join(_HERE, "_ref", "ref_constants.h")) as f:
+        for line in f:
+            m = re.match(r"enum \{ (\w+) = \(?(-?\d+)\)? \};", line)
+            if m:
+                out[m.group(1)] = int(m.group(2))
+    return out
+
+
+class RefSubface(C.Structure):
+    _fields_ = [("icbeg", C.c_int), ("icend", C.c_int), ("jcbeg", C.c_int), ("jcend", C.c_int),
+                ("norm", C.c_void_p), ("rface", C.c_void_p), ("uslip", C.c_void_p), ("tns_wall", C.c_void_p)]
+
+
+# AdfbSubface.bcType (include/adflow_b200.h) -> name of the reference's BC constant
+_BC_NAME = {1: "symm", 2: "nswalladiabatic", 3: "farfield", 4: "eulerwall", 5: "extrap", 6: "nswallisothermal"}
+
+
+def bind_bcs(hb, prm):
+    """nBocos / nViscBocos / BCType / BCFaceID / BCData of blockPointers from hb.subfaces.  The reference
+    numbers the viscous wall subfaces first (1..nViscBocos); the relative order is otherwise kept."""
+    cst = ref_constants()
+    subs = sorted(hb.subfaces, key=lambda s_: 0 if s_["bcType"] in (2, 6) else 1)
+    nvisc = sum(1 for s_ in subs if s_["bcType"] in (2, 6)) if prm.equations != 1 else 0
+    _seti("bp_nbocos", len(subs)); _seti("bp_nviscbocos", nvisc)
+    bct = (C.c_int * 64).in_dll(lib(), "bp_bctype")
+    bcf = (C.c_int * 64).in_dll(lib(), "bp_bcfaceid")
+    tab = (RefSubface * 64).in_dll(lib(), "bcd")
+    keep = []
+    for q, s_ in enumerate(subs):
+        bct[q] = cst[_BC_NAME[s_["bcType"]]]
+        bcf[q] = s_["faceId"]
+        tab[q].icbeg, tab[q].icend, tab[q].jcbeg, tab[q].jcend = s_["icBeg"], s_["icEnd"], s_["jcBeg"], s_["jcEnd"]
+        na, nb = s_["icEnd"] - s_["icBeg"] + 1, s_["jcEnd"] - s_["jcBeg"] + 1
+        for field, key, ncomp in (("norm", "norm", 3), ("rface", "rface", 1), ("uslip", "uSlip", 3),
+                                  ("tns_wall", "TNSWall", 1)):
+            a = s_.get(key)
+            a = np.zeros((na, nb, ncomp), order="F") if a is None else np.asfortranarray(a, dtype=np.float64)
+            keep.append(a)
+            setattr(tab[q], field, a.ctypes.data)
+    _seti("viscwallbctreatment", cst["constantpressure"] if prm.wallBCConstantPressure else cst["linextrapolpressure"])
+    _seti("eulerwallbctreatment", cst["constantpressure"] if prm.reserved else cst["linextrapolpressure"])
+    w = (C.c_double * 10).in_dll(lib(), "winf")
+    for q in range(6):
+        w[q] = prm.wInf[q]
+    return keep
 
 
 class RefBlock:
@@ -132,6 +184,8 @@ class RefBlock:
               "bmtk1": bmt[1:d.ie + 1, 1:d.je + 1, 1], "bmtk2": bmt[1:d.ie + 1, 1:d.je + 1, d.ke]}
         for n, v in sl.items():
             self.a[n] = f(np.array(v, dtype=np.float64, order="F"))
+        self.a["s"] = np.zeros(box + (3,), order="F")
+        self.a["globalcell"] = np.zeros(box, dtype=np.int32, order="F")
         self.a["iblank"] = f(hb.iblank.astype(np.int32).copy(order="F"))
         for ref, mine in (("pori", "porI"), ("porj", "porJ"), ("pork", "porK")):
             self.a[ref] = f(getattr(hb, mine).astype(np.int32).copy(order="F"))
@@ -172,6 +226,7 @@ def call(hb, prm, routine, *int_args, rkstage=1, rfil=1.0, bmt=None):
     _seti("rkstage", rkstage)
     rb = RefBlock(hb, prm, bmt)
     rb.bind()
+    rb.keep = bind_bcs(hb, prm)
     _BOUND = rb
     getattr(lib(), routine)(*[C.byref(C.c_int(int(v))) for v in int_args])
     return rb

@@ -1,0 +1,61 @@
+"""Pins the oracle's boundary conditions against the reference's own routines (translated Fortran -> C,
+oracle/_ref): applyAllBC_block (src/solver/BCRoutines.F90:57-218) with bcSymm1stHalo/2ndHalo, bcNSWallAdiabatic,
+bcFarfield, bcEulerWall, extrapolate2ndHalo, computeEtot and setBCPointers (src/utils/utils.F90:881-1174).
+Bit-exact on every array the BCs write (w, p, rlv, rev incl. both halo layers)."""
+import numpy as np
+import pytest
+
+from oracle import refblockette as rb
+from util import case
+
+pytestmark = pytest.mark.skipif(not rb.available(), reason="oracle/_ref/libblockette_ref.so not built")
+
+IMIN, IMAX, JMIN, JMAX, KMIN, KMAX = 1, 2, 3, 4, 5, 6
+SYMM, WALL, FAR, EULERWALL = 1, 2, 3, 4
+
+
+def _check(prm, hb, second_halo=True):
+    from oracle.pyoracle import Oracle
+
+    ho = hb.copy()
+    Oracle(ho, prm).apply_flow_bc(second_halo)
+    r = rb.call(hb, prm, "bcroutines_applyallbc_block", int(second_halo))
+    changed = 0
+    for ref, mine in (("w", "w"), ("p", "p"), ("rlv", "rlv"), ("rev", "rev")):
+        a, b = r.a[ref], getattr(ho, mine)
+        assert np.array_equal(a, b), "%s differs: max abs %.3e" % (ref, np.abs(a - b).max())
+        changed += int(not np.array_equal(b, getattr(hb, mine)))
+    assert changed > 0  # the BCs did something
+
+
+@pytest.mark.parametrize("eq", ["Euler", "laminar NS", "RANS"])
+@pytest.mark.parametrize("second", [True, False])
+def test_default_faces(eq, second):
+    """synthetic default: wall kMin (Euler wall for Euler), symmetry jMin, far field elsewhere"""
+    prm, hb = case(9, 8, 7, {"equationType": eq})
+    _check(prm, hb, second)
+
+
+@pytest.mark.parametrize("perm", [
+    {IMIN: WALL, IMAX: FAR, JMIN: FAR, JMAX: SYMM, KMIN: FAR, KMAX: FAR},
+    {IMIN: FAR, IMAX: WALL, JMIN: SYMM, JMAX: FAR, KMIN: FAR, KMAX: SYMM},
+    {IMIN: SYMM, IMAX: SYMM, JMIN: WALL, JMAX: FAR, KMIN: FAR, KMAX: WALL},
+    {IMIN: FAR, IMAX: FAR, JMIN: FAR, JMAX: WALL, KMIN: SYMM, KMAX: FAR},
+])
+def test_every_face_orientation(perm):
+    prm, hb = case(8, 7, 9, {"equationType": "RANS"}, physical_faces=perm)
+    _check(prm, hb, True)
+
+
+@pytest.mark.parametrize("treat", ["constant pressure extrapolation", "linear pressure extrapolation"])
+def test_wall_pressure_treatment(treat):
+    prm, hb = case(8, 7, 9, {"equationType": "RANS", "viscWallTreatment": treat})
+    _check(prm, hb, True)
+
+
+@pytest.mark.parametrize("const_p", [0, 1])
+def test_euler_wall(const_p):
+    perm = {IMIN: FAR, IMAX: FAR, JMIN: SYMM, JMAX: FAR, KMIN: EULERWALL, KMAX: EULERWALL}
+    prm, hb = case(8, 7, 9, {"equationType": "Euler"}, physical_faces=perm)
+    prm.reserved = const_p
+    _check(prm, hb, True)

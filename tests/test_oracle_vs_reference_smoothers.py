@@ -6,9 +6,8 @@
   residuals.F90   residualAveraging :1785-2080, computeDwDADI :1038-1755 (+ tridiagSolve)
   smoothers.F90   executeRkStage :90-382, executeDADIStep :425-693
 
-The driver-level calls inside those routines (setPointers, applyAllBC, whalo1/2) are no-op stubs
-(oracle/ref_env.c): one block, and the oracle side is run with zero BC subfaces, so both sides
-execute exactly the interior update.  Comparison is bit-exact.
+The stages end with the reference's own applyAllBC (BCRoutines.F90, also translated); setPointers and the
+halo exchange whalo1/2 are no-op stubs (one block, no neighbours; oracle/ref_env.c).  Bit-exact.
 """
 import numpy as np
 import pytest
@@ -23,7 +22,6 @@ def _oracle(hb, prm):
     from oracle.pyoracle import Oracle
 
     ho = hb.copy()
-    ho.subfaces = []  # BCs are applied outside the translated routines
     return ho, Oracle(ho, prm)
 
 
@@ -84,12 +82,11 @@ def test_rk_stage(eq, stage, avg):
     ho, o = _oracle(hb, prm)
     o.rk_stage(stage)
     r = rb.call(hb, prm, "smoothers_executerkstage", rkstage=stage)
-    ow = hb.d.owned()
     for l in range(5):
-        _eq(r.a["w"][ow][..., l], ho.w[ow][..., l], "w[%d]" % l)
-    _eq(r.a["p"][ow], ho.p[ow], "p")
-    _eq(r.a["rlv"][ow], ho.rlv[ow], "rlv")
-    _eq(r.a["rev"][ow], ho.rev[ow], "rev")
+        _eq(r.a["w"][..., l], ho.w[..., l], "w[%d]" % l)  # whole box: owned cells and BC halos
+    _eq(r.a["p"], ho.p, "p")
+    _eq(r.a["rlv"], ho.rlv, "rlv")
+    _eq(r.a["rev"], ho.rev, "rev")
 
 
 @pytest.mark.parametrize("eq", ["Euler", "laminar NS", "RANS"])
@@ -112,10 +109,9 @@ def test_dadi_step(eq, avg):
     ho, o = _oracle(hb, prm)
     o.dadi_step()
     r = rb.call(hb, prm, "smoothers_executedadistep", rkstage=0)
-    ow = hb.d.owned()
     for l in range(5):
-        _eq(r.a["w"][ow][..., l], ho.w[ow][..., l], "w[%d]" % l)
-    _eq(r.a["p"][ow], ho.p[ow], "p")
+        _eq(r.a["w"][..., l], ho.w[..., l], "w[%d]" % l)
+    _eq(r.a["p"], ho.p, "p")
 
 
 @pytest.mark.parametrize("shape", [(12, 9, 10), (4, 15, 7)])
