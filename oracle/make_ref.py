@@ -38,10 +38,7 @@ PATCHES = [
     # wall stress tensor storage into viscSubface (storeWallTensor): surface-force path, out of scope
     (r"^viscsubface\(.*$", "continue"),
     (r"visc[ijk]m(in|ax)pointer\([^()]*\)", "0"),
-    # sa_block: the turbulence BC treatment (bmt matrices in, halo values out) is done by the harness;
-    # steady flow, so the unsteady term is identically absent (turbUtils.F90:456-460 returns at once)
-    (r"^call bcturbtreatment$", "continue"),
-    (r"^call applyallturbbcthisblock\(.*$", "continue"),
+    # sa_block: steady flow, so the unsteady term is identically absent (turbUtils.F90:456-460 returns at once)
     (r"^call unsteadyturbterm\(.*$", "continue"),
     # saSolve: wall-function branch (wallFunctions = .false. on the path) uses BCData/viscSubface
     ("block", r"^testwallfunctions: if", r"^end if testwallfunctions"),
@@ -66,7 +63,7 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  noresaveraging alwaysresaveraging alternateresaveraging turbrelax turbrelaximplicit turbrelaxexplicit
  bp_nx bp_ny bp_nz bp_il bp_jl bp_kl bp_ie bp_je bp_ke bp_ib bp_jb bp_kb bp_addgridvelocities
  bp_righthanded bp_sectionid bp_blockismoving bp_nbkglobal bp_nbocos bp_nviscbocos
- viscwallbctreatment eulerwallbctreatment outflowtreatment
+ viscwallbctreatment eulerwallbctreatment outflowtreatment wallfunctions
  symm symmpolar nswalladiabatic nswallisothermal farfield eulerwall extrap supersonicinflow supersonicoutflow
  subsonicinflow subsonicoutflow massbleedoutflow imin imax jmin jmax kmin kmax
  constantpressure linextrapolpressure quadextrapolpressure normalmomentum""".split()
@@ -162,13 +159,17 @@ UNITS = [
                                               "bcnswallisothermal", "bcfarfield", "bceulerwall", "bcextrap",
                                               "computeetot", "extrapolate2ndhalo"], ()),
     ("turbulence/turbUtils.F90", "turbutils_", ["computeeddyviscosity", "saeddyviscosity", "turbadvection"], ()),
+    ("turbulence/turbBCRoutines.F90", "turbbcroutines_",
+     ["applyallturbbcthisblock", "bceddynowall", "bceddywall", "bcturbfarfield", "bcturbinflow", "bcturbinterface",
+      "bcturboutflow", "bcturbsymm", "bcturbtreatment", "bcturbwall", "turb2ndhalo"], ("USE_TAPENADE",)),
     ("turbulence/sa.F90", "sa_", ["sa_block", "sasource", "saviscous", "saresscale", "sasolve"], ()),
     ("solver/residuals.F90", "residuals_", ["residualaveraging", "computedwdadi", "tridiagsolve"], ()),
     ("solver/smoothers.F90", "smoothers_", ["executerkstage", "executedadistep"], ()),
 ]
 RENAME_MODULES = {"blockpointers": "bp_", "flowutils": "flowutils_", "turbutils": "turbutils_",
                   "residuals": "residuals_", "smoothers": "smoothers_", "sa": "sa_",
-                  "bcpointers": "bcpointers_", "bcroutines": "bcroutines_"}
+                  "bcpointers": "bcpointers_", "bcroutines": "bcroutines_",
+                  "turbbcroutines": "turbbcroutines_"}
 
 
 def main():
@@ -193,6 +194,7 @@ def main():
         f.write("/* GENERATED by oracle/make_ref.py -- prototypes of the translated reference procedures */\n")
         f.write("\n".join(tr.all_protos) + "\n")
     consts = f90toc.translate_parameters(os.path.join(ref, "src", "modules", "constants.F90"))
+    consts += f90toc.translate_parameters(os.path.join(ref, "src", "modules", "paramTurb.F90"))
     with open(os.path.join(outdir, "ref_constants.h"), "w") as f:
         f.write(consts)
     return 0

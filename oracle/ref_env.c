@@ -39,7 +39,7 @@ int turbrelax = 2 /* turbRelaxImplicit */;
 double alfaturb;
 
 int bp_nbocos = 0, bp_nviscbocos = 0, bp_bctype[64], bp_bcfaceid[64];
-int viscwallbctreatment = 1, eulerwallbctreatment = 1, outflowtreatment = 1;
+int viscwallbctreatment = 1, eulerwallbctreatment = 1, outflowtreatment = 1, wallfunctions = 0;
 double winf[10];
 double *bp_s;
 int *bp_globalcell;

@@ -60,7 +60,7 @@ void terminate(const char* routine, const char* msg); /* src/utils/utils.F90 ter
 
 /* boundary-condition bookkeeping of the current block (blockPointers nBocos, BCType, BCFaceID, BCData) */
 extern int bp_nbocos, bp_nviscbocos, bp_bctype[64], bp_bcfaceid[64];
-extern int viscwallbctreatment, eulerwallbctreatment, outflowtreatment;
+extern int viscwallbctreatment, eulerwallbctreatment, outflowtreatment, wallfunctions;
 extern double winf[10];
 extern double *bp_s;
 extern int *bp_globalcell;
@@ -86,6 +86,8 @@ static inline long bcd_size(int nn) {
 static inline double bcd_norm(int nn, int i, int j, int l) { return bcd[nn - 1].norm[bcd_off(nn, i, j) + (l - 1) * bcd_size(nn)]; }
 static inline double bcd_uslip(int nn, int i, int j, int l) { return bcd[nn - 1].uslip[bcd_off(nn, i, j) + (l - 1) * bcd_size(nn)]; }
 static inline double bcd_rface(int nn, int i, int j) { return bcd[nn - 1].rface[bcd_off(nn, i, j)]; }
+/* turbulence inflow data: inflow BCs are outside section 8, never reached */
+static inline double bcd_turbinlet(int nn, int i, int j, int l) { (void)nn; (void)i; (void)j; (void)l; return 0.0; }
 static inline double bcd_tns_wall(int nn, int i, int j) { return bcd[nn - 1].tns_wall[bcd_off(nn, i, j)]; }
 
 /* driver-level procedures outside the translated set (no-op stubs, see ref_env.c) */

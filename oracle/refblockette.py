@@ -184,6 +184,7 @@ class RefBlock:
               "bmtk1": bmt[1:d.ie + 1, 1:d.je + 1, 1], "bmtk2": bmt[1:d.ie + 1, 1:d.je + 1, d.ke]}
         for n, v in sl.items():
             self.a[n] = f(np.array(v, dtype=np.float64, order="F"))
+            self.a[n.replace("bmt", "bvt")] = np.zeros(v.shape, order="F")
         self.a["s"] = np.zeros(box + (3,), order="F")
         self.a["globalcell"] = np.zeros(box, dtype=np.int32, order="F")
         self.a["iblank"] = f(hb.iblank.astype(np.int32).copy(order="F"))
@@ -230,6 +231,12 @@ def call(hb, prm, routine, *int_args, rkstage=1, rfil=1.0, bmt=None):
     _BOUND = rb
     getattr(lib(), routine)(*[C.byref(C.c_int(int(v))) for v in int_args])
     return rb
+
+
+def again(routine, *int_args):
+    """call another translated procedure on the block bound by the last call()/residual_core()"""
+    getattr(lib(), routine)(*[C.byref(C.c_int(int(v))) for v in int_args])
+    return _BOUND
 
 
 def call_core(flags=FLAG_FLOW | FLAG_TURB):

@@ -59,3 +59,27 @@ def test_euler_wall(const_p):
     prm, hb = case(8, 7, 9, {"equationType": "Euler"}, physical_faces=perm)
     prm.reserved = const_p
     _check(prm, hb, True)
+
+
+@pytest.mark.parametrize("perm", [
+    None,
+    {IMIN: WALL, IMAX: FAR, JMIN: FAR, JMAX: SYMM, KMIN: FAR, KMAX: FAR},
+    {IMIN: FAR, IMAX: WALL, JMIN: SYMM, JMAX: FAR, KMIN: FAR, KMAX: SYMM},
+    {IMIN: SYMM, IMAX: FAR, JMIN: WALL, JMAX: FAR, KMIN: FAR, KMAX: WALL},
+])
+@pytest.mark.parametrize("second", [True, False])
+def test_turbulence_bcs(perm, second):
+    """bcTurbTreatment + applyAllTurbBCThisBlock (src/turbulence/turbBCRoutines.F90:49-236, 662-797) with
+    bcTurbWall / bcTurbSymm / bcTurbFarfield, bcEddyWall / bcEddyNoWall and turb2ndHalo"""
+    from oracle.pyoracle import Oracle
+
+    kw = {} if perm is None else {"physical_faces": perm}
+    prm, hb = case(8, 7, 9, {"equationType": "RANS"}, **kw)
+    hb.subfaces.sort(key=lambda s_: 0 if s_["bcType"] in (2, 6) else 1)  # reference: viscous subfaces first
+    ho = hb.copy()
+    Oracle(ho, prm).apply_turb_bc(second)
+    rb.call(hb, prm, "turbbcroutines_bcturbtreatment")
+    r = rb.again("turbbcroutines_applyallturbbcthisblock", int(second))
+    assert np.array_equal(r.a["w"][..., 5], ho.w[..., 5]), np.abs(r.a["w"][..., 5] - ho.w[..., 5]).max()
+    assert np.array_equal(r.a["rev"], ho.rev)
+    assert not np.array_equal(ho.w[..., 5], hb.w[..., 5])

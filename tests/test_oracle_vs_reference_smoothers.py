@@ -119,20 +119,21 @@ def test_dadi_step(eq, avg):
                                  {"useApproxSA": True}, {"useRotationSA": True}])
 def test_sa_block_ddadi(shape, opt):
     """sa_block (src/turbulence/sa.F90:16-86): saSource, turbAdvection (turbUtils.F90:828-1553), saViscous,
-    saResScale, saSolve (DD-ADI, :717-1267), saEddyViscosity.  The turbulence BC matrices bmt* are an input
-    (bcTurbTreatment is outside the translated set): taken from the oracle's own treatment."""
+    saResScale, saSolve (DD-ADI, :717-1267), saEddyViscosity, and the turbulence BC treatment around them
+    (bcTurbTreatment / applyAllTurbBCThisBlock, src/turbulence/turbBCRoutines.F90)."""
     o_ = {"equationType": "RANS"}
     o_.update(opt)
     prm, hb = case(*shape, o_)
     from oracle.pyoracle import Oracle
 
+    # the reference numbers the viscous-wall subfaces first (1..nViscBocos) and applies the turbulence BCs in
+    # subface order, which decides the values of halo cells on block edges shared by two subfaces
+    hb.subfaces.sort(key=lambda s_: 0 if s_["bcType"] in (2, 6) else 1)
     ho = hb.copy()
     Oracle(ho, prm).sa_block()
-    bmt = ho.scratch[..., 2].copy(order="F")
-    assert np.abs(bmt).max() == 1.0
-    r = rb.call(hb, prm, "sa_sa_block", 0, bmt=bmt)
+    r = rb.call(hb, prm, "sa_sa_block", 0)
     ow = hb.d.owned()
     _eq(r.a["dw"][ow][..., 5], ho.dw[ow][..., 5], "dw(itu1) after saResScale")
-    _eq(r.a["w"][ow][..., 5], ho.w[ow][..., 5], "nuTilde after the DD-ADI update")
-    _eq(r.a["rev"][ow], ho.rev[ow], "rev")
+    _eq(r.a["w"][..., 5], ho.w[..., 5], "nuTilde after the DD-ADI update and the turbulence BCs (whole box)")
+    _eq(r.a["rev"], ho.rev, "rev")
     assert np.abs(ho.w[ow][..., 5] - hb.w[ow][..., 5]).max() > 0.0
