@@ -1,6 +1,6 @@
 /*
  * adflow_oracle.c -- CPU restatement of the ADflow residual hot path.
- * TEST INFRASTRUCTURE ONLY; see adflow_oracle.h (PARITY UNPINNED notice).
+ * TEST INFRASTRUCTURE ONLY; see adflow_oracle.h (how parity is pinned).
  *
  * Operator order and arithmetic follow src/NKSolver/blockette.F90 (the
  * reference's own self-contained statement of the residual) applied to the

@@ -6,13 +6,22 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load it.
  *
- * PARITY UNPINNED: the reference (Fortran + MPI + PETSc + CGNS) cannot be built
- * or imported in this environment and its regression meshes are not in the
- * tree, so this restatement cannot be checked against reference output or the
- * golden JSONs (tests/reg_tests/refs/, 36 json files).  It is pinned only by the
- * mesh-independent invariants the reference itself relies on (free-stream
- * preservation, discrete conservation, FD consistency, tridiagonal
- * multiply-back) -- see tests/test_oracle_invariants.py.
+ * PARITY PINNED against the reference's own routines, bit for bit.  The reference
+ * as a whole (Fortran + MPI + PETSc + CGNS) cannot be built here (no Fortran
+ * compiler), but its hot-path routines are plain Fortran 90 loops: oracle/f90toc.py
+ * translates them statement by statement to C FROM THE SOURCE WHERE IT LIES
+ * (/root/reference, never copied), oracle/Makefile target `ref` compiles the result
+ * with gcc -O2 -ffp-contract=off into oracle/_ref/libblockette_ref.so, and
+ * tests/test_oracle_vs_reference*.py assert np.array_equal between that library and
+ * this restatement on seeded blocks for: blocketteResCore and all its flux / SA /
+ * time-step routines (exact and approximate variants, scalar/matrix/upwind), state
+ * preparation, metrics and volumes, flow and turbulence BCs, residual averaging,
+ * the RK stage, computeDwDADI + the DADI step, and the SA DD-ADI block solve.
+ * STILL UNPINNED (no reference arithmetic to run): PETSc's matrix-free differencing
+ * parameter h (adfb_mffd_*), and the halo-exchange index lists, which are built by
+ * the reference's preprocessing from CGNS connectivity (checked instead against a
+ * numpy model and by partition independence).  The golden JSONs of the reference
+ * (tests/reg_tests/refs/) need its CGNS meshes, which are not in the tree.
  *
  * Layout: every array lives in one uniform box (0:ib,0:jb,0:kb) (column-major,
  * i fastest) so that the Fortran index (i,j,k) IS the C offset

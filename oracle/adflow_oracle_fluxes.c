@@ -3,7 +3,7 @@
  * matrix dissipation (inviscidDissFluxMatrix, src/NKSolver/blockette.F90:2457-3027; block twin
  * src/solver/fluxes.F90:403-1047) and the upwind/Roe scheme (inviscidUpwindFlux,
  * blockette.F90:3341-4365; src/solver/fluxes.F90:1438-2532).  TEST INFRASTRUCTURE ONLY
- * (PARITY UNPINNED, see adflow_oracle.h).
+ * (pinned bit-exact against oracle/_ref, see adflow_oracle.h).
  */
 #include "orc_internal.h"
 

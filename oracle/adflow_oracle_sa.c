@@ -2,7 +2,7 @@
  * adflow_oracle_sa.c -- CPU restatement of the Spalart-Allmaras DD-ADI solve
  * (sa_block / saSolve, src/turbulence/sa.F90:16-86,717-1267 with the block-path
  * saSource :89-344, turbAdvection src/turbulence/turbUtils.F90:828-1553, saViscous
- * sa.F90:346-676, saResScale :678-714).  TEST INFRASTRUCTURE ONLY (PARITY UNPINNED).
+ * sa.F90:346-676, saResScale :678-714).  TEST INFRASTRUCTURE ONLY (pinned, see adflow_oracle.h).
  *
  * Work arrays: scratch slot 0 = dvt (idvt), slot 1 = qq (central jacobian), slot 2 = bmt
  * (turbulence BC matrix of the face a halo cell belongs to, bcTurbTreatment).

@@ -1,7 +1,7 @@
 /*
  * adflow_oracle_smooth.c -- CPU restatement of the boundary conditions and the
  * Runge-Kutta smoother of the ADflow hot path.  TEST INFRASTRUCTURE ONLY
- * (PARITY UNPINNED, see adflow_oracle.h).
+ * (pinned bit-exact against oracle/_ref, see adflow_oracle.h).
  */
 #include "orc_internal.h"
 

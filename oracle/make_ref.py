@@ -159,6 +159,7 @@ UNITS = [
                                               "bcnswallisothermal", "bcfarfield", "bceulerwall", "bcextrap",
                                               "computeetot", "extrapolate2ndhalo"], ()),
     ("turbulence/turbUtils.F90", "turbutils_", ["computeeddyviscosity", "saeddyviscosity", "turbadvection"], ()),
+    ("adjoint/adjointExtra.F90", "adjointextra_", ["volume_block", "metric_block"], ()),
     ("turbulence/turbBCRoutines.F90", "turbbcroutines_",
      ["applyallturbbcthisblock", "bceddynowall", "bceddywall", "bcturbfarfield", "bcturbinflow", "bcturbinterface",
       "bcturboutflow", "bcturbsymm", "bcturbtreatment", "bcturbwall", "turb2ndhalo"], ("USE_TAPENADE",)),

@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py; never by the product package.
-PARITY UNPINNED (see oracle/adflow_oracle.h).
+Parity: pinned bit-exact against the translated reference routines (oracle/adflow_oracle.h).
 """
 import ctypes as C
 import os

@@ -1,9 +1,10 @@
 """Regenerates tests/golden/oracle_golden.json.
 
 These are ORACLE-generated regression vectors (norms/checksums of the CPU restatement on the
-seeded synthetic blocks), NOT outputs of the reference: the reference (Fortran + MPI + PETSc +
-CGNS) cannot be built or imported here and its regression meshes are absent (DESIGN.md
-section 2, "parity unpinned").  They freeze the oracle so that an accidental change to it, to
+seeded synthetic blocks), NOT outputs of the reference executable: the reference (Fortran + MPI + PETSc + CGNS) cannot be
+built as a whole here and its regression meshes are absent.  The oracle that produces them is
+itself pinned bit-exact against the reference's own routines (translated to C, oracle/_ref;
+tests/test_oracle_vs_reference*.py).  They freeze the oracle so that an accidental change to it, to
 the synthetic generator or to the option handling is caught by `-m "not gpu"`, and they give the
 GPU tests a second, file-based comparison target.
 

@@ -1,7 +1,7 @@
 """Mesh-independent invariants that pin the CPU oracle.
 
-The reference cannot be built or imported here and its regression meshes are not
-in the tree ("parity unpinned"), so the oracle is held to the invariants the
+Independent of (and older than) the bit-exact comparison with the translated reference
+routines in tests/test_oracle_vs_reference*.py, the oracle is held to the invariants the
 reference's own tests rely on: free-stream preservation
 (getFreeStreamResidual, src/NKSolver/NKSolvers.F90:303-320), discrete conservation
 of the telescoping face-flux scatter (src/solver/fluxes.F90:103-104) and agreement

@@ -152,3 +152,11 @@ def test_intermediates_match_reference():
         assert np.array_equal(r.a[ref][c1], getattr(ho, mine)[c1]), ref
     for q, n in enumerate(["ux", "uy", "uz", "vx", "vy", "vz", "wx", "wy", "wz", "qx", "qy", "qz"]):
         assert np.array_equal(r.a[n][nd], ho.grad[nd + (q,)]), n
+
+
+@pytest.mark.parametrize("rfil", [0.56, 0.25])
+@pytest.mark.parametrize("disc", DISCS)
+def test_runge_kutta_dissipation_fraction(rfil, disc):
+    """rFil (iteration module): fraction of new dissipation / viscous flux at intermediate RK stages"""
+    prm, hb = _prepare(10, 9, 11, {"equationType": "RANS", "discretization": disc})
+    _compare_dw(prm, hb, FLOW | TURB, rfil=rfil)

@@ -83,3 +83,32 @@ def test_turbulence_bcs(perm, second):
     assert np.array_equal(r.a["w"][..., 5], ho.w[..., 5]), np.abs(r.a["w"][..., 5] - ho.w[..., 5]).max()
     assert np.array_equal(r.a["rev"], ho.rev)
     assert not np.array_equal(ho.w[..., 5], hb.w[..., 5])
+
+
+@pytest.mark.parametrize("right_handed", [True, False])
+def test_metrics_and_volumes(right_handed):
+    """volume_block / metric_block (src/adjoint/adjointExtra.F90:5-298): cell volumes incl. halo cells and
+    the face-normal arrays si/sj/sk from the node coordinates"""
+    from oracle.pyoracle import Oracle
+
+    prm, hb = case(9, 7, 8, {"equationType": "RANS"})
+    if not right_handed:
+        hb.x[..., 0] *= -1.0
+        hb.right_handed = False
+    ho = hb.copy()
+    for n in ("vol", "si", "sj", "sk"):
+        getattr(ho, n)[...] = 0.0
+    o = Oracle(ho, prm)
+    o.volume(); o.metrics()
+    h2 = hb.copy()
+    for n in ("vol", "si", "sj", "sk"):
+        getattr(h2, n)[...] = 0.0
+    rb.call(h2, prm, "adjointextra_volume_block")
+    r = rb.again("adjointextra_metric_block")
+    d = hb.d
+    c1 = (slice(1, d.ie + 1), slice(1, d.je + 1), slice(1, d.ke + 1))
+    assert np.array_equal(r.a["vol"][c1], ho.vol[c1]), np.abs(r.a["vol"][c1] - ho.vol[c1]).max()
+    for n in ("si", "sj", "sk"):
+        sl = d.ref_slices(n) + (slice(None),)
+        assert np.array_equal(r.a[n][sl], getattr(ho, n)[sl]), n
+        assert np.abs(getattr(ho, n)[sl]).max() > 0
