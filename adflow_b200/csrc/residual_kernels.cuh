@@ -168,10 +168,11 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
     ri = dmax_(ri, 1.e-25); rj = dmax_(rj, 1.e-25); rk = dmax_(rk, 1.e-25);
     // (ri/rj)**adis etc. via three logs and three exps (|adis*log(ratio)| < 10: error < 1e-15)
     const double li = log(ri), lj = log(rj), lk = log(rk);
-    const double rij = exp(adis * (li - lj)), rjk = exp(adis * (lj - lk)), rki = exp(adis * (lk - li));
-    b.radI[c] = ri * (1.0 + 1.0 / rij + rki);
+    // (ri/rk)**adis = (ri/rj)**adis * (rj/rk)**adis: two exps instead of three (one more rounding, 1e-16)
+    const double rij = exp(adis * (li - lj)), rjk = exp(adis * (lj - lk)), rik = rij * rjk;
+    b.radI[c] = ri * (1.0 + 1.0 / rij + 1.0 / rik);
     b.radJ[c] = rj * (1.0 + 1.0 / rjk + rij);
-    b.radK[c] = rk * (1.0 + 1.0 / rki + rjk);
+    b.radK[c] = rk * (1.0 + rik + rjk);
 
     if (!updateDt) return;
     if (i < 2 || i > d.il || j < 2 || j > d.jl || k < 2 || k > d.kl) return;
@@ -812,6 +813,37 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
     const int dissApprox = (flags & ADFB_RES_DISS_APPROX) ? 1 : 0, viscApprox = (flags & ADFB_RES_VISC_APPROX) ? 1 : 0;
     if ((dissApprox || viscApprox) && persistFw) return 1;  // approximate variants exist on the blockette path only
     dim3 tb(32, 4, 2);
+    // The SA row reads only the state and static geometry and writes dw(itu1); the flow rows write dw(1:5).
+    // The two chains are independent, so k_sa is forked onto a side stream (also inside graph capture) and
+    // joined at the end: both chains are latency bound, their warps interleave on the SMs.
+    static cudaStream_t s_side = nullptr;
+    static cudaEvent_t s_fork = nullptr, s_join = nullptr;
+    static int s_conc = -1;
+    if (s_conc < 0) {
+        const char* e = getenv("ADFB_SA_CONCURRENT");
+        s_conc = e ? atoi(e) : 1;
+    }
+    const bool fork = turbRes && flowRes && s_conc && !g_kt.on;
+    if (turbRes) {
+        dim3 tr = tune_block("ADFB_SA_BLOCK", dim3(32, 4, 1));
+        dim3 g((d.nx + tr.x - 1) / tr.x, (d.ny + tr.y - 1) / tr.y, (d.nz + tr.z - 1) / tr.z);
+        if (fork) {
+            if (!s_side) {
+                if (cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking) != cudaSuccess) return 1;
+                if (cudaEventCreateWithFlags(&s_fork, cudaEventDisableTiming) != cudaSuccess) return 1;
+                if (cudaEventCreateWithFlags(&s_join, cudaEventDisableTiming) != cudaSuccess) return 1;
+            }
+            cudaEventRecord(s_fork, stream);
+            cudaStreamWaitEvent(s_side, s_fork, 0);
+            k_sa<<<g, tr, 0, s_side>>>(d, b);
+            g_kt.launches++; g_kt.count[K_SA]++;
+            cudaEventRecord(s_join, s_side);
+        } else {
+            KT_BEGIN(K_SA, stream);
+            k_sa<<<g, tr, 0, stream>>>(d, b);
+            KT_END(K_SA, stream);
+        }
+    }
     if (doRad || (flowRes && doDiss)) {
         dim3 g((d.NI + tb.x - 1) / tb.x, (d.NJ + tb.y - 1) / tb.y, (d.NK + tb.z - 1) / tb.z);
         KT_BEGIN(K_PREP, stream);
@@ -824,13 +856,6 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         KT_BEGIN(K_NODAL, stream);
         k_nodal<<<g, tn, 0, stream>>>(d, b, doVisc && !viscApprox, dissApprox);
         KT_END(K_NODAL, stream);
-    }
-    if (turbRes) {
-        dim3 tr = tune_block("ADFB_SA_BLOCK", dim3(32, 4, 1));
-        dim3 g((d.nx + tr.x - 1) / tr.x, (d.ny + tr.y - 1) / tr.y, (d.nz + tr.z - 1) / tr.z);
-        KT_BEGIN(K_SA, stream);
-        k_sa<<<g, tr, 0, stream>>>(d, b);
-        KT_END(K_SA, stream);
     }
     if (flowRes) {
         dim3 tr = tune_block("ADFB_FACES_BLOCK", dim3(32, 4, 1));
@@ -864,5 +889,6 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         else k_div<false><<<g2, tb, 0, stream>>>(d, b, rFil, persistFw);
         KT_END(K_DIV, stream);
     }
+    if (fork) cudaStreamWaitEvent(stream, s_join, 0);
     return (int)cudaGetLastError();
 }

@@ -2,8 +2,8 @@
 //
 //   k_bc_turb / k_bc_flow : applyAllTurbBCThisBlock (src/turbulence/turbBCRoutines.F90:49-236)
 //                           and applyAllBC_block (src/solver/BCRoutines.F90:57-222) for the BC
-//                           classes of the BASELINE configs: symmetry, adiabatic NS wall,
-//                           far field, Euler wall.  One launch per subface and phase, issued
+//                           classes: symmetry, adiabatic / isothermal NS wall,
+//                           far field, extrapolation, Euler wall.  One launch per subface and phase, issued
 //                           in the reference's order (edge/corner halos depend on it).
 //   k_rk_scale / k_rk_update : executeRkStage (src/solver/smoothers.F90:90-382)
 //   k_resavg_line            : residualAveraging (src/solver/residuals.F90:1785-2080)
@@ -16,7 +16,7 @@ struct FaceDev {
     long long sa, sb;  // in-plane strides
     int icBeg, icEnd, jcBeg, jcEnd;
     int bcType;
-    const double *norm, *rface, *uSlip;
+    const double *norm, *rface, *uSlip, *TNSWall;
 };
 
 static FaceDev make_face(const Dims& d, const AdfbSubface& sf) {
@@ -31,7 +31,7 @@ static FaceDev make_face(const Dims& d, const AdfbSubface& sf) {
     }
     f.icBeg = sf.icBeg; f.icEnd = sf.icEnd; f.jcBeg = sf.jcBeg; f.jcEnd = sf.jcEnd;
     f.bcType = sf.bcType;
-    f.norm = sf.norm; f.rface = sf.rface; f.uSlip = sf.uSlip;
+    f.norm = sf.norm; f.rface = sf.rface; f.uSlip = sf.uSlip; f.TNSWall = sf.TNSWall;
     return f;
 }
 
@@ -128,6 +128,48 @@ __global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, 
                 if (p1 <= 0.0) p1 = b.p[c2];
                 b.p[c1] = p1;
             }
+            bc_etot(b, N, c1);
+            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            break;
+        }
+        case ADFB_BC_NSWALL_ISOTHERMAL: {  // bcNSWallIsoThermal, BCRoutines.F90:579-691
+            double us1 = 0.0, us2 = 0.0, us3 = 0.0;
+            if (f.uSlip) { us1 = f.uSlip[o]; us2 = f.uSlip[o + na * nb]; us3 = f.uSlip[o + 2 * na * nb]; }
+            const double tw = f.TNSWall[o];
+            const double t2 = b.p[c2] / (c_prm.RGas * w[c2]);
+            double t1 = 2.0 * tw - t2;
+            t1 = dmax_(0.5 * tw, t1);
+            t1 = dmin_(2.0 * tw, t1);
+            double p1;
+            if (c_prm.wallBCConstantPressure) {
+                p1 = b.p[c2];
+            } else {
+                p1 = 2.0 * b.p[c2] - b.p[c3];
+                if (p1 <= 0.0) p1 = b.p[c2];
+            }
+            b.p[c1] = p1;
+            w[c1] = p1 / (c_prm.RGas * t1);
+            w[N + c1] = -w[N + c2] + 2.0 * us1;
+            w[2 * N + c1] = -w[2 * N + c2] + 2.0 * us2;
+            w[3 * N + c1] = -w[3 * N + c2] + 2.0 * us3;
+            b.rlv[c1] = b.rlv[c2];
+            if (eddy) b.rev[c1] = -b.rev[c2];
+            bc_etot(b, N, c1);
+            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            break;
+        }
+        case ADFB_BC_EXTRAP: {  // bcExtrap, BCRoutines.F90:1479-1570 (linear extrapolation, fw2 = 2, fw3 = -1)
+            double r1 = 2.0 * w[c2] + -1.0 * w[c3];
+            r1 = dmax_(0.5 * w[c2], r1);
+            w[c1] = r1;
+            w[N + c1] = 2.0 * w[N + c2] + -1.0 * w[N + c3];
+            w[2 * N + c1] = 2.0 * w[2 * N + c2] + -1.0 * w[2 * N + c3];
+            w[3 * N + c1] = 2.0 * w[3 * N + c2] + -1.0 * w[3 * N + c3];
+            double p1 = 2.0 * b.p[c2] + -1.0 * b.p[c3];
+            p1 = dmax_(0.5 * b.p[c2], p1);
+            b.p[c1] = p1;
+            if (viscous) b.rlv[c1] = b.rlv[c2];
+            if (eddy) b.rev[c1] = b.rev[c2];
             bc_etot(b, N, c1);
             if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
             break;
@@ -338,7 +380,9 @@ static int launch_bc_flow(const Dims& d, const BlockDev& b, const std::vector<Ad
     if (secondHalo)
         for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SYMM) launch_bc_one(d, b, sf, secondHalo, 2, s);
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_NSWALL_ADIABATIC) launch_bc_one(d, b, sf, secondHalo, 0, s);
+    for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_NSWALL_ISOTHERMAL) launch_bc_one(d, b, sf, secondHalo, 0, s);
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_FARFIELD) launch_bc_one(d, b, sf, secondHalo, 0, s);
+    for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_EXTRAP) launch_bc_one(d, b, sf, secondHalo, 0, s);
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_EULERWALL) launch_bc_one(d, b, sf, secondHalo, 0, s);
     return (int)cudaGetLastError();
 }

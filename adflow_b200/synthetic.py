@@ -240,4 +240,8 @@ def make_subface(blk, face, bc):
     mag = np.sqrt((s * s).sum(axis=-1))
     mag = np.where(mag > 0, mag, 1.0)
     norm = np.asfortranarray(mult * s / mag[..., None])
-    return {"bcType": bc, "faceId": face, "icBeg": 1, "icEnd": n1, "jcBeg": 1, "jcEnd": n2, "norm": norm}
+    sub = {"bcType": bc, "faceId": face, "icBeg": 1, "icEnd": n1, "jcBeg": 1, "jcEnd": n2, "norm": norm}
+    if bc == 6:  # isothermal wall: BCData%TNS_Wall, non-dimensional (T_inf = 1), smooth 5 % variation
+        a, c = np.meshgrid(np.arange(n1), np.arange(n2), indexing="ij")
+        sub["TNSWall"] = np.asfortranarray(1.08 + 0.05 * np.sin(0.37 * a) * np.cos(0.23 * c))
+    return sub

@@ -127,6 +127,46 @@ static void bc_flow_subface(const OrcBlock* b, const AdfbParams* prm, const Adfb
                 if (secondHalo) bc_extrap2(b, d, prm, c0, c1, c2);
                 break;
             }
+            case ADFB_BC_NSWALL_ISOTHERMAL: { /* bcNSWallIsoThermal, BCRoutines.F90:579-691 */
+                double us1 = zero, us2 = zero, us3 = zero;
+                long o = (ia - sf->icBeg) + na * (jb_ - sf->jcBeg);
+                if (sf->uSlip) { us1 = sf->uSlip[o]; us2 = sf->uSlip[o + na * nb]; us3 = sf->uSlip[o + 2 * na * nb]; }
+                double tw = sf->TNSWall[o];
+                double t2 = b->p[c2] / (prm->RGas * W(c2, IRHO));
+                double t1 = two * tw - t2;
+                t1 = dmax(half * tw, t1);
+                t1 = dmin(two * tw, t1);
+                if (prm->wallBCConstantPressure) {
+                    b->p[c1] = b->p[c2] - four * third * zero;
+                } else {
+                    b->p[c1] = 2 * b->p[c2] - b->p[c3];
+                    if (b->p[c1] <= zero) b->p[c1] = b->p[c2];
+                }
+                W(c1, IRHO) = b->p[c1] / (prm->RGas * t1);
+                W(c1, IVX) = -W(c2, IVX) + two * us1;
+                W(c1, IVY) = -W(c2, IVY) + two * us2;
+                W(c1, IVZ) = -W(c2, IVZ) + two * us3;
+                b->rlv[c1] = b->rlv[c2];
+                if (eddy) b->rev[c1] = -b->rev[c2];
+                bc_etot(b, d, gam, c1);
+                if (secondHalo) bc_extrap2(b, d, prm, c0, c1, c2);
+                break;
+            }
+            case ADFB_BC_EXTRAP: { /* bcExtrap, BCRoutines.F90:1479-1570: extrap => fw2 = 2, fw3 = -1 */
+                double fw2 = two, fw3 = -one, factor = half;
+                W(c1, IRHO) = fw2 * W(c2, IRHO) + fw3 * W(c3, IRHO);
+                W(c1, IRHO) = dmax(factor * W(c2, IRHO), W(c1, IRHO));
+                W(c1, IVX) = fw2 * W(c2, IVX) + fw3 * W(c3, IVX);
+                W(c1, IVY) = fw2 * W(c2, IVY) + fw3 * W(c3, IVY);
+                W(c1, IVZ) = fw2 * W(c2, IVZ) + fw3 * W(c3, IVZ);
+                b->p[c1] = fw2 * b->p[c2] + fw3 * b->p[c3];
+                b->p[c1] = dmax(factor * b->p[c2], b->p[c1]);
+                if (viscous) b->rlv[c1] = b->rlv[c2];
+                if (eddy) b->rev[c1] = b->rev[c2];
+                bc_etot(b, d, gam, c1);
+                if (secondHalo) bc_extrap2(b, d, prm, c0, c1, c2);
+                break;
+            }
             case ADFB_BC_FARFIELD: {
                 double gm1 = gam - one, ovgm1 = one / gm1;
                 double r0 = one / prm->wInf[IRHO], u0 = prm->wInf[IVX], v0 = prm->wInf[IVY], w0 = prm->wInf[IVZ];
@@ -194,7 +234,9 @@ void orc_apply_flow_bc(const OrcBlock* b, const AdfbParams* prm, int nSub, const
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SYMM) bc_flow_subface(b, prm, &sf[n], secondHalo, 1);
     if (secondHalo) for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SYMM) bc_flow_subface(b, prm, &sf[n], secondHalo, 2);
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_NSWALL_ADIABATIC) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
+    for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_NSWALL_ISOTHERMAL) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_FARFIELD) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
+    for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_EXTRAP) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_EULERWALL) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
 }
 

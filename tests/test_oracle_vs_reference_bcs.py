@@ -11,7 +11,7 @@ from util import case
 pytestmark = pytest.mark.skipif(not rb.available(), reason="oracle/_ref/libblockette_ref.so not built")
 
 IMIN, IMAX, JMIN, JMAX, KMIN, KMAX = 1, 2, 3, 4, 5, 6
-SYMM, WALL, FAR, EULERWALL = 1, 2, 3, 4
+SYMM, WALL, FAR, EULERWALL, EXTRAP, ISOWALL = 1, 2, 3, 4, 5, 6
 
 
 def _check(prm, hb, second_halo=True):
@@ -47,6 +47,18 @@ def test_every_face_orientation(perm):
     _check(prm, hb, True)
 
 
+@pytest.mark.parametrize("perm", [
+    {IMIN: EXTRAP, IMAX: FAR, JMIN: SYMM, JMAX: FAR, KMIN: ISOWALL, KMAX: EXTRAP},
+    {IMIN: ISOWALL, IMAX: EXTRAP, JMIN: EXTRAP, JMAX: ISOWALL, KMIN: FAR, KMAX: SYMM},
+])
+@pytest.mark.parametrize("treat", ["constant pressure extrapolation", "linear pressure extrapolation"])
+def test_isothermal_wall_and_extrapolation(perm, treat):
+    """bcNSWallIsoThermal :579-691 (BCData%TNS_Wall) and bcExtrap :1479-1570"""
+    prm, hb = case(8, 7, 9, {"equationType": "RANS", "viscWallTreatment": treat}, physical_faces=perm)
+    _check(prm, hb, True)
+    _check(prm, hb, False)
+
+
 @pytest.mark.parametrize("treat", ["constant pressure extrapolation", "linear pressure extrapolation"])
 def test_wall_pressure_treatment(treat):
     prm, hb = case(8, 7, 9, {"equationType": "RANS", "viscWallTreatment": treat})
@@ -66,6 +78,7 @@ def test_euler_wall(const_p):
     {IMIN: WALL, IMAX: FAR, JMIN: FAR, JMAX: SYMM, KMIN: FAR, KMAX: FAR},
     {IMIN: FAR, IMAX: WALL, JMIN: SYMM, JMAX: FAR, KMIN: FAR, KMAX: SYMM},
     {IMIN: SYMM, IMAX: FAR, JMIN: WALL, JMAX: FAR, KMIN: FAR, KMAX: WALL},
+    {IMIN: EXTRAP, IMAX: FAR, JMIN: SYMM, JMAX: ISOWALL, KMIN: ISOWALL, KMAX: EXTRAP},
 ])
 @pytest.mark.parametrize("second", [True, False])
 def test_turbulence_bcs(perm, second):

@@ -16,10 +16,16 @@ def box_close(a, b, tol, name):
     assert err < tol, "%s: rel max %.3e" % (name, err)
 
 
-@pytest.mark.parametrize("options", [None, {"equationType": "Euler"}, {"equationType": "laminar NS"},
-                                     {"viscWallTreatment": "linear pressure extrapolation"}])
-def test_bcs_match_oracle(cuda_lib, options):
-    prm, hb = case(13, 11, 9, options)
+ISO_EXTRAP_FACES = {1: 5, 2: 3, 3: 1, 4: 3, 5: 6, 6: 5}  # iMin extrap, jMin symm, kMin isothermal wall, kMax extrap
+
+
+@pytest.mark.parametrize("options,faces", [(None, None), ({"equationType": "Euler"}, None),
+                                           ({"equationType": "laminar NS"}, None),
+                                           ({"viscWallTreatment": "linear pressure extrapolation"}, None),
+                                           (None, ISO_EXTRAP_FACES),
+                                           ({"viscWallTreatment": "linear pressure extrapolation"}, ISO_EXTRAP_FACES)])
+def test_bcs_match_oracle(cuda_lib, options, faces):
+    prm, hb = case(13, 11, 9, options, **({} if faces is None else {"physical_faces": faces}))
     ho = hb.copy()
     o = Oracle(ho, prm)
     o.apply_turb_bc(True)
