@@ -159,84 +159,99 @@ __device__ __forceinline__ void dadi_post(const BlockDev& b, int N, int c, doubl
             (ge + 0.5 * xfact * uu / len) * dw4 + (ge - 0.5 * xfact * uu / len) * dw5) * volfact;
 }
 
-// one thread = one grid line of nl owned cells along sd.  dd (3 coefficient sets) is kept in
-// scratch slots 0..2; ff lives in dw.
+// The sweep is split so that only the recurrence itself is serial:
+//   k_dadi_coef   (one thread per cell)      : cell coefficients of the sweep direction -> work[0..8],
+//                                              incoming change of basis applied to dw in place
+//   k_dadi_thomas (one thread per line and variable): Thomas elimination / back substitution
+//                                              (tridiagsolve, residuals.F90:1750-1783) reading only
+//                                              the precomputed arrays
+//   k_dadi_post   (one thread per cell, k sweep only): T_zeta and the -1/vol scaling
+// `work` is the face-flux workspace b.flux (free while the smoother update runs): slots 0..8 cell
+// coefficients, 9..13 the eliminated super-diagonal per variable, 14..18 the forward-swept rhs.
 template <int DIR>
-__global__ void __launch_bounds__(64) k_dadi_line(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2, double cfl) {
-    const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
-    const int q2 = blockIdx.y * blockDim.y + threadIdx.y + 2;
-    if (q1 > n1 + 1 || q2 > n2 + 1) return;
+__global__ void __launch_bounds__(128) k_dadi_coef(Dims d, BlockDev b, int sd, double cfl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
+    if (i > d.il || j > d.jl || k > d.kl) return;
     const int N = (int)d.N;
-    const int base = q1 * s1 + q2 * s2;
+    const int c = i + (int)d.sJ * j + (int)d.sK * k;
     const bool viscous = c_prm.equations != ADFB_EULER, eddy = c_prm.equations == ADFB_RANS;
     const double* s = DIR == 0 ? b.sj : (DIR == 1 ? b.si : b.sk);
     const double* slow = DIR == 2 ? b.sj : s;  // reference quirk, residuals.F90:1625-1627
-    double* ddA = b.scratch;
+    DadiCoef A;
+    dadi_cell(b, N, c, sd, s, slow, cfl, viscous, eddy, A);
+    double* w = b.flux;
+#pragma unroll
+    for (int t = 0; t < 3; t++) { w[t * N + c] = A.dP[t]; w[(3 + t) * N + c] = A.dM[t]; }
+    w[6 * N + c] = A.vt1; w[7 * N + c] = A.vt3; w[8 * N + c] = A.dtrb;
+    double f[5];
+#pragma unroll
+    for (int n = 0; n < 5; n++) f[n] = b.dw[n * N + c];
+    dadi_pre<DIR>(b, N, c, cfl, f);
+#pragma unroll
+    for (int n = 0; n < 5; n++) b.dw[n * N + c] = f[n];
+}
+
+__global__ void __launch_bounds__(128) k_dadi_post(Dims d, BlockDev b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
+    if (i > d.il || j > d.jl || k > d.kl) return;
+    const int N = (int)d.N;
+    const int c = i + (int)d.sJ * j + (int)d.sK * k;
+    double f[5];
+#pragma unroll
+    for (int n = 0; n < 5; n++) f[n] = b.dw[n * N + c];
+    dadi_post(b, N, c, f);
+#pragma unroll
+    for (int n = 0; n < 5; n++) b.dw[n * N + c] = f[n];
+}
+
+// one thread = one grid line (nl owned cells along sd) of one variable n = blockIdx.z
+__global__ void __launch_bounds__(64) k_dadi_thomas(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2) {
+    const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int q2 = blockIdx.y + 2;
+    if (q1 > n1 + 1 || q2 > n2 + 1) return;
+    const int n = blockIdx.z;
+    const int t = n < 3 ? 0 : n - 2;   // coefficient set: (u), (u+c), (u-c)
+    const int N = (int)d.N;
+    const int base = q1 * s1 + q2 * s2;
     const int l = nl + 1;
-    const int typ[5] = {0, 0, 0, 1, 2};
-    if (nl <= 1) {  // `if (jl > 2)` guards: no implicit solve, but the changes of basis still apply
-        const int c = base + 2 * sd;
-        double f[5];
-#pragma unroll
-        for (int n = 0; n < 5; n++) f[n] = b.dw[n * N + c];
-        dadi_pre<DIR>(b, N, c, cfl, f);
-        if (DIR == 2) dadi_post(b, N, c, f);
-#pragma unroll
-        for (int n = 0; n < 5; n++) b.dw[n * N + c] = f[n];
-        return;
-    }
-    DadiCoef Am, A0, Ap;   // cells m-1, m, m+1
-    dadi_cell(b, N, base + 2 * sd, sd, s, slow, cfl, viscous, eddy, A0);
-    Am = A0;
-    double ddp[3] = {0.0, 0.0, 0.0}, ffp[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (nl <= 1) return;  // `if (jl > 2)` guards: no implicit solve (changes of basis done by k_dadi_coef / k_dadi_post)
+    const double* __restrict__ dP = b.flux + t * N;
+    const double* __restrict__ dM = b.flux + (3 + t) * N;
+    const double* __restrict__ vt1 = b.flux + 6 * N;
+    const double* __restrict__ vt3 = b.flux + 7 * N;
+    const double* __restrict__ dtrb = b.flux + 8 * N;
+    double* __restrict__ dd = b.flux + (9 + n) * N;
+    double* __restrict__ fo = b.flux + (14 + n) * N;
+    double* __restrict__ f = b.dw + n * N;
+    double ddp = 0.0, ffp = 0.0;
+#pragma unroll 4
     for (int m = 2; m <= l; m++) {
         const int c = base + m * sd;
-        if (m < l) dadi_cell(b, N, c + sd, sd, s, slow, cfl, viscous, eddy, Ap);
-        double f[5];
-#pragma unroll
-        for (int n = 0; n < 5; n++) f[n] = b.dw[n * N + c];
-        dadi_pre<DIR>(b, N, c, cfl, f);
-        const double vt2 = A0.vt1 + A0.vt3;
-        double d0[3], bbm[3], ddm[3];
-#pragma unroll
-        for (int t = 0; t < 3; t++) {
-            const double cc = 1.0 + (vt2 + A0.dP[t] - A0.dM[t]) * A0.dtrb;
-            bbm[t] = (m > 2) ? (-Am.vt1 - Am.dP[t]) * A0.dtrb : 0.0;
-            const double dsup = (m < l) ? (-Ap.vt3 + Ap.dM[t]) * A0.dtrb : 0.0;
-            d0[t] = (m == 2) ? 1.0 / cc : 1.0 / (cc - bbm[t] * ddp[t]);
-            ddm[t] = dsup * d0[t];
-            ddA[t * N + c] = ddm[t];
-        }
-#pragma unroll
-        for (int n = 0; n < 5; n++) {
-            const int t = typ[n];
-            f[n] = (m == 2) ? f[n] * d0[t] : (f[n] - bbm[t] * ffp[n]) * d0[t];
-            ffp[n] = f[n];
-        }
-#pragma unroll
-        for (int t = 0; t < 3; t++) ddp[t] = ddm[t];
-        if (m < l) {
-#pragma unroll
-            for (int n = 0; n < 5; n++) b.dw[n * N + c] = f[n];
-        } else {  // last cell is final after the forward sweep
-            if (DIR == 2) dadi_post(b, N, c, f);
-#pragma unroll
-            for (int n = 0; n < 5; n++) b.dw[n * N + c] = f[n];
-        }
-        Am = A0; A0 = Ap;
+        const double dt = dtrb[c];
+        const double vt2 = vt1[c] + vt3[c];
+        const double cc = 1.0 + (vt2 + dP[c] - dM[c]) * dt;
+        const double bbm = (m > 2) ? (-vt1[c - sd] - dP[c - sd]) * dt : 0.0;
+        const double dsup = (m < l) ? (-vt3[c + sd] + dM[c + sd]) * dt : 0.0;
+        const double d0 = (m == 2) ? 1.0 / cc : 1.0 / (cc - bbm * ddp);
+        const double ddm = dsup * d0;
+        dd[c] = ddm;
+        double fv = f[c];
+        fv = (m == 2) ? fv * d0 : (fv - bbm * ffp) * d0;
+        fo[c] = fv;
+        ffp = fv; ddp = ddm;
     }
-    // back substitution; ffp holds ff(l) in the sweep basis
+    // back substitution; ffp holds ff(l)
+    f[base + l * sd] = ffp;
+#pragma unroll 4
     for (int m = l - 1; m >= 2; m--) {
         const int c = base + m * sd;
-        double f[5];
-#pragma unroll
-        for (int n = 0; n < 5; n++) {
-            f[n] = b.dw[n * N + c] - ddA[typ[n] * N + c] * ffp[n];
-            ffp[n] = f[n];
-        }
-        if (DIR == 2) dadi_post(b, N, c, f);
-#pragma unroll
-        for (int n = 0; n < 5; n++) b.dw[n * N + c] = f[n];
+        const double fv = fo[c] - dd[c] * ffp;
+        f[c] = fv;
+        ffp = fv;
     }
 }
 
@@ -245,24 +260,32 @@ __global__ void __launch_bounds__(64) k_dadi_line(Dims d, BlockDev b, int sd, in
 // computedwDADI including the -cfl*dtl*vol scaling of executeDADIStep (smoothers.F90:515-528)
 static int launch_dadi(const Dims& d, const BlockDev& b, const AdfbParams& prm, cudaStream_t s) {
     const int sJ = (int)d.sJ, sK = (int)d.sK;
-    dim3 tb(32, 1);
-    {
-        dim3 g((d.nx + 31) / 32, d.nz);
-        KT_BEGIN(K_DADI, s);
-        k_dadi_line<0><<<g, tb, 0, s>>>(d, b, sJ, d.ny, 1, d.nx, sK, d.nz, prm.cfl);
-        KT_END(K_DADI, s);
-    }
-    {
-        dim3 g((d.ny + 31) / 32, d.nz);
-        KT_BEGIN(K_DADI, s);
-        k_dadi_line<1><<<g, tb, 0, s>>>(d, b, 1, d.nx, sJ, d.ny, sK, d.nz, prm.cfl);
-        KT_END(K_DADI, s);
-    }
-    {
-        dim3 g((d.nx + 31) / 32, d.ny);
-        KT_BEGIN(K_DADI, s);
-        k_dadi_line<2><<<g, tb, 0, s>>>(d, b, sK, d.nz, 1, d.nx, sJ, d.ny, prm.cfl);
-        KT_END(K_DADI, s);
-    }
+    const dim3 tc(32, 4, 1);
+    const dim3 gc((d.nx + 31) / 32, (d.ny + 3) / 4, d.nz);
+    const dim3 tb(32, 1, 1);
+    // j sweep
+    KT_BEGIN(K_DADI, s);
+    k_dadi_coef<0><<<gc, tc, 0, s>>>(d, b, sJ, prm.cfl);
+    KT_END(K_DADI, s);
+    KT_BEGIN(K_DADI, s);
+    k_dadi_thomas<<<dim3((d.nx + 31) / 32, d.nz, 5), tb, 0, s>>>(d, b, sJ, d.ny, 1, d.nx, sK, d.nz);
+    KT_END(K_DADI, s);
+    // i sweep
+    KT_BEGIN(K_DADI, s);
+    k_dadi_coef<1><<<gc, tc, 0, s>>>(d, b, 1, prm.cfl);
+    KT_END(K_DADI, s);
+    KT_BEGIN(K_DADI, s);
+    k_dadi_thomas<<<dim3((d.ny + 31) / 32, d.nz, 5), tb, 0, s>>>(d, b, 1, d.nx, sJ, d.ny, sK, d.nz);
+    KT_END(K_DADI, s);
+    // k sweep
+    KT_BEGIN(K_DADI, s);
+    k_dadi_coef<2><<<gc, tc, 0, s>>>(d, b, sK, prm.cfl);
+    KT_END(K_DADI, s);
+    KT_BEGIN(K_DADI, s);
+    k_dadi_thomas<<<dim3((d.nx + 31) / 32, d.ny, 5), tb, 0, s>>>(d, b, sK, d.nz, 1, d.nx, sJ, d.ny);
+    KT_END(K_DADI, s);
+    KT_BEGIN(K_DADI, s);
+    k_dadi_post<<<gc, tc, 0, s>>>(d, b);
+    KT_END(K_DADI, s);
     return (int)cudaGetLastError();
 }

@@ -184,53 +184,71 @@ __global__ void __launch_bounds__(128, 4) k_sa_rhs(Dims d, BlockDev b, double fa
     b.scratch[N + c] = factor * qq;                 // saSolve :853-866 (implicit relaxation)
 }
 
-// one dd-ADI sweep along sd; nl owned cells per line; multiplyByQQ: j and i sweeps (:996-998)
-__global__ void __launch_bounds__(64) k_sa_line(Dims d, BlockDev b, int axis, int sd, int nl, int s1, int n1, int s2, int n2,
-                                                int multiplyByQQ) {
+// one dd-ADI sweep along sd (saSolve, sa.F90:868-1255), split so that only the recurrence is serial:
+//   k_sa_coef   (one thread per cell): off-diagonals bb, dd (diffusion + first-order upwind advection)
+//               and the rhs ff = dvt * rblank  -> workspace b.flux slots 0..2
+//   k_sa_thomas (one thread per line): backward elimination m = l..2 and forward substitution
+//               (:979-998) reading only precomputed arrays; eliminated diagonal / rhs in slots 3, 4
+__global__ void __launch_bounds__(128) k_sa_coef(Dims d, BlockDev b, int axis, int sd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
+    if (i > d.il || j > d.jl || k > d.kl) return;
+    const int N = (int)d.N;
+    const int c = i + (int)d.sJ * j + (int)d.sK * k;
+    const double* s = axis == 0 ? b.si : (axis == 1 ? b.sj : b.sk);
+    const double* ssum = b.ssum + 3 * axis * N;
+    const double nu = b.rlv[c] / b.w[c];
+    double c1m, c1p, xa, ya, za;
+    sa_diff_coef(b, N, c, sd, s, ssum, nu, c1m, c1p, xa, ya, za);
+    double bb = -c1m, dd = -c1p;
+    const double uu = xa * b.w[N + c] + ya * b.w[2 * N + c] + za * b.w[3 * N + c];
+    const double um = uu < 0.0 ? uu : 0.0, up = uu > 0.0 ? uu : 0.0;
+    bb = bb - up;
+    dd = dd + um;
+    const double rblank = dmax_((double)b.iblank[c], 0.0);
+    b.flux[c] = bb * rblank;
+    b.flux[N + c] = dd * rblank;
+    b.flux[2 * N + c] = b.scratch[c] * rblank;
+}
+
+__global__ void __launch_bounds__(64) k_sa_thomas(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2, int multiplyByQQ) {
     const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
-    const int q2 = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int q2 = blockIdx.y + 2;
     if (q1 > n1 + 1 || q2 > n2 + 1) return;
     const int N = (int)d.N;
     const int base = q1 * s1 + q2 * s2;
-    const double* s = axis == 0 ? b.si : (axis == 1 ? b.sj : b.sk);
-    const double* ssum = b.ssum + 3 * axis * N;
-    double* dvt = b.scratch;
-    const double* qq = b.scratch + N;
-    double* ccA = b.scratch + 3 * N;   // eliminated diagonal
-    double* bbA = b.scratch + 4 * N;   // sub-diagonal (needed again in the forward pass)
+    const double* __restrict__ bbA = b.flux;
+    const double* __restrict__ ddA = b.flux + N;
+    const double* __restrict__ ffA = b.flux + 2 * N;
+    double* __restrict__ ccO = b.flux + 3 * N;
+    double* __restrict__ ffO = b.flux + 4 * N;
+    const double* __restrict__ qq = b.scratch + N;
+    double* __restrict__ dvt = b.scratch;
     const int l = nl + 1;
     // backward elimination m = l .. 2 (row l is untouched by it)
     double ccp = 0.0, ffp = 0.0, bbp = 0.0;
+#pragma unroll 4
     for (int m = l; m >= 2; m--) {
         const int c = base + m * sd;
-        const double nu = b.rlv[c] / b.w[c];
-        double c1m, c1p, xa, ya, za;
-        sa_diff_coef(b, N, c, sd, s, ssum, nu, c1m, c1p, xa, ya, za);
-        double bb = -c1m, dd = -c1p;
-        const double uu = xa * b.w[N + c] + ya * b.w[2 * N + c] + za * b.w[3 * N + c];
-        const double um = uu < 0.0 ? uu : 0.0, up = uu > 0.0 ? uu : 0.0;
-        bb = bb - up;
-        dd = dd + um;
-        const double rblank = dmax_((double)b.iblank[c], 0.0);
-        double cc = qq[c];
-        double ff = dvt[c] * rblank;
-        bb = bb * rblank;
-        dd = dd * rblank;
+        double cc = qq[c], ff = ffA[c];
+        const double bb = bbA[c], dd = ddA[c];
         if (m < l) {
             const double f = dd / ccp;
             cc = cc - f * bbp;
             ff = ff - f * ffp;
         }
-        ccA[c] = cc; bbA[c] = bb; dvt[c] = ff;
+        ccO[c] = cc; ffO[c] = ff;
         ccp = cc; ffp = ff; bbp = bb;
     }
     // forward substitution
     double xm = 0.0;
+#pragma unroll 4
     for (int m = 2; m <= l; m++) {
         const int c = base + m * sd;
-        double ff = dvt[c];
+        double ff = ffO[c];
         if (m > 2) ff = ff - bbA[c] * xm;
-        ff = ff / ccA[c];
+        ff = ff / ccO[c];
         xm = ff;
         dvt[c] = multiplyByQQ ? ff * qq[c] : ff;
     }
@@ -275,25 +293,18 @@ static int launch_sa_block(const Dims& d, const BlockDev& b, const AdfbParams& p
         k_sa_rhs<<<g, tr, 0, s>>>(d, b, factor);
         KT_END(K_SASOLVE, s);
     }
-    dim3 tl(32, 1);
-    {
-        dim3 g((d.nx + 31) / 32, d.nz);
+    const dim3 tl(32, 1), tc(32, 4, 1), gc((d.nx + 31) / 32, (d.ny + 3) / 4, d.nz);
+    auto sweep = [&](int axis, int sd, int nl, int s1, int n1, int s2, int n2, int mult) {
         KT_BEGIN(K_SASOLVE, s);
-        k_sa_line<<<g, tl, 0, s>>>(d, b, 1, sJ, d.ny, 1, d.nx, sK, d.nz, 1);
+        k_sa_coef<<<gc, tc, 0, s>>>(d, b, axis, sd);
         KT_END(K_SASOLVE, s);
-    }
-    {
-        dim3 g((d.ny + 31) / 32, d.nz);
         KT_BEGIN(K_SASOLVE, s);
-        k_sa_line<<<g, tl, 0, s>>>(d, b, 0, 1, d.nx, sJ, d.ny, sK, d.nz, 1);
+        k_sa_thomas<<<dim3((n1 + 31) / 32, n2), tl, 0, s>>>(d, b, sd, nl, s1, n1, s2, n2, mult);
         KT_END(K_SASOLVE, s);
-    }
-    {
-        dim3 g((d.nx + 31) / 32, d.ny);
-        KT_BEGIN(K_SASOLVE, s);
-        k_sa_line<<<g, tl, 0, s>>>(d, b, 2, sK, d.nz, 1, d.nx, sJ, d.ny, 0);
-        KT_END(K_SASOLVE, s);
-    }
+    };
+    sweep(1, sJ, d.ny, 1, d.nx, sK, d.nz, 1);   // j lines
+    sweep(0, 1, d.nx, sJ, d.ny, sK, d.nz, 1);   // i lines
+    sweep(2, sK, d.nz, 1, d.nx, sJ, d.ny, 0);   // k lines
     {
         dim3 tb(32, 4, 2);
         dim3 g((d.nx + 31) / 32, (d.ny + 3) / 4, (d.nz + 1) / 2);

@@ -300,53 +300,77 @@ __device__ __forceinline__ double ra_rfl(const BlockDev& b, const Dims& d, long 
     const double dpk = fabs(p[c + d.sK] - 2.0 * p0 + p[c - d.sK]) / (p[c + d.sK] + 2.0 * p0 + p[c - d.sK] + plim);
     return 1.0 / (1.0 + 2.0 * (dpi + dpj + dpk));
 }
-__global__ void __launch_bounds__(128) k_resavg_line(Dims d, BlockDev b, long long sd, int n, long long s1, int n1, long long s2,
+// residualAveraging (residuals.F90:1785-2080), split so that only the recurrences are serial.
+// Workspace b.flux: slot 0 rfl (pressure switch, one pass per call), 1 t, 2 d, 3 epz of the current
+// direction, 4..8 the forward-swept residuals.
+__global__ void __launch_bounds__(256) k_resavg_rfl(Dims d, BlockDev b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
+    if (i > d.il || j > d.jl || k > d.kl) return;
+    const long long c = ADFB_IDX(i, j, k);
+    b.flux[c] = ra_rfl(b, d, c, 0.001 * c_prm.pInfCorr);
+}
+// one thread per line: epz(i), t(i) = 1/(1 + epz(i) + epz(i-1) - epz(i-1) d(i-1)), d(i) = t(i) epz(i)
+__global__ void __launch_bounds__(128) k_resavg_coef(Dims d, BlockDev b, long long sd, int n, long long s1, int n1, long long s2,
                                                      int n2, double rfl0) {
     const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int q2 = blockIdx.y * blockDim.y + threadIdx.y + 2;
     if (q1 > n1 + 1 || q2 > n2 + 1) return;
     const long long N = d.N;
     const long long base = q1 * s1 + q2 * s2;
-    const double plim = 0.001 * c_prm.pInfCorr, smoop = c_prm.smoop;
-    double* epzA = b.scratch;       // epz(i)
-    double* dA = b.scratch + N;     // d(i)
+    const double smoop = c_prm.smoop;
+    const double* __restrict__ rfl = b.flux;
+    double* __restrict__ tA = b.flux + N;
+    double* __restrict__ dA = b.flux + 2 * N;
+    double* __restrict__ epzA = b.flux + 3 * N;
     const int l = n + 1;
-    // forward sweep fused with the coefficient recurrences
-    double epzm = 0.0, dm = 0.0;    // epz(i-1), d(i-1) ; epz(1) = d(1) = 0
-    double rflc = ra_rfl(b, d, base + 2 * sd, plim);
-    double dwm[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // dw(i-1) after the forward update (multiplied by epz(1)=0 at i=2)
+    double epzm = 0.0, dm = 0.0;  // epz(1) = d(1) = 0
+#pragma unroll 4
     for (int i = 2; i <= l; i++) {
         const long long c = base + i * sd;
         double epz = 0.0;
         if (i <= n) {
-            const double rfln = ra_rfl(b, d, c + sd, plim);
-            const double r = rfl0 * (rflc + rfln);
+            const double r = rfl0 * (rfl[c] + rfl[c + sd]);
             epz = 0.25 * smoop * dmax_(r * r - 1.0, 0.0) * dmax_((double)b.iblank[c], 0.0);
-            rflc = rfln;
         }
         const double t = 1.0 / (1.0 + epz + epzm - epzm * dm);
         const double dd = t * epz;
-#pragma unroll
-        for (int m = 0; m < 5; m++) {
-            const double v = t * (b.dw[m * N + c] + epzm * dwm[m]);
-            b.dw[m * N + c] = v;
-            dwm[m] = v;
-        }
-        dA[c] = dd;
-        epzA[c] = epz;
+        tA[c] = t; dA[c] = dd; epzA[c] = epz;
         epzm = epz; dm = dd;
     }
-    // backward substitution i = n .. 2
-    for (int m = 0; m < 5; m++) dwm[m] = b.dw[m * N + base + l * sd];
+}
+// one thread per line and variable m = blockIdx.z: forward sweep and back substitution
+__global__ void __launch_bounds__(128) k_resavg_sweep(Dims d, BlockDev b, long long sd, int n, long long s1, int n1, long long s2,
+                                                      int n2) {
+    const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int q2 = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    if (q1 > n1 + 1 || q2 > n2 + 1) return;
+    const long long N = d.N;
+    const long long base = q1 * s1 + q2 * s2;
+    const int m = blockIdx.z;
+    const double* __restrict__ tA = b.flux + N;
+    const double* __restrict__ dA = b.flux + 2 * N;
+    const double* __restrict__ epzA = b.flux + 3 * N;
+    double* __restrict__ fo = b.flux + (4 + m) * N;
+    double* __restrict__ dw = b.dw + m * N;
+    const int l = n + 1;
+    double dwm = 0.0;  // dw(i-1) after the forward update (multiplied by epz(1) = 0 at i = 2)
+#pragma unroll 4
+    for (int i = 2; i <= l; i++) {
+        const long long c = base + i * sd;
+        const double epzm = (i > 2) ? epzA[c - sd] : 0.0;
+        const double v = tA[c] * (dw[c] + epzm * dwm);
+        fo[c] = v;
+        dwm = v;
+    }
+    dw[base + l * sd] = dwm;
+#pragma unroll 4
     for (int i = n; i >= 2; i--) {
         const long long c = base + i * sd;
-        const double dd = dA[c];
-#pragma unroll
-        for (int m = 0; m < 5; m++) {
-            const double v = b.dw[m * N + c] + dd * dwm[m];
-            b.dw[m * N + c] = v;
-            dwm[m] = v;
-        }
+        const double v = fo[c] + dA[c] * dwm;
+        dw[c] = v;
+        dwm = v;
     }
 }
 
@@ -389,12 +413,21 @@ static int launch_bc_flow(const Dims& d, const BlockDev& b, const std::vector<Ad
 
 static int launch_residual_averaging(const Dims& d, const BlockDev& b, const AdfbParams& prm, cudaStream_t s) {
     const double rfl0 = 0.5 * prm.cfl / prm.cflLimit;
-    dim3 tb(32, 4);
+    {
+        dim3 tb(32, 4, 2);
+        dim3 g((d.nx + 31) / 32, (d.ny + 3) / 4, (d.nz + 1) / 2);
+        KT_BEGIN(K_RK, s);
+        k_resavg_rfl<<<g, tb, 0, s>>>(d, b);
+        KT_END(K_RK, s);
+    }
+    dim3 tb(32, 2);
     auto run = [&](long long sd, int n, long long s1, int n1, long long s2, int n2) {
         if (n <= 1) return;
-        dim3 g((n1 + 31) / 32, (n2 + 3) / 4);
         KT_BEGIN(K_RK, s);
-        k_resavg_line<<<g, tb, 0, s>>>(d, b, sd, n, s1, n1, s2, n2, rfl0);
+        k_resavg_coef<<<dim3((n1 + 31) / 32, (n2 + 1) / 2), tb, 0, s>>>(d, b, sd, n, s1, n1, s2, n2, rfl0);
+        KT_END(K_RK, s);
+        KT_BEGIN(K_RK, s);
+        k_resavg_sweep<<<dim3((n1 + 31) / 32, (n2 + 1) / 2, 5), tb, 0, s>>>(d, b, sd, n, s1, n1, s2, n2);
         KT_END(K_RK, s);
     };
     run(1, d.nx, d.sJ, d.ny, d.sK, d.nz);

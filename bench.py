@@ -333,6 +333,45 @@ def main():
     res_ms = sum(ms_k[i] for i in range(nk)) / args.steps  # every kernel of the step (preamble, BCs, halo, core)
     _ = flags_core
 
+    # ---- the other operators of the metric (smoothers, SA solve, matrix-free matvec): N = 1 only --------
+    others = None
+    if world == 1:
+        others = {}
+        nrep = max(3, min(10, args.steps))
+
+        def ev_time(fn):
+            fn()  # warm-up (graph capture, lazy allocations)
+            return timed_steps(fn, nrep) / nrep
+
+        s.timeStep(False)
+        s.smootherResidual(0)
+        for name, fn, bpc in (
+            ("rk_cycle_5stage", lambda: s.rkCycle(), 5 * 272.0),
+            ("dadi_step", lambda: s.dadiStep(), 236.0 + 160.0),
+            ("sa_ddadi_3subiter", lambda: s.turbSolveDDADI(3), 3 * 156.0),
+        ):
+            ms = ev_time(fn)
+            others[name] = {"ms": ms, "Mcells/s": cells / (ms * 1e-3) / 1e6, "algorithmic_bytes_per_cell": bpc,
+                            "GB/s": bpc * cells / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": bpc * cells / (ms * 1e-3) / 1e9 / peaks()[0]}
+        # matrix-free matvec y = (F(U + h a) - F(U)) / h through the vector API (host vectors, so PCIe included)
+        s.uploadState(0, hb)
+        U = s.getStates()
+        s.mffdSetBase(U)
+        a = np.random.default_rng(7).standard_normal(U.size)
+        y = np.zeros_like(a)
+        s.mffdApply(a, 1e-7, out=y)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            s.mffdApply(a, 1e-7, out=y)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / nrep
+        others["mffd_matvec_host_vectors"] = {
+            "ms": ms, "Mcells/s": cells / (ms * 1e-3) / 1e6, "algorithmic_bytes_per_cell": 464.0,
+            "GB/s": 464.0 * cells / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 464.0 * cells / (ms * 1e-3) / 1e9 / peaks()[0],
+            "note": "unfused form: perturb + residual + difference (464 B/cell); a and y are pageable host vectors, "
+                    "so the time includes 2 x %d MB over PCIe" % (a.nbytes >> 20)}
+
     # max over ranks
     ms_step = ms_total / args.steps
     if world > 1:
@@ -364,6 +403,8 @@ def main():
                          "algorithmic_bytes_per_cell": BYTES_PER_CELL, "kernels": kernels},
             "clocks": clocks,
         }
+        if others:
+            line["other_operators"] = others
         if not args.no_cpu_baseline:
             v, reps, kind = cpu_baseline_single(shape)
             line["cpu_baseline"] = {"value": v, "unit": "Mcells/s", "cores": 1, "kind": kind,
