@@ -167,7 +167,8 @@ __device__ __forceinline__ void dadi_post(const BlockDev& b, int N, int c, doubl
 //                                              the precomputed arrays
 //   k_dadi_post   (one thread per cell, k sweep only): T_zeta and the -1/vol scaling
 // `work` is the face-flux workspace b.flux (free while the smoother update runs): slots 0..8 cell
-// coefficients, 9..13 the eliminated super-diagonal per variable, 14..18 the forward-swept rhs.
+// coefficients, 9..13 the eliminated super-diagonal per variable, 14..18 the forward-swept rhs,
+// 19..27 the tridiagonal rows per coefficient set (k_dadi_tri).
 template <int DIR>
 __global__ void __launch_bounds__(128) k_dadi_coef(Dims d, BlockDev b, int sd, double cfl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
@@ -208,6 +209,28 @@ __global__ void __launch_bounds__(128) k_dadi_post(Dims d, BlockDev b) {
     for (int n = 0; n < 5; n++) b.dw[n * N + c] = f[n];
 }
 
+// tridiagonal rows of the three coefficient sets from the cell coefficients of the cell and its two line
+// neighbours (residuals.F90:1374-1391): work slots 19+t (diagonal), 22+t (sub-), 25+t (super-diagonal)
+__global__ void __launch_bounds__(256) k_dadi_tri(Dims d, BlockDev b, int sd, int dirIdx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
+    if (i > d.il || j > d.jl || k > d.kl) return;
+    const int N = (int)d.N;
+    const int c = i + (int)d.sJ * j + (int)d.sK * k;
+    const int m = dirIdx == 0 ? j : (dirIdx == 1 ? i : k);
+    const int l = dirIdx == 0 ? d.jl : (dirIdx == 1 ? d.il : d.kl);
+    const double* w = b.flux;
+    const double dt = w[8 * N + c];
+    const double vt2 = w[6 * N + c] + w[7 * N + c];
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        b.flux[(19 + t) * N + c] = 1.0 + (vt2 + w[t * N + c] - w[(3 + t) * N + c]) * dt;
+        b.flux[(22 + t) * N + c] = (m > 2) ? (-w[6 * N + c - sd] - w[t * N + c - sd]) * dt : 0.0;
+        b.flux[(25 + t) * N + c] = (m < l) ? (-w[7 * N + c + sd] + w[(3 + t) * N + c + sd]) * dt : 0.0;
+    }
+}
+
 // one thread = one grid line (nl owned cells along sd) of one variable n = blockIdx.z
 __global__ void __launch_bounds__(64) k_dadi_thomas(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2) {
     const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
@@ -219,39 +242,56 @@ __global__ void __launch_bounds__(64) k_dadi_thomas(Dims d, BlockDev b, int sd, 
     const int base = q1 * s1 + q2 * s2;
     const int l = nl + 1;
     if (nl <= 1) return;  // `if (jl > 2)` guards: no implicit solve (changes of basis done by k_dadi_coef / k_dadi_post)
-    const double* __restrict__ dP = b.flux + t * N;
-    const double* __restrict__ dM = b.flux + (3 + t) * N;
-    const double* __restrict__ vt1 = b.flux + 6 * N;
-    const double* __restrict__ vt3 = b.flux + 7 * N;
-    const double* __restrict__ dtrb = b.flux + 8 * N;
+    const double* __restrict__ ccA = b.flux + (19 + t) * N;
+    const double* __restrict__ bbA = b.flux + (22 + t) * N;
+    const double* __restrict__ dsA = b.flux + (25 + t) * N;
     double* __restrict__ dd = b.flux + (9 + n) * N;
     double* __restrict__ fo = b.flux + (14 + n) * N;
     double* __restrict__ f = b.dw + n * N;
     double ddp = 0.0, ffp = 0.0;
-#pragma unroll 4
-    for (int m = 2; m <= l; m++) {
-        const int c = base + m * sd;
-        const double dt = dtrb[c];
-        const double vt2 = vt1[c] + vt3[c];
-        const double cc = 1.0 + (vt2 + dP[c] - dM[c]) * dt;
-        const double bbm = (m > 2) ? (-vt1[c - sd] - dP[c - sd]) * dt : 0.0;
-        const double dsup = (m < l) ? (-vt3[c + sd] + dM[c + sd]) * dt : 0.0;
-        const double d0 = (m == 2) ? 1.0 / cc : 1.0 / (cc - bbm * ddp);
-        const double ddm = dsup * d0;
-        dd[c] = ddm;
-        double fv = f[c];
-        fv = (m == 2) ? fv * d0 : (fv - bbm * ffp) * d0;
-        fo[c] = fv;
-        ffp = fv; ddp = ddm;
+    // The recurrence is walked in chunks of CH cells: all loads (and the recurrence-independent
+    // arithmetic) of a chunk are issued first, so their latencies overlap; only 1/(cc - bb*dd) and
+    // the rhs update form the serial chain.
+    constexpr int CH = 8;
+    for (int m0 = 2; m0 <= l; m0 += CH) {
+        double cc[CH], bb[CH], ds[CH], fv[CH];
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const int m = m0 + u;
+            if (m <= l) { const int c = base + m * sd; cc[u] = ccA[c]; bb[u] = bbA[c]; ds[u] = dsA[c]; fv[u] = f[c]; }
+        }
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const int m = m0 + u;
+            if (m <= l) {
+                const int c = base + m * sd;
+                const double d0 = (m == 2) ? 1.0 / cc[u] : 1.0 / (cc[u] - bb[u] * ddp);
+                const double ddm = ds[u] * d0;
+                dd[c] = ddm;
+                const double v = (m == 2) ? fv[u] * d0 : (fv[u] - bb[u] * ffp) * d0;
+                fo[c] = v;
+                ffp = v; ddp = ddm;
+            }
+        }
     }
     // back substitution; ffp holds ff(l)
     f[base + l * sd] = ffp;
-#pragma unroll 4
-    for (int m = l - 1; m >= 2; m--) {
-        const int c = base + m * sd;
-        const double fv = fo[c] - dd[c] * ffp;
-        f[c] = fv;
-        ffp = fv;
+    for (int m0 = l - 1; m0 >= 2; m0 -= CH) {
+        double fr[CH], dr[CH];
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const int m = m0 - u;
+            if (m >= 2) { const int c = base + m * sd; fr[u] = fo[c]; dr[u] = dd[c]; }
+        }
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const int m = m0 - u;
+            if (m >= 2) {
+                const double v = fr[u] - dr[u] * ffp;
+                f[base + m * sd] = v;
+                ffp = v;
+            }
+        }
     }
 }
 
@@ -268,6 +308,9 @@ static int launch_dadi(const Dims& d, const BlockDev& b, const AdfbParams& prm, 
     k_dadi_coef<0><<<gc, tc, 0, s>>>(d, b, sJ, prm.cfl);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
+    k_dadi_tri<<<gc, tc, 0, s>>>(d, b, sJ, 0);
+    KT_END(K_DADI, s);
+    KT_BEGIN(K_DADI, s);
     k_dadi_thomas<<<dim3((d.nx + 31) / 32, d.nz, 5), tb, 0, s>>>(d, b, sJ, d.ny, 1, d.nx, sK, d.nz);
     KT_END(K_DADI, s);
     // i sweep
@@ -275,11 +318,17 @@ static int launch_dadi(const Dims& d, const BlockDev& b, const AdfbParams& prm, 
     k_dadi_coef<1><<<gc, tc, 0, s>>>(d, b, 1, prm.cfl);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
+    k_dadi_tri<<<gc, tc, 0, s>>>(d, b, 1, 1);
+    KT_END(K_DADI, s);
+    KT_BEGIN(K_DADI, s);
     k_dadi_thomas<<<dim3((d.ny + 31) / 32, d.nz, 5), tb, 0, s>>>(d, b, 1, d.nx, sJ, d.ny, sK, d.nz);
     KT_END(K_DADI, s);
     // k sweep
     KT_BEGIN(K_DADI, s);
     k_dadi_coef<2><<<gc, tc, 0, s>>>(d, b, sK, prm.cfl);
+    KT_END(K_DADI, s);
+    KT_BEGIN(K_DADI, s);
+    k_dadi_tri<<<gc, tc, 0, s>>>(d, b, sK, 2);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
     k_dadi_thomas<<<dim3((d.nx + 31) / 32, d.ny, 5), tb, 0, s>>>(d, b, sK, d.nz, 1, d.nx, sJ, d.ny);

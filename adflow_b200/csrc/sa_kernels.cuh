@@ -228,29 +228,50 @@ __global__ void __launch_bounds__(64) k_sa_thomas(Dims d, BlockDev b, int sd, in
     const int l = nl + 1;
     // backward elimination m = l .. 2 (row l is untouched by it)
     double ccp = 0.0, ffp = 0.0, bbp = 0.0;
-#pragma unroll 4
-    for (int m = l; m >= 2; m--) {
-        const int c = base + m * sd;
-        double cc = qq[c], ff = ffA[c];
-        const double bb = bbA[c], dd = ddA[c];
-        if (m < l) {
-            const double f = dd / ccp;
-            cc = cc - f * bbp;
-            ff = ff - f * ffp;
+    constexpr int CH = 8;   // chunked walk: loads of a chunk first (latencies overlap), then the serial chain
+    for (int m0 = l; m0 >= 2; m0 -= CH) {
+        double cq[CH], fq[CH], bq[CH], dq[CH];
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const int m = m0 - u;
+            if (m >= 2) { const int c = base + m * sd; cq[u] = qq[c]; fq[u] = ffA[c]; bq[u] = bbA[c]; dq[u] = ddA[c]; }
         }
-        ccO[c] = cc; ffO[c] = ff;
-        ccp = cc; ffp = ff; bbp = bb;
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const int m = m0 - u;
+            if (m >= 2) {
+                const int c = base + m * sd;
+                double cc = cq[u], ff = fq[u];
+                if (m < l) {
+                    const double f = dq[u] / ccp;
+                    cc = cc - f * bbp;
+                    ff = ff - f * ffp;
+                }
+                ccO[c] = cc; ffO[c] = ff;
+                ccp = cc; ffp = ff; bbp = bq[u];
+            }
+        }
     }
     // forward substitution
     double xm = 0.0;
-#pragma unroll 4
-    for (int m = 2; m <= l; m++) {
-        const int c = base + m * sd;
-        double ff = ffO[c];
-        if (m > 2) ff = ff - bbA[c] * xm;
-        ff = ff / ccO[c];
-        xm = ff;
-        dvt[c] = multiplyByQQ ? ff * qq[c] : ff;
+    for (int m0 = 2; m0 <= l; m0 += CH) {
+        double fq[CH], bq[CH], cq[CH], qv[CH];
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const int m = m0 + u;
+            if (m <= l) { const int c = base + m * sd; fq[u] = ffO[c]; bq[u] = bbA[c]; cq[u] = ccO[c]; qv[u] = qq[c]; }
+        }
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const int m = m0 + u;
+            if (m <= l) {
+                double ff = fq[u];
+                if (m > 2) ff = ff - bq[u] * xm;
+                ff = ff / cq[u];
+                xm = ff;
+                dvt[base + m * sd] = multiplyByQQ ? ff * qv[u] : ff;
+            }
+        }
     }
 }
 

@@ -301,8 +301,8 @@ __device__ __forceinline__ double ra_rfl(const BlockDev& b, const Dims& d, long 
     return 1.0 / (1.0 + 2.0 * (dpi + dpj + dpk));
 }
 // residualAveraging (residuals.F90:1785-2080), split so that only the recurrences are serial.
-// Workspace b.flux: slot 0 rfl (pressure switch, one pass per call), 1 t, 2 d, 3 epz of the current
-// direction, 4..8 the forward-swept residuals.
+// Workspace b.flux: slot 0 rfl (pressure switch), 1..3 epz of the i, j, k direction (both one pass per
+// call, one thread per cell), 4..8 the forward-swept residuals, 9..13 d(i) per variable.
 __global__ void __launch_bounds__(256) k_resavg_rfl(Dims d, BlockDev b) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
@@ -311,66 +311,80 @@ __global__ void __launch_bounds__(256) k_resavg_rfl(Dims d, BlockDev b) {
     const long long c = ADFB_IDX(i, j, k);
     b.flux[c] = ra_rfl(b, d, c, 0.001 * c_prm.pInfCorr);
 }
-// one thread per line: epz(i), t(i) = 1/(1 + epz(i) + epz(i-1) - epz(i-1) d(i-1)), d(i) = t(i) epz(i)
-__global__ void __launch_bounds__(128) k_resavg_coef(Dims d, BlockDev b, long long sd, int n, long long s1, int n1, long long s2,
-                                                     int n2, double rfl0) {
-    const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
-    const int q2 = blockIdx.y * blockDim.y + threadIdx.y + 2;
-    if (q1 > n1 + 1 || q2 > n2 + 1) return;
-    const long long N = d.N;
-    const long long base = q1 * s1 + q2 * s2;
-    const double smoop = c_prm.smoop;
-    const double* __restrict__ rfl = b.flux;
-    double* __restrict__ tA = b.flux + N;
-    double* __restrict__ dA = b.flux + 2 * N;
-    double* __restrict__ epzA = b.flux + 3 * N;
-    const int l = n + 1;
-    double epzm = 0.0, dm = 0.0;  // epz(1) = d(1) = 0
-#pragma unroll 4
-    for (int i = 2; i <= l; i++) {
-        const long long c = base + i * sd;
-        double epz = 0.0;
-        if (i <= n) {
-            const double r = rfl0 * (rfl[c] + rfl[c + sd]);
-            epz = 0.25 * smoop * dmax_(r * r - 1.0, 0.0) * dmax_((double)b.iblank[c], 0.0);
-        }
-        const double t = 1.0 / (1.0 + epz + epzm - epzm * dm);
-        const double dd = t * epz;
-        tA[c] = t; dA[c] = dd; epzA[c] = epz;
-        epzm = epz; dm = dd;
-    }
+// epz(i) = 1/4 smoop max(r^2 - 1, 0) max(iblank, 0), r = rfl0 (rfl(i) + rfl(i+1)), for i < l; epz(l) = 0
+__global__ void __launch_bounds__(256) k_resavg_eps(Dims d, BlockDev b, double rfl0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
+    if (i > d.il || j > d.jl || k > d.kl) return;
+    const long long c = ADFB_IDX(i, j, k), N = d.N;
+    const double* rfl = b.flux;
+    const double smoop = c_prm.smoop, r0 = rfl[c], rblank = dmax_((double)b.iblank[c], 0.0);
+    double e = 0.0, r;
+    if (i < d.il) { r = rfl0 * (r0 + rfl[c + 1]); e = 0.25 * smoop * dmax_(r * r - 1.0, 0.0) * rblank; }
+    b.flux[N + c] = e;
+    e = 0.0;
+    if (j < d.jl) { r = rfl0 * (r0 + rfl[c + d.sJ]); e = 0.25 * smoop * dmax_(r * r - 1.0, 0.0) * rblank; }
+    b.flux[2 * N + c] = e;
+    e = 0.0;
+    if (k < d.kl) { r = rfl0 * (r0 + rfl[c + d.sK]); e = 0.25 * smoop * dmax_(r * r - 1.0, 0.0) * rblank; }
+    b.flux[3 * N + c] = e;
 }
-// one thread per line and variable m = blockIdx.z: forward sweep and back substitution
-__global__ void __launch_bounds__(128) k_resavg_sweep(Dims d, BlockDev b, long long sd, int n, long long s1, int n1, long long s2,
-                                                      int n2) {
+// one thread per line and variable m = blockIdx.z: t(i) = 1/(1 + epz(i) + epz(i-1) - epz(i-1) d(i-1)),
+// d(i) = t(i) epz(i), forward sweep dw(i) = t(i) (dw(i) + epz(i-1) dw(i-1)), back substitution
+__global__ void __launch_bounds__(64) k_resavg_sweep(Dims d, BlockDev b, int dir, long long sd, int n, long long s1, int n1,
+                                                     long long s2, int n2) {
     const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int q2 = blockIdx.y * blockDim.y + threadIdx.y + 2;
     if (q1 > n1 + 1 || q2 > n2 + 1) return;
     const long long N = d.N;
     const long long base = q1 * s1 + q2 * s2;
     const int m = blockIdx.z;
-    const double* __restrict__ tA = b.flux + N;
-    const double* __restrict__ dA = b.flux + 2 * N;
-    const double* __restrict__ epzA = b.flux + 3 * N;
+    const double* __restrict__ epzA = b.flux + (1 + dir) * N;
     double* __restrict__ fo = b.flux + (4 + m) * N;
+    double* __restrict__ dA = b.flux + (9 + m) * N;
     double* __restrict__ dw = b.dw + m * N;
     const int l = n + 1;
-    double dwm = 0.0;  // dw(i-1) after the forward update (multiplied by epz(1) = 0 at i = 2)
-#pragma unroll 4
-    for (int i = 2; i <= l; i++) {
-        const long long c = base + i * sd;
-        const double epzm = (i > 2) ? epzA[c - sd] : 0.0;
-        const double v = tA[c] * (dw[c] + epzm * dwm);
-        fo[c] = v;
-        dwm = v;
+    double dwm = 0.0, epzm = 0.0, dm = 0.0;  // epz(1) = d(1) = 0
+    constexpr int CH = 8;  // chunked walk: loads of a chunk first, then the serial chain
+    for (int i0 = 2; i0 <= l; i0 += CH) {
+        double eq[CH], wq[CH];
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const int i = i0 + u;
+            if (i <= l) { const long long c = base + i * sd; eq[u] = epzA[c]; wq[u] = dw[c]; }
+        }
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const int i = i0 + u;
+            if (i <= l) {
+                const long long c = base + i * sd;
+                const double epz = eq[u];
+                const double t = 1.0 / (1.0 + epz + epzm - epzm * dm);
+                const double dd = t * epz;
+                const double v = t * (wq[u] + epzm * dwm);
+                fo[c] = v; dA[c] = dd;
+                dwm = v; epzm = epz; dm = dd;
+            }
+        }
     }
     dw[base + l * sd] = dwm;
-#pragma unroll 4
-    for (int i = n; i >= 2; i--) {
-        const long long c = base + i * sd;
-        const double v = fo[c] + dA[c] * dwm;
-        dw[c] = v;
-        dwm = v;
+    for (int i0 = n; i0 >= 2; i0 -= CH) {
+        double fq[CH], dq[CH];
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const int i = i0 - u;
+            if (i >= 2) { const long long c = base + i * sd; fq[u] = fo[c]; dq[u] = dA[c]; }
+        }
+#pragma unroll
+        for (int u = 0; u < CH; u++) {
+            const int i = i0 - u;
+            if (i >= 2) {
+                const double v = fq[u] + dq[u] * dwm;
+                dw[base + i * sd] = v;
+                dwm = v;
+            }
+        }
     }
 }
 
@@ -419,20 +433,20 @@ static int launch_residual_averaging(const Dims& d, const BlockDev& b, const Adf
         KT_BEGIN(K_RK, s);
         k_resavg_rfl<<<g, tb, 0, s>>>(d, b);
         KT_END(K_RK, s);
+        KT_BEGIN(K_RK, s);
+        k_resavg_eps<<<g, tb, 0, s>>>(d, b, rfl0);
+        KT_END(K_RK, s);
     }
     dim3 tb(32, 2);
-    auto run = [&](long long sd, int n, long long s1, int n1, long long s2, int n2) {
+    auto run = [&](int dir, long long sd, int n, long long s1, int n1, long long s2, int n2) {
         if (n <= 1) return;
         KT_BEGIN(K_RK, s);
-        k_resavg_coef<<<dim3((n1 + 31) / 32, (n2 + 1) / 2), tb, 0, s>>>(d, b, sd, n, s1, n1, s2, n2, rfl0);
-        KT_END(K_RK, s);
-        KT_BEGIN(K_RK, s);
-        k_resavg_sweep<<<dim3((n1 + 31) / 32, (n2 + 1) / 2, 5), tb, 0, s>>>(d, b, sd, n, s1, n1, s2, n2);
+        k_resavg_sweep<<<dim3((n1 + 31) / 32, (n2 + 1) / 2, 5), tb, 0, s>>>(d, b, dir, sd, n, s1, n1, s2, n2);
         KT_END(K_RK, s);
     };
-    run(1, d.nx, d.sJ, d.ny, d.sK, d.nz);
-    run(d.sJ, d.ny, 1, d.nx, d.sK, d.nz);
-    run(d.sK, d.nz, 1, d.nx, d.sJ, d.ny);
+    run(0, 1, d.nx, d.sJ, d.ny, d.sK, d.nz);
+    run(1, d.sJ, d.ny, 1, d.nx, d.sK, d.nz);
+    run(2, d.sK, d.nz, 1, d.nx, d.sJ, d.ny);
     return (int)cudaGetLastError();
 }
 
