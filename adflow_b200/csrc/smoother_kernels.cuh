@@ -57,6 +57,9 @@ __device__ __forceinline__ void bc_extrap2(const BlockDev& b, long long N, long 
 }
 
 __global__ void __launch_bounds__(128) k_bc_turb(Dims d, BlockDev b, FaceDev f, int secondHalo) {
+    // launched with programmatic stream serialization: the launch overlaps the tail of the previous
+    // kernel, the data dependency is honoured here
+    cudaGridDependencySynchronize();
     const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
     const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
     if (ia > f.icEnd || jb > f.jcEnd) return;
@@ -84,6 +87,7 @@ __global__ void __launch_bounds__(128) k_bc_turb(Dims d, BlockDev b, FaceDev f, 
 
 // phase: 1 = symmetry first halo, 2 = symmetry second halo, 0 = everything else
 __global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, int secondHalo, int phase) {
+    cudaGridDependencySynchronize();
     const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
     const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
     if (ia > f.icEnd || jb > f.jcEnd) return;
@@ -391,13 +395,28 @@ __global__ void __launch_bounds__(64) k_resavg_sweep(Dims d, BlockDev b, int dir
 }  // namespace
 
 // ---------------------------------------------------------------------------
+// Launch with the programmatic-dependent-launch attribute (the kernel must call
+// cudaGridDependencySynchronize() before touching memory).  ADFB_PDL=0 falls back to a plain launch.
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kern)(KArgs...), dim3 g, dim3 tb, cudaStream_t s, Args... args) {
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("ADFB_PDL"); pdl = e ? atoi(e) : 1; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = g; cfg.blockDim = tb; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static int launch_bc_turb(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, int secondHalo, cudaStream_t s) {
     for (const AdfbSubface& sf : subs) {
         FaceDev f = make_face(d, sf);
         dim3 tb(32, 4);
         dim3 g((f.icEnd - f.icBeg + 1 + 31) / 32, (f.jcEnd - f.jcBeg + 1 + 3) / 4);
         KT_BEGIN(K_BC, s);
-        k_bc_turb<<<g, tb, 0, s>>>(d, b, f, secondHalo);
+        launch_pdl(k_bc_turb, g, tb, s, d, b, f, secondHalo);
         KT_END(K_BC, s);
     }
     return (int)cudaGetLastError();
@@ -408,7 +427,7 @@ static void launch_bc_one(const Dims& d, const BlockDev& b, const AdfbSubface& s
     dim3 tb(32, 4);
     dim3 g((f.icEnd - f.icBeg + 1 + 31) / 32, (f.jcEnd - f.jcBeg + 1 + 3) / 4);
     KT_BEGIN(K_BC, s);
-    k_bc_flow<<<g, tb, 0, s>>>(d, b, f, secondHalo, phase);
+    launch_pdl(k_bc_flow, g, tb, s, d, b, f, secondHalo, phase);
     KT_END(K_BC, s);
 }
 
