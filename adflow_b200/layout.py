@@ -53,14 +53,14 @@ class BlockDims:
 
 
 # number of trailing components of each array class
-NCOMP = {"x": 3, "si": 3, "sj": 3, "sk": 3, "fw": 5, "wn": 5, "dss": 3, "grad": 12, "scratch": 10}
+NCOMP = {"x": 3, "si": 3, "sj": 3, "sk": 3, "fw": 5, "wn": 5, "dss": 3, "grad": 12, "scratch": 10, "wallTau": 27}
 
 
 class HostBlock:
     """All per-block host arrays in uniform boxes (numpy, Fortran order)."""
 
     REAL = ["p", "rlv", "rev", "vol", "volRef", "d2Wall", "ss", "aa", "radI", "radJ", "radK", "dtl", "pn", "shock"]
-    VEC = ["x", "si", "sj", "sk", "fw", "wn", "dss", "grad", "scratch"]
+    VEC = ["x", "si", "sj", "sk", "fw", "wn", "dss", "grad", "scratch", "wallTau"]
 
     def __init__(self, nx, ny, nz, nw=6, right_handed=True):
         self.d = BlockDims(nx, ny, nz)

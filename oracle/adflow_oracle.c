@@ -393,7 +393,7 @@ void orc_nodal_gradients(const OrcBlock* b) {
    (block twin src/solver/fluxes.F90:2534-3485; blockette QCR floor 1e-10).
    Wall tau/q storage (viscSubface) is not part of the residual and omitted. */
 static void viscous_dir(const OrcBlock* b, const AdfbParams* prm, Dims d, const double* s, const int8_t* por,
-                        long sd, long t1, long t2, int i0, int j0, int k0, double rFilv) {
+                        long sd, long t1, long t2, int i0, int j0, int k0, double rFilv, int dir) {
     const double xminn = 1.e-10, twoThird = two * third, Ccr1 = 0.3;
     double gam = prm->gammaInf;
     for (int k = k0; k <= d.kl; k++) for (int j = j0; j <= d.jl; j++) for (int i = i0; i <= d.il; i++) {
@@ -462,13 +462,18 @@ static void viscous_dir(const OrcBlock* b, const AdfbParams* prm, Dims d, const 
                        (ubar * tauxz + vbar * tauyz + wbar * tauzz) * s3 - q_x * s1 - q_y * s2 - q_z * s3;
         FW(c, IMX) -= fmx; FW(c, IMY) -= fmy; FW(c, IMZ) -= fmz; FW(c, IRHOE) -= frhoE;
         FW(cp, IMX) += fmx; FW(cp, IMY) += fmy; FW(cp, IMZ) += fmz; FW(cp, IRHOE) += frhoE;
+        if (b->wallTau) { /* tmpStore / viscSubface%tau,%q (blockette.F90:5812-5838): kept for every face */
+            double* t = b->wallTau + (long)dir * 9 * d.N;
+            t[c] = tauxx; t[d.N + c] = tauyy; t[2 * d.N + c] = tauzz; t[3 * d.N + c] = tauxy; t[4 * d.N + c] = tauxz;
+            t[5 * d.N + c] = tauyz; t[6 * d.N + c] = q_x; t[7 * d.N + c] = q_y; t[8 * d.N + c] = q_z;
+        }
     }
 }
 void orc_viscous_flux(const OrcBlock* b, const AdfbParams* prm, double rFil) {
     Dims d = dims_of(b);
-    viscous_dir(b, prm, d, b->sk, b->porK, d.sK, d.sI, d.sJ, 2, 2, 1, rFil);
-    viscous_dir(b, prm, d, b->sj, b->porJ, d.sJ, d.sI, d.sK, 2, 1, 2, rFil);
-    viscous_dir(b, prm, d, b->si, b->porI, d.sI, d.sJ, d.sK, 1, 2, 2, rFil);
+    viscous_dir(b, prm, d, b->sk, b->porK, d.sK, d.sI, d.sJ, 2, 2, 1, rFil, 2);
+    viscous_dir(b, prm, d, b->sj, b->porJ, d.sJ, d.sI, d.sK, 2, 1, 2, rFil, 1);
+    viscous_dir(b, prm, d, b->si, b->porI, d.sI, d.sJ, d.sK, 1, 2, 2, rFil, 0);
 }
 
 /* ------------------------------------------------------------------------ */

@@ -53,6 +53,8 @@ typedef struct OrcBlock {
     double *wn, *pn;        /* 5 comps / 1 */
     double *scratch;        /* 10 comps: DADI work, SA qq etc. */
     double *shock;          /* frozen shock sensor (referenceShockSensor) */
+    double *wallTau;        /* [dir 0..2][tauxx,yy,zz,xy,xz,yz,qx,qy,qz][box]: viscous stress / heat flux of
+                               every face (viscSubface%tau, %q are its boundary planes); NULL = not stored */
 } OrcBlock;
 
 #ifdef __cplusplus
@@ -90,6 +92,10 @@ void orc_dadi_step(const OrcBlock* b, const AdfbParams* prm, int nSub, const Adf
 void orc_diss_matrix(const OrcBlock* b, const AdfbParams* prm, double rFil);
 void orc_upwind_flux(const OrcBlock* b, const AdfbParams* prm, double rFil);
 void orc_reference_shock_sensor(const OrcBlock* b, const AdfbParams* prm);
+/* wallIntegrationFace (src/solver/surfaceIntegrations.F90:406-881), force and moment part: out = Fp(3), Fv(3),
+   Mp(3), Mv(3) summed over the wall subfaces (viscous walls: pressure + viscous, Euler walls: pressure) */
+void orc_wall_forces(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf, const double refPoint[3],
+                     double pRef, double out[12]);
 void orc_diss_scalar_approx(const OrcBlock* b, const AdfbParams* prm);
 void orc_diss_matrix_approx(const OrcBlock* b, const AdfbParams* prm, double rFil);
 void orc_viscous_flux_approx(const OrcBlock* b, const AdfbParams* prm, double rFil);

@@ -611,3 +611,67 @@ void orc_dadi_step(const OrcBlock* b, const AdfbParams* prm, int nSub, const Adf
     orc_eddy_viscosity(b, prm, 0);
     orc_apply_flow_bc(b, prm, nSub, sf, 1);
 }
+
+/* ------------------------------------------------------------------------ */
+/* wallIntegrationFace, src/solver/surfaceIntegrations.F90:406-881: pressure and viscous force / moment sums of
+   the wall subfaces.  BCPointers planes (setBCPointers with spatialPointers): pp2 / pp1 = first interior / first
+   halo pressure, ssi = face normal of the wall face, xx = its node coordinates, fact = -1 on min faces.
+   Owned face cells only (inBeg+1:inEnd): 2..l of the two in-plane directions. */
+void orc_wall_forces(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sfs, const double refPoint[3],
+                     double pRef, double out[12]) {
+    Dims d = dims_of(b);
+    for (int q = 0; q < 12; q++) out[q] = zero;
+    for (int n = 0; n < nSub; n++) {
+        const AdfbSubface* sf = &sfs[n];
+        int viscWall = sf->bcType == ADFB_BC_NSWALL_ADIABATIC || sf->bcType == ADFB_BC_NSWALL_ISOTHERMAL;
+        if (!viscWall && sf->bcType != ADFB_BC_EULERWALL) continue;
+        Face f = face_of(d, sf->faceId);
+        int dir = (sf->faceId - 1) / 2, isMin = (sf->faceId % 2) == 1;
+        double fact = isMin ? -one : one;
+        const double* s = dir == 0 ? b->si : (dir == 1 ? b->sj : b->sk);
+        long sd = dir == 0 ? d.sI : (dir == 1 ? d.sJ : d.sK);
+        int la = (f.sa == d.sI) ? d.il : (f.sa == d.sJ ? d.jl : d.kl);
+        int lb = (f.sb == d.sJ) ? d.jl : d.kl;
+        int a0 = sf->icBeg < 2 ? 2 : sf->icBeg, a1 = sf->icEnd > la ? la : sf->icEnd;
+        int b0 = sf->jcBeg < 2 ? 2 : sf->jcBeg, b1 = sf->jcEnd > lb ? lb : sf->jcEnd;
+        double Fp[3] = {0, 0, 0}, Fv[3] = {0, 0, 0}, Mp[3] = {0, 0, 0}, Mv[3] = {0, 0, 0};
+        for (int jb_ = b0; jb_ <= b1; jb_++) for (int ia = a0; ia <= a1; ia++) {
+            long q = ia * f.sa + jb_ * f.sb;
+            long c1 = f.off[1] + q, c2 = f.off[2] + q;
+            long cf = isMin ? c1 : c2;   /* face index: face between halo and interior cell */
+            (void)sd;
+            double pm1 = fact * (half * (b->p[c2] + b->p[c1]) - prm->pInf) * pRef;
+            /* face centre: the four nodes of the face; node (ia, jb) is the upper one, the lower ones are -sa, -sb */
+            double xc[3];
+            for (int m = 0; m < 3; m++)
+                xc[m] = fourth * (X(cf - f.sa - f.sb, m) + X(cf - f.sb, m) + X(cf - f.sa, m) + X(cf, m));
+            double blk = dmax((double)b->iblank[c2], zero);
+            double fx = pm1 * s[cf], fy = pm1 * s[d.N + cf], fz = pm1 * s[2 * d.N + cf];
+            double rx = xc[0] - refPoint[0], ry = xc[1] - refPoint[1], rz = xc[2] - refPoint[2];
+            Fp[0] += fx * blk; Fp[1] += fy * blk; Fp[2] += fz * blk;
+            Mp[0] += (ry * fz - rz * fy) * blk; Mp[1] += (rz * fx - rx * fz) * blk; Mp[2] += (rx * fy - ry * fx) * blk;
+        }
+        if (viscWall && b->wallTau) {
+            const double* t = b->wallTau + (long)dir * 9 * d.N;
+            for (int jb_ = b0; jb_ <= b1; jb_++) for (int ia = a0; ia <= a1; ia++) {
+                long q = ia * f.sa + jb_ * f.sb;
+                long c1 = f.off[1] + q, c2 = f.off[2] + q;
+                long cf = isMin ? c1 : c2;
+                double blk = dmax((double)b->iblank[c2], zero);
+                double txx = t[cf], tyy = t[d.N + cf], tzz = t[2 * d.N + cf], txy = t[3 * d.N + cf], txz = t[4 * d.N + cf],
+                       tyz = t[5 * d.N + cf];
+                double s1 = s[cf], s2 = s[d.N + cf], s3 = s[2 * d.N + cf];
+                double fx = -fact * (txx * s1 + txy * s2 + txz * s3) * pRef;
+                double fy = -fact * (txy * s1 + tyy * s2 + tyz * s3) * pRef;
+                double fz = -fact * (txz * s1 + tyz * s2 + tzz * s3) * pRef;
+                double xc[3];
+                for (int m = 0; m < 3; m++)
+                    xc[m] = fourth * (X(cf - f.sa - f.sb, m) + X(cf - f.sb, m) + X(cf - f.sa, m) + X(cf, m));
+                double rx = xc[0] - refPoint[0], ry = xc[1] - refPoint[1], rz = xc[2] - refPoint[2];
+                Fv[0] += fx * blk; Fv[1] += fy * blk; Fv[2] += fz * blk;
+                Mv[0] += (ry * fz - rz * fy) * blk; Mv[1] += (rz * fx - rx * fz) * blk; Mv[2] += (rx * fy - ry * fx) * blk;
+            }
+        }
+        for (int m = 0; m < 3; m++) { out[m] += Fp[m]; out[3 + m] += Fv[m]; out[6 + m] += Mp[m]; out[9 + m] += Mv[m]; }
+    }
+}

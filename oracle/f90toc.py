@@ -24,7 +24,7 @@ harness fills from AdfbParams.
 import re
 import sys
 
-INTRINSIC_REAL = {"sqrt": "sqrt", "exp": "exp", "log10": "log10", "log": "log"}
+INTRINSIC_REAL = {"sqrt": "sqrt", "exp": "exp", "log10": "log10", "log": "log", "cos": "cos", "sin": "sin"}
 
 
 # ----------------------------------------------------------------------------- lexing
@@ -409,7 +409,7 @@ class Translator:
                     return arr.ctype
                 if n in ("max", "min", "abs", "sign", "dim", "mod", "mydim"):
                     return "int" if all(self.etype(a, sc) == "int" for a in e[2]) else "double"
-                if n in ("real", "sqrt", "exp", "log10", "log"):
+                if n in ("real", "sqrt", "exp", "log10", "log", "cos", "sin"):
                     return "double"
                 if n in ("int", "present", "associated") or n in self.env.int_funcs:
                     return "int"

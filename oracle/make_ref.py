@@ -45,9 +45,14 @@ PATCHES = [
     # ALE (deforming-mesh unsteady) hooks of applyAllBC: steady path, both return at once in the reference
     (r"^call interplevelalebc_block$", "continue"),
     (r"^call recoverlevelalebc_block$", "continue"),
+    # wallIntegrationFace: per-face output arrays of BCData (Fp, Fv, area: post-processing only) are not kept
+    (r"^bcdata\(mm\)%(fp|fv|area)\b.*=.*$", "continue"),
+    (r"^bcdata\(mm\)%fv = zero$", "continue"),
     # BCData(nn)%comp(...) -> accessor functions over the harness' subface table (oracle/ref_env.h)
     (r"bcdata\((\w+)\)%(\w+)\(", r"bcd_\2(\1, "),
     (r"bcdata\((\w+)\)%(\w+)", r"bcd_\2(\1)"),
+    # viscSubface(mm)%tau(i,j,l) (read side, surface integration) -> accessor over the harness' wall-stress table
+    (r"viscsubface\((\w+)\)%(\w+)\(", r"vsf_\2(\1, "),
     # module-wide `use X` without only-list inside routines: names resolve through ref_env.h
 ]
 
@@ -64,6 +69,7 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  bp_nx bp_ny bp_nz bp_il bp_jl bp_kl bp_ie bp_je bp_ke bp_ib bp_jb bp_kb bp_addgridvelocities
  bp_righthanded bp_sectionid bp_blockismoving bp_nbkglobal bp_nbocos bp_nviscbocos
  viscwallbctreatment eulerwallbctreatment outflowtreatment wallfunctions
+ spectralsol computesepsensorks computecavitation cavexponent
  symm symmpolar nswalladiabatic nswallisothermal farfield eulerwall extrap supersonicinflow supersonicoutflow
  subsonicinflow subsonicoutflow massbleedoutflow imin imax jmin jmax kmin kmax
  constantpressure linextrapolpressure quadextrapolpressure normalmomentum""".split()
@@ -128,6 +134,12 @@ def env_arrays():
     arrs["bp_bctype"] = A("bp_bctype", "int", [("1", "64")])
     arrs["bp_bcfaceid"] = A("bp_bcfaceid", "int", [("1", "64")])
     arrs["winf"] = A("winf", "double", [("1", "10")])
+    # inputPhysics / inputCostFunctions data of the surface integration
+    arrs["veldirfreestream"] = A("veldirfreestream", "double", [("1", "3")])
+    arrs["pointref"] = A("pointref", "double", [("1", "3")])
+    arrs["momentaxis"] = A("momentaxis", "double", [("1", "3"), ("1", "2")])
+    arrs["cpmin_family"] = A("cpmin_family", "double", [("1", "4")])
+    arrs["sepsenmaxfamily"] = A("sepsenmaxfamily", "double", [("1", "4")])
     arrs["turbresscale"] = A("turbresscale", "double", [("1", "4")])
     arrs["etark"] = A("etark", "double", [("1", "6")])
     arrs["cdisrk"] = A("cdisrk", "double", [("1", "6")])
@@ -160,6 +172,7 @@ UNITS = [
                                               "computeetot", "extrapolate2ndhalo"], ()),
     ("turbulence/turbUtils.F90", "turbutils_", ["computeeddyviscosity", "saeddyviscosity", "turbadvection"], ()),
     ("adjoint/adjointExtra.F90", "adjointextra_", ["volume_block", "metric_block"], ()),
+    ("solver/surfaceIntegrations.F90", "surfaceintegrations_", ["wallintegrationface", "ksaggregationfunction"], ()),
     ("turbulence/turbBCRoutines.F90", "turbbcroutines_",
      ["applyallturbbcthisblock", "bceddynowall", "bceddywall", "bcturbfarfield", "bcturbinflow", "bcturbinterface",
       "bcturboutflow", "bcturbsymm", "bcturbtreatment", "bcturbwall", "turb2ndhalo"], ("USE_TAPENADE",)),
@@ -170,7 +183,7 @@ UNITS = [
 RENAME_MODULES = {"blockpointers": "bp_", "flowutils": "flowutils_", "turbutils": "turbutils_",
                   "residuals": "residuals_", "smoothers": "smoothers_", "sa": "sa_",
                   "bcpointers": "bcpointers_", "bcroutines": "bcroutines_",
-                  "turbbcroutines": "turbbcroutines_"}
+                  "turbbcroutines": "turbbcroutines_", "surfaceintegrations": "surfaceintegrations_"}
 
 
 def main():
@@ -179,7 +192,7 @@ def main():
         print("make_ref: %s/src not found -- reference not present, nothing generated" % ref)
         return 0
     env = f90toc.Env(ENV_INTS, env_arrays(), ["getcorrectfork", "bcd_icbeg", "bcd_icend", "bcd_jcbeg", "bcd_jcend",
-                                              "bcd_inbeg", "bcd_inend", "bcd_jnbeg", "bcd_jnend"], dict(ENV_SUBS))
+                                              "bcd_inbeg", "bcd_inend", "bcd_jnbeg", "bcd_jnend", "bcd_iblank"], dict(ENV_SUBS))
     outdir = os.path.join(HERE, "_ref")
     os.makedirs(outdir, exist_ok=True)
     tr = None

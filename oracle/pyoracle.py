@@ -33,7 +33,7 @@ class OrcBlock(C.Structure):
         + [(n, C.c_void_p) for n in (
             "w", "p", "rlv", "rev", "x", "si", "sj", "sk", "vol", "volRef", "d2Wall",
             "porI", "porJ", "porK", "iblank", "dw", "fw", "ss", "dss",
-            "aa", "radI", "radJ", "radK", "dtl", "grad", "wn", "pn", "scratch", "shock")]
+            "aa", "radI", "radJ", "radK", "dtl", "grad", "wn", "pn", "scratch", "shock", "wallTau")]
     )
 
 
@@ -152,6 +152,14 @@ class Oracle:
     def sa_block(self):
         n, arr = self._subfaces()
         self.L.orc_sa_block(_p(self.ob), _p(self.prm), C.c_int(n), arr)
+
+    def wall_forces(self, ref_point=(0.0, 0.0, 0.0), p_ref=1.0):
+        """Fp, Fv, Mp, Mv (each 3) of the wall subfaces; needs a residual evaluation first (stores wallTau)"""
+        n, arr = self._subfaces()
+        rp = (C.c_double * 3)(*ref_point)
+        out = (C.c_double * 12)()
+        self.L.orc_wall_forces(_p(self.ob), _p(self.prm), C.c_int(n), arr, rp, C.c_double(p_ref), out)
+        return np.array(list(out)).reshape(4, 3)
 
     def reference_shock_sensor(self):
         self.L.orc_reference_shock_sensor(_p(self.ob), _p(self.prm))

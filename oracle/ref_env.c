@@ -46,6 +46,12 @@ int *bp_globalcell;
 double *bp_bvti1, *bp_bvti2, *bp_bvtj1, *bp_bvtj2, *bp_bvtk1, *bp_bvtk2;
 RefSubface bcd[64];
 
+int spectralsol = 1, computesepsensorks = 0, computecavitation = 0, cavexponent = 0;
+double pref = 1.0, lref = 1.0, machcoef = 1.0, cpmin_rho = 1.0, cavitationnumber = 1.0, cavsensorsharpness = 10.0, cavsensoroffset = 0.0;
+double sepsensorsharpness = 10.0, sepsensoroffset = 0.0, sepsensorkssharpness = 10.0, sepsensorksphi = 90.0, sepsensorksoffset = 0.0,
+       sepsenmaxrho = 1.0;
+double veldirfreestream[3] = {1.0, 0.0, 0.0}, pointref[3], momentaxis[6] = {0, 0, 0, 1, 0, 0}, cpmin_family[4], sepsenmaxfamily[4];
+
 /* Driver-level procedures that are NOT part of the translated set.  One block, pointers bound by
    the harness; halo exchange (no neighbours) is a no-op. */
 void setpointers(int* nn, int* level, int* sps) { (void)nn; (void)level; (void)sps; }

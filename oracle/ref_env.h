@@ -69,6 +69,9 @@ extern double *bp_bvti1, *bp_bvti2, *bp_bvtj1, *bp_bvtj2, *bp_bvtk1, *bp_bvtk2;
 typedef struct {
     int icbeg, icend, jcbeg, jcend;
     double *norm, *rface, *uslip, *tns_wall;
+    int inbeg, inend, jnbeg, jnend; /* node range of the subface (owned face cells are inBeg+1:inEnd) */
+    int* iblank;                    /* BCData%iblank: iblank of the adjacent interior cell, (icBeg:icEnd, jcBeg:jcEnd) */
+    double* tau;                    /* viscSubface%tau(:,:,6), same layout */
 } RefSubface;
 extern RefSubface bcd[64];
 static inline int bcd_icbeg(int nn) { return bcd[nn - 1].icbeg; }
@@ -88,7 +91,20 @@ static inline double bcd_uslip(int nn, int i, int j, int l) { return bcd[nn - 1]
 static inline double bcd_rface(int nn, int i, int j) { return bcd[nn - 1].rface[bcd_off(nn, i, j)]; }
 /* turbulence inflow data: inflow BCs are outside section 8, never reached */
 static inline double bcd_turbinlet(int nn, int i, int j, int l) { (void)nn; (void)i; (void)j; (void)l; return 0.0; }
+static inline int bcd_inbeg(int nn) { return bcd[nn - 1].inbeg; }
+static inline int bcd_inend(int nn) { return bcd[nn - 1].inend; }
+static inline int bcd_jnbeg(int nn) { return bcd[nn - 1].jnbeg; }
+static inline int bcd_jnend(int nn) { return bcd[nn - 1].jnend; }
+static inline int bcd_iblank(int nn, int i, int j) { return bcd[nn - 1].iblank[bcd_off(nn, i, j)]; }
+static inline double bcd_cptarget(int nn, int i, int j) { (void)nn; (void)i; (void)j; return 0.0; } /* Cp-target cost function: unused */
+static inline double vsf_tau(int nn, int i, int j, int l) { return bcd[nn - 1].tau[bcd_off(nn, i, j) + (l - 1) * bcd_size(nn)]; }
 static inline double bcd_tns_wall(int nn, int i, int j) { return bcd[nn - 1].tns_wall[bcd_off(nn, i, j)]; }
+
+/* inputPhysics / inputCostFunctions / flowVarRefState data read by wallIntegrationFace */
+extern int spectralsol, computesepsensorks, computecavitation, cavexponent;
+extern double pref, lref, machcoef, cpmin_rho, cavitationnumber, cavsensorsharpness, cavsensoroffset;
+extern double sepsensorsharpness, sepsensoroffset, sepsensorkssharpness, sepsensorksphi, sepsensorksoffset, sepsenmaxrho;
+extern double veldirfreestream[3], pointref[3], momentaxis[6], cpmin_family[4], sepsenmaxfamily[4];
 
 /* driver-level procedures outside the translated set (no-op stubs, see ref_env.c) */
 void setpointers(int* nn, int* level, int* sps);

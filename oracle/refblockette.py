@@ -111,7 +111,9 @@ def ref_constants():
 
 class RefSubface(C.Structure):
     _fields_ = [("icbeg", C.c_int), ("icend", C.c_int), ("jcbeg", C.c_int), ("jcend", C.c_int),
-                ("norm", C.c_void_p), ("rface", C.c_void_p), ("uslip", C.c_void_p), ("tns_wall", C.c_void_p)]
+                ("norm", C.c_void_p), ("rface", C.c_void_p), ("uslip", C.c_void_p), ("tns_wall", C.c_void_p),
+                ("inbeg", C.c_int), ("inend", C.c_int), ("jnbeg", C.c_int), ("jnend", C.c_int),
+                ("iblank", C.c_void_p), ("tau", C.c_void_p)]
 
 
 # AdfbSubface.bcType (include/adflow_b200.h) -> name of the reference's BC constant
@@ -140,6 +142,28 @@ def bind_bcs(hb, prm):
             a = np.zeros((na, nb, ncomp), order="F") if a is None else np.asfortranarray(a, dtype=np.float64)
             keep.append(a)
             setattr(tab[q], field, a.ctypes.data)
+        # node range (owned face cells inBeg+1:inEnd), BCData%iblank and viscSubface%tau planes of the subface
+        d = hb.d
+        face = s_["faceId"]
+        la, lb = {1: (d.jl, d.kl), 2: (d.jl, d.kl), 3: (d.il, d.kl), 4: (d.il, d.kl), 5: (d.il, d.jl), 6: (d.il, d.jl)}[face]
+        tab[q].inbeg, tab[q].inend = max(s_["icBeg"], 2) - 1, min(s_["icEnd"], la)
+        tab[q].jnbeg, tab[q].jnend = max(s_["jcBeg"], 2) - 1, min(s_["jcEnd"], lb)
+        ra, rb = slice(s_["icBeg"], s_["icEnd"] + 1), slice(s_["jcBeg"], s_["jcEnd"] + 1)
+        inner = {1: 2, 2: d.il, 3: 2, 4: d.jl, 5: 2, 6: d.kl}[face]       # first interior cell plane
+        fplane = {1: 1, 2: d.il, 3: 1, 4: d.jl, 5: 1, 6: d.kl}[face]      # index of the boundary face
+        ax = (face - 1) // 2
+
+        def plane(arr, idx):
+            sl = [ra, rb]
+            sl.insert(ax, idx)
+            return arr[tuple(sl)]
+
+        ib_ = np.asfortranarray(plane(hb.iblank, inner).astype(np.int32))
+        keep.append(ib_)
+        tab[q].iblank = ib_.ctypes.data
+        tau = np.asfortranarray(plane(hb.wallTau, fplane)[..., 9 * ax:9 * ax + 6].astype(np.float64))
+        keep.append(tau)
+        tab[q].tau = tau.ctypes.data
     _seti("viscwallbctreatment", cst["constantpressure"] if prm.wallBCConstantPressure else cst["linextrapolpressure"])
     _seti("eulerwallbctreatment", cst["constantpressure"] if prm.reserved else cst["linextrapolpressure"])
     w = (C.c_double * 10).in_dll(lib(), "winf")
@@ -237,6 +261,31 @@ def again(routine, *int_args):
     """call another translated procedure on the block bound by the last call()/residual_core()"""
     getattr(lib(), routine)(*[C.byref(C.c_int(int(v))) for v in int_args])
     return _BOUND
+
+
+def wall_forces(hb, prm, ref_point=(0.0, 0.0, 0.0), p_ref=1.0):
+    """wallIntegrationFace (src/solver/surfaceIntegrations.F90:406-881) over every wall subface of hb, after
+    setBCPointers(mm, .true.); hb.wallTau must hold the stored wall stresses (viscSubface%tau).  Returns
+    Fp, Fv, Mp, Mv as a (4, 3) array (localValues(iFp:), (iFv:), (iMp:), (iMv:))."""
+    global _BOUND
+    cst = ref_constants()
+    set_params(prm, hb.nw)
+    _setd("pref", p_ref); _setd("lref", 1.0); _setd("machcoef", 1.0)
+    pr = (C.c_double * 3).in_dll(lib(), "pointref")
+    for q in range(3):
+        pr[q] = ref_point[q]
+    rb = RefBlock(hb, prm)
+    rb.bind()
+    rb.keep = bind_bcs(hb, prm)
+    _BOUND = rb
+    subs = sorted(hb.subfaces, key=lambda s_: 0 if s_["bcType"] in (2, 6) else 1)
+    local = (C.c_double * cst["nlocalvalues"])()
+    for mm, s_ in enumerate(subs, start=1):
+        if s_["bcType"] in (2, 4, 6):
+            lib().setbcpointers(C.byref(C.c_int(mm)), C.byref(C.c_int(1)))
+            lib().surfaceintegrations_wallintegrationface(local, C.byref(C.c_int(mm)))
+    v = np.array(list(local))
+    return np.stack([v[cst[k] - 1:cst[k] + 2] for k in ("ifp", "ifv", "imp", "imv")])
 
 
 def call_core(flags=FLAG_FLOW | FLAG_TURB):
