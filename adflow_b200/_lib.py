@@ -17,7 +17,7 @@ ABI_SYMBOLS = [
     "adfb_init", "adfb_finalize", "adfb_get_unique_id", "adfb_last_error", "adfb_device_count",
     "adfb_block_create", "adfb_block_destroy", "adfb_block_set_geometry", "adfb_block_set_bc",
     "adfb_set_params", "adfb_upload_state", "adfb_download_state", "adfb_upload_visc",
-    "adfb_download_residual", "adfb_download_intermed", "adfb_residual", "adfb_norms", "adfb_synchronize",
+    "adfb_download_residual", "adfb_download_intermed", "adfb_residual", "adfb_norms", "adfb_synchronize", "adfb_forces",
     "adfb_get_states", "adfb_set_states", "adfb_get_res", "adfb_state_size",
     "adfb_comm_set_pattern", "adfb_halo_exchange",
     "adfb_reference_shock_sensor", "adfb_form_function", "adfb_mffd_set_base", "adfb_mffd_apply", "adfb_mffd_last_h",
@@ -68,6 +68,7 @@ def load():
     L.adfb_download_array.argtypes = [ci, C.c_char_p, vp]
     L.adfb_residual.argtypes = [ci, cu]
     L.adfb_norms.argtypes = [C.POINTER(C.c_double)]
+    L.adfb_forces.argtypes = [ci, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]
     for fn in (L.adfb_get_states, L.adfb_set_states, L.adfb_get_res):
         fn.argtypes = [vp, C.c_longlong]
     L.adfb_state_size.restype = C.c_longlong

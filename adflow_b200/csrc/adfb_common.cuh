@@ -52,6 +52,10 @@ struct BlockDev {
     double *vn;                         // 12: cell-centre unit vector + 1/length per face direction
     double *flux;                       // 30: face fluxes (15 used in merged mode)
     double *shock;                      // frozen shock sensor (referenceShockSensor)
+    // viscSubface%tau / %q of the six block-boundary face planes (storeWallTensor): [dir][side][9][plane], plane
+    // stride wallP, in-plane index ia + (dir == 0 ? NJ : NI) * jb
+    double *wallTau;
+    long long wallP;
 };
 
 // single translation unit (adflow_b200.cu includes every *_kernels.cuh)

@@ -370,6 +370,11 @@ int adfb_block_create(int blk, int level, int nx, int ny, int nz, int nw, int ri
     rc |= dalloc(b, &v.wn, N * 5); rc |= dalloc(b, &v.pn, N); rc |= dalloc(b, &v.scratch, N * 10);
     rc |= dalloc(b, &v.ssum, N * 9); rc |= dalloc(b, &v.sv, N * 9); rc |= dalloc(b, &v.ovol, N);
     rc |= dalloc(b, &v.vn, N * 12); rc |= dalloc(b, &v.flux, N * 30); rc |= dalloc(b, &v.shock, N);
+    {
+        const long long pI = (long long)b.d.NJ * b.d.NK, pJ = (long long)b.d.NI * b.d.NK, pK = (long long)b.d.NI * b.d.NJ;
+        v.wallP = pI > pJ ? (pI > pK ? pI : pK) : (pJ > pK ? pJ : pK);
+        rc |= dalloc(b, &v.wallTau, (size_t)(3 * 2 * 9) * v.wallP);
+    }
     if (rc) {
         for (void* q : b.allocs) cudaFree(q);
         b.allocs.clear();
@@ -1045,6 +1050,32 @@ int adfb_norms(double out[2]) {
         CK(cudaStreamSynchronize(g.stream));
         out[0] = g.hRed[0]; out[1] = g.hRed[1];
     }
+    return 0;
+}
+
+// getForces / wallIntegrationFace: Fp(3), Fv(3), Mp(3), Mv(3) over the wall subfaces of all local blocks of
+// `level`, all-reduced.  The viscous part uses the wall stresses stored by the last adfb_residual call that had
+// ADFB_RES_STORE_WALL set.
+int adfb_forces(int level, const double refPoint[3], double pRef, double out[12]) {
+    NEED_INIT();
+    if (!refPoint || !out) return fail("adfb_forces: null");
+    if (g.dRedN < 16) {
+        if (g.dRed) cudaFree(g.dRed);
+        CK(cudaMalloc((void**)&g.dRed, 2050 * sizeof(double)));
+        g.dRedN = 2050;
+    }
+    CK(cudaMemsetAsync(g.dRed, 0, 12 * sizeof(double), g.stream));
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != level) continue;
+        if (launch_wall_forces(b.d, b.dev, b.subfaces, refPoint, pRef, g.dRed, g.stream)) return fail("force kernel failed");
+    }
+    if (g.nranks > 1) {
+        const int rc = g.nccl.AllReduce(g.dRed, g.dRed, 12, kNcclDouble, kNcclSum, g.comm, g.stream);
+        if (rc != 0) return fail("ncclAllReduce: %s", g.nccl.GetErrorString(rc));
+    }
+    CK(cudaMemcpyAsync(g.hRed, g.dRed, 12 * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    for (int q = 0; q < 12; q++) out[q] = g.hRed[q];
     return 0;
 }
 

@@ -287,7 +287,7 @@ template <bool VISCOUS, int DISC, int APPROX>
 __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int sd, int t1, int t2, int dir,
                                           const double* __restrict__ s, int8_t por, const double* __restrict__ rad,
                                           const double* __restrict__ dss, const CellState& m, double rFil, int doDiss,
-                                          int doVisc, double fc[5], double fd[5]) {
+                                          int doVisc, double fc[5], double fd[5], double* tq = nullptr) {
     const int cp = c + sd;
     const CellState q = load_cell(b, N, cp);
     const double s1 = s[c], s2 = s[N + c], s3 = s[2 * N + c];
@@ -554,13 +554,17 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
         fd[3] += tauxz * s1 + tauyz * s2 + tauzz * s3;
         fd[4] += (ubar * tauxx + vbar * tauxy + wbar * tauxz) * s1 + (ubar * tauxy + vbar * tauyy + wbar * tauyz) * s2 +
                  (ubar * tauxz + vbar * tauyz + wbar * tauzz) * s3 - q_x * s1 - q_y * s2 - q_z * s3;
+        if (tq) {  // storeWallTensor: viscSubface%tau, %q of a boundary face (blockette.F90:5812-5838)
+            tq[0] = tauxx; tq[1] = tauyy; tq[2] = tauzz; tq[3] = tauxy; tq[4] = tauxz; tq[5] = tauyz;
+            tq[6] = q_x; tq[7] = q_y; tq[8] = q_z;
+        }
     }
 }
 
 // k_faces: plus faces of cell (i,j,k), i 1:il, j 1:jl, k 1:kl.  MERGED: one array G = fc - fd per
 // face (net outflow of the low cell) -> flux[dir*5 + l]; otherwise fc -> flux[dir*10 + l],
 // fd -> flux[dir*10 + 5 + l] (smoother path: fw persists between RK stages).
-template <bool VISCOUS, bool MERGED, int DISC, int APPROX>
+template <bool VISCOUS, bool MERGED, int DISC, int APPROX, bool STOREWALL = false>
 __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDev b, double rFil, int doVisc, int doDiss) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
@@ -570,9 +574,18 @@ __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDe
     const int c = i + sJ * j + sK * k;
     const CellState m = load_cell(b, N, c);
     double fc[5], fd[5];
+    double tq[9];
+    double* const tqp = STOREWALL ? tq : nullptr;
+    // boundary-plane store of the wall stress tensor: plane (dir, side), in-plane index pi
+    auto store_wall = [&](int dir, int side, long long pi) {
+        double* dst = b.wallTau + ((long long)(dir * 2 + side) * 9) * b.wallP + pi;
+#pragma unroll
+        for (int l = 0; l < 9; l++) dst[l * b.wallP] = tq[l];
+    };
     const bool oi = i >= 2, oj = j >= 2, ok = k >= 2;
     if (oj && ok) {
-        face_flux<VISCOUS, DISC, APPROX>(b, N, c, 1, sJ, sK, 0, b.si, b.porI[c], b.radI, b.dss, m, rFil, doDiss, doVisc, fc, fd);
+        face_flux<VISCOUS, DISC, APPROX>(b, N, c, 1, sJ, sK, 0, b.si, b.porI[c], b.radI, b.dss, m, rFil, doDiss, doVisc, fc, fd, tqp);
+        if (STOREWALL && (i == 1 || i == d.il)) store_wall(0, i == 1 ? 0 : 1, j + (long long)d.NJ * k);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
             if (MERGED) b.flux[l * N + c] = fc[l] - fd[l];
@@ -580,7 +593,8 @@ __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDe
         }
     }
     if (oi && ok) {
-        face_flux<VISCOUS, DISC, APPROX>(b, N, c, sJ, 1, sK, 1, b.sj, b.porJ[c], b.radJ, b.dss + N, m, rFil, doDiss, doVisc, fc, fd);
+        face_flux<VISCOUS, DISC, APPROX>(b, N, c, sJ, 1, sK, 1, b.sj, b.porJ[c], b.radJ, b.dss + N, m, rFil, doDiss, doVisc, fc, fd, tqp);
+        if (STOREWALL && (j == 1 || j == d.jl)) store_wall(1, j == 1 ? 0 : 1, i + (long long)d.NI * k);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
             if (MERGED) b.flux[(5 + l) * N + c] = fc[l] - fd[l];
@@ -588,7 +602,8 @@ __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDe
         }
     }
     if (oi && oj) {
-        face_flux<VISCOUS, DISC, APPROX>(b, N, c, sK, 1, sJ, 2, b.sk, b.porK[c], b.radK, b.dss + 2 * N, m, rFil, doDiss, doVisc, fc, fd);
+        face_flux<VISCOUS, DISC, APPROX>(b, N, c, sK, 1, sJ, 2, b.sk, b.porK[c], b.radK, b.dss + 2 * N, m, rFil, doDiss, doVisc, fc, fd, tqp);
+        if (STOREWALL && (k == 1 || k == d.kl)) store_wall(2, k == 1 ? 0 : 1, i + (long long)d.NI * j);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
             if (MERGED) b.flux[(10 + l) * N + c] = fc[l] - fd[l];
@@ -870,7 +885,12 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         else ADFB_LAUNCH_FACES(V, M, ADFB_UPWIND, A);                       \
     } while (0)
         const int approx = dissApprox | (viscApprox << 1);
-        if (approx == 0) {
+        const bool storeWall = (flags & ADFB_RES_STORE_WALL) && viscous && doVisc && merged && approx == 0;
+        if (storeWall) {  // exact viscous flux + viscSubface%tau/%q planes for the force integration
+            if (prm.spaceDiscr == ADFB_DISS_SCALAR) k_faces<true, true, ADFB_DISS_SCALAR, 0, true><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
+            else if (prm.spaceDiscr == ADFB_DISS_MATRIX) k_faces<true, true, ADFB_DISS_MATRIX, 0, true><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
+            else k_faces<true, true, ADFB_UPWIND, 0, true><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
+        } else if (approx == 0) {
             if (viscous) { if (merged) ADFB_FACES_DISC(true, true, 0); else ADFB_FACES_DISC(true, false, 0); }
             else { if (merged) ADFB_FACES_DISC(false, true, 0); else ADFB_FACES_DISC(false, false, 0); }
         } else if (viscous) {

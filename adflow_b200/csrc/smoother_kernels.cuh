@@ -392,6 +392,65 @@ __global__ void __launch_bounds__(64) k_resavg_sweep(Dims d, BlockDev b, int dir
     }
 }
 
+// wallIntegrationFace, force and moment part (src/solver/surfaceIntegrations.F90:406-881): one CTA per wall
+// subface; every thread sums its face cells in index order, then a fixed-order tree reduction, so the result
+// is run-to-run reproducible.  acc = Fp(3), Fv(3), Mp(3), Mv(3).
+__global__ void __launch_bounds__(256) k_wall_forces(Dims d, BlockDev b, FaceDev f, int dir, int isMin, int la, int lb, int viscWall,
+                                                     double r0, double r1, double r2, double pRef, double* acc) {
+    __shared__ double sh[12][256];
+    const long long N = d.N;
+    const double fact = isMin ? -1.0 : 1.0;
+    const double* s = dir == 0 ? b.si : (dir == 1 ? b.sj : b.sk);
+    const int a0 = f.icBeg < 2 ? 2 : f.icBeg, a1 = f.icEnd > la ? la : f.icEnd;
+    const int b0 = f.jcBeg < 2 ? 2 : f.jcBeg, b1 = f.jcEnd > lb ? lb : f.jcEnd;
+    const int na = a1 - a0 + 1, nb = b1 - b0 + 1;
+    const long long pstride = dir == 0 ? d.NJ : d.NI;
+    const double* tau = b.wallTau + ((long long)(dir * 2 + (isMin ? 0 : 1)) * 9) * b.wallP;
+    double v[12];
+#pragma unroll
+    for (int q = 0; q < 12; q++) v[q] = 0.0;
+    for (int idx = threadIdx.x; idx < na * nb; idx += blockDim.x) {
+        const int ia = a0 + idx % na, jb = b0 + idx / na;
+        const long long q = ia * f.sa + jb * f.sb;
+        const long long c1 = f.off[1] + q, c2 = f.off[2] + q;
+        const long long cf = isMin ? c1 : c2;
+        const double blk = dmax_((double)b.iblank[c2], 0.0);
+        double xc[3];
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const double* xm = b.x + m * N;
+            xc[m] = 0.25 * (xm[cf - f.sa - f.sb] + xm[cf - f.sb] + xm[cf - f.sa] + xm[cf]);
+        }
+        const double rx = xc[0] - r0, ry = xc[1] - r1, rz = xc[2] - r2;
+        const double s1 = s[cf], s2 = s[N + cf], s3 = s[2 * N + cf];
+        const double pm1 = fact * (0.5 * (b.p[c2] + b.p[c1]) - c_prm.pInf) * pRef;
+        double fx = pm1 * s1, fy = pm1 * s2, fz = pm1 * s3;
+        v[0] += fx * blk; v[1] += fy * blk; v[2] += fz * blk;
+        v[6] += (ry * fz - rz * fy) * blk; v[7] += (rz * fx - rx * fz) * blk; v[8] += (rx * fy - ry * fx) * blk;
+        if (viscWall) {
+            const long long pi = ia + pstride * jb;
+            const double txx = tau[pi], tyy = tau[b.wallP + pi], tzz = tau[2 * b.wallP + pi], txy = tau[3 * b.wallP + pi],
+                         txz = tau[4 * b.wallP + pi], tyz = tau[5 * b.wallP + pi];
+            fx = -fact * (txx * s1 + txy * s2 + txz * s3) * pRef;
+            fy = -fact * (txy * s1 + tyy * s2 + tyz * s3) * pRef;
+            fz = -fact * (txz * s1 + tyz * s2 + tzz * s3) * pRef;
+            v[3] += fx * blk; v[4] += fy * blk; v[5] += fz * blk;
+            v[9] += (ry * fz - rz * fy) * blk; v[10] += (rz * fx - rx * fz) * blk; v[11] += (rx * fy - ry * fx) * blk;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 12; q++) sh[q][threadIdx.x] = v[q];
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+#pragma unroll
+            for (int q = 0; q < 12; q++) sh[q][threadIdx.x] += sh[q][threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 12) acc[threadIdx.x] += sh[threadIdx.x][0];
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -500,5 +559,21 @@ static int launch_dadi_update(const Dims& d, const BlockDev& b, const AdfbParams
     KT_BEGIN(K_RK, s);
     k_rk_update<<<g, tb, 0, s>>>(d, b, 0, 0.0, prm.equations == ADFB_RANS ? 6 : 5, 1);
     KT_END(K_RK, s);
+    return (int)cudaGetLastError();
+}
+
+// forces of all wall subfaces of one block, accumulated into acc[12] (device)
+static int launch_wall_forces(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, const double rp[3], double pRef,
+                              double* acc, cudaStream_t s) {
+    for (const AdfbSubface& sf : subs) {
+        const bool viscWall = sf.bcType == ADFB_BC_NSWALL_ADIABATIC || sf.bcType == ADFB_BC_NSWALL_ISOTHERMAL;
+        if (!viscWall && sf.bcType != ADFB_BC_EULERWALL) continue;
+        FaceDev f = make_face(d, sf);
+        const int dir = (sf.faceId - 1) / 2, isMin = (sf.faceId % 2) == 1;
+        const int la = dir == 0 ? d.jl : d.il, lb = dir == 2 ? d.jl : d.kl;
+        KT_BEGIN(K_MISC, s);
+        k_wall_forces<<<1, 256, 0, s>>>(d, b, f, dir, isMin, la, lb, viscWall ? 1 : 0, rp[0], rp[1], rp[2], pRef, acc);
+        KT_END(K_MISC, s);
+    }
     return (int)cudaGetLastError();
 }

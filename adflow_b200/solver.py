@@ -159,6 +159,30 @@ class ADFLOW_B200:
         check(self.L.adfb_norms(out), "adfb_norms")
         return np.array([out[0], out[1]])
 
+    def getForces(self, ref_point=(0.0, 0.0, 0.0), p_ref=1.0, level=1):
+        """Fp, Fv, Mp, Mv (rows) summed over the wall subfaces of all ranks -- wallIntegrationFace,
+        src/solver/surfaceIntegrations.F90:406-881.  Call residual(flags | RES_STORE_WALL) first (as the
+        reference's getSolution does through blocketteRes(useStoreWall=.true.))."""
+        rp = (C.c_double * 3)(*ref_point)
+        out = (C.c_double * 12)()
+        check(self.L.adfb_forces(level, rp, float(p_ref), out), "adfb_forces")
+        return np.array(list(out)).reshape(4, 3)
+
+    def evalFunctions(self, lift_dir, drag_dir, mach_coef, surface_ref=1.0, length_ref=1.0, l_ref=1.0, p_ref=1.0,
+                      ref_point=(0.0, 0.0, 0.0)):
+        """cl, cd, force and moment coefficients as getCostFunctions forms them
+        (src/solver/surfaceIntegrations.F90:43-63, 253-300): fact = 2/(gammaInf MachCoef^2 surfaceRef LRef^2 pRef)."""
+        F = self.getForces(ref_point, p_ref)
+        fact = 2.0 / (self.prm.gammaInf * mach_coef * mach_coef * surface_ref * l_ref * l_ref * p_ref)
+        force, moment = F[0] + F[1], F[2] + F[3]
+        cforce = fact * force
+        cmoment = (fact / (length_ref * l_ref)) * moment
+        return {"fx": force[0], "fy": force[1], "fz": force[2], "cfx": cforce[0], "cfy": cforce[1], "cfz": cforce[2],
+                "cl": float(np.dot(cforce, lift_dir)), "cd": float(np.dot(cforce, drag_dir)),
+                "clp": float(np.dot(fact * F[0], lift_dir)), "clv": float(np.dot(fact * F[1], lift_dir)),
+                "cdp": float(np.dot(fact * F[0], drag_dir)), "cdv": float(np.dot(fact * F[1], drag_dir)),
+                "cmx": cmoment[0], "cmy": cmoment[1], "cmz": cmoment[2]}
+
     def synchronize(self):
         check(self.L.adfb_synchronize(), "adfb_synchronize")
 

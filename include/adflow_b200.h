@@ -189,6 +189,11 @@ int adfb_residual(int level, unsigned flags);
    blocks, all-reduced (getCurrentResidual, NKSolvers.F90:335-370). out[0]=rho, out[1]=total */
 int adfb_norms(double out[2]);
 int adfb_synchronize(void);
+/* wallIntegrationFace / getForces (src/solver/surfaceIntegrations.F90:406-881, src/warping/getForces.F90):
+   out = Fp(3), Fv(3), Mp(3), Mv(3) summed over the wall subfaces (viscous walls: pressure + viscous, Euler walls:
+   pressure) of all blocks of `level` on all ranks; moments about refPoint; forces scaled by pRef like the
+   reference.  The viscous part needs a preceding adfb_residual(level, flags | ADFB_RES_STORE_WALL). */
+int adfb_forces(int level, const double refPoint[3], double pRef, double out[12]);
 
 /* referenceShockSensor (src/adjoint/adjointUtils.F90:1900-1950): freeze the shock sensor
    field (p for Euler, p/rho**gamma otherwise) used by the ADFB_RES_DISS_APPROX variants */
