@@ -107,5 +107,16 @@ struct KTimer {
     void reset() { collect(); for (int i = 0; i < K_NUM; i++) { ms[i] = 0; count[i] = 0; } }
 };
 static KTimer g_kt;
+
+// lanes per line for the partitioned Thomas kernels (tridiag_part.cuh): 8 lanes x <= 16 rows, 16 lanes x <= 16
+// rows, or 0 = one thread per line (short or very long lines).  ADFB_PART=0 forces the serial kernels.
+static inline int adfb_part_lanes(int nl) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("ADFB_PART"); enabled = e ? atoi(e) : 1; }
+    if (!enabled) return 0;
+    if (nl >= 16 && nl <= 128) return 8;
+    if (nl > 128 && nl <= 256) return 16;
+    return 0;
+}
 #define KT_BEGIN(id, stream) g_kt.begin(id, stream)
 #define KT_END(id, stream) g_kt.end(id, stream)

@@ -303,6 +303,12 @@ static int launch_dadi(const Dims& d, const BlockDev& b, const AdfbParams& prm, 
     const dim3 tc(32, 4, 1);
     const dim3 gc((d.nx + 31) / 32, (d.ny + 3) / 4, d.nz);
     const dim3 tb(32, 1, 1);
+    // (a partitioned, 8-lanes-per-line variant of this solve was measured slower here: with 5 systems per line the
+    // serial walks already fill the machine and the partition method does 2.5x the arithmetic; it pays for the
+    // single-system SA solve only, see sa_kernels.cuh)
+    auto thomas = [&](int sd, int nl, int s1, int n1, int s2, int n2) {
+        k_dadi_thomas<<<dim3((n1 + 31) / 32, n2, 5), tb, 0, s>>>(d, b, sd, nl, s1, n1, s2, n2);
+    };
     // j sweep
     KT_BEGIN(K_DADI, s);
     k_dadi_coef<0><<<gc, tc, 0, s>>>(d, b, sJ, prm.cfl);
@@ -311,7 +317,7 @@ static int launch_dadi(const Dims& d, const BlockDev& b, const AdfbParams& prm, 
     k_dadi_tri<<<gc, tc, 0, s>>>(d, b, sJ, 0);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
-    k_dadi_thomas<<<dim3((d.nx + 31) / 32, d.nz, 5), tb, 0, s>>>(d, b, sJ, d.ny, 1, d.nx, sK, d.nz);
+    thomas(sJ, d.ny, 1, d.nx, sK, d.nz);
     KT_END(K_DADI, s);
     // i sweep
     KT_BEGIN(K_DADI, s);
@@ -321,7 +327,7 @@ static int launch_dadi(const Dims& d, const BlockDev& b, const AdfbParams& prm, 
     k_dadi_tri<<<gc, tc, 0, s>>>(d, b, 1, 1);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
-    k_dadi_thomas<<<dim3((d.ny + 31) / 32, d.nz, 5), tb, 0, s>>>(d, b, 1, d.nx, sJ, d.ny, sK, d.nz);
+    thomas(1, d.nx, sJ, d.ny, sK, d.nz);
     KT_END(K_DADI, s);
     // k sweep
     KT_BEGIN(K_DADI, s);
@@ -331,7 +337,7 @@ static int launch_dadi(const Dims& d, const BlockDev& b, const AdfbParams& prm, 
     k_dadi_tri<<<gc, tc, 0, s>>>(d, b, sK, 2);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
-    k_dadi_thomas<<<dim3((d.nx + 31) / 32, d.ny, 5), tb, 0, s>>>(d, b, sK, d.nz, 1, d.nx, sJ, d.ny);
+    thomas(sK, d.nz, 1, d.nx, sJ, d.ny);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
     k_dadi_post<<<gc, tc, 0, s>>>(d, b);

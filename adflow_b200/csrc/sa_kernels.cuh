@@ -12,6 +12,7 @@
 // scratch slots: 0 = dvt, 1 = qq, 2 = bmt, 3 = eliminated diagonal of the current sweep.
 #pragma once
 #include "adfb_common.cuh"
+#include "tridiag_part.cuh"
 #include "smoother_kernels.cuh"
 #include <math.h>
 
@@ -275,6 +276,46 @@ __global__ void __launch_bounds__(64) k_sa_thomas(Dims d, BlockDev b, int sd, in
     }
 }
 
+// the same sweep with every line spread over P lanes (tridiag_part.cuh); LS = 32 / P lines per warp
+template <int P, int M>
+__global__ void __launch_bounds__(32) k_sa_thomas_part(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2, int multiplyByQQ) {
+    typedef PartThomas<P, M> PT;
+    const int lane = threadIdx.x, p = lane / PT::LS, lw = lane % PT::LS;
+    int line = blockIdx.x * PT::LS + lw;
+    const bool valid = line < n1 * n2;
+    if (!valid) line = n1 * n2 - 1;  // every lane takes part in the shuffles; surplus lanes redo the last line
+    const int N = (int)d.N;
+    const int base = (line % n1 + 2) * s1 + (line / n1 + 2) * s2;
+    const double* __restrict__ bbA = b.flux;
+    const double* __restrict__ ddA = b.flux + N;
+    const double* __restrict__ ffA = b.flux + 2 * N;
+    const double* __restrict__ qq = b.scratch + N;
+    double* __restrict__ dvt = b.scratch;
+    int start, m;
+    PT::chunk(nl, p, start, m);
+    double ra[M], rb[M], rc[M], rd[M];
+#pragma unroll
+    for (int t = 0; t < M; t++) {
+        ra[t] = 0.0; rb[t] = 1.0; rc[t] = 0.0; rd[t] = 0.0;
+        if (t < m) {
+            const int c = base + (2 + start + t) * sd;
+            ra[t] = (start + t > 0) ? bbA[c] : 0.0;
+            rb[t] = qq[c];
+            rc[t] = (start + t < nl - 1) ? ddA[c] : 0.0;
+            rd[t] = ffA[c];
+        }
+    }
+    PT::solve(ra, rb, rc, rd, m, p, lw);
+    if (!valid) return;
+#pragma unroll
+    for (int t = 0; t < M; t++) {
+        if (t < m) {
+            const int c = base + (2 + start + t) * sd;
+            dvt[c] = multiplyByQQ ? rd[t] * qq[c] : rd[t];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_sa_update(Dims d, BlockDev b) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
@@ -320,7 +361,11 @@ static int launch_sa_block(const Dims& d, const BlockDev& b, const AdfbParams& p
         k_sa_coef<<<gc, tc, 0, s>>>(d, b, axis, sd);
         KT_END(K_SASOLVE, s);
         KT_BEGIN(K_SASOLVE, s);
-        k_sa_thomas<<<dim3((n1 + 31) / 32, n2), tl, 0, s>>>(d, b, sd, nl, s1, n1, s2, n2, mult);
+        const int part = adfb_part_lanes(nl);
+        if (part == 8 && nl <= 96) k_sa_thomas_part<8, 12><<<(n1 * n2 + 3) / 4, 32, 0, s>>>(d, b, sd, nl, s1, n1, s2, n2, mult);
+        else if (part == 8) k_sa_thomas_part<8, 16><<<(n1 * n2 + 3) / 4, 32, 0, s>>>(d, b, sd, nl, s1, n1, s2, n2, mult);
+        else if (part == 16) k_sa_thomas_part<16, 16><<<(n1 * n2 + 1) / 2, 32, 0, s>>>(d, b, sd, nl, s1, n1, s2, n2, mult);
+        else k_sa_thomas<<<dim3((n1 + 31) / 32, n2), tl, 0, s>>>(d, b, sd, nl, s1, n1, s2, n2, mult);
         KT_END(K_SASOLVE, s);
     };
     sweep(1, sJ, d.ny, 1, d.nx, sK, d.nz, 1);   // j lines

@@ -52,6 +52,9 @@ def test_oracle_dadi_smoother_reduces_residual():
     ({"equationType": "laminar NS"}, (9, 12, 8)),
     ({"resAveraging": "always", "CFL": 5.0}, (10, 9, 8)),
     (None, (1, 7, 6)),
+    (None, (20, 17, 16)),         # lines >= 16 cells: partitioned Thomas kernels (8 lanes per line)
+    ({"resAveraging": "always", "CFL": 5.0}, (33, 18, 40)),
+    ({"equationType": "Euler"}, (16, 35, 9)),   # mixed: i, j partitioned, k serial
 ])
 def test_dadi_step_matches_oracle(cuda_lib, options, shape):
     prm, hb0 = case(*shape, options)

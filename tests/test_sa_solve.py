@@ -44,6 +44,8 @@ def test_oracle_sa_residual_row_equals_blockette_row():
     (None, (9, 12, 7), 3),
     ({"turbulenceOrder": "second order"}, (10, 9, 8), 2),
     ({"turbulenceProduction": "vorticity", "useft2SA": False}, (8, 9, 10), 1),
+    (None, (20, 17, 16), 2),      # lines >= 16 cells: partitioned Thomas kernels (8 lanes per line)
+    (None, (33, 40, 18), 1),
 ])
 def test_sa_ddadi_matches_oracle(cuda_lib, options, shape, niter):
     prm, hb0 = case(*shape, options)

@@ -111,8 +111,9 @@ def test_rk_cycle_matches_oracle(cuda_lib, options):
         box_close(rlv[c1], ho.rlv[c1], 1e-11, "rlv")
 
 
-def test_residual_averaging_matches_oracle(cuda_lib):
-    prm, hb = case(18, 7, 9, {"CFL": 6.0, "resAveraging": "always", "nRKStages": 1})
+@pytest.mark.parametrize("shape", [(18, 7, 9), (20, 17, 16), (36, 19, 41)])
+def test_residual_averaging_matches_oracle(cuda_lib, shape):
+    prm, hb = case(*shape, {"CFL": 6.0, "resAveraging": "always", "nRKStages": 1})
     # one RK stage with averaging: compare dw after the stage (scaled + smoothed)
     ho = hb.copy()
     o = Oracle(ho, prm)
