@@ -67,11 +67,15 @@ struct Context {
         int *rBlk = nullptr, *rLocal = nullptr, *rCount = nullptr; long long *rOff = nullptr, *rCum = nullptr;
         int *iSrcBlk = nullptr, *iDstBlk = nullptr; long long *iSrcOff = nullptr, *iDstOff = nullptr;
         double *sendBuf = nullptr, *recvBuf = nullptr;
+        // overset pattern only: donor-block strides and the 8 interpolation weights per send / internal entry
+        bool interp = false;
+        long long *sSJ = nullptr, *sSK = nullptr, *iSJ = nullptr, *iSK = nullptr;
+        double *sW = nullptr, *iW = nullptr;
         CommVarTable* dTab = nullptr;   // unused (kept for layout); tables are cached per selection
         int tabBlocks = 0;
         std::map<int, CommVarTable*> tabs;  // key: start | end<<4 | commP<<8 | commV<<9
         std::vector<void*> allocs;
-    } pat;
+    } pat, ovPat;   // 1-to-1 (commPatternCell_2nd / internalCell_2nd) and overset (commPatternOverset / internalOverset)
     // CUDA graphs of whole entry points (launch-latency bound sequences of small kernels)
     std::map<unsigned long long, cudaGraphExec_t> graphs;
     std::map<unsigned long long, long long> graphLaunches;
@@ -291,6 +295,8 @@ int adfb_finalize(void) {
     drop_graphs();
     for (void* q : g.pat.allocs) cudaFree(q);
     g.pat = Context::Pattern();
+    for (void* q : g.ovPat.allocs) cudaFree(q);
+    g.ovPat = Context::Pattern();
     if (g.comm) { g.nccl.CommDestroy(g.comm); g.comm = nullptr; }
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
@@ -571,13 +577,14 @@ int adfb_get_res(double* res, long long n) { return vec_io(res, n, 2); }
 // ---------------------------------------------------------------------------
 // halo exchange
 }  // extern "C" (templates need C++ linkage)
+static Context::Pattern* g_upPat = nullptr;   // pattern that owns the uploads of the current set call
 template <typename T>
 static int pat_upload(T** dst, const std::vector<T>& src) {
     *dst = nullptr;
     if (src.empty()) return 0;
     void* q = nullptr;
     if (cudaMalloc(&q, src.size() * sizeof(T)) != cudaSuccess) return fail("comm pattern: cudaMalloc failed");
-    g.pat.allocs.push_back(q);
+    (g_upPat ? g_upPat : &g.pat)->allocs.push_back(q);
     if (cudaMemcpy(q, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return fail("comm pattern: copy failed");
     *dst = (T*)q;
     return 0;
@@ -598,19 +605,17 @@ static int list_to_offsets(const int* list, long long n, std::vector<int>& blk, 
     return 0;
 }
 
-extern "C" {
-int adfb_comm_set_pattern(int level, int nNbr, const int* nbrRank, const int* sendCount, const int* recvCount,
-                          const int* sendList, const int* recvList, int nInternal, const int* donorList,
-                          const int* haloList) {
-    NEED_INIT();
-    (void)level;
+static int set_pattern_impl(Context::Pattern& P, int nNbr, const int* nbrRank, const int* sendCount, const int* recvCount,
+                            const int* sendList, const double* sendInterp, const int* recvList, int nInternal,
+                            const int* donorList, const double* donorInterp, const int* haloList, bool interp) {
     if (nNbr < 0 || nInternal < 0) return fail("adfb_comm_set_pattern: negative counts");
     drop_graphs();
     if (nNbr > 0 && g.nranks == 1) return fail("adfb_comm_set_pattern: neighbour ranks given but adfb_init was called with nranks = 1");
-    CK(cudaStreamSynchronize(g.stream));
-    for (void* q : g.pat.allocs) cudaFree(q);
-    g.pat = Context::Pattern();
-    Context::Pattern& P = g.pat;
+    if (cudaStreamSynchronize(g.stream) != cudaSuccess) return fail("stream sync failed");
+    for (void* q : P.allocs) cudaFree(q);
+    P = Context::Pattern();
+    P.interp = interp;
+    g_upPat = &P;
     std::vector<long long> cumS, cumR;
     std::vector<int> locS, locR, cntS, cntR;
     for (int m = 0; m < nNbr; m++) {
@@ -622,9 +627,24 @@ int adfb_comm_set_pattern(int level, int nNbr, const int* nbrRank, const int* se
     }
     P.nInt = nInternal;
     std::vector<int> blk; std::vector<long long> off;
+    // donor entries of an overset pattern: all 8 cells (i..i+1, ...) must exist, and the block strides travel along
+    auto donor_extra = [&](const int* list, long long n, const double* w, long long** dSJ, long long** dSK, double** dW, const char* what) -> int {
+        if (!w) return fail("adfb_comm_set_overset: %s interpolation weights missing", what);
+        std::vector<long long> sj(n), sk(n);
+        for (long long e = 0; e < n; e++) {
+            Block* b = get_block(list[4 * e]);
+            const Dims& d = b->d;
+            if (list[4 * e + 1] + 1 > d.ib || list[4 * e + 2] + 1 > d.jb || list[4 * e + 3] + 1 > d.kb)
+                return fail("adfb_comm_set_overset: %s entry %lld: donor stencil leaves block %d", what, e, list[4 * e]);
+            sj[e] = d.sJ; sk[e] = d.sK;
+        }
+        std::vector<double> wv(w, w + 8 * n);
+        return pat_upload(dSJ, sj) || pat_upload(dSK, sk) || pat_upload(dW, wv);
+    };
     if (P.nSend) {
         if (list_to_offsets(sendList, P.nSend, blk, off, "send")) return 1;
         if (pat_upload(&P.sBlk, blk) || pat_upload(&P.sOff, off) || pat_upload(&P.sCum, cumS) || pat_upload(&P.sLocal, locS) || pat_upload(&P.sCount, cntS)) return 1;
+        if (interp && donor_extra(sendList, P.nSend, sendInterp, &P.sSJ, &P.sSK, &P.sW, "send")) return 1;
     }
     if (P.nRecv) {
         if (list_to_offsets(recvList, P.nRecv, blk, off, "recv")) return 1;
@@ -633,25 +653,46 @@ int adfb_comm_set_pattern(int level, int nNbr, const int* nbrRank, const int* se
     if (P.nInt) {
         if (list_to_offsets(donorList, P.nInt, blk, off, "donor")) return 1;
         if (pat_upload(&P.iSrcBlk, blk) || pat_upload(&P.iSrcOff, off)) return 1;
+        if (interp && donor_extra(donorList, P.nInt, donorInterp, &P.iSJ, &P.iSK, &P.iW, "donor")) return 1;
         if (list_to_offsets(haloList, P.nInt, blk, off, "halo")) return 1;
         if (pat_upload(&P.iDstBlk, blk) || pat_upload(&P.iDstOff, off)) return 1;
     }
     void* q = nullptr;
-    if (P.nSend) { CK(cudaMalloc(&q, (size_t)P.nSend * ADFB_MAX_COMM_VARS * 8)); P.allocs.push_back(q); P.sendBuf = (double*)q; }
-    if (P.nRecv) { CK(cudaMalloc(&q, (size_t)P.nRecv * ADFB_MAX_COMM_VARS * 8)); P.allocs.push_back(q); P.recvBuf = (double*)q; }
+    if (P.nSend) { if (cudaMalloc(&q, (size_t)P.nSend * ADFB_MAX_COMM_VARS * 8) != cudaSuccess) return fail("comm pattern: cudaMalloc failed"); P.allocs.push_back(q); P.sendBuf = (double*)q; }
+    if (P.nRecv) { if (cudaMalloc(&q, (size_t)P.nRecv * ADFB_MAX_COMM_VARS * 8) != cudaSuccess) return fail("comm pattern: cudaMalloc failed"); P.allocs.push_back(q); P.recvBuf = (double*)q; }
     P.tabBlocks = (int)g.blocks.size();
-    CK(cudaMalloc(&q, sizeof(CommVarTable) * (P.tabBlocks > 0 ? P.tabBlocks : 1)));
-    P.allocs.push_back(q); P.dTab = (CommVarTable*)q;
     P.set = true;
+    g_upPat = nullptr;
     return 0;
+}
+
+extern "C" {
+int adfb_comm_set_pattern(int level, int nNbr, const int* nbrRank, const int* sendCount, const int* recvCount,
+                          const int* sendList, const int* recvList, int nInternal, const int* donorList,
+                          const int* haloList) {
+    NEED_INIT();
+    (void)level;
+    return set_pattern_impl(g.pat, nNbr, nbrRank, sendCount, recvCount, sendList, nullptr, recvList, nInternal, donorList, nullptr,
+                            haloList, false);
+}
+int adfb_comm_set_overset(int level, int nNbr, const int* nbrRank, const int* sendCount, const int* recvCount,
+                          const int* sendList, const double* sendInterp, const int* recvList, int nInternal,
+                          const int* donorList, const double* donorInterp, const int* haloList) {
+    NEED_INIT();
+    (void)level;
+    return set_pattern_impl(g.ovPat, nNbr, nbrRank, sendCount, recvCount, sendList, sendInterp, recvList, nInternal, donorList,
+                            donorInterp, haloList, true);
 }
 
 // whalo1to1 part of whalo2/whalo1 for the variable selection of setCommPointers
 // (src/utils/haloExchange.F90:356-470)
 static int halo_exchange_impl(int level, int start, int end, int commPressure, int commViscous, bool etotOwned) {
-    Context::Pattern& P = g.pat;
     const bool viscous = g.prm.equations != ADFB_EULER, eddy = g.prm.equations == ADFB_RANS;
-    if (P.set && (P.nSend || P.nRecv || P.nInt)) {
+    // whalo1to1 with commPatternCell_2nd / internalCell_2nd, then wOverset with commPatternOverset / internalOverset
+    // (whalo2, haloExchange.F90:139-146); orphan averaging is not supported (nOrphans must be 0)
+    for (Context::Pattern* PP : {&g.pat, &g.ovPat}) {
+        Context::Pattern& P = *PP;
+        if (!(P.set && (P.nSend || P.nRecv || P.nInt))) continue;
         if ((int)g.blocks.size() != P.tabBlocks) return fail("halo exchange: blocks changed after adfb_comm_set_pattern");
         const int key = start | (end << 4) | ((commPressure ? 1 : 0) << 8) | ((commViscous ? 1 : 0) << 9);
         int nVar = 0;
@@ -691,7 +732,11 @@ static int halo_exchange_impl(int level, int start, int end, int commPressure, i
         if (P.nSend) {
             const long long n = P.nSend * nVar;
             KT_BEGIN(K_HALO, g.stream);
-            k_halo_pack<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.sBlk, P.sOff, P.sCum, P.sLocal, P.sCount, dTab, nVar, P.nSend, P.sendBuf);
+            if (P.interp)
+                k_halo_pack_interp<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.sBlk, P.sOff, P.sCum, P.sLocal, P.sCount, P.sSJ, P.sSK,
+                                                                                     P.sW, dTab, nVar, P.nSend, P.sendBuf);
+            else
+                k_halo_pack<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.sBlk, P.sOff, P.sCum, P.sLocal, P.sCount, dTab, nVar, P.nSend, P.sendBuf);
             KT_END(K_HALO, g.stream);
         }
         if (!P.nbrRank.empty()) {
@@ -708,7 +753,11 @@ static int halo_exchange_impl(int level, int start, int end, int commPressure, i
         if (P.nInt) {
             const long long n = P.nInt * nVar;
             KT_BEGIN(K_HALO, g.stream);
-            k_halo_internal<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.iSrcBlk, P.iSrcOff, P.iDstBlk, P.iDstOff, dTab, nVar, P.nInt);
+            if (P.interp)
+                k_halo_internal_interp<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.iSrcBlk, P.iSrcOff, P.iSJ, P.iSK, P.iW, P.iDstBlk,
+                                                                                         P.iDstOff, dTab, nVar, P.nInt);
+            else
+                k_halo_internal<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.iSrcBlk, P.iSrcOff, P.iDstBlk, P.iDstOff, dTab, nVar, P.nInt);
             KT_END(K_HALO, g.stream);
         }
         if (P.nRecv) {

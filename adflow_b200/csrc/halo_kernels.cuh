@@ -46,6 +46,38 @@ __global__ void __launch_bounds__(256) k_halo_unpack(const int* __restrict__ ent
     const int v = (int)(q / n);
     tab[entBlk[e]].ptr[v][entOff[e]] = buf[(long long)nVar * entCum[e] + (long long)v * entCount[e] + entLocal[e]];
 }
+// overset donors (wOversetGeneric, haloExchange.F90:1471-1654): the value sent for a fringe cell is the weighted
+// sum of the 8 cells (i..i+1, j..j+1, k..k+1) of the donor block, weights interp(1:8) in the reference's order
+// (i fastest); sJ/sK of the donor block come with the entry
+__device__ __forceinline__ double interp8(const double* __restrict__ v, long long o, long long sJ, long long sK,
+                                          const double* __restrict__ w) {
+    return w[0] * v[o] + w[1] * v[o + 1] + w[2] * v[o + sJ] + w[3] * v[o + 1 + sJ] + w[4] * v[o + sK] + w[5] * v[o + 1 + sK] +
+           w[6] * v[o + sJ + sK] + w[7] * v[o + 1 + sJ + sK];
+}
+__global__ void __launch_bounds__(256) k_halo_pack_interp(const int* __restrict__ entBlk, const long long* __restrict__ entOff,
+                                                          const long long* __restrict__ entCum, const int* __restrict__ entLocal,
+                                                          const int* __restrict__ entCount, const long long* __restrict__ entSJ,
+                                                          const long long* __restrict__ entSK, const double* __restrict__ wgt,
+                                                          const CommVarTable* __restrict__ tab, int nVar, long long n,
+                                                          double* __restrict__ buf) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n * nVar) return;
+    const long long e = q % n;
+    const int v = (int)(q / n);
+    buf[(long long)nVar * entCum[e] + (long long)v * entCount[e] + entLocal[e]] =
+        interp8(tab[entBlk[e]].ptr[v], entOff[e], entSJ[e], entSK[e], wgt + 8 * e);
+}
+__global__ void __launch_bounds__(256) k_halo_internal_interp(const int* __restrict__ srcBlk, const long long* __restrict__ srcOff,
+                                                              const long long* __restrict__ srcSJ, const long long* __restrict__ srcSK,
+                                                              const double* __restrict__ wgt, const int* __restrict__ dstBlk,
+                                                              const long long* __restrict__ dstOff,
+                                                              const CommVarTable* __restrict__ tab, int nVar, long long n) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n * nVar) return;
+    const long long e = q % n;
+    const int v = (int)(q / n);
+    tab[dstBlk[e]].ptr[v][dstOff[e]] = interp8(tab[srcBlk[e]].ptr[v], srcOff[e], srcSJ[e], srcSK[e], wgt + 8 * e);
+}
 // same-rank donor -> halo copies (haloExchange.F90:654-676)
 __global__ void __launch_bounds__(256) k_halo_internal(const int* __restrict__ srcBlk, const long long* __restrict__ srcOff,
                                                        const int* __restrict__ dstBlk, const long long* __restrict__ dstOff,

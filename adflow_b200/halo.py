@@ -177,3 +177,90 @@ def make_grid_blocks(grid, rank, prm, seed=314):
                             physical_faces=tuple(grid.physical_faces(b)))
         out.append(hb)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# overset (interpolating) exchange: wOversetGeneric, src/utils/haloExchange.F90:1471-1654
+def trilinear_weights(frac):
+    """the 8 weights of sendList%interp / donorInterp from the fractional position (u, v, w) in the donor
+    stencil, in the reference's order (i fastest): the reference stores the weights themselves, computed by
+    fracToWeights (src/overset/oversetUtilities.F90) = tensor product of (1-u, u), (1-v, v), (1-w, w)."""
+    u, v, w = frac
+    return np.array([(1 - u) * (1 - v) * (1 - w), u * (1 - v) * (1 - w), (1 - u) * v * (1 - w), u * v * (1 - w),
+                     (1 - u) * (1 - v) * w, u * (1 - v) * w, (1 - u) * v * w, u * v * w])
+
+
+def build_overset_pattern(entries, rank=0, owner=None):
+    """entries: list of (donorBlock, (i, j, k) low corner, frac (u,v,w), fringeBlock, (i, j, k)) with GLOBAL block
+    ids; owner[b] = rank of block b (default all on rank 0).  Returns the pattern of `rank` with local block ids
+    (position among the rank's blocks in ascending global id), message entries ordered as they appear."""
+    nblk = 1 + max(max(e[0], e[3]) for e in entries)
+    owner = [0] * nblk if owner is None else list(owner)
+    local = {}
+    for b in range(nblk):
+        local[b] = sum(1 for q in range(b) if owner[q] == owner[b])
+    send, recv, don, halo, dw, sw = {}, {}, [], [], [], {}
+    for db, dijk, frac, fb, fijk in entries:
+        w = trilinear_weights(frac)
+        if owner[db] == rank and owner[fb] == rank:
+            don.append((local[db],) + tuple(dijk)); halo.append((local[fb],) + tuple(fijk)); dw.append(w)
+        elif owner[db] == rank:
+            send.setdefault(owner[fb], []).append((local[db],) + tuple(dijk)); sw.setdefault(owner[fb], []).append(w)
+        elif owner[fb] == rank:
+            recv.setdefault(owner[db], []).append((local[fb],) + tuple(fijk))
+    peers = sorted(set(send) | set(recv))
+    i4 = lambda rows: np.array(rows, dtype=np.int32).reshape(-1, 4)  # noqa: E731
+    return {
+        "nbrRank": np.array(peers, dtype=np.int32),
+        "sendCount": np.array([len(send.get(q, [])) for q in peers], dtype=np.int32),
+        "recvCount": np.array([len(recv.get(q, [])) for q in peers], dtype=np.int32),
+        "sendList": i4([r for q in peers for r in send.get(q, [])]),
+        "sendInterp": np.array([w for q in peers for w in sw.get(q, [])], dtype=np.float64).reshape(-1, 8),
+        "recvList": i4([r for q in peers for r in recv.get(q, [])]),
+        "donorList": i4(don), "donorInterp": np.array(dw, dtype=np.float64).reshape(-1, 8), "haloList": i4(halo),
+    }
+
+
+def _interp8(a, rows, wts):
+    i, j, k = rows[:, 1], rows[:, 2], rows[:, 3]
+    return (wts[:, 0] * a[i, j, k] + wts[:, 1] * a[i + 1, j, k] + wts[:, 2] * a[i, j + 1, k] + wts[:, 3] * a[i + 1, j + 1, k] +
+            wts[:, 4] * a[i, j, k + 1] + wts[:, 5] * a[i + 1, j, k + 1] + wts[:, 6] * a[i, j + 1, k + 1] +
+            wts[:, 7] * a[i + 1, j + 1, k + 1])
+
+
+def exchange_numpy_overset(blocks, pat, vars_of, sendrecv=None):
+    """wOversetGeneric on numpy blocks (same conventions as exchange_numpy)."""
+    V = [vars_of(b) for b in blocks]
+    nvar = len(V[0]) if V else 0
+    so = 0
+    recvbufs = []
+    for m, peer in enumerate(pat["nbrRank"]):
+        ns, nr = int(pat["sendCount"][m]), int(pat["recvCount"][m])
+        sl, sw = pat["sendList"][so:so + ns], pat["sendInterp"][so:so + ns]
+        buf = np.empty((nvar, ns))
+        for v in range(nvar):
+            for b in np.unique(sl[:, 0]):
+                sel = sl[:, 0] == b
+                buf[v, sel] = _interp8(V[b][v], sl[sel], sw[sel])
+        recvbufs.append(sendrecv(int(peer), buf, (nvar, nr)))
+        so += ns
+    dl, hl, dwt = pat["donorList"], pat["haloList"], pat["donorInterp"]
+    if len(dl):
+        vals = np.empty((nvar, len(dl)))
+        for v in range(nvar):
+            for b in np.unique(dl[:, 0]):
+                sel = dl[:, 0] == b
+                vals[v, sel] = _interp8(V[b][v], dl[sel], dwt[sel])
+        for v in range(nvar):
+            for b in np.unique(hl[:, 0]):
+                sel = hl[:, 0] == b
+                V[b][v][hl[sel, 1], hl[sel, 2], hl[sel, 3]] = vals[v, sel]
+    ro = 0
+    for m, _peer in enumerate(pat["nbrRank"]):
+        nr = int(pat["recvCount"][m])
+        rl = pat["recvList"][ro:ro + nr]
+        for v in range(nvar):
+            for b in np.unique(rl[:, 0]):
+                sel = rl[:, 0] == b
+                V[b][v][rl[sel, 1], rl[sel, 2], rl[sel, 3]] = recvbufs[m][v, sel]
+        ro += nr

@@ -84,6 +84,16 @@ class ADFLOW_B200:
                                            p(a["sendList"]), p(a["recvList"]), len(a["donorList"]), p(a["donorList"]),
                                            p(a["haloList"])), "adfb_comm_set_pattern")
 
+    def setOversetPattern(self, pat, level=1):
+        """Upload an overset (interpolating) communication pattern: the keys of setCommPattern plus the
+        8 weights per donor entry in "sendInterp" / "donorInterp" (adflow_b200.halo.build_overset_pattern)."""
+        a = {k: np.ascontiguousarray(v, dtype=(np.float64 if k.endswith("Interp") else np.int32)) for k, v in pat.items()}
+        self._keep.append(a)
+        p = lambda x: x.ctypes.data if x.size else None  # noqa: E731
+        check(self.L.adfb_comm_set_overset(level, len(a["nbrRank"]), p(a["nbrRank"]), p(a["sendCount"]), p(a["recvCount"]),
+                                           p(a["sendList"]), p(a["sendInterp"]), p(a["recvList"]), len(a["donorList"]),
+                                           p(a["donorList"]), p(a["donorInterp"]), p(a["haloList"])), "adfb_comm_set_overset")
+
     def haloExchange(self, start=1, end=None, comm_pressure=True, comm_gamma=True, comm_viscous=True, level=1):
         """whalo2(level, start, end, commPressure, commGamma, commViscous)."""
         if end is None:

@@ -225,6 +225,16 @@ double adfb_mffd_last_h(void);
 int adfb_comm_set_pattern(int level, int nNbr, const int* nbrRank, const int* sendCount, const int* recvCount,
                           const int* sendList, const int* recvList, int nInternal, const int* donorList,
                           const int* haloList);
+/* Device copy of the overset communication pattern commPatternOverset / internalOverset
+   (src/modules/communication.F90, built by the overset connectivity search).  Same list conventions as
+   adfb_comm_set_pattern; a donor entry (block, i, j, k) names the LOW corner of the 2x2x2 donor stencil and
+   sendInterp / donorInterp hold its 8 weights per entry in the reference's order (sendList%interp(j,1:8),
+   i fastest: (i,j,k), (i+1,j,k), (i,j+1,k), ...), wOversetGeneric src/utils/haloExchange.F90:1471-1654.
+   Once set, adfb_halo_exchange (and every call that exchanges halos) runs the overset exchange right after the
+   1-to-1 exchange like whalo2 does; orphan averaging is not supported (nOrphans must be 0). */
+int adfb_comm_set_overset(int level, int nNbr, const int* nbrRank, const int* sendCount, const int* recvCount,
+                          const int* sendList, const double* sendInterp, const int* recvList, int nInternal,
+                          const int* donorList, const double* donorInterp, const int* haloList);
 /* whalo2(level, start, end, commPressure, commGamma, commViscous)
    (src/utils/haloExchange.F90:109-199): w(start:end) [1-based], p, rlv, rev of all
    listed halo cells; grouped ncclSend/ncclRecv over NVLink; then computeEtotBlock on
