@@ -202,14 +202,20 @@ def make_block(nx, ny, nz, prm, origin=(0, 0, 0), global_n=None, first_cell="aut
     blk.d2Wall[d.owned()] = np.abs(cc[d.owned() + (2,)])
     # subfaces: wall on kMin, symmetry on jMin, far field elsewhere
     blk.subfaces = []
+    # physical_faces: the faces that carry a physical BC (default layout), or a dict face -> bcType
     for face in physical_faces:
-        bc = BC_FARFIELD
-        if face == KMIN:
-            bc = BC_WALL if prm.equations != EULER else BC_EULERWALL
-        elif face == JMIN:
-            bc = BC_SYMM
+        if isinstance(physical_faces, dict):
+            bc = physical_faces[face]
+            if prm.equations == EULER and bc in (BC_WALL, 6):
+                bc = BC_EULERWALL
+        else:
+            bc = BC_FARFIELD
+            if face == KMIN:
+                bc = BC_WALL if prm.equations != EULER else BC_EULERWALL
+            elif face == JMIN:
+                bc = BC_SYMM
         blk.subfaces.append(make_subface(blk, face, bc))
-        if bc in (BC_WALL, BC_EULERWALL, BC_EXTRAP):  # setPorosities
+        if bc in (BC_WALL, BC_EULERWALL, BC_EXTRAP, 6):  # setPorosities
             if face == IMIN: blk.porI[1, :, :] = 0
             if face == IMAX: blk.porI[d.il, :, :] = 0
             if face == JMIN: blk.porJ[:, 1, :] = 0

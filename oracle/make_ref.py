@@ -69,7 +69,7 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  bp_nx bp_ny bp_nz bp_il bp_jl bp_kl bp_ie bp_je bp_ke bp_ib bp_jb bp_kb bp_addgridvelocities
  bp_righthanded bp_sectionid bp_blockismoving bp_nbkglobal bp_nbocos bp_nviscbocos
  viscwallbctreatment eulerwallbctreatment outflowtreatment wallfunctions
- spectralsol computesepsensorks computecavitation cavexponent
+ spectralsol computesepsensorks computecavitation cavexponent rvfn
  symm symmpolar nswalladiabatic nswallisothermal farfield eulerwall extrap supersonicinflow supersonicoutflow
  subsonicinflow subsonicoutflow massbleedoutflow imin imax jmin jmax kmin kmax
  constantpressure linextrapolpressure quadextrapolpressure normalmomentum""".split()
@@ -175,7 +175,7 @@ UNITS = [
     ("solver/surfaceIntegrations.F90", "surfaceintegrations_", ["wallintegrationface", "ksaggregationfunction"], ()),
     ("turbulence/turbBCRoutines.F90", "turbbcroutines_",
      ["applyallturbbcthisblock", "bceddynowall", "bceddywall", "bcturbfarfield", "bcturbinflow", "bcturbinterface",
-      "bcturboutflow", "bcturbsymm", "bcturbtreatment", "bcturbwall", "turb2ndhalo"], ("USE_TAPENADE",)),
+      "bcturboutflow", "bcturbsymm", "bcturbtreatment", "bcturbwall", "turb2ndhalo"], ()),
     ("turbulence/sa.F90", "sa_", ["sa_block", "sasource", "saviscous", "saresscale", "sasolve"], ()),
     ("solver/residuals.F90", "residuals_", ["residualaveraging", "computedwdadi", "tridiagsolve"], ()),
     ("solver/smoothers.F90", "smoothers_", ["executerkstage", "executedadistep"], ()),

@@ -46,7 +46,7 @@ int *bp_globalcell;
 double *bp_bvti1, *bp_bvti2, *bp_bvtj1, *bp_bvtj2, *bp_bvtk1, *bp_bvtk2;
 RefSubface bcd[64];
 
-int spectralsol = 1, computesepsensorks = 0, computecavitation = 0, cavexponent = 0;
+int spectralsol = 1, computesepsensorks = 0, computecavitation = 0, cavexponent = 0, rvfn = 1;
 double pref = 1.0, lref = 1.0, machcoef = 1.0, cpmin_rho = 1.0, cavitationnumber = 1.0, cavsensorsharpness = 10.0, cavsensoroffset = 0.0;
 double sepsensorsharpness = 10.0, sepsensoroffset = 0.0, sepsensorkssharpness = 10.0, sepsensorksphi = 90.0, sepsensorksoffset = 0.0,
        sepsenmaxrho = 1.0;

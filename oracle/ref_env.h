@@ -101,7 +101,7 @@ static inline double vsf_tau(int nn, int i, int j, int l) { return bcd[nn - 1].t
 static inline double bcd_tns_wall(int nn, int i, int j) { return bcd[nn - 1].tns_wall[bcd_off(nn, i, j)]; }
 
 /* inputPhysics / inputCostFunctions / flowVarRefState data read by wallIntegrationFace */
-extern int spectralsol, computesepsensorks, computecavitation, cavexponent;
+extern int spectralsol, computesepsensorks, computecavitation, cavexponent, rvfn;
 extern double pref, lref, machcoef, cpmin_rho, cavitationnumber, cavsensorsharpness, cavsensoroffset;
 extern double sepsensorsharpness, sepsensoroffset, sepsensorkssharpness, sepsensorksphi, sepsensorksoffset, sepsenmaxrho;
 extern double veldirfreestream[3], pointref[3], momentaxis[6], cpmin_family[4], sepsenmaxfamily[4];
