@@ -78,6 +78,7 @@ def load():
     L.adfb_mffd_apply.argtypes = [vp, vp, C.c_longlong, C.c_double]
     L.adfb_mffd_last_h.restype = C.c_double
     L.adfb_comm_set_pattern.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, vp, vp]
+    L.adfb_comm_set_overset.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp]
     L.adfb_halo_exchange.argtypes = [ci] * 6
     L.adfb_apply_bcs.argtypes = [ci, ci, ci]
     L.adfb_timestep.argtypes = [ci, ci]

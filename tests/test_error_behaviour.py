@@ -35,7 +35,7 @@ def test_misuse_returns_nonzero_with_message(cuda_lib):
         v = np.zeros(7)
         assert L.adfb_set_states(v.ctypes.data, 7) != 0 and "does not match" in _err(L)
         assert L.adfb_mffd_apply(v.ctypes.data, v.ctypes.data, 7, 1e-7) != 0 and "set_base" in _err(L)
-        assert L.adfb_halo_exchange(1, 3, 2, 1, 0, 1) != 0 and "bad variable range" in _err(L)
+        assert L.adfb_halo_exchange(1, 0, 7, 1, 0, 1) != 0 and "bad variable range" in _err(L)
         bad = make_params()
         bad.equations = 9
         assert L.adfb_set_params(C.byref(bad)) != 0 and "bad equations" in _err(L)
