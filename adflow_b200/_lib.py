@@ -34,6 +34,10 @@ class AdfbSubface(C.Structure):
         ("bcType", C.c_int32), ("faceId", C.c_int32),
         ("icBeg", C.c_int32), ("icEnd", C.c_int32), ("jcBeg", C.c_int32), ("jcEnd", C.c_int32),
         ("norm", C.c_void_p), ("rface", C.c_void_p), ("uSlip", C.c_void_p), ("TNSWall", C.c_void_p),
+        ("ps", C.c_void_p), ("rho", C.c_void_p), ("velx", C.c_void_p), ("vely", C.c_void_p), ("velz", C.c_void_p),
+        ("ptInlet", C.c_void_p), ("ttInlet", C.c_void_p), ("htInlet", C.c_void_p), ("flowXdirInlet", C.c_void_p),
+        ("flowYdirInlet", C.c_void_p), ("flowZdirInlet", C.c_void_p), ("turbInlet", C.c_void_p),
+        ("subsonicInletTreatment", C.c_int32), ("pad_", C.c_int32),
     ]
 
 

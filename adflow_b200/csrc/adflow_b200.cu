@@ -454,6 +454,20 @@ int adfb_block_set_bc(int blk, int nSub, const AdfbSubface* subfaces) {
             return 0;
         };
         if (up(sf.norm, 3) || up(sf.rface, 1) || up(sf.uSlip, 3) || up(sf.TNSWall, 1)) return 1;
+        if (up(sf.ps, 1) || up(sf.rho, 1) || up(sf.velx, 1) || up(sf.vely, 1) || up(sf.velz, 1) || up(sf.ptInlet, 1) || up(sf.ttInlet, 1) ||
+            up(sf.htInlet, 1) || up(sf.flowXdirInlet, 1) || up(sf.flowYdirInlet, 1) || up(sf.flowZdirInlet, 1) || up(sf.turbInlet, 1))
+            return 1;
+        if (sf.bcType == ADFB_BC_SUBSONIC_OUTFLOW && !sf.ps) return fail("adfb_block_set_bc: subsonic outflow needs ps");
+        if (sf.bcType == ADFB_BC_SUPERSONIC_INFLOW && !(sf.ps && sf.rho && sf.velx && sf.vely && sf.velz))
+            return fail("adfb_block_set_bc: supersonic inflow needs rho, velx, vely, velz, ps");
+        if (sf.bcType == ADFB_BC_SUBSONIC_INFLOW) {
+            if (sf.subsonicInletTreatment == 1) {
+                if (!(sf.ptInlet && sf.ttInlet && sf.htInlet && sf.flowXdirInlet && sf.flowYdirInlet && sf.flowZdirInlet))
+                    return fail("adfb_block_set_bc: subsonic inflow (totalConditions) needs ptInlet, ttInlet, htInlet, flow?dirInlet");
+            } else if (sf.subsonicInletTreatment == 2) {
+                if (!(sf.rho && sf.velx && sf.vely && sf.velz)) return fail("adfb_block_set_bc: subsonic inflow (massFlow) needs rho, velx, vely, velz");
+            } else return fail("adfb_block_set_bc: subsonicInletTreatment must be 1 (totalConditions) or 2 (massFlow)");
+        }
         b->subfaces.push_back(sf);
     }
     return 0;

@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(128) k_sa_bmt(Dims d, BlockDev b, FaceDev f) {
     const long long na = f.icEnd - f.icBeg + 1, nb = f.jcEnd - f.jcBeg + 1;
     const long long o = (ia - f.icBeg) + na * (jb - f.jcBeg);
     double bmt = -1.0;
-    if (f.bcType == ADFB_BC_NSWALL_ADIABATIC || f.bcType == ADFB_BC_NSWALL_ISOTHERMAL) bmt = 1.0;
+    if (f.bcType == ADFB_BC_NSWALL_ADIABATIC || f.bcType == ADFB_BC_NSWALL_ISOTHERMAL || f.bcType == ADFB_BC_SUBSONIC_INFLOW ||
+        f.bcType == ADFB_BC_SUPERSONIC_INFLOW) bmt = 1.0;   // bcTurbWall / bcTurbInflow
     else if (f.bcType == ADFB_BC_FARFIELD) {
         const double dot = f.norm[o] * c_prm.wInf[1] + f.norm[o + na * nb] * c_prm.wInf[2] + f.norm[o + 2 * na * nb] * c_prm.wInf[3] -
                            (f.rface ? f.rface[o] : 0.0);

@@ -17,6 +17,8 @@ struct FaceDev {
     int icBeg, icEnd, jcBeg, jcEnd;
     int bcType;
     const double *norm, *rface, *uSlip, *TNSWall;
+    const double *ps, *rho, *velx, *vely, *velz, *ptInlet, *ttInlet, *htInlet, *fxd, *fyd, *fzd, *turbInlet;
+    int inletTreatment;
 };
 
 static FaceDev make_face(const Dims& d, const AdfbSubface& sf) {
@@ -32,6 +34,10 @@ static FaceDev make_face(const Dims& d, const AdfbSubface& sf) {
     f.icBeg = sf.icBeg; f.icEnd = sf.icEnd; f.jcBeg = sf.jcBeg; f.jcEnd = sf.jcEnd;
     f.bcType = sf.bcType;
     f.norm = sf.norm; f.rface = sf.rface; f.uSlip = sf.uSlip; f.TNSWall = sf.TNSWall;
+    f.ps = sf.ps; f.rho = sf.rho; f.velx = sf.velx; f.vely = sf.vely; f.velz = sf.velz;
+    f.ptInlet = sf.ptInlet; f.ttInlet = sf.ttInlet; f.htInlet = sf.htInlet;
+    f.fxd = sf.flowXdirInlet; f.fyd = sf.flowYdirInlet; f.fzd = sf.flowZdirInlet; f.turbInlet = sf.turbInlet;
+    f.inletTreatment = sf.subsonicInletTreatment;
     return f;
 }
 
@@ -75,7 +81,10 @@ __global__ void __launch_bounds__(128) k_bc_turb(Dims d, BlockDev b, FaceDev f, 
         const double dot = f.norm[o] * c_prm.wInf[1] + f.norm[o + na * nb] * c_prm.wInf[2] + f.norm[o + 2 * na * nb] * c_prm.wInf[3] -
                            (f.rface ? f.rface[o] : 0.0);
         if (dot > 0.0) bmt = -1.0; else bvt = c_prm.wInf[5];
-    } else bmt = -1.0;  // symm, Euler wall, extrapolation: zero gradient
+    } else if (f.bcType == ADFB_BC_SUBSONIC_INFLOW || f.bcType == ADFB_BC_SUPERSONIC_INFLOW) {
+        bvt = 2.0 * (f.turbInlet ? f.turbInlet[o] : 0.0);   // bcTurbInflow, turbBCRoutines.F90:460-515
+        bmt = 1.0;
+    } else bmt = -1.0;  // symm, Euler wall, extrapolation, outflow: zero gradient
     double* nt = b.w + 5 * N;
     double v1 = bvt;
     v1 = v1 - bmt * nt[c2];
@@ -162,20 +171,111 @@ __global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, 
             if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
             break;
         }
-        case ADFB_BC_EXTRAP: {  // bcExtrap, BCRoutines.F90:1479-1570 (linear extrapolation, fw2 = 2, fw3 = -1)
-            double r1 = 2.0 * w[c2] + -1.0 * w[c3];
+        case ADFB_BC_EXTRAP:
+        case ADFB_BC_SUPERSONIC_OUTFLOW: {  // bcExtrap, BCRoutines.F90:1479-1570
+            double fw2 = 2.0, fw3 = -1.0;   // extrap: linear; supersonic outflow: outflowTreatment
+            if (f.bcType == ADFB_BC_SUPERSONIC_OUTFLOW && !c_prm.outflowLinearExtrapol) { fw2 = 1.0; fw3 = 0.0; }
+            double r1 = fw2 * w[c2] + fw3 * w[c3];
             r1 = dmax_(0.5 * w[c2], r1);
             w[c1] = r1;
-            w[N + c1] = 2.0 * w[N + c2] + -1.0 * w[N + c3];
-            w[2 * N + c1] = 2.0 * w[2 * N + c2] + -1.0 * w[2 * N + c3];
-            w[3 * N + c1] = 2.0 * w[3 * N + c2] + -1.0 * w[3 * N + c3];
-            double p1 = 2.0 * b.p[c2] + -1.0 * b.p[c3];
+            w[N + c1] = fw2 * w[N + c2] + fw3 * w[N + c3];
+            w[2 * N + c1] = fw2 * w[2 * N + c2] + fw3 * w[2 * N + c3];
+            w[3 * N + c1] = fw2 * w[3 * N + c2] + fw3 * w[3 * N + c3];
+            double p1 = fw2 * b.p[c2] + fw3 * b.p[c3];
             p1 = dmax_(0.5 * b.p[c2], p1);
             b.p[c1] = p1;
             if (viscous) b.rlv[c1] = b.rlv[c2];
             if (eddy) b.rev[c1] = b.rev[c2];
             bc_etot(b, N, c1);
             if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            break;
+        }
+        case ADFB_BC_SUBSONIC_OUTFLOW: {  // bcSubsonicOutflow, BCRoutines.F90:693-802
+            const double pExit = f.ps[o];
+            const double ovg = 1.0 / gam, ovgm1 = 1.0 / (gam - 1.0);
+            const double pInt = b.p[c2];
+            const double r = 1.0 / w[c2];
+            const double a2 = gam * pInt * r;
+            double a = sqrt(a2);
+            const double ue = w[N + c2], ve = w[2 * N + c2], we = w[3 * N + c2];
+            const double qne = ue * n1 + ve * n2 + we * n3;
+            const double ss = pInt * pow(r, gam);
+            const double ac = qne + 2.0 * a * ovgm1;
+            const double r1 = pow(pExit / ss, ovg);
+            w[c1] = r1;
+            b.p[c1] = pExit;
+            a = sqrt(gam * pExit / r1);
+            const double qnh = ac - 2.0 * a * ovgm1;
+            w[N + c1] = ue + (qnh - qne) * n1;
+            w[2 * N + c1] = ve + (qnh - qne) * n2;
+            w[3 * N + c1] = we + (qnh - qne) * n3;
+            if (viscous) b.rlv[c1] = b.rlv[c2];
+            if (eddy) b.rev[c1] = b.rev[c2];
+            bc_etot(b, N, c1);
+            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            break;
+        }
+        case ADFB_BC_SUBSONIC_INFLOW: {  // bcSubsonicInflow, BCRoutines.F90:804-1061 (cpConstant)
+            const double gm1 = gam - 1.0, ovgm1 = 1.0 / gm1;
+            const double r = 1.0 / w[c2];
+            double a2 = gam * b.p[c2] * r;
+            double beta = w[N + c2] * n1 + w[2 * N + c2] * n2 + w[3 * N + c2] * n3 + 2.0 * ovgm1 * sqrt(a2);
+            if (f.inletTreatment == 1) {   // totalConditions
+                const double govgm1 = gam / (gam - 1.0);
+                const double ptot = f.ptInlet[o], ttot = f.ttInlet[o], htot = f.htInlet[o];
+                const double ssx = f.fxd[o], ssy = f.fyd[o], ssz = f.fzd[o];
+                double scaleFact = 1.0;
+                if (c_prm.hScalingInlet) scaleFact = sqrt(htot / (r * (w[4 * N + c2] + b.p[c2])));
+                beta = beta * scaleFact;
+                double q2 = w[N + c2] * w[N + c2] + w[2 * N + c2] * w[2 * N + c2] + w[3 * N + c2] * w[3 * N + c2];
+                const double a2tot = gm1 * (htot - r * (w[4 * N + c2] + b.p[c2]) + 0.5 * q2) + a2;
+                const double alpha = n1 * ssx + n2 * ssy + n3 * ssz;
+                const double aa2 = 0.5 * gm1 * alpha * alpha + 1.0;
+                const double bb = -gm1 * alpha * beta;
+                const double cc = 0.5 * gm1 * beta * beta - 2.0 * ovgm1 * a2tot;
+                double dd = bb * bb - 4.0 * aa2 * cc;
+                dd = sqrt(dmax_(0.0, dd));
+                double q = (-bb + dd) / (2.0 * aa2);
+                q = dmax_(0.0, q);
+                q2 = q * q;
+                a2 = a2tot - 0.5 * gm1 * q2;
+                double m2 = q2 / a2;
+                m2 = dmin_(1.0, m2);
+                q2 = m2 * a2;
+                q = sqrt(q2);
+                a2 = a2tot - 0.5 * gm1 * q2;
+                w[N + c1] = q * ssx; w[2 * N + c1] = q * ssy; w[3 * N + c1] = q * ssz;
+                const double ts = a2 / (gam * c_prm.RGas);
+                const double ratio = pow(ts / ttot, govgm1);
+                b.p[c1] = ptot * ratio;
+                w[c1] = (ptot * ratio) / (c_prm.RGas * ts);
+            } else {                        // massFlow
+                const double rho = f.rho[o], velx = f.velx[o], vely = f.vely[o], velz = f.velz[o];
+                a2 = 0.5 * gm1 * (beta - velx * n1 - vely * n2 - velz * n3);
+                a2 = dmax_(0.0, a2);
+                a2 = a2 * a2;
+                b.p[c1] = rho * a2 / gam;
+                w[c1] = rho; w[N + c1] = velx; w[2 * N + c1] = vely; w[3 * N + c1] = velz;
+            }
+            if (viscous) b.rlv[c1] = b.rlv[c2];
+            if (eddy) b.rev[c1] = b.rev[c2];
+            bc_etot(b, N, c1);
+            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            break;
+        }
+        case ADFB_BC_SUPERSONIC_INFLOW: {  // bcSupersonicInflow, BCRoutines.F90:1411-1477
+            w[c1] = f.rho[o]; w[N + c1] = f.velx[o]; w[2 * N + c1] = f.vely[o]; w[3 * N + c1] = f.velz[o];
+            b.p[c1] = f.ps[o];
+            if (viscous) b.rlv[c1] = b.rlv[c2];
+            if (eddy) b.rev[c1] = b.rev[c2];
+            bc_etot(b, N, c1);
+            if (secondHalo) {
+                w[c0] = f.rho[o]; w[N + c0] = f.velx[o]; w[2 * N + c0] = f.vely[o]; w[3 * N + c0] = f.velz[o];
+                b.p[c0] = f.ps[o];
+                if (viscous) b.rlv[c0] = b.rlv[c1];
+                if (eddy) b.rev[c0] = b.rev[c1];
+                bc_etot(b, N, c0);
+            }
             break;
         }
         case ADFB_BC_FARFIELD: {  // bcFarfield, BCRoutines.F90:1282-1396
@@ -498,8 +598,12 @@ static int launch_bc_flow(const Dims& d, const BlockDev& b, const std::vector<Ad
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_NSWALL_ADIABATIC) launch_bc_one(d, b, sf, secondHalo, 0, s);
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_NSWALL_ISOTHERMAL) launch_bc_one(d, b, sf, secondHalo, 0, s);
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_FARFIELD) launch_bc_one(d, b, sf, secondHalo, 0, s);
-    for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_EXTRAP) launch_bc_one(d, b, sf, secondHalo, 0, s);
+    for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SUBSONIC_OUTFLOW) launch_bc_one(d, b, sf, secondHalo, 0, s);
+    for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SUBSONIC_INFLOW) launch_bc_one(d, b, sf, secondHalo, 0, s);
+    for (const AdfbSubface& sf : subs)
+        if (sf.bcType == ADFB_BC_EXTRAP || sf.bcType == ADFB_BC_SUPERSONIC_OUTFLOW) launch_bc_one(d, b, sf, secondHalo, 0, s);
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_EULERWALL) launch_bc_one(d, b, sf, secondHalo, 0, s);
+    for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SUPERSONIC_INFLOW) launch_bc_one(d, b, sf, secondHalo, 0, s);
     return (int)cudaGetLastError();
 }
 

@@ -39,6 +39,7 @@ class AdfbParams(C.Structure):
         ("useQCR", C.c_int32), ("useft2SA", C.c_int32), ("useRotationSA", C.c_int32), ("approxSA", C.c_int32),
         ("secondOrdTurb", C.c_int32), ("limiter", C.c_int32), ("resAveraging", C.c_int32),
         ("nSubiterTurb", C.c_int32), ("wallBCConstantPressure", C.c_int32), ("reserved", C.c_int32),
+        ("hScalingInlet", C.c_int32), ("outflowLinearExtrapol", C.c_int32),
     ]
 
 

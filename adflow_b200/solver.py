@@ -50,10 +50,12 @@ class ADFLOW_B200:
             for q, s in enumerate(hb.subfaces):
                 sf[q].bcType, sf[q].faceId = s["bcType"], s["faceId"]
                 sf[q].icBeg, sf[q].icEnd, sf[q].jcBeg, sf[q].jcEnd = s["icBeg"], s["icEnd"], s["jcBeg"], s["jcEnd"]
-                for name in ("norm", "rface", "uSlip", "TNSWall"):
+                sf[q].subsonicInletTreatment = int(s.get("subsonicInletTreatment", 0))
+                for name in ("norm", "rface", "uSlip", "TNSWall", "ps", "rho", "velx", "vely", "velz", "ptInlet", "ttInlet", "htInlet",
+                             "flowXdirInlet", "flowYdirInlet", "flowZdirInlet", "turbInlet"):
                     a = s.get(name)
                     if a is not None:
-                        a = np.asfortranarray(a)
+                        a = np.asfortranarray(a, dtype=np.float64)
                         keep.append(a)
                         setattr(sf[q], name, a.ctypes.data)
             check(self.L.adfb_block_set_bc(blk, n, sf), "adfb_block_set_bc")

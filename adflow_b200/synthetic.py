@@ -214,7 +214,7 @@ def make_block(nx, ny, nz, prm, origin=(0, 0, 0), global_n=None, first_cell="aut
                 bc = BC_WALL if prm.equations != EULER else BC_EULERWALL
             elif face == JMIN:
                 bc = BC_SYMM
-        blk.subfaces.append(make_subface(blk, face, bc))
+        blk.subfaces.append(make_subface(blk, face, bc, prm))
         if bc in (BC_WALL, BC_EULERWALL, BC_EXTRAP, 6):  # setPorosities
             if face == IMIN: blk.porI[1, :, :] = 0
             if face == IMAX: blk.porI[d.il, :, :] = 0
@@ -226,7 +226,7 @@ def make_block(nx, ny, nz, prm, origin=(0, 0, 0), global_n=None, first_cell="aut
     return blk
 
 
-def make_subface(blk, face, bc):
+def make_subface(blk, face, bc, prm=None):
     """BCData of one whole block face: cell range 1:ie x 1:je of the two in-plane
     directions (halo-extended like icBeg:icEnd, src/utils/utils.F90:895-900) and the
     unit outward normal from the face's s-vector (boundaryNormals,
@@ -247,7 +247,31 @@ def make_subface(blk, face, bc):
     mag = np.where(mag > 0, mag, 1.0)
     norm = np.asfortranarray(mult * s / mag[..., None])
     sub = {"bcType": bc, "faceId": face, "icBeg": 1, "icEnd": n1, "jcBeg": 1, "jcEnd": n2, "norm": norm}
+    a, c = np.meshgrid(np.arange(n1), np.arange(n2), indexing="ij")
+    wig = np.sin(0.37 * a) * np.cos(0.23 * c)          # smooth in-plane variation of the prescribed data
     if bc == 6:  # isothermal wall: BCData%TNS_Wall, non-dimensional (T_inf = 1), smooth 5 % variation
-        a, c = np.meshgrid(np.arange(n1), np.arange(n2), indexing="ij")
-        sub["TNSWall"] = np.asfortranarray(1.08 + 0.05 * np.sin(0.37 * a) * np.cos(0.23 * c))
+        sub["TNSWall"] = np.asfortranarray(1.08 + 0.05 * wig)
+    if prm is not None and bc in (7, 8, 9, 10):
+        F = np.asfortranarray
+        g, R = prm.gammaInf, prm.RGas
+        rho, u, v, w_ = prm.wInf[0], prm.wInf[1], prm.wInf[2], prm.wInf[3]
+        if bc == 7:      # subsonic outflow: static pressure
+            sub["ps"] = F(prm.pInf * (0.97 + 0.02 * wig))
+        if bc == 9:      # supersonic inflow: full state
+            sub.update(rho=F(rho * (1.02 + 0.01 * wig)), velx=F(u * (1.5 + 0.02 * wig)), vely=F(v + 0.01 * wig),
+                       velz=F(w_ + 0.02 * wig), ps=F(prm.pInf * (1.05 + 0.01 * wig)))
+        if bc == 8:      # subsonic inflow; treatment chosen by the face parity so that both branches are exercised
+            sub["subsonicInletTreatment"] = 1 if face % 2 == 1 else 2
+            m2 = (u * u + v * v + w_ * w_) / (g * prm.pInf / rho)
+            tt = (prm.pInf / (R * rho)) * (1.0 + 0.5 * (g - 1.0) * m2)
+            pt = prm.pInf * (1.0 + 0.5 * (g - 1.0) * m2) ** (g / (g - 1.0))
+            dirn = -norm + 0.05 * wig[..., None]
+            dirn = dirn / np.sqrt((dirn * dirn).sum(-1))[..., None]
+            sub.update(ptInlet=F(pt * (1.0 + 0.01 * wig)), ttInlet=F(tt * (1.0 + 0.005 * wig)),
+                       htInlet=F(g / (g - 1.0) * R * tt * (1.0 + 0.005 * wig)), flowXdirInlet=F(dirn[..., 0]),
+                       flowYdirInlet=F(dirn[..., 1]), flowZdirInlet=F(dirn[..., 2]),
+                       rho=F(rho * (1.01 + 0.01 * wig)), velx=F(-0.3 * norm[..., 0] + 0.01 * wig),
+                       vely=F(-0.3 * norm[..., 1]), velz=F(-0.3 * norm[..., 2]))
+        if bc in (8, 9) and prm.equations == RANS:
+            sub["turbInlet"] = F(prm.wInf[5] * (1.0 + 0.1 * wig))
     return sub

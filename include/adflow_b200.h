@@ -60,7 +60,11 @@ enum {
     ADFB_BC_FARFIELD = 3,
     ADFB_BC_EULERWALL = 4,
     ADFB_BC_EXTRAP = 5,
-    ADFB_BC_NSWALL_ISOTHERMAL = 6
+    ADFB_BC_NSWALL_ISOTHERMAL = 6,
+    ADFB_BC_SUBSONIC_OUTFLOW = 7,   /* bcSubsonicOutflow (also MassBleedOutflow), needs ps */
+    ADFB_BC_SUBSONIC_INFLOW = 8,    /* bcSubsonicInflow: totalConditions (ptInlet, ttInlet, htInlet, flow?dirInlet) or massFlow (rho, vel?) */
+    ADFB_BC_SUPERSONIC_INFLOW = 9,  /* bcSupersonicInflow: rho, velx, vely, velz, ps prescribed */
+    ADFB_BC_SUPERSONIC_OUTFLOW = 10 /* bcExtrap with outflowTreatment (constant or linear extrapolation) */
 };
 /* block faces, reference order iMin..kMax (src/modules/constants.F90 iMin=1..kMax=6) */
 enum { ADFB_IMIN = 1, ADFB_IMAX = 2, ADFB_JMIN = 3, ADFB_JMAX = 4, ADFB_KMIN = 5, ADFB_KMAX = 6 };
@@ -121,6 +125,8 @@ typedef struct AdfbParams {
     int32_t nSubiterTurb;
     int32_t wallBCConstantPressure; /* viscWallBCTreatment == constantPressure */
     int32_t reserved;
+    int32_t hScalingInlet;         /* inputDiscretization hScalingInlet (subsonic inflow, total conditions) */
+    int32_t outflowLinearExtrapol; /* outflowTreatment == linExtrapol (default constantExtrapol), supersonic outflow */
 } AdfbParams;
 
 /* One boundary subface of a block, mirroring BCDataType (src/modules/block.F90:52-156)
@@ -135,6 +141,13 @@ typedef struct AdfbSubface {
     const double* rface;  /* BCData%rface (grid normal velocity), NULL == 0 */
     const double* uSlip;  /* BCData%uSlip(:,:,3), NULL == 0 */
     const double* TNSWall; /* isothermal walls only */
+    /* in/outflow data of BCData (src/modules/block.F90:100-140), extents (icBeg:icEnd, jcBeg:jcEnd); NULL if unused */
+    const double* ps;                       /* static pressure: subsonic outflow, supersonic inflow */
+    const double *rho, *velx, *vely, *velz; /* supersonic inflow, subsonic inflow with massFlow treatment */
+    const double *ptInlet, *ttInlet, *htInlet, *flowXdirInlet, *flowYdirInlet, *flowZdirInlet; /* total conditions */
+    const double* turbInlet;                /* BCData%turbInlet(:,:,nt1:nt2): turbulence variable at inflow faces */
+    int32_t subsonicInletTreatment;         /* 1 totalConditions, 2 massFlow (constants.F90:237-238) */
+    int32_t pad_;
 } AdfbSubface;
 
 /* ---- life cycle ---------------------------------------------------------- */

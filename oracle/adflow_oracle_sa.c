@@ -33,7 +33,8 @@ static void sa_bmt(const OrcBlock* b, const AdfbParams* prm, int nSub, const Adf
         for (int jb_ = s->jcBeg; jb_ <= s->jcEnd; jb_++) for (int ia = s->icBeg; ia <= s->icEnd; ia++) {
             long o = (ia - s->icBeg) + na * (jb_ - s->jcBeg);
             double bmt = zero;
-            if (s->bcType == ADFB_BC_NSWALL_ADIABATIC || s->bcType == ADFB_BC_NSWALL_ISOTHERMAL) bmt = one;
+            if (s->bcType == ADFB_BC_NSWALL_ADIABATIC || s->bcType == ADFB_BC_NSWALL_ISOTHERMAL ||
+                s->bcType == ADFB_BC_SUBSONIC_INFLOW || s->bcType == ADFB_BC_SUPERSONIC_INFLOW) bmt = one; /* bcTurbWall, bcTurbInflow */
             else if (s->bcType == ADFB_BC_FARFIELD) {
                 double dot = s->norm[o] * prm->wInf[IVX] + s->norm[o + na * nb] * prm->wInf[IVY] + s->norm[o + 2 * na * nb] * prm->wInf[IVZ] -
                              (s->rface ? s->rface[o] : zero);

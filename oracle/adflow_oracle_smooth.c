@@ -67,7 +67,13 @@ static void bc_turb_subface(const OrcBlock* b, const AdfbParams* prm, const Adfb
             double dot = NRM(sf, ia, jb_, 0) * prm->wInf[IVX] + NRM(sf, ia, jb_, 1) * prm->wInf[IVY] +
                          NRM(sf, ia, jb_, 2) * prm->wInf[IVZ] - (sf->rface ? sf->rface[(ia - sf->icBeg) + na * (jb_ - sf->jcBeg)] : zero);
             if (dot > zero) bmt = -one; else bvt = prm->wInf[ITU1];
-        } else if (sf->bcType == ADFB_BC_EULERWALL) bmt = -one; /* bcTurbSymm is used for Euler walls (:706) */
+        } else if (sf->bcType == ADFB_BC_SUBSONIC_INFLOW || sf->bcType == ADFB_BC_SUPERSONIC_INFLOW) {
+            /* bcTurbInflow, turbBCRoutines.F90:460-515 */
+            long oo = (ia - sf->icBeg) + na * (jb_ - sf->jcBeg);
+            bvt = two * (sf->turbInlet ? sf->turbInlet[oo] : zero);
+            bmt = one;
+        } else if (sf->bcType == ADFB_BC_SUBSONIC_OUTFLOW || sf->bcType == ADFB_BC_SUPERSONIC_OUTFLOW) bmt = -one; /* bcTurbOutflow */
+        else if (sf->bcType == ADFB_BC_EULERWALL) bmt = -one; /* bcTurbSymm is used for Euler walls (:706) */
         else if (sf->bcType == ADFB_BC_EXTRAP) bmt = -one;     /* bcTurbOutflow: zero gradient (:564-613) */
         W(c1, ITU1) = bvt;
         W(c1, ITU1) = W(c1, ITU1) - bmt * W(c2, ITU1);
@@ -152,8 +158,100 @@ static void bc_flow_subface(const OrcBlock* b, const AdfbParams* prm, const Adfb
                 if (secondHalo) bc_extrap2(b, d, prm, c0, c1, c2);
                 break;
             }
-            case ADFB_BC_EXTRAP: { /* bcExtrap, BCRoutines.F90:1479-1570: extrap => fw2 = 2, fw3 = -1 */
+            case ADFB_BC_SUBSONIC_OUTFLOW: { /* bcSubsonicOutflow, BCRoutines.F90:693-802 */
+                long o = (ia - sf->icBeg) + na * (jb_ - sf->jcBeg);
+                double pExit = sf->ps[o];
+                double ovg = one / gam, ovgm1 = one / (gam - one);
+                double pInt = b->p[c2];
+                double r = one / W(c2, IRHO);
+                double a2 = gam * pInt * r;
+                double a = sqrt(a2);
+                double ue = W(c2, IVX), ve = W(c2, IVY), we = W(c2, IVZ);
+                double qne = ue * n1 + ve * n2 + we * n3;
+                double ss = pInt * pow(r, gam);
+                double ac = qne + two * a * ovgm1;
+                W(c1, IRHO) = pow(pExit / ss, ovg);
+                b->p[c1] = pExit;
+                a = sqrt(gam * pExit / W(c1, IRHO));
+                double qnh = ac - two * a * ovgm1;
+                W(c1, IVX) = ue + (qnh - qne) * n1;
+                W(c1, IVY) = ve + (qnh - qne) * n2;
+                W(c1, IVZ) = we + (qnh - qne) * n3;
+                if (viscous) b->rlv[c1] = b->rlv[c2];
+                if (eddy) b->rev[c1] = b->rev[c2];
+                bc_etot(b, d, gam, c1);
+                if (secondHalo) bc_extrap2(b, d, prm, c0, c1, c2);
+                break;
+            }
+            case ADFB_BC_SUBSONIC_INFLOW: { /* bcSubsonicInflow, BCRoutines.F90:804-1061, cpConstant */
+                long o = (ia - sf->icBeg) + na * (jb_ - sf->jcBeg);
+                double govgm1 = gam / (gam - one);
+                double gm1 = gam - one, ovgm1 = one / gm1;
+                double r = one / W(c2, IRHO);
+                double a2 = gam * b->p[c2] * r;
+                double beta = W(c2, IVX) * n1 + W(c2, IVY) * n2 + W(c2, IVZ) * n3 + two * ovgm1 * sqrt(a2);
+                if (sf->subsonicInletTreatment == 1) { /* totalConditions */
+                    double ptot = sf->ptInlet[o], ttot = sf->ttInlet[o], htot = sf->htInlet[o];
+                    double ssx = sf->flowXdirInlet[o], ssy = sf->flowYdirInlet[o], ssz = sf->flowZdirInlet[o];
+                    double scaleFact = one;
+                    if (prm->hScalingInlet) scaleFact = sqrt(htot / (r * (W(c2, IRHOE) + b->p[c2])));
+                    beta = beta * scaleFact;
+                    double q2 = W(c2, IVX) * W(c2, IVX) + W(c2, IVY) * W(c2, IVY) + W(c2, IVZ) * W(c2, IVZ);
+                    double a2tot = gm1 * (htot - r * (W(c2, IRHOE) + b->p[c2]) + half * q2) + a2;
+                    double alpha = n1 * ssx + n2 * ssy + n3 * ssz;
+                    double aa2 = half * gm1 * alpha * alpha + one;
+                    double bb = -gm1 * alpha * beta;
+                    double cc = half * gm1 * beta * beta - two * ovgm1 * a2tot;
+                    double dd = bb * bb - four * aa2 * cc;
+                    dd = sqrt(dmax(zero, dd));
+                    double q = (-bb + dd) / (two * aa2);
+                    q = dmax(zero, q);
+                    q2 = q * q;
+                    a2 = a2tot - half * gm1 * q2;
+                    double m2 = q2 / a2;
+                    m2 = dmin(one, m2);
+                    q2 = m2 * a2;
+                    q = sqrt(q2);
+                    a2 = a2tot - half * gm1 * q2;
+                    W(c1, IVX) = q * ssx; W(c1, IVY) = q * ssy; W(c1, IVZ) = q * ssz;
+                    double ts = a2 / (gam * prm->RGas);
+                    double ratio = pow(ts / ttot, govgm1);
+                    b->p[c1] = ptot * ratio;
+                    W(c1, IRHO) = (ptot * ratio) / (prm->RGas * ts);
+                } else { /* massFlow */
+                    double rho = sf->rho[o], velx = sf->velx[o], vely = sf->vely[o], velz = sf->velz[o];
+                    a2 = half * gm1 * (beta - velx * n1 - vely * n2 - velz * n3);
+                    a2 = dmax(zero, a2);
+                    a2 = a2 * a2;
+                    b->p[c1] = rho * a2 / gam;
+                    W(c1, IRHO) = rho; W(c1, IVX) = velx; W(c1, IVY) = vely; W(c1, IVZ) = velz;
+                }
+                if (viscous) b->rlv[c1] = b->rlv[c2];
+                if (eddy) b->rev[c1] = b->rev[c2];
+                bc_etot(b, d, gam, c1);
+                if (secondHalo) bc_extrap2(b, d, prm, c0, c1, c2);
+                break;
+            }
+            case ADFB_BC_SUPERSONIC_INFLOW: { /* bcSupersonicInflow, BCRoutines.F90:1411-1477 */
+                long o = (ia - sf->icBeg) + na * (jb_ - sf->jcBeg);
+                W(c1, IRHO) = sf->rho[o]; W(c1, IVX) = sf->velx[o]; W(c1, IVY) = sf->vely[o]; W(c1, IVZ) = sf->velz[o];
+                b->p[c1] = sf->ps[o];
+                if (viscous) b->rlv[c1] = b->rlv[c2];
+                if (eddy) b->rev[c1] = b->rev[c2];
+                bc_etot(b, d, gam, c1);
+                if (secondHalo) {
+                    W(c0, IRHO) = sf->rho[o]; W(c0, IVX) = sf->velx[o]; W(c0, IVY) = sf->vely[o]; W(c0, IVZ) = sf->velz[o];
+                    b->p[c0] = sf->ps[o];
+                    if (viscous) b->rlv[c0] = b->rlv[c1];
+                    if (eddy) b->rev[c0] = b->rev[c1];
+                    bc_etot(b, d, gam, c0);
+                }
+                break;
+            }
+            case ADFB_BC_EXTRAP:
+            case ADFB_BC_SUPERSONIC_OUTFLOW: { /* bcExtrap, BCRoutines.F90:1479-1570 */
                 double fw2 = two, fw3 = -one, factor = half;
+                if (sf->bcType == ADFB_BC_SUPERSONIC_OUTFLOW && !prm->outflowLinearExtrapol) { fw2 = one; fw3 = zero; }
                 W(c1, IRHO) = fw2 * W(c2, IRHO) + fw3 * W(c3, IRHO);
                 W(c1, IRHO) = dmax(factor * W(c2, IRHO), W(c1, IRHO));
                 W(c1, IVX) = fw2 * W(c2, IVX) + fw3 * W(c3, IVX);
@@ -236,8 +334,12 @@ void orc_apply_flow_bc(const OrcBlock* b, const AdfbParams* prm, int nSub, const
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_NSWALL_ADIABATIC) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_NSWALL_ISOTHERMAL) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_FARFIELD) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
-    for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_EXTRAP) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
+    for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SUBSONIC_OUTFLOW) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
+    for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SUBSONIC_INFLOW) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
+    for (n = 0; n < nSub; n++)
+        if (sf[n].bcType == ADFB_BC_EXTRAP || sf[n].bcType == ADFB_BC_SUPERSONIC_OUTFLOW) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_EULERWALL) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
+    for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SUPERSONIC_INFLOW) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
 }
 
 /* ------------------------------------------------------------------------ */

@@ -69,7 +69,7 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  bp_nx bp_ny bp_nz bp_il bp_jl bp_kl bp_ie bp_je bp_ke bp_ib bp_jb bp_kb bp_addgridvelocities
  bp_righthanded bp_sectionid bp_blockismoving bp_nbkglobal bp_nbocos bp_nviscbocos
  viscwallbctreatment eulerwallbctreatment outflowtreatment wallfunctions
- spectralsol computesepsensorks computecavitation cavexponent rvfn
+ spectralsol computesepsensorks computecavitation cavexponent rvfn hscalinginlet totalconditions massflow
  symm symmpolar nswalladiabatic nswallisothermal farfield eulerwall extrap supersonicinflow supersonicoutflow
  subsonicinflow subsonicoutflow massbleedoutflow imin imax jmin jmax kmin kmax
  constantpressure linextrapolpressure quadextrapolpressure normalmomentum""".split()
@@ -168,7 +168,8 @@ UNITS = [
     ("modules/BCPointers.F90", "bcpointers_", [], ("USE_TAPENADE",)),
     ("utils/utils.F90", "", ["setbcpointers"], ()),
     ("solver/BCRoutines.F90", "bcroutines_", ["applyallbc", "applyallbc_block", "bcsymm1sthalo", "bcsymm2ndhalo", "bcnswalladiabatic",
-                                              "bcnswallisothermal", "bcfarfield", "bceulerwall", "bcextrap",
+                                              "bcnswallisothermal", "bcfarfield", "bceulerwall", "bcextrap", "bcsubsonicoutflow",
+                                              "bcsubsonicinflow", "bcsupersonicinflow",
                                               "computeetot", "extrapolate2ndhalo"], ()),
     ("turbulence/turbUtils.F90", "turbutils_", ["computeeddyviscosity", "saeddyviscosity", "turbadvection"], ()),
     ("adjoint/adjointExtra.F90", "adjointextra_", ["volume_block", "metric_block"], ()),
@@ -192,7 +193,8 @@ def main():
         print("make_ref: %s/src not found -- reference not present, nothing generated" % ref)
         return 0
     env = f90toc.Env(ENV_INTS, env_arrays(), ["getcorrectfork", "bcd_icbeg", "bcd_icend", "bcd_jcbeg", "bcd_jcend",
-                                              "bcd_inbeg", "bcd_inend", "bcd_jnbeg", "bcd_jnend", "bcd_iblank"], dict(ENV_SUBS))
+                                              "bcd_inbeg", "bcd_inend", "bcd_jnbeg", "bcd_jnend", "bcd_iblank",
+                                              "bcd_subsonicinlettreatment"], dict(ENV_SUBS))
     outdir = os.path.join(HERE, "_ref")
     os.makedirs(outdir, exist_ok=True)
     tr = None

@@ -109,7 +109,9 @@ class Oracle:
         for q, s in enumerate(subs):
             arr[q].bcType, arr[q].faceId = s["bcType"], s["faceId"]
             arr[q].icBeg, arr[q].icEnd, arr[q].jcBeg, arr[q].jcEnd = s["icBeg"], s["icEnd"], s["jcBeg"], s["jcEnd"]
-            for name in ("norm", "rface", "uSlip", "TNSWall"):
+            arr[q].subsonicInletTreatment = int(s.get("subsonicInletTreatment", 0))
+            for name in ("norm", "rface", "uSlip", "TNSWall", "ps", "rho", "velx", "vely", "velz", "ptInlet", "ttInlet", "htInlet",
+                         "flowXdirInlet", "flowYdirInlet", "flowZdirInlet", "turbInlet"):
                 a = s.get(name)
                 if a is not None:
                     a = np.asfortranarray(a, dtype=np.float64)

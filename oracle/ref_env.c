@@ -39,7 +39,7 @@ int turbrelax = 2 /* turbRelaxImplicit */;
 double alfaturb;
 
 int bp_nbocos = 0, bp_nviscbocos = 0, bp_bctype[64], bp_bcfaceid[64];
-int viscwallbctreatment = 1, eulerwallbctreatment = 1, outflowtreatment = 1, wallfunctions = 0;
+int viscwallbctreatment = 1, eulerwallbctreatment = 1, outflowtreatment = 1, wallfunctions = 0, hscalinginlet = 0;
 double winf[10];
 double *bp_s;
 int *bp_globalcell;
@@ -66,12 +66,10 @@ UNREACHABLE(turbutils_kweddyviscosity)
 UNREACHABLE(turbutils_ssteddyviscosity)
 UNREACHABLE(turbutils_kteddyviscosity)
 UNREACHABLE(turbutils_vfeddyviscosity)
-/* boundary-condition types outside section 8 (polar symmetry, in/outflow) */
+/* boundary-condition types outside section 8 (polar symmetry) */
 UNREACHABLE(bcroutines_bcsymmpolar1sthalo)
 UNREACHABLE(bcroutines_bcsymmpolar2ndhalo)
-UNREACHABLE(bcroutines_bcsubsonicoutflow)
-UNREACHABLE(bcroutines_bcsubsonicinflow)
-UNREACHABLE(bcroutines_bcsupersonicinflow)
+
 
 /* src/utils/utils.F90:486-500 */
 int getcorrectfork(void) { return kpresent && currentlevel <= groundlevel; }

@@ -60,7 +60,7 @@ void terminate(const char* routine, const char* msg); /* src/utils/utils.F90 ter
 
 /* boundary-condition bookkeeping of the current block (blockPointers nBocos, BCType, BCFaceID, BCData) */
 extern int bp_nbocos, bp_nviscbocos, bp_bctype[64], bp_bcfaceid[64];
-extern int viscwallbctreatment, eulerwallbctreatment, outflowtreatment, wallfunctions;
+extern int viscwallbctreatment, eulerwallbctreatment, outflowtreatment, wallfunctions, hscalinginlet;
 extern double winf[10];
 extern double *bp_s;
 extern int *bp_globalcell;
@@ -72,6 +72,9 @@ typedef struct {
     int inbeg, inend, jnbeg, jnend; /* node range of the subface (owned face cells are inBeg+1:inEnd) */
     int* iblank;                    /* BCData%iblank: iblank of the adjacent interior cell, (icBeg:icEnd, jcBeg:jcEnd) */
     double* tau;                    /* viscSubface%tau(:,:,6), same layout */
+    /* in/outflow data */
+    double *ps, *rho, *velx, *vely, *velz, *ptinlet, *ttinlet, *htinlet, *flowxdirinlet, *flowydirinlet, *flowzdirinlet, *turbinlet;
+    int subsonicinlettreatment, pad_;
 } RefSubface;
 extern RefSubface bcd[64];
 static inline int bcd_icbeg(int nn) { return bcd[nn - 1].icbeg; }
@@ -89,8 +92,12 @@ static inline long bcd_size(int nn) {
 static inline double bcd_norm(int nn, int i, int j, int l) { return bcd[nn - 1].norm[bcd_off(nn, i, j) + (l - 1) * bcd_size(nn)]; }
 static inline double bcd_uslip(int nn, int i, int j, int l) { return bcd[nn - 1].uslip[bcd_off(nn, i, j) + (l - 1) * bcd_size(nn)]; }
 static inline double bcd_rface(int nn, int i, int j) { return bcd[nn - 1].rface[bcd_off(nn, i, j)]; }
-/* turbulence inflow data: inflow BCs are outside section 8, never reached */
-static inline double bcd_turbinlet(int nn, int i, int j, int l) { (void)nn; (void)i; (void)j; (void)l; return 0.0; }
+#define BCD_SCALAR(name) static inline double bcd_##name(int nn, int i, int j) { return bcd[nn - 1].name[bcd_off(nn, i, j)]; }
+BCD_SCALAR(ps) BCD_SCALAR(rho) BCD_SCALAR(velx) BCD_SCALAR(vely) BCD_SCALAR(velz) BCD_SCALAR(ptinlet) BCD_SCALAR(ttinlet)
+BCD_SCALAR(htinlet) BCD_SCALAR(flowxdirinlet) BCD_SCALAR(flowydirinlet) BCD_SCALAR(flowzdirinlet)
+static inline int bcd_subsonicinlettreatment(int nn) { return bcd[nn - 1].subsonicinlettreatment; }
+/* BCData%turbInlet(i, j, nt1:nt2): one turbulence variable (SA) */
+static inline double bcd_turbinlet(int nn, int i, int j, int l) { (void)l; return bcd[nn - 1].turbinlet[bcd_off(nn, i, j)]; }
 static inline int bcd_inbeg(int nn) { return bcd[nn - 1].inbeg; }
 static inline int bcd_inend(int nn) { return bcd[nn - 1].inend; }
 static inline int bcd_jnbeg(int nn) { return bcd[nn - 1].jnbeg; }

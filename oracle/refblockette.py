@@ -113,11 +113,15 @@ class RefSubface(C.Structure):
     _fields_ = [("icbeg", C.c_int), ("icend", C.c_int), ("jcbeg", C.c_int), ("jcend", C.c_int),
                 ("norm", C.c_void_p), ("rface", C.c_void_p), ("uslip", C.c_void_p), ("tns_wall", C.c_void_p),
                 ("inbeg", C.c_int), ("inend", C.c_int), ("jnbeg", C.c_int), ("jnend", C.c_int),
-                ("iblank", C.c_void_p), ("tau", C.c_void_p)]
+                ("iblank", C.c_void_p), ("tau", C.c_void_p)] + [
+                    (n, C.c_void_p) for n in ("ps", "rho", "velx", "vely", "velz", "ptinlet", "ttinlet", "htinlet", "flowxdirinlet",
+                                              "flowydirinlet", "flowzdirinlet", "turbinlet")] + [
+                    ("subsonicinlettreatment", C.c_int), ("pad_", C.c_int)]
 
 
 # AdfbSubface.bcType (include/adflow_b200.h) -> name of the reference's BC constant
-_BC_NAME = {1: "symm", 2: "nswalladiabatic", 3: "farfield", 4: "eulerwall", 5: "extrap", 6: "nswallisothermal"}
+_BC_NAME = {1: "symm", 2: "nswalladiabatic", 3: "farfield", 4: "eulerwall", 5: "extrap", 6: "nswallisothermal",
+            7: "subsonicoutflow", 8: "subsonicinflow", 9: "supersonicinflow", 10: "supersonicoutflow"}
 
 
 def bind_bcs(hb, prm):
@@ -142,6 +146,15 @@ def bind_bcs(hb, prm):
             a = np.zeros((na, nb, ncomp), order="F") if a is None else np.asfortranarray(a, dtype=np.float64)
             keep.append(a)
             setattr(tab[q], field, a.ctypes.data)
+        for field, key in (("ps", "ps"), ("rho", "rho"), ("velx", "velx"), ("vely", "vely"), ("velz", "velz"),
+                           ("ptinlet", "ptInlet"), ("ttinlet", "ttInlet"), ("htinlet", "htInlet"),
+                           ("flowxdirinlet", "flowXdirInlet"), ("flowydirinlet", "flowYdirInlet"),
+                           ("flowzdirinlet", "flowZdirInlet"), ("turbinlet", "turbInlet")):
+            a = s_.get(key)
+            a = np.zeros((na, nb), order="F") if a is None else np.asfortranarray(a, dtype=np.float64)
+            keep.append(a)
+            setattr(tab[q], field, a.ctypes.data)
+        tab[q].subsonicinlettreatment = int(s_.get("subsonicInletTreatment", 0))
         # node range (owned face cells inBeg+1:inEnd), BCData%iblank and viscSubface%tau planes of the subface
         d = hb.d
         face = s_["faceId"]
@@ -166,6 +179,8 @@ def bind_bcs(hb, prm):
         tab[q].tau = tau.ctypes.data
     _seti("viscwallbctreatment", cst["constantpressure"] if prm.wallBCConstantPressure else cst["linextrapolpressure"])
     _seti("eulerwallbctreatment", cst["constantpressure"] if prm.reserved else cst["linextrapolpressure"])
+    _seti("hscalinginlet", prm.hScalingInlet)
+    _seti("outflowtreatment", cst["linextrapol"] if prm.outflowLinearExtrapol else cst["constantextrapol"])
     w = (C.c_double * 10).in_dll(lib(), "winf")
     for q in range(6):
         w[q] = prm.wInf[q]

@@ -12,6 +12,7 @@ pytestmark = pytest.mark.skipif(not rb.available(), reason="oracle/_ref/libblock
 
 IMIN, IMAX, JMIN, JMAX, KMIN, KMAX = 1, 2, 3, 4, 5, 6
 SYMM, WALL, FAR, EULERWALL, EXTRAP, ISOWALL = 1, 2, 3, 4, 5, 6
+SUBOUT, SUBIN, SUPIN, SUPOUT = 7, 8, 9, 10
 
 
 def _check(prm, hb, second_halo=True):
@@ -59,6 +60,23 @@ def test_isothermal_wall_and_extrapolation(perm, treat):
     _check(prm, hb, False)
 
 
+@pytest.mark.parametrize("perm", [
+    {IMIN: SUBIN, IMAX: SUBOUT, JMIN: SYMM, JMAX: FAR, KMIN: WALL, KMAX: SUPOUT},      # iMin: total conditions
+    {IMIN: SUPIN, IMAX: SUPOUT, JMIN: SUBOUT, JMAX: SUBIN, KMIN: FAR, KMAX: WALL},     # jMax: mass flow
+    {IMIN: SUBOUT, IMAX: SUBIN, JMIN: WALL, JMAX: SUPOUT, KMIN: SUBIN, KMAX: SUPIN},   # iMax mass flow, kMin total
+])
+@pytest.mark.parametrize("eq", ["Euler", "RANS"])
+@pytest.mark.parametrize("flagset", [(0, 0), (1, 1)])
+def test_inflow_outflow(perm, eq, flagset):
+    """bcSubsonicOutflow :693-802, bcSubsonicInflow :804-1061 (totalConditions and massFlow, cpConstant),
+    bcSupersonicInflow :1411-1477, bcExtrap for SupersonicOutflow with outflowTreatment"""
+    prm, hb = case(8, 7, 9, {"equationType": eq}, physical_faces=perm)
+    prm.hScalingInlet, prm.outflowLinearExtrapol = flagset
+    hb.subfaces.sort(key=lambda s_: 0 if s_["bcType"] in (2, 6) else 1)
+    _check(prm, hb, True)
+    _check(prm, hb, False)
+
+
 @pytest.mark.parametrize("treat", ["constant pressure extrapolation", "linear pressure extrapolation"])
 def test_wall_pressure_treatment(treat):
     prm, hb = case(8, 7, 9, {"equationType": "RANS", "viscWallTreatment": treat})
@@ -79,6 +97,7 @@ def test_euler_wall(const_p):
     {IMIN: FAR, IMAX: WALL, JMIN: SYMM, JMAX: FAR, KMIN: FAR, KMAX: SYMM},
     {IMIN: SYMM, IMAX: FAR, JMIN: WALL, JMAX: FAR, KMIN: FAR, KMAX: WALL},
     {IMIN: EXTRAP, IMAX: FAR, JMIN: SYMM, JMAX: ISOWALL, KMIN: ISOWALL, KMAX: EXTRAP},
+    {IMIN: SUBIN, IMAX: SUBOUT, JMIN: SUPIN, JMAX: SUPOUT, KMIN: WALL, KMAX: FAR},
 ])
 @pytest.mark.parametrize("second", [True, False])
 def test_turbulence_bcs(perm, second):
