@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "adfb_download_residual", "adfb_download_intermed", "adfb_residual", "adfb_norms", "adfb_synchronize", "adfb_forces",
     "adfb_get_states", "adfb_set_states", "adfb_get_res", "adfb_state_size",
     "adfb_comm_set_pattern", "adfb_comm_set_overset", "adfb_halo_exchange",
-    "adfb_reference_shock_sensor", "adfb_form_function", "adfb_mffd_set_base", "adfb_mffd_apply", "adfb_mffd_last_h",
+    "adfb_reference_shock_sensor", "adfb_form_function", "adfb_mffd_set_base", "adfb_mffd_apply", "adfb_mffd_apply_device", "adfb_mffd_last_h",
     "adfb_apply_bcs", "adfb_timestep", "adfb_smoother_residual", "adfb_rk_stage", "adfb_rk_cycle", "adfb_dadi_step", "adfb_dadi_cycle", "adfb_sa_ddadi",
 ]
 
@@ -80,6 +80,7 @@ def load():
     L.adfb_form_function.argtypes = [vp, vp, C.c_longlong]
     L.adfb_mffd_set_base.argtypes = [vp, C.c_longlong]
     L.adfb_mffd_apply.argtypes = [vp, vp, C.c_longlong, C.c_double]
+    L.adfb_mffd_apply_device.argtypes = [vp, vp, C.c_longlong, C.c_double]
     L.adfb_mffd_last_h.restype = C.c_double
     L.adfb_comm_set_pattern.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, vp, vp]
     L.adfb_comm_set_overset.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp]

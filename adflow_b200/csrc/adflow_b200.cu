@@ -926,19 +926,14 @@ int adfb_mffd_set_base(const double* U, long long n) {
 // MatMult of the MFFD shell: y = (F(U + h a) - F(U)) / h.  h > 0: use it as given;
 // h <= 0: PETSc's default Walker-Pernice choice h = error_rel * sqrt(1 + ||U||) / ||a||
 // with error_rel = sqrt(machine epsilon) (PARITY UNPINNED at this boundary).
-int adfb_mffd_apply(const double* a, double* y, long long n, double h) {
-    NEED_INIT();
-    if (!g.nkHaveBase) return fail("adfb_mffd_apply: adfb_mffd_set_base has not been called");
-    const long long need = adfb_state_size();
-    if (!a || !y || n != need || (size_t)need > g.nkN) return fail("adfb_mffd_apply: vector length %lld != local state size %lld", n, need);
-    CK(cudaMemcpyAsync(g.nkA, a, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+// y = (F(U + h a) - F(U)) / h with a in g.nkA, y into g.nkY (device); returns 2 when a == 0 (y = 0, no residual)
+static int mffd_core(long long need, double h) {
     if (h <= 0.0) {
         double aa = 0.0;
         if (nk_sumsq(g.nkA, need, &aa)) return 1;
         if (aa == 0.0) {
-            memset(y, 0, need * sizeof(double));
             g.nkLastH = 0.0;
-            return 0;
+            return 2;
         }
         h = 1.4901161193847656e-08 * sqrt(1.0 + g.nkUnorm) / sqrt(aa);
     }
@@ -946,7 +941,43 @@ int adfb_mffd_apply(const double* a, double* y, long long n, double h) {
     if (nk_vec_kernel(g.nkA, g.nkU, nullptr, h, 1)) return 1;
     if (adfb_residual(1, kNkFlags)) return 1;
     if (nk_vec_kernel(nullptr, g.nkF0, g.nkY, h, 3)) return 1;
+    return 0;
+}
+int adfb_mffd_apply(const double* a, double* y, long long n, double h) {
+    NEED_INIT();
+    if (!g.nkHaveBase) return fail("adfb_mffd_apply: adfb_mffd_set_base has not been called");
+    const long long need = adfb_state_size();
+    if (!a || !y || n != need || (size_t)need > g.nkN) return fail("adfb_mffd_apply: vector length %lld != local state size %lld", n, need);
+    CK(cudaMemcpyAsync(g.nkA, a, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    const int rc = mffd_core(need, h);
+    if (rc == 1) return 1;
+    if (rc == 2) {
+        CK(cudaStreamSynchronize(g.stream));
+        memset(y, 0, need * sizeof(double));
+        return 0;
+    }
     CK(cudaMemcpyAsync(y, g.nkY, need * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+// the same product for Krylov vectors that already live on THIS device (PETSc VECCUDA: VecCUDAGetArrayRead /
+// VecCUDAGetArrayWrite): no PCIe traffic; the result is complete when the call returns
+int adfb_mffd_apply_device(const double* aDev, double* yDev, long long n, double h) {
+    NEED_INIT();
+    if (!g.nkHaveBase) return fail("adfb_mffd_apply_device: adfb_mffd_set_base has not been called");
+    const long long need = adfb_state_size();
+    if (!aDev || !yDev || n != need || (size_t)need > g.nkN)
+        return fail("adfb_mffd_apply_device: vector length %lld != local state size %lld", n, need);
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, aDev) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != g.device)
+        return fail("adfb_mffd_apply_device: a is not a device pointer of device %d", g.device);
+    if (cudaPointerGetAttributes(&at, yDev) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != g.device)
+        return fail("adfb_mffd_apply_device: y is not a device pointer of device %d", g.device);
+    CK(cudaMemcpyAsync(g.nkA, aDev, need * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+    const int rc = mffd_core(need, h);
+    if (rc == 1) return 1;
+    if (rc == 2) CK(cudaMemsetAsync(yDev, 0, need * sizeof(double), g.stream));
+    else CK(cudaMemcpyAsync(yDev, g.nkY, need * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     return 0;
 }

@@ -246,5 +246,9 @@ class ADFLOW_B200:
         check(self.L.adfb_mffd_apply(a.ctypes.data, y.ctypes.data, a.size, float(h)), "adfb_mffd_apply")
         return y
 
+    def mffdApplyDevice(self, a_ptr, y_ptr, n, h=-1.0):
+        """the same product for vectors resident on this GPU (raw device pointers, e.g. torch.Tensor.data_ptr())"""
+        check(self.L.adfb_mffd_apply_device(a_ptr, y_ptr, int(n), float(h)), "adfb_mffd_apply_device")
+
     def mffdLastH(self):
         return float(self.L.adfb_mffd_last_h())

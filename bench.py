@@ -370,6 +370,21 @@ def main():
             s.mffdApply(a, 1e-7, out=y)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3 / nrep
+        da = torch.from_numpy(a.copy()).cuda()
+        dy = torch.empty_like(da)
+        s.mffdApplyDevice(da.data_ptr(), dy.data_ptr(), da.numel(), 1e-7)
+        torch.cuda.synchronize()
+        assert float((dy.cpu() - torch.from_numpy(y)).abs().max()) == 0.0   # same product as through host vectors
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            s.mffdApplyDevice(da.data_ptr(), dy.data_ptr(), da.numel(), 1e-7)
+        torch.cuda.synchronize()
+        msd = (time.perf_counter() - t0) * 1e3 / nrep
+        others["mffd_matvec_device_vectors"] = {
+            "ms": msd, "Mcells/s": cells / (msd * 1e-3) / 1e6, "algorithmic_bytes_per_cell": 464.0,
+            "GB/s": 464.0 * cells / (msd * 1e-3) / 1e9, "frac_of_hbm_peak": 464.0 * cells / (msd * 1e-3) / 1e9 / peaks()[0],
+            "note": "a and y resident on the GPU (adfb_mffd_apply_device, the PETSc VECCUDA path): perturb + full residual "
+                    "(blocketteRes incl. BCs) + difference, no PCIe"}
         others["mffd_matvec_host_vectors"] = {
             "ms": ms, "Mcells/s": cells / (ms * 1e-3) / 1e6, "algorithmic_bytes_per_cell": 464.0,
             "GB/s": 464.0 * cells / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 464.0 * cells / (ms * 1e-3) / 1e9 / peaks()[0],

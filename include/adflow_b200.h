@@ -224,6 +224,9 @@ int adfb_mffd_set_base(const double* U, long long n);
    h > 0 is used as given; h <= 0 selects PETSc's default Walker-Pernice
    h = sqrt(eps) * sqrt(1 + ||U||) / ||a|| (norms reduced on the device, all-reduced). */
 int adfb_mffd_apply(const double* a, double* y, long long n, double h);
+/* the same product for vectors that already live on this device (e.g. PETSc VECCUDA arrays from
+   VecCUDAGetArrayRead / VecCUDAGetArrayWrite inside the MatShell's MATOP_MULT): no host copies */
+int adfb_mffd_apply_device(const double* aDev, double* yDev, long long n, double h);
 double adfb_mffd_last_h(void);
 
 /* ---- halo exchange (src/utils/haloExchange.F90) ---------------------------- */

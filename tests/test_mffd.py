@@ -71,3 +71,32 @@ def test_mffd_walker_pernice_h_and_fd_consistency(cuda_lib):
     hc = 1e-6 / np.abs(a).max()
     yc = (oracle_form_function(prm, hb, U + hc * a) - oracle_form_function(prm, hb, U - hc * a)) / (2 * hc)
     assert rel_l2(y, yc) < 5e-3
+
+
+def test_mffd_device_vectors_equal_host_vectors(cuda_lib):
+    """adfb_mffd_apply_device (vectors resident on the GPU, the PETSc VECCUDA path) gives bit-identical results"""
+    import torch
+
+    prm, hb = case(11, 9, 8)
+    s = ADFLOW_B200(prm)
+    try:
+        s.addBlock(hb)
+        U = s.getStates()
+        s.mffdSetBase(U)
+        a = np.random.default_rng(3).standard_normal(U.size)
+        y_host = s.mffdApply(a, 1e-7)
+        da = torch.from_numpy(a).cuda()
+        dy = torch.zeros_like(da)
+        s.mffdApplyDevice(da.data_ptr(), dy.data_ptr(), da.numel(), 1e-7)
+        assert np.array_equal(dy.cpu().numpy(), y_host)
+        # Walker-Pernice h on the device, and the a == 0 shortcut
+        s.mffdApplyDevice(da.data_ptr(), dy.data_ptr(), da.numel(), -1.0)
+        assert s.mffdLastH() > 0 and np.array_equal(dy.cpu().numpy(), s.mffdApply(a, -1.0))
+        dz = torch.zeros_like(da)
+        s.mffdApplyDevice(dz.data_ptr(), dy.data_ptr(), da.numel(), -1.0)
+        assert float(dy.abs().max()) == 0.0
+        # host pointers are rejected loudly
+        import ctypes as C
+        assert s.L.adfb_mffd_apply_device(a.ctypes.data, a.ctypes.data, a.size, 1e-7) != 0
+    finally:
+        s.close()
