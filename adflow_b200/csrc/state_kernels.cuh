@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) k_shock(Dims d, BlockDev b) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.N) return;
     const double p = b.p[c];
-    b.shock[c] = (c_prm.equations == ADFB_EULER) ? p : p / pow(b.w[c], c_prm.gammaInf);
+    // pressure for Euler and for matrix dissipation, entropy otherwise (adjointUtils.F90:1930-1947)
+    b.shock[c] = (c_prm.equations == ADFB_EULER || c_prm.spaceDiscr == ADFB_DISS_MATRIX) ? p : p / pow(b.w[c], c_prm.gammaInf);
 }
 
 // computeEtotBlock(2,il,2,jl,2,kl) (src/utils/flowUtils.F90:551-672, cpConstant)

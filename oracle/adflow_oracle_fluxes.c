@@ -208,12 +208,16 @@ void orc_upwind_flux(const OrcBlock* b, const AdfbParams* prm, double rFil) {
 /* Approximate (preconditioner / ANK) flux variants, src/NKSolver/blockette.F90:
    inviscidDissFluxScalarApprox :4367-4617, inviscidDissFluxMatrixApprox :4619-5166,
    viscousFluxApprox :6467-6837.  The sensor is the FROZEN shockSensor array
-   (referenceShockSensor, src/adjoint/adjointUtils.F90:1900-1950), first-order differences,
-   fourth-difference dissipation lumped into the second with `sigma`. */
+   (referenceShockSensor, src/adjoint/adjointUtils.F90:1909-1969), first-order differences,
+   fourth-difference dissipation lumped into the second with `sigma`.
+   The sensor is the pressure for Euler AND for matrix dissipation (:1930), the entropy otherwise; the
+   reference fills only the cells the dissipation stencils read (no edge/corner halos, :1941-1965), here the
+   whole box is filled -- the extra cells are never read. */
 void orc_reference_shock_sensor(const OrcBlock* b, const AdfbParams* prm) {
     Dims d = dims_of(b);
+    int pressure = prm->equations == ADFB_EULER || prm->spaceDiscr == ADFB_DISS_MATRIX;
     for (long c = 0; c < d.N; c++)
-        b->shock[c] = prm->equations == ADFB_EULER ? b->p[c] : b->p[c] / pow(W(c, IRHO), prm->gammaInf);
+        b->shock[c] = pressure ? b->p[c] : b->p[c] / pow(W(c, IRHO), prm->gammaInf);
 }
 
 static void diss_scalar_approx_dir(const OrcBlock* b, const AdfbParams* prm, Dims d, const double* rad, const double* dss,

@@ -134,6 +134,7 @@ def env_arrays():
     arrs["bp_bctype"] = A("bp_bctype", "int", [("1", "64")])
     arrs["bp_bcfaceid"] = A("bp_bcfaceid", "int", [("1", "64")])
     arrs["winf"] = A("winf", "double", [("1", "10")])
+    arrs["monloc"] = A("monloc", "double", [("1", "16")])
     # inputPhysics / inputCostFunctions data of the surface integration
     arrs["veldirfreestream"] = A("veldirfreestream", "double", [("1", "3")])
     arrs["pointref"] = A("pointref", "double", [("1", "3")])
@@ -166,7 +167,8 @@ UNITS = [
                                            "etot", "eint"], ("USE_TAPENADE",)),
     ("NKSolver/blockette.F90", "", ROUTINES, ()),
     ("modules/BCPointers.F90", "bcpointers_", [], ("USE_TAPENADE",)),
-    ("utils/utils.F90", "", ["setbcpointers"], ()),
+    ("utils/utils.F90", "", ["setbcpointers", "sumresiduals", "sumallresiduals"], ()),
+    ("adjoint/adjointUtils.F90", "adjointutils_", ["referenceshocksensor"], ()),
     ("solver/BCRoutines.F90", "bcroutines_", ["applyallbc", "applyallbc_block", "bcsymm1sthalo", "bcsymm2ndhalo", "bcnswalladiabatic",
                                               "bcnswallisothermal", "bcfarfield", "bceulerwall", "bcextrap", "bcsubsonicoutflow",
                                               "bcsubsonicinflow", "bcsupersonicinflow",

@@ -41,6 +41,7 @@ double alfaturb;
 int bp_nbocos = 0, bp_nviscbocos = 0, bp_bctype[64], bp_bcfaceid[64];
 int viscwallbctreatment = 1, eulerwallbctreatment = 1, outflowtreatment = 1, wallfunctions = 0, hscalinginlet = 0;
 double winf[10];
+double monloc[16];
 double *bp_s;
 int *bp_globalcell;
 double *bp_bvti1, *bp_bvti2, *bp_bvtj1, *bp_bvtj2, *bp_bvtk1, *bp_bvtk2;

@@ -62,6 +62,7 @@ void terminate(const char* routine, const char* msg); /* src/utils/utils.F90 ter
 extern int bp_nbocos, bp_nviscbocos, bp_bctype[64], bp_bcfaceid[64];
 extern int viscwallbctreatment, eulerwallbctreatment, outflowtreatment, wallfunctions, hscalinginlet;
 extern double winf[10];
+extern double monloc[16];   /* module monitor: local residual sums */
 extern double *bp_s;
 extern int *bp_globalcell;
 extern double *bp_bvti1, *bp_bvti2, *bp_bvtj1, *bp_bvtj2, *bp_bvtk1, *bp_bvtk2;

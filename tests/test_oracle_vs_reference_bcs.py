@@ -144,3 +144,42 @@ def test_metrics_and_volumes(right_handed):
         sl = d.ref_slices(n) + (slice(None),)
         assert np.array_equal(r.a[n][sl], getattr(ho, n)[sl]), n
         assert np.abs(getattr(ho, n)[sl]).max() > 0
+
+
+@pytest.mark.parametrize("opt", [{"equationType": "Euler"}, {"equationType": "RANS"},
+                                 {"equationType": "RANS", "discretization": "central plus matrix dissipation"},
+                                 {"equationType": "laminar NS", "discretization": "upwind"}])
+def test_reference_shock_sensor(opt):
+    """referenceShockSensor (src/adjoint/adjointUtils.F90:1909-1969): pressure for Euler and matrix dissipation,
+    entropy otherwise; compared on the cells the reference fills (owned i/j columns incl. their halos, all k)"""
+    from oracle.pyoracle import Oracle
+
+    prm, hb = case(9, 8, 7, opt)
+    ho = hb.copy()
+    Oracle(ho, prm).reference_shock_sensor()
+    hb.shock[...] = -7.0
+    r = rb.call(hb, prm, "adjointutils_referenceshocksensor")
+    got = r.a["shocksensor"]
+    filled = got != -7.0
+    d = hb.d
+    assert filled[2:d.il + 1, 2:d.jl + 1, :].all() and filled[0:2, 2:d.jl + 1, 2:d.kl + 1].all()
+    assert np.array_equal(got[filled], ho.shock[filled])
+
+
+def test_residual_norms():
+    """sumResiduals / sumAllResiduals (src/utils/utils.F90:6364-6459): the two monitored sums of getCurrentResidual"""
+    import ctypes as C
+
+    from oracle.pyoracle import Oracle
+
+    prm, hb = case(9, 8, 7, {"equationType": "RANS"})
+    o = Oracle(hb, prm)
+    o.residual_core(8 | 16)
+    want = o.norms()
+    mon0 = (C.c_double * 16).in_dll(rb.lib(), "monloc")
+    for q in range(16):
+        mon0[q] = 0.0                            # monLoc accumulates
+    rb.call(hb, prm, "sumresiduals", 1, 1)      # (nn = irho, mm = 1)
+    rb.again("sumallresiduals", 2)
+    mon = (C.c_double * 16).in_dll(rb.lib(), "monloc")
+    assert mon[0] == want[0] and mon[1] == want[1]
