@@ -70,6 +70,7 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  bp_righthanded bp_sectionid bp_blockismoving bp_nbkglobal bp_nbocos bp_nviscbocos
  viscwallbctreatment eulerwallbctreatment outflowtreatment wallfunctions
  spectralsol computesepsensorks computecavitation cavexponent rvfn hscalinginlet totalconditions massflow
+ lumpeddiss viscpc spacediscrcoarse smoother rungekutta dadi
  symm symmpolar nswalladiabatic nswallisothermal farfield eulerwall extrap supersonicinflow supersonicoutflow
  subsonicinflow subsonicoutflow massbleedoutflow imin imax jmin jmax kmin kmax
  constantpressure linextrapolpressure quadextrapolpressure normalmomentum""".split()
@@ -111,6 +112,7 @@ def env_arrays():
     arrs["bp_dw"] = refarr("dw", "double", *c2, ncomp="nw")
     arrs["bp_fw"] = refarr("fw", "double", *c2, ncomp="nwf")
     arrs["bp_scratch"] = refarr("scratch", "double", *c2, ncomp=10)
+    arrs["bp_wr"] = refarr("wr", "double", *c0, ncomp="nwf")
     arrs["bp_x"] = refarr("x", "double", ("0", "0", "0"), ("bp_ie", "bp_je", "bp_ke"), ncomp=3)
     arrs["bp_si"] = refarr("si", "double", ("0", "1", "1"), ("bp_ie", "bp_je", "bp_ke"), ncomp=3)
     arrs["bp_sj"] = refarr("sj", "double", ("1", "0", "1"), ("bp_ie", "bp_je", "bp_ke"), ncomp=3)
@@ -164,7 +166,7 @@ UNITS = [
     # USE_TAPENADE (the reference's own switch for its AD-differentiable subset) drops the cp-curve-fit
     # branches of eint/computeEtotBlock, which need tables outside the path (cpModel == cpConstant here)
     ("utils/flowUtils.F90", "flowutils_", ["computeetotblock", "computelamviscosity", "computepressuresimple",
-                                           "etot", "eint"], ("USE_TAPENADE",)),
+                                           "etot", "eint", "computespeedofsoundsquared", "allnodalgradients"], ("USE_TAPENADE",)),
     ("NKSolver/blockette.F90", "", ROUTINES, ()),
     ("modules/BCPointers.F90", "bcpointers_", [], ("USE_TAPENADE",)),
     ("utils/utils.F90", "", ["setbcpointers", "sumresiduals", "sumallresiduals"], ()),
@@ -182,11 +184,18 @@ UNITS = [
     ("turbulence/sa.F90", "sa_", ["sa_block", "sasource", "saviscous", "saresscale", "sasolve"], ()),
     ("solver/residuals.F90", "residuals_", ["residualaveraging", "computedwdadi", "tridiagsolve"], ()),
     ("solver/smoothers.F90", "smoothers_", ["executerkstage", "executedadistep"], ()),
+    # the block-path residual of the smoother loops: fluxes.F90 (block twins of the blockette routines) and
+    # residual_block / initres_block; USE_TAPENADE drops the ALE hooks and the coarse-grid dissipation calls
+    ("solver/fluxes.F90", "fluxes_", ["inviscidcentralflux", "invisciddissfluxscalar", "invisciddissfluxmatrix", "inviscidupwindflux",
+                                      "viscousflux", "invisciddissfluxscalarapprox", "invisciddissfluxmatrixapprox",
+                                      "viscousfluxapprox"], ("USE_TAPENADE",)),
+    ("solver/residuals.F90", "residuals_", ["residual_block", "initres_block"], ("USE_TAPENADE",), "residuals_block_ref.c"),
 ]
 RENAME_MODULES = {"blockpointers": "bp_", "flowutils": "flowutils_", "turbutils": "turbutils_",
                   "residuals": "residuals_", "smoothers": "smoothers_", "sa": "sa_",
                   "bcpointers": "bcpointers_", "bcroutines": "bcroutines_",
-                  "turbbcroutines": "turbbcroutines_", "surfaceintegrations": "surfaceintegrations_"}
+                  "turbbcroutines": "turbbcroutines_", "surfaceintegrations": "surfaceintegrations_",
+                  "fluxes": "fluxes_"}
 
 
 def main():
@@ -200,11 +209,12 @@ def main():
     outdir = os.path.join(HERE, "_ref")
     os.makedirs(outdir, exist_ok=True)
     tr = None
-    for rel, prefix, routines, defined in UNITS:
+    for unit in UNITS:
+        rel, prefix, routines, defined = unit[:4]
         src = os.path.join(ref, "src", rel)
         code, tr = f90toc.translate_module(src, only=set(routines), env=env, rename_modules=RENAME_MODULES,
                                            patches=PATCHES, defined=defined, tr=tr, prefix=prefix)
-        out = os.path.join(outdir, os.path.basename(rel).replace(".F90", "").lower() + "_ref.c")
+        out = os.path.join(outdir, unit[4] if len(unit) > 4 else os.path.basename(rel).replace(".F90", "").lower() + "_ref.c")
         with open(out, "w") as f:
             f.write(code)
         print("make_ref: wrote %s (%d lines)" % (out, code.count("\n")))

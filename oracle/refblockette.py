@@ -71,6 +71,7 @@ def set_params(prm, nw, rfil=1.0):
     _seti("orderturb", 2 if prm.secondOrdTurb else 1); _seti("precond", 1); _seti("riemann", 1)
     _seti("riemanncoarse", 1); _seti("approxsa", prm.approxSA)
     _seti("usedisscontinuation", 0); _seti("currentlevel", 1); _seti("groundlevel", 1)
+    _seti("lumpeddiss", 0); _seti("viscpc", 0); _seti("spacediscrcoarse", _REF_SPACEDISCR[prm.spaceDiscr]); _seti("smoother", 1)
     _seti("ntimeintervalsspectral", 1); _seti("oversetpresent", 0)
     for n in ("pInfCorr", "rhoInf", "gammaInf", "RGas", "prandtl", "prandtlTurb", "vis2", "vis4", "sigma", "adis",
               "acousticScaleFactor", "kappaCoef", "rsaK", "rsaCb1", "rsaCb2", "rsaCb3", "rsaCv1", "rsaCw1", "rsaCw2",
@@ -208,6 +209,7 @@ class RefBlock:
             self.a[n] = np.zeros(box, order="F")
         self.a["dw"] = f(hb.dw.copy(order="F"))
         self.a["fw"] = np.zeros(box + (5,), order="F")
+        self.a["wr"] = np.zeros(box + (5,), order="F")
         self.a["wn"] = f(hb.wn.copy(order="F"))
         self.a["pn"] = f(hb.pn.copy(order="F"))
         self.a["scratch"] = f(hb.scratch.copy(order="F"))
@@ -301,6 +303,11 @@ def wall_forces(hb, prm, ref_point=(0.0, 0.0, 0.0), p_ref=1.0):
             lib().surfaceintegrations_wallintegrationface(local, C.byref(C.c_int(mm)))
     v = np.array(list(local))
     return np.stack([v[cst[k] - 1:cst[k] + 2] for k in ("ifp", "ifv", "imp", "imv")])
+
+
+def set_int(name, value):
+    """set an integer module variable of the translated reference (e.g. "rkstage") between calls"""
+    _seti(name, value)
 
 
 def call_core(flags=FLAG_FLOW | FLAG_TURB):

@@ -137,3 +137,29 @@ def test_sa_block_ddadi(shape, opt):
     _eq(r.a["w"][..., 5], ho.w[..., 5], "nuTilde after the DD-ADI update and the turbulence BCs (whole box)")
     _eq(r.a["rev"], ho.rev, "rev")
     assert np.abs(ho.w[ow][..., 5] - hb.w[ow][..., 5]).max() > 0.0
+
+
+@pytest.mark.parametrize("opt", [{"equationType": "Euler"}, {"equationType": "RANS"},
+                                 {"equationType": "RANS", "discretization": "central plus matrix dissipation"},
+                                 {"equationType": "laminar NS", "discretization": "upwind"}])
+def test_block_residual_with_persistent_fw(opt):
+    """initres_block + residual_block (src/solver/residuals.F90:4-346, 427-955) with the block flux routines of
+    src/solver/fluxes.F90 over three Runge-Kutta stages: rFil = cdisRK(rkStage+1) = 1, 0, 0.56 -- the dissipative /
+    viscous part fw persists between the stages and is blended with (1 - rFil)"""
+    prm, hb = case(11, 9, 10, opt)
+    ho, o = _oracle(hb, prm)
+    ho.fw[...] = 0.0
+    first = True
+    ow = hb.d.owned()
+    for stage in (0, 1, 2):
+        o.residual_block(prm.cdisRK[stage])
+        if first:
+            r = rb.call(hb, prm, "residuals_initres_block", 1, 5, 1, 1, rkstage=stage)
+            first = False
+        else:
+            rb.set_int("rkstage", stage)
+            r = rb.again("residuals_initres_block", 1, 5, 1, 1)
+        r = rb.again("residuals_residual_block")
+        for l in range(5):
+            _eq(r.a["dw"][ow][..., l], ho.dw[ow][..., l], "stage %d dw[%d]" % (stage, l))
+            _eq(r.a["fw"][ow][..., l], ho.fw[ow][..., l], "stage %d fw[%d]" % (stage, l))
