@@ -44,6 +44,8 @@ PATCHES = [
     ("block", r"^testwallfunctions: if", r"^end if testwallfunctions"),
     # ALE (deforming-mesh unsteady) hooks of applyAllBC: steady path, both return at once in the reference
     (r"^call interplevelalebc_block$", "continue"),
+    # actuator-zone source terms (sourceTerms): no actuator regions on the path
+    (r"^call sourceterms\(\)$", "continue"),
     (r"^call recoverlevelalebc_block$", "continue"),
     # wallIntegrationFace: per-face output arrays of BCData (Fp, Fv, area: post-processing only) are not kept
     (r"^bcdata\(mm\)%(fp|fv|area)\b.*=.*$", "continue"),
@@ -70,7 +72,7 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  bp_righthanded bp_sectionid bp_blockismoving bp_nbkglobal bp_nbocos bp_nviscbocos
  viscwallbctreatment eulerwallbctreatment outflowtreatment wallfunctions
  spectralsol computesepsensorks computecavitation cavexponent rvfn hscalinginlet totalconditions massflow
- lumpeddiss viscpc spacediscrcoarse smoother rungekutta dadi
+ lumpeddiss viscpc spacediscrcoarse smoother rungekutta dadi nrkstages nsubiterations subit
  symm symmpolar nswalladiabatic nswallisothermal farfield eulerwall extrap supersonicinflow supersonicoutflow
  subsonicinflow subsonicoutflow massbleedoutflow imin imax jmin jmax kmin kmax
  constantpressure linextrapolpressure quadextrapolpressure normalmomentum""".split()
@@ -182,8 +184,8 @@ UNITS = [
      ["applyallturbbcthisblock", "bceddynowall", "bceddywall", "bcturbfarfield", "bcturbinflow", "bcturbinterface",
       "bcturboutflow", "bcturbsymm", "bcturbtreatment", "bcturbwall", "turb2ndhalo"], ()),
     ("turbulence/sa.F90", "sa_", ["sa_block", "sasource", "saviscous", "saresscale", "sasolve"], ()),
-    ("solver/residuals.F90", "residuals_", ["residualaveraging", "computedwdadi", "tridiagsolve"], ()),
-    ("solver/smoothers.F90", "smoothers_", ["executerkstage", "executedadistep"], ()),
+    ("solver/residuals.F90", "residuals_", ["residualaveraging", "computedwdadi", "tridiagsolve", "initres", "residual"], ()),
+    ("solver/smoothers.F90", "smoothers_", ["executerkstage", "executedadistep", "rungekuttasmoother", "dadismoother"], ()),
     # the block-path residual of the smoother loops: fluxes.F90 (block twins of the blockette routines) and
     # residual_block / initres_block; USE_TAPENADE drops the ALE hooks and the coarse-grid dissipation calls
     ("solver/fluxes.F90", "fluxes_", ["inviscidcentralflux", "invisciddissfluxscalar", "invisciddissfluxmatrix", "inviscidupwindflux",

@@ -72,6 +72,7 @@ def set_params(prm, nw, rfil=1.0):
     _seti("riemanncoarse", 1); _seti("approxsa", prm.approxSA)
     _seti("usedisscontinuation", 0); _seti("currentlevel", 1); _seti("groundlevel", 1)
     _seti("lumpeddiss", 0); _seti("viscpc", 0); _seti("spacediscrcoarse", _REF_SPACEDISCR[prm.spaceDiscr]); _seti("smoother", 1)
+    _seti("nrkstages", prm.nRKStages)
     _seti("ntimeintervalsspectral", 1); _seti("oversetpresent", 0)
     for n in ("pInfCorr", "rhoInf", "gammaInf", "RGas", "prandtl", "prandtlTurb", "vis2", "vis4", "sigma", "adis",
               "acousticScaleFactor", "kappaCoef", "rsaK", "rsaCb1", "rsaCb2", "rsaCb3", "rsaCv1", "rsaCw1", "rsaCw2",
@@ -208,7 +209,7 @@ class RefBlock:
         for n in ("sfacei", "sfacej", "sfacek"):
             self.a[n] = np.zeros(box, order="F")
         self.a["dw"] = f(hb.dw.copy(order="F"))
-        self.a["fw"] = np.zeros(box + (5,), order="F")
+        self.a["fw"] = f(hb.fw.copy(order="F"))
         self.a["wr"] = np.zeros(box + (5,), order="F")
         self.a["wn"] = f(hb.wn.copy(order="F"))
         self.a["pn"] = f(hb.pn.copy(order="F"))
@@ -216,6 +217,9 @@ class RefBlock:
         self.a["dtl"] = f(hb.dtl.copy(order="F"))
         for n in self.OUT[2:]:
             self.a[n] = np.zeros(box, order="F")
+        # spectral radii and speed of sound are INPUTS of the block-path residual (computed by timeStep)
+        for ref, mine in (("radi", "radI"), ("radj", "radJ"), ("radk", "radK"), ("aa", "aa")):
+            self.a[ref] = f(getattr(hb, mine).copy(order="F"))
         # turbulence BC matrices per block face (block.F90 bmti1(je,ke,nt1:nt2,nt1:nt2) ...); `bmt` is a box
         # array holding the scalar SA value of each boundary face at its first-halo cell
         if bmt is None:

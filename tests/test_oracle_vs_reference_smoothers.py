@@ -147,6 +147,10 @@ def test_block_residual_with_persistent_fw(opt):
     src/solver/fluxes.F90 over three Runge-Kutta stages: rFil = cdisRK(rkStage+1) = 1, 0, 0.56 -- the dissipative /
     viscous part fw persists between the stages and is blended with (1 - rFil)"""
     prm, hb = case(11, 9, 10, opt)
+    from oracle.pyoracle import Oracle
+
+    Oracle(hb, prm).time_step(True)        # spectral radii: inputs of the dissipation
+    assert np.abs(hb.radI).max() > 0
     ho, o = _oracle(hb, prm)
     ho.fw[...] = 0.0
     first = True
@@ -163,3 +167,53 @@ def test_block_residual_with_persistent_fw(opt):
         for l in range(5):
             _eq(r.a["dw"][ow][..., l], ho.dw[ow][..., l], "stage %d dw[%d]" % (stage, l))
             _eq(r.a["fw"][ow][..., l], ho.fw[ow][..., l], "stage %d fw[%d]" % (stage, l))
+
+
+@pytest.mark.parametrize("opt", [{"equationType": "Euler", "nRKStages": 3}, {"equationType": "RANS"},
+                                 {"equationType": "RANS", "resAveraging": "never", "nRKStages": 4},
+                                 {"equationType": "laminar NS", "discretization": "central plus matrix dissipation"}])
+def test_full_runge_kutta_cycle(opt):
+    """RungeKuttaSmoother (src/solver/smoothers.F90:4-86) end to end: stage updates, residual averaging, the
+    reference's own applyAllBC after every stage, initres + residual with the stage's cdisRK between the stages.
+    Everything in the loop is the translated reference; only the halo exchange is a no-op (one block)."""
+    prm, hb = _residual_state((12, 9, 10), opt)
+    hb.subfaces.sort(key=lambda s_: 0 if s_["bcType"] in (2, 6) else 1)
+    hb.fw[...] = 0.0
+    from oracle.pyoracle import Oracle
+
+    Oracle(hb, prm).residual_block(prm.cdisRK[0])     # entry state of the smoother: residual of stage 0 incl. fw
+    ho, o = _oracle(hb, prm)
+    o.rk_smoother()
+    r = rb.call(hb, prm, "smoothers_rungekuttasmoother")
+    r.a["fw"][...]  # noqa: B018  (bound array)
+    for l in range(5):
+        _eq(r.a["w"][..., l], ho.w[..., l], "w[%d]" % l)
+    _eq(r.a["p"], ho.p, "p")
+    ow = hb.d.owned()
+    _eq(r.a["dw"][ow][..., :5], ho.dw[ow][..., :5], "dw of the last residual")
+    assert np.abs(ho.w[ow][..., :5] - hb.w[ow][..., :5]).max() > 0
+
+
+@pytest.mark.parametrize("opt", [{"equationType": "Euler"}, {"equationType": "RANS"}])
+def test_full_dadi_smoother(opt):
+    """DADISmoother (src/solver/smoothers.F90:383-421) with nSubiterations = 2: step, initres + residual (rFil = 1
+    for smoother == DADI), step -- everything inside is the translated reference"""
+    o_ = dict(opt)
+    o_["smoother"] = "DADI"
+    prm, hb = _residual_state((10, 12, 9), o_)
+    hb.subfaces.sort(key=lambda s_: 0 if s_["bcType"] in (2, 6) else 1)
+    ho, o = _oracle(hb, prm)
+    o.dadi_step(); o.residual_block(1.0); o.dadi_step()
+    import ctypes as C
+
+    rb.set_params(prm, hb.nw)
+    rb.set_int("smoother", 2); rb.set_int("nsubiterations", 2); rb.set_int("rkstage", 0)
+    r = rb.RefBlock(hb, prm)
+    r.bind()
+    r.keep = rb.bind_bcs(hb, prm)
+    rb._BOUND = r
+    rb.lib().smoothers_dadismoother()
+    rb.set_int("smoother", 1); rb.set_int("nsubiterations", 1)
+    for l in range(5):
+        _eq(r.a["w"][..., l], ho.w[..., l], "w[%d]" % l)
+    _eq(r.a["p"], ho.p, "p")
