@@ -72,7 +72,7 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  bp_righthanded bp_sectionid bp_blockismoving bp_nbkglobal bp_nbocos bp_nviscbocos
  viscwallbctreatment eulerwallbctreatment outflowtreatment wallfunctions
  spectralsol computesepsensorks computecavitation cavexponent rvfn hscalinginlet totalconditions massflow
- lumpeddiss viscpc spacediscrcoarse smoother rungekutta dadi nrkstages nsubiterations subit
+ lumpeddiss viscpc spacediscrcoarse smoother rungekutta dadi nrkstages nsubiterations subit radiineededfine radiineededcoarse dirscaling
  symm symmpolar nswalladiabatic nswallisothermal farfield eulerwall extrap supersonicinflow supersonicoutflow
  subsonicinflow subsonicoutflow massbleedoutflow imin imax jmin jmax kmin kmax
  constantpressure linextrapolpressure quadextrapolpressure normalmomentum""".split()
@@ -188,6 +188,7 @@ UNITS = [
     ("solver/smoothers.F90", "smoothers_", ["executerkstage", "executedadistep", "rungekuttasmoother", "dadismoother"], ()),
     # the block-path residual of the smoother loops: fluxes.F90 (block twins of the blockette routines) and
     # residual_block / initres_block; USE_TAPENADE drops the ALE hooks and the coarse-grid dissipation calls
+    ("solver/solverUtils.F90", "solverutils_", ["timestep_block"], ("USE_TAPENADE",)),
     ("solver/fluxes.F90", "fluxes_", ["inviscidcentralflux", "invisciddissfluxscalar", "invisciddissfluxmatrix", "inviscidupwindflux",
                                       "viscousflux", "invisciddissfluxscalarapprox", "invisciddissfluxmatrixapprox",
                                       "viscousfluxapprox"], ("USE_TAPENADE",)),
@@ -197,7 +198,7 @@ RENAME_MODULES = {"blockpointers": "bp_", "flowutils": "flowutils_", "turbutils"
                   "residuals": "residuals_", "smoothers": "smoothers_", "sa": "sa_",
                   "bcpointers": "bcpointers_", "bcroutines": "bcroutines_",
                   "turbbcroutines": "turbbcroutines_", "surfaceintegrations": "surfaceintegrations_",
-                  "fluxes": "fluxes_"}
+                  "fluxes": "fluxes_", "solverutils": "solverutils_"}
 
 
 def main():

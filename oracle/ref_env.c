@@ -41,7 +41,7 @@ double alfaturb;
 int bp_nbocos = 0, bp_nviscbocos = 0, bp_bctype[64], bp_bcfaceid[64];
 int viscwallbctreatment = 1, eulerwallbctreatment = 1, outflowtreatment = 1, wallfunctions = 0, hscalinginlet = 0;
 double winf[10];
-int lumpeddiss = 0, viscpc = 0, spacediscrcoarse = 1, smoother = 1 /* RungeKutta */, nrkstages = 5, nsubiterations = 1, subit = 0;
+int lumpeddiss = 0, viscpc = 0, spacediscrcoarse = 1, smoother = 1 /* RungeKutta */, nrkstages = 5, nsubiterations = 1, subit = 0, radiineededfine = 1, radiineededcoarse = 1, dirscaling = 1;
 double* bp_wr;
 double monloc[16];
 double *bp_s;

@@ -62,7 +62,7 @@ void terminate(const char* routine, const char* msg); /* src/utils/utils.F90 ter
 extern int bp_nbocos, bp_nviscbocos, bp_bctype[64], bp_bcfaceid[64];
 extern int viscwallbctreatment, eulerwallbctreatment, outflowtreatment, wallfunctions, hscalinginlet;
 extern double winf[10];
-extern int lumpeddiss, viscpc, spacediscrcoarse, smoother, nrkstages, nsubiterations, subit;   /* iteration / inputDiscretization / inputIteration */
+extern int lumpeddiss, viscpc, spacediscrcoarse, smoother, nrkstages, nsubiterations, subit, radiineededfine, radiineededcoarse, dirscaling;   /* iteration / inputDiscretization / inputIteration */
 extern double* bp_wr;
 extern double monloc[16];   /* module monitor: local residual sums */
 extern double *bp_s;

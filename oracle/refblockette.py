@@ -73,6 +73,9 @@ def set_params(prm, nw, rfil=1.0):
     _seti("usedisscontinuation", 0); _seti("currentlevel", 1); _seti("groundlevel", 1)
     _seti("lumpeddiss", 0); _seti("viscpc", 0); _seti("spacediscrcoarse", _REF_SPACEDISCR[prm.spaceDiscr]); _seti("smoother", 1)
     _seti("nrkstages", prm.nRKStages)
+    # inputParamRoutines.F90:2824-2833: directional scaling and stored radii only with scalar dissipation
+    scalar = int(prm.spaceDiscr == 1)
+    _seti("dirscaling", scalar); _seti("radiineededfine", scalar); _seti("radiineededcoarse", scalar)
     _seti("ntimeintervalsspectral", 1); _seti("oversetpresent", 0)
     for n in ("pInfCorr", "rhoInf", "gammaInf", "RGas", "prandtl", "prandtlTurb", "vis2", "vis4", "sigma", "adis",
               "acousticScaleFactor", "kappaCoef", "rsaK", "rsaCb1", "rsaCb2", "rsaCb3", "rsaCv1", "rsaCw1", "rsaCw2",

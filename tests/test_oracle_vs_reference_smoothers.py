@@ -217,3 +217,23 @@ def test_full_dadi_smoother(opt):
     for l in range(5):
         _eq(r.a["w"][..., l], ho.w[..., l], "w[%d]" % l)
     _eq(r.a["p"], ho.p, "p")
+
+
+@pytest.mark.parametrize("disc", ["central plus scalar dissipation", "central plus matrix dissipation", "upwind"])
+@pytest.mark.parametrize("eq", ["Euler", "RANS"])
+def test_time_step_block(disc, eq):
+    """timeStep_block (src/solver/solverUtils.F90:43-355), the block twin used by the smoother loops: local time
+    step for every discretisation; the spectral radii are stored only where the reference needs them (scalar
+    dissipation, inputParamRoutines.F90:2824-2833)"""
+    from oracle.pyoracle import Oracle
+
+    prm, hb = case(9, 8, 7, {"equationType": eq, "discretization": disc})
+    ho = hb.copy()
+    Oracle(ho, prm).time_step(True)
+    r = rb.call(hb, prm, "solverutils_timestep_block", 0)
+    d = hb.d
+    _eq(r.a["dtl"][d.owned()], ho.dtl[d.owned()], "dtl")
+    if disc.startswith("central plus scalar"):
+        c1 = (slice(1, d.ie + 1), slice(1, d.je + 1), slice(1, d.ke + 1))
+        for ref, mine in (("radi", "radI"), ("radj", "radJ"), ("radk", "radK")):
+            _eq(r.a[ref][c1], getattr(ho, mine)[c1], ref)
