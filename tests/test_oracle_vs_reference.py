@@ -160,3 +160,18 @@ def test_runge_kutta_dissipation_fraction(rfil, disc):
     """rFil (iteration module): fraction of new dissipation / viscous flux at intermediate RK stages"""
     prm, hb = _prepare(10, 9, 11, {"equationType": "RANS", "discretization": disc})
     _compare_dw(prm, hb, FLOW | TURB, rfil=rfil)
+
+
+@pytest.mark.parametrize("disc", DISCS)
+def test_iblank_holes_fringes_and_porosities(disc):
+    """overset blanking (iblank 0 = hole, -1 = fringe: residual multiplied by max(iblank, 0)) and the three face
+    porosities (normalFlux / boundFlux / noFlux) in the flux routines"""
+    prm, hb = _prepare(12, 10, 9, {"equationType": "RANS", "discretization": disc})
+    hb.iblank[4:7, 4:6, 3:5] = 0
+    hb.iblank[8, 8, 6] = -1
+    hb.iblank[2:4, 9, 2:5] = -1
+    hb.porI[5, 3:6, 4:7] = -1     # noFlux
+    hb.porJ[3:8, 6, 5] = 0        # boundFlux in the interior
+    hb.porK[6, 7, 2:9] = -1
+    _compare_dw(prm, hb, FLOW | TURB)
+    _compare_dw(prm, hb, FLOW | TURB | DISS_APPROX | VISC_APPROX)

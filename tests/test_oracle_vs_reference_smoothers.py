@@ -237,3 +237,27 @@ def test_time_step_block(disc, eq):
         c1 = (slice(1, d.ie + 1), slice(1, d.je + 1), slice(1, d.ke + 1))
         for ref, mine in (("radi", "radI"), ("radj", "radJ"), ("radk", "radK")):
             _eq(r.a[ref][c1], getattr(ho, mine)[c1], ref)
+
+
+def test_smoothers_with_iblank():
+    """blanked cells in the smoother stages: residual averaging (epz * max(iblank,0)), DADI (dual_dt * max(iblank,0))
+    and the SA solve (rblank)"""
+    from oracle.pyoracle import Oracle
+
+    prm, hb = _residual_state((12, 9, 10), {"equationType": "RANS", "resAveraging": "always"})
+    hb.iblank[4:7, 4:6, 3:5] = 0
+    hb.iblank[8, 8, 6] = -1
+    hb.subfaces.sort(key=lambda s_: 0 if s_["bcType"] in (2, 6) else 1)
+    Oracle(hb, prm).residual_block(1.0)
+    ho, o = _oracle(hb, prm)
+    o.rk_stage(1)
+    r = rb.call(hb, prm, "smoothers_executerkstage", rkstage=1)
+    _eq(r.a["w"], ho.w, "w after the RK stage")
+    ho, o = _oracle(hb, prm)
+    o.dadi_step()
+    r = rb.call(hb, prm, "smoothers_executedadistep", rkstage=0)
+    _eq(r.a["w"], ho.w, "w after the DADI step")
+    ho, o = _oracle(hb, prm)
+    o.sa_block()
+    r = rb.call(hb, prm, "sa_sa_block", 0)
+    _eq(r.a["w"][..., 5], ho.w[..., 5], "nuTilde after sa_block")
