@@ -848,6 +848,7 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
                 if (cudaEventCreateWithFlags(&s_fork, cudaEventDisableTiming) != cudaSuccess) return 1;
                 if (cudaEventCreateWithFlags(&s_join, cudaEventDisableTiming) != cudaSuccess) return 1;
             }
+            cudaStreamCopyAttributes(s_side, stream);   // same L2 access-policy window as the main stream
             cudaEventRecord(s_fork, stream);
             cudaStreamWaitEvent(s_side, s_fork, 0);
             k_sa<<<g, tr, 0, s_side>>>(d, b);
