@@ -120,3 +120,20 @@ static inline int adfb_part_lanes(int nl) {
 }
 #define KT_BEGIN(id, stream) g_kt.begin(id, stream)
 #define KT_END(id, stream) g_kt.end(id, stream)
+
+// ---------------------------------------------------------------------------
+// Launch with the programmatic-dependent-launch attribute (the kernel must call
+// cudaGridDependencySynchronize() before touching memory).  ADFB_PDL=0 falls back to a plain launch.
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kern)(KArgs...), dim3 g, dim3 tb, cudaStream_t s, Args... args) {
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("ADFB_PDL"); pdl = e ? atoi(e) : 1; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = g; cfg.blockDim = tb; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+

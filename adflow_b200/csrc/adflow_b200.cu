@@ -1060,7 +1060,7 @@ int adfb_timestep(int level, int onlyRadii) {
         dim3 tb(32, 4, 2);
         dim3 gr((b.d.NI + 31) / 32, (b.d.NJ + 3) / 4, (b.d.NK + 1) / 2);
         KT_BEGIN(K_PREP, g.stream);
-        k_prep<<<gr, tb, 0, g.stream>>>(b.d, b.dev, onlyRadii ? 0 : 1, 1);
+        launch_pdl(k_prep, gr, tb, g.stream, b.d, b.dev, onlyRadii ? 0 : 1, 1);
         KT_END(K_PREP, g.stream);
     }
     CK(cudaGetLastError());

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256) k_geom(Dims d, BlockDev b) {
 // k_prep: entropy (inviscidDissFluxScalar, blockette.F90:3055-3089), speed of sound squared
 // (:5168-5203), spectral radii and local time step (timeStep, :1899-2148).
 __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, int doRad) {
+    cudaGridDependencySynchronize();  // launched with programmatic stream serialization (launch_pdl)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = blockIdx.z * blockDim.z + threadIdx.z;
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
 // the reference's three scatter sweeps add, in this order:  -K(layer k) +K(layer k+1)
 // -J(layer j) +J(layer j+1) -I(layer i) +I(layer i+1), then scale by 1/(8 vol).
 __global__ void __launch_bounds__(NODAL_TPB, NODAL_MINB) k_nodal(Dims d, BlockDev b, int doGrad, int dissApprox) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 1;
@@ -566,6 +568,7 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
 // fd -> flux[dir*10 + 5 + l] (smoother path: fw persists between RK stages).
 template <bool VISCOUS, bool MERGED, int DISC, int APPROX, bool STOREWALL = false>
 __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDev b, double rFil, int doVisc, int doDiss) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 1;
@@ -760,6 +763,7 @@ __global__ void __launch_bounds__(SA_TPB, SA_MINB) k_sa(Dims d, BlockDev b) {
 // Order per variable: -Fi(c-1) +Fi(c) -Fj(c-sJ) +Fj(c) -Fk(c-sK) +Fk(c), like the reference's sweeps.
 template <bool MERGED>
 __global__ void __launch_bounds__(256) k_div(Dims d, BlockDev b, double rFil, int persistFw) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -863,14 +867,14 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
     if (doRad || (flowRes && doDiss)) {
         dim3 g((d.NI + tb.x - 1) / tb.x, (d.NJ + tb.y - 1) / tb.y, (d.NK + tb.z - 1) / tb.z);
         KT_BEGIN(K_PREP, stream);
-        k_prep<<<g, tb, 0, stream>>>(d, b, updateDt, doRad);
+        launch_pdl(k_prep, g, tb, stream, d, b, updateDt, doRad);
         KT_END(K_PREP, stream);
     }
     if (flowRes && doDiss) {
         dim3 tn = tune_block("ADFB_NODAL_BLOCK", dim3(32, 4, 2));
         dim3 g((d.ie + tn.x - 1) / tn.x, (d.je + tn.y - 1) / tn.y, (d.ke + tn.z - 1) / tn.z);
         KT_BEGIN(K_NODAL, stream);
-        k_nodal<<<g, tn, 0, stream>>>(d, b, doVisc && !viscApprox, dissApprox);
+        launch_pdl(k_nodal, g, tn, stream, d, b, (int)(doVisc && !viscApprox), dissApprox);
         KT_END(K_NODAL, stream);
     }
     if (flowRes) {
@@ -878,7 +882,7 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         dim3 g((d.il + tr.x - 1) / tr.x, (d.jl + tr.y - 1) / tr.y, (d.kl + tr.z - 1) / tr.z);
         const bool merged = !persistFw;
         KT_BEGIN(K_RESID, stream);
-#define ADFB_LAUNCH_FACES(V, M, D, A) k_faces<V, M, D, A><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss)
+#define ADFB_LAUNCH_FACES(V, M, D, A) launch_pdl(k_faces<V, M, D, A>, g, tr, stream, d, b, rFil, doVisc, doDiss)
 #define ADFB_FACES_DISC(V, M, A)                                           \
     do {                                                                   \
         if (prm.spaceDiscr == ADFB_DISS_SCALAR) ADFB_LAUNCH_FACES(V, M, ADFB_DISS_SCALAR, A); \
@@ -888,9 +892,9 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         const int approx = dissApprox | (viscApprox << 1);
         const bool storeWall = (flags & ADFB_RES_STORE_WALL) && viscous && doVisc && merged && approx == 0;
         if (storeWall) {  // exact viscous flux + viscSubface%tau/%q planes for the force integration
-            if (prm.spaceDiscr == ADFB_DISS_SCALAR) k_faces<true, true, ADFB_DISS_SCALAR, 0, true><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
-            else if (prm.spaceDiscr == ADFB_DISS_MATRIX) k_faces<true, true, ADFB_DISS_MATRIX, 0, true><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
-            else k_faces<true, true, ADFB_UPWIND, 0, true><<<g, tr, 0, stream>>>(d, b, rFil, doVisc, doDiss);
+            if (prm.spaceDiscr == ADFB_DISS_SCALAR) launch_pdl(k_faces<true, true, ADFB_DISS_SCALAR, 0, true>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+            else if (prm.spaceDiscr == ADFB_DISS_MATRIX) launch_pdl(k_faces<true, true, ADFB_DISS_MATRIX, 0, true>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+            else launch_pdl(k_faces<true, true, ADFB_UPWIND, 0, true>, g, tr, stream, d, b, rFil, doVisc, doDiss);
         } else if (approx == 0) {
             if (viscous) { if (merged) ADFB_FACES_DISC(true, true, 0); else ADFB_FACES_DISC(true, false, 0); }
             else { if (merged) ADFB_FACES_DISC(false, true, 0); else ADFB_FACES_DISC(false, false, 0); }
@@ -906,8 +910,8 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         KT_END(K_RESID, stream);
         dim3 g2((d.nx + tb.x - 1) / tb.x, (d.ny + tb.y - 1) / tb.y, (d.nz + tb.z - 1) / tb.z);
         KT_BEGIN(K_DIV, stream);
-        if (merged) k_div<true><<<g2, tb, 0, stream>>>(d, b, rFil, persistFw);
-        else k_div<false><<<g2, tb, 0, stream>>>(d, b, rFil, persistFw);
+        if (merged) launch_pdl(k_div<true>, g2, tb, stream, d, b, rFil, persistFw);
+        else launch_pdl(k_div<false>, g2, tb, stream, d, b, rFil, persistFw);
         KT_END(K_DIV, stream);
     }
     if (fork) cudaStreamWaitEvent(stream, s_join, 0);

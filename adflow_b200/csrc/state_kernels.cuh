@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256) k_metrics(Dims d, BlockDev b, double fact
 
 // p on [pLo,pHi] (owned, or 0:ib with halos), rlv/rev on [vLo,vHi] (owned, or 1:ie with halos)
 __global__ void __launch_bounds__(256) k_state_prep(Dims d, BlockDev b, int includeHalos, int nw, int etot) {
+    cudaGridDependencySynchronize();  // launched with programmatic stream serialization (launch_pdl)
     const int lo = includeHalos ? 0 : 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x + lo;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + lo;
@@ -236,7 +237,7 @@ static int launch_state_prep(const Dims& d, const BlockDev& b, const AdfbParams&
     const int ni = includeHalos ? d.NI : d.nx, nj = includeHalos ? d.NJ : d.ny, nk = includeHalos ? d.NK : d.nz;
     dim3 g((ni + tb.x - 1) / tb.x, (nj + tb.y - 1) / tb.y, (nk + tb.z - 1) / tb.z);
     KT_BEGIN(K_STATE, stream);
-    k_state_prep<<<g, tb, 0, stream>>>(d, b, includeHalos ? 1 : 0, prm.equations == ADFB_RANS ? 6 : 5, etot ? 1 : 0);
+    launch_pdl(k_state_prep, g, tb, stream, d, b, includeHalos ? 1 : 0, prm.equations == ADFB_RANS ? 6 : 5, etot ? 1 : 0);
     KT_END(K_STATE, stream);
     return (int)cudaGetLastError();
 }
