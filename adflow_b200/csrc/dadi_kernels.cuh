@@ -171,6 +171,7 @@ __device__ __forceinline__ void dadi_post(const BlockDev& b, int N, int c, doubl
 // 19..27 the tridiagonal rows per coefficient set (k_dadi_tri).
 template <int DIR>
 __global__ void __launch_bounds__(128) k_dadi_coef(Dims d, BlockDev b, int sd, double cfl) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(128) k_dadi_coef(Dims d, BlockDev b, int sd, d
 }
 
 __global__ void __launch_bounds__(128) k_dadi_post(Dims d, BlockDev b) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -212,6 +214,7 @@ __global__ void __launch_bounds__(128) k_dadi_post(Dims d, BlockDev b) {
 // tridiagonal rows of the three coefficient sets from the cell coefficients of the cell and its two line
 // neighbours (residuals.F90:1374-1391): work slots 19+t (diagonal), 22+t (sub-), 25+t (super-diagonal)
 __global__ void __launch_bounds__(256) k_dadi_tri(Dims d, BlockDev b, int sd, int dirIdx) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -233,6 +236,7 @@ __global__ void __launch_bounds__(256) k_dadi_tri(Dims d, BlockDev b, int sd, in
 
 // one thread = one grid line (nl owned cells along sd) of one variable n = blockIdx.z
 __global__ void __launch_bounds__(64) k_dadi_thomas(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2) {
+    cudaGridDependencySynchronize();
     const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int q2 = blockIdx.y + 2;
     if (q1 > n1 + 1 || q2 > n2 + 1) return;
@@ -307,40 +311,40 @@ static int launch_dadi(const Dims& d, const BlockDev& b, const AdfbParams& prm, 
     // serial walks already fill the machine and the partition method does 2.5x the arithmetic; it pays for the
     // single-system SA solve only, see sa_kernels.cuh)
     auto thomas = [&](int sd, int nl, int s1, int n1, int s2, int n2) {
-        k_dadi_thomas<<<dim3((n1 + 31) / 32, n2, 5), tb, 0, s>>>(d, b, sd, nl, s1, n1, s2, n2);
+        launch_pdl(k_dadi_thomas, dim3((n1 + 31) / 32, n2, 5), tb, s, d, b, sd, nl, s1, n1, s2, n2);
     };
     // j sweep
     KT_BEGIN(K_DADI, s);
-    k_dadi_coef<0><<<gc, tc, 0, s>>>(d, b, sJ, prm.cfl);
+    launch_pdl(k_dadi_coef<0>, gc, tc, s, d, b, sJ, prm.cfl);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
-    k_dadi_tri<<<gc, tc, 0, s>>>(d, b, sJ, 0);
+    launch_pdl(k_dadi_tri, gc, tc, s, d, b, sJ, 0);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
     thomas(sJ, d.ny, 1, d.nx, sK, d.nz);
     KT_END(K_DADI, s);
     // i sweep
     KT_BEGIN(K_DADI, s);
-    k_dadi_coef<1><<<gc, tc, 0, s>>>(d, b, 1, prm.cfl);
+    launch_pdl(k_dadi_coef<1>, gc, tc, s, d, b, 1, prm.cfl);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
-    k_dadi_tri<<<gc, tc, 0, s>>>(d, b, 1, 1);
+    launch_pdl(k_dadi_tri, gc, tc, s, d, b, 1, 1);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
     thomas(1, d.nx, sJ, d.ny, sK, d.nz);
     KT_END(K_DADI, s);
     // k sweep
     KT_BEGIN(K_DADI, s);
-    k_dadi_coef<2><<<gc, tc, 0, s>>>(d, b, sK, prm.cfl);
+    launch_pdl(k_dadi_coef<2>, gc, tc, s, d, b, sK, prm.cfl);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
-    k_dadi_tri<<<gc, tc, 0, s>>>(d, b, sK, 2);
+    launch_pdl(k_dadi_tri, gc, tc, s, d, b, sK, 2);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
     thomas(sK, d.nz, 1, d.nx, sJ, d.ny);
     KT_END(K_DADI, s);
     KT_BEGIN(K_DADI, s);
-    k_dadi_post<<<gc, tc, 0, s>>>(d, b);
+    launch_pdl(k_dadi_post, gc, tc, s, d, b);
     KT_END(K_DADI, s);
     return (int)cudaGetLastError();
 }

@@ -19,6 +19,7 @@
 namespace {
 
 __global__ void __launch_bounds__(128) k_sa_bmt(Dims d, BlockDev b, FaceDev f) {
+    cudaGridDependencySynchronize();
     const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
     const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
     if (ia > f.icEnd || jb > f.jcEnd) return;
@@ -67,6 +68,7 @@ __device__ __forceinline__ void sa_diff_coef(const BlockDev& b, int N, int c, in
 }
 
 __global__ void __launch_bounds__(128, 4) k_sa_rhs(Dims d, BlockDev b, double factor) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(128, 4) k_sa_rhs(Dims d, BlockDev b, double fa
 //   k_sa_thomas (one thread per line): backward elimination m = l..2 and forward substitution
 //               (:979-998) reading only precomputed arrays; eliminated diagonal / rhs in slots 3, 4
 __global__ void __launch_bounds__(128) k_sa_coef(Dims d, BlockDev b, int axis, int sd) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -215,6 +218,7 @@ __global__ void __launch_bounds__(128) k_sa_coef(Dims d, BlockDev b, int axis, i
 }
 
 __global__ void __launch_bounds__(64) k_sa_thomas(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2, int multiplyByQQ) {
+    cudaGridDependencySynchronize();
     const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int q2 = blockIdx.y + 2;
     if (q1 > n1 + 1 || q2 > n2 + 1) return;
@@ -280,6 +284,7 @@ __global__ void __launch_bounds__(64) k_sa_thomas(Dims d, BlockDev b, int sd, in
 // the same sweep with every line spread over P lanes (tridiag_part.cuh); LS = 32 / P lines per warp
 template <int P, int M>
 __global__ void __launch_bounds__(32) k_sa_thomas_part(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2, int multiplyByQQ) {
+    cudaGridDependencySynchronize();
     typedef PartThomas<P, M> PT;
     const int lane = threadIdx.x, p = lane / PT::LS, lw = lane % PT::LS;
     int line = blockIdx.x * PT::LS + lw;
@@ -318,6 +323,7 @@ __global__ void __launch_bounds__(32) k_sa_thomas_part(Dims d, BlockDev b, int s
 }
 
 __global__ void __launch_bounds__(256) k_sa_update(Dims d, BlockDev b) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -345,7 +351,7 @@ static int launch_sa_block(const Dims& d, const BlockDev& b, const AdfbParams& p
         dim3 tb(32, 4);
         dim3 g((f.icEnd - f.icBeg + 1 + 31) / 32, (f.jcEnd - f.jcBeg + 1 + 3) / 4);
         KT_BEGIN(K_SASOLVE, s);
-        k_sa_bmt<<<g, tb, 0, s>>>(d, b, f);
+        launch_pdl(k_sa_bmt, g, tb, s, d, b, f);
         KT_END(K_SASOLVE, s);
     }
     const double factor = 1.0 + (1.0 - prm.alfaTurb) / prm.alfaTurb;
@@ -353,20 +359,20 @@ static int launch_sa_block(const Dims& d, const BlockDev& b, const AdfbParams& p
         dim3 tr(32, 4, 1);
         dim3 g((d.nx + 31) / 32, (d.ny + 3) / 4, d.nz);
         KT_BEGIN(K_SASOLVE, s);
-        k_sa_rhs<<<g, tr, 0, s>>>(d, b, factor);
+        launch_pdl(k_sa_rhs, g, tr, s, d, b, factor);
         KT_END(K_SASOLVE, s);
     }
     const dim3 tl(32, 1), tc(32, 4, 1), gc((d.nx + 31) / 32, (d.ny + 3) / 4, d.nz);
     auto sweep = [&](int axis, int sd, int nl, int s1, int n1, int s2, int n2, int mult) {
         KT_BEGIN(K_SASOLVE, s);
-        k_sa_coef<<<gc, tc, 0, s>>>(d, b, axis, sd);
+        launch_pdl(k_sa_coef, gc, tc, s, d, b, axis, sd);
         KT_END(K_SASOLVE, s);
         KT_BEGIN(K_SASOLVE, s);
         const int part = adfb_part_lanes(nl);
-        if (part == 8 && nl <= 96) k_sa_thomas_part<8, 12><<<(n1 * n2 + 3) / 4, 32, 0, s>>>(d, b, sd, nl, s1, n1, s2, n2, mult);
-        else if (part == 8) k_sa_thomas_part<8, 16><<<(n1 * n2 + 3) / 4, 32, 0, s>>>(d, b, sd, nl, s1, n1, s2, n2, mult);
-        else if (part == 16) k_sa_thomas_part<16, 16><<<(n1 * n2 + 1) / 2, 32, 0, s>>>(d, b, sd, nl, s1, n1, s2, n2, mult);
-        else k_sa_thomas<<<dim3((n1 + 31) / 32, n2), tl, 0, s>>>(d, b, sd, nl, s1, n1, s2, n2, mult);
+        if (part == 8 && nl <= 96) launch_pdl(k_sa_thomas_part<8, 12>, (n1 * n2 + 3) / 4, 32, s, d, b, sd, nl, s1, n1, s2, n2, mult);
+        else if (part == 8) launch_pdl(k_sa_thomas_part<8, 16>, (n1 * n2 + 3) / 4, 32, s, d, b, sd, nl, s1, n1, s2, n2, mult);
+        else if (part == 16) launch_pdl(k_sa_thomas_part<16, 16>, (n1 * n2 + 1) / 2, 32, s, d, b, sd, nl, s1, n1, s2, n2, mult);
+        else launch_pdl(k_sa_thomas, dim3((n1 + 31) / 32, n2), tl, s, d, b, sd, nl, s1, n1, s2, n2, mult);
         KT_END(K_SASOLVE, s);
     };
     sweep(1, sJ, d.ny, 1, d.nx, sK, d.nz, 1);   // j lines
@@ -376,7 +382,7 @@ static int launch_sa_block(const Dims& d, const BlockDev& b, const AdfbParams& p
         dim3 tb(32, 4, 2);
         dim3 g((d.nx + 31) / 32, (d.ny + 3) / 4, (d.nz + 1) / 2);
         KT_BEGIN(K_SASOLVE, s);
-        k_sa_update<<<g, tb, 0, s>>>(d, b);
+        launch_pdl(k_sa_update, g, tb, s, d, b);
         KT_END(K_SASOLVE, s);
     }
     if (launch_bc_turb(d, b, subs, 1, s)) return 1;

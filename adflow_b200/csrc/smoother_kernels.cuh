@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, 
 // ---------------------------------------------------------------------------
 // executeRkStage part 1: dw *= cfl*etaRK(stage)*dtl, smoothers.F90:196-218
 __global__ void __launch_bounds__(256) k_rk_scale(Dims d, BlockDev b, double tmp) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -348,6 +349,7 @@ __global__ void __launch_bounds__(256) k_rk_scale(Dims d, BlockDev b, double tmp
 // scaleDt != 0 folds part 1 in (used when no residual averaging runs in between).
 // fromCurrent != 0: the DADI update, which starts from the current w, p instead of wn, pn (smoothers.F90:614-640)
 __global__ void __launch_bounds__(256) k_rk_update(Dims d, BlockDev b, int scaleDt, double tmp, int nw, int fromCurrent) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -408,6 +410,7 @@ __device__ __forceinline__ double ra_rfl(const BlockDev& b, const Dims& d, long 
 // Workspace b.flux: slot 0 rfl (pressure switch), 1..3 epz of the i, j, k direction (both one pass per
 // call, one thread per cell), 4..8 the forward-swept residuals, 9..13 d(i) per variable.
 __global__ void __launch_bounds__(256) k_resavg_rfl(Dims d, BlockDev b) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -417,6 +420,7 @@ __global__ void __launch_bounds__(256) k_resavg_rfl(Dims d, BlockDev b) {
 }
 // epz(i) = 1/4 smoop max(r^2 - 1, 0) max(iblank, 0), r = rfl0 (rfl(i) + rfl(i+1)), for i < l; epz(l) = 0
 __global__ void __launch_bounds__(256) k_resavg_eps(Dims d, BlockDev b, double rfl0) {
+    cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -438,6 +442,7 @@ __global__ void __launch_bounds__(256) k_resavg_eps(Dims d, BlockDev b, double r
 // d(i) = t(i) epz(i), forward sweep dw(i) = t(i) (dw(i) + epz(i-1) dw(i-1)), back substitution
 __global__ void __launch_bounds__(64) k_resavg_sweep(Dims d, BlockDev b, int dir, long long sd, int n, long long s1, int n1,
                                                      long long s2, int n2) {
+    cudaGridDependencySynchronize();
     const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int q2 = blockIdx.y * blockDim.y + threadIdx.y + 2;
     if (q1 > n1 + 1 || q2 > n2 + 1) return;
@@ -497,6 +502,7 @@ __global__ void __launch_bounds__(64) k_resavg_sweep(Dims d, BlockDev b, int dir
 // is run-to-run reproducible.  acc = Fp(3), Fv(3), Mp(3), Mv(3).
 __global__ void __launch_bounds__(256) k_wall_forces(Dims d, BlockDev b, FaceDev f, int dir, int isMin, int la, int lb, int viscWall,
                                                      double r0, double r1, double r2, double pRef, double* acc) {
+    cudaGridDependencySynchronize();
     __shared__ double sh[12][256];
     const long long N = d.N;
     const double fact = isMin ? -1.0 : 1.0;
@@ -597,17 +603,17 @@ static int launch_residual_averaging(const Dims& d, const BlockDev& b, const Adf
         dim3 tb(32, 4, 2);
         dim3 g((d.nx + 31) / 32, (d.ny + 3) / 4, (d.nz + 1) / 2);
         KT_BEGIN(K_RK, s);
-        k_resavg_rfl<<<g, tb, 0, s>>>(d, b);
+        launch_pdl(k_resavg_rfl, g, tb, s, d, b);
         KT_END(K_RK, s);
         KT_BEGIN(K_RK, s);
-        k_resavg_eps<<<g, tb, 0, s>>>(d, b, rfl0);
+        launch_pdl(k_resavg_eps, g, tb, s, d, b, rfl0);
         KT_END(K_RK, s);
     }
     dim3 tb(32, 2);
     auto run = [&](int dir, long long sd, int n, long long s1, int n1, long long s2, int n2) {
         if (n <= 1) return;
         KT_BEGIN(K_RK, s);
-        k_resavg_sweep<<<dim3((n1 + 31) / 32, (n2 + 1) / 2, 5), tb, 0, s>>>(d, b, dir, sd, n, s1, n1, s2, n2);
+        launch_pdl(k_resavg_sweep, dim3((n1 + 31) / 32, (n2 + 1) / 2, 5), tb, s, d, b, dir, sd, n, s1, n1, s2, n2);
         KT_END(K_RK, s);
     };
     run(0, 1, d.nx, d.sJ, d.ny, d.sK, d.nz);
@@ -624,15 +630,15 @@ static int launch_rk_update(const Dims& d, const BlockDev& b, const AdfbParams& 
     const int nw = prm.equations == ADFB_RANS ? 6 : 5;
     if (smooth) {
         KT_BEGIN(K_RK, s);
-        k_rk_scale<<<g, tb, 0, s>>>(d, b, tmp);
+        launch_pdl(k_rk_scale, g, tb, s, d, b, tmp);
         KT_END(K_RK, s);
         if (launch_residual_averaging(d, b, prm, s)) return 1;
         KT_BEGIN(K_RK, s);
-        k_rk_update<<<g, tb, 0, s>>>(d, b, 0, tmp, nw, 0);
+        launch_pdl(k_rk_update, g, tb, s, d, b, 0, tmp, nw, 0);
         KT_END(K_RK, s);
     } else {
         KT_BEGIN(K_RK, s);
-        k_rk_update<<<g, tb, 0, s>>>(d, b, 1, tmp, nw, 0);
+        launch_pdl(k_rk_update, g, tb, s, d, b, 1, tmp, nw, 0);
         KT_END(K_RK, s);
     }
     return (int)cudaGetLastError();
@@ -645,7 +651,7 @@ static int launch_dadi_update(const Dims& d, const BlockDev& b, const AdfbParams
     dim3 tb(32, 4, 2);
     dim3 g((d.nx + 31) / 32, (d.ny + 3) / 4, (d.nz + 1) / 2);
     KT_BEGIN(K_RK, s);
-    k_rk_update<<<g, tb, 0, s>>>(d, b, 0, 0.0, prm.equations == ADFB_RANS ? 6 : 5, 1);
+    launch_pdl(k_rk_update, g, tb, s, d, b, 0, 0.0, prm.equations == ADFB_RANS ? 6 : 5, 1);
     KT_END(K_RK, s);
     return (int)cudaGetLastError();
 }
@@ -660,7 +666,7 @@ static int launch_wall_forces(const Dims& d, const BlockDev& b, const std::vecto
         const int dir = (sf.faceId - 1) / 2, isMin = (sf.faceId % 2) == 1;
         const int la = dir == 0 ? d.jl : d.il, lb = dir == 2 ? d.jl : d.kl;
         KT_BEGIN(K_MISC, s);
-        k_wall_forces<<<1, 256, 0, s>>>(d, b, f, dir, isMin, la, lb, viscWall ? 1 : 0, rp[0], rp[1], rp[2], pRef, acc);
+        launch_pdl(k_wall_forces, 1, 256, s, d, b, f, dir, isMin, la, lb, viscWall ? 1 : 0, rp[0], rp[1], rp[2], pRef, acc);
         KT_END(K_MISC, s);
     }
     return (int)cudaGetLastError();
