@@ -81,6 +81,7 @@ struct Context {
     std::map<unsigned long long, cudaGraphExec_t> graphs;
     std::map<unsigned long long, long long> graphLaunches;
     bool useGraphs = true;
+    bool capturing = false;
 };
 
 Context g;
@@ -192,7 +193,9 @@ int run_graphed(unsigned long long key, F body) {
         const char* e = getenv("ADFB_GRAPH_NCCL"); ncclOk = (e && e[0] == '0') ? 0 : 1;  // NCCL send/recv capture fine with NCCL >= 2.9
         const char* n = getenv("ADFB_NO_GRAPH"); if (n && n[0] == '1') g.useGraphs = false;
     }
-    if (!g.useGraphs || g_kt.on || (g.nranks > 1 && !ncclOk)) return body();
+    // an entry point called from inside another one's capture runs inline (the flag lives in the context: a
+    // function-local static would be one per template instantiation)
+    if (!g.useGraphs || g_kt.on || g.capturing || (g.nranks > 1 && !ncclOk)) return body();
     auto it = g.graphs.find(key);
     if (it == g.graphs.end()) {
         // relaxed mode: the lazily built halo variable tables may cudaMalloc/cudaMemcpy (on the
@@ -200,7 +203,9 @@ int run_graphed(unsigned long long key, F body) {
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeRelaxed));
         const long long l0 = g_kt.launches;
+        g.capturing = true;
         const int rc = body();
+        g.capturing = false;
         const long long nl = g_kt.launches - l0;
         cudaError_t e = cudaStreamEndCapture(g.stream, &graph);
         if (rc != 0 || e != cudaSuccess || !graph) {
@@ -1069,7 +1074,7 @@ int adfb_timestep(int level, int onlyRadii) {
 
 // `initres(1,nwf); sourceTerms; residual` of the smoother loops (smoothers.F90:73-75,
 // multiGrid.F90:883-888): mean-flow residual with rFil = cdisRK(rkStage+1), fw persistent.
-int adfb_smoother_residual(int level, int rkStage) {
+static int adfb_smoother_residual_body(int level, int rkStage) {
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_smoother_residual: adfb_set_params has not been called");
     if (rkStage < 0 || rkStage > 5) return fail("adfb_smoother_residual: rkStage %d out of range", rkStage);
@@ -1081,9 +1086,15 @@ int adfb_smoother_residual(int level, int rkStage) {
     CK(cudaGetLastError());
     return 0;
 }
+int adfb_smoother_residual(int level, int rkStage) {
+    NEED_INIT();
+    const unsigned long long key = (3ull << 40) | ((unsigned long long)level << 32) | (unsigned)rkStage;
+    set_l2_window();
+    return run_graphed(key, [&]() { return adfb_smoother_residual_body(level, rkStage); });
+}
 
 // executeRkStage, src/solver/smoothers.F90:90-382
-int adfb_rk_stage(int level, int rkStage) {
+static int adfb_rk_stage_body(int level, int rkStage) {
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_rk_stage: adfb_set_params has not been called");
     if (rkStage < 1 || rkStage > g.prm.nRKStages) return fail("adfb_rk_stage: stage %d out of 1..%d", rkStage, g.prm.nRKStages);
@@ -1097,9 +1108,15 @@ int adfb_rk_stage(int level, int rkStage) {
     CK(cudaGetLastError());
     return 0;
 }
+int adfb_rk_stage(int level, int rkStage) {
+    NEED_INIT();
+    const unsigned long long key = (2ull << 40) | ((unsigned long long)level << 32) | (unsigned)rkStage;
+    set_l2_window();
+    return run_graphed(key, [&]() { return adfb_rk_stage_body(level, rkStage); });
+}
 
 // executeDADIStep, src/solver/smoothers.F90:425-693
-int adfb_dadi_step(int level) {
+static int adfb_dadi_step_body(int level) {
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_dadi_step: adfb_set_params has not been called");
     for (Block& b : g.blocks) {
@@ -1112,9 +1129,15 @@ int adfb_dadi_step(int level) {
     CK(cudaGetLastError());
     return 0;
 }
+int adfb_dadi_step(int level) {
+    NEED_INIT();
+    const unsigned long long key = (4ull << 40) | ((unsigned long long)level << 32);
+    set_l2_window();
+    return run_graphed(key, [&]() { return adfb_dadi_step_body(level); });
+}
 
 // DADISmoother, src/solver/smoothers.F90:383-421
-int adfb_dadi_cycle(int level, int nSubiterations) {
+static int adfb_dadi_cycle_body(int level, int nSubiterations) {
     NEED_INIT();
     if (nSubiterations < 1) return fail("adfb_dadi_cycle: nSubiterations must be >= 1");
     for (int sub = 1; sub <= nSubiterations - 1; sub++) {
@@ -1123,9 +1146,15 @@ int adfb_dadi_cycle(int level, int nSubiterations) {
     }
     return adfb_dadi_step(level);
 }
+int adfb_dadi_cycle(int level, int nSubiterations) {
+    NEED_INIT();
+    const unsigned long long key = (7ull << 40) | ((unsigned long long)level << 32) | (unsigned)nSubiterations;
+    set_l2_window();
+    return run_graphed(key, [&]() { return adfb_dadi_cycle_body(level, nSubiterations); });
+}
 
 // turbSolveDDADI, src/turbulence/turbAPI.F90:4-95 (Spalart-Allmaras)
-int adfb_sa_ddadi(int level, int nSubIterTurb) {
+static int adfb_sa_ddadi_body(int level, int nSubIterTurb) {
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_sa_ddadi: adfb_set_params has not been called");
     if (g.prm.equations != ADFB_RANS) return fail("adfb_sa_ddadi: equations are not RANS");
@@ -1141,9 +1170,15 @@ int adfb_sa_ddadi(int level, int nSubIterTurb) {
     CK(cudaGetLastError());
     return 0;
 }
+int adfb_sa_ddadi(int level, int nSubIterTurb) {
+    NEED_INIT();
+    const unsigned long long key = (5ull << 40) | ((unsigned long long)level << 32) | (unsigned)nSubIterTurb;
+    set_l2_window();
+    return run_graphed(key, [&]() { return adfb_sa_ddadi_body(level, nSubIterTurb); });
+}
 
 // RungeKuttaSmoother, src/solver/smoothers.F90:4-86
-int adfb_rk_cycle(int level) {
+static int adfb_rk_cycle_body(int level) {
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_rk_cycle: adfb_set_params has not been called");
     for (Block& b : g.blocks) {
@@ -1156,6 +1191,12 @@ int adfb_rk_cycle(int level) {
         if (adfb_smoother_residual(level, st)) return 1;
     }
     return adfb_rk_stage(level, g.prm.nRKStages);
+}
+int adfb_rk_cycle(int level) {
+    NEED_INIT();
+    const unsigned long long key = (6ull << 40) | ((unsigned long long)level << 32);
+    set_l2_window();
+    return run_graphed(key, [&]() { return adfb_rk_cycle_body(level); });
 }
 
 int adfb_norms(double out[2]) {
