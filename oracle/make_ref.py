@@ -47,6 +47,8 @@ PATCHES = [
     # actuator-zone source terms (sourceTerms): no actuator regions on the path
     (r"^call sourceterms\(\)$", "continue"),
     (r"^call recoverlevelalebc_block$", "continue"),
+    (r"^call interplevelale_block$", "continue"),
+    (r"^call recoverlevelale_block$", "continue"),
     # wallIntegrationFace: per-face output arrays of BCData (Fp, Fv, area: post-processing only) are not kept
     (r"^bcdata\(mm\)%(fp|fv|area)\b.*=.*$", "continue"),
     (r"^bcdata\(mm\)%fv = zero$", "continue"),
@@ -56,6 +58,19 @@ PATCHES = [
     # viscSubface(mm)%tau(i,j,l) (read side, surface integration) -> accessor over the harness' wall-stress table
     (r"viscsubface\((\w+)\)%(\w+)\(", r"vsf_\2(\1, "),
     # module-wide `use X` without only-list inside routines: names resolve through ref_env.h
+]
+
+MG_PATCHES = [
+    (r"flowdoms\(nn,\s*finelevel,\s*sps\)%(\w+)", r"fl_\1"),
+    (r"flowdoms\(nn,\s*coarselevel,\s*(?:sps|1)\)%bcdata", r"cl_bcdata_unused"),
+    (r"flowdoms\(nn,\s*coarselevel,\s*(?:sps|1)\)%(\w+)", r"cl_\1"),
+    (r"^type\(bcdatatype\).*$", "integer(kind=inttype) :: bcdata_unused"),
+    (r"^bcdata => cl_bcdata_unused$", "continue"),
+    (r"bcdata\((\w+)\)%(\w+)\(", r"cbcd_\2(\1, "),
+    (r"bcdata\((\w+)\)%(\w+)", r"cbcd_\2(\1)"),
+    # full-multigrid start-up only (corrections = .false.): outside the path
+    (r"^if \(\.not\. corrections\) call extrapolatesolution$", "continue"),
+    (r"^if \(\.not\. corrections\) call extrapolateviscosities$", "continue"),
 ]
 
 # external (other-module) data the translated routines see; declared in oracle/ref_env.h
@@ -75,7 +90,10 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  lumpeddiss viscpc spacediscrcoarse smoother rungekutta dadi nrkstages nsubiterations subit radiineededfine radiineededcoarse dirscaling
  symm symmpolar nswalladiabatic nswallisothermal farfield eulerwall extrap supersonicinflow supersonicoutflow
  subsonicinflow subsonicoutflow massbleedoutflow imin imax jmin jmax kmin kmax
- constantpressure linextrapolpressure quadextrapolpressure normalmomentum""".split()
+ constantpressure linextrapolpressure quadextrapolpressure normalmomentum
+ fl_ib fl_jb fl_kb cl_il cl_jl cl_kl cl_ie cl_je cl_ke cl_ib cl_jb cl_kb cl_nbocos mgboundcorr bcdirichlet0 bcneumann
+ slidinginterface oversetouterbound domaininterfaceall domaininterfacerhouvw domaininterfacep domaininterfacerho
+ domaininterfacetotal""".split()
 
 BOX_STRIDES = ["1", "(bp_ib + 1)", "(bp_ib + 1) * (bp_jb + 1)", "(bp_ib + 1) * (bp_jb + 1) * (bp_kb + 1)"]
 
@@ -135,6 +153,25 @@ def env_arrays():
         arrs["bp_" + n.replace("bmt", "bvt")] = A("bp_" + n.replace("bmt", "bvt"), "double", [("1", a), ("1", b), ("nt1", "1")])
     for n in ["rotmatrixi", "rotmatrixj", "rotmatrixk"]:
         arrs["bp_" + n] = A("bp_" + n, "double", [("1", "1")])
+    # multigrid: w1/p1 (solution at the start of the coarse-level visit), restriction / interpolation tables
+    arrs["bp_w1"] = refarr("w1", "double", *c1, ncomp="nwf")
+    arrs["bp_p1"] = refarr("p1", "double", *c1)
+    for dname, e, l in (("i", "bp_ie", "bp_il"), ("j", "bp_je", "bp_jl"), ("k", "bp_ke", "bp_kl")):
+        arrs["bp_mg%sfine" % dname] = A("bp_mg%sfine" % dname, "int", [("1", e), ("1", "2")])
+        arrs["bp_mg%sweight" % dname] = A("bp_mg%sweight" % dname, "double", [("2", "(%s) - 1" % l)])
+        arrs["bp_mg%scoarse" % dname] = A("bp_mg%scoarse" % dname, "int", [("2", "(%s) - 1" % l), ("1", "2")])
+    # the other level's block (fine level in transferToCoarseGrid, coarse level in transferToFineGrid)
+    for pre in ("fl", "cl"):
+        st = ["1", "(%s_ib + 1)" % pre, "(%s_ib + 1) * (%s_jb + 1)" % (pre, pre),
+              "(%s_ib + 1) * (%s_jb + 1) * (%s_kb + 1)" % (pre, pre, pre)]
+        bnd = [("0", "%s_ib + 1" % pre), ("0", "%s_jb + 1" % pre), ("0", "%s_kb + 1" % pre)]
+        for n in ("p", "vol", "rev", "p1"):
+            arrs["%s_%s" % (pre, n)] = A("%s_%s" % (pre, n), "double", list(bnd), strides=st[:3], base=["0", "0", "0"])
+        arrs["%s_iblank" % pre] = A("%s_iblank" % pre, "int", list(bnd), strides=st[:3], base=["0", "0", "0"])
+        for n, nc in (("w", "nw"), ("w1", "nwf")):
+            arrs["%s_%s" % (pre, n)] = A("%s_%s" % (pre, n), "double", list(bnd) + [("1", nc)], strides=st, base=["0", "0", "0", "1"])
+    arrs["cl_bctype"] = A("cl_bctype", "int", [("1", "64")])
+    arrs["cl_bcfaceid"] = A("cl_bcfaceid", "int", [("1", "64")])
     arrs["bp_bctype"] = A("bp_bctype", "int", [("1", "64")])
     arrs["bp_bcfaceid"] = A("bp_bcfaceid", "int", [("1", "64")])
     arrs["winf"] = A("winf", "double", [("1", "10")])
@@ -192,13 +229,21 @@ UNITS = [
     ("solver/fluxes.F90", "fluxes_", ["inviscidcentralflux", "invisciddissfluxscalar", "invisciddissfluxmatrix", "inviscidupwindflux",
                                       "viscousflux", "invisciddissfluxscalarapprox", "invisciddissfluxmatrixapprox",
                                       "viscousfluxapprox"], ("USE_TAPENADE",)),
-    ("solver/residuals.F90", "residuals_", ["residual_block", "initres_block"], ("USE_TAPENADE",), "residuals_block_ref.c"),
+    # coarse-level (first order) dissipation of the multigrid cycle and residual_block WITH its coarse-level branch
+    ("solver/fluxes.F90", "fluxes_", ["invisciddissfluxscalarcoarse", "invisciddissfluxmatrixcoarse"], (), "fluxes_coarse_ref.c"),
+    ("solver/residuals.F90", "residuals_", ["initres_block"], ("USE_TAPENADE",), "residuals_initres_ref.c"),
+    ("solver/residuals.F90", "residuals_", ["residual_block"], (), "residuals_block_ref.c"),
+    # multigrid transfer operators.  flowDoms(nn, fineLevel / coarseLevel, sps)%x (the OTHER level's block, next
+    # to the blockPointers of the current one) -> fl_x / cl_x env data bound by the harness; the coarse block's
+    # BCData -> accessor functions over a second subface table (cbcd)
+    ("solver/multiGrid.F90", "multigrid_", ["transfertocoarsegrid", "transfertofinegrid", "setcornerrowhalos",
+                                            "setcorrectionscoarsehalos"], (), None, MG_PATCHES),
 ]
 RENAME_MODULES = {"blockpointers": "bp_", "flowutils": "flowutils_", "turbutils": "turbutils_",
                   "residuals": "residuals_", "smoothers": "smoothers_", "sa": "sa_",
                   "bcpointers": "bcpointers_", "bcroutines": "bcroutines_",
                   "turbbcroutines": "turbbcroutines_", "surfaceintegrations": "surfaceintegrations_",
-                  "fluxes": "fluxes_", "solverutils": "solverutils_"}
+                  "fluxes": "fluxes_", "solverutils": "solverutils_", "multigrid": "multigrid_"}
 
 
 def main():
@@ -208,16 +253,17 @@ def main():
         return 0
     env = f90toc.Env(ENV_INTS, env_arrays(), ["getcorrectfork", "bcd_icbeg", "bcd_icend", "bcd_jcbeg", "bcd_jcend",
                                               "bcd_inbeg", "bcd_inend", "bcd_jnbeg", "bcd_jnend", "bcd_iblank",
-                                              "bcd_subsonicinlettreatment"], dict(ENV_SUBS))
+                                              "bcd_subsonicinlettreatment", "cbcd_icbeg", "cbcd_icend", "cbcd_jcbeg", "cbcd_jcend"], dict(ENV_SUBS))
     outdir = os.path.join(HERE, "_ref")
     os.makedirs(outdir, exist_ok=True)
     tr = None
     for unit in UNITS:
         rel, prefix, routines, defined = unit[:4]
+        patches = (list(unit[5]) if len(unit) > 5 else []) + PATCHES
         src = os.path.join(ref, "src", rel)
         code, tr = f90toc.translate_module(src, only=set(routines), env=env, rename_modules=RENAME_MODULES,
-                                           patches=PATCHES, defined=defined, tr=tr, prefix=prefix)
-        out = os.path.join(outdir, unit[4] if len(unit) > 4 else os.path.basename(rel).replace(".F90", "").lower() + "_ref.c")
+                                           patches=patches, defined=defined, tr=tr, prefix=prefix)
+        out = os.path.join(outdir, unit[4] if len(unit) > 4 and unit[4] else os.path.basename(rel).replace(".F90", "").lower() + "_ref.c")
         with open(out, "w") as f:
             f.write(code)
         print("make_ref: wrote %s (%d lines)" % (out, code.count("\n")))

@@ -11,6 +11,7 @@ double pinfcorr, rhoinf, gammainf, timeref = 1.0, rgas, tref;
 int equations, equationmode, turbmodel, turbprod, useqcr, useft2sa, userotationsa;
 double prandtl, prandtlturb;
 int spacediscr, orderturb, limiter, precond, riemann, riemanncoarse, approxsa;
+double vis2coarse = 0.5;
 double vis2, vis4, sigma, adis, acousticscalefactor, kappacoef;
 int usedisscontinuation = 0;
 double disscontmagnitude, disscontmidpoint, disscontsharpness;
@@ -57,7 +58,23 @@ double veldirfreestream[3] = {1.0, 0.0, 0.0}, pointref[3], momentaxis[6] = {0, 0
 
 /* Driver-level procedures that are NOT part of the translated set.  One block, pointers bound by
    the harness; halo exchange (no neighbours) is a no-op. */
-void setpointers(int* nn, int* level, int* sps) { (void)nn; (void)level; (void)sps; }
+void (*setpointers_hook)(int level) = NULL;
+void setpointers(int* nn, int* level, int* sps) { (void)nn; (void)sps; if (setpointers_hook) setpointers_hook(*level); }
+/* timeStep (src/solver/solverUtils.F90:4-41): loop over the blocks of currentLevel around timeStep_block */
+void solverutils_timestep_block(int* onlyradii);
+void solverutils_timestep(int* onlyradii) {
+    int one = 1;
+    setpointers(&one, &currentlevel, &one);
+    solverutils_timestep_block(onlyradii);
+}
+
+double *bp_w1, *bp_p1, *bp_mgiweight, *bp_mgjweight, *bp_mgkweight;
+int *bp_mgifine, *bp_mgjfine, *bp_mgkfine, *bp_mgicoarse, *bp_mgjcoarse, *bp_mgkcoarse;
+int fl_ib, fl_jb, fl_kb, cl_il, cl_jl, cl_kl, cl_ie, cl_je, cl_ke, cl_ib, cl_jb, cl_kb, cl_nbocos, mgboundcorr;
+double *fl_w, *fl_p, *fl_vol, *fl_rev, *fl_w1, *fl_p1, *cl_w, *cl_p, *cl_vol, *cl_rev, *cl_w1, *cl_p1;
+int *fl_iblank, *cl_iblank, cl_bctype[64], cl_bcfaceid[64];
+double fcoll = 1.0;
+RefSubface cbcd[64];
 void whalo1(int* a, int* b, int* c, int* d, int* e, int* f) { (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; }
 void whalo2(int* a, int* b, int* c, int* d, int* e, int* f) { (void)a; (void)b; (void)c; (void)d; (void)e; (void)f; }
 
@@ -72,6 +89,8 @@ UNREACHABLE(turbutils_vfeddyviscosity)
 /* boundary-condition types outside section 8 (polar symmetry) */
 UNREACHABLE(bcroutines_bcsymmpolar1sthalo)
 UNREACHABLE(bcroutines_bcsymmpolar2ndhalo)
+/* full-multigrid start-up (transferToFineGrid(corrections = .false.)) is outside the path */
+void turbbcroutines_applyallturbbc(int* secondhalo) { (void)secondhalo; terminate("applyAllTurbBC", "full-multigrid start-up is outside the translated hot path"); }
 
 
 /* src/utils/utils.F90:486-500 */

@@ -23,6 +23,7 @@ extern int equations, equationmode, turbmodel, turbprod, useqcr, useft2sa, usero
 extern double prandtl, prandtlturb;
 /* inputDiscretization */
 extern int spacediscr, orderturb, limiter, precond, riemann, riemanncoarse, approxsa;
+extern double vis2coarse;
 extern double vis2, vis4, sigma, adis, acousticscalefactor, kappacoef;
 /* inputIteration */
 extern int usedisscontinuation;
@@ -115,6 +116,30 @@ extern int spectralsol, computesepsensorks, computecavitation, cavexponent, rvfn
 extern double pref, lref, machcoef, cpmin_rho, cavitationnumber, cavsensorsharpness, cavsensoroffset;
 extern double sepsensorsharpness, sepsensoroffset, sepsensorkssharpness, sepsensorksphi, sepsensorksoffset, sepsenmaxrho;
 extern double veldirfreestream[3], pointref[3], momentaxis[6], cpmin_family[4], sepsenmaxfamily[4];
+
+/* multigrid (src/solver/multiGrid.F90): w1/p1 and the restriction / interpolation tables of the current block, the
+   OTHER level's block that transferToCoarseGrid (fine: fl_) and transferToFineGrid (coarse: cl_) reach through
+   flowDoms(nn, level, sps), and the coarse block's BCData (cbcd) */
+extern double *bp_w1, *bp_p1, *bp_mgiweight, *bp_mgjweight, *bp_mgkweight;
+extern int *bp_mgifine, *bp_mgjfine, *bp_mgkfine, *bp_mgicoarse, *bp_mgjcoarse, *bp_mgkcoarse;
+extern int fl_ib, fl_jb, fl_kb, cl_il, cl_jl, cl_kl, cl_ie, cl_je, cl_ke, cl_ib, cl_jb, cl_kb, cl_nbocos, mgboundcorr;
+extern double *fl_w, *fl_p, *fl_vol, *fl_rev, *fl_w1, *fl_p1, *cl_w, *cl_p, *cl_vol, *cl_rev, *cl_w1, *cl_p1;
+extern int *fl_iblank, *cl_iblank, cl_bctype[64], cl_bcfaceid[64];
+extern double fcoll;
+extern RefSubface cbcd[64];
+static inline int cbcd_icbeg(int nn) { return cbcd[nn - 1].icbeg; }
+static inline int cbcd_icend(int nn) { return cbcd[nn - 1].icend; }
+static inline int cbcd_jcbeg(int nn) { return cbcd[nn - 1].jcbeg; }
+static inline int cbcd_jcend(int nn) { return cbcd[nn - 1].jcend; }
+static inline double cbcd_norm(int nn, int i, int j, int l) {
+    const RefSubface* s = &cbcd[nn - 1];
+    const long na = s->icend - s->icbeg + 1, nb = s->jcend - s->jcbeg + 1;
+    return s->norm[(i - s->icbeg) + na * (j - s->jcbeg) + (l - 1) * na * nb];
+}
+/* setPointers(nn, level, sps): the harness registers a callback that rebinds bp_* and bcd to the block of `level` */
+extern void (*setpointers_hook)(int level);
+void solverutils_timestep(int* onlyradii);
+void turbbcroutines_applyallturbbc(int* secondhalo);
 
 /* driver-level procedures outside the translated set (no-op stubs, see ref_env.c) */
 void setpointers(int* nn, int* level, int* sps);
