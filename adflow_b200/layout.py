@@ -53,14 +53,15 @@ class BlockDims:
 
 
 # number of trailing components of each array class
-NCOMP = {"x": 3, "si": 3, "sj": 3, "sk": 3, "fw": 5, "wn": 5, "dss": 3, "grad": 12, "scratch": 10, "wallTau": 27}
+NCOMP = {"x": 3, "si": 3, "sj": 3, "sk": 3, "fw": 5, "wn": 5, "dss": 3, "grad": 12, "scratch": 10, "wallTau": 27,
+         "wr": 5, "w1": 5}
 
 
 class HostBlock:
     """All per-block host arrays in uniform boxes (numpy, Fortran order)."""
 
-    REAL = ["p", "rlv", "rev", "vol", "volRef", "d2Wall", "ss", "aa", "radI", "radJ", "radK", "dtl", "pn", "shock"]
-    VEC = ["x", "si", "sj", "sk", "fw", "wn", "dss", "grad", "scratch", "wallTau"]
+    REAL = ["p", "rlv", "rev", "vol", "volRef", "d2Wall", "ss", "aa", "radI", "radJ", "radK", "dtl", "pn", "shock", "p1"]
+    VEC = ["x", "si", "sj", "sk", "fw", "wn", "dss", "grad", "scratch", "wallTau", "wr", "w1"]
 
     def __init__(self, nx, ny, nz, nw=6, right_handed=True):
         self.d = BlockDims(nx, ny, nz)
@@ -79,6 +80,12 @@ class HostBlock:
         self.iblank = np.ones(box, dtype=np.int32, order="F")
         self.d2Wall[...] = 1.0
         self.subfaces = []  # list of dicts: bcType, faceId, icBeg.., norm (ndarray), ...
+        # multigrid (src/modules/block.F90 mgIFine ... mgKCoarse): level 1 = finest; a coarse block carries the
+        # restriction tables mg{I,J,K}Fine (1:ie, 2) / mg{I,J,K}Weight (2:il) towards ITS fine block, a fine block the
+        # interpolation tables mg{I,J,K}Coarse (2:il, 2) towards its coarse block; stored with the Fortran index as the
+        # numpy index (row 0 / rows 0-1 unused)
+        self.level = 1
+        self.mg = {}
 
     def ref(self, name):
         """Contiguous Fortran-order copy of `name` with the reference's extents."""

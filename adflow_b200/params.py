@@ -35,11 +35,13 @@ class AdfbParams(C.Structure):
         ("etaRK", C.c_double * 6), ("cdisRK", C.c_double * 6),
         ("alfaTurb", C.c_double), ("turbResScale", C.c_double),
         ("cflLimit", C.c_double), ("smoop", C.c_double), ("sigma", C.c_double),
+        ("vis2Coarse", C.c_double), ("fcoll", C.c_double),
         ("equations", C.c_int32), ("spaceDiscr", C.c_int32), ("nRKStages", C.c_int32), ("turbProd", C.c_int32),
         ("useQCR", C.c_int32), ("useft2SA", C.c_int32), ("useRotationSA", C.c_int32), ("approxSA", C.c_int32),
         ("secondOrdTurb", C.c_int32), ("limiter", C.c_int32), ("resAveraging", C.c_int32),
         ("nSubiterTurb", C.c_int32), ("wallBCConstantPressure", C.c_int32), ("reserved", C.c_int32),
         ("hScalingInlet", C.c_int32), ("outflowLinearExtrapol", C.c_int32),
+        ("mgBoundCorr", C.c_int32), ("spaceDiscrCoarse", C.c_int32),
     ]
 
 
@@ -53,6 +55,9 @@ DEFAULT_OPTIONS = {
     "discretization": "central plus scalar dissipation",
     "vis2": 0.25,
     "vis4": 0.0156,
+    "vis2Coarse": 0.5,
+    "coarseDiscretization": "central plus scalar dissipation",
+    "MGCycle": "sg",
     "dissipationScalingExponent": 0.67,
     "acousticScaleFactor": 1.0,
     "turbulenceOrder": "first order",
@@ -196,6 +201,11 @@ def make_params(options=None, mach=0.8, alpha_deg=1.8, P=20000.0, T=220.0, R=287
     for i in range(6):
         prm.wInf[i] = w[i]
     prm.vis2, prm.vis4 = opt["vis2"], opt["vis4"]
+    # multigrid: vis2Coarse (pyADflow default 0.5), fcoll = 1 and mgBoundCorr = bcDirichlet0 are not pyADflow options
+    # (inputParamRoutines.F90:3921-3923)
+    prm.vis2Coarse, prm.fcoll, prm.mgBoundCorr = opt["vis2Coarse"], 1.0, 0
+    prm.spaceDiscrCoarse = {"central plus scalar dissipation": DISS_SCALAR, "central plus matrix dissipation": DISS_MATRIX,
+                            "upwind": UPWIND}[opt["coarseDiscretization"]]
     prm.adis = opt["dissipationScalingExponent"]
     prm.acousticScaleFactor = opt["acousticScaleFactor"]
     prm.kappaCoef = opt["kappaCoef"]

@@ -275,3 +275,99 @@ def make_subface(blk, face, bc, prm=None):
         if bc in (8, 9) and prm.equations == RANS:
             sub["turbInlet"] = F(prm.wInf[5] * (1.0 + 0.1 * wig))
     return sub
+
+
+# ---------------------------------------------------------------------------------------------
+# multigrid: coarse block of a synthetic block (what createCoarseBlocks, src/preprocessing/coarseUtils.F90, sets up)
+def mg_kept_nodes(n_cells):
+    """iCo(1:il): fine nodes kept on the coarse level.  Every other node; the last node is always kept, so an odd
+    number of cells ends in an irregular coarse cell made of ONE fine cell (weight 1/2, coarseUtils.F90:283-296)."""
+    il = n_cells + 1
+    keep = np.zeros(il + 1, dtype=bool)      # index 1..il
+    keep[1:il + 1:2] = True
+    keep[il] = True
+    return keep
+
+
+def mg_tables_1d(keep, ie_c, ie_f, ib_f):
+    """mgIFine(1:ie_c, 2), mgIWeight(2:il_c), mgICoarse(2:il_f, 2) of one direction from iCo = `keep`
+    (coarseUtils.F90:270-352); Fortran index == numpy index."""
+    il_f = keep.size - 1
+    fine = np.zeros((ie_c + 1, 2), dtype=np.int32)
+    wgt = np.zeros(ie_c + 1)
+    coarse = np.zeros((ie_f + 1, 2), dtype=np.int32)
+    fine[1] = (0, 1)
+    fine[ie_c] = (ie_f, ib_f)
+    ii = 2
+    for i in range(2, il_f + 1):
+        if keep[i]:
+            if keep[i - 1]:
+                fine[ii] = (i, i); wgt[ii] = 0.5
+            else:
+                fine[ii] = (i - 1, i); wgt[ii] = 1.0
+            ii += 1
+    ii = 2
+    for i in range(2, il_f + 1):
+        if keep[i]:
+            coarse[i] = (ii, ii) if keep[i - 1] else (ii, ii + 1)
+            ii += 1
+        else:
+            coarse[i] = (ii, ii - 1)
+    return fine, wgt, coarse
+
+
+def make_coarse_block(fine, prm):
+    """The next coarser level of `fine`: nodes = the kept fine nodes (halo nodes extrapolated), metrics, volumes,
+    wall distance (volume average), porosities and boundary subfaces of the same types, restriction tables on the
+    coarse block and interpolation tables on `fine` (fine.mg is updated).  The state is left zero: it is the
+    output of the restriction."""
+    df = fine.d
+    keeps = [mg_kept_nodes(n) for n in (df.nx, df.ny, df.nz)]
+    nc = [int(k.sum()) - 1 for k in keeps]
+    blk = HostBlock(*nc, nw=fine.nw, right_handed=fine.right_handed)
+    blk.level = fine.level + 1
+    d = blk.d
+    idx = [np.flatnonzero(k) for k in keeps]                      # fine node index of coarse node 1..il_c
+    x = np.zeros(d.box + (3,), order="F")
+    x[1:d.il + 1, 1:d.jl + 1, 1:d.kl + 1] = fine.x[np.ix_(idx[0], idx[1], idx[2])]
+    x[0], x[d.ie] = 2 * x[1] - x[2], 2 * x[d.il] - x[d.il - 1]
+    x[:, 0], x[:, d.je] = 2 * x[:, 1] - x[:, 2], 2 * x[:, d.jl] - x[:, d.jl - 1]
+    x[:, :, 0], x[:, :, d.ke] = 2 * x[:, :, 1] - x[:, :, 2], 2 * x[:, :, d.kl] - x[:, :, d.kl - 1]
+    blk.x[...] = x
+    compute_metrics(blk)
+    compute_volumes(blk)
+    tabs = [mg_tables_1d(keeps[a], (d.ie, d.je, d.ke)[a], (df.ie, df.je, df.ke)[a], (df.ib, df.jb, df.kb)[a]) for a in range(3)]
+    for a, nm in enumerate("IJK"):
+        blk.mg["mg%sFine" % nm], blk.mg["mg%sWeight" % nm] = tabs[a][0], tabs[a][1]
+        fine.mg["mg%sCoarse" % nm] = tabs[a][2]
+    # wall distance of the coarse cells: volume-weighted average of the fine cells
+    ow = d.owned()
+    fI, fJ, fK = (blk.mg["mg%sFine" % nm] for nm in "IJK")
+    num = np.zeros((d.nx, d.ny, d.nz)); den = np.zeros_like(num)
+    for a in (0, 1):
+        for b_ in (0, 1):
+            for c in (0, 1):
+                sel = np.ix_(fI[2:d.il + 1, a], fJ[2:d.jl + 1, b_], fK[2:d.kl + 1, c])
+                num += fine.vol[sel] * fine.d2Wall[sel]; den += fine.vol[sel]
+    blk.d2Wall[...] = 1.0
+    blk.d2Wall[ow] = num / den
+    blk.subfaces = []
+    for s in fine.subfaces:
+        face, bc = s["faceId"], s["bcType"]
+        blk.subfaces.append(make_subface(blk, face, bc, prm))
+        if bc in (BC_WALL, BC_EULERWALL, BC_EXTRAP, 6):
+            if face == IMIN: blk.porI[1, :, :] = 0
+            if face == IMAX: blk.porI[d.il, :, :] = 0
+            if face == JMIN: blk.porJ[:, 1, :] = 0
+            if face == JMAX: blk.porJ[:, d.jl, :] = 0
+            if face == KMIN: blk.porK[:, :, 1] = 0
+            if face == KMAX: blk.porK[:, :, d.kl] = 0
+    # a benign state so that halo cells never hold zeros (divisions): free stream, overwritten by the restriction
+    for l in range(fine.nw):
+        blk.w[..., l] = prm.wInf[l]
+    blk.w[..., 4] = prm.wInf[4]
+    blk.p[...] = prm.pInf
+    blk.rlv[...] = lam_viscosity(prm, blk.p, blk.w[..., 0]) if prm.equations != EULER else 0.0
+    if prm.equations == RANS:
+        blk.rev[...] = eddy_viscosity(prm, blk.w, blk.rlv)
+    return blk

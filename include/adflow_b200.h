@@ -110,6 +110,9 @@ typedef struct AdfbParams {
     double turbResScale;  /* NKSolvers.F90:1295-1307 */
     double cflLimit, smoop; /* residual averaging, residuals.F90:1850-1893 */
     double sigma;           /* dissipationLumpingParameter of the *Approx dissipation (blockette.F90:4416) */
+    /* multigrid: inputDiscretization vis2Coarse (first-order coarse-level dissipation, fluxes.F90:4977-5203) and
+       inputIteration fcoll (relaxation of the restricted residual, multiGrid.F90:306-317) */
+    double vis2Coarse, fcoll;
     /* integer switches */
     int32_t equations;    /* ADFB_EULER / NS / RANS */
     int32_t spaceDiscr;   /* ADFB_DISS_SCALAR ... */
@@ -127,6 +130,8 @@ typedef struct AdfbParams {
     int32_t reserved;
     int32_t hScalingInlet;         /* inputDiscretization hScalingInlet (subsonic inflow, total conditions) */
     int32_t outflowLinearExtrapol; /* outflowTreatment == linExtrapol (default constantExtrapol), supersonic outflow */
+    int32_t mgBoundCorr;           /* 0 = bcDirichlet0 (default), 1 = bcNeumann0: boundary halos of the interpolated corrections */
+    int32_t spaceDiscrCoarse;      /* coarse-level discretisation; only ADFB_DISS_SCALAR is supported on level > 1 */
 } AdfbParams;
 
 /* One boundary subface of a block, mirroring BCDataType (src/modules/block.F90:52-156)

@@ -141,6 +141,7 @@ void orc_lam_viscosity(const OrcBlock* b, const AdfbParams* prm, int includeHalo
 void orc_eddy_viscosity(const OrcBlock* b, const AdfbParams* prm, int includeHalos) {
     Dims d = dims_of(b);
     if (prm->equations != ADFB_RANS) return;
+    if (b->level > 1) return;  /* computeEddyViscosity returns at once on coarse levels, turbUtils.F90:606-616 */
     int i0 = includeHalos ? 1 : 2, i1 = includeHalos ? d.ie : d.il;
     int j0 = includeHalos ? 1 : 2, j1 = includeHalos ? d.je : d.jl;
     int k0 = includeHalos ? 1 : 2, k1 = includeHalos ? d.ke : d.kl;
@@ -193,6 +194,10 @@ void orc_time_step(const OrcBlock* b, const AdfbParams* prm, int updateDt) {
         double qsk = uux * sx + uuy * sy + uuz * sz - sFace;
         double rk = half * (fabs(qsk) + asf * sqrt(cc2 * (sx * sx + sy * sy + sz * sz)));
         if (updateDt) b->dtl[c] = ri + rj + rk;
+        if (b->level > 1) {  /* doScaling = dirScaling .and. currentLevel <= groundLevel, solverUtils.F90:106 */
+            b->radI[c] = ri; b->radJ[c] = rj; b->radK[c] = rk;
+            continue;
+        }
         ri = dmax(ri, eps_); rj = dmax(rj, eps_); rk = dmax(rk, eps_);
         double rij = pow(ri / rj, adis), rjk = pow(rj / rk, adis), rki = pow(rk / ri, adis);
         b->radI[c] = ri * (one + one / rij + rki);

@@ -35,7 +35,8 @@
 #include "../include/adflow_b200.h"
 
 typedef struct OrcBlock {
-    int32_t nx, ny, nz, nw, rightHanded, pad_;
+    int32_t nx, ny, nz, nw, rightHanded;
+    int32_t level;          /* multigrid level, 0/1 = finest (ground level); > 1: coarse-level branches of the smoother path */
     /* state (cell, 2 halos) */
     double *w, *p, *rlv, *rev;
     /* geometry */
@@ -55,6 +56,7 @@ typedef struct OrcBlock {
     double *shock;          /* frozen shock sensor (referenceShockSensor) */
     double *wallTau;        /* [dir 0..2][tauxx,yy,zz,xy,xz,yz,qx,qy,qz][box]: viscous stress / heat flux of
                                every face (viscSubface%tau, %q are its boundary planes); NULL = not stored */
+    double *wr, *w1, *p1;   /* multigrid: residual forcing term (5), solution at the start of the coarse visit (5 / 1) */
 } OrcBlock;
 
 #ifdef __cplusplus
@@ -102,6 +104,17 @@ void orc_viscous_flux_approx(const OrcBlock* b, const AdfbParams* prm, double rF
 /* adflow_oracle_sa.c: one sa_block(resOnly=.false.) = residual + DD-ADI solve + rev + turbulence BCs */
 void orc_sa_block(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf);
 void orc_rk_smoother(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf);
+/* adflow_oracle_mg.c: multigrid transfer operators and the coarse-level residual (src/solver/multiGrid.F90) */
+void orc_diss_scalar_coarse(const OrcBlock* b, const AdfbParams* prm, double rFil);
+void orc_residual_block_coarse(const OrcBlock* b, const AdfbParams* prm, double rFil, int init);
+void orc_mg_corner_row_halos(const OrcBlock* b, const AdfbParams* prm);
+void orc_mg_restrict(const OrcBlock* coarse, const OrcBlock* fine, const AdfbParams* prm, const int32_t* mgIFine,
+                     const int32_t* mgJFine, const int32_t* mgKFine, const double* mgIWeight, const double* mgJWeight,
+                     const double* mgKWeight);
+void orc_mg_store_w1(const OrcBlock* coarse);
+void orc_mg_forcing(const OrcBlock* coarse, const AdfbParams* prm);
+void orc_mg_prolong(const OrcBlock* fine, const OrcBlock* coarse, const AdfbParams* prm, int nSubCoarse, const AdfbSubface* sfCoarse,
+                    const int32_t* mgICoarse, const int32_t* mgJCoarse, const int32_t* mgKCoarse);
 #ifdef __cplusplus
 }
 #endif

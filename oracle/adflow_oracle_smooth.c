@@ -327,8 +327,12 @@ void orc_apply_turb_bc(const OrcBlock* b, const AdfbParams* prm, int nSub, const
 /* applyAllBC_block order, src/solver/BCRoutines.F90:81-216: symm 1st halo, symm 2nd
    halo, (polar), adiabatic walls, isothermal walls, far field, (outflow, inflow),
    extrapolation, Euler walls, (supersonic inflow) */
-void orc_apply_flow_bc(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf, int secondHalo) {
+void orc_apply_flow_bc(const OrcBlock* b, const AdfbParams* prm0, int nSub, const AdfbSubface* sf, int secondHalo) {
     int n;
+    /* coarse levels: constant pressure at viscous and inviscid walls, BCRoutines.F90:550,642,1100 */
+    AdfbParams prmL = *prm0;
+    if (b->level > 1) { prmL.wallBCConstantPressure = 1; prmL.reserved = 1; }
+    const AdfbParams* prm = &prmL;
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SYMM) bc_flow_subface(b, prm, &sf[n], secondHalo, 1);
     if (secondHalo) for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SYMM) bc_flow_subface(b, prm, &sf[n], secondHalo, 2);
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_NSWALL_ADIABATIC) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
@@ -395,6 +399,7 @@ void orc_residual_averaging(const OrcBlock* b, const AdfbParams* prm) {
    residual_block (:4-346) with rFil = cdisRK(rkStage+1) for the RK smoother.
    Radii are NOT recomputed (timeStep is a separate call in executeMGCycle). */
 void orc_residual_block(const OrcBlock* b, const AdfbParams* prm, double rFil) {
+    if (b->level > 1) { orc_residual_block_coarse(b, prm, rFil, 1); return; }  /* initRes: dw = wr, 1st-order dissipation */
     Dims d = dims_of(b);
     int viscous = prm->equations != ADFB_EULER;
     memset(b->dw, 0, sizeof(double) * 5 * d.N);
@@ -415,8 +420,12 @@ void orc_residual_block(const OrcBlock* b, const AdfbParams* prm, double rFil) {
 
 /* executeRkStage: src/solver/smoothers.F90:90-382 (steady, fine level, no precond);
    BCs and halo exchange are the caller's (single block: BCs only). */
-void orc_rk_stage(const OrcBlock* b, const AdfbParams* prm, int rkStage, int nSub, const AdfbSubface* sf) {
+void orc_rk_stage(const OrcBlock* b, const AdfbParams* prm0, int rkStage, int nSub, const AdfbSubface* sf) {
     Dims d = dims_of(b);
+    /* currentCfl = cflCoarse unless currentLevel == 1; secondHalo only on the ground level (smoothers.F90:131-140) */
+    AdfbParams prmL = *prm0;
+    if (b->level > 1) prmL.cfl = prm0->cflCoarse;
+    const AdfbParams* prm = &prmL;
     double tmp = prm->cfl * prm->etaRK[rkStage - 1];
     int smooth = prm->resAveraging == 1 || (prm->resAveraging == 2 && (rkStage % 2) == 1);
     for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
@@ -447,7 +456,7 @@ void orc_rk_stage(const OrcBlock* b, const AdfbParams* prm, int rkStage, int nSu
     orc_etot(b, prm, 2, d.il, 2, d.jl, 2, d.kl);
     orc_lam_viscosity(b, prm, 0);
     orc_eddy_viscosity(b, prm, 0);
-    orc_apply_flow_bc(b, prm, nSub, sf, 1);
+    orc_apply_flow_bc(b, prm, nSub, sf, b->level > 1 ? 0 : 1);
 }
 
 /* RungeKuttaSmoother: src/solver/smoothers.F90:4-86.  On entry residual (rFil =

@@ -91,11 +91,19 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  symm symmpolar nswalladiabatic nswallisothermal farfield eulerwall extrap supersonicinflow supersonicoutflow
  subsonicinflow subsonicoutflow massbleedoutflow imin imax jmin jmax kmin kmax
  constantpressure linextrapolpressure quadextrapolpressure normalmomentum
- fl_ib fl_jb fl_kb cl_il cl_jl cl_kl cl_ie cl_je cl_ke cl_ib cl_jb cl_kb cl_nbocos mgboundcorr bcdirichlet0 bcneumann
+ sh_ib sh_jb sh_kb fl_ib fl_jb fl_kb cl_il cl_jl cl_kl cl_ie cl_je cl_ke cl_ib cl_jb cl_kb cl_nbocos mgboundcorr bcdirichlet0 bcneumann
  slidinginterface oversetouterbound domaininterfaceall domaininterfacerhouvw domaininterfacep domaininterfacerho
  domaininterfacetotal""".split()
 
 BOX_STRIDES = ["1", "(bp_ib + 1)", "(bp_ib + 1) * (bp_jb + 1)", "(bp_ib + 1) * (bp_jb + 1) * (bp_kb + 1)"]
+
+
+# setPointers (src/utils/utils.F90:3419-3477) points dw, fw, scratch, wn, pn, dtl, radI/J/K, gamma and rlv of EVERY grid
+# level at the finest level's arrays: on a coarse level they are the fine arrays indexed with coarse indices.  Their
+# strides therefore come from the dimensions of the array that is actually bound (sh_ib/jb/kb, set by the harness:
+# the current block's for single-level use, the finest block's inside a multigrid cycle)
+SH_STRIDES = ["1", "(sh_ib + 1)", "(sh_ib + 1) * (sh_jb + 1)", "(sh_ib + 1) * (sh_jb + 1) * (sh_kb + 1)"]
+SHARED = {"dw", "fw", "scratch", "wn", "pn", "dtl", "radi", "radj", "radk", "gamma", "rlv"}
 
 
 def refarr(name, ctype, lo, hi, ncomp=None, comp_lo="1"):
@@ -104,11 +112,12 @@ def refarr(name, ctype, lo, hi, ncomp=None, comp_lo="1"):
     the uniform box (0:ib,0:jb,0:kb[,ncomp]) that ref_env.h exposes, hence explicit strides and origin 0."""
     bounds = [(l, "(%s) - (%s) + 1" % (h, l)) for l, h in zip(lo, hi)]
     base = ["0", "0", "0"]
-    strides = BOX_STRIDES[:3]
+    st = SH_STRIDES if name in SHARED else BOX_STRIDES
+    strides = st[:3]
     if ncomp is not None:
         bounds.append((comp_lo, str(ncomp)))
         base.append(comp_lo)
-        strides = BOX_STRIDES[:4]
+        strides = st[:4]
     return f90toc.Array("bp_" + name, ctype, bounds, strides=strides, base=base)
 
 

@@ -18,7 +18,7 @@ def build(force=False):
     src = os.path.join(_HERE, "adflow_oracle.c")
     stale = (not os.path.exists(so)) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(so)
-        for f in ("adflow_oracle.c", "adflow_oracle_smooth.c", "adflow_oracle_sa.c", "adflow_oracle_fluxes.c", "adflow_oracle.h", "orc_internal.h",
+        for f in ("adflow_oracle.c", "adflow_oracle_smooth.c", "adflow_oracle_sa.c", "adflow_oracle_fluxes.c", "adflow_oracle_mg.c", "adflow_oracle.h", "orc_internal.h",
                   "../include/adflow_b200.h")
     )
     if force or stale:
@@ -29,11 +29,11 @@ def build(force=False):
 
 class OrcBlock(C.Structure):
     _fields_ = (
-        [(n, C.c_int32) for n in ("nx", "ny", "nz", "nw", "rightHanded", "pad_")]
+        [(n, C.c_int32) for n in ("nx", "ny", "nz", "nw", "rightHanded", "level")]
         + [(n, C.c_void_p) for n in (
             "w", "p", "rlv", "rev", "x", "si", "sj", "sk", "vol", "volRef", "d2Wall",
             "porI", "porJ", "porK", "iblank", "dw", "fw", "ss", "dss",
-            "aa", "radI", "radJ", "radK", "dtl", "grad", "wn", "pn", "scratch", "shock", "wallTau")]
+            "aa", "radI", "radJ", "radK", "dtl", "grad", "wn", "pn", "scratch", "shock", "wallTau", "wr", "w1", "p1")]
     )
 
 
@@ -58,6 +58,7 @@ def orc_block(hb):
     ob = OrcBlock()
     ob.nx, ob.ny, ob.nz, ob.nw = hb.d.nx, hb.d.ny, hb.d.nz, hb.nw
     ob.rightHanded = int(hb.right_handed)
+    ob.level = int(getattr(hb, "level", 1))
     for n, _t in OrcBlock._fields_[6:]:
         a = getattr(hb, n)
         assert a.flags.f_contiguous, n
@@ -168,3 +169,38 @@ class Oracle:
 
     def call(self, name, *args):
         getattr(self.L, name)(_p(self.ob), *args)
+
+    # -- multigrid (adflow_oracle_mg.c); `self` is the block named first in each docstring -------------------------
+    @staticmethod
+    def _tab(a, dtype):
+        a = np.ascontiguousarray(np.asfortranarray(a, dtype=dtype).ravel(order="F"))
+        return a, a.ctypes.data_as(C.c_void_p)
+
+    def residual_block_coarse(self, rfil=1.0, init=1):
+        self.L.orc_residual_block_coarse(_p(self.ob), _p(self.prm), C.c_double(rfil), C.c_int(init))
+
+    def diss_scalar_coarse(self, rfil=1.0):
+        self.L.orc_diss_scalar_coarse(_p(self.ob), _p(self.prm), C.c_double(rfil))
+
+    def mg_corner_row_halos(self):
+        self.L.orc_mg_corner_row_halos(_p(self.ob), _p(self.prm))
+
+    def mg_restrict(self, fine):
+        """COARSE block: restriction of `fine` (an Oracle) into wr / w / p / rev + etot, rlv, rev, corner row halos"""
+        mg = self.hb.mg
+        keep = [self._tab(mg[n], np.int32) for n in ("mgIFine", "mgJFine", "mgKFine")]
+        keep += [self._tab(mg[n], np.float64) for n in ("mgIWeight", "mgJWeight", "mgKWeight")]
+        self.L.orc_mg_restrict(_p(self.ob), _p(fine.ob), _p(self.prm), *[k[1] for k in keep])
+
+    def mg_store_w1(self):
+        self.L.orc_mg_store_w1(_p(self.ob))
+
+    def mg_forcing(self):
+        self.L.orc_mg_forcing(_p(self.ob), _p(self.prm))
+
+    def mg_prolong(self, coarse):
+        """FINE block: interpolate the corrections of `coarse` (an Oracle) and update w, p (+ etot, rlv, rev)"""
+        mg = self.hb.mg
+        keep = [self._tab(mg[n], np.int32) for n in ("mgICoarse", "mgJCoarse", "mgKCoarse")]
+        n, arr = coarse._subfaces()
+        self.L.orc_mg_prolong(_p(self.ob), _p(coarse.ob), _p(self.prm), C.c_int(n), arr, *[k[1] for k in keep])

@@ -122,6 +122,7 @@ extern double veldirfreestream[3], pointref[3], momentaxis[6], cpmin_family[4], 
    flowDoms(nn, level, sps), and the coarse block's BCData (cbcd) */
 extern double *bp_w1, *bp_p1, *bp_mgiweight, *bp_mgjweight, *bp_mgkweight;
 extern int *bp_mgifine, *bp_mgjfine, *bp_mgkfine, *bp_mgicoarse, *bp_mgjcoarse, *bp_mgkcoarse;
+extern int sh_ib, sh_jb, sh_kb; /* box of the (finest-level) arrays that dw, fw, dtl, rad*, rlv, gamma, wn, pn, scratch point at */
 extern int fl_ib, fl_jb, fl_kb, cl_il, cl_jl, cl_kl, cl_ie, cl_je, cl_ke, cl_ib, cl_jb, cl_kb, cl_nbocos, mgboundcorr;
 extern double *fl_w, *fl_p, *fl_vol, *fl_rev, *fl_w1, *fl_p1, *cl_w, *cl_p, *cl_vol, *cl_rev, *cl_w1, *cl_p1;
 extern int *fl_iblank, *cl_iblank, cl_bctype[64], cl_bcfaceid[64];

@@ -129,16 +129,20 @@ _BC_NAME = {1: "symm", 2: "nswalladiabatic", 3: "farfield", 4: "eulerwall", 5: "
             7: "subsonicoutflow", 8: "subsonicinflow", 9: "supersonicinflow", 10: "supersonicoutflow"}
 
 
-def bind_bcs(hb, prm):
+def bind_bcs(hb, prm, other_level=False):
     """nBocos / nViscBocos / BCType / BCFaceID / BCData of blockPointers from hb.subfaces.  The reference
-    numbers the viscous wall subfaces first (1..nViscBocos); the relative order is otherwise kept."""
+    numbers the viscous wall subfaces first (1..nViscBocos); the relative order is otherwise kept.
+    other_level: fill flowDoms(nn, coarseLevel)%{nBocos, BCType, BCFaceID, BCData} (cl_*, cbcd) instead."""
     cst = ref_constants()
     subs = sorted(hb.subfaces, key=lambda s_: 0 if s_["bcType"] in (2, 6) else 1)
     nvisc = sum(1 for s_ in subs if s_["bcType"] in (2, 6)) if prm.equations != 1 else 0
-    _seti("bp_nbocos", len(subs)); _seti("bp_nviscbocos", nvisc)
-    bct = (C.c_int * 64).in_dll(lib(), "bp_bctype")
-    bcf = (C.c_int * 64).in_dll(lib(), "bp_bcfaceid")
-    tab = (RefSubface * 64).in_dll(lib(), "bcd")
+    pre = "cl_" if other_level else "bp_"
+    _seti(pre + "nbocos", len(subs))
+    if not other_level:
+        _seti("bp_nviscbocos", nvisc)
+    bct = (C.c_int * 64).in_dll(lib(), pre + "bctype")
+    bcf = (C.c_int * 64).in_dll(lib(), pre + "bcfaceid")
+    tab = (RefSubface * 64).in_dll(lib(), "cbcd" if other_level else "bcd")
     keep = []
     for q, s_ in enumerate(subs):
         bct[q] = cst[_BC_NAME[s_["bcType"]]]
@@ -213,7 +217,18 @@ class RefBlock:
             self.a[n] = np.zeros(box, order="F")
         self.a["dw"] = f(hb.dw.copy(order="F"))
         self.a["fw"] = f(hb.fw.copy(order="F"))
-        self.a["wr"] = np.zeros(box + (5,), order="F")
+        self.a["wr"] = f(hb.wr.copy(order="F"))
+        self.a["w1"] = f(hb.w1.copy(order="F"))
+        self.a["p1"] = f(hb.p1.copy(order="F"))
+        # multigrid tables with the reference's declared bounds: mgIFine(1:ie, 2), mgIWeight(2:il), mgICoarse(2:il, 2)
+        ext = {"I": (d.ie, d.il), "J": (d.je, d.jl), "K": (d.ke, d.kl)}
+        for nm, (e_, l_) in ext.items():
+            mg = getattr(hb, "mg", {})
+            if "mg%sFine" % nm in mg:
+                self.a["mg%sfine" % nm.lower()] = f(np.array(mg["mg%sFine" % nm][1:e_ + 1, :], dtype=np.int32, order="F"))
+                self.a["mg%sweight" % nm.lower()] = f(np.array(mg["mg%sWeight" % nm][2:l_ + 1], dtype=np.float64))
+            if "mg%sCoarse" % nm in mg:
+                self.a["mg%scoarse" % nm.lower()] = f(np.array(mg["mg%sCoarse" % nm][2:l_ + 1, :], dtype=np.int32, order="F"))
         self.a["wn"] = f(hb.wn.copy(order="F"))
         self.a["pn"] = f(hb.pn.copy(order="F"))
         self.a["scratch"] = f(hb.scratch.copy(order="F"))
@@ -239,8 +254,14 @@ class RefBlock:
         for ref, mine in (("pori", "porI"), ("porj", "porJ"), ("pork", "porK")):
             self.a[ref] = f(getattr(hb, mine).astype(np.int32).copy(order="F"))
 
-    def bind(self):
+    SHARED = ("dw", "fw", "scratch", "wn", "pn", "dtl", "radi", "radj", "radk", "gamma", "rlv")
+
+    def bind(self, shared_from=None):
+        """blockPointers <- this block.  shared_from: the finest-level RefBlock whose dw, fw, scratch, wn, pn, dtl,
+        radI/J/K, gamma, rlv every level points at (setPointers, utils.F90:3419-3477); default: this block's own."""
         d = self.hb.d
+        sh = (shared_from or self).hb.d
+        _seti("sh_ib", sh.ib); _seti("sh_jb", sh.jb); _seti("sh_kb", sh.kb)
         for n, v in (("nx", d.nx), ("ny", d.ny), ("nz", d.nz), ("il", d.il), ("jl", d.jl), ("kl", d.kl),
                      ("ie", d.ie), ("je", d.je), ("ke", d.ke), ("ib", d.ib), ("jb", d.jb), ("kb", d.kb)):
             _seti("bp_" + n, v)
@@ -248,6 +269,8 @@ class RefBlock:
         _seti("bp_sectionid", 1); _seti("bp_blockismoving", 0); _seti("bp_nbkglobal", 1)
         for n, arr in self.a.items():
             assert arr.flags.f_contiguous
+            if shared_from is not None and n in self.SHARED:
+                arr = shared_from.a[n]
             _setp("bp_" + n, arr)
 
 
@@ -322,3 +345,70 @@ def call_core(flags=FLAG_FLOW | FLAG_TURB):
     args = [C.byref(C.c_int(1 if flags & m else 0)) for m in
             (FLAG_DISS_APPROX, FLAG_VISC_APPROX, FLAG_UPDATE_INTERMED, FLAG_FLOW, FLAG_TURB, FLAG_STORE_WALL)]
     lib().blocketterescore(*args)
+
+
+class RefMG:
+    """Two grid levels of one block for the translated multigrid routines (src/solver/multiGrid.F90).  setPointers
+    (nn, level, sps) of the reference is served by a callback that rebinds blockPointers (bp_*) and BCData (bcd) to
+    the block of `level`; the OTHER level's arrays that the transfer routines reach through flowDoms(nn, level, sps)
+    are bound once (fl_* = fine block, cl_* / cbcd = coarse block)."""
+
+    def __init__(self, fine_hb, coarse_hb, prm):
+        global _BOUND
+        self.prm = prm
+        set_params(prm, fine_hb.nw)
+        _setd("vis2coarse", prm.vis2Coarse); _setd("fcoll", prm.fcoll); _seti("mgboundcorr", prm.mgBoundCorr)
+        _seti("spacediscrcoarse", _REF_SPACEDISCR[prm.spaceDiscrCoarse])
+        self.lv = {1: RefBlock(fine_hb, prm), 2: RefBlock(coarse_hb, prm)}
+        self.keep = {}
+        L = lib()
+
+        def hook(level):
+            rb = self.lv[level]
+            rb.bind(shared_from=self.lv[1] if level != 1 else None)
+            self.keep[level] = bind_bcs(rb.hb, prm)
+
+        self._hook = C.CFUNCTYPE(None, C.c_int)(hook)
+        C.c_void_p.in_dll(L, "setpointers_hook").value = C.cast(self._hook, C.c_void_p).value
+        f, c = self.lv[1], self.lv[2]
+        for n, v in (("ib", f.hb.d.ib), ("jb", f.hb.d.jb), ("kb", f.hb.d.kb)):
+            _seti("fl_" + n, v)
+        dc = c.hb.d
+        for n in ("il", "jl", "kl", "ie", "je", "ke", "ib", "jb", "kb"):
+            _seti("cl_" + n, getattr(dc, n))
+        for n in ("w", "p", "vol", "rev", "w1", "p1", "iblank"):
+            _setp("fl_" + n, f.a[n]); _setp("cl_" + n, c.a[n])
+        self.keep["cl"] = bind_bcs(c.hb, prm, other_level=True)
+        _BOUND = self
+
+    def seed_coarse_shared(self):
+        """put the coarse block's dw, fw, dtl, radI/J/K, rlv, ... where the reference keeps them: in the finest
+        level's arrays at the coarse indices (for tests that start in the middle of a cycle)"""
+        dc = self.lv[2].hb.d
+        sl = (slice(0, dc.ib + 1), slice(0, dc.jb + 1), slice(0, dc.kb + 1))
+        for n in RefBlock.SHARED:
+            self.lv[1].a[n][sl] = self.lv[2].a[n]
+
+    def close(self):
+        C.c_void_p.in_dll(lib(), "setpointers_hook").value = None
+        _seti("currentlevel", 1)
+
+    def call(self, level, routine, *int_args, rkstage=None):
+        """setPointers(1, level, 1), currentLevel = level, then one translated procedure"""
+        _seti("currentlevel", level); _seti("groundlevel", 1)
+        if rkstage is not None:
+            _seti("rkstage", rkstage)
+        self._hook(level)
+        getattr(lib(), routine)(*[C.byref(C.c_int(int(v))) for v in int_args])
+        return self.lv[level]
+
+    def transfer_to_coarse(self):
+        """transferToCoarseGrid from level 1: fine residual, restriction, coarse BCs, coarse residual, forcing term"""
+        _seti("currentlevel", 1); _seti("groundlevel", 1)
+        lib().multigrid_transfertocoarsegrid()
+        assert C.c_int.in_dll(lib(), "currentlevel").value == 2
+
+    def transfer_to_fine(self):
+        """currentLevel = 1; transferToFineGrid(.true.)"""
+        _seti("currentlevel", 1); _seti("groundlevel", 1)
+        lib().multigrid_transfertofinegrid(C.byref(C.c_int(1)))

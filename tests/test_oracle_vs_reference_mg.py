@@ -1,0 +1,156 @@
+"""Pin the oracle's multigrid pieces (oracle/adflow_oracle_mg.c + the coarse-level branches of the smoother path)
+BIT FOR BIT against the reference's own routines: transferToCoarseGrid, transferToFineGrid, setCornerRowHalos,
+setCorrectionsCoarseHalos (src/solver/multiGrid.F90), inviscidDissFluxScalarCoarse (src/solver/fluxes.F90), the coarse
+branches of initRes_block / residual_block / timeStep_block / executeRkStage / the wall BCs, translated to C where the
+source lies (oracle/_ref).  Skipped where the translated library is absent."""
+import numpy as np
+import pytest
+
+from adflow_b200 import synthetic as syn
+from oracle import refblockette as rb
+from oracle.pyoracle import Oracle
+
+from util import case
+
+pytestmark = pytest.mark.skipif(not rb.available(), reason="oracle/_ref not built (no /root/reference at build time)")
+
+CASES = [((12, 8, 10), None), ((9, 7, 6), None), ((8, 6, 6), {"equationType": "Euler"}),
+         ((6, 9, 5), {"equationType": "laminar NS"})]
+
+
+def two_levels(shape, options, seed=314):
+    prm, fine = case(*shape, options, seed=seed)
+    # the reference numbers the viscous wall subfaces first (nViscBocos); where subfaces share edge halos the order
+    # of application matters (setCorrectionsCoarseHalos), so both sides use that order
+    fine.subfaces.sort(key=lambda s_: 0 if s_["bcType"] in (2, 6) else 1)
+    coarse = syn.make_coarse_block(fine, prm)
+    # halos of the fine block as the smoother leaves them
+    o = Oracle(fine, prm)
+    o.apply_turb_bc(True); o.apply_flow_bc(True)
+    return prm, fine, coarse
+
+
+def oracle_transfer_to_coarse(prm, fine, coarse):
+    """transferToCoarseGrid (multiGrid.F90:5-324) composed from the oracle's pieces, one block per level"""
+    of, oc = Oracle(fine, prm), Oracle(coarse, prm)
+    of.time_step(False)                      # timeStep(.true.): only the spectral radii
+    of.residual_block(prm.cdisRK[0])         # rkStage = 0 -> rFil = cdisRK(1); initres + residual
+    oc.mg_restrict(of)
+    oc.apply_flow_bc(False)                  # applyAllBC(.false.); whalo1: no neighbours
+    oc.time_step(True)                       # timeStep(.false.)
+    oc.mg_store_w1()
+    oc.residual_block_coarse(prm.cdisRK[0], init=0)
+    oc.mg_forcing()
+    return of, oc
+
+
+def eq(a, b, name):
+    assert np.isfinite(a).all(), name
+    assert np.array_equal(a, b), "%s: max |diff| %.3e" % (name, np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("shape,options", CASES)
+def test_transfer_to_coarse_grid(shape, options):
+    prm, fine, coarse = two_levels(shape, options)
+    f2, c2 = fine.copy(), coarse.copy()
+    mg = rb.RefMG(f2, c2, prm)
+    try:
+        mg.transfer_to_coarse()
+    finally:
+        mg.close()
+    rf, rc = mg.lv[1].a, mg.lv[2].a
+    oracle_transfer_to_coarse(prm, fine, coarse)
+    d, df = coarse.d, fine.d
+    ow, owf = d.owned(), df.owned()
+    c1 = (slice(1, d.ie + 1), slice(1, d.je + 1), slice(1, d.ke + 1))
+    # dw, fw, dtl, radI/J/K, rlv of every level ARE the finest level's arrays in the reference (setPointers):
+    # the coarse values sit in the fine arrays at the coarse indices
+    eq(coarse.wr[ow], rc["wr"][ow], "wr (forcing term)")
+    eq(coarse.dw[ow][..., :5], rf["dw"][ow][..., :5], "coarse dw")
+    eq(coarse.w[c1][..., :5], rc["w"][c1][..., :5], "coarse w incl. first halos")
+    eq(coarse.p[c1], rc["p"][c1], "coarse p")
+    eq(coarse.w1[c1], rc["w1"][c1], "w1")
+    eq(coarse.p1[c1], rc["p1"][c1], "p1")
+    eq(coarse.dtl[ow], rf["dtl"][ow], "coarse dtl")
+    for n, m in (("radI", "radi"), ("radJ", "radj"), ("radK", "radk")):
+        eq(getattr(coarse, n)[c1], rf[m][c1], n)
+    if prm.equations != 1:
+        eq(coarse.rlv[c1], rf["rlv"][c1], "coarse rlv")
+    if prm.equations == 3:
+        eq(coarse.rev[c1], rc["rev"][c1], "coarse rev")
+
+
+@pytest.mark.parametrize("shape,options", CASES[:3])
+def test_coarse_level_rk_smoother(shape, options):
+    """RungeKuttaSmoother on level 2: dw = wr start, cflCoarse, first-order dissipation, no second halos"""
+    prm, fine, coarse = two_levels(shape, options)
+    oracle_transfer_to_coarse(prm, fine, coarse)
+    f2, c2 = fine.copy(), coarse.copy()
+    mg = rb.RefMG(f2, c2, prm)
+    try:
+        mg.seed_coarse_shared()
+        mg.call(2, "smoothers_rungekuttasmoother")
+    finally:
+        mg.close()
+    rc, rf = mg.lv[2].a, mg.lv[1].a
+    Oracle(coarse, prm).rk_smoother()
+    d = coarse.d
+    c1 = (slice(1, d.ie + 1), slice(1, d.je + 1), slice(1, d.ke + 1))
+    assert np.abs(coarse.w[d.owned()][..., :5] - c2.w[d.owned()][..., :5]).max() > 0
+    eq(coarse.w[c1][..., :5], rc["w"][c1][..., :5], "coarse w after the RK cycle")
+    eq(coarse.p[c1], rc["p"][c1], "coarse p after the RK cycle")
+    eq(coarse.dw[d.owned()][..., :5], rf["dw"][d.owned()][..., :5], "coarse dw")
+
+
+@pytest.mark.parametrize("shape,options", CASES)
+@pytest.mark.parametrize("neumann", [0, 1])
+def test_transfer_to_fine_grid(shape, options, neumann):
+    prm, fine, coarse = two_levels(shape, options)
+    prm.mgBoundCorr = neumann
+    oracle_transfer_to_coarse(prm, fine, coarse)
+    Oracle(coarse, prm).rk_smoother()        # something to interpolate
+    f2, c2 = fine.copy(), coarse.copy()
+    mg = rb.RefMG(f2, c2, prm)
+    try:
+        mg.transfer_to_fine()
+    finally:
+        mg.close()
+    rf, rc = mg.lv[1].a, mg.lv[2].a
+    of, oc = Oracle(fine, prm), Oracle(coarse, prm)
+    of.mg_prolong(oc)
+    of.apply_flow_bc(True)                   # applyAllBC(secondHalo = .true.); whalo2: no neighbours
+    d, dc = fine.d, coarse.d
+    c1c = (slice(1, dc.ie + 1), slice(1, dc.je + 1), slice(1, dc.ke + 1))
+    eq(coarse.w[c1c][..., :5], rc["w"][c1c][..., :5], "corrections on the coarse block (incl. boundary halos)")
+    eq(fine.dw[d.owned()][..., :5], rf["dw"][d.owned()][..., :5], "interpolated corrections")
+    assert np.abs(fine.w[d.owned()][..., :5] - f2.w[d.owned()][..., :5]).max() > 0
+    eq(fine.w[..., :5], rf["w"][..., :5], "fine w (whole box)")
+    eq(fine.p, rf["p"], "fine p")
+    if prm.equations != 1:
+        eq(fine.rlv, rf["rlv"], "fine rlv")
+    if prm.equations == 3:
+        eq(fine.rev, rf["rev"], "fine rev")
+
+
+def test_coarse_dissipation_and_corner_row_halos():
+    prm, fine, coarse = two_levels((10, 8, 6), None)
+    oracle_transfer_to_coarse(prm, fine, coarse)
+    rng = np.random.default_rng(1)
+    coarse.fw[...] = 1e-3 * rng.standard_normal(coarse.fw.shape)
+    c2 = coarse.copy()
+    mg = rb.RefMG(fine.copy(), c2, prm)
+    try:
+        mg.seed_coarse_shared()
+        rb._setd("rfil", 0.56)
+        mg.call(2, "fluxes_invisciddissfluxscalarcoarse")
+        mg.call(2, "multigrid_setcornerrowhalos", 5)
+    finally:
+        mg.close()
+    rc = mg.lv[2].a
+    oc = Oracle(coarse, prm)
+    oc.diss_scalar_coarse(0.56)
+    oc.mg_corner_row_halos()
+    ow = coarse.d.owned()
+    eq(coarse.fw[ow], mg.lv[1].a["fw"][ow], "fw")
+    eq(coarse.w[..., :5], rc["w"][..., :5], "w after the momentum round trip + corner row halos")
+    eq(coarse.p, rc["p"], "p")
