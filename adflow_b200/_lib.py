@@ -22,6 +22,7 @@ ABI_SYMBOLS = [
     "adfb_comm_set_pattern", "adfb_comm_set_overset", "adfb_halo_exchange",
     "adfb_reference_shock_sensor", "adfb_form_function", "adfb_mffd_set_base", "adfb_mffd_apply", "adfb_mffd_apply_device", "adfb_mffd_last_h",
     "adfb_apply_bcs", "adfb_timestep", "adfb_smoother_residual", "adfb_rk_stage", "adfb_rk_cycle", "adfb_dadi_step", "adfb_dadi_cycle", "adfb_sa_ddadi",
+    "adfb_block_set_mg", "adfb_mg_restrict", "adfb_mg_prolong", "adfb_mg_cycle",
 ]
 
 
@@ -93,6 +94,10 @@ def load():
     L.adfb_dadi_step.argtypes = [ci]
     L.adfb_dadi_cycle.argtypes = [ci, ci]
     L.adfb_sa_ddadi.argtypes = [ci, ci]
+    L.adfb_block_set_mg.argtypes = [ci, ci] + [vp] * 9
+    L.adfb_mg_restrict.argtypes = [ci]
+    L.adfb_mg_prolong.argtypes = [ci]
+    L.adfb_mg_cycle.argtypes = [ci, vp, ci]
     L.adfb_launch_count.restype = C.c_longlong
     L.adfb_stream.restype = C.c_void_p
     _lib = L

@@ -56,6 +56,11 @@ struct BlockDev {
     // stride wallP, in-plane index ia + (dir == 0 ? NJ : NI) * jb
     double *wallTau;
     long long wallP;
+    // multigrid: residual forcing term (5), solution at the start of the coarse-level visit (5 / 1), and the
+    // level flag: coarse = 1 on levels > 1 (no directional scaling of the radii, constant-pressure walls, frozen
+    // eddy viscosity, first-order dissipation: the currentLevel > groundLevel branches of the reference)
+    double *wr, *w1, *p1;
+    int coarse;
 };
 
 // single translation unit (adflow_b200.cu includes every *_kernels.cuh)

@@ -19,6 +19,7 @@
 #include "state_kernels.cuh"
 #include "residual_kernels.cuh"
 #include "smoother_kernels.cuh"
+#include "mg_kernels.cuh"
 #include "halo_kernels.cuh"
 #include "dadi_kernels.cuh"
 #include "sa_kernels.cuh"
@@ -35,6 +36,11 @@ struct Block {
     std::vector<AdfbSubface> subfaces;  // host copies (device arrays in bcDev)
     size_t slabBytes = 0;               // w, p, rlv, rev slab
     std::vector<void*> bcAllocs;
+    // multigrid: the next finer / coarser block of the same mesh block and the transfer tables (on the coarse
+    // block: mg?Fine, mg?Weight; the fine block's mg?Coarse are kept with the coarse block as well)
+    int fineBlk = -1, coarseBlk = -1;
+    MgTables mg = {};
+    std::vector<void*> mgAllocs;
 };
 
 struct Context {
@@ -76,12 +82,16 @@ struct Context {
         int tabBlocks = 0;
         std::map<int, CommVarTable*> tabs;  // key: start | end<<4 | commP<<8 | commV<<9
         std::vector<void*> allocs;
-    } pat, ovPat;   // 1-to-1 (commPatternCell_2nd / internalCell_2nd) and overset (commPatternOverset / internalOverset)
+    };
+    // per grid level: 1-to-1 (commPatternCell_2nd / internalCell_2nd; _1st lists on coarse levels) and overset
+    // (commPatternOverset / internalOverset)
+    std::map<int, Pattern> pats, ovPats;
     // CUDA graphs of whole entry points (launch-latency bound sequences of small kernels)
     std::map<unsigned long long, cudaGraphExec_t> graphs;
     std::map<unsigned long long, long long> graphLaunches;
     bool useGraphs = true;
     bool capturing = false;
+    int mgInitWr = 1;   // coarse-level smoother residual starts from wr (0 inside transferToCoarseGrid: from zero)
 };
 
 Context g;
@@ -299,10 +309,10 @@ int adfb_finalize(void) {
     for (double** p : {&g.nkA, &g.nkU, &g.nkF0, &g.nkY}) { if (*p) cudaFree(*p); *p = nullptr; }
     g.nkN = 0; g.nkHaveBase = false;
     drop_graphs();
-    for (void* q : g.pat.allocs) cudaFree(q);
-    g.pat = Context::Pattern();
-    for (void* q : g.ovPat.allocs) cudaFree(q);
-    g.ovPat = Context::Pattern();
+    for (auto* M : {&g.pats, &g.ovPats}) {
+        for (auto& kv : *M) for (void* q : kv.second.allocs) cudaFree(q);
+        M->clear();
+    }
     if (g.comm) { g.nccl.CommDestroy(g.comm); g.comm = nullptr; }
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
@@ -386,6 +396,8 @@ int adfb_block_create(int blk, int level, int nx, int ny, int nz, int nw, int ri
     rc |= dalloc(b, &v.wn, N * 5); rc |= dalloc(b, &v.pn, N); rc |= dalloc(b, &v.scratch, N * 10);
     rc |= dalloc(b, &v.ssum, N * 9); rc |= dalloc(b, &v.sv, N * 9); rc |= dalloc(b, &v.ovol, N);
     rc |= dalloc(b, &v.vn, N * 12); rc |= dalloc(b, &v.flux, N * 30); rc |= dalloc(b, &v.shock, N);
+    rc |= dalloc(b, &v.wr, N * 5); rc |= dalloc(b, &v.w1, N * 5); rc |= dalloc(b, &v.p1, N);
+    v.coarse = level > 1 ? 1 : 0;
     {
         const long long pI = (long long)b.d.NJ * b.d.NK, pJ = (long long)b.d.NI * b.d.NK, pK = (long long)b.d.NI * b.d.NJ;
         v.wallP = pI > pJ ? (pI > pK ? pI : pK) : (pJ > pK ? pJ : pK);
@@ -408,6 +420,7 @@ int adfb_block_destroy(int blk) {
     cudaStreamSynchronize(g.stream);
     for (void* q : b->allocs) cudaFree(q);
     for (void* q : b->bcAllocs) cudaFree(q);
+    for (void* q : b->mgAllocs) cudaFree(q);
     *b = Block();
     return 0;
 }
@@ -560,6 +573,9 @@ int adfb_download_array(int blk, const char* name, double* out) {
     else if (s == "radI") src = v.radI;
     else if (s == "radJ") src = v.radJ;
     else if (s == "radK") src = v.radK;
+    else if (s == "wr") { src = v.wr; nc = 5; }
+    else if (s == "w1") { src = v.w1; nc = 5; }
+    else if (s == "p1") src = v.p1;
     else return fail("adfb_download_array: unknown array '%s'", s.c_str());
     if (get(*b, C2, src, out, nc, 8)) return 1;
     CK(cudaStreamSynchronize(g.stream));
@@ -608,7 +624,8 @@ static int pat_upload(T** dst, const std::vector<T>& src) {
     if (src.empty()) return 0;
     void* q = nullptr;
     if (cudaMalloc(&q, src.size() * sizeof(T)) != cudaSuccess) return fail("comm pattern: cudaMalloc failed");
-    (g_upPat ? g_upPat : &g.pat)->allocs.push_back(q);
+    if (!g_upPat) { cudaFree(q); return fail("comm pattern: internal error (no upload target)"); }
+    g_upPat->allocs.push_back(q);
     if (cudaMemcpy(q, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return fail("comm pattern: copy failed");
     *dst = (T*)q;
     return 0;
@@ -695,16 +712,14 @@ int adfb_comm_set_pattern(int level, int nNbr, const int* nbrRank, const int* se
                           const int* sendList, const int* recvList, int nInternal, const int* donorList,
                           const int* haloList) {
     NEED_INIT();
-    (void)level;
-    return set_pattern_impl(g.pat, nNbr, nbrRank, sendCount, recvCount, sendList, nullptr, recvList, nInternal, donorList, nullptr,
+    return set_pattern_impl(g.pats[level], nNbr, nbrRank, sendCount, recvCount, sendList, nullptr, recvList, nInternal, donorList, nullptr,
                             haloList, false);
 }
 int adfb_comm_set_overset(int level, int nNbr, const int* nbrRank, const int* sendCount, const int* recvCount,
                           const int* sendList, const double* sendInterp, const int* recvList, int nInternal,
                           const int* donorList, const double* donorInterp, const int* haloList) {
     NEED_INIT();
-    (void)level;
-    return set_pattern_impl(g.ovPat, nNbr, nbrRank, sendCount, recvCount, sendList, sendInterp, recvList, nInternal, donorList,
+    return set_pattern_impl(g.ovPats[level], nNbr, nbrRank, sendCount, recvCount, sendList, sendInterp, recvList, nInternal, donorList,
                             donorInterp, haloList, true);
 }
 
@@ -714,7 +729,11 @@ static int halo_exchange_impl(int level, int start, int end, int commPressure, i
     const bool viscous = g.prm.equations != ADFB_EULER, eddy = g.prm.equations == ADFB_RANS;
     // whalo1to1 with commPatternCell_2nd / internalCell_2nd, then wOverset with commPatternOverset / internalOverset
     // (whalo2, haloExchange.F90:139-146); orphan averaging is not supported (nOrphans must be 0)
-    for (Context::Pattern* PP : {&g.pat, &g.ovPat}) {
+    Context::Pattern* both[2] = {nullptr, nullptr};
+    { auto it = g.pats.find(level); if (it != g.pats.end()) both[0] = &it->second; }
+    { auto it = g.ovPats.find(level); if (it != g.ovPats.end()) both[1] = &it->second; }
+    for (Context::Pattern* PP : both) {
+        if (!PP) continue;
         Context::Pattern& P = *PP;
         if (!(P.set && (P.nSend || P.nRecv || P.nInt))) continue;
         if ((int)g.blocks.size() != P.tabBlocks) return fail("halo exchange: blocks changed after adfb_comm_set_pattern");
@@ -722,7 +741,7 @@ static int halo_exchange_impl(int level, int start, int end, int commPressure, i
         int nVar = 0;
         {
             Block* b0 = nullptr;
-            for (Block& b : g.blocks) if (b.alive) { b0 = &b; break; }
+            for (Block& b : g.blocks) if (b.alive && b.level == level) { b0 = &b; break; }
             if (!b0) return 0;
             for (int l = start; l <= end && l <= b0->nw; l++) nVar++;
             if (commPressure) nVar++;
@@ -1072,6 +1091,7 @@ int adfb_timestep(int level, int onlyRadii) {
     return 0;
 }
 
+static void launch_mg_cells1(const Dims& d, const BlockDev& b, int mode, cudaStream_t s);
 // `initres(1,nwf); sourceTerms; residual` of the smoother loops (smoothers.F90:73-75,
 // multiGrid.F90:883-888): mean-flow residual with rFil = cdisRK(rkStage+1), fw persistent.
 static int adfb_smoother_residual_body(int level, int rkStage) {
@@ -1081,14 +1101,18 @@ static int adfb_smoother_residual_body(int level, int rkStage) {
     const double rFil = g.prm.cdisRK[rkStage];
     for (Block& b : g.blocks) {
         if (!b.alive || b.level != level) continue;
-        if (launch_residual_core(b.d, b.dev, g.prm, ADFB_RES_FLOW, rFil, 1, 0, g.stream)) return fail("residual launch failed");
+        // coarse level: initRes starts from the residual forcing term (dw = wr)
+        if (launch_residual_core(b.d, b.dev, g.prm, ADFB_RES_FLOW, rFil, 1, 0, g.stream, level > 1 ? g.mgInitWr : 0))
+            return fail("residual launch failed%s", level > 1 && g.prm.spaceDiscrCoarse != ADFB_DISS_SCALAR
+                                                        ? ": only scalar dissipation is supported on coarse levels" : "");
+        if (level > 1 && fabs(rFil) >= 1.e-10) launch_mg_cells1(b.d, b.dev, 2, g.stream);
     }
     CK(cudaGetLastError());
     return 0;
 }
 int adfb_smoother_residual(int level, int rkStage) {
     NEED_INIT();
-    const unsigned long long key = (3ull << 40) | ((unsigned long long)level << 32) | (unsigned)rkStage;
+    const unsigned long long key = (3ull << 40) | ((unsigned long long)level << 32) | ((unsigned)g.mgInitWr << 8) | (unsigned)rkStage;
     set_l2_window();
     return run_graphed(key, [&]() { return adfb_smoother_residual_body(level, rkStage); });
 }
@@ -1100,10 +1124,14 @@ static int adfb_rk_stage_body(int level, int rkStage) {
     if (rkStage < 1 || rkStage > g.prm.nRKStages) return fail("adfb_rk_stage: stage %d out of 1..%d", rkStage, g.prm.nRKStages);
     for (Block& b : g.blocks) {
         if (!b.alive || b.level != level) continue;
-        if (launch_rk_update(b.d, b.dev, g.prm, rkStage, g.stream)) return fail("RK update launch failed");
-        if (launch_bc_flow(b.d, b.dev, b.subfaces, 1, g.stream)) return fail("flow BC launch failed");
+        // currentCfl = cflCoarse unless currentLevel == 1; second halos only on the ground level (smoothers.F90:131-140)
+        AdfbParams prmL = g.prm;
+        if (level > 1) prmL.cfl = g.prm.cflCoarse;
+        if (launch_rk_update(b.d, b.dev, prmL, rkStage, g.stream, level > 1 ? 5 : 0)) return fail("RK update launch failed");
+        if (launch_bc_flow(b.d, b.dev, b.subfaces, level > 1 ? 0 : 1, g.stream)) return fail("flow BC launch failed");
     }
-    // whalo2(level, 1, nwf, T, T, T): the trailing computeEtotBlock is idempotent here
+    // whalo2(level, 1, nwf, T, T, T) / whalo1 on coarse levels (the pattern of the level holds the matching lists):
+    // the trailing computeEtotBlock is idempotent here
     if (halo_exchange_impl(level, 1, 5, 1, 1, false)) return 1;
     CK(cudaGetLastError());
     return 0;
@@ -1199,12 +1227,213 @@ int adfb_rk_cycle(int level) {
     return run_graphed(key, [&]() { return adfb_rk_cycle_body(level); });
 }
 
+
+// ---------------------------------------------------------------------------
+// multigrid (src/solver/multiGrid.F90)
+static void launch_mg_cells1(const Dims& d, const BlockDev& b, int mode, cudaStream_t s) {
+    dim3 tb(32, 4, 2);
+    dim3 gr((d.ie + 31) / 32, (d.je + 3) / 4, (d.ke + 1) / 2);
+    KT_BEGIN(K_MISC, s);
+    launch_pdl(k_mg_cells1, gr, tb, s, d, b, mode);
+    KT_END(K_MISC, s);
+}
+
+int adfb_block_set_mg(int coarseBlk, int fineBlk, const int32_t* mgIFine, const int32_t* mgJFine, const int32_t* mgKFine,
+                      const double* mgIWeight, const double* mgJWeight, const double* mgKWeight, const int32_t* mgICoarse,
+                      const int32_t* mgJCoarse, const int32_t* mgKCoarse) {
+    NEED_INIT();
+    drop_graphs();
+    Block* c = get_block(coarseBlk);
+    Block* f = get_block(fineBlk);
+    if (!c || !f) return fail("adfb_block_set_mg: no block %d / %d", coarseBlk, fineBlk);
+    if (c->level != f->level + 1) return fail("adfb_block_set_mg: block %d (level %d) is not one level coarser than block %d (level %d)",
+                                              coarseBlk, c->level, fineBlk, f->level);
+    if (!mgIFine || !mgJFine || !mgKFine || !mgIWeight || !mgJWeight || !mgKWeight || !mgICoarse || !mgJCoarse || !mgKCoarse)
+        return fail("adfb_block_set_mg: all nine tables are required");
+    // reference extents -> tables indexed by the Fortran index: mg?Fine(1:ie,2), mg?Weight(2:il), mg?Coarse(2:il_f,2)
+    const int ce[3] = {c->d.ie, c->d.je, c->d.ke}, cl[3] = {c->d.il, c->d.jl, c->d.kl};
+    const int fe[3] = {f->d.ie, f->d.je, f->d.ke}, fl[3] = {f->d.il, f->d.jl, f->d.kl};
+    const int32_t* fin[3] = {mgIFine, mgJFine, mgKFine};
+    const double* wgt[3] = {mgIWeight, mgJWeight, mgKWeight};
+    const int32_t* coa[3] = {mgICoarse, mgJCoarse, mgKCoarse};
+    for (void* q : c->mgAllocs) cudaFree(q);
+    c->mgAllocs.clear();
+    const int* dF[3]; const double* dW[3]; const int* dC[3];
+    for (int a = 0; a < 3; a++) {
+        std::vector<int> hf((size_t)(ce[a] + 1) * 2, 0), hc((size_t)(fe[a] + 1) * 2, 0);
+        std::vector<double> hw((size_t)ce[a] + 1, 0.0);
+        for (int m = 0; m < 2; m++)
+            for (int i = 1; i <= ce[a]; i++) {
+                const int v = fin[a][(i - 1) + ce[a] * m];
+                if (v < 0 || v > fe[a] + 1) return fail("adfb_block_set_mg: mgFine entry %d out of the fine block", v);
+                hf[i + (ce[a] + 1) * m] = v;
+            }
+        for (int i = 2; i <= cl[a]; i++) hw[i] = wgt[a][i - 2];
+        for (int m = 0; m < 2; m++)
+            for (int i = 2; i <= fl[a]; i++) {
+                const int v = coa[a][(i - 2) + (fl[a] - 1) * m];
+                if (v < 1 || v > ce[a]) return fail("adfb_block_set_mg: mgCoarse entry %d out of the coarse block (1:%d)", v, ce[a]);
+                hc[i + (fe[a] + 1) * m] = v;
+            }
+        void *q1 = nullptr, *q2 = nullptr, *q3 = nullptr;
+        CK(cudaMalloc(&q1, hf.size() * sizeof(int))); c->mgAllocs.push_back(q1);
+        CK(cudaMalloc(&q2, hw.size() * sizeof(double))); c->mgAllocs.push_back(q2);
+        CK(cudaMalloc(&q3, hc.size() * sizeof(int))); c->mgAllocs.push_back(q3);
+        CK(cudaMemcpy(q1, hf.data(), hf.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(q2, hw.data(), hw.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(q3, hc.data(), hc.size() * sizeof(int), cudaMemcpyHostToDevice));
+        dF[a] = (const int*)q1; dW[a] = (const double*)q2; dC[a] = (const int*)q3;
+    }
+    c->mg.fI = dF[0]; c->mg.fJ = dF[1]; c->mg.fK = dF[2];
+    c->mg.wI = dW[0]; c->mg.wJ = dW[1]; c->mg.wK = dW[2];
+    c->mg.cI = dC[0]; c->mg.cJ = dC[1]; c->mg.cK = dC[2];
+    c->fineBlk = fineBlk; f->coarseBlk = coarseBlk;
+    return 0;
+}
+
+// transferToCoarseGrid, multiGrid.F90:5-324: from `fineLevel` to fineLevel + 1
+static int adfb_mg_restrict_body(int fineLevel) {
+    const int cl = fineLevel + 1;
+    // fine residual: rkStage = 0; timeStep(.true.) = spectral radii only; initres; residual
+    if (adfb_timestep(fineLevel, 1)) return 1;
+    if (adfb_smoother_residual(fineLevel, 0)) return 1;
+    bool any = false;
+    for (Block& c : g.blocks) {
+        if (!c.alive || c.level != cl) continue;
+        if (c.fineBlk < 0) return fail("adfb_mg_restrict: block of level %d without adfb_block_set_mg", cl);
+        if (!c.haveMetrics) return fail("adfb_mg_restrict: geometry of a coarse block was never set");
+        Block& f = g.blocks[c.fineBlk];
+        any = true;
+        dim3 tb(32, 4, 1);
+        dim3 gr((c.d.nx + 31) / 32, (c.d.ny + 3) / 4, c.d.nz);
+        KT_BEGIN(K_MISC, g.stream);
+        launch_pdl(k_mg_restrict, gr, tb, g.stream, c.d, c.dev, f.d, f.dev, c.mg);
+        KT_END(K_MISC, g.stream);
+        KT_BEGIN(K_MISC, g.stream);
+        launch_pdl(k_mg_corner_rows, dim3(1), dim3(256), g.stream, c.d, c.dev);
+        KT_END(K_MISC, g.stream);
+        if (launch_bc_flow(c.d, c.dev, c.subfaces, 0, g.stream)) return fail("flow BC launch failed");
+    }
+    if (!any) return fail("adfb_mg_restrict: no blocks on level %d", cl);
+    // whalo1(currentLevel, 1, nwf, T, T, T)
+    if (halo_exchange_impl(cl, 1, 5, 1, 1, false)) return 1;
+    if (adfb_timestep(cl, 0)) return 1;
+    for (Block& c : g.blocks) {
+        if (!c.alive || c.level != cl) continue;
+        launch_mg_cells1(c.d, c.dev, 0, g.stream);
+    }
+    // residual of the restricted solution, started from zero, rFil = cdisRK(1)
+    g.mgInitWr = 0;
+    const int rc = adfb_smoother_residual(cl, 0);
+    g.mgInitWr = 1;
+    if (rc) return 1;
+    for (Block& c : g.blocks) {
+        if (!c.alive || c.level != cl) continue;
+        dim3 tb(32, 4, 2);
+        dim3 gr((c.d.nx + 31) / 32, (c.d.ny + 3) / 4, (c.d.nz + 1) / 2);
+        KT_BEGIN(K_MISC, g.stream);
+        launch_pdl(k_mg_forcing, gr, tb, g.stream, c.d, c.dev, g.prm.fcoll);
+        KT_END(K_MISC, g.stream);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+int adfb_mg_restrict(int fineLevel) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_mg_restrict: adfb_set_params has not been called");
+    const unsigned long long key = (8ull << 40) | ((unsigned long long)fineLevel << 32);
+    set_l2_window();
+    return run_graphed(key, [&]() { return adfb_mg_restrict_body(fineLevel); });
+}
+
+// transferToFineGrid(corrections = .true.), multiGrid.F90:326-654: from fineLevel + 1 to `fineLevel`
+static int adfb_mg_prolong_body(int fineLevel) {
+    const int cl = fineLevel + 1;
+    const double fact = g.prm.mgBoundCorr == 0 ? 0.0 : 1.0;
+    for (Block& c : g.blocks) {
+        if (!c.alive || c.level != cl) continue;
+        if (c.fineBlk < 0) return fail("adfb_mg_prolong: block of level %d without adfb_block_set_mg", cl);
+        Block& f = g.blocks[c.fineBlk];
+        launch_mg_cells1(c.d, c.dev, 1, g.stream);
+        for (const AdfbSubface& sf : c.subfaces) {   // setCorrectionsCoarseHalos: BCData order
+            FaceDev fd = make_face(c.d, sf);
+            dim3 tb(32, 4);
+            dim3 gr((fd.icEnd - fd.icBeg + 1 + 31) / 32, (fd.jcEnd - fd.jcBeg + 1 + 3) / 4);
+            KT_BEGIN(K_BC, g.stream);
+            launch_pdl(k_mg_corr_halos, gr, tb, g.stream, c.d, c.dev, fd, fact);
+            KT_END(K_BC, g.stream);
+        }
+        dim3 tb(32, 4, 1);
+        dim3 gr((f.d.nx + 31) / 32, (f.d.ny + 3) / 4, f.d.nz);
+        KT_BEGIN(K_MISC, g.stream);
+        launch_pdl(k_mg_prolong, gr, tb, g.stream, f.d, f.dev, c.d, c.dev, c.mg, f.nw);
+        KT_END(K_MISC, g.stream);
+        // applyAllBC(secondHalo): second halos on the ground level only
+        if (launch_bc_flow(f.d, f.dev, f.subfaces, fineLevel > 1 ? 0 : 1, g.stream)) return fail("flow BC launch failed");
+    }
+    if (halo_exchange_impl(fineLevel, 1, 5, 1, 1, false)) return 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+int adfb_mg_prolong(int fineLevel) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_mg_prolong: adfb_set_params has not been called");
+    const unsigned long long key = (9ull << 40) | ((unsigned long long)fineLevel << 32);
+    set_l2_window();
+    return run_graphed(key, [&]() { return adfb_mg_prolong_body(fineLevel); });
+}
+
+// executeMGCycle, multiGrid.F90:825-955, for the cycling strategy of setCycleStrategy (:957-1030): entries
+// -1 = prolongate to the next finer level, 0 = smoothing step, +1 = restrict to the next coarser level.
+// Ground level 1.  The turbulence solve and the final residual of the cycle are included (:933-951).
+static int adfb_mg_cycle_body(int nSteps, const int* cycling, int smoother) {
+    int level = 1;
+    for (int n = 0; n < nSteps; n++) {
+        switch (cycling[n]) {
+            case -1:
+                level -= 1;
+                if (level < 1) return fail("adfb_mg_cycle: cycling strategy leaves the grid hierarchy");
+                if (adfb_mg_prolong(level)) return 1;
+                break;
+            case 0:
+                if (n > 0 && cycling[n - 1] != 1) {
+                    if (adfb_timestep(level, 0)) return 1;
+                    if (adfb_smoother_residual(level, 0)) return 1;
+                }
+                if (smoother == 0) { if (adfb_rk_cycle(level)) return 1; }
+                else return fail("adfb_mg_cycle: only the Runge-Kutta smoother is available on the multigrid path");
+                break;
+            case 1:
+                if (adfb_mg_restrict(level)) return 1;
+                level += 1;
+                break;
+            default: return fail("adfb_mg_cycle: cycling entry %d", cycling[n]);
+        }
+    }
+    if (level != 1) return fail("adfb_mg_cycle: the strategy does not end on the ground level");
+    if (g.prm.equations == ADFB_RANS)
+        if (adfb_sa_ddadi(1, g.prm.nSubiterTurb)) return 1;
+    if (adfb_timestep(1, 0)) return 1;
+    return adfb_smoother_residual(1, 0);
+}
+int adfb_mg_cycle(int nSteps, const int* cycling, int smoother) {
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_mg_cycle: adfb_set_params has not been called");
+    if (nSteps < 1 || nSteps > 4096 || !cycling) return fail("adfb_mg_cycle: bad cycling strategy");
+    unsigned long long h = 1469598103934665603ull;
+    for (int n = 0; n < nSteps; n++) h = (h ^ (unsigned long long)(cycling[n] + 2)) * 1099511628211ull;
+    const unsigned long long key = (10ull << 40) | (h & 0xffffffffffull);
+    set_l2_window();
+    std::vector<int> cyc(cycling, cycling + nSteps);
+    return run_graphed(key, [&]() { return adfb_mg_cycle_body(nSteps, cyc.data(), smoother); });
+}
+
 int adfb_norms(double out[2]) {
     NEED_INIT();
     if (!out) return fail("adfb_norms: null");
     out[0] = out[1] = 0.0;
     for (Block& b : g.blocks) {
-        if (!b.alive) continue;
+        if (!b.alive || b.level != 1) continue;
         const int nPart = 1024;
         if (g.dRedN < (size_t)2 * nPart + 2) {
             if (g.dRed) cudaFree(g.dRed);

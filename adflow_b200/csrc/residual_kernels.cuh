@@ -166,6 +166,9 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
     double rj = 0.5 * (fabs(ux * sxj + uy * syj + uz * szj) + asf * sqrt(cc2 * s2j));
     double rk = 0.5 * (fabs(ux * sxk + uy * syk + uz * szk) + asf * sqrt(cc2 * s2k));
     double dt = ri + rj + rk;
+    if (b.coarse) {   // doScaling = dirScaling .and. currentLevel <= groundLevel (solverUtils.F90:106)
+        b.radI[c] = ri; b.radJ[c] = rj; b.radK[c] = rk;
+    } else {
     ri = dmax_(ri, 1.e-25); rj = dmax_(rj, 1.e-25); rk = dmax_(rk, 1.e-25);
     // (ri/rj)**adis etc. via three logs and three exps (|adis*log(ratio)| < 10: error < 1e-15)
     const double li = log(ri), lj = log(rj), lk = log(rk);
@@ -174,6 +177,7 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
     b.radI[c] = ri * (1.0 + 1.0 / rij + 1.0 / rik);
     b.radJ[c] = rj * (1.0 + 1.0 / rjk + rij);
     b.radK[c] = rk * (1.0 + rik + rjk);
+    }
 
     if (!updateDt) return;
     if (i < 2 || i > d.il || j < 2 || j > d.jl || k < 2 || k > d.kl) return;
@@ -284,7 +288,8 @@ __device__ __forceinline__ CellState load_cell(const BlockDev& b, int N, int c) 
     return s;
 }
 
-// APPROX bit 0: first-order/lumped dissipation (*Approx routines), bit 1: thin-layer viscous flux
+// APPROX bit 0: first-order/lumped dissipation (*Approx routines), bit 1: thin-layer viscous flux,
+// bit 2: first-order coarse-level scalar dissipation (inviscidDissFluxScalarCoarse, fluxes.F90:4977-5203)
 template <bool VISCOUS, int DISC, int APPROX>
 __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int sd, int t1, int t2, int dir,
                                           const double* __restrict__ s, int8_t por, const double* __restrict__ rad,
@@ -311,7 +316,16 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
     }
 #pragma unroll
     for (int l = 0; l < 5; l++) fd[l] = 0.0;
-    if (DISC == ADFB_DISS_SCALAR && !(APPROX & 1) && doDiss) {  // scalar JST
+    if (DISC == ADFB_DISS_SCALAR && (APPROX & 4) && doDiss) {
+        const double ppor = (por == ADFB_NORMALFLUX) ? 0.5 : 0.0;
+        const double dis0 = rFil * c_prm.vis2Coarse * ppor * (rad[c] + rad[cp]);
+        fd[0] = dis0 * (q.r - m.r);
+        fd[1] = dis0 * (q.u * q.r - m.u * m.r);
+        fd[2] = dis0 * (q.v * q.r - m.v * m.r);
+        fd[3] = dis0 * (q.w * q.r - m.w * m.r);
+        fd[4] = dis0 * ((q.e + q.p) - (m.e + m.p));
+    }
+    if (DISC == ADFB_DISS_SCALAR && !(APPROX & 5) && doDiss) {  // scalar JST
         const CellState mm = load_cell(b, N, c - sd), qq = load_cell(b, N, cp + sd);
         const double fis2 = rFil * c_prm.vis2, fis4 = rFil * c_prm.vis4;
         const double ppor = (por == ADFB_NORMALFLUX) ? 0.5 : 0.0;
@@ -329,7 +343,7 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
         ddw = (q.e + q.p) - (m.e + m.p);
         fd[4] = dis2 * ddw - dis4 * ((qq.e + qq.p) - (mm.e + mm.p) - 3.0 * ddw);
     }
-    if (DISC == ADFB_DISS_SCALAR && (APPROX & 1) && doDiss) {  // inviscidDissFluxScalarApprox, blockette.F90:4367-4617
+    if (DISC == ADFB_DISS_SCALAR && (APPROX & 1) && !(APPROX & 4) && doDiss) {  // inviscidDissFluxScalarApprox, blockette.F90:4367-4617
         const double ppor = (por == ADFB_NORMALFLUX) ? 0.5 : 0.0;
         const double rrad = ppor * (rad[c] + rad[cp]);
         const double dis2 = c_prm.vis2 * rrad * dmin_(0.25, dmax_(dss[c], dss[cp])) + c_prm.sigma * c_prm.vis4 * rrad;
@@ -762,7 +776,7 @@ __global__ void __launch_bounds__(SA_TPB, SA_MINB) k_sa(Dims d, BlockDev b) {
 // k_div: flux divergence + sumDwandFw epilogue (blockette.F90:6839-6864) for one owned cell.
 // Order per variable: -Fi(c-1) +Fi(c) -Fj(c-sJ) +Fj(c) -Fk(c-sK) +Fk(c), like the reference's sweeps.
 template <bool MERGED>
-__global__ void __launch_bounds__(256) k_div(Dims d, BlockDev b, double rFil, int persistFw) {
+__global__ void __launch_bounds__(256) k_div(Dims d, BlockDev b, double rFil, int persistFw, int initWr) {
     cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
@@ -788,7 +802,7 @@ __global__ void __launch_bounds__(256) k_div(Dims d, BlockDev b, double rFil, in
         const double sfil = 1.0 - rFil;
 #pragma unroll
         for (int l = 0; l < 5; l++) {
-            double a = 0.0;
+            double a = initWr ? b.wr[l * N + c] : 0.0;   // initRes on a coarse level: dw = wr (residuals.F90:485-497)
             a -= F[l * N + c - 1];
             a += F[l * N + c];
             a -= F[(10 + l) * N + c - sJ];
@@ -822,7 +836,7 @@ static int launch_geom(const Dims& d, const BlockDev& b, cudaStream_t stream) {
 
 // doRad: 1 = recompute spectral radii + dtl (blockette order), 0 = keep them (block/smoother path)
 static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbParams& prm, unsigned flags, double rFil,
-                                int persistFw, int doRad, cudaStream_t stream) {
+                                int persistFw, int doRad, cudaStream_t stream, int initWr = 0) {
     const int flowRes = (flags & ADFB_RES_FLOW) != 0;
     const int turbRes = ((flags & ADFB_RES_TURB) != 0) && prm.equations == ADFB_RANS;
     const int updateDt = 1;  // blockette timeStep always computes dtl (blockette.F90:1929-1932)
@@ -891,7 +905,11 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
     } while (0)
         const int approx = dissApprox | (viscApprox << 1);
         const bool storeWall = (flags & ADFB_RES_STORE_WALL) && viscous && doVisc && merged && approx == 0;
-        if (storeWall) {  // exact viscous flux + viscSubface%tau/%q planes for the force integration
+        if (b.coarse) {   // coarse multigrid level: first-order scalar dissipation, block path only
+            if (merged || approx || prm.spaceDiscrCoarse != ADFB_DISS_SCALAR) return 1;
+            if (viscous) launch_pdl(k_faces<true, false, ADFB_DISS_SCALAR, 4>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+            else launch_pdl(k_faces<false, false, ADFB_DISS_SCALAR, 4>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+        } else if (storeWall) {  // exact viscous flux + viscSubface%tau/%q planes for the force integration
             if (prm.spaceDiscr == ADFB_DISS_SCALAR) launch_pdl(k_faces<true, true, ADFB_DISS_SCALAR, 0, true>, g, tr, stream, d, b, rFil, doVisc, doDiss);
             else if (prm.spaceDiscr == ADFB_DISS_MATRIX) launch_pdl(k_faces<true, true, ADFB_DISS_MATRIX, 0, true>, g, tr, stream, d, b, rFil, doVisc, doDiss);
             else launch_pdl(k_faces<true, true, ADFB_UPWIND, 0, true>, g, tr, stream, d, b, rFil, doVisc, doDiss);
@@ -910,8 +928,8 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         KT_END(K_RESID, stream);
         dim3 g2((d.nx + tb.x - 1) / tb.x, (d.ny + tb.y - 1) / tb.y, (d.nz + tb.z - 1) / tb.z);
         KT_BEGIN(K_DIV, stream);
-        if (merged) launch_pdl(k_div<true>, g2, tb, stream, d, b, rFil, persistFw);
-        else launch_pdl(k_div<false>, g2, tb, stream, d, b, rFil, persistFw);
+        if (merged) launch_pdl(k_div<true>, g2, tb, stream, d, b, rFil, persistFw, 0);
+        else launch_pdl(k_div<false>, g2, tb, stream, d, b, rFil, persistFw, initWr);
         KT_END(K_DIV, stream);
     }
     if (fork) cudaStreamWaitEvent(stream, s_join, 0);

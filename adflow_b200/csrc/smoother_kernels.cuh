@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, 
             w[3 * N + c1] = -w[3 * N + c2] + 2.0 * us3;
             b.rlv[c1] = b.rlv[c2];
             if (eddy) b.rev[c1] = -b.rev[c2];
-            if (c_prm.wallBCConstantPressure) {
+            if (c_prm.wallBCConstantPressure || b.coarse) {   // BCRoutines.F90:550,642: coarse levels use constant pressure
                 b.p[c1] = b.p[c2];
             } else {
                 double p1 = 2.0 * b.p[c2] - b.p[c3];
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, 
             t1 = dmax_(0.5 * tw, t1);
             t1 = dmin_(2.0 * tw, t1);
             double p1;
-            if (c_prm.wallBCConstantPressure) {
+            if (c_prm.wallBCConstantPressure || b.coarse) {   // BCRoutines.F90:550,642: coarse levels use constant pressure
                 p1 = b.p[c2];
             } else {
                 p1 = 2.0 * b.p[c2] - b.p[c3];
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, 
             break;
         }
         case ADFB_BC_EULERWALL: {  // bcEulerWall, BCRoutines.F90:1063-1280 (constant / linear pressure)
-            const double grad = c_prm.reserved ? 0.0 : b.p[c3] - b.p[c2];
+            const double grad = (c_prm.reserved || b.coarse) ? 0.0 : b.p[c3] - b.p[c2];   // BCRoutines.F90:1100
             b.p[c1] = dmax_(b.p[c2] - grad, 0.0);
             const double u = w[N + c2], v = w[2 * N + c2], ww = w[3 * N + c2];
             const double vn = 2.0 * (rface - u * n1 - v * n2 - ww * n3);
@@ -622,12 +622,12 @@ static int launch_residual_averaging(const Dims& d, const BlockDev& b, const Adf
     return (int)cudaGetLastError();
 }
 
-static int launch_rk_update(const Dims& d, const BlockDev& b, const AdfbParams& prm, int rkStage, cudaStream_t s) {
+static int launch_rk_update(const Dims& d, const BlockDev& b, const AdfbParams& prm, int rkStage, cudaStream_t s, int nwOverride = 0) {
     const double tmp = prm.cfl * prm.etaRK[rkStage - 1];
     const bool smooth = prm.resAveraging == 1 || (prm.resAveraging == 2 && (rkStage % 2) == 1);
     dim3 tb(32, 4, 2);
     dim3 g((d.nx + 31) / 32, (d.ny + 3) / 4, (d.nz + 1) / 2);
-    const int nw = prm.equations == ADFB_RANS ? 6 : 5;
+    const int nw = nwOverride ? nwOverride : (prm.equations == ADFB_RANS ? 6 : 5);   // 5: eddy viscosity frozen (coarse levels)
     if (smooth) {
         KT_BEGIN(K_RK, s);
         launch_pdl(k_rk_scale, g, tb, s, d, b, tmp);

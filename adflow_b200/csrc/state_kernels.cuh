@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) k_state_prep(Dims d, BlockDev b, int incl
     const double T = p / (c_prm.RGas * rho);
     const double rlv = c_prm.muSuth * ((c_prm.TSuth + c_prm.SSuth) / (T + c_prm.SSuth)) * pow(T / c_prm.TSuth, 1.5);
     b.rlv[c] = rlv;
-    if (c_prm.equations != ADFB_RANS || nw < 6) return;
+    if (c_prm.equations != ADFB_RANS || nw < 6 || b.coarse) return;  // computeEddyViscosity: ground level only
     const double rnuSA = b.w[5 * N + c] * rho;
     const double chi = rnuSA / rlv;
     const double chi3 = chi * chi * chi;

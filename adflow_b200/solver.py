@@ -129,6 +129,60 @@ class ADFLOW_B200:
         """DADISmoother (src/solver/smoothers.F90:383)."""
         check(self.L.adfb_dadi_cycle(level, n_subiterations), "adfb_dadi_cycle")
 
+    # -- multigrid (src/solver/multiGrid.F90) ----------------------------------------------------------------
+    def addCoarseBlock(self, coarse_hb, fine_blk):
+        """Device mirror of the next coarser level of block `fine_blk` + the transfer tables (createCoarseBlocks,
+        src/preprocessing/coarseUtils.F90): coarse_hb.mg holds mg?Fine / mg?Weight, the fine HostBlock's mg holds
+        mg?Coarse (see synthetic.make_coarse_block).  Returns the coarse block id."""
+        fine_hb = self.blocks[fine_blk]
+        blk = self.addBlock(coarse_hb, level=coarse_hb.level)
+        dc, df = coarse_hb.d, fine_hb.d
+        f = np.asfortranarray
+        tabs = []
+        for nm, e in zip("IJK", (dc.ie, dc.je, dc.ke)):
+            tabs.append(f(coarse_hb.mg["mg%sFine" % nm][1:e + 1, :].astype(np.int32)))
+        for nm, l in zip("IJK", (dc.il, dc.jl, dc.kl)):
+            tabs.append(np.ascontiguousarray(coarse_hb.mg["mg%sWeight" % nm][2:l + 1], dtype=np.float64))
+        for nm, l in zip("IJK", (df.il, df.jl, df.kl)):
+            tabs.append(f(fine_hb.mg["mg%sCoarse" % nm][2:l + 1, :].astype(np.int32)))
+        check(self.L.adfb_block_set_mg(blk, fine_blk, *[t.ctypes.data for t in tabs]), "adfb_block_set_mg")
+        return blk
+
+    def mgRestrict(self, fine_level=1):
+        """transferToCoarseGrid from fine_level to fine_level + 1"""
+        check(self.L.adfb_mg_restrict(fine_level), "adfb_mg_restrict")
+
+    def mgProlong(self, fine_level=1):
+        """transferToFineGrid(corrections=.true.) from fine_level + 1 to fine_level"""
+        check(self.L.adfb_mg_prolong(fine_level), "adfb_mg_prolong")
+
+    @staticmethod
+    def cycleStrategy(spec):
+        """inputIteration%cycleStrategy of the pyADflow option MGCycle ('sg', '2v', '3w', ...), extractMgInfo /
+        setEntriesWcycle, src/inputParam/inputParamRoutines.F90:880-945,1127-1180: an n-level V cycle is
+        (0 1)^(n-1) (0 -1)^(n-1); a W cycle is 0 1 W(n-1) W(n-1) 0 -1 with W(2) = 0 1 0 -1."""
+        spec = spec.lower()
+        if spec == "sg":
+            return [0]
+        n, kind = int(spec[:-1]), spec[-1]
+        if n < 2 or kind not in "vw":
+            raise ValueError("MGCycle must be sg, <n>v or <n>w with n >= 2")
+        if kind == "v":
+            return [0, 1] * (n - 1) + [0, -1] * (n - 1)
+
+        def wcyc(levels):
+            if levels == 2:
+                return [0, 1, 0, -1]
+            inner = wcyc(levels - 1)
+            return [0, 1] + inner + inner + [0, -1]
+
+        return wcyc(n)
+
+    def mgCycle(self, cycling, smoother="RK"):
+        """executeMGCycle on ground level 1 with cycling in {-1, 0, +1} (iteration%cycling)"""
+        cyc = np.ascontiguousarray(cycling, dtype=np.int32)
+        check(self.L.adfb_mg_cycle(len(cyc), cyc.ctypes.data, {"RK": 0}[smoother]), "adfb_mg_cycle")
+
     def turbSolveDDADI(self, n_sub_iter_turb=None, level=1):
         """turbSolveDDADI (src/turbulence/turbAPI.F90:4)."""
         n = self.prm.nSubiterTurb if n_sub_iter_turb is None else n_sub_iter_turb

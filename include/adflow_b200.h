@@ -290,6 +290,32 @@ int adfb_sa_ddadi(int level, int nSubIterTurb);
 /* DADISmoother (src/solver/smoothers.F90:383-421) */
 int adfb_dadi_cycle(int level, int nSubiterations);
 
+/* ---- multigrid (src/solver/multiGrid.F90) ------------------------------------------------------------------
+   Grid levels: blocks created with level = 1 (finest) .. n; geometry, BCs and the communication pattern are set
+   per block / per level like on the finest level (coarse levels exchange the first halos only: pass the 1st-halo
+   lists, commPatternCell_1st / internalCell_1st).  On levels > 1 the entry points take the reference's
+   currentLevel > groundLevel branches: dw starts from the residual forcing term wr (initRes_block,
+   residuals.F90:485-497), first-order scalar dissipation with vis2Coarse (inviscidDissFluxScalarCoarse,
+   fluxes.F90:4977-5203; spaceDiscrCoarse must be ADFB_DISS_SCALAR), no directional scaling of the spectral radii
+   (solverUtils.F90:106), cflCoarse and no second halos in the RK stage (smoothers.F90:131-140), constant-pressure
+   walls (BCRoutines.F90:550,642,1100), frozen eddy viscosity (turbUtils.F90:606-616).
+   adfb_block_set_mg: tables of createCoarseBlocks (src/preprocessing/coarseUtils.F90:254-420) with the reference's
+   extents: mg{I,J,K}Fine(1:ie,2), mg{I,J,K}Weight(2:il) of the COARSE block, mg{I,J,K}Coarse(2:il,2) of the FINE block. */
+int adfb_block_set_mg(int coarseBlk, int fineBlk, const int32_t* mgIFine, const int32_t* mgJFine, const int32_t* mgKFine,
+                      const double* mgIWeight, const double* mgJWeight, const double* mgKWeight, const int32_t* mgICoarse,
+                      const int32_t* mgJCoarse, const int32_t* mgKCoarse);
+/* transferToCoarseGrid (multiGrid.F90:5-324) from fineLevel to fineLevel + 1: fine residual, restriction of the
+   solution (volume weighted) and of the residual, setCornerRowHalos, applyAllBC(.false.), whalo1, timeStep, w1/p1,
+   coarse residual and the residual forcing term wr (relaxation fcoll) */
+int adfb_mg_restrict(int fineLevel);
+/* transferToFineGrid(corrections = .true.) (multiGrid.F90:326-654) from fineLevel + 1 to fineLevel: corrections
+   w - w1 / p - p1, setCorrectionsCoarseHalos (mgBoundCorr), trilinear interpolation, state update, BCs, exchange */
+int adfb_mg_prolong(int fineLevel);
+/* executeMGCycle (multiGrid.F90:825-955) on ground level 1 with the strategy of setCycleStrategy (:957-1030):
+   cycling(1:nSteps) in {-1 prolongate, 0 smooth, +1 restrict}; smoother 0 = Runge-Kutta.  Ends like the reference
+   with turbSolveDDADI (RANS), timeStep and the ground-level residual. */
+int adfb_mg_cycle(int nSteps, const int* cycling, int smoother);
+
 #ifdef __cplusplus
 }
 #endif

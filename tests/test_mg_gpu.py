@@ -1,0 +1,186 @@
+"""Multigrid on the device (adfb_mg_restrict / adfb_mg_prolong / adfb_mg_cycle and the coarse-level branches of the
+smoother entry points) against the oracle, which is pinned bit for bit against the reference's multiGrid.F90
+(tests/test_oracle_vs_reference_mg.py).  Tolerances as in test_smoother_parity.py: 1e-12 on residual-like arrays,
+1e-10 on state changes over a smoother cycle."""
+import numpy as np
+import pytest
+
+from adflow_b200 import synthetic as syn
+from adflow_b200.solver import ADFLOW_B200
+from oracle.pyoracle import Oracle
+
+from util import case, rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+
+
+def make_levels(shape, options, nlev):
+    prm, fine = case(*shape, options)
+    o = Oracle(fine, prm)
+    o.apply_turb_bc(True); o.apply_flow_bc(True)
+    levels = [fine]
+    for _ in range(nlev - 1):
+        levels.append(syn.make_coarse_block(levels[-1], prm))
+    return prm, levels
+
+
+def oracle_transfer_to_coarse(prm, fine, coarse):
+    of, oc = Oracle(fine, prm), Oracle(coarse, prm)
+    of.time_step(False)
+    of.residual_block(prm.cdisRK[0])
+    oc.mg_restrict(of)
+    oc.apply_flow_bc(False)
+    oc.time_step(True)
+    oc.mg_store_w1()
+    oc.residual_block_coarse(prm.cdisRK[0], init=0)
+    oc.mg_forcing()
+
+
+def oracle_mg_cycle(prm, levels, cycling):
+    """executeMGCycle (multiGrid.F90:825-955), ground level 1, one block per level"""
+    lv = 0
+    for n, c in enumerate(cycling):
+        if c == -1:
+            lv -= 1
+            of, oc = Oracle(levels[lv], prm), Oracle(levels[lv + 1], prm)
+            of.mg_prolong(oc)
+            of.apply_flow_bc(lv == 0)
+        elif c == 0:
+            o = Oracle(levels[lv], prm)
+            if n > 0 and cycling[n - 1] != 1:
+                o.time_step(True)
+                o.residual_block(prm.cdisRK[0])
+            o.rk_smoother()
+        else:
+            oracle_transfer_to_coarse(prm, levels[lv], levels[lv + 1])
+            lv += 1
+    o = Oracle(levels[0], prm)
+    if prm.equations == 3:
+        for _ in range(prm.nSubiterTurb):
+            o.sa_block()
+    o.time_step(True)
+    o.residual_block(prm.cdisRK[0])
+
+
+def device(prm, levels):
+    s = ADFLOW_B200(prm)
+    s.addBlock(levels[0])
+    for q in range(1, len(levels)):
+        s.addCoarseBlock(levels[q], q - 1)
+    return s
+
+
+def prepare_fine(o):
+    o.time_step(True)
+    o.hb.fw[...] = 0
+    o.residual_block(o.prm.cdisRK[0])
+
+
+@pytest.mark.parametrize("shape,options", [((16, 12, 10), None), ((13, 9, 7), None), ((12, 8, 8), {"equationType": "Euler"}),
+                                           ((10, 12, 6), {"equationType": "laminar NS"})])
+def test_restrict_smooth_prolong_match_oracle(cuda_lib, shape, options):
+    prm, levels = make_levels(shape, options, 2)
+    dev_levels = [l.copy() for l in levels]
+    fine, coarse = levels
+    s = device(prm, dev_levels)
+    try:
+        # --- transferToCoarseGrid
+        oracle_transfer_to_coarse(prm, fine, coarse)
+        s.mgRestrict(1)
+        d = coarse.d
+        ow = d.owned()
+        c1 = (slice(1, d.ie + 1), slice(1, d.je + 1), slice(1, d.ke + 1))
+        w, p, rlv, rev = s.downloadState(1)
+        assert rel_max(w[c1][..., :5], coarse.w[c1][..., :5]) < 1e-13
+        assert rel_max(p[c1], coarse.p[c1]) < 1e-13
+        if prm.equations != 1:
+            assert rel_max(rlv[c1], coarse.rlv[c1]) < 1e-13
+        if prm.equations == 3:
+            assert rel_max(rev[c1], coarse.rev[c1]) < 1e-13
+        wr = s.downloadArray(1, "wr", 5)
+        dw = s.downloadResidual(1)
+        w1 = s.downloadArray(1, "w1", 5)
+        for l in range(5):
+            assert rel_l2(wr[ow + (l,)], coarse.wr[ow + (l,)]) < 1e-11, ("wr", l, rel_l2(wr[ow + (l,)], coarse.wr[ow + (l,)]))
+            assert rel_l2(dw[ow + (l,)], coarse.dw[ow + (l,)]) < 1e-12, ("dw", l)
+        assert rel_max(w1[c1], coarse.w1[c1]) < 1e-13
+        assert rel_max(s.downloadArray(1, "dtl")[ow], coarse.dtl[ow]) < 1e-12
+        # --- Runge-Kutta smoother on the coarse level
+        w0 = coarse.w.copy()
+        Oracle(coarse, prm).rk_smoother()
+        s.rkCycle(level=2)
+        w, p, rlv, rev = s.downloadState(1)
+        for l in range(5):
+            a, b = w[ow + (l,)] - w0[ow + (l,)], coarse.w[ow + (l,)] - w0[ow + (l,)]
+            assert np.abs(b).max() > 0
+            assert rel_l2(a, b) < 1e-9, ("coarse state change", l, rel_l2(a, b))
+        assert rel_max(w[c1][..., :5], coarse.w[c1][..., :5]) < 1e-11
+        # --- transferToFineGrid
+        f0 = fine.w.copy()
+        of, oc = Oracle(fine, prm), Oracle(coarse, prm)
+        of.mg_prolong(oc)
+        of.apply_flow_bc(True)
+        s.mgProlong(1)
+        w, p, rlv, rev = s.downloadState(0)
+        owf = fine.d.owned()
+        for l in range(5):
+            a, b = w[owf + (l,)] - f0[owf + (l,)], fine.w[owf + (l,)] - f0[owf + (l,)]
+            assert np.abs(b).max() > 0
+            assert rel_l2(a, b) < 1e-9, ("fine correction", l, rel_l2(a, b))
+        assert rel_max(w[..., :5], fine.w[..., :5]) < 1e-11
+        assert rel_max(p, fine.p) < 1e-11
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("shape,options,cycle", [((16, 12, 8), None, "2v"), ((16, 16, 8), None, "3w"),
+                                                 ((12, 12, 8), {"equationType": "Euler", "nRKStages": 3, "resAveraging": "never"}, "3v")])
+def test_mg_cycle_matches_oracle(cuda_lib, shape, options, cycle):
+    nlev = int(cycle[0])
+    prm, levels = make_levels(shape, options, nlev)
+    dev_levels = [l.copy() for l in levels]
+    cyc = ADFLOW_B200.cycleStrategy(cycle)
+    prepare_fine(Oracle(levels[0], prm))
+    w0 = levels[0].w.copy()
+    oracle_mg_cycle(prm, levels, cyc)
+    s = device(prm, dev_levels)
+    try:
+        s.timeStep(False)
+        s.smootherResidual(0)
+        s.mgCycle(cyc)
+        w, p, rlv, rev = s.downloadState(0)
+        dw = s.downloadResidual(0)
+        # a second cycle replays the captured graph
+        s.mgCycle(cyc)
+        w2, *_ = s.downloadState(0)
+    finally:
+        s.close()
+    fine = levels[0]
+    ow = fine.d.owned()
+    for l in range(5):
+        a, b = w[ow + (l,)] - w0[ow + (l,)], fine.w[ow + (l,)] - w0[ow + (l,)]
+        assert np.abs(b).max() > 0
+        assert rel_l2(a, b) < 1e-8, ("state change over the cycle", l, rel_l2(a, b))
+        assert rel_l2(dw[ow + (l,)], fine.dw[ow + (l,)]) < 1e-8, ("residual after the cycle", l)
+    assert rel_max(w[..., :5], fine.w[..., :5]) < 1e-10
+    assert np.isfinite(w2).all() and np.abs(w2 - w).max() > 0
+
+
+def test_cycle_strategy_and_errors(cuda_lib):
+    assert ADFLOW_B200.cycleStrategy("sg") == [0]
+    assert ADFLOW_B200.cycleStrategy("2v") == [0, 1, 0, -1]
+    assert len(ADFLOW_B200.cycleStrategy("4w")) == 28      # computeNstepsWcycle(4) = 4 + 2 * (4 + 2 * 4)
+    prm, levels = make_levels((8, 8, 6), None, 2)
+    s = ADFLOW_B200(prm)
+    try:
+        s.addBlock(levels[0])
+        from adflow_b200._lib import AdflowB200Error
+        with pytest.raises(AdflowB200Error):
+            s.mgRestrict(1)                 # no coarse level
+        s.addBlock(levels[1], level=2)      # coarse block without tables
+        with pytest.raises(AdflowB200Error):
+            s.mgRestrict(1)
+        with pytest.raises(AdflowB200Error):
+            s.mgCycle([0, 1, 0])            # does not return to the ground level
+    finally:
+        s.close()
