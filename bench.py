@@ -392,6 +392,25 @@ def main():
             "note": "unfused form: perturb + residual + difference (464 B/cell); a and y are pinned host vectors, "
                     "so the time includes 2 x %d MB over PCIe" % (a.nbytes >> 20)}
 
+        # one multigrid cycle (the smoother of config C3: 4W, Runge-Kutta) on the same block: 4 grid levels
+        from adflow_b200 import synthetic as syn
+        lv = [hb]
+        for _ in range(3):
+            lv.append(syn.make_coarse_block(lv[-1], prm))
+        for q in range(1, 4):
+            s.addCoarseBlock(lv[q], q - 1)
+        s.uploadState(0, hb)
+        s.applyBCs(True, True)
+        s.timeStep(False)
+        s.smootherResidual(0)
+        cyc = ADFLOW_B200.cycleStrategy("4w")
+        msg = ev_time(lambda: s.mgCycle(cyc))
+        others["mg_4w_rk_cycle"] = {
+            "ms": msg, "Mcells/s": cells / (msg * 1e-3) / 1e6,
+            "levels": ["%dx%dx%d" % (b_.d.nx, b_.d.ny, b_.d.nz) for b_ in lv], "steps_in_cycle": len(cyc),
+            "note": "executeMGCycle: %d smoothing steps (5-stage RK each), %d restrictions, %d prolongations, then "
+                    "turbSolveDDADI + timeStep + residual on the fine level" % (cyc.count(0), cyc.count(1), cyc.count(-1))}
+
     # max over ranks
     ms_step = ms_total / args.steps
     if world > 1:
