@@ -77,9 +77,15 @@ class ADFLOW_B200:
         """blocketteRes (src/NKSolver/blockette.F90:70-297) on all local blocks."""
         check(self.L.adfb_residual(level, flags), "adfb_residual")
 
-    def setCommPattern(self, pat, level=1):
-        """Upload a 1-to-1 communication pattern (adflow_b200.halo.build_cartesian_pattern)."""
-        a = {k: np.ascontiguousarray(v, dtype=np.int32) for k, v in pat.items()}
+    def setCommPattern(self, pat, level=1, block_offset=0):
+        """Upload the 1-to-1 communication pattern of one grid level (adflow_b200.halo.build_cartesian_pattern).
+        block_offset: added to the pattern's local block indices (device ids of a coarse level's blocks follow the
+        finer levels')."""
+        a = {k: np.ascontiguousarray(v, dtype=np.int32).copy() for k, v in pat.items()}
+        if block_offset:
+            for k in ("sendList", "recvList", "donorList", "haloList"):
+                if a[k].size:
+                    a[k][:, 0] += block_offset
         self._keep.append(a)
         p = lambda x: x.ctypes.data if x.size else None  # noqa: E731
         check(self.L.adfb_comm_set_pattern(level, len(a["nbrRank"]), p(a["nbrRank"]), p(a["sendCount"]), p(a["recvCount"]),

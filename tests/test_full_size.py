@@ -89,7 +89,7 @@ def test_c2_free_stream_preservation(cuda_lib):
 
 def test_c2_partition_independence(cuda_lib):
     """The same global mesh and state as ONE block and as 2 x 2 x 2 blocks joined by the 1-to-1 exchange: every
-    owned cell sees the same stencil values, so the residuals agree to round-off of the recomputed halo rhoE."""
+    owned cell sees the same stencil values, so the residuals agree to round-off."""
     prm = make_params()
     res = {}
     # the synthetic state carries per-block noise: build the 8 blocks first and assemble the single block's owned
@@ -109,6 +109,10 @@ def test_c2_partition_independence(cuda_lib):
             for hb in blocks:
                 s.addBlock(hb)
             s.setCommPattern(build_cartesian_pattern(grid, 0))
+            # blocketteRes applies the BCs before the exchange (like the reference): the BC halos on the edge between
+            # a physical face and a block interface are computed from the interface halos of the PREVIOUS evaluation,
+            # so the comparison is made on the second evaluation, when those hold the neighbour's current values
+            s.residual(RES_FLOW | RES_TURB)
             s.residual(RES_FLOW | RES_TURB)
             g = np.zeros(C2 + (6,))
             for q, b in enumerate(grid.local_blocks(0)):

@@ -184,3 +184,82 @@ def test_cycle_strategy_and_errors(cuda_lib):
             s.mgCycle([0, 1, 0])            # does not return to the ground level
     finally:
         s.close()
+
+
+def test_two_block_v_cycle_with_halo_exchange_per_level(cuda_lib):
+    """2 blocks per level on one GPU: transferToCoarseGrid / the coarse RK stages / transferToFineGrid with the
+    exchange of each level's own pattern (whalo1 on level 2) between the per-block operations."""
+    from adflow_b200 import make_params
+    from adflow_b200.halo import BlockGrid, build_cartesian_pattern, comm_vars, exchange_numpy, make_grid_blocks
+
+    prm = make_params({"equationType": "laminar NS", "nRKStages": 3, "resAveraging": "never"})
+    gf = BlockGrid((2, 1, 1), (8, 8, 6), nranks=1)
+    fine = make_grid_blocks(gf, 0, prm)
+    pf = build_cartesian_pattern(gf, 0)
+    vars_ = lambda hb: comm_vars(hb, 1, 5, True, True, True, False)  # noqa: E731
+    for hb in fine:
+        o = Oracle(hb, prm)
+        o.apply_flow_bc(True)
+    exchange_numpy(fine, pf, vars_)
+    coarse = [syn.make_coarse_block(hb, prm) for hb in fine]
+    gc = BlockGrid((2, 1, 1), (4, 4, 3), nranks=1)
+    pc = build_cartesian_pattern(gc, 0)
+    dev_f, dev_c = [b.copy() for b in fine], [b.copy() for b in coarse]
+
+    def rk_smoother(blocks, pat, second):
+        for hb in blocks:
+            np.copyto(hb.wn, hb.w[..., :5]); np.copyto(hb.pn, hb.p)
+        for st in range(1, prm.nRKStages + 1):
+            for hb in blocks:
+                Oracle(hb, prm).rk_stage(st)
+            exchange_numpy(blocks, pat, vars_)
+            if st < prm.nRKStages:
+                for hb in blocks:
+                    Oracle(hb, prm).residual_block(prm.cdisRK[st])
+
+    # the fine residual the cycle starts from
+    for hb in fine:
+        prepare_fine(Oracle(hb, prm))
+    w0 = [hb.w.copy() for hb in fine]
+    # executeMGCycle for 2v = 0 1 0 -1 (+ timeStep, residual at the end)
+    rk_smoother(fine, pf, True)
+    for f, c in zip(fine, coarse):
+        of, oc = Oracle(f, prm), Oracle(c, prm)
+        of.time_step(False); of.residual_block(prm.cdisRK[0])
+        oc.mg_restrict(of); oc.apply_flow_bc(False)
+    exchange_numpy(coarse, pc, vars_)
+    for c in coarse:
+        oc = Oracle(c, prm)
+        oc.time_step(True); oc.mg_store_w1(); oc.residual_block_coarse(prm.cdisRK[0], init=0); oc.mg_forcing()
+    rk_smoother(coarse, pc, False)
+    for f, c in zip(fine, coarse):
+        of, oc = Oracle(f, prm), Oracle(c, prm)
+        of.mg_prolong(oc); of.apply_flow_bc(True)
+    exchange_numpy(fine, pf, vars_)
+    for f in fine:
+        o = Oracle(f, prm)
+        o.time_step(True); o.residual_block(prm.cdisRK[0])
+
+    s = ADFLOW_B200(prm)
+    try:
+        for hb in dev_f:
+            s.addBlock(hb)
+        for q, hb in enumerate(dev_c):
+            s.addCoarseBlock(hb, q)
+        s.setCommPattern(pf, level=1)
+        s.setCommPattern(pc, level=2, block_offset=2)
+        s.timeStep(False)
+        s.smootherResidual(0)
+        s.mgCycle(ADFLOW_B200.cycleStrategy("2v"))
+        for q, hb in enumerate(fine):
+            w, p, rlv, rev = s.downloadState(q)
+            dw = s.downloadResidual(q)
+            ow = hb.d.owned()
+            for l in range(5):
+                a, b = w[ow + (l,)] - w0[q][ow + (l,)], hb.w[ow + (l,)] - w0[q][ow + (l,)]
+                assert np.abs(b).max() > 0
+                assert rel_l2(a, b) < 1e-8, (q, l, rel_l2(a, b))
+                assert rel_l2(dw[ow + (l,)], hb.dw[ow + (l,)]) < 1e-8, (q, l)
+            assert rel_max(w[..., :5], hb.w[..., :5]) < 1e-10, q    # halos incl. the exchanged ones
+    finally:
+        s.close()
