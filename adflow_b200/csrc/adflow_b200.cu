@@ -1149,9 +1149,11 @@ static int adfb_dadi_step_body(int level) {
     if (!g.havePrm) return fail("adfb_dadi_step: adfb_set_params has not been called");
     for (Block& b : g.blocks) {
         if (!b.alive || b.level != level) continue;
-        if (launch_dadi(b.d, b.dev, g.prm, g.stream)) return fail("DADI launch failed");
-        if (launch_dadi_update(b.d, b.dev, g.prm, g.stream)) return fail("DADI update launch failed");
-        if (launch_bc_flow(b.d, b.dev, b.subfaces, 1, g.stream)) return fail("flow BC launch failed");
+        AdfbParams prmL = g.prm;   // coarse levels: cflCoarse, first halos only, frozen eddy viscosity (smoothers.F90:463-472)
+        if (level > 1) prmL.cfl = g.prm.cflCoarse;
+        if (launch_dadi(b.d, b.dev, prmL, g.stream)) return fail("DADI launch failed");
+        if (launch_dadi_update(b.d, b.dev, prmL, g.stream, level > 1 ? 5 : 0)) return fail("DADI update launch failed");
+        if (launch_bc_flow(b.d, b.dev, b.subfaces, level > 1 ? 0 : 1, g.stream)) return fail("flow BC launch failed");
     }
     if (halo_exchange_impl(level, 1, 5, 1, 1, false)) return 1;
     CK(cudaGetLastError());
@@ -1401,7 +1403,7 @@ static int adfb_mg_cycle_body(int nSteps, const int* cycling, int smoother) {
                     if (adfb_smoother_residual(level, 0)) return 1;
                 }
                 if (smoother == 0) { if (adfb_rk_cycle(level)) return 1; }
-                else return fail("adfb_mg_cycle: only the Runge-Kutta smoother is available on the multigrid path");
+                else if (adfb_dadi_cycle(level, smoother)) return 1;   // DADISmoother: nSubiterations steps on every level (groundLevel == 1)
                 break;
             case 1:
                 if (adfb_mg_restrict(level)) return 1;
@@ -1420,8 +1422,10 @@ int adfb_mg_cycle(int nSteps, const int* cycling, int smoother) {
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_mg_cycle: adfb_set_params has not been called");
     if (nSteps < 1 || nSteps > 4096 || !cycling) return fail("adfb_mg_cycle: bad cycling strategy");
+    if (smoother < 0 || smoother > 64) return fail("adfb_mg_cycle: smoother must be 0 (Runge-Kutta) or nSubiterations >= 1 (DADI)");
     unsigned long long h = 1469598103934665603ull;
     for (int n = 0; n < nSteps; n++) h = (h ^ (unsigned long long)(cycling[n] + 2)) * 1099511628211ull;
+    h = (h ^ (unsigned long long)(smoother + 7)) * 1099511628211ull;
     const unsigned long long key = (10ull << 40) | (h & 0xffffffffffull);
     set_l2_window();
     std::vector<int> cyc(cycling, cycling + nSteps);

@@ -645,13 +645,13 @@ static int launch_rk_update(const Dims& d, const BlockDev& b, const AdfbParams& 
 }
 
 // state update of executeDADIStep (smoothers.F90:595-650) after computedwDADI
-static int launch_dadi_update(const Dims& d, const BlockDev& b, const AdfbParams& prm, cudaStream_t s) {
+static int launch_dadi_update(const Dims& d, const BlockDev& b, const AdfbParams& prm, cudaStream_t s, int nwOverride = 0) {
     if (prm.resAveraging == 1)  // rkStage == 0 in the DADI smoother: `alternate` never smooths (smoothers.F90:461-469)
         if (launch_residual_averaging(d, b, prm, s)) return 1;
     dim3 tb(32, 4, 2);
     dim3 g((d.nx + 31) / 32, (d.ny + 3) / 4, (d.nz + 1) / 2);
     KT_BEGIN(K_RK, s);
-    launch_pdl(k_rk_update, g, tb, s, d, b, 0, 0.0, prm.equations == ADFB_RANS ? 6 : 5, 1);
+    launch_pdl(k_rk_update, g, tb, s, d, b, 0, 0.0, nwOverride ? nwOverride : (prm.equations == ADFB_RANS ? 6 : 5), 1);
     KT_END(K_RK, s);
     return (int)cudaGetLastError();
 }

@@ -184,10 +184,11 @@ class ADFLOW_B200:
 
         return wcyc(n)
 
-    def mgCycle(self, cycling, smoother="RK"):
-        """executeMGCycle on ground level 1 with cycling in {-1, 0, +1} (iteration%cycling)"""
+    def mgCycle(self, cycling, smoother="RK", n_subiterations=1):
+        """executeMGCycle on ground level 1 with cycling in {-1, 0, +1} (iteration%cycling); smoother "RK" or "DADI" """
         cyc = np.ascontiguousarray(cycling, dtype=np.int32)
-        check(self.L.adfb_mg_cycle(len(cyc), cyc.ctypes.data, {"RK": 0}[smoother]), "adfb_mg_cycle")
+        sm = 0 if smoother == "RK" else int(n_subiterations)
+        check(self.L.adfb_mg_cycle(len(cyc), cyc.ctypes.data, sm), "adfb_mg_cycle")
 
     def turbSolveDDADI(self, n_sub_iter_turb=None, level=1):
         """turbSolveDDADI (src/turbulence/turbAPI.F90:4)."""

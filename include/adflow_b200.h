@@ -312,7 +312,8 @@ int adfb_mg_restrict(int fineLevel);
    w - w1 / p - p1, setCorrectionsCoarseHalos (mgBoundCorr), trilinear interpolation, state update, BCs, exchange */
 int adfb_mg_prolong(int fineLevel);
 /* executeMGCycle (multiGrid.F90:825-955) on ground level 1 with the strategy of setCycleStrategy (:957-1030):
-   cycling(1:nSteps) in {-1 prolongate, 0 smooth, +1 restrict}; smoother 0 = Runge-Kutta.  Ends like the reference
+   cycling(1:nSteps) in {-1 prolongate, 0 smooth, +1 restrict}; smoother 0 = RungeKuttaSmoother, n >= 1 = DADISmoother
+   with nSubiterations = n (smoothers.F90:400-420).  Ends like the reference
    with turbSolveDDADI (RANS), timeStep and the ground-level residual. */
 int adfb_mg_cycle(int nSteps, const int* cycling, int smoother);
 

@@ -691,8 +691,13 @@ void orc_compute_dw_dadi(const OrcBlock* b, const AdfbParams* prm) {
 }
 
 /* executeDADIStep: src/solver/smoothers.F90:425-693 (steady, fine level) */
-void orc_dadi_step(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf) {
+void orc_dadi_step(const OrcBlock* b, const AdfbParams* prm0, int nSub, const AdfbSubface* sf) {
     Dims d = dims_of(b);
+    /* currentCfl = cflCoarse unless currentLevel == 1 (smoothers.F90:469-472, residuals.F90:1113-1116); second halos
+       only on the ground level (smoothers.F90:463-467) */
+    AdfbParams prmL = *prm0;
+    if (b->level > 1) prmL.cfl = prm0->cflCoarse;
+    const AdfbParams* prm = &prmL;
     for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
         long c = IDX(i, j, k);
         double dt = -prm->cfl * b->dtl[c] * b->vol[c];
@@ -720,7 +725,7 @@ void orc_dadi_step(const OrcBlock* b, const AdfbParams* prm, int nSub, const Adf
     orc_etot(b, prm, 2, d.il, 2, d.jl, 2, d.kl);
     orc_lam_viscosity(b, prm, 0);
     orc_eddy_viscosity(b, prm, 0);
-    orc_apply_flow_bc(b, prm, nSub, sf, 1);
+    orc_apply_flow_bc(b, prm, nSub, sf, b->level > 1 ? 0 : 1);
 }
 
 /* ------------------------------------------------------------------------ */

@@ -36,8 +36,9 @@ def oracle_transfer_to_coarse(prm, fine, coarse):
     oc.mg_forcing()
 
 
-def oracle_mg_cycle(prm, levels, cycling):
-    """executeMGCycle (multiGrid.F90:825-955), ground level 1, one block per level"""
+def oracle_mg_cycle(prm, levels, cycling, dadi_subiter=0):
+    """executeMGCycle (multiGrid.F90:825-955), ground level 1, one block per level; dadi_subiter > 0: DADISmoother
+    with that many sub-iterations instead of RungeKuttaSmoother"""
     lv = 0
     for n, c in enumerate(cycling):
         if c == -1:
@@ -50,7 +51,13 @@ def oracle_mg_cycle(prm, levels, cycling):
             if n > 0 and cycling[n - 1] != 1:
                 o.time_step(True)
                 o.residual_block(prm.cdisRK[0])
-            o.rk_smoother()
+            if dadi_subiter:
+                for _ in range(dadi_subiter - 1):
+                    o.dadi_step()
+                    o.residual_block(1.0)
+                o.dadi_step()
+            else:
+                o.rk_smoother()
         else:
             oracle_transfer_to_coarse(prm, levels[lv], levels[lv + 1])
             lv += 1
@@ -164,6 +171,30 @@ def test_mg_cycle_matches_oracle(cuda_lib, shape, options, cycle):
         assert rel_l2(dw[ow + (l,)], fine.dw[ow + (l,)]) < 1e-8, ("residual after the cycle", l)
     assert rel_max(w[..., :5], fine.w[..., :5]) < 1e-10
     assert np.isfinite(w2).all() and np.abs(w2 - w).max() > 0
+
+
+def test_mg_cycle_with_dadi_smoother(cuda_lib):
+    prm, levels = make_levels((16, 12, 8), {"smoother": "DADI", "resAveraging": "never"}, 3)
+    dev_levels = [l.copy() for l in levels]
+    cyc = ADFLOW_B200.cycleStrategy("3w")
+    prepare_fine(Oracle(levels[0], prm))
+    w0 = levels[0].w.copy()
+    oracle_mg_cycle(prm, levels, cyc, dadi_subiter=2)
+    s = device(prm, dev_levels)
+    try:
+        s.timeStep(False)
+        s.smootherResidual(0)
+        s.mgCycle(cyc, smoother="DADI", n_subiterations=2)
+        w, p, rlv, rev = s.downloadState(0)
+    finally:
+        s.close()
+    fine = levels[0]
+    ow = fine.d.owned()
+    for l in range(5):
+        a, b = w[ow + (l,)] - w0[ow + (l,)], fine.w[ow + (l,)] - w0[ow + (l,)]
+        assert np.abs(b).max() > 0
+        assert rel_l2(a, b) < 1e-7, ("state change over the cycle", l, rel_l2(a, b))
+    assert rel_max(w[..., :5], fine.w[..., :5]) < 1e-9
 
 
 def test_cycle_strategy_and_errors(cuda_lib):

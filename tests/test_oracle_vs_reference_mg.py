@@ -154,3 +154,31 @@ def test_coarse_dissipation_and_corner_row_halos():
     eq(coarse.fw[ow], mg.lv[1].a["fw"][ow], "fw")
     eq(coarse.w[..., :5], rc["w"][..., :5], "w after the momentum round trip + corner row halos")
     eq(coarse.p, rc["p"], "p")
+
+
+@pytest.mark.parametrize("shape,options", [((12, 8, 10), None), ((8, 6, 6), {"equationType": "Euler", "resAveraging": "always"})])
+def test_coarse_level_dadi_smoother(shape, options):
+    """DADISmoother on level 2: nSubiterations executeDADIStep with the coarse residual (dw = wr start) in between,
+    cflCoarse, first halos only"""
+    prm, fine, coarse = two_levels(shape, options)
+    oracle_transfer_to_coarse(prm, fine, coarse)
+    f2, c2 = fine.copy(), coarse.copy()
+    mg = rb.RefMG(f2, c2, prm)
+    try:
+        mg.seed_coarse_shared()
+        rb.set_int("smoother", 2); rb.set_int("nsubiterations", 3); rb.set_int("rkstage", 0)
+        mg.call(2, "smoothers_dadismoother")
+    finally:
+        rb.set_int("smoother", 1); rb.set_int("nsubiterations", 1)
+        mg.close()
+    rc, rf = mg.lv[2].a, mg.lv[1].a
+    oc = Oracle(coarse, prm)
+    for _ in range(2):
+        oc.dadi_step()
+        oc.residual_block(1.0)
+    oc.dadi_step()
+    d = coarse.d
+    c1 = (slice(1, d.ie + 1), slice(1, d.je + 1), slice(1, d.ke + 1))
+    assert np.abs(coarse.w[d.owned()][..., :5] - c2.w[d.owned()][..., :5]).max() > 0
+    eq(coarse.w[c1][..., :5], rc["w"][c1][..., :5], "coarse w after the DADI step")
+    eq(coarse.p[c1], rc["p"][c1], "coarse p after the DADI step")
