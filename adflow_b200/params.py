@@ -45,6 +45,28 @@ class AdfbParams(C.Structure):
     ]
 
 
+class AdfbAnkParams(C.Structure):
+    """ctypes twin of ``struct AdfbAnkParams`` (include/adflow_b200.h); defaults = pyADflow's ANK options"""
+
+    _fields_ = [("cfl", C.c_double), ("cflLimit", C.c_double), ("turbCFLScale", C.c_double), ("physLSTol", C.c_double),
+                ("physLSTolTurb", C.c_double), ("stepMin", C.c_double), ("stepFactor", C.c_double), ("machInf", C.c_double),
+                ("coupled", C.c_int32), ("useDissApprox", C.c_int32), ("useFullVisc", C.c_int32), ("charTimeStepType", C.c_int32)]
+
+
+def make_ank_params(cfl=5.0, coupled=False, char_time_step="None", mach=0.8, **kw):
+    """ANKCFL0 5.0, ANKCFLLimit 1e5, ANKTurbCFLScale 1.0, ANKPhysicalLSTol 0.2, ANKPhysicalLSTolTurb 0.99, ANKStepMin
+    0.01, ANKStepFactor 1.0, ANKUseApproxSA ... (adflow/pyADflow.py defaults); first-order (approximate) fluxes are the
+    ANK default until ANKSecondOrdSwitchTol"""
+    a = AdfbAnkParams()
+    a.cfl, a.cflLimit, a.turbCFLScale = cfl, kw.get("cflLimit", 1e5), kw.get("turbCFLScale", 1.0)
+    a.physLSTol, a.physLSTolTurb = kw.get("physLSTol", 0.2), kw.get("physLSTolTurb", 0.99)
+    a.stepMin, a.stepFactor, a.machInf = kw.get("stepMin", 0.01), kw.get("stepFactor", 1.0), mach
+    a.coupled = int(coupled)
+    a.useDissApprox, a.useFullVisc = int(kw.get("useDissApprox", True)), int(kw.get("useFullVisc", True))
+    a.charTimeStepType = {"None": 0, "VLR": 1, "Turkel": 2}[char_time_step]
+    return a
+
+
 EULER, NS, RANS = 1, 2, 3
 DISS_SCALAR, DISS_MATRIX, UPWIND = 1, 2, 4
 PROD_STRAIN, PROD_VORTICITY = 1, 2

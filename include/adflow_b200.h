@@ -290,6 +290,40 @@ int adfb_sa_ddadi(int level, int nSubIterTurb);
 /* DADISmoother (src/solver/smoothers.F90:383-421) */
 int adfb_dadi_cycle(int level, int nSubiterations);
 
+/* ---- ANK pieces (module ANKSolver, src/NKSolver/NKSolvers.F90) -------------------------------------------------
+   The approximate Newton-Krylov solver keeps PETSc's GMRES; the library provides the operator it applies and the
+   two per-cell reductions around it.  State vectors hold nState = 5 (ANK_coupled = 0: flow variables only) or nw
+   (coupled) entries per owned cell, cell-major like getStates (setWANK :2975-3011). */
+typedef struct AdfbAnkParams {
+    double cfl;             /* ANK_CFL */
+    double cflLimit;        /* ANK_CFLLimit (blending of the characteristic time step) */
+    double turbCFLScale;    /* ANK_turbCFLScale */
+    double physLSTol;       /* ANK_physLSTol */
+    double physLSTolTurb;   /* ANK_physLSTolTurb */
+    double stepMin;         /* ANK_stepMin */
+    double stepFactor;      /* ANK_stepFactor */
+    double machInf;         /* inputPhysics mach (VLR / Turkel truncation) */
+    int32_t coupled;        /* ANK_coupled: turbulence variable in the vectors */
+    int32_t useDissApprox;  /* ANK_useDissApprox -> blocketteRes(useDissApprox) */
+    int32_t useFullVisc;    /* ANK_useFullVisc: useViscApprox = (.not. useFullVisc) .and. useDissApprox (:2489) */
+    int32_t charTimeStepType; /* ANK_charTimeStepType: 0 'None', 1 'VLR', 2 'Turkel' */
+} AdfbAnkParams;
+int adfb_ank_set_params(const AdfbAnkParams* ank);
+/* computeTimeStepMat / computeTimeStepBlock (:2041-2329): the nState x nState block of every owned cell from the
+   CURRENT state, dtl (last time-step evaluation) and ANK_CFL; kept on the device for adfb_ank_form_function */
+int adfb_ank_time_step_mat(void);
+/* FormFunction_mf of ANKSolver (:2468-2538): setWANK(inVec); blocketteRes(useDissApprox, useViscApprox, useTurbRes =
+   coupled); setRVec / setRVecANK; rVec += timeStepMat * inVec */
+int adfb_ank_form_function(const double* inVec, double* rVec, long long n);
+/* matrix-free product with that function (the MatMFFD shell of the ANK KSP, :1890-1905): base state U (host), then
+   y = (F(U + h a) - F(U)) / h for host vectors; h <= 0: PETSc's default differencing parameter as in adfb_mffd_apply */
+int adfb_ank_mffd_set_base(const double* U, long long n);
+int adfb_ank_mffd_apply(const double* a, double* y, long long n, double h);
+/* physicalityCheckANK (:3013-3210): largest step lambda <= *lambdaP that changes rho and rhoE by at most physLSTol
+   (and decreases the turbulence variable by at most physLSTolTurb; individual turbulence updates that would be more
+   limiting than stepFactor * stepMin are clipped in deltaW instead), MIN-reduced over the ranks */
+int adfb_ank_physicality_check(const double* wVec, double* deltaW, long long n, double* lambdaP);
+
 /* ---- multigrid (src/solver/multiGrid.F90) ------------------------------------------------------------------
    Grid levels: blocks created with level = 1 (finest) .. n; geometry, BCs and the communication pattern are set
    per block / per level like on the finest level (coarse levels exchange the first halos only: pass the 1st-halo

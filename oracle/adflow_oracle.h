@@ -115,6 +115,9 @@ void orc_mg_store_w1(const OrcBlock* coarse);
 void orc_mg_forcing(const OrcBlock* coarse, const AdfbParams* prm);
 void orc_mg_prolong(const OrcBlock* fine, const OrcBlock* coarse, const AdfbParams* prm, int nSubCoarse, const AdfbSubface* sfCoarse,
                     const int32_t* mgICoarse, const int32_t* mgJCoarse, const int32_t* mgKCoarse);
+/* adflow_oracle_ank.c: ANK pieces (module ANKSolver of src/NKSolver/NKSolvers.F90) */
+void orc_ank_time_step_block(const OrcBlock* b, const AdfbParams* prm, const AdfbAnkParams* ank, int i, int j, int k, double* blk);
+double orc_ank_physicality_check(const AdfbAnkParams* ank, int nState, long nCells, const double* wVec, double* dVec, double lambdaP);
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,8 @@ def preprocess(text, defined=()):
                 stack.append(name in defined)
             elif d == "ifndef":
                 stack.append(name not in defined)
+            elif d == "if":
+                stack.append(True)   # `#if PETSC_VERSION_GE(...)`: the current-PETSc branch
             elif d == "else":
                 stack[-1] = not stack[-1]
             elif d == "endif":
@@ -1088,9 +1090,13 @@ static inline int f90_ipow(int x, int n) { int r = 1; for (int q = 0; q < n; q++
 """
 
 
-def translate_module(src_path, only, env, rename_modules, patches=(), defined=(), tr=None, prefix=""):
+def translate_module(src_path, only, env, rename_modules, patches=(), defined=(), tr=None, prefix="", module=None):
     text = open(src_path).read()
     lines = preprocess(text, defined)
+    if module is not None:   # a file with several modules: keep `module <name>` ... `end module <name>`
+        a = next(q for q, l in enumerate(lines) if re.match(r"module\s+%s\s*$" % module, l))
+        b = next(q for q, l in enumerate(lines) if q > a and re.match(r"end\s*module", l))
+        lines = lines[a:b + 1]
     for patch in patches:
         if patch[0] == "block":  # ("block", first-line regex, last-line regex): drop the lines in between, inclusive
             out, skipping = [], False

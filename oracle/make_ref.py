@@ -73,6 +73,25 @@ MG_PATCHES = [
     (r"^if \(\.not\. corrections\) call extrapolateviscosities$", "continue"),
 ]
 
+# ANK pieces of NKSolvers.F90 (module ANKSolver): PETSc vectors -> harness arrays, MPI reduction -> copy (one rank),
+# character option -> integer code, MATMUL/TRANSPOSE of the nState x nState blocks -> helpers in ref_env.c
+ANK_PATCHES = [
+    (r"^call vecgetarrayf90\(wvec, wvec_pointer, ierr\)$", "wvec_pointer => ank_wvec"),
+    (r"^call vecgetarrayf90\(deltaw, dvec_pointer, ierr\)$", "dvec_pointer => ank_dvec"),
+    (r"^call vecrestorearrayf90\(.*$", "continue"),
+    (r"^call echk\(.*$", "continue"),
+    (r"^call mpi_allreduce\(lambdal, lambdap_recv,.*$", "lambdap_recv = lambdal"),
+    (r"myisnan\(lambdal\)", "(lambdal /= lambdal)"),
+    (r"ank_chartimesteptype == '(?i:none)'", "ank_chartimestepcode == 0"),
+    (r"ank_chartimesteptype == '(?i:vlr)'", "ank_chartimestepcode == 1"),
+    (r"ank_chartimesteptype == '(?i:turkel)'", "ank_chartimestepcode == 2"),
+    (r"^timestepblock = matmul\((\w+), transpose\((\w+)\)\)$", r"call ank_matmul_nt(\1, \2, timestepblock)"),
+    (r"^timestepblock = matmul\((\w+), (\w+)\)$", r"call ank_matmul(\1, \2, timestepblock)"),
+    # `use inputPhysics, only: machInf => mach`: the module's free-stream Mach number, NOT the local variable mach
+    (r"machinf", "ank_machinf"),
+    (r"ank_machinf => mach", "ank_machinf"),
+]
+
 # external (other-module) data the translated routines see; declared in oracle/ref_env.h
 ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequations nsequations eulerequations
  steady unsteady timespectral spalartallmaras dissscalar dissmatrix upwind currentlevel groundlevel
@@ -91,7 +110,7 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  symm symmpolar nswalladiabatic nswallisothermal farfield eulerwall extrap supersonicinflow supersonicoutflow
  subsonicinflow subsonicoutflow massbleedoutflow imin imax jmin jmax kmin kmax
  constantpressure linextrapolpressure quadextrapolpressure normalmomentum
- sh_ib sh_jb sh_kb fl_ib fl_jb fl_kb cl_il cl_jl cl_kl cl_ie cl_je cl_ke cl_ib cl_jb cl_kb cl_nbocos mgboundcorr bcdirichlet0 bcneumann
+ ank_chartimestepcode ank_nvec sh_ib sh_jb sh_kb fl_ib fl_jb fl_kb cl_il cl_jl cl_kl cl_ie cl_je cl_ke cl_ib cl_jb cl_kb cl_nbocos mgboundcorr bcdirichlet0 bcneumann
  slidinginterface oversetouterbound domaininterfaceall domaininterfacerhouvw domaininterfacep domaininterfacerho
  domaininterfacetotal""".split()
 
@@ -179,6 +198,9 @@ def env_arrays():
         arrs["%s_iblank" % pre] = A("%s_iblank" % pre, "int", list(bnd), strides=st[:3], base=["0", "0", "0"])
         for n, nc in (("w", "nw"), ("w1", "nwf")):
             arrs["%s_%s" % (pre, n)] = A("%s_%s" % (pre, n), "double", list(bnd) + [("1", nc)], strides=st, base=["0", "0", "0", "1"])
+    # ANK: the PETSc vectors wVec / deltaW as plain arrays (bound by the harness)
+    arrs["ank_wvec"] = A("ank_wvec", "double", [("1", "ank_nvec")], pointer=True) if False else A("ank_wvec", "double", [("1", "ank_nvec")])
+    arrs["ank_dvec"] = A("ank_dvec", "double", [("1", "ank_nvec")])
     arrs["cl_bctype"] = A("cl_bctype", "int", [("1", "64")])
     arrs["cl_bcfaceid"] = A("cl_bcfaceid", "int", [("1", "64")])
     arrs["bp_bctype"] = A("bp_bctype", "int", [("1", "64")])
@@ -206,6 +228,8 @@ ENV_SUBS = {
     "setpointers": [("nn", "int", False), ("level", "int", False), ("sps", "int", False)],
     "whalo1": [(n, "int", False) for n in ("level", "start", "end", "commpressure", "commgamma", "commviscous")],
     "whalo2": [(n, "int", False) for n in ("level", "start", "end", "commpressure", "commgamma", "commviscous")],
+    "ank_matmul": [("a", "double", True), ("b", "double", True), ("c", "double", True)],
+    "ank_matmul_nt": [("a", "double", True), ("b", "double", True), ("c", "double", True)],
 }
 
 
@@ -247,6 +271,9 @@ UNITS = [
     # BCData -> accessor functions over a second subface table (cbcd)
     ("solver/multiGrid.F90", "multigrid_", ["transfertocoarsegrid", "transfertofinegrid", "setcornerrowhalos",
                                             "setcorrectionscoarsehalos"], (), None, MG_PATCHES),
+    # ANK: time-step block of the matrix-free operator and the physicality check of the update
+    ("NKSolver/NKSolvers.F90", "anksolver_", ["computetimestepblock", "physicalitycheckank"], (), "anksolver_ref.c", ANK_PATCHES,
+     "anksolver"),
 ]
 RENAME_MODULES = {"blockpointers": "bp_", "flowutils": "flowutils_", "turbutils": "turbutils_",
                   "residuals": "residuals_", "smoothers": "smoothers_", "sa": "sa_",
@@ -271,7 +298,8 @@ def main():
         patches = (list(unit[5]) if len(unit) > 5 else []) + PATCHES
         src = os.path.join(ref, "src", rel)
         code, tr = f90toc.translate_module(src, only=set(routines), env=env, rename_modules=RENAME_MODULES,
-                                           patches=patches, defined=defined, tr=tr, prefix=prefix)
+                                           patches=patches, defined=defined, tr=tr, prefix=prefix,
+                                           module=unit[6] if len(unit) > 6 else None)
         out = os.path.join(outdir, unit[4] if len(unit) > 4 and unit[4] else os.path.basename(rel).replace(".F90", "").lower() + "_ref.c")
         with open(out, "w") as f:
             f.write(code)

@@ -18,7 +18,7 @@ def build(force=False):
     src = os.path.join(_HERE, "adflow_oracle.c")
     stale = (not os.path.exists(so)) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(so)
-        for f in ("adflow_oracle.c", "adflow_oracle_smooth.c", "adflow_oracle_sa.c", "adflow_oracle_fluxes.c", "adflow_oracle_mg.c", "adflow_oracle.h", "orc_internal.h",
+        for f in ("adflow_oracle.c", "adflow_oracle_smooth.c", "adflow_oracle_sa.c", "adflow_oracle_fluxes.c", "adflow_oracle_mg.c", "adflow_oracle_ank.c", "adflow_oracle.h", "orc_internal.h",
                   "../include/adflow_b200.h")
     )
     if force or stale:
@@ -204,3 +204,18 @@ class Oracle:
         keep = [self._tab(mg[n], np.int32) for n in ("mgICoarse", "mgJCoarse", "mgKCoarse")]
         n, arr = coarse._subfaces()
         self.L.orc_mg_prolong(_p(self.ob), _p(coarse.ob), _p(self.prm), C.c_int(n), arr, *[k[1] for k in keep])
+
+    # -- ANK pieces (adflow_oracle_ank.c) ---------------------------------------------------------------------------
+    def ank_time_step_block(self, ank, i, j, k):
+        n = self.hb.nw if ank.coupled else 5
+        out = np.zeros((n, n), order="F")
+        self.L.orc_ank_time_step_block(_p(self.ob), _p(self.prm), _p(ank), C.c_int(i), C.c_int(j), C.c_int(k), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def ank_physicality_check(self, ank, w_vec, d_vec, lambda_p):
+        """returns the new lambdaP; d_vec is clipped in place (coupled turbulence updates)"""
+        n = self.hb.nw if ank.coupled else 5
+        f = self.L.orc_ank_physicality_check
+        f.restype = C.c_double
+        return f(_p(ank), C.c_int(n), C.c_long(w_vec.size // n), w_vec.ctypes.data_as(C.c_void_p), d_vec.ctypes.data_as(C.c_void_p),
+                 C.c_double(lambda_p))

@@ -102,3 +102,28 @@ void terminate(const char* routine, const char* msg) {
     fprintf(stderr, "reference terminate() in %s: %s\n", routine, msg);
     abort();
 }
+
+/* ANK helpers: MATMUL / TRANSPOSE of the nState x nState blocks (column-major), terms summed in index order */
+int ank_chartimestepcode = 0, ank_nvec = 0;
+double ank_machinf = 0.0, *ank_wvec, *ank_dvec;
+extern int anksolver_nstate;
+void ank_matmul(double* a, double* b, double* c) {
+    const int n = anksolver_nstate;
+    double t[64];
+    for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
+        double s = 0.0;
+        for (int k = 0; k < n; k++) s += a[i + n * k] * b[k + n * j];
+        t[i + n * j] = s;
+    }
+    for (int q = 0; q < n * n; q++) c[q] = t[q];
+}
+void ank_matmul_nt(double* a, double* b, double* c) {
+    const int n = anksolver_nstate;
+    double t[64];
+    for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
+        double s = 0.0;
+        for (int k = 0; k < n; k++) s += a[i + n * k] * b[j + n * k];
+        t[i + n * j] = s;
+    }
+    for (int q = 0; q < n * n; q++) c[q] = t[q];
+}

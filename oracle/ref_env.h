@@ -142,6 +142,13 @@ extern void (*setpointers_hook)(int level);
 void solverutils_timestep(int* onlyradii);
 void turbbcroutines_applyallturbbc(int* secondhalo);
 
+/* ANK (module ANKSolver of src/NKSolver/NKSolvers.F90): option code of ANK_charTimeStepType ('None' 0, 'VLR' 1,
+   'Turkel' 2), free-stream Mach number, the PETSc vectors wVec / deltaW as arrays, nState x nState helpers */
+extern int ank_chartimestepcode, ank_nvec;
+extern double ank_machinf, *ank_wvec, *ank_dvec;
+void ank_matmul(double* a, double* b, double* c);     /* c = MATMUL(a, b) */
+void ank_matmul_nt(double* a, double* b, double* c);  /* c = MATMUL(a, TRANSPOSE(b)) */
+
 /* driver-level procedures outside the translated set (no-op stubs, see ref_env.c) */
 void setpointers(int* nn, int* level, int* sps);
 void whalo1(int* level, int* start, int* end, int* commpressure, int* commgamma, int* commviscous);
