@@ -20,6 +20,7 @@
 #include "residual_kernels.cuh"
 #include "smoother_kernels.cuh"
 #include "mg_kernels.cuh"
+#include "ank_kernels.cuh"
 #include "halo_kernels.cuh"
 #include "dadi_kernels.cuh"
 #include "sa_kernels.cuh"
@@ -91,6 +92,12 @@ struct Context {
     std::map<unsigned long long, long long> graphLaunches;
     bool useGraphs = true;
     bool capturing = false;
+    // ANK (module ANKSolver): options, per-cell time-step blocks, the perturbed vector of the last product
+    AdfbAnkParams ank;
+    bool haveAnk = false, ankHaveT = false, ankHaveBase = false;
+    double *ankT = nullptr, *ankPert = nullptr;
+    size_t ankTN = 0, ankPertN = 0;
+    double ankUnorm = 0.0;
     int mgInitWr = 1;   // coarse-level smoother residual starts from wr (0 inside transferToCoarseGrid: from zero)
 };
 
@@ -1229,6 +1236,173 @@ int adfb_rk_cycle(int level) {
     return run_graphed(key, [&]() { return adfb_rk_cycle_body(level); });
 }
 
+
+// ---------------------------------------------------------------------------
+// ANK pieces (module ANKSolver, src/NKSolver/NKSolvers.F90)
+static int ank_nstate(const Block& b) { return g.ank.coupled ? b.nw : 5; }
+static long long ank_vec_size(void) {
+    long long n = 0;
+    for (Block& b : g.blocks)
+        if (b.alive && b.level == 1) n += (long long)b.d.nx * b.d.ny * b.d.nz * ank_nstate(b);
+    return n;
+}
+static unsigned ank_res_flags(void) {
+    unsigned f = ADFB_RES_FLOW;
+    if (g.ank.useDissApprox) f |= ADFB_RES_DISS_APPROX;
+    if (!g.ank.useFullVisc && g.ank.useDissApprox) f |= ADFB_RES_VISC_APPROX;   // :2489
+    if (g.ank.coupled) f |= ADFB_RES_TURB;
+    return f;
+}
+int adfb_ank_set_params(const AdfbAnkParams* ank) {
+    NEED_INIT();
+    if (!ank) return fail("adfb_ank_set_params: null");
+    if (!(ank->cfl > 0.0) || !(ank->cflLimit > 0.0) || !(ank->turbCFLScale > 0.0)) return fail("adfb_ank_set_params: CFL values must be positive");
+    if (ank->charTimeStepType < 0 || ank->charTimeStepType > 2) return fail("adfb_ank_set_params: charTimeStepType %d (0 None, 1 VLR, 2 Turkel)", ank->charTimeStepType);
+    if (ank->coupled && g.havePrm && g.prm.equations != ADFB_RANS) return fail("adfb_ank_set_params: coupled ANK needs the RANS equations");
+    g.ank = *ank;
+    g.haveAnk = true; g.ankHaveT = false; g.ankHaveBase = false;
+    return 0;
+}
+int adfb_ank_time_step_mat(void) {
+    NEED_INIT();
+    if (!g.havePrm || !g.haveAnk) return fail("adfb_ank_time_step_mat: adfb_set_params / adfb_ank_set_params have not been called");
+    size_t need = 0;
+    for (Block& b : g.blocks)
+        if (b.alive && b.level == 1) need += (size_t)b.d.nx * b.d.ny * b.d.nz * ank_nstate(b) * ank_nstate(b);
+    if (g.ankTN < need) {
+        if (g.ankT) cudaFree(g.ankT);
+        g.ankT = nullptr; g.ankTN = 0;
+        CK(cudaMalloc((void**)&g.ankT, need * sizeof(double)));
+        g.ankTN = need;
+    }
+    size_t off = 0;
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != 1) continue;
+        const long long nc = (long long)b.d.nx * b.d.ny * b.d.nz;
+        const int ns = ank_nstate(b);
+        KT_BEGIN(K_MFFD, g.stream);
+        if (ns == 5) k_ank_tsblock<5><<<(unsigned)((nc + 63) / 64), 64, 0, g.stream>>>(b.d, b.dev, g.ank, g.ankT + off);
+        else k_ank_tsblock<6><<<(unsigned)((nc + 63) / 64), 64, 0, g.stream>>>(b.d, b.dev, g.ank, g.ankT + off);
+        KT_END(K_MFFD, g.stream);
+        off += (size_t)nc * ns * ns;
+    }
+    CK(cudaGetLastError());
+    g.ankHaveT = true;
+    return 0;
+}
+static int ank_vec_kernel(const double* vec, const double* base, double* out, double* pert, double h, int mode) {
+    long long off = 0;
+    size_t offT = 0;
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != 1) continue;
+        const int ns = ank_nstate(b);
+        const long long nc = (long long)b.d.nx * b.d.ny * b.d.nz, n = nc * ns;
+        KT_BEGIN(K_MFFD, g.stream);
+        k_ankvec<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(b.d, b.dev, ns, vec ? vec + off : nullptr, base ? base + off : nullptr,
+                                                                    out ? out + off : nullptr, pert ? pert + off : nullptr,
+                                                                    g.ankT ? g.ankT + offT : nullptr, h, mode);
+        KT_END(K_MFFD, g.stream);
+        off += n;
+        offT += (size_t)nc * ns * ns;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+static int ank_ready(const char* who, long long n, long long* need) {
+    if (!g.havePrm || !g.haveAnk) return fail("%s: adfb_set_params / adfb_ank_set_params have not been called", who);
+    if (!g.ankHaveT) return fail("%s: adfb_ank_time_step_mat has not been called", who);
+    *need = ank_vec_size();
+    if (n != *need) return fail("%s: vector length %lld != %lld (nState entries per owned cell)", who, n, *need);
+    if (nk_buffers(adfb_state_size())) return 1;
+    if (g.ankPertN < (size_t)*need) {
+        if (g.ankPert) cudaFree(g.ankPert);
+        g.ankPert = nullptr; g.ankPertN = 0;
+        CK(cudaMalloc((void**)&g.ankPert, *need * sizeof(double)));
+        g.ankPertN = *need;
+    }
+    return 0;
+}
+// FormFunction_mf (:2468-2538)
+int adfb_ank_form_function(const double* inVec, double* rVec, long long n) {
+    NEED_INIT();
+    long long need = 0;
+    if (!inVec || !rVec) return fail("adfb_ank_form_function: null vector");
+    if (ank_ready("adfb_ank_form_function", n, &need)) return 1;
+    CK(cudaMemcpyAsync(g.nkA, inVec, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    if (ank_vec_kernel(g.nkA, nullptr, nullptr, nullptr, 0.0, 0)) return 1;
+    if (adfb_residual(1, ank_res_flags())) return 1;
+    if (ank_vec_kernel(g.nkA, nullptr, g.nkY, nullptr, 1.0, 2)) return 1;
+    CK(cudaMemcpyAsync(rVec, g.nkY, need * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+int adfb_ank_mffd_set_base(const double* U, long long n) {
+    NEED_INIT();
+    long long need = 0;
+    if (!U) return fail("adfb_ank_mffd_set_base: null vector");
+    if (ank_ready("adfb_ank_mffd_set_base", n, &need)) return 1;
+    CK(cudaMemcpyAsync(g.nkU, U, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    if (ank_vec_kernel(g.nkU, nullptr, nullptr, nullptr, 0.0, 0)) return 1;
+    if (adfb_residual(1, ank_res_flags())) return 1;
+    if (ank_vec_kernel(g.nkU, nullptr, g.nkF0, nullptr, 1.0, 2)) return 1;
+    double uu = 0.0;
+    if (nk_sumsq(g.nkU, need, &uu)) return 1;
+    g.ankUnorm = sqrt(uu);
+    g.ankHaveBase = true;
+    g.nkHaveBase = false;   // the NK base shares the buffers
+    return 0;
+}
+int adfb_ank_mffd_apply(const double* a, double* y, long long n, double h) {
+    NEED_INIT();
+    long long need = 0;
+    if (!a || !y) return fail("adfb_ank_mffd_apply: null vector");
+    if (ank_ready("adfb_ank_mffd_apply", n, &need)) return 1;
+    if (!g.ankHaveBase) return fail("adfb_ank_mffd_apply: adfb_ank_mffd_set_base has not been called");
+    CK(cudaMemcpyAsync(g.nkA, a, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    if (h <= 0.0) {
+        double aa = 0.0;
+        if (nk_sumsq(g.nkA, need, &aa)) return 1;
+        if (aa == 0.0) { g.nkLastH = 0.0; memset(y, 0, need * sizeof(double)); return 0; }
+        h = 1.4901161193847656e-08 * sqrt(1.0 + g.ankUnorm) / sqrt(aa);
+    }
+    g.nkLastH = h;
+    if (ank_vec_kernel(g.nkA, g.nkU, nullptr, g.ankPert, h, 1)) return 1;
+    if (adfb_residual(1, ank_res_flags())) return 1;
+    if (ank_vec_kernel(g.ankPert, g.nkF0, g.nkY, nullptr, h, 3)) return 1;
+    CK(cudaMemcpyAsync(y, g.nkY, need * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+// physicalityCheckANK (:3013-3210)
+int adfb_ank_physicality_check(const double* wVec, double* deltaW, long long n, double* lambdaP) {
+    NEED_INIT();
+    if (!g.haveAnk) return fail("adfb_ank_physicality_check: adfb_ank_set_params has not been called");
+    if (!wVec || !deltaW || !lambdaP) return fail("adfb_ank_physicality_check: null argument");
+    const long long need = ank_vec_size();
+    if (n != need) return fail("adfb_ank_physicality_check: vector length %lld != %lld", n, need);
+    if (nk_buffers(adfb_state_size())) return 1;
+    CK(cudaMemcpyAsync(g.nkA, wVec, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.nkY, deltaW, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    int ns = 5;
+    for (Block& b : g.blocks) if (b.alive && b.level == 1) { ns = ank_nstate(b); break; }
+    const int nPart = 512;
+    KT_BEGIN(K_MFFD, g.stream);
+    k_ank_phys<<<nPart, 256, 0, g.stream>>>(need / ns, ns, g.ank.coupled, g.ank, g.nkA, g.nkY, *lambdaP, g.dRed);
+    KT_END(K_MFFD, g.stream);
+    KT_BEGIN(K_MFFD, g.stream);
+    k_min_final<<<1, 256, 0, g.stream>>>(g.dRed, nPart);
+    KT_END(K_MFFD, g.stream);
+    if (g.nranks > 1) {
+        const int rc = g.nccl.AllReduce(g.dRed + nPart, g.dRed + nPart, 1, kNcclDouble, kNcclMin, g.comm, g.stream);
+        if (rc != 0) return fail("ncclAllReduce: %s", g.nccl.GetErrorString(rc));
+    }
+    CK(cudaMemcpyAsync(g.hRed, g.dRed + nPart, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    if (g.ank.coupled) CK(cudaMemcpyAsync(deltaW, g.nkY, need * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaGetLastError());
+    *lambdaP = g.hRed[0];
+    return 0;
+}
 
 // ---------------------------------------------------------------------------
 // multigrid (src/solver/multiGrid.F90)

@@ -135,6 +135,44 @@ class ADFLOW_B200:
         """DADISmoother (src/solver/smoothers.F90:383)."""
         check(self.L.adfb_dadi_cycle(level, n_subiterations), "adfb_dadi_cycle")
 
+    # -- ANK pieces (module ANKSolver, src/NKSolver/NKSolvers.F90) ----------------------------------------------
+    def ankSetParams(self, ank):
+        self._ank = ank
+        check(self.L.adfb_ank_set_params(C.byref(ank)), "adfb_ank_set_params")
+
+    def ankTimeStepMat(self):
+        """computeTimeStepMat: blocks from the current state and dtl (call timeStep / a residual with
+        RES_UPDATE_INTERMED first)"""
+        check(self.L.adfb_ank_time_step_mat(), "adfb_ank_time_step_mat")
+
+    def ankVecSize(self):
+        ns = lambda hb: hb.nw if self._ank.coupled else 5  # noqa: E731
+        return sum(hb.d.ncells * ns(hb) for hb in self.blocks if getattr(hb, "level", 1) == 1)
+
+    def ankFormFunction(self, in_vec):
+        v = np.ascontiguousarray(in_vec, dtype=np.float64)
+        r = np.empty_like(v)
+        check(self.L.adfb_ank_form_function(v.ctypes.data, r.ctypes.data, v.size), "adfb_ank_form_function")
+        return r
+
+    def ankMffdSetBase(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        check(self.L.adfb_ank_mffd_set_base(U.ctypes.data, U.size), "adfb_ank_mffd_set_base")
+
+    def ankMffdApply(self, a, h=-1.0):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        y = np.empty_like(a)
+        check(self.L.adfb_ank_mffd_apply(a.ctypes.data, y.ctypes.data, a.size, h), "adfb_ank_mffd_apply")
+        return y
+
+    def ankPhysicalityCheck(self, w_vec, delta_w, lambda_p=1.0):
+        """returns (lambdaP, deltaW) -- deltaW with the clipped turbulence updates (coupled ANK)"""
+        w = np.ascontiguousarray(w_vec, dtype=np.float64)
+        dv = np.array(delta_w, dtype=np.float64, order="C", copy=True)
+        lam = C.c_double(lambda_p)
+        check(self.L.adfb_ank_physicality_check(w.ctypes.data, dv.ctypes.data, w.size, C.byref(lam)), "adfb_ank_physicality_check")
+        return lam.value, dv
+
     # -- multigrid (src/solver/multiGrid.F90) ----------------------------------------------------------------
     def addCoarseBlock(self, coarse_hb, fine_blk):
         """Device mirror of the next coarser level of block `fine_blk` + the transfer tables (createCoarseBlocks,

@@ -1,0 +1,121 @@
+"""ANK pieces on the device (adfb_ank_*): the matrix-free operator F(v) = R_approx(v) + timeStepMat v of ANKSolver's
+FormFunction_mf, its finite-difference product, and the physicality check -- against the oracle, whose
+computeTimeStepBlock / physicalityCheckANK are pinned bit for bit against the reference
+(tests/test_oracle_vs_reference_ank.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from adflow_b200.params import make_ank_params
+from adflow_b200.solver import ADFLOW_B200, RES_DISS_APPROX, RES_FLOW, RES_TURB, RES_VISC_APPROX
+from oracle.pyoracle import Oracle
+
+from util import case, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def vec_of(hb, ns):
+    return np.ascontiguousarray(np.transpose(hb.w[hb.d.owned()][..., :ns], (2, 1, 0, 3)).reshape(-1))
+
+
+def oracle_blocks(prm, ank, hb):
+    """timeStepMat of the state in hb (dtl current): (ncells, ns, ns), cell-major like the vectors"""
+    d = hb.d
+    o = Oracle(hb, prm)
+    out = []
+    for k in range(2, d.kl + 1):
+        for j in range(2, d.jl + 1):
+            for i in range(2, d.il + 1):
+                out.append(o.ank_time_step_block(ank, i, j, k))
+    return np.array(out)
+
+
+def oracle_ank_function(prm, ank, hb, T, vec):
+    """FormFunction_mf of ANKSolver: setWANK, blocketteRes(approx flags), setRVec(ANK), + timeStepMat * vec"""
+    d = hb.d
+    ns = hb.nw if ank.coupled else 5
+    ow = d.owned()
+    h2 = hb.copy()
+    h2.w[ow + (slice(0, ns),)] = np.asarray(vec).reshape(d.nz, d.ny, d.nx, ns).transpose(2, 1, 0, 3)
+    o = Oracle(h2, prm)
+    o.pressure(False); o.lam_viscosity(False); o.eddy_viscosity(False)
+    o.apply_turb_bc(True); o.apply_flow_bc(True)
+    o.L.orc_etot(C.byref(o.ob), C.byref(prm), 2, d.il, 2, d.jl, 2, d.kl)
+    flags = RES_FLOW | (RES_TURB if ank.coupled else 0)
+    if ank.useDissApprox:
+        flags |= RES_DISS_APPROX
+    if ank.useDissApprox and not ank.useFullVisc:
+        flags |= RES_VISC_APPROX
+    o.residual_core(flags)
+    r = h2.dw[ow][..., :ns] / h2.volRef[ow][..., None]
+    if ns > 5:
+        r[..., 5] *= prm.turbResScale
+    r = np.transpose(r, (2, 1, 0, 3)).reshape(-1, ns)
+    v = np.asarray(vec).reshape(-1, ns)
+    return (r + np.einsum("qlm,qm->ql", T, v)).reshape(-1)
+
+
+@pytest.mark.parametrize("options,coupled,kind,fullvisc", [(None, False, "None", True), (None, True, "None", False),
+                                                          (None, False, "VLR", True), ({"equationType": "Euler"}, False, "Turkel", True)])
+def test_ank_operator_and_product(cuda_lib, options, coupled, kind, fullvisc):
+    prm, hb = case(11, 9, 8, options)
+    ank = make_ank_params(cfl=5.0, coupled=coupled, char_time_step=kind, mach=0.8, cflLimit=50.0, turbCFLScale=2.0, useFullVisc=fullvisc)
+    ns = hb.nw if coupled else 5
+    o = Oracle(hb, prm)
+    o.apply_turb_bc(True); o.apply_flow_bc(True)
+    o.time_step(True)
+    o.call("orc_speed_of_sound", C.byref(prm))
+    o.reference_shock_sensor()
+    T = oracle_blocks(prm, ank, hb)
+    U = vec_of(hb, ns)
+    rng = np.random.default_rng(5)
+    v = U * (1.0 + 0.01 * rng.standard_normal(U.size))
+    a = rng.standard_normal(U.size) * np.abs(U).clip(1e-6)
+    Fref = oracle_ank_function(prm, ank, hb, T, v)
+    h = 1e-6
+    F0 = oracle_ank_function(prm, ank, hb, T, U)
+    yref = (oracle_ank_function(prm, ank, hb, T, U + h * a) - F0) / h
+    s = ADFLOW_B200(prm)
+    try:
+        s.addBlock(hb)
+        s.ankSetParams(ank)
+        s.referenceShockSensor()
+        s.residual(RES_FLOW | RES_TURB | 4)        # useUpdateIntermed: dtl, spectral radii (and aa) of the current state
+        s.ankTimeStepMat()
+        F = s.ankFormFunction(v)
+        s.ankMffdSetBase(U)
+        y = s.ankMffdApply(a, h)
+        y2 = s.ankMffdApply(a, -1.0)
+    finally:
+        s.close()
+    assert rel_l2(F, Fref) < 1e-11, rel_l2(F, Fref)
+    assert rel_l2(y, yref) < 1e-5, rel_l2(y, yref)
+    assert rel_l2(y2, yref) < 5e-2     # PETSc's default h: consistent first-order quotient
+    # the time-step term is really there: F differs from the bare residual by T v
+    assert np.abs(np.einsum("qlm,qm->ql", T, v.reshape(-1, ns))).max() > 0
+
+
+@pytest.mark.parametrize("coupled", [False, True])
+def test_ank_physicality_check(cuda_lib, coupled):
+    prm, hb = case(10, 9, 7)
+    ank = make_ank_params(coupled=coupled)
+    ns = hb.nw if coupled else 5
+    wv = vec_of(hb, ns)
+    rng = np.random.default_rng(11)
+    dv = rng.standard_normal(wv.size) * np.abs(wv) * 0.4
+    if coupled:
+        dv[5::6][:50] = wv[5::6][:50] * 500.0
+    s = ADFLOW_B200(prm)
+    try:
+        s.addBlock(hb)
+        s.ankSetParams(ank)
+        for lam0 in (1.0, 0.03):
+            d_ref = dv.copy()
+            lam_ref = Oracle(hb, prm).ank_physicality_check(ank, wv, d_ref, lam0)
+            lam, d_dev = s.ankPhysicalityCheck(wv, dv, lam0)
+            assert lam == lam_ref and 0 < lam <= lam0
+            assert np.array_equal(d_dev, d_ref)
+    finally:
+        s.close()
