@@ -31,6 +31,9 @@
 #ifndef FACES_MINB
 #define FACES_MINB 4
 #endif
+#ifndef FACES_MINB_SPLIT
+#define FACES_MINB_SPLIT 6
+#endif
 #ifndef SA_TPB
 #define SA_TPB 128
 #endif
@@ -290,7 +293,8 @@ __device__ __forceinline__ CellState load_cell(const BlockDev& b, int N, int c) 
 
 // APPROX bit 0: first-order/lumped dissipation (*Approx routines), bit 1: thin-layer viscous flux,
 // bit 2: first-order coarse-level scalar dissipation (inviscidDissFluxScalarCoarse, fluxes.F90:4977-5203)
-template <bool VISCOUS, int DISC, int APPROX>
+// PART: 0 = everything, 1 = central + dissipation only, 2 = viscous flux only (split launch, ADFB_SPLIT_FACES)
+template <bool VISCOUS, int DISC, int APPROX, int PART = 0>
 __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int sd, int t1, int t2, int dir,
                                           const double* __restrict__ s, int8_t por, const double* __restrict__ rad,
                                           const double* __restrict__ dss, const CellState& m, double rFil, int doDiss,
@@ -298,7 +302,7 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
     const int cp = c + sd;
     const CellState q = load_cell(b, N, cp);
     const double s1 = s[c], s2 = s[N + c], s3 = s[2 * N + c];
-    {   // central
+    if (PART != 2) {   // central
         double vnp = q.u * s1 + q.v * s2 + q.w * s3;
         double vnm = m.u * s1 + m.v * s2 + m.w * s3;
         double porVel = 1.0, porFlux = 0.5;
@@ -316,6 +320,8 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
     }
 #pragma unroll
     for (int l = 0; l < 5; l++) fd[l] = 0.0;
+    if (PART == 2) doDiss = 0;
+    if (PART == 1) doVisc = 0;
     if (DISC == ADFB_DISS_SCALAR && (APPROX & 4) && doDiss) {
         const double ppor = (por == ADFB_NORMALFLUX) ? 0.5 : 0.0;
         const double dis0 = rFil * c_prm.vis2Coarse * ppor * (rad[c] + rad[cp]);
@@ -358,8 +364,9 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
         const double fis2 = rFil * c_prm.vis2, fis4 = rFil * c_prm.vis4;
         const double ppor = (por == ADFB_NORMALFLUX) ? 1.0 : 0.0;
         double dr, dru, drv, drw, dre;
-        if (APPROX & 1) {  // inviscidDissFluxMatrixApprox, blockette.F90:4672-4690
-            const double dis2 = fis2 * ppor * dmin_(0.25, dmax_(dss[c], dss[cp])) + c_prm.sigma * fis4 * ppor;
+        if (APPROX & 5) {  // inviscidDissFluxMatrixApprox, blockette.F90:4672-4690; bit 2: ...MatrixCoarse, fluxes.F90:5205-5711
+            const double dis2 = (APPROX & 4) ? rFil * c_prm.vis2Coarse * ppor
+                                             : fis2 * ppor * dmin_(0.25, dmax_(dss[c], dss[cp])) + c_prm.sigma * fis4 * ppor;
             dr = dis2 * (q.r - m.r);
             dru = dis2 * (q.r * q.u - m.r * m.u);
             drv = dis2 * (q.r * q.v - m.r * m.v);
@@ -580,8 +587,8 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
 // k_faces: plus faces of cell (i,j,k), i 1:il, j 1:jl, k 1:kl.  MERGED: one array G = fc - fd per
 // face (net outflow of the low cell) -> flux[dir*5 + l]; otherwise fc -> flux[dir*10 + l],
 // fd -> flux[dir*10 + 5 + l] (smoother path: fw persists between RK stages).
-template <bool VISCOUS, bool MERGED, int DISC, int APPROX, bool STOREWALL = false>
-__global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDev b, double rFil, int doVisc, int doDiss) {
+template <bool VISCOUS, bool MERGED, int DISC, int APPROX, bool STOREWALL = false, int PART = 0>
+__global__ void __launch_bounds__(FACES_TPB, PART == 0 ? FACES_MINB : FACES_MINB_SPLIT) k_faces(Dims d, BlockDev b, double rFil, int doVisc, int doDiss) {
     cudaGridDependencySynchronize();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
@@ -601,29 +608,32 @@ __global__ void __launch_bounds__(FACES_TPB, FACES_MINB) k_faces(Dims d, BlockDe
     };
     const bool oi = i >= 2, oj = j >= 2, ok = k >= 2;
     if (oj && ok) {
-        face_flux<VISCOUS, DISC, APPROX>(b, N, c, 1, sJ, sK, 0, b.si, b.porI[c], b.radI, b.dss, m, rFil, doDiss, doVisc, fc, fd, tqp);
+        face_flux<VISCOUS, DISC, APPROX, PART>(b, N, c, 1, sJ, sK, 0, b.si, b.porI[c], b.radI, b.dss, m, rFil, doDiss, doVisc, fc, fd, tqp);
         if (STOREWALL && (i == 1 || i == d.il)) store_wall(0, i == 1 ? 0 : 1, j + (long long)d.NJ * k);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
-            if (MERGED) b.flux[l * N + c] = fc[l] - fd[l];
+            if (MERGED && PART == 2) b.flux[(15 + l) * N + c] = -fd[l];
+            else if (MERGED) b.flux[l * N + c] = fc[l] - fd[l];
             else { b.flux[l * N + c] = fc[l]; b.flux[(5 + l) * N + c] = fd[l]; }
         }
     }
     if (oi && ok) {
-        face_flux<VISCOUS, DISC, APPROX>(b, N, c, sJ, 1, sK, 1, b.sj, b.porJ[c], b.radJ, b.dss + N, m, rFil, doDiss, doVisc, fc, fd, tqp);
+        face_flux<VISCOUS, DISC, APPROX, PART>(b, N, c, sJ, 1, sK, 1, b.sj, b.porJ[c], b.radJ, b.dss + N, m, rFil, doDiss, doVisc, fc, fd, tqp);
         if (STOREWALL && (j == 1 || j == d.jl)) store_wall(1, j == 1 ? 0 : 1, i + (long long)d.NI * k);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
-            if (MERGED) b.flux[(5 + l) * N + c] = fc[l] - fd[l];
+            if (MERGED && PART == 2) b.flux[(20 + l) * N + c] = -fd[l];
+            else if (MERGED) b.flux[(5 + l) * N + c] = fc[l] - fd[l];
             else { b.flux[(10 + l) * N + c] = fc[l]; b.flux[(15 + l) * N + c] = fd[l]; }
         }
     }
     if (oi && oj) {
-        face_flux<VISCOUS, DISC, APPROX>(b, N, c, sK, 1, sJ, 2, b.sk, b.porK[c], b.radK, b.dss + 2 * N, m, rFil, doDiss, doVisc, fc, fd, tqp);
+        face_flux<VISCOUS, DISC, APPROX, PART>(b, N, c, sK, 1, sJ, 2, b.sk, b.porK[c], b.radK, b.dss + 2 * N, m, rFil, doDiss, doVisc, fc, fd, tqp);
         if (STOREWALL && (k == 1 || k == d.kl)) store_wall(2, k == 1 ? 0 : 1, i + (long long)d.NI * j);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
-            if (MERGED) b.flux[(10 + l) * N + c] = fc[l] - fd[l];
+            if (MERGED && PART == 2) b.flux[(25 + l) * N + c] = -fd[l];
+            else if (MERGED) b.flux[(10 + l) * N + c] = fc[l] - fd[l];
             else { b.flux[(20 + l) * N + c] = fc[l]; b.flux[(25 + l) * N + c] = fd[l]; }
         }
     }
@@ -787,15 +797,25 @@ __global__ void __launch_bounds__(256) k_div(Dims d, BlockDev b, double rFil, in
     const double rblank = dmax_((double)b.iblank[c], 0.0);
     const double* F = b.flux;
     if (MERGED) {
+        const bool split = initWr == 2;   // k_faces ran as two launches: inviscid part in slots 0..14, viscous in 15..29
 #pragma unroll
         for (int l = 0; l < 5; l++) {
             double a = 0.0;
+            if (split) {
+                a -= F[l * N + c - 1] + F[(15 + l) * N + c - 1];
+                a += F[l * N + c] + F[(15 + l) * N + c];
+                a -= F[(5 + l) * N + c - sJ] + F[(20 + l) * N + c - sJ];
+                a += F[(5 + l) * N + c] + F[(20 + l) * N + c];
+                a -= F[(10 + l) * N + c - sK] + F[(25 + l) * N + c - sK];
+                a += F[(10 + l) * N + c] + F[(25 + l) * N + c];
+            } else {
             a -= F[l * N + c - 1];
             a += F[l * N + c];
             a -= F[(5 + l) * N + c - sJ];
             a += F[(5 + l) * N + c];
             a -= F[(10 + l) * N + c - sK];
             a += F[(10 + l) * N + c];
+            }
             b.dw[l * N + c] = a * rblank;
         }
     } else {
@@ -835,6 +855,11 @@ static int launch_geom(const Dims& d, const BlockDev& b, cudaStream_t stream) {
 }
 
 // doRad: 1 = recompute spectral radii + dtl (blockette order), 0 = keep them (block/smoother path)
+static bool split_faces() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ADFB_SPLIT_FACES"); v = e ? atoi(e) : 0; }
+    return v != 0;
+}
 static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbParams& prm, unsigned flags, double rFil,
                                 int persistFw, int doRad, cudaStream_t stream, int initWr = 0) {
     const int flowRes = (flags & ADFB_RES_FLOW) != 0;
@@ -904,15 +929,34 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         else ADFB_LAUNCH_FACES(V, M, ADFB_UPWIND, A);                       \
     } while (0)
         const int approx = dissApprox | (viscApprox << 1);
+        int splitDone = 0;
         const bool storeWall = (flags & ADFB_RES_STORE_WALL) && viscous && doVisc && merged && approx == 0;
         if (b.coarse) {   // coarse multigrid level: first-order scalar dissipation, block path only
-            if (merged || approx || prm.spaceDiscrCoarse != ADFB_DISS_SCALAR) return 1;
-            if (viscous) launch_pdl(k_faces<true, false, ADFB_DISS_SCALAR, 4>, g, tr, stream, d, b, rFil, doVisc, doDiss);
-            else launch_pdl(k_faces<false, false, ADFB_DISS_SCALAR, 4>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+            if (merged || approx || (prm.spaceDiscrCoarse != ADFB_DISS_SCALAR && prm.spaceDiscrCoarse != ADFB_DISS_MATRIX)) return 1;
+            if (prm.spaceDiscrCoarse == ADFB_DISS_SCALAR) {
+                if (viscous) launch_pdl(k_faces<true, false, ADFB_DISS_SCALAR, 4>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+                else launch_pdl(k_faces<false, false, ADFB_DISS_SCALAR, 4>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+            } else {
+                if (viscous) launch_pdl(k_faces<true, false, ADFB_DISS_MATRIX, 4>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+                else launch_pdl(k_faces<false, false, ADFB_DISS_MATRIX, 4>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+            }
         } else if (storeWall) {  // exact viscous flux + viscSubface%tau/%q planes for the force integration
             if (prm.spaceDiscr == ADFB_DISS_SCALAR) launch_pdl(k_faces<true, true, ADFB_DISS_SCALAR, 0, true>, g, tr, stream, d, b, rFil, doVisc, doDiss);
             else if (prm.spaceDiscr == ADFB_DISS_MATRIX) launch_pdl(k_faces<true, true, ADFB_DISS_MATRIX, 0, true>, g, tr, stream, d, b, rFil, doVisc, doDiss);
             else launch_pdl(k_faces<true, true, ADFB_UPWIND, 0, true>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+        } else if (approx == 0 && viscous && merged && doVisc && split_faces()) {
+            // two launches with fewer registers each (ADFB_SPLIT_FACES=1): central + dissipation, then viscous
+            if (prm.spaceDiscr == ADFB_DISS_SCALAR) {
+                launch_pdl(k_faces<true, true, ADFB_DISS_SCALAR, 0, false, 1>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+                launch_pdl(k_faces<true, true, ADFB_DISS_SCALAR, 0, false, 2>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+            } else if (prm.spaceDiscr == ADFB_DISS_MATRIX) {
+                launch_pdl(k_faces<true, true, ADFB_DISS_MATRIX, 0, false, 1>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+                launch_pdl(k_faces<true, true, ADFB_DISS_MATRIX, 0, false, 2>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+            } else {
+                launch_pdl(k_faces<true, true, ADFB_UPWIND, 0, false, 1>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+                launch_pdl(k_faces<true, true, ADFB_UPWIND, 0, false, 2>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+            }
+            splitDone = 1;
         } else if (approx == 0) {
             if (viscous) { if (merged) ADFB_FACES_DISC(true, true, 0); else ADFB_FACES_DISC(true, false, 0); }
             else { if (merged) ADFB_FACES_DISC(false, true, 0); else ADFB_FACES_DISC(false, false, 0); }
@@ -928,7 +972,7 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         KT_END(K_RESID, stream);
         dim3 g2((d.nx + tb.x - 1) / tb.x, (d.ny + tb.y - 1) / tb.y, (d.nz + tb.z - 1) / tb.z);
         KT_BEGIN(K_DIV, stream);
-        if (merged) launch_pdl(k_div<true>, g2, tb, stream, d, b, rFil, persistFw, 0);
+        if (merged) launch_pdl(k_div<true>, g2, tb, stream, d, b, rFil, persistFw, splitDone ? 2 : 0);
         else launch_pdl(k_div<false>, g2, tb, stream, d, b, rFil, persistFw, initWr);
         KT_END(K_DIV, stream);
     }

@@ -131,7 +131,7 @@ typedef struct AdfbParams {
     int32_t hScalingInlet;         /* inputDiscretization hScalingInlet (subsonic inflow, total conditions) */
     int32_t outflowLinearExtrapol; /* outflowTreatment == linExtrapol (default constantExtrapol), supersonic outflow */
     int32_t mgBoundCorr;           /* 0 = bcDirichlet0 (default), 1 = bcNeumann0: boundary halos of the interpolated corrections */
-    int32_t spaceDiscrCoarse;      /* coarse-level discretisation; only ADFB_DISS_SCALAR is supported on level > 1 */
+    int32_t spaceDiscrCoarse;      /* coarse-level discretisation: ADFB_DISS_SCALAR or ADFB_DISS_MATRIX on levels > 1 */
 } AdfbParams;
 
 /* One boundary subface of a block, mirroring BCDataType (src/modules/block.F90:52-156)
@@ -330,7 +330,7 @@ int adfb_ank_physicality_check(const double* wVec, double* deltaW, long long n, 
    lists, commPatternCell_1st / internalCell_1st).  On levels > 1 the entry points take the reference's
    currentLevel > groundLevel branches: dw starts from the residual forcing term wr (initRes_block,
    residuals.F90:485-497), first-order scalar dissipation with vis2Coarse (inviscidDissFluxScalarCoarse,
-   fluxes.F90:4977-5203; spaceDiscrCoarse must be ADFB_DISS_SCALAR), no directional scaling of the spectral radii
+   fluxes.F90:4977-5203, or inviscidDissFluxMatrixCoarse :5205-5711 with spaceDiscrCoarse = ADFB_DISS_MATRIX), no directional scaling of the spectral radii
    (solverUtils.F90:106), cflCoarse and no second halos in the RK stage (smoothers.F90:131-140), constant-pressure
    walls (BCRoutines.F90:550,642,1100), frozen eddy viscosity (turbUtils.F90:606-616).
    adfb_block_set_mg: tables of createCoarseBlocks (src/preprocessing/coarseUtils.F90:254-420) with the reference's

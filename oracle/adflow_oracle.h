@@ -106,6 +106,7 @@ void orc_sa_block(const OrcBlock* b, const AdfbParams* prm, int nSub, const Adfb
 void orc_rk_smoother(const OrcBlock* b, const AdfbParams* prm, int nSub, const AdfbSubface* sf);
 /* adflow_oracle_mg.c: multigrid transfer operators and the coarse-level residual (src/solver/multiGrid.F90) */
 void orc_diss_scalar_coarse(const OrcBlock* b, const AdfbParams* prm, double rFil);
+void orc_diss_matrix_coarse(const OrcBlock* b, const AdfbParams* prm, double rFil);
 void orc_residual_block_coarse(const OrcBlock* b, const AdfbParams* prm, double rFil, int init);
 void orc_mg_corner_row_halos(const OrcBlock* b, const AdfbParams* prm);
 void orc_mg_restrict(const OrcBlock* coarse, const OrcBlock* fine, const AdfbParams* prm, const int32_t* mgIFine,

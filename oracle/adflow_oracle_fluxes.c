@@ -253,7 +253,8 @@ void orc_diss_scalar_approx(const OrcBlock* b, const AdfbParams* prm) {
 }
 
 static void diss_matrix_approx_dir(const OrcBlock* b, const AdfbParams* prm, Dims d, const double* s, const double* dss,
-                                   const int8_t* por, long sd, int i0, int j0, int k0, double fis2, double fis4) {
+                                   const int8_t* por, long sd, int i0, int j0, int k0, double fis2, double fis4, double fis0) {
+    /* fis0 >= 0: inviscidDissFluxMatrixCoarse (fluxes.F90:5205-5711), dis0 = fis0 * ppor instead of the sensor form */
     const double dpMax = 0.25, epsAcoustic = 0.25, epsShear = 0.025;
     double gam = prm->gammaInf;
     const double* p = b->p;
@@ -261,7 +262,7 @@ static void diss_matrix_approx_dir(const OrcBlock* b, const AdfbParams* prm, Dim
         long c = IDX(i, j, k), cp = c + sd;
         double ppor = zero;
         if (por[c] == ADFB_NORMALFLUX) ppor = one;
-        double dis2 = fis2 * ppor * dmin(dpMax, dmax(dss[c], dss[cp])) + prm->sigma * fis4 * ppor;
+        double dis2 = fis0 >= zero ? fis0 * ppor : fis2 * ppor * dmin(dpMax, dmax(dss[c], dss[cp])) + prm->sigma * fis4 * ppor;
         double dr = dis2 * (W(cp, IRHO) - W(c, IRHO));
         double dru = dis2 * (W(cp, IRHO) * W(cp, IVX) - W(c, IRHO) * W(c, IVX));
         double drv = dis2 * (W(cp, IRHO) * W(cp, IVY) - W(c, IRHO) * W(c, IVY));
@@ -314,9 +315,23 @@ void orc_diss_matrix_approx(const OrcBlock* b, const AdfbParams* prm, double rFi
                                         oneMinOmega * (fabs(ss[c + sd] - ss[c]) + fabs(ss[c] - ss[c - sd])) + plim));
         }
     }
-    diss_matrix_approx_dir(b, prm, d, b->si, b->dss, b->porI, d.sI, 1, 2, 2, fis2, fis4);
-    diss_matrix_approx_dir(b, prm, d, b->sj, b->dss + d.N, b->porJ, d.sJ, 2, 1, 2, fis2, fis4);
-    diss_matrix_approx_dir(b, prm, d, b->sk, b->dss + 2 * d.N, b->porK, d.sK, 2, 2, 1, fis2, fis4);
+    diss_matrix_approx_dir(b, prm, d, b->si, b->dss, b->porI, d.sI, 1, 2, 2, fis2, fis4, -one);
+    diss_matrix_approx_dir(b, prm, d, b->sj, b->dss + d.N, b->porJ, d.sJ, 2, 1, 2, fis2, fis4, -one);
+    diss_matrix_approx_dir(b, prm, d, b->sk, b->dss + 2 * d.N, b->porK, d.sK, 2, 2, 1, fis2, fis4, -one);
+}
+
+/* inviscidDissFluxMatrixCoarse, fluxes.F90:5205-5711: first-order matrix dissipation of the coarse multigrid levels */
+void orc_diss_matrix_coarse(const OrcBlock* b, const AdfbParams* prm, double rFil) {
+    Dims d = dims_of(b);
+    if (fabs(rFil) < thresholdReal) return;
+    double fis0 = rFil * prm->vis2Coarse, sfil = one - rFil;
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
+        long c = IDX(i, j, k);
+        for (int l = 0; l < 5; l++) FW(c, l) = sfil * FW(c, l);
+    }
+    diss_matrix_approx_dir(b, prm, d, b->si, b->dss, b->porI, d.sI, 1, 2, 2, zero, zero, fis0);
+    diss_matrix_approx_dir(b, prm, d, b->sj, b->dss + d.N, b->porJ, d.sJ, 2, 1, 2, zero, zero, fis0);
+    diss_matrix_approx_dir(b, prm, d, b->sk, b->dss + 2 * d.N, b->porK, d.sK, 2, 2, 1, zero, zero, fis0);
 }
 
 /* viscousFluxApprox: thin-layer viscous flux, sweeps i, j, k (blockette.F90:6467-6837) */

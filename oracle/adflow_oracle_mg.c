@@ -75,7 +75,8 @@ void orc_residual_block_coarse(const OrcBlock* b, const AdfbParams* prm, double 
         memset(b->dw, 0, sizeof(double) * 5 * d.N);
     }
     orc_central_flux(b, prm);
-    orc_diss_scalar_coarse(b, prm, rFil);
+    if (prm->spaceDiscrCoarse == ADFB_DISS_MATRIX) orc_diss_matrix_coarse(b, prm, rFil);
+    else orc_diss_scalar_coarse(b, prm, rFil);
     if (viscous && fabs(rFil) > thresholdReal) {
         orc_speed_of_sound(b, prm);
         orc_nodal_gradients(b);

@@ -182,6 +182,9 @@ class Oracle:
     def diss_scalar_coarse(self, rfil=1.0):
         self.L.orc_diss_scalar_coarse(_p(self.ob), _p(self.prm), C.c_double(rfil))
 
+    def diss_matrix_coarse(self, rfil=1.0):
+        self.L.orc_diss_matrix_coarse(_p(self.ob), _p(self.prm), C.c_double(rfil))
+
     def mg_corner_row_halos(self):
         self.L.orc_mg_corner_row_halos(_p(self.ob), _p(self.prm))
 

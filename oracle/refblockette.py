@@ -359,6 +359,7 @@ class RefMG:
         set_params(prm, fine_hb.nw)
         _setd("vis2coarse", prm.vis2Coarse); _setd("fcoll", prm.fcoll); _seti("mgboundcorr", prm.mgBoundCorr)
         _seti("spacediscrcoarse", _REF_SPACEDISCR[prm.spaceDiscrCoarse])
+        _seti("radiineededcoarse", int(prm.spaceDiscrCoarse == 1))   # inputParamRoutines.F90:2824-2833
         self.lv = {1: RefBlock(fine_hb, prm), 2: RefBlock(coarse_hb, prm)}
         self.keep = {}
         L = lib()

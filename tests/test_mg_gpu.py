@@ -84,7 +84,8 @@ def prepare_fine(o):
 
 
 @pytest.mark.parametrize("shape,options", [((16, 12, 10), None), ((13, 9, 7), None), ((12, 8, 8), {"equationType": "Euler"}),
-                                           ((10, 12, 6), {"equationType": "laminar NS"})])
+                                           ((10, 12, 6), {"equationType": "laminar NS"}),
+                                           ((12, 10, 8), {"coarseDiscretization": "central plus matrix dissipation"})])
 def test_restrict_smooth_prolong_match_oracle(cuda_lib, shape, options):
     prm, levels = make_levels(shape, options, 2)
     dev_levels = [l.copy() for l in levels]
@@ -294,3 +295,124 @@ def test_two_block_v_cycle_with_halo_exchange_per_level(cuda_lib):
             assert rel_max(w[..., :5], hb.w[..., :5]) < 1e-10, q    # halos incl. the exchanged ones
     finally:
         s.close()
+
+
+def _mg_nccl_worker(rank, world, port, q):
+    import ctypes as C
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from adflow_b200 import _lib, make_params
+    from adflow_b200.halo import BlockGrid, build_cartesian_pattern, make_grid_blocks
+    L = _lib.load()
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = (C.c_char * 128)()
+        assert L.adfb_get_unique_id(buf) == 0
+        uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    dist.broadcast(uid, 0)
+    prm = make_params(_TWO_GPU_OPTS)
+    gf = BlockGrid((2, 1, 1), _TWO_GPU_SHAPE, nranks=world)
+    fine = make_grid_blocks(gf, rank, prm)
+    gc = BlockGrid((2, 1, 1), tuple(n // 2 for n in _TWO_GPU_SHAPE), nranks=world)
+    s = ADFLOW_B200(prm, device=rank, rank=rank, nranks=world, unique_id=bytes(uid.numpy().tobytes()))
+    for hb in fine:
+        s.addBlock(hb)
+    for qb, hb in enumerate(fine):
+        s.addCoarseBlock(syn.make_coarse_block(hb, prm), qb)
+    s.setCommPattern(build_cartesian_pattern(gf, rank), level=1)
+    s.setCommPattern(build_cartesian_pattern(gc, rank), level=2, block_offset=len(fine))
+    s.applyBCs(True, False)
+    s.haloExchange(1, 5, True, True, True)
+    s.timeStep(False)
+    s.smootherResidual(0)
+    s.mgCycle(ADFLOW_B200.cycleStrategy("2v"))
+    out = {}
+    for lq, b in enumerate(gf.local_blocks(rank)):
+        out[b] = s.downloadState(lq)[0]
+    s.close()
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+_TWO_GPU_OPTS = {"equationType": "laminar NS", "nRKStages": 3, "resAveraging": "never"}
+_TWO_GPU_SHAPE = (8, 8, 6)
+
+
+def test_two_gpu_v_cycle_matches_single_process_oracle(cuda_lib):
+    """one fine + one coarse block per GPU, NCCL exchange of each level's pattern inside the multigrid cycle"""
+    if cuda_lib.adfb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+
+    import torch.multiprocessing as mp
+    from adflow_b200 import make_params
+    from adflow_b200.halo import BlockGrid, build_cartesian_pattern, comm_vars, exchange_numpy, make_grid_blocks
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_mg_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        _rank, out = q.get(timeout=600)
+        got.update(out)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    # the same cycle with the oracle, all blocks in one process
+    prm = make_params(_TWO_GPU_OPTS)
+    gf = BlockGrid((2, 1, 1), _TWO_GPU_SHAPE, nranks=1)
+    fine = make_grid_blocks(gf, 0, prm)
+    pf = build_cartesian_pattern(gf, 0)
+    coarse = [syn.make_coarse_block(hb, prm) for hb in fine]
+    pc = build_cartesian_pattern(BlockGrid((2, 1, 1), tuple(n // 2 for n in _TWO_GPU_SHAPE), nranks=1), 0)
+    vars_ = lambda hb: comm_vars(hb, 1, 5, True, True, True, False)  # noqa: E731
+
+    def rk_smoother(blocks, pat):
+        for hb in blocks:
+            np.copyto(hb.wn, hb.w[..., :5]); np.copyto(hb.pn, hb.p)
+        for st in range(1, prm.nRKStages + 1):
+            for hb in blocks:
+                Oracle(hb, prm).rk_stage(st)
+            exchange_numpy(blocks, pat, vars_)
+            if st < prm.nRKStages:
+                for hb in blocks:
+                    Oracle(hb, prm).residual_block(prm.cdisRK[st])
+
+    for hb in fine:
+        Oracle(hb, prm).apply_flow_bc(True)
+    exchange_numpy(fine, pf, vars_)
+    w0 = [hb.w.copy() for hb in fine]
+    for hb in fine:
+        prepare_fine(Oracle(hb, prm))
+    rk_smoother(fine, pf)
+    for f, c in zip(fine, coarse):
+        of, oc = Oracle(f, prm), Oracle(c, prm)
+        of.time_step(False); of.residual_block(prm.cdisRK[0])
+        oc.mg_restrict(of); oc.apply_flow_bc(False)
+    exchange_numpy(coarse, pc, vars_)
+    for c in coarse:
+        oc = Oracle(c, prm)
+        oc.time_step(True); oc.mg_store_w1(); oc.residual_block_coarse(prm.cdisRK[0], init=0); oc.mg_forcing()
+    rk_smoother(coarse, pc)
+    for f, c in zip(fine, coarse):
+        of, oc = Oracle(f, prm), Oracle(c, prm)
+        of.mg_prolong(oc); of.apply_flow_bc(True)
+    exchange_numpy(fine, pf, vars_)
+    for b, hb in enumerate(fine):
+        ow = hb.d.owned()
+        for l in range(5):
+            a, r = got[b][ow + (l,)] - w0[b][ow + (l,)], hb.w[ow + (l,)] - w0[b][ow + (l,)]
+            assert np.abs(r).max() > 0
+            assert rel_l2(a, r) < 1e-8, (b, l, rel_l2(a, r))
+        assert rel_max(got[b][..., :5], hb.w[..., :5]) < 1e-10, b

@@ -15,7 +15,8 @@ from util import case
 pytestmark = pytest.mark.skipif(not rb.available(), reason="oracle/_ref not built (no /root/reference at build time)")
 
 CASES = [((12, 8, 10), None), ((9, 7, 6), None), ((8, 6, 6), {"equationType": "Euler"}),
-         ((6, 9, 5), {"equationType": "laminar NS"})]
+         ((6, 9, 5), {"equationType": "laminar NS"}),
+         ((10, 8, 6), {"coarseDiscretization": "central plus matrix dissipation"})]
 
 
 def two_levels(shape, options, seed=314):
@@ -182,3 +183,23 @@ def test_coarse_level_dadi_smoother(shape, options):
     assert np.abs(coarse.w[d.owned()][..., :5] - c2.w[d.owned()][..., :5]).max() > 0
     eq(coarse.w[c1][..., :5], rc["w"][c1][..., :5], "coarse w after the DADI step")
     eq(coarse.p[c1], rc["p"][c1], "coarse p after the DADI step")
+
+
+def test_coarse_matrix_dissipation():
+    """inviscidDissFluxMatrixCoarse (coarseDiscretization = matrix dissipation)"""
+    prm, fine, coarse = two_levels((10, 8, 6), {"coarseDiscretization": "central plus matrix dissipation"})
+    oracle_transfer_to_coarse(prm, fine, coarse)
+    rng = np.random.default_rng(1)
+    coarse.fw[...] = 1e-3 * rng.standard_normal(coarse.fw.shape)
+    c2 = coarse.copy()
+    mg = rb.RefMG(fine.copy(), c2, prm)
+    try:
+        mg.seed_coarse_shared()
+        rb._setd("rfil", 0.56)
+        mg.call(2, "fluxes_invisciddissfluxmatrixcoarse")
+    finally:
+        mg.close()
+    Oracle(coarse, prm).diss_matrix_coarse(0.56)
+    ow = coarse.d.owned()
+    assert np.abs(coarse.fw[ow] - c2.fw[ow]).max() > 0
+    eq(coarse.fw[ow], mg.lv[1].a["fw"][ow], "fw")
