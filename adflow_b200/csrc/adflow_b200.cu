@@ -473,6 +473,7 @@ int adfb_block_set_bc(int blk, int nSub, const AdfbSubface* subfaces) {
     for (int s = 0; s < nSub; s++) {
         AdfbSubface sf = subfaces[s];
         if (sf.faceId < ADFB_IMIN || sf.faceId > ADFB_KMAX) return fail("adfb_block_set_bc: bad faceId %d", sf.faceId);
+        if (sf.bcType < ADFB_BC_SYMM || sf.bcType > ADFB_BC_SYMMPOLAR) return fail("adfb_block_set_bc: unsupported bcType %d", sf.bcType);
         const size_t n = (size_t)(sf.icEnd - sf.icBeg + 1) * (sf.jcEnd - sf.jcBeg + 1);
         auto up = [&](const double*& hp, int ncomp) -> int {
             if (!hp) return 0;

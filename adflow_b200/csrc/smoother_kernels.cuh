@@ -19,6 +19,7 @@ struct FaceDev {
     const double *norm, *rface, *uSlip, *TNSWall;
     const double *ps, *rho, *velx, *vely, *velz, *ptInlet, *ttInlet, *htInlet, *fxd, *fyd, *fzd, *turbInlet;
     int inletTreatment;
+    long long xoff;   // node plane of the boundary face (polar symmetry reads the mesh)
 };
 
 static FaceDev make_face(const Dims& d, const AdfbSubface& sf) {
@@ -38,6 +39,7 @@ static FaceDev make_face(const Dims& d, const AdfbSubface& sf) {
     f.ptInlet = sf.ptInlet; f.ttInlet = sf.ttInlet; f.htInlet = sf.htInlet;
     f.fxd = sf.flowXdirInlet; f.fyd = sf.flowYdirInlet; f.fzd = sf.flowZdirInlet; f.turbInlet = sf.turbInlet;
     f.inletTreatment = sf.subsonicInletTreatment;
+    f.xoff = (sf.faceId == ADFB_IMIN || sf.faceId == ADFB_JMIN || sf.faceId == ADFB_KMIN) ? f.off[1] : f.off[2];
     return f;
 }
 
@@ -119,6 +121,24 @@ __global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, 
             w[N + ch] = u - vn * n1;
             w[2 * N + ch] = v - vn * n2;
             w[3 * N + ch] = ww - vn * n3;
+            w[4 * N + ch] = w[4 * N + ci];
+            b.p[ch] = b.p[ci];
+            if (viscous) b.rlv[ch] = b.rlv[ci];
+            if (eddy) b.rev[ch] = b.rev[ci];
+            break;
+        }
+        case ADFB_BC_SYMMPOLAR: {  // bcSymmPolar1stHalo / 2ndHalo, BCRoutines.F90:332-486
+            const long long ch = phase == 1 ? c1 : c0, ci = phase == 1 ? c2 : c3;
+            const long long nA = f.xoff + q, nB = f.xoff + (ia - 1) * f.sa + (jb - 1) * f.sb;
+            double nnx = b.x[nA] - b.x[nB], nny = b.x[N + nA] - b.x[N + nB], nnz = b.x[2 * N + nA] - b.x[2 * N + nB];
+            double tmp = 1.0 / sqrt(nnx * nnx + nny * nny + nnz * nnz);
+            nnx = nnx * tmp; nny = nny * tmp; nnz = nnz * tmp;
+            const double u = w[N + ci], v = w[2 * N + ci], ww = w[3 * N + ci];
+            tmp = 2.0 * (u * nnx + v * nny + ww * nnz);
+            w[ch] = w[ci];
+            w[N + ch] = tmp * nnx - u;
+            w[2 * N + ch] = tmp * nny - v;
+            w[3 * N + ch] = tmp * nnz - ww;
             w[4 * N + ch] = w[4 * N + ci];
             b.p[ch] = b.p[ci];
             if (viscous) b.rlv[ch] = b.rlv[ci];
@@ -585,6 +605,9 @@ static int launch_bc_flow(const Dims& d, const BlockDev& b, const std::vector<Ad
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SYMM) launch_bc_one(d, b, sf, secondHalo, 1, s);
     if (secondHalo)
         for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SYMM) launch_bc_one(d, b, sf, secondHalo, 2, s);
+    for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SYMMPOLAR) launch_bc_one(d, b, sf, secondHalo, 1, s);
+    if (secondHalo)
+        for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SYMMPOLAR) launch_bc_one(d, b, sf, secondHalo, 2, s);
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_NSWALL_ADIABATIC) launch_bc_one(d, b, sf, secondHalo, 0, s);
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_NSWALL_ISOTHERMAL) launch_bc_one(d, b, sf, secondHalo, 0, s);
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_FARFIELD) launch_bc_one(d, b, sf, secondHalo, 0, s);

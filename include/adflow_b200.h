@@ -64,7 +64,9 @@ enum {
     ADFB_BC_SUBSONIC_OUTFLOW = 7,   /* bcSubsonicOutflow (also MassBleedOutflow), needs ps */
     ADFB_BC_SUBSONIC_INFLOW = 8,    /* bcSubsonicInflow: totalConditions (ptInlet, ttInlet, htInlet, flow?dirInlet) or massFlow (rho, vel?) */
     ADFB_BC_SUPERSONIC_INFLOW = 9,  /* bcSupersonicInflow: rho, velx, vely, velz, ps prescribed */
-    ADFB_BC_SUPERSONIC_OUTFLOW = 10 /* bcExtrap with outflowTreatment (constant or linear extrapolation) */
+    ADFB_BC_SUPERSONIC_OUTFLOW = 10, /* bcExtrap with outflowTreatment (constant or linear extrapolation) */
+    ADFB_BC_SYMMPOLAR = 11          /* bcSymmPolar1stHalo/2ndHalo (BCRoutines.F90:332-486): singular (polar) line, the
+                                       mirror direction is the diagonal of the collapsed face, taken from the mesh x */
 };
 /* block faces, reference order iMin..kMax (src/modules/constants.F90 iMin=1..kMax=6) */
 enum { ADFB_IMIN = 1, ADFB_IMAX = 2, ADFB_JMIN = 3, ADFB_JMAX = 4, ADFB_KMIN = 5, ADFB_KMAX = 6 };

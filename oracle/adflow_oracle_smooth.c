@@ -111,6 +111,27 @@ static void bc_flow_subface(const OrcBlock* b, const AdfbParams* prm, const Adfb
                 if (eddy) b->rev[ch] = b->rev[ci];
                 break;
             }
+            case ADFB_BC_SYMMPOLAR: {  /* bcSymmPolar1stHalo / 2ndHalo, BCRoutines.F90:332-486 */
+                long ch = phase == 1 ? c1 : c0, ci = phase == 1 ? c2 : c3;
+                /* xx(i+1,j+1,:) - xx(i,j,:): diagonal of the (collapsed) boundary face, nodes (ia,jb) and (ia-1,jb-1) */
+                int isMin = sf->faceId == ADFB_IMIN || sf->faceId == ADFB_JMIN || sf->faceId == ADFB_KMIN;
+                long xo = isMin ? f.off[1] : f.off[2];
+                long nA = xo + ia * f.sa + jb_ * f.sb, nB = xo + (ia - 1) * f.sa + (jb_ - 1) * f.sb;
+                double nnx = X(nA, 0) - X(nB, 0), nny = X(nA, 1) - X(nB, 1), nnz = X(nA, 2) - X(nB, 2);
+                double tmp = one / sqrt(nnx * nnx + nny * nny + nnz * nnz);
+                nnx = nnx * tmp; nny = nny * tmp; nnz = nnz * tmp;
+                tmp = two * (W(ci, IVX) * nnx + W(ci, IVY) * nny + W(ci, IVZ) * nnz);
+                double vtx = tmp * nnx, vty = tmp * nny, vtz = tmp * nnz;
+                W(ch, IRHO) = W(ci, IRHO);
+                W(ch, IVX) = vtx - W(ci, IVX);
+                W(ch, IVY) = vty - W(ci, IVY);
+                W(ch, IVZ) = vtz - W(ci, IVZ);
+                W(ch, IRHOE) = W(ci, IRHOE);
+                b->p[ch] = b->p[ci];
+                if (viscous) b->rlv[ch] = b->rlv[ci];
+                if (eddy) b->rev[ch] = b->rev[ci];
+                break;
+            }
             case ADFB_BC_NSWALL_ADIABATIC: {
                 double us1 = zero, us2 = zero, us3 = zero;
                 if (sf->uSlip) {
@@ -335,6 +356,8 @@ void orc_apply_flow_bc(const OrcBlock* b, const AdfbParams* prm0, int nSub, cons
     const AdfbParams* prm = &prmL;
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SYMM) bc_flow_subface(b, prm, &sf[n], secondHalo, 1);
     if (secondHalo) for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SYMM) bc_flow_subface(b, prm, &sf[n], secondHalo, 2);
+    for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SYMMPOLAR) bc_flow_subface(b, prm, &sf[n], secondHalo, 1);
+    if (secondHalo) for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_SYMMPOLAR) bc_flow_subface(b, prm, &sf[n], secondHalo, 2);
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_NSWALL_ADIABATIC) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_NSWALL_ISOTHERMAL) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);
     for (n = 0; n < nSub; n++) if (sf[n].bcType == ADFB_BC_FARFIELD) bc_flow_subface(b, prm, &sf[n], secondHalo, 0);

@@ -243,7 +243,8 @@ UNITS = [
     ("modules/BCPointers.F90", "bcpointers_", [], ("USE_TAPENADE",)),
     ("utils/utils.F90", "", ["setbcpointers", "sumresiduals", "sumallresiduals"], ()),
     ("adjoint/adjointUtils.F90", "adjointutils_", ["referenceshocksensor"], ()),
-    ("solver/BCRoutines.F90", "bcroutines_", ["applyallbc", "applyallbc_block", "bcsymm1sthalo", "bcsymm2ndhalo", "bcnswalladiabatic",
+    ("solver/BCRoutines.F90", "bcroutines_", ["applyallbc", "applyallbc_block", "bcsymm1sthalo", "bcsymm2ndhalo", "bcsymmpolar1sthalo",
+                                              "bcsymmpolar2ndhalo", "bcnswalladiabatic",
                                               "bcnswallisothermal", "bcfarfield", "bceulerwall", "bcextrap", "bcsubsonicoutflow",
                                               "bcsubsonicinflow", "bcsupersonicinflow",
                                               "computeetot", "extrapolate2ndhalo"], ()),

@@ -87,9 +87,6 @@ UNREACHABLE(turbutils_kweddyviscosity)
 UNREACHABLE(turbutils_ssteddyviscosity)
 UNREACHABLE(turbutils_kteddyviscosity)
 UNREACHABLE(turbutils_vfeddyviscosity)
-/* boundary-condition types outside section 8 (polar symmetry) */
-UNREACHABLE(bcroutines_bcsymmpolar1sthalo)
-UNREACHABLE(bcroutines_bcsymmpolar2ndhalo)
 /* full-multigrid start-up (transferToFineGrid(corrections = .false.)) is outside the path */
 void turbbcroutines_applyallturbbc(int* secondhalo) { (void)secondhalo; terminate("applyAllTurbBC", "full-multigrid start-up is outside the translated hot path"); }
 

@@ -126,7 +126,7 @@ class RefSubface(C.Structure):
 
 # AdfbSubface.bcType (include/adflow_b200.h) -> name of the reference's BC constant
 _BC_NAME = {1: "symm", 2: "nswalladiabatic", 3: "farfield", 4: "eulerwall", 5: "extrap", 6: "nswallisothermal",
-            7: "subsonicoutflow", 8: "subsonicinflow", 9: "supersonicinflow", 10: "supersonicoutflow"}
+            7: "subsonicoutflow", 8: "subsonicinflow", 9: "supersonicinflow", 10: "supersonicoutflow", 11: "symmpolar"}
 
 
 def bind_bcs(hb, prm, other_level=False):

@@ -183,3 +183,20 @@ def test_residual_norms():
     rb.again("sumallresiduals", 2)
     mon = (C.c_double * 16).in_dll(rb.lib(), "monloc")
     assert mon[0] == want[0] and mon[1] == want[1]
+
+
+SYMMPOLAR = 11
+
+
+@pytest.mark.parametrize("perm", [
+    {IMIN: SYMMPOLAR, IMAX: FAR, JMIN: SYMM, JMAX: FAR, KMIN: WALL, KMAX: FAR},
+    {IMIN: FAR, IMAX: FAR, JMIN: FAR, JMAX: SYMMPOLAR, KMIN: FAR, KMAX: SYMMPOLAR},
+    {IMIN: WALL, IMAX: SYMMPOLAR, JMIN: SYMMPOLAR, JMAX: FAR, KMIN: SYMMPOLAR, KMAX: FAR},
+])
+@pytest.mark.parametrize("second", [True, False])
+def test_polar_symmetry(perm, second):
+    """bcSymmPolar1stHalo / bcSymmPolar2ndHalo (BCRoutines.F90:332-486): mirror direction from the face diagonal
+    xx(i+1,j+1) - xx(i,j) (setBCPointers with spatial pointers)"""
+    prm, hb = case(8, 7, 9, {"equationType": "RANS"}, physical_faces=perm)
+    hb.subfaces.sort(key=lambda s_: 0 if s_["bcType"] in (2, 6) else 1)
+    _check(prm, hb, second)

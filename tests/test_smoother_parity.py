@@ -18,6 +18,7 @@ def box_close(a, b, tol, name):
 
 ISO_EXTRAP_FACES = {1: 5, 2: 3, 3: 1, 4: 3, 5: 6, 6: 5}  # iMin extrap, jMin symm, kMin isothermal wall, kMax extrap
 INOUT_FACES = {1: 8, 2: 7, 3: 9, 4: 10, 5: 2, 6: 8}      # subsonic in (total) / out, supersonic in / out, wall, subsonic in (mass flow)
+POLAR_FACES = {1: 11, 2: 3, 3: 1, 4: 11, 5: 2, 6: 11}    # polar symmetry on a min and two max faces
 
 
 @pytest.mark.parametrize("options,faces", [(None, None), ({"equationType": "Euler"}, None),
@@ -25,7 +26,8 @@ INOUT_FACES = {1: 8, 2: 7, 3: 9, 4: 10, 5: 2, 6: 8}      # subsonic in (total) /
                                            ({"viscWallTreatment": "linear pressure extrapolation"}, None),
                                            (None, ISO_EXTRAP_FACES),
                                            ({"viscWallTreatment": "linear pressure extrapolation"}, ISO_EXTRAP_FACES),
-                                           (None, INOUT_FACES), ({"equationType": "Euler"}, INOUT_FACES)])
+                                           (None, INOUT_FACES), ({"equationType": "Euler"}, INOUT_FACES),
+                                           (None, POLAR_FACES)])
 def test_bcs_match_oracle(cuda_lib, options, faces):
     prm, hb = case(13, 11, 9, options, **({} if faces is None else {"physical_faces": faces}))
     ho = hb.copy()
