@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "adfb_reference_shock_sensor", "adfb_form_function", "adfb_mffd_set_base", "adfb_mffd_apply", "adfb_mffd_apply_device", "adfb_mffd_last_h",
     "adfb_apply_bcs", "adfb_timestep", "adfb_smoother_residual", "adfb_rk_stage", "adfb_rk_cycle", "adfb_dadi_step", "adfb_dadi_cycle", "adfb_sa_ddadi",
     "adfb_block_set_mg", "adfb_mg_restrict", "adfb_mg_prolong", "adfb_mg_cycle",
-    "adfb_ank_set_params", "adfb_ank_time_step_mat", "adfb_ank_form_function", "adfb_ank_mffd_set_base", "adfb_ank_mffd_apply",
+    "adfb_ank_set_params", "adfb_ank_time_step_mat", "adfb_ank_form_function", "adfb_ank_mffd_set_base", "adfb_ank_mffd_apply", "adfb_ank_mffd_apply_device",
     "adfb_ank_physicality_check",
 ]
 
@@ -104,6 +104,7 @@ def load():
     L.adfb_ank_form_function.argtypes = [vp, vp, C.c_longlong]
     L.adfb_ank_mffd_set_base.argtypes = [vp, C.c_longlong]
     L.adfb_ank_mffd_apply.argtypes = [vp, vp, C.c_longlong, C.c_double]
+    L.adfb_ank_mffd_apply_device.argtypes = [vp, vp, C.c_longlong, C.c_double]
     L.adfb_ank_physicality_check.argtypes = [vp, vp, C.c_longlong, C.POINTER(C.c_double)]
     L.adfb_launch_count.restype = C.c_longlong
     L.adfb_stream.restype = C.c_void_p

@@ -1354,6 +1354,20 @@ int adfb_ank_mffd_set_base(const double* U, long long n) {
     g.nkHaveBase = false;   // the NK base shares the buffers
     return 0;
 }
+// y = (F(U + h a) - F(U)) / h with a in g.nkA, y into g.nkY; returns 2 when a == 0
+static int ank_mffd_core(long long need, double h) {
+    if (h <= 0.0) {
+        double aa = 0.0;
+        if (nk_sumsq(g.nkA, need, &aa)) return 1;
+        if (aa == 0.0) { g.nkLastH = 0.0; return 2; }
+        h = 1.4901161193847656e-08 * sqrt(1.0 + g.ankUnorm) / sqrt(aa);
+    }
+    g.nkLastH = h;
+    if (ank_vec_kernel(g.nkA, g.nkU, nullptr, g.ankPert, h, 1)) return 1;
+    if (adfb_residual(1, ank_res_flags())) return 1;
+    if (ank_vec_kernel(g.ankPert, g.nkF0, g.nkY, nullptr, h, 3)) return 1;
+    return 0;
+}
 int adfb_ank_mffd_apply(const double* a, double* y, long long n, double h) {
     NEED_INIT();
     long long need = 0;
@@ -1361,17 +1375,30 @@ int adfb_ank_mffd_apply(const double* a, double* y, long long n, double h) {
     if (ank_ready("adfb_ank_mffd_apply", n, &need)) return 1;
     if (!g.ankHaveBase) return fail("adfb_ank_mffd_apply: adfb_ank_mffd_set_base has not been called");
     CK(cudaMemcpyAsync(g.nkA, a, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-    if (h <= 0.0) {
-        double aa = 0.0;
-        if (nk_sumsq(g.nkA, need, &aa)) return 1;
-        if (aa == 0.0) { g.nkLastH = 0.0; memset(y, 0, need * sizeof(double)); return 0; }
-        h = 1.4901161193847656e-08 * sqrt(1.0 + g.ankUnorm) / sqrt(aa);
-    }
-    g.nkLastH = h;
-    if (ank_vec_kernel(g.nkA, g.nkU, nullptr, g.ankPert, h, 1)) return 1;
-    if (adfb_residual(1, ank_res_flags())) return 1;
-    if (ank_vec_kernel(g.ankPert, g.nkF0, g.nkY, nullptr, h, 3)) return 1;
+    const int rc = ank_mffd_core(need, h);
+    if (rc == 1) return 1;
+    if (rc == 2) { CK(cudaStreamSynchronize(g.stream)); memset(y, 0, need * sizeof(double)); return 0; }
     CK(cudaMemcpyAsync(y, g.nkY, need * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+// the same product for Krylov vectors resident on this device (PETSc VECCUDA), like adfb_mffd_apply_device
+int adfb_ank_mffd_apply_device(const double* aDev, double* yDev, long long n, double h) {
+    NEED_INIT();
+    long long need = 0;
+    if (!aDev || !yDev) return fail("adfb_ank_mffd_apply_device: null vector");
+    if (ank_ready("adfb_ank_mffd_apply_device", n, &need)) return 1;
+    if (!g.ankHaveBase) return fail("adfb_ank_mffd_apply_device: adfb_ank_mffd_set_base has not been called");
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, aDev) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != g.device)
+        return fail("adfb_ank_mffd_apply_device: a is not a device pointer of device %d", g.device);
+    if (cudaPointerGetAttributes(&at, yDev) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != g.device)
+        return fail("adfb_ank_mffd_apply_device: y is not a device pointer of device %d", g.device);
+    CK(cudaMemcpyAsync(g.nkA, aDev, need * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+    const int rc = ank_mffd_core(need, h);
+    if (rc == 1) return 1;
+    if (rc == 2) CK(cudaMemsetAsync(yDev, 0, need * sizeof(double), g.stream));
+    else CK(cudaMemcpyAsync(yDev, g.nkY, need * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     return 0;
 }

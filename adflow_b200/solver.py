@@ -165,6 +165,9 @@ class ADFLOW_B200:
         check(self.L.adfb_ank_mffd_apply(a.ctypes.data, y.ctypes.data, a.size, h), "adfb_ank_mffd_apply")
         return y
 
+    def ankMffdApplyDevice(self, a_ptr, y_ptr, n, h=-1.0):
+        check(self.L.adfb_ank_mffd_apply_device(a_ptr, y_ptr, n, h), "adfb_ank_mffd_apply_device")
+
     def ankPhysicalityCheck(self, w_vec, delta_w, lambda_p=1.0):
         """returns (lambdaP, deltaW) -- deltaW with the clipped turbulence updates (coupled ANK)"""
         w = np.ascontiguousarray(w_vec, dtype=np.float64)

@@ -392,6 +392,28 @@ def main():
             "note": "unfused form: perturb + residual + difference (464 B/cell); a and y are pinned host vectors, "
                     "so the time includes 2 x %d MB over PCIe" % (a.nbytes >> 20)}
 
+        # ANK matrix-free product (approximate fluxes + time-step term), vectors resident on the device
+        from adflow_b200.params import make_ank_params
+        s.uploadState(0, hb)
+        s.ankSetParams(make_ank_params(cfl=5.0, coupled=False))
+        s.referenceShockSensor()
+        s.residual(flags_full | 4)
+        s.ankTimeStepMat()
+        Ua = np.ascontiguousarray(np.transpose(hb.w[hb.d.owned()][..., :5], (2, 1, 0, 3)).reshape(-1))
+        s.ankMffdSetBase(Ua)
+        dka = torch.from_numpy(np.random.default_rng(9).standard_normal(Ua.size)).cuda()
+        dky = torch.empty_like(dka)
+        s.ankMffdApplyDevice(dka.data_ptr(), dky.data_ptr(), dka.numel(), 1e-7)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            s.ankMffdApplyDevice(dka.data_ptr(), dky.data_ptr(), dka.numel(), 1e-7)
+        torch.cuda.synchronize()
+        msa = (time.perf_counter() - t0) * 1e3 / nrep
+        others["ank_mffd_matvec_device_vectors"] = {
+            "ms": msa, "Mcells/s": cells / (msa * 1e-3) / 1e6,
+            "note": "ANKSolver FormFunction_mf product (decoupled, nState = 5): perturb + blocketteRes with the approximate "
+                    "dissipation (flow rows only) + timeStepMat term + difference, vectors on the GPU"}
         # one multigrid cycle (the smoother of config C3: 4W, Runge-Kutta) on the same block: 4 grid levels
         from adflow_b200 import synthetic as syn
         lv = [hb]

@@ -321,6 +321,8 @@ int adfb_ank_form_function(const double* inVec, double* rVec, long long n);
    y = (F(U + h a) - F(U)) / h for host vectors; h <= 0: PETSc's default differencing parameter as in adfb_mffd_apply */
 int adfb_ank_mffd_set_base(const double* U, long long n);
 int adfb_ank_mffd_apply(const double* a, double* y, long long n, double h);
+/* the same product with a and y resident on this GPU (PETSc VECCUDA arrays): no PCIe traffic */
+int adfb_ank_mffd_apply_device(const double* aDev, double* yDev, long long n, double h);
 /* physicalityCheckANK (:3013-3210): largest step lambda <= *lambdaP that changes rho and rhoE by at most physLSTol
    (and decreases the turbulence variable by at most physLSTolTurb; individual turbulence updates that would be more
    limiting than stepFactor * stepMin are clipped in deltaW instead), MIN-reduced over the ranks */

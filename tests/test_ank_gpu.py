@@ -88,6 +88,11 @@ def test_ank_operator_and_product(cuda_lib, options, coupled, kind, fullvisc):
         s.ankMffdSetBase(U)
         y = s.ankMffdApply(a, h)
         y2 = s.ankMffdApply(a, -1.0)
+        import torch
+        da = torch.from_numpy(a.copy()).cuda()
+        dy = torch.zeros_like(da)
+        s.ankMffdApplyDevice(da.data_ptr(), dy.data_ptr(), da.numel(), h)
+        assert np.array_equal(dy.cpu().numpy(), y)
     finally:
         s.close()
     assert rel_l2(F, Fref) < 1e-11, rel_l2(F, Fref)
