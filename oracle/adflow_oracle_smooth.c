@@ -62,7 +62,7 @@ static void bc_turb_subface(const OrcBlock* b, const AdfbParams* prm, const Adfb
         double bmt = zero, bvt = zero;
         int wall = sf->bcType == ADFB_BC_NSWALL_ADIABATIC || sf->bcType == ADFB_BC_NSWALL_ISOTHERMAL;
         if (wall) bmt = one;
-        else if (sf->bcType == ADFB_BC_SYMM) bmt = -one;
+        else if (sf->bcType == ADFB_BC_SYMM || sf->bcType == ADFB_BC_SYMMPOLAR) bmt = -one;   /* bcTurbSymm, turbBCRoutines.F90:765 */
         else if (sf->bcType == ADFB_BC_FARFIELD) {
             double dot = NRM(sf, ia, jb_, 0) * prm->wInf[IVX] + NRM(sf, ia, jb_, 1) * prm->wInf[IVY] +
                          NRM(sf, ia, jb_, 2) * prm->wInf[IVZ] - (sf->rface ? sf->rface[(ia - sf->icBeg) + na * (jb_ - sf->jcBeg)] : zero);

@@ -98,6 +98,7 @@ def test_euler_wall(const_p):
     {IMIN: SYMM, IMAX: FAR, JMIN: WALL, JMAX: FAR, KMIN: FAR, KMAX: WALL},
     {IMIN: EXTRAP, IMAX: FAR, JMIN: SYMM, JMAX: ISOWALL, KMIN: ISOWALL, KMAX: EXTRAP},
     {IMIN: SUBIN, IMAX: SUBOUT, JMIN: SUPIN, JMAX: SUPOUT, KMIN: WALL, KMAX: FAR},
+    {IMIN: 11, IMAX: FAR, JMIN: SYMM, JMAX: 11, KMIN: WALL, KMAX: 11},   # polar symmetry: bcTurbSymm
 ])
 @pytest.mark.parametrize("second", [True, False])
 def test_turbulence_bcs(perm, second):
