@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "adfb_apply_bcs", "adfb_timestep", "adfb_smoother_residual", "adfb_rk_stage", "adfb_rk_cycle", "adfb_dadi_step", "adfb_dadi_cycle", "adfb_sa_ddadi",
     "adfb_block_set_mg", "adfb_mg_restrict", "adfb_mg_prolong", "adfb_mg_cycle",
     "adfb_ank_set_params", "adfb_ank_time_step_mat", "adfb_ank_form_function", "adfb_ank_mffd_set_base", "adfb_ank_mffd_apply", "adfb_ank_mffd_apply_device",
-    "adfb_ank_physicality_check",
+    "adfb_ank_physicality_check", "adfb_gmres_solve",
 ]
 
 
@@ -106,6 +106,7 @@ def load():
     L.adfb_ank_mffd_apply.argtypes = [vp, vp, C.c_longlong, C.c_double]
     L.adfb_ank_mffd_apply_device.argtypes = [vp, vp, C.c_longlong, C.c_double]
     L.adfb_ank_physicality_check.argtypes = [vp, vp, C.c_longlong, C.POINTER(C.c_double)]
+    L.adfb_gmres_solve.argtypes = [ci, vp, vp, C.c_longlong, ci, ci, C.c_double, C.c_double, vp, vp, C.POINTER(ci), C.POINTER(C.c_double)]
     L.adfb_launch_count.restype = C.c_longlong
     L.adfb_stream.restype = C.c_void_p
     _lib = L

@@ -21,6 +21,7 @@
 #include "smoother_kernels.cuh"
 #include "mg_kernels.cuh"
 #include "ank_kernels.cuh"
+#include "krylov_kernels.cuh"
 #include "halo_kernels.cuh"
 #include "dadi_kernels.cuh"
 #include "sa_kernels.cuh"
@@ -98,6 +99,9 @@ struct Context {
     double *ankT = nullptr, *ankPert = nullptr;
     size_t ankTN = 0, ankPertN = 0;
     double ankUnorm = 0.0;
+    // device GMRES workspace: (restart + 2) vectors + reduction scratch
+    double *kryV = nullptr, *kryRed = nullptr;
+    size_t kryVN = 0;
     int mgInitWr = 1;   // coarse-level smoother residual starts from wr (0 inside transferToCoarseGrid: from zero)
 };
 
@@ -287,7 +291,7 @@ int adfb_init(int device, const void* ncclUniqueId, int rank, int nranks) {
     CK(cudaSetDevice(device));
     if (!g.stream) CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     g.device = device; g.rank = rank; g.nranks = nranks;
-    if (!g.hRed) CK(cudaMallocHost((void**)&g.hRed, 64 * sizeof(double)));
+    if (!g.hRed) CK(cudaMallocHost((void**)&g.hRed, 256 * sizeof(double)));
     g.ready = true;
     g.err.clear();
     if (nranks > 1) {
@@ -1633,6 +1637,158 @@ int adfb_mg_cycle(int nSteps, const int* cycling, int smoother) {
     set_l2_window();
     std::vector<int> cyc(cycling, cycling + nSteps);
     return run_graphed(key, [&]() { return adfb_mg_cycle_body(nSteps, cyc.data(), smoother); });
+}
+
+// ---------------------------------------------------------------------------
+// Right-preconditioned restarted GMRES on the device for the matrix-free NK (op 0, adfb_mffd_set_base first) or ANK
+// (op 1, adfb_ank_mffd_set_base first) operator: what PETSc's KSPGMRES does for NK_KSP / ANK_KSP
+// (NKSolvers.F90:395-435, 2009-2037: GMRES, restart = subspace, right preconditioning, classical Gram-Schmidt without
+// refinement, zero initial guess), with the Krylov vectors resident on the GPU.  The preconditioner (ASM/ILU of
+// the assembled approximate Jacobian in the reference) stays outside: pc == NULL is the identity, otherwise
+// pc(ctx, inDev, outDev, n) applies M^-1 to a device vector.
+static int kry_apply_op(int op, const double* inDev, double* outDev, long long n) {
+    CK(cudaMemcpyAsync(g.nkA, inDev, n * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+    const int rc = op == 0 ? mffd_core(n, -1.0) : ank_mffd_core(n, -1.0);
+    if (rc == 1) return 1;
+    if (rc == 2) CK(cudaMemsetAsync(outDev, 0, n * sizeof(double), g.stream));
+    else CK(cudaMemcpyAsync(outDev, g.nkY, n * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+    return 0;
+}
+static int kry_dots(const double* V, long long ld, int nv, const double* w, long long n, double* hOut) {
+    KT_BEGIN(K_MFFD, g.stream);
+    k_multidot<<<ADFB_GMRES_PARTS, 256, 0, g.stream>>>(V, ld, nv, w, n, g.kryRed);
+    KT_END(K_MFFD, g.stream);
+    double* fin = g.kryRed + (size_t)ADFB_GMRES_PARTS * ADFB_GMRES_MAXV;
+    KT_BEGIN(K_MFFD, g.stream);
+    k_multidot_final<<<nv, 256, 0, g.stream>>>(g.kryRed, ADFB_GMRES_PARTS, nv, fin);
+    KT_END(K_MFFD, g.stream);
+    if (g.nranks > 1) {
+        const int rc = g.nccl.AllReduce(fin, fin, nv, kNcclDouble, kNcclSum, g.comm, g.stream);
+        if (rc != 0) return fail("ncclAllReduce: %s", g.nccl.GetErrorString(rc));
+    }
+    CK(cudaMemcpyAsync(g.hRed, fin, nv * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    for (int i = 0; i < nv; i++) hOut[i] = g.hRed[i];
+    return 0;
+}
+int adfb_gmres_solve(int op, const double* rhs, double* x, long long n, int restart, int maxIts, double rtol, double atol,
+                     AdfbPrecondFn pc, void* pcCtx, int* itsOut, double* resNormOut) {
+    NEED_INIT();
+    if (!rhs || !x) return fail("adfb_gmres_solve: null vector");
+    if (op != 0 && op != 1) return fail("adfb_gmres_solve: op must be 0 (NK product) or 1 (ANK product)");
+    if (restart < 1 || restart > ADFB_GMRES_MAXV - 2) return fail("adfb_gmres_solve: restart must be in 1..%d", ADFB_GMRES_MAXV - 2);
+    if (maxIts < 1) return fail("adfb_gmres_solve: maxIts must be >= 1");
+    long long need = 0;
+    if (op == 0) {
+        if (!g.nkHaveBase) return fail("adfb_gmres_solve: adfb_mffd_set_base has not been called");
+        need = adfb_state_size();
+    } else {
+        if (ank_ready("adfb_gmres_solve", n, &need)) return 1;
+        if (!g.ankHaveBase) return fail("adfb_gmres_solve: adfb_ank_mffd_set_base has not been called");
+    }
+    if (n != need) return fail("adfb_gmres_solve: vector length %lld != %lld", n, need);
+    const int m = restart;
+    const size_t nvec = (size_t)m + 4;   // V_0..V_m, w, z, xDev
+    if (g.kryVN < nvec * (size_t)n) {
+        if (g.kryV) cudaFree(g.kryV);
+        g.kryV = nullptr; g.kryVN = 0;
+        CK(cudaMalloc((void**)&g.kryV, nvec * (size_t)n * sizeof(double)));
+        g.kryVN = nvec * (size_t)n;
+    }
+    if (!g.kryRed) CK(cudaMalloc((void**)&g.kryRed, ((size_t)ADFB_GMRES_PARTS + 1) * ADFB_GMRES_MAXV * sizeof(double)));
+    if (!g.hRed) return fail("adfb_gmres_solve: reduction buffer missing");
+    double* V = g.kryV;
+    double* w = V + (size_t)(m + 1) * n;
+    double* z = w + n;
+    double* xd = z + n;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    CK(cudaMemsetAsync(xd, 0, n * sizeof(double), g.stream));
+    // r0 = b (zero initial guess, like the reference's KSPs)
+    CK(cudaMemcpyAsync(w, rhs, n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    double bb = 0.0;
+    if (kry_dots(w, n, 1, w, n, &bb)) return 1;
+    const double bnorm = sqrt(bb);
+    double rnorm = bnorm;
+    const double target = fmax(rtol * bnorm, atol);
+    int its = 0;
+    std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), gg(m + 1), hcol(m + 2);
+    bool first = true;
+    while (its < maxIts && rnorm > target) {
+        if (!first) {   // restart: r = b - A M^-1 ... with right preconditioning x already holds M^-1 (V y): r = b - A x
+            if (kry_apply_op(op, xd, w, n)) return 1;
+            CK(cudaMemcpyAsync(z, rhs, n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+            GmresCoef c1 = {}; c1.c[0] = 1.0;
+            k_axpy_many<<<nb, 256, 0, g.stream>>>(z, n, 1, c1, -1.0, w, n);   // w = -w + b
+            if (kry_dots(w, n, 1, w, n, &bb)) return 1;
+            rnorm = sqrt(bb);
+            if (rnorm <= target) break;
+        }
+        first = false;
+        k_scale_to<<<nb, 256, 0, g.stream>>>(w, 1.0 / rnorm, V, n);
+        std::fill(gg.begin(), gg.end(), 0.0);
+        gg[0] = rnorm;
+        int j = 0;
+        for (; j < m && its < maxIts; j++) {
+            const double* vj = V + (size_t)j * n;
+            const double* zin = vj;
+            if (pc) {
+                CK(cudaStreamSynchronize(g.stream));
+                if (pc(pcCtx, vj, z, n)) return fail("adfb_gmres_solve: the preconditioner callback failed");
+                zin = z;
+            }
+            if (kry_apply_op(op, zin, w, n)) return 1;
+            // classical Gram-Schmidt: all projections from the unmodified w, then one update
+            if (kry_dots(V, n, j + 1, w, n, hcol.data())) return 1;
+            GmresCoef cf = {};
+            for (int i = 0; i <= j; i++) cf.c[i] = -hcol[i];
+            k_axpy_many<<<nb, 256, 0, g.stream>>>(V, n, j + 1, cf, 1.0, w, n);
+            double ww = 0.0;
+            if (kry_dots(w, n, 1, w, n, &ww)) return 1;
+            hcol[j + 1] = sqrt(ww);
+            if (hcol[j + 1] > 0.0) k_scale_to<<<nb, 256, 0, g.stream>>>(w, 1.0 / hcol[j + 1], V + (size_t)(j + 1) * n, n);
+            // Givens rotations on the new column
+            for (int i = 0; i < j; i++) {
+                const double t = cs[i] * hcol[i] + sn[i] * hcol[i + 1];
+                hcol[i + 1] = -sn[i] * hcol[i] + cs[i] * hcol[i + 1];
+                hcol[i] = t;
+            }
+            const double den = hypot(hcol[j], hcol[j + 1]);
+            cs[j] = den > 0.0 ? hcol[j] / den : 1.0;
+            sn[j] = den > 0.0 ? hcol[j + 1] / den : 0.0;
+            hcol[j] = den;
+            gg[j + 1] = -sn[j] * gg[j];
+            gg[j] = cs[j] * gg[j];
+            for (int i = 0; i <= j; i++) H[(size_t)i + (size_t)(m + 1) * j] = hcol[i];
+            its++;
+            rnorm = fabs(gg[j + 1]);
+            if (rnorm <= target || den == 0.0) { j++; break; }
+        }
+        // y = H^-1 g (upper triangular), x += M^-1 (V y)
+        const int k = j;
+        std::vector<double> y(k);
+        for (int i = k - 1; i >= 0; i--) {
+            double t = gg[i];
+            for (int l = i + 1; l < k; l++) t -= H[(size_t)i + (size_t)(m + 1) * l] * y[l];
+            y[i] = t / H[(size_t)i + (size_t)(m + 1) * i];
+        }
+        GmresCoef cy = {};
+        for (int i = 0; i < k; i++) cy.c[i] = y[i];
+        if (pc) {
+            k_axpy_many<<<nb, 256, 0, g.stream>>>(V, n, k, cy, 0.0, w, n);
+            CK(cudaStreamSynchronize(g.stream));
+            if (pc(pcCtx, w, z, n)) return fail("adfb_gmres_solve: the preconditioner callback failed");
+            GmresCoef c1 = {}; c1.c[0] = 1.0;
+            k_axpy_many<<<nb, 256, 0, g.stream>>>(z, n, 1, c1, 1.0, xd, n);
+        } else {
+            k_axpy_many<<<nb, 256, 0, g.stream>>>(V, n, k, cy, 1.0, xd, n);
+        }
+    }
+    CK(cudaMemcpyAsync(x, xd, n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaGetLastError());
+    if (itsOut) *itsOut = its;
+    if (resNormOut) *resNormOut = rnorm;
+    return 0;
 }
 
 int adfb_norms(double out[2]) {

@@ -168,6 +168,16 @@ class ADFLOW_B200:
     def ankMffdApplyDevice(self, a_ptr, y_ptr, n, h=-1.0):
         check(self.L.adfb_ank_mffd_apply_device(a_ptr, y_ptr, n, h), "adfb_ank_mffd_apply_device")
 
+    def gmresSolve(self, rhs, op="ANK", restart=30, max_its=60, rtol=1e-6, atol=1e-50):
+        """right-preconditioned restarted GMRES on the device (identity preconditioner) for the NK or ANK product;
+        returns (x, iterations, residual norm estimate)"""
+        b = np.ascontiguousarray(rhs, dtype=np.float64)
+        x = np.zeros_like(b)
+        its, rn = C.c_int(0), C.c_double(0.0)
+        check(self.L.adfb_gmres_solve({"NK": 0, "ANK": 1}[op], b.ctypes.data, x.ctypes.data, b.size, restart, max_its, rtol, atol,
+                                      None, None, C.byref(its), C.byref(rn)), "adfb_gmres_solve")
+        return x, its.value, rn.value
+
     def ankPhysicalityCheck(self, w_vec, delta_w, lambda_p=1.0):
         """returns (lambdaP, deltaW) -- deltaW with the clipped turbulence updates (coupled ANK)"""
         w = np.ascontiguousarray(w_vec, dtype=np.float64)

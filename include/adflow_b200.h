@@ -328,6 +328,16 @@ int adfb_ank_mffd_apply_device(const double* aDev, double* yDev, long long n, do
    limiting than stepFactor * stepMin are clipped in deltaW instead), MIN-reduced over the ranks */
 int adfb_ank_physicality_check(const double* wVec, double* deltaW, long long n, double* lambdaP);
 
+/* Device GMRES for the two matrix-free operators: what PETSc's KSPGMRES does for NK_KSP / ANK_KSP (NKSolvers.F90:395-435,
+   2009-2037: restart = subspace, right preconditioning, classical Gram-Schmidt without refinement, zero initial guess),
+   with the Krylov basis resident on the GPU.  op 0: the NK product (adfb_mffd_set_base first), op 1: the ANK product
+   (adfb_ank_time_step_mat + adfb_ank_mffd_set_base first).  pc == NULL: identity; otherwise pc(ctx, inDev, outDev, n) applies
+   the right preconditioner M^-1 to a DEVICE vector (the reference's ASM/ILU of the assembled approximate Jacobian stays
+   with PETSc).  rhs, x: host vectors; its / resNorm (||b - A x|| estimate) may be NULL. */
+typedef int (*AdfbPrecondFn)(void* ctx, const double* inDev, double* outDev, long long n);
+int adfb_gmres_solve(int op, const double* rhs, double* x, long long n, int restart, int maxIts, double rtol, double atol,
+                     AdfbPrecondFn pc, void* pcCtx, int* its, double* resNorm);
+
 /* ---- multigrid (src/solver/multiGrid.F90) ------------------------------------------------------------------
    Grid levels: blocks created with level = 1 (finest) .. n; geometry, BCs and the communication pattern are set
    per block / per level like on the finest level (coarse levels exchange the first halos only: pass the 1st-halo
