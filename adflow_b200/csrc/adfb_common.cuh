@@ -61,6 +61,7 @@ struct BlockDev {
     // eddy viscosity, first-order dissipation: the currentLevel > groundLevel branches of the reference)
     double *wr, *w1, *p1;
     int coarse;
+    const void* bcList;   // device-resident BcList (smoother_kernels.cuh) of the block's subfaces, or null
 };
 
 // single translation unit (adflow_b200.cu includes every *_kernels.cuh)

@@ -505,6 +505,16 @@ int adfb_block_set_bc(int blk, int nSub, const AdfbSubface* subfaces) {
         }
         b->subfaces.push_back(sf);
     }
+    // device-resident list of the subfaces for the two-launch BC path (k_bc_bulk / k_bc_frame)
+    b->dev.bcList = nullptr;
+    BcList L;
+    if (make_bc_list(b->d, b->subfaces, &L)) {
+        void* q = nullptr;
+        CK(cudaMalloc(&q, sizeof(BcList)));
+        b->bcAllocs.push_back(q);
+        CK(cudaMemcpy(q, &L, sizeof(BcList), cudaMemcpyHostToDevice));
+        b->dev.bcList = q;
+    }
     return 0;
 }
 
@@ -898,9 +908,8 @@ static int residual_body(int level, unsigned flags) {
         if (!(flags & ADFB_RES_SKIP_PREAMBLE)) {
             // blocketteRes :213-226: p, rlv, rev on owned cells, then turbulence and flow BCs
             if (launch_state_prep(b.d, b.dev, g.prm, false, (flags & ADFB_RES_FLOW) != 0, g.stream)) return fail("state prep launch failed");
-            if (g.prm.equations == ADFB_RANS && (flags & ADFB_RES_TURB))
-                if (launch_bc_turb(b.d, b.dev, b.subfaces, 1, g.stream)) return fail("turbulence BC launch failed");
-            if (launch_bc_flow(b.d, b.dev, b.subfaces, 1, g.stream)) return fail("flow BC launch failed");
+            if (launch_bc_all(b.d, b.dev, b.subfaces, 1, g.prm.equations == ADFB_RANS && (flags & ADFB_RES_TURB), g.stream))
+                return fail("BC launch failed");
         }
     }
     if (!(flags & ADFB_RES_SKIP_PREAMBLE)) {
@@ -1080,9 +1089,7 @@ int adfb_apply_bcs(int level, int secondHalo, int withTurb) {
     if (!g.havePrm) return fail("adfb_apply_bcs: adfb_set_params has not been called");
     for (Block& b : g.blocks) {
         if (!b.alive || b.level != level) continue;
-        if (withTurb && g.prm.equations == ADFB_RANS)
-            if (launch_bc_turb(b.d, b.dev, b.subfaces, secondHalo, g.stream)) return fail("turbulence BC launch failed");
-        if (launch_bc_flow(b.d, b.dev, b.subfaces, secondHalo, g.stream)) return fail("flow BC launch failed");
+        if (launch_bc_all(b.d, b.dev, b.subfaces, secondHalo, withTurb && g.prm.equations == ADFB_RANS, g.stream)) return fail("BC launch failed");
     }
     return 0;
 }
@@ -1647,6 +1654,7 @@ int adfb_mg_cycle(int nSteps, const int* cycling, int smoother) {
 // the assembled approximate Jacobian in the reference) stays outside: pc == NULL is the identity, otherwise
 // pc(ctx, inDev, outDev, n) applies M^-1 to a device vector.
 static int kry_apply_op(int op, const double* inDev, double* outDev, long long n) {
+    if (op == 2) return ank_vec_kernel(inDev, nullptr, outDev, nullptr, 1.0, 4);   // y = timeStepMat x (linear)
     CK(cudaMemcpyAsync(g.nkA, inDev, n * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
     const int rc = op == 0 ? mffd_core(n, -1.0) : ank_mffd_core(n, -1.0);
     if (rc == 1) return 1;
@@ -1675,7 +1683,7 @@ int adfb_gmres_solve(int op, const double* rhs, double* x, long long n, int rest
                      AdfbPrecondFn pc, void* pcCtx, int* itsOut, double* resNormOut) {
     NEED_INIT();
     if (!rhs || !x) return fail("adfb_gmres_solve: null vector");
-    if (op != 0 && op != 1) return fail("adfb_gmres_solve: op must be 0 (NK product) or 1 (ANK product)");
+    if (op < 0 || op > 2) return fail("adfb_gmres_solve: op must be 0 (NK product), 1 (ANK product) or 2 (time-step matrix)");
     if (restart < 1 || restart > ADFB_GMRES_MAXV - 2) return fail("adfb_gmres_solve: restart must be in 1..%d", ADFB_GMRES_MAXV - 2);
     if (maxIts < 1) return fail("adfb_gmres_solve: maxIts must be >= 1");
     long long need = 0;
@@ -1684,7 +1692,7 @@ int adfb_gmres_solve(int op, const double* rhs, double* x, long long n, int rest
         need = adfb_state_size();
     } else {
         if (ank_ready("adfb_gmres_solve", n, &need)) return 1;
-        if (!g.ankHaveBase) return fail("adfb_gmres_solve: adfb_ank_mffd_set_base has not been called");
+        if (op == 1 && !g.ankHaveBase) return fail("adfb_gmres_solve: adfb_ank_mffd_set_base has not been called");
     }
     if (n != need) return fail("adfb_gmres_solve: vector length %lld != %lld", n, need);
     const int m = restart;

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(64) k_ank_tsblock(Dims d, BlockDev b, AdfbAnkP
 //  mode 1: perturbed setWANK             w(1:ns) <- base + h*vec;  pert <- base + h*vec (kept for the time-step term)
 //  mode 2: F = setRVec(ANK) + T*in       out <- dw/volRef (* turbResScale on the turbulence row) + sum_c T(l,c)*in(c)
 //  mode 3: (F - base) / h
+//  mode 4: out <- T*in only (the block-diagonal time-step matrix as a linear operator)
 __global__ void __launch_bounds__(256) k_ankvec(Dims d, BlockDev b, int ns, const double* __restrict__ vec, const double* __restrict__ base,
                                                 double* __restrict__ out, double* __restrict__ pert, const double* __restrict__ T, double h,
                                                 int mode) {
@@ -155,12 +156,13 @@ __global__ void __launch_bounds__(256) k_ankvec(Dims d, BlockDev b, int ns, cons
     const double ovv = 1.0 / b.volRef[c];
     double r = b.dw[l * d.N + c] * ovv;
     if (l >= 5) r = b.dw[l * d.N + c] * ovv * c_prm.turbResScale;
+    if (mode == 4) r = 0.0;
     const double* Tc = T + cell * (ns * ns);
     const double* in = vec + cell * ns;
     double a = 0.0;
     for (int m = 0; m < ns; m++) a += Tc[l + ns * m] * in[m];
     r = r + a;
-    out[q] = mode == 2 ? r : (r - base[q]) / h;
+    out[q] = (mode == 2 || mode == 4) ? r : (r - base[q]) / h;
 }
 
 // one thread per cell; part[blockIdx.x] = min over the block; deltaW clipped in place

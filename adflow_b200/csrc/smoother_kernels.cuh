@@ -64,13 +64,7 @@ __device__ __forceinline__ void bc_extrap2(const BlockDev& b, long long N, long 
     bc_etot(b, N, c0);
 }
 
-__global__ void __launch_bounds__(128) k_bc_turb(Dims d, BlockDev b, FaceDev f, int secondHalo) {
-    // launched with programmatic stream serialization: the launch overlaps the tail of the previous
-    // kernel, the data dependency is honoured here
-    cudaGridDependencySynchronize();
-    const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
-    const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
-    if (ia > f.icEnd || jb > f.jcEnd) return;
+__device__ __forceinline__ void bc_turb_cell(const Dims& d, const BlockDev& b, const FaceDev& f, int ia, int jb, int secondHalo) {
     const long long N = d.N;
     const long long q = ia * f.sa + jb * f.sb;
     const long long c0 = f.off[0] + q, c1 = f.off[1] + q, c2 = f.off[2] + q;
@@ -97,11 +91,7 @@ __global__ void __launch_bounds__(128) k_bc_turb(Dims d, BlockDev b, FaceDev f, 
 }
 
 // phase: 1 = symmetry first halo, 2 = symmetry second halo, 0 = everything else
-__global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, int secondHalo, int phase) {
-    cudaGridDependencySynchronize();
-    const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
-    const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
-    if (ia > f.icEnd || jb > f.jcEnd) return;
+__device__ __noinline__ void bc_flow_cell(const Dims& d, const BlockDev& b, const FaceDev& f, int ia, int jb, int secondHalo, int phase) {
     const long long N = d.N;
     const long long q = ia * f.sa + jb * f.sb;
     const long long c0 = f.off[0] + q, c1 = f.off[1] + q, c2 = f.off[2] + q, c3 = f.off[3] + q;
@@ -350,6 +340,122 @@ __global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, 
     }
 }
 
+// one launch per subface and phase (general path: more than ADFB_BC_MAXSUB subfaces on a block)
+__global__ void __launch_bounds__(128) k_bc_turb(Dims d, BlockDev b, FaceDev f, int secondHalo) {
+    // launched with programmatic stream serialization: the launch overlaps the tail of the previous
+    // kernel, the data dependency is honoured here
+    cudaGridDependencySynchronize();
+    const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
+    const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
+    if (ia > f.icEnd || jb > f.jcEnd) return;
+    bc_turb_cell(d, b, f, ia, jb, secondHalo);
+}
+__global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, int secondHalo, int phase) {
+    cudaGridDependencySynchronize();
+    const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
+    const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
+    if (ia > f.icEnd || jb > f.jcEnd) return;
+    bc_flow_cell(d, b, f, ia, jb, secondHalo, phase);
+}
+
+// ---------------------------------------------------------------------------
+// All BCs of a block in TWO launches.  The order in which applyAllBC_block / applyAllTurbBCThisBlock visit the
+// subfaces only matters where subfaces share halo cells: the frame of every subface (in-plane index outside the owned
+// range 2:l, i.e. the edge and corner halos).  Face cells with owned in-plane indices read owned cells and write halo
+// cells no other subface touches, so
+//   k_bc_bulk  : those cells of ALL subfaces at once (turbulence BC, then the flow BC incl. both symmetry phases), and
+//   k_bc_frame : the frames, one CTA walking the reference's ordered list of (subface, phase) items with a barrier
+//                between items (a frame has 2(na+nb) cells).
+// A frame cell may read a bulk halo cell of a subface that comes LATER in the reference's order (there: the old value);
+// every such cell is written again by that later subface's own frame item, which reads the earlier subface's bulk
+// cells -- already updated in the reference as well -- so the final halo values are the reference's.
+#define ADFB_BC_MAXSUB 12
+struct BcList {
+    int n;
+    int la[ADFB_BC_MAXSUB], lb[ADFB_BC_MAXSUB];   // owned upper index of the two in-plane directions (il/jl/kl)
+    FaceDev f[ADFB_BC_MAXSUB];
+};
+
+__device__ __forceinline__ void bc_all_cell(const Dims& d, const BlockDev& b, const FaceDev& f, int ia, int jb, int secondHalo,
+                                            int withTurb, int withFlow) {
+    if (withTurb) bc_turb_cell(d, b, f, ia, jb, secondHalo);
+    if (!withFlow) return;
+    if (f.bcType == ADFB_BC_SYMM || f.bcType == ADFB_BC_SYMMPOLAR) {
+        bc_flow_cell(d, b, f, ia, jb, secondHalo, 1);
+        if (secondHalo) bc_flow_cell(d, b, f, ia, jb, secondHalo, 2);
+    } else {
+        bc_flow_cell(d, b, f, ia, jb, secondHalo, 0);
+    }
+}
+__global__ void __launch_bounds__(128) k_bc_bulk(Dims d, BlockDev b, const BcList* __restrict__ Lp, int secondHalo, int withTurb, int withFlow) {
+    cudaGridDependencySynchronize();
+    const BcList& L = *Lp;
+    const int s = blockIdx.z;
+    const FaceDev& f = L.f[s];
+    const int a0 = f.icBeg > 2 ? f.icBeg : 2, a1 = f.icEnd < L.la[s] ? f.icEnd : L.la[s];
+    const int b0 = f.jcBeg > 2 ? f.jcBeg : 2, b1 = f.jcEnd < L.lb[s] ? f.jcEnd : L.lb[s];
+    const int ia = blockIdx.x * blockDim.x + threadIdx.x + a0;
+    const int jb = blockIdx.y * blockDim.y + threadIdx.y + b0;
+    if (ia > a1 || jb > b1) return;
+    bc_all_cell(d, b, f, ia, jb, secondHalo, withTurb, withFlow);
+}
+// the q-th frame cell of subface range [ic0..ic1] x [jc0..jc1] around the owned box [a0..a1] x [b0..b1]
+__device__ __forceinline__ bool frame_cell(int q, int ic0, int ic1, int jc0, int jc1, int a0, int a1, int b0, int b1, int* ia, int* jb) {
+    const int na = ic1 - ic0 + 1;
+    const int rowsLo = (b0 - jc0) > 0 ? (b0 - jc0) : 0, rowsHi = (jc1 - b1) > 0 ? (jc1 - b1) : 0;
+    int n = rowsLo * na;
+    if (q < n) { *ia = ic0 + q % na; *jb = jc0 + q / na; return true; }
+    q -= n;
+    n = rowsHi * na;
+    if (q < n) { *ia = ic0 + q % na; *jb = b1 + 1 + q / na; return true; }
+    q -= n;
+    const int colsLo = (a0 - ic0) > 0 ? (a0 - ic0) : 0, colsHi = (ic1 - a1) > 0 ? (ic1 - a1) : 0;
+    const int nbMid = (b1 >= b0) ? (b1 - b0 + 1) : 0, nc = colsLo + colsHi;
+    if (nc == 0 || q >= nc * nbMid) return false;
+    const int col = q % nc;
+    *jb = b0 + q / nc;
+    *ia = col < colsLo ? ic0 + col : a1 + 1 + (col - colsLo);
+    return true;
+}
+__global__ void __launch_bounds__(256) k_bc_frame(Dims d, BlockDev b, const BcList* __restrict__ Lp, int secondHalo, int withTurb, int withFlow) {
+    cudaGridDependencySynchronize();
+    const BcList& L = *Lp;
+    // ordered items: (subface, kind) with kind 3 = turbulence BC, else the flow phase
+    __shared__ short itemS[4 * ADFB_BC_MAXSUB + 4], itemK[4 * ADFB_BC_MAXSUB + 4];
+    __shared__ int nItems;
+    if (threadIdx.x == 0) {
+        int n = 0;
+        if (withTurb) for (int s = 0; s < L.n; s++) { itemS[n] = (short)s; itemK[n++] = 3; }
+        if (withFlow) {
+            for (int s = 0; s < L.n; s++) if (L.f[s].bcType == ADFB_BC_SYMM) { itemS[n] = (short)s; itemK[n++] = 1; }
+            if (secondHalo) for (int s = 0; s < L.n; s++) if (L.f[s].bcType == ADFB_BC_SYMM) { itemS[n] = (short)s; itemK[n++] = 2; }
+            for (int s = 0; s < L.n; s++) if (L.f[s].bcType == ADFB_BC_SYMMPOLAR) { itemS[n] = (short)s; itemK[n++] = 1; }
+            if (secondHalo) for (int s = 0; s < L.n; s++) if (L.f[s].bcType == ADFB_BC_SYMMPOLAR) { itemS[n] = (short)s; itemK[n++] = 2; }
+            const int order[8][2] = {{ADFB_BC_NSWALL_ADIABATIC, -1}, {ADFB_BC_NSWALL_ISOTHERMAL, -1}, {ADFB_BC_FARFIELD, -1},
+                                     {ADFB_BC_SUBSONIC_OUTFLOW, -1}, {ADFB_BC_SUBSONIC_INFLOW, -1}, {ADFB_BC_EXTRAP, ADFB_BC_SUPERSONIC_OUTFLOW},
+                                     {ADFB_BC_EULERWALL, -1}, {ADFB_BC_SUPERSONIC_INFLOW, -1}};
+            for (int g = 0; g < 8; g++)
+                for (int s = 0; s < L.n; s++)
+                    if (L.f[s].bcType == order[g][0] || L.f[s].bcType == order[g][1]) { itemS[n] = (short)s; itemK[n++] = 0; }
+        }
+        nItems = n;
+    }
+    __syncthreads();
+    for (int it = 0; it < nItems; it++) {
+        const int s = itemS[it], kind = itemK[it];
+        const FaceDev& f = L.f[s];
+        const int a0 = f.icBeg > 2 ? f.icBeg : 2, a1 = f.icEnd < L.la[s] ? f.icEnd : L.la[s];
+        const int b0 = f.jcBeg > 2 ? f.jcBeg : 2, b1 = f.jcEnd < L.lb[s] ? f.jcEnd : L.lb[s];
+        for (int q = threadIdx.x;; q += blockDim.x) {
+            int ia, jb;
+            if (!frame_cell(q, f.icBeg, f.icEnd, f.jcBeg, f.jcEnd, a0, a1, b0, b1, &ia, &jb)) break;
+            if (kind == 3) bc_turb_cell(d, b, f, ia, jb, secondHalo);
+            else bc_flow_cell(d, b, f, ia, jb, secondHalo, kind);
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------
 // executeRkStage part 1: dw *= cfl*etaRK(stage)*dtl, smoothers.F90:196-218
 __global__ void __launch_bounds__(256) k_rk_scale(Dims d, BlockDev b, double tmp) {
@@ -579,7 +685,52 @@ __global__ void __launch_bounds__(256) k_wall_forces(Dims d, BlockDev b, FaceDev
 
 }  // namespace
 
+static bool bc_two_launch() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ADFB_BC_FUSED"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+// all BCs of a block in two launches (k_bc_bulk + k_bc_frame); returns -1 when the general path must be used
+static int launch_bc_fused(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, int secondHalo, int withTurb, int withFlow,
+                           cudaStream_t s) {
+    if (!bc_two_launch() || subs.empty() || (int)subs.size() > ADFB_BC_MAXSUB || !b.bcList) return -1;
+    int ma = 1, mb = 1;
+    for (const AdfbSubface& sf : subs) {
+        const int la = (sf.faceId == ADFB_IMIN || sf.faceId == ADFB_IMAX) ? d.jl : d.il;
+        const int lb = (sf.faceId == ADFB_KMIN || sf.faceId == ADFB_KMAX) ? d.jl : d.kl;
+        if (la - 1 > ma) ma = la - 1;
+        if (lb - 1 > mb) mb = lb - 1;
+    }
+    dim3 tb(32, 4);
+    dim3 g((ma + 31) / 32, (mb + 3) / 4, (unsigned)subs.size());
+    const BcList* L = (const BcList*)b.bcList;
+    KT_BEGIN(K_BC, s);
+    launch_pdl(k_bc_bulk, g, tb, s, d, b, L, secondHalo, withTurb, withFlow);
+    KT_END(K_BC, s);
+    KT_BEGIN(K_BC, s);
+    launch_pdl(k_bc_frame, dim3(1), dim3(256), s, d, b, L, secondHalo, withTurb, withFlow);
+    KT_END(K_BC, s);
+    return (int)cudaGetLastError();
+}
+// host image of the device-resident subface list of a block (uploaded by adfb_block_set_bc)
+static bool make_bc_list(const Dims& d, const std::vector<AdfbSubface>& subs, BcList* L) {
+    if (subs.empty() || (int)subs.size() > ADFB_BC_MAXSUB) return false;
+    memset(L, 0, sizeof(BcList));
+    L->n = (int)subs.size();
+    for (int q = 0; q < L->n; q++) {
+        L->f[q] = make_face(d, subs[q]);
+        const int face = subs[q].faceId;
+        L->la[q] = (face == ADFB_IMIN || face == ADFB_IMAX) ? d.jl : d.il;
+        L->lb[q] = (face == ADFB_KMIN || face == ADFB_KMAX) ? d.jl : d.kl;
+    }
+    return true;
+}
+
 static int launch_bc_turb(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, int secondHalo, cudaStream_t s) {
+    {
+        const int rc = launch_bc_fused(d, b, subs, secondHalo, 1, 0, s);
+        if (rc >= 0) return rc;
+    }
     for (const AdfbSubface& sf : subs) {
         FaceDev f = make_face(d, sf);
         dim3 tb(32, 4);
@@ -602,6 +753,10 @@ static void launch_bc_one(const Dims& d, const BlockDev& b, const AdfbSubface& s
 
 // applyAllBC_block order, src/solver/BCRoutines.F90:81-216
 static int launch_bc_flow(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, int secondHalo, cudaStream_t s) {
+    {
+        const int rc = launch_bc_fused(d, b, subs, secondHalo, 0, 1, s);
+        if (rc >= 0) return rc;
+    }
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SYMM) launch_bc_one(d, b, sf, secondHalo, 1, s);
     if (secondHalo)
         for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SYMM) launch_bc_one(d, b, sf, secondHalo, 2, s);
@@ -618,6 +773,14 @@ static int launch_bc_flow(const Dims& d, const BlockDev& b, const std::vector<Ad
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_EULERWALL) launch_bc_one(d, b, sf, secondHalo, 0, s);
     for (const AdfbSubface& sf : subs) if (sf.bcType == ADFB_BC_SUPERSONIC_INFLOW) launch_bc_one(d, b, sf, secondHalo, 0, s);
     return (int)cudaGetLastError();
+}
+
+// turbulence BCs of all subfaces, then the flow BCs (blocketteRes :213-226, applyAllTurbBC + applyAllBC)
+static int launch_bc_all(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, int secondHalo, int withTurb, cudaStream_t s) {
+    const int rc = launch_bc_fused(d, b, subs, secondHalo, withTurb, 1, s);
+    if (rc >= 0) return rc;
+    if (withTurb && launch_bc_turb(d, b, subs, secondHalo, s)) return 1;
+    return launch_bc_flow(d, b, subs, secondHalo, s);
 }
 
 static int launch_residual_averaging(const Dims& d, const BlockDev& b, const AdfbParams& prm, cudaStream_t s) {

@@ -174,7 +174,7 @@ class ADFLOW_B200:
         b = np.ascontiguousarray(rhs, dtype=np.float64)
         x = np.zeros_like(b)
         its, rn = C.c_int(0), C.c_double(0.0)
-        check(self.L.adfb_gmres_solve({"NK": 0, "ANK": 1}[op], b.ctypes.data, x.ctypes.data, b.size, restart, max_its, rtol, atol,
+        check(self.L.adfb_gmres_solve({"NK": 0, "ANK": 1, "TSMAT": 2}[op], b.ctypes.data, x.ctypes.data, b.size, restart, max_its, rtol, atol,
                                       None, None, C.byref(its), C.byref(rn)), "adfb_gmres_solve")
         return x, its.value, rn.value
 

@@ -331,7 +331,8 @@ int adfb_ank_physicality_check(const double* wVec, double* deltaW, long long n, 
 /* Device GMRES for the two matrix-free operators: what PETSc's KSPGMRES does for NK_KSP / ANK_KSP (NKSolvers.F90:395-435,
    2009-2037: restart = subspace, right preconditioning, classical Gram-Schmidt without refinement, zero initial guess),
    with the Krylov basis resident on the GPU.  op 0: the NK product (adfb_mffd_set_base first), op 1: the ANK product
-   (adfb_ank_time_step_mat + adfb_ank_mffd_set_base first).  pc == NULL: identity; otherwise pc(ctx, inDev, outDev, n) applies
+   (adfb_ank_time_step_mat + adfb_ank_mffd_set_base first), op 2: the block-diagonal time-step matrix alone (a linear
+   operator; used to verify the solver).  pc == NULL: identity; otherwise pc(ctx, inDev, outDev, n) applies
    the right preconditioner M^-1 to a DEVICE vector (the reference's ASM/ILU of the assembled approximate Jacobian stays
    with PETSc).  rhs, x: host vectors; its / resNorm (||b - A x|| estimate) may be NULL. */
 typedef int (*AdfbPrecondFn)(void* ctx, const double* inDev, double* outDev, long long n);
