@@ -91,7 +91,7 @@ __device__ __forceinline__ void bc_turb_cell(const Dims& d, const BlockDev& b, c
 }
 
 // phase: 1 = symmetry first halo, 2 = symmetry second halo, 0 = everything else
-__device__ __noinline__ void bc_flow_cell(const Dims& d, const BlockDev& b, const FaceDev& f, int ia, int jb, int secondHalo, int phase) {
+__device__ __forceinline__ void bc_flow_cell(const Dims& d, const BlockDev& b, const FaceDev& f, int ia, int jb, int secondHalo, int phase) {
     const long long N = d.N;
     const long long q = ia * f.sa + jb * f.sb;
     const long long c0 = f.off[0] + q, c1 = f.off[1] + q, c2 = f.off[2] + q, c3 = f.off[3] + q;
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(256) k_wall_forces(Dims d, BlockDev b, FaceDev
 
 static bool bc_two_launch() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("ADFB_BC_FUSED"); v = e ? atoi(e) : 1; }
+    if (v < 0) { const char* e = getenv("ADFB_BC_FUSED"); v = e ? atoi(e) : 0; }   // measured slower: off by default
     return v != 0;
 }
 // all BCs of a block in two launches (k_bc_bulk + k_bc_frame); returns -1 when the general path must be used

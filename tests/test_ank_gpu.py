@@ -183,7 +183,7 @@ def test_device_gmres_on_a_linear_operator(cuda_lib, kind, coupled):
     calls = []
 
     def pc(ctx, in_ptr, out_ptr, n):
-        v = torch.as_tensor(DevVec(in_ptr, n, True), device="cuda").reshape(-1, ns)
+        v = torch.as_tensor(DevVec(in_ptr, n, False), device="cuda").reshape(-1, ns)   # torch rejects read-only views
         out = torch.as_tensor(DevVec(out_ptr, n, False), device="cuda").reshape(-1, ns)
         out.copy_(torch.einsum("qlm,qm->ql", Tinv, v))
         torch.cuda.synchronize()
@@ -204,7 +204,8 @@ def test_device_gmres_on_a_linear_operator(cuda_lib, kind, coupled):
         itp, rnp = C.c_int(0), C.c_double(0.0)
         rc = s.L.adfb_gmres_solve(2, b.ctypes.data, xp.ctypes.data, b.size, restart, max_its, 1e-10, 1e-50, C.cast(pc_c, C.c_void_p), None,
                                   C.byref(itp), C.byref(rnp))
-        assert rc == 0
+        from adflow_b200._lib import check
+        check(rc, "adfb_gmres_solve with a preconditioner callback")
     finally:
         s.close()
     xh, its_h = _host_gmres(apply, b, restart, max_its, rtol)
