@@ -41,8 +41,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C2 = (96, 72, 64)
-# DRAM traffic of one residual step on C2 measured by ncu (profiles/r01c_ncu_summary.md)
-NCU_TRAFFIC_BYTES = 570.4e6
+# DRAM traffic of one residual step on C2 measured by ncu (profiles/r01d_ncu_summary.md: sum over the six residual kernels)
+NCU_TRAFFIC_BYTES = 568.1e6
 BYTES_PER_CELL = 176.0  # RANS-SA residual, metrics from x, algorithmic
 METRIC = "Mcells/s RANS-SA residual"
 
@@ -460,7 +460,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES if tuple(shape) == tuple(C2) else None,
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the six residual kernels of "
-                                         "one step, ncu --set full capture profiles/r01c_ncu_summary.md (k_faces alone: 229 MB)",
+                                         "one step, ncu --set full capture profiles/r01d_ncu_summary.md (k_faces alone: 229 MB)",
                          "peak_source": peak_src,
                          "kernel": "whole residual step: all launches (state prep, BCs, halo pack/unpack, k_prep, k_nodal, "
                                    "k_resid) charged against 176 B/cell",
