@@ -66,6 +66,16 @@ struct BlockDev {
 
 // single translation unit (adflow_b200.cu includes every *_kernels.cuh)
 __constant__ AdfbParams c_prm;
+// Programmatic dependent launch: every PDL-launched kernel first waits for its predecessor (grid dependency sync: the
+// predecessor has completed and its writes are visible), then -- with ADFB_PDL_TRIGGER=1 -- signals at once that ITS
+// dependent may be launched, so that the dependent's blocks are scheduled while this kernel's last wave drains; the
+// dependent still waits at its own grid dependency sync before touching memory.
+__constant__ int c_pdlTrigger;
+#define ADFB_PDL_SYNC()                                                  \
+    do {                                                                 \
+        cudaGridDependencySynchronize();                                 \
+        if (c_pdlTrigger) cudaTriggerProgrammaticLaunchCompletion();     \
+    } while (0)
 
 #define ADFB_IDX(i, j, k) ((long long)(i) + d.sJ * (long long)(j) + d.sK * (long long)(k))
 

@@ -372,6 +372,11 @@ int adfb_set_params(const AdfbParams* prm) {
     g.prm = *prm;
     g.havePrm = true;
     CK(cudaMemcpyToSymbolAsync(c_prm, &g.prm, sizeof(AdfbParams), 0, cudaMemcpyHostToDevice, g.stream));
+    {
+        static int trig = -1;
+        if (trig < 0) { const char* e = getenv("ADFB_PDL_TRIGGER"); trig = e ? atoi(e) : 0; }
+        CK(cudaMemcpyToSymbolAsync(c_pdlTrigger, &trig, sizeof(int), 0, cudaMemcpyHostToDevice, g.stream));
+    }
     CK(cudaStreamSynchronize(g.stream));
     return 0;
 }

@@ -171,7 +171,7 @@ __device__ __forceinline__ void dadi_post(const BlockDev& b, int N, int c, doubl
 // 19..27 the tridiagonal rows per coefficient set (k_dadi_tri).
 template <int DIR>
 __global__ void __launch_bounds__(128) k_dadi_coef(Dims d, BlockDev b, int sd, double cfl) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(128) k_dadi_coef(Dims d, BlockDev b, int sd, d
 }
 
 __global__ void __launch_bounds__(128) k_dadi_post(Dims d, BlockDev b) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128) k_dadi_post(Dims d, BlockDev b) {
 // tridiagonal rows of the three coefficient sets from the cell coefficients of the cell and its two line
 // neighbours (residuals.F90:1374-1391): work slots 19+t (diagonal), 22+t (sub-), 25+t (super-diagonal)
 __global__ void __launch_bounds__(256) k_dadi_tri(Dims d, BlockDev b, int sd, int dirIdx) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) k_dadi_tri(Dims d, BlockDev b, int sd, in
 
 // one thread = one grid line (nl owned cells along sd) of one variable n = blockIdx.z
 __global__ void __launch_bounds__(64) k_dadi_thomas(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int q2 = blockIdx.y + 2;
     if (q1 > n1 + 1 || q2 > n2 + 1) return;

@@ -31,7 +31,7 @@ __device__ __forceinline__ double lam_visc(double p, double rho) {
 }
 
 __global__ void __launch_bounds__(128) k_mg_restrict(Dims d, BlockDev b, Dims df, BlockDev f, MgTables t) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -77,7 +77,7 @@ __device__ __forceinline__ void crh_copy(const BlockDev& b, long long N, long lo
 }
 // one CTA; group g copies are independent of each other, groups are ordered
 __global__ void __launch_bounds__(256) k_mg_corner_rows(Dims d, BlockDev b) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const long long N = d.N;
     const int t = threadIdx.x, nt = blockDim.x;
     auto mn = [](int a, int c) { return a < c ? a : c; };
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_mg_corner_rows(Dims d, BlockDev b) {
 // mode 0: w1 = w, p1 = p (1:ie);  mode 1: corrections w -= w1, w(irhoE) = p - p1 (1:ie);
 // mode 2: the w round trip of inviscidDissFluxScalarCoarse (1:ie)
 __global__ void __launch_bounds__(256) k_mg_cells1(Dims d, BlockDev b, int mode) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 1;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) k_mg_cells1(Dims d, BlockDev b, int mode)
 }
 
 __global__ void __launch_bounds__(256) k_mg_forcing(Dims d, BlockDev b, double fcoll) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) k_mg_forcing(Dims d, BlockDev b, double f
 }
 
 __global__ void __launch_bounds__(128) k_mg_corr_halos(Dims d, BlockDev b, FaceDev f, double fact) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
     const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
     if (ia > f.icEnd || jb > f.jcEnd) return;
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(128) k_mg_corr_halos(Dims d, BlockDev b, FaceD
 }
 
 __global__ void __launch_bounds__(128) k_mg_prolong(Dims d, BlockDev b, Dims dc, BlockDev cb, MgTables t, int nw) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;

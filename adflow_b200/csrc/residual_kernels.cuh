@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_geom(Dims d, BlockDev b) {
 // k_prep: entropy (inviscidDissFluxScalar, blockette.F90:3055-3089), speed of sound squared
 // (:5168-5203), spectral radii and local time step (timeStep, :1899-2148).
 __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, int doRad) {
-    cudaGridDependencySynchronize();  // launched with programmatic stream serialization (launch_pdl)
+    ADFB_PDL_SYNC();  // launched with programmatic stream serialization (launch_pdl)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = blockIdx.z * blockDim.z + threadIdx.z;
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
 // the reference's three scatter sweeps add, in this order:  -K(layer k) +K(layer k+1)
 // -J(layer j) +J(layer j+1) -I(layer i) +I(layer i+1), then scale by 1/(8 vol).
 __global__ void __launch_bounds__(NODAL_TPB, NODAL_MINB) k_nodal(Dims d, BlockDev b, int doGrad, int dissApprox) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 1;
@@ -589,7 +589,7 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
 // fd -> flux[dir*10 + 5 + l] (smoother path: fw persists between RK stages).
 template <bool VISCOUS, bool MERGED, int DISC, int APPROX, bool STOREWALL = false, int PART = 0>
 __global__ void __launch_bounds__(FACES_TPB, PART == 0 ? FACES_MINB : FACES_MINB_SPLIT) k_faces(Dims d, BlockDev b, double rFil, int doVisc, int doDiss) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 1;
@@ -787,7 +787,7 @@ __global__ void __launch_bounds__(SA_TPB, SA_MINB) k_sa(Dims d, BlockDev b) {
 // Order per variable: -Fi(c-1) +Fi(c) -Fj(c-sJ) +Fj(c) -Fk(c-sK) +Fk(c), like the reference's sweeps.
 template <bool MERGED>
 __global__ void __launch_bounds__(256) k_div(Dims d, BlockDev b, double rFil, int persistFw, int initWr) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;

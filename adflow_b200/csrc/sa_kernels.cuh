@@ -19,7 +19,7 @@
 namespace {
 
 __global__ void __launch_bounds__(128) k_sa_bmt(Dims d, BlockDev b, FaceDev f) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
     const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
     if (ia > f.icEnd || jb > f.jcEnd) return;
@@ -68,7 +68,7 @@ __device__ __forceinline__ void sa_diff_coef(const BlockDev& b, int N, int c, in
 }
 
 __global__ void __launch_bounds__(128, 4) k_sa_rhs(Dims d, BlockDev b, double factor) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(128, 4) k_sa_rhs(Dims d, BlockDev b, double fa
 //   k_sa_thomas (one thread per line): backward elimination m = l..2 and forward substitution
 //               (:979-998) reading only precomputed arrays; eliminated diagonal / rhs in slots 3, 4
 __global__ void __launch_bounds__(128) k_sa_coef(Dims d, BlockDev b, int axis, int sd) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(128) k_sa_coef(Dims d, BlockDev b, int axis, i
 }
 
 __global__ void __launch_bounds__(64) k_sa_thomas(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2, int multiplyByQQ) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int q2 = blockIdx.y + 2;
     if (q1 > n1 + 1 || q2 > n2 + 1) return;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(64) k_sa_thomas(Dims d, BlockDev b, int sd, in
 // the same sweep with every line spread over P lanes (tridiag_part.cuh); LS = 32 / P lines per warp
 template <int P, int M>
 __global__ void __launch_bounds__(32) k_sa_thomas_part(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2, int multiplyByQQ) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     typedef PartThomas<P, M> PT;
     const int lane = threadIdx.x, p = lane / PT::LS, lw = lane % PT::LS;
     int line = blockIdx.x * PT::LS + lw;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(32) k_sa_thomas_part(Dims d, BlockDev b, int s
 }
 
 __global__ void __launch_bounds__(256) k_sa_update(Dims d, BlockDev b) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;

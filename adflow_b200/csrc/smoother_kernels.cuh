@@ -344,14 +344,14 @@ __device__ __forceinline__ void bc_flow_cell(const Dims& d, const BlockDev& b, c
 __global__ void __launch_bounds__(128) k_bc_turb(Dims d, BlockDev b, FaceDev f, int secondHalo) {
     // launched with programmatic stream serialization: the launch overlaps the tail of the previous
     // kernel, the data dependency is honoured here
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
     const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
     if (ia > f.icEnd || jb > f.jcEnd) return;
     bc_turb_cell(d, b, f, ia, jb, secondHalo);
 }
 __global__ void __launch_bounds__(128) k_bc_flow(Dims d, BlockDev b, FaceDev f, int secondHalo, int phase) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
     const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
     if (ia > f.icEnd || jb > f.jcEnd) return;
@@ -388,7 +388,7 @@ __device__ __forceinline__ void bc_all_cell(const Dims& d, const BlockDev& b, co
     }
 }
 __global__ void __launch_bounds__(128) k_bc_bulk(Dims d, BlockDev b, const BcList* __restrict__ Lp, int secondHalo, int withTurb, int withFlow) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const BcList& L = *Lp;
     const int s = blockIdx.z;
     const FaceDev& f = L.f[s];
@@ -418,7 +418,7 @@ __device__ __forceinline__ bool frame_cell(int q, int ic0, int ic1, int jc0, int
     return true;
 }
 __global__ void __launch_bounds__(256) k_bc_frame(Dims d, BlockDev b, const BcList* __restrict__ Lp, int secondHalo, int withTurb, int withFlow) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const BcList& L = *Lp;
     // ordered items: (subface, kind) with kind 3 = turbulence BC, else the flow phase
     __shared__ short itemS[4 * ADFB_BC_MAXSUB + 4], itemK[4 * ADFB_BC_MAXSUB + 4];
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(256) k_bc_frame(Dims d, BlockDev b, const BcLi
 // ---------------------------------------------------------------------------
 // executeRkStage part 1: dw *= cfl*etaRK(stage)*dtl, smoothers.F90:196-218
 __global__ void __launch_bounds__(256) k_rk_scale(Dims d, BlockDev b, double tmp) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(256) k_rk_scale(Dims d, BlockDev b, double tmp
 // scaleDt != 0 folds part 1 in (used when no residual averaging runs in between).
 // fromCurrent != 0: the DADI update, which starts from the current w, p instead of wn, pn (smoothers.F90:614-640)
 __global__ void __launch_bounds__(256) k_rk_update(Dims d, BlockDev b, int scaleDt, double tmp, int nw, int fromCurrent) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -536,7 +536,7 @@ __device__ __forceinline__ double ra_rfl(const BlockDev& b, const Dims& d, long 
 // Workspace b.flux: slot 0 rfl (pressure switch), 1..3 epz of the i, j, k direction (both one pass per
 // call, one thread per cell), 4..8 the forward-swept residuals, 9..13 d(i) per variable.
 __global__ void __launch_bounds__(256) k_resavg_rfl(Dims d, BlockDev b) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(256) k_resavg_rfl(Dims d, BlockDev b) {
 }
 // epz(i) = 1/4 smoop max(r^2 - 1, 0) max(iblank, 0), r = rfl0 (rfl(i) + rfl(i+1)), for i < l; epz(l) = 0
 __global__ void __launch_bounds__(256) k_resavg_eps(Dims d, BlockDev b, double rfl0) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(256) k_resavg_eps(Dims d, BlockDev b, double r
 // d(i) = t(i) epz(i), forward sweep dw(i) = t(i) (dw(i) + epz(i-1) dw(i-1)), back substitution
 __global__ void __launch_bounds__(64) k_resavg_sweep(Dims d, BlockDev b, int dir, long long sd, int n, long long s1, int n1,
                                                      long long s2, int n2) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     const int q1 = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int q2 = blockIdx.y * blockDim.y + threadIdx.y + 2;
     if (q1 > n1 + 1 || q2 > n2 + 1) return;
@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(64) k_resavg_sweep(Dims d, BlockDev b, int dir
 // is run-to-run reproducible.  acc = Fp(3), Fv(3), Mp(3), Mv(3).
 __global__ void __launch_bounds__(256) k_wall_forces(Dims d, BlockDev b, FaceDev f, int dir, int isMin, int la, int lb, int viscWall,
                                                      double r0, double r1, double r2, double pRef, double* acc) {
-    cudaGridDependencySynchronize();
+    ADFB_PDL_SYNC();
     __shared__ double sh[12][256];
     const long long N = d.N;
     const double fact = isMin ? -1.0 : 1.0;

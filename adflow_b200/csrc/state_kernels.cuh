@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) k_metrics(Dims d, BlockDev b, double fact
 
 // p on [pLo,pHi] (owned, or 0:ib with halos), rlv/rev on [vLo,vHi] (owned, or 1:ie with halos)
 __global__ void __launch_bounds__(256) k_state_prep(Dims d, BlockDev b, int includeHalos, int nw, int etot) {
-    cudaGridDependencySynchronize();  // launched with programmatic stream serialization (launch_pdl)
+    ADFB_PDL_SYNC();  // launched with programmatic stream serialization (launch_pdl)
     const int lo = includeHalos ? 0 : 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x + lo;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + lo;

@@ -53,3 +53,15 @@ def test_fails_loudly_without_gpu():
     prm = make_params()
     assert L.adfb_set_params(C.byref(prm)) != 0  # not initialised -> error, never a CPU path
     assert L.adfb_residual(1, 8 | 16) != 0
+
+
+def test_integration_doc_binds_every_abi_symbol():
+    """INTEGRATION.md shows the ISO_C_BINDING interface a maintainer adds: it has to cover the whole C ABI"""
+    import os
+    import re
+
+    from adflow_b200._lib import ABI_SYMBOLS
+
+    doc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    bound = set(re.findall(r'bind\(c,\s*name="(\w+)"\)', doc))
+    assert sorted(set(ABI_SYMBOLS) - bound) == []
