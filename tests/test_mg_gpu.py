@@ -416,3 +416,34 @@ def test_two_gpu_v_cycle_matches_single_process_oracle(cuda_lib):
             assert np.abs(r).max() > 0
             assert rel_l2(a, r) < 1e-8, (b, l, rel_l2(a, r))
         assert rel_max(got[b][..., :5], hb.w[..., :5]) < 1e-10, b
+
+
+def test_multigrid_accelerates_convergence_like_the_oracle(cuda_lib):
+    """ten cycles, Euler: the density-residual history of the device follows the oracle's cycle by cycle, and the
+    3W cycle converges about twice as fast per cycle as the single-grid smoother (what multigrid is for)"""
+    opts = {"equationType": "Euler"}
+    hist = {}
+    for name, nlev in (("sg", 1), ("3w", 3)):
+        prm, levels = make_levels((16, 16, 8), opts, nlev)
+        dev_levels = [l.copy() for l in levels]
+        cyc = ADFLOW_B200.cycleStrategy(name)
+        prepare_fine(Oracle(levels[0], prm))
+        ref = [Oracle(levels[0], prm).norms()[0]]
+        for _ in range(10):
+            oracle_mg_cycle(prm, levels, cyc)
+            ref.append(Oracle(levels[0], prm).norms()[0])
+        s = device(prm, dev_levels)
+        try:
+            s.timeStep(False)
+            s.smootherResidual(0)
+            got = [s.getResNorms()[0]]
+            for _ in range(10):
+                s.mgCycle(cyc)
+                got.append(s.getResNorms()[0])
+        finally:
+            s.close()
+        ref, got = np.sqrt(ref), np.sqrt(got)
+        assert np.allclose(got, ref, rtol=1e-7, atol=0), (name, np.abs(got / ref - 1).max())
+        hist[name] = got
+    assert hist["3w"][-1] < 0.6 * hist["sg"][-1], (hist["3w"][-1], hist["sg"][-1])
+    assert hist["sg"][-1] < hist["sg"][0]
