@@ -229,11 +229,15 @@ int run_graphed(unsigned long long key, F body) {
         g.capturing = false;
         const long long nl = g_kt.launches - l0;
         cudaError_t e = cudaStreamEndCapture(g.stream, &graph);
-        if (rc != 0 || e != cudaSuccess || !graph) {
+        if (rc != 0) {   // the entry point itself failed (misuse): report it; graphs stay enabled for later calls
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
-            g.useGraphs = false;  // fall back to direct launches for the rest of the run
-            if (rc != 0) return rc;
+            return rc;
+        }
+        if (e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            g.useGraphs = false;  // capture is not possible here: direct launches for the rest of the run
             return body();
         }
         cudaGraphExec_t exec = nullptr;
