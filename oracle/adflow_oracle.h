@@ -16,7 +16,10 @@
  * this restatement on seeded blocks for: blocketteResCore and all its flux / SA /
  * time-step routines (exact and approximate variants, scalar/matrix/upwind), state
  * preparation, metrics and volumes, flow and turbulence BCs, residual averaging,
- * the RK stage, computeDwDADI + the DADI step, and the SA DD-ADI block solve.
+ * the RK stage, computeDwDADI + the DADI step, the SA DD-ADI block solve, the multigrid transfer operators with
+ * the coarse-level branches of residual / time step / smoothers / BCs (multiGrid.F90), and the ANK time-step block
+ * and physicality check (NKSolvers.F90, module ANKSolver).  tests/golden/reference_golden.json keeps outputs of the
+ * translated reference for use where oracle/_ref is absent.
  * STILL UNPINNED (no reference arithmetic to run): PETSc's matrix-free differencing
  * parameter h (adfb_mffd_*), and the halo-exchange index lists, which are built by
  * the reference's preprocessing from CGNS connectivity (checked instead against a
