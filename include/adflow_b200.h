@@ -162,16 +162,20 @@ typedef struct AdfbSubface {
    nranks == 1.  Replaces nothing in the reference (no device exists there);
    called after partitionAndReadGrid (adflow/pyADflow.py:236). */
 int adfb_init(int device, const void* ncclUniqueId, int rank, int nranks);
+/* releases every device resource; the counterpart of releaseMemoryPart1/2 (src/utils/utils.F90) at the end of a run */
 int adfb_finalize(void);
 /* rank 0 calls this and broadcasts the 128 bytes over its own transport (MPI_Bcast
    in the Fortran host, torch.distributed in the Python harness). */
 int adfb_get_unique_id(void* out128);
+/* message of the last failing call on this rank; the Fortran side hands it to terminate() (src/utils/utils.F90:501) */
 int adfb_last_error(char* buf, int n);
+/* number of visible CUDA devices (used to map local MPI ranks to GPUs; no counterpart in the reference) */
 int adfb_device_count(void);
 
 /* ---- data model (src/modules/block.F90:205-752 blockType) ----------------- */
 /* after allocMemFlovarPart2 (src/initFlow/initializeFlow.F90:686-722) */
 int adfb_block_create(int blk, int level, int nx, int ny, int nz, int nw, int rightHanded);
+/* deallocation of one flowDoms(nn, level, sps) entry (deallocateBlock, src/utils/utils.F90) */
 int adfb_block_destroy(int blk);
 /* after preprocessing / each mesh warp (updateGeometryInfo).  si/sj/sk may be NULL:
    they are then computed on the device from x with the blockette `metrics`
@@ -180,9 +184,10 @@ int adfb_block_set_geometry(int blk, const double* x, const double* si, const do
                             const double* sk, const double* vol, const double* volRef,
                             const double* d2Wall, const int8_t* porI, const int8_t* porJ,
                             const int8_t* porK, const int32_t* iblank);
-/* after updateBCDataAllLevels */
+/* after updateBCDataAllLevels (src/bcdata/BCData.F90): BCData(mm)%norm, rface, uSlip, TNS_Wall, ps, ptInlet ... of block.F90:52-156 */
 int adfb_block_set_bc(int blk, int nSub, const AdfbSubface* subfaces);
-/* whenever options / AeroProblem change (setOption, _setAeroProblemData) */
+/* whenever options / AeroProblem change (setOption, _setAeroProblemData in adflow/pyADflow.py; the module variables of
+   src/modules/inputParam.F90, flowVarRefState, paramTurb that referenceState, src/initFlow/initializeFlow.F90:10-182, fills) */
 int adfb_set_params(const AdfbParams* prm);
 
 /* ---- explicit sync points (NKSolvers.F90:1378-1485 getStates/setStates/getRes) */
@@ -208,6 +213,8 @@ int adfb_residual(int level, unsigned flags);
 /* Sum of (dw(irho)/vol)^2 and of all (dw/vol)^2 over owned cells of all local
    blocks, all-reduced (getCurrentResidual, NKSolvers.F90:335-370). out[0]=rho, out[1]=total */
 int adfb_norms(double out[2]);
+/* blocks until the library stream is idle (the reference is synchronous: needed only before timing or host reads
+   that bypass the download calls) */
 int adfb_synchronize(void);
 /* wallIntegrationFace / getForces (src/solver/surfaceIntegrations.F90:406-881, src/warping/getForces.F90):
    out = Fp(3), Fv(3), Mp(3), Mv(3) summed over the wall subfaces (viscous walls: pressure + viscous, Euler walls:
