@@ -323,6 +323,10 @@ int adfb_finalize(void) {
     g.dVec = nullptr; g.dVecN = 0;
     for (double** p : {&g.nkA, &g.nkU, &g.nkF0, &g.nkY}) { if (*p) cudaFree(*p); *p = nullptr; }
     g.nkN = 0; g.nkHaveBase = false;
+    // ANK / Krylov state belongs to the context as well: a later adfb_init starts from scratch
+    for (double** p : {&g.ankT, &g.ankPert, &g.kryV, &g.kryRed}) { if (*p) cudaFree(*p); *p = nullptr; }
+    g.ankTN = 0; g.ankPertN = 0; g.kryVN = 0;
+    g.haveAnk = false; g.ankHaveT = false; g.ankHaveBase = false;
     drop_graphs();
     for (auto* M : {&g.pats, &g.ovPats}) {
         for (auto& kv : *M) for (void* q : kv.second.allocs) cudaFree(q);
