@@ -7,6 +7,7 @@ reference's own tests rely on: free-stream preservation
 of the telescoping face-flux scatter (src/solver/fluxes.F90:103-104) and agreement
 of the independently written numpy metrics with the C restatement."""
 import numpy as np
+import pytest
 
 from adflow_b200 import make_params
 from adflow_b200 import synthetic as syn
@@ -107,3 +108,81 @@ def test_residual_is_finite_and_deterministic():
     Oracle(b, prm).residual_core(FLOW | TURB)
     assert np.isfinite(a.dw).all()
     assert np.array_equal(a.dw, b.dw)
+
+
+def _mg_levels(prm, fine, nlev):
+    levels = [fine]
+    for _ in range(nlev - 1):
+        levels.append(syn.make_coarse_block(levels[-1], prm))
+    return levels
+
+
+def test_multigrid_restriction_is_conservative_and_prolongation_reproduces_constants():
+    """transferToCoarseGrid: the restricted state is the volume-weighted mean (so volume integrals are kept exactly on
+    regular coarsening) and wr sums the fine residuals; transferToFineGrid: a constant correction is interpolated to
+    the same constant (the 27/9/3/1 weights sum to 64)"""
+    prm, fine = case(8, 6, 4, {"equationType": "Euler"})
+    coarse = syn.make_coarse_block(fine, prm)
+    of, oc = Oracle(fine, prm), Oracle(coarse, prm)
+    rng = np.random.default_rng(4)
+    fine.dw[...] = rng.standard_normal(fine.dw.shape)
+    oc.mg_restrict(of)
+    ow, owc = fine.d.owned(), coarse.d.owned()
+    for l in range(4):   # density and the primitive velocities: volume-weighted averages
+        fi = (fine.vol[ow] * fine.w[ow + (l,)]).sum()
+        cv = sum(fine.vol[ow][a::2, b::2, c::2] for a in (0, 1) for b in (0, 1) for c in (0, 1))
+        assert abs((cv * coarse.w[owc + (l,)]).sum() - fi) <= 1e-13 * abs(fi), l
+    for l in range(5):   # restricted residual = sum of the 8 fine residuals (weights 1 on regular coarsening)
+        assert abs(coarse.wr[owc + (l,)].sum() - fine.dw[ow + (l,)].sum()) <= 1e-12 * np.abs(fine.dw[ow + (l,)]).sum(), l
+    # constant correction
+    prm.mgBoundCorr = 1   # bcNeumann0: the boundary halos of the corrections copy the interior value
+    np.copyto(coarse.w1, coarse.w[..., :5]); np.copyto(coarse.p1, coarse.p)
+    delta = np.array([1e-3, 2e-3, -1e-3, 5e-4])
+    for l in range(4):
+        coarse.w[..., l] += delta[l]
+    coarse.p[...] += 7e-3
+    for s_ in coarse.subfaces:    # no mirroring: treat every face like a generic boundary
+        s_["bcType"] = 3
+    w0, p0 = fine.w.copy(), fine.p.copy()
+    of.mg_prolong(oc)
+    for l in range(4):
+        assert np.abs((fine.w[ow + (l,)] - w0[ow + (l,)]) - delta[l]).max() < 1e-15, l
+    assert np.abs((fine.p[ow] - p0[ow]) - 7e-3).max() < 1e-14
+
+
+@pytest.mark.parametrize("cycle,nlev", [("2v", 2), ("3w", 3)])
+def test_multigrid_cycle_leaves_a_converged_solution_converged(cycle, nlev):
+    """free stream on a warped mesh (far field all round): the fine residual is zero to round-off, so the residual
+    forcing term cancels the coarse residual and every level's update is round-off: the cycle must not disturb it"""
+    from adflow_b200.solver import ADFLOW_B200
+
+    prm = make_params({"equationType": "Euler", "nRKStages": 3, "resAveraging": "never"})
+    fine = syn.make_block(8, 8, 8, prm, physical_faces={f: 3 for f in range(1, 7)})
+    for l in range(fine.nw):
+        fine.w[..., l] = prm.wInf[l]
+    fine.p[...] = prm.pInf
+    levels = _mg_levels(prm, fine, nlev)
+    o = Oracle(fine, prm)
+    o.apply_flow_bc(True)
+    o.time_step(True); fine.fw[...] = 0; o.residual_block(prm.cdisRK[0])
+    w0 = fine.w.copy()
+    lv = 0
+    cyc = ADFLOW_B200.cycleStrategy(cycle)
+    for n, c in enumerate(cyc):     # executeMGCycle with the oracle's pieces
+        if c == -1:
+            lv -= 1
+            of, oc = Oracle(levels[lv], prm), Oracle(levels[lv + 1], prm)
+            of.mg_prolong(oc); of.apply_flow_bc(lv == 0)
+        elif c == 0:
+            ol = Oracle(levels[lv], prm)
+            if n > 0 and cyc[n - 1] != 1:
+                ol.time_step(True); ol.residual_block(prm.cdisRK[0])
+            ol.rk_smoother()
+        else:
+            of, oc = Oracle(levels[lv], prm), Oracle(levels[lv + 1], prm)
+            of.time_step(False); of.residual_block(prm.cdisRK[0])
+            oc.mg_restrict(of); oc.apply_flow_bc(False); oc.time_step(True); oc.mg_store_w1()
+            oc.residual_block_coarse(prm.cdisRK[0], init=0); oc.mg_forcing()
+            lv += 1
+    ow = fine.d.owned()
+    assert np.abs(fine.w[ow] - w0[ow]).max() < 1e-11 * np.abs(w0[ow]).max()
