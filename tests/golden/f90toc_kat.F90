@@ -2,6 +2,7 @@ module kat
     implicit none
     real(kind=realType) :: acc
     integer(kind=intType) :: counter
+    real(kind=realType), dimension(:, :, :), allocatable :: qq
 contains
 
     subroutine scalars(n, x, res)
@@ -122,6 +123,33 @@ contains
         call optional_and_shape(m, 3, 2, res(1))
         call optional_and_shape(m, 3, 2, res(2), .true.)
     end subroutine driver_shape
+    subroutine alloc_case(n, res)
+        ! module-level allocatable with explicit lower bounds (sa_block: allocate(qq(2:il, 2:jl, 2:kl))), named constructs,
+        ! integer min/max
+        integer(kind=intType), intent(in) :: n
+        real(kind=realType), dimension(4), intent(out) :: res
+        integer(kind=intType) :: i, j, k, m
+        allocate (qq(2:n, 2:n + 1, 0:1))
+        do k = 0, 1
+            do j = 2, n + 1
+                do i = 2, n
+                    qq(i, j, k) = real(100 * k + 10 * j + i, realType)
+                end do
+            end do
+        end do
+        res(1) = qq(2, 2, 0) + qq(n, n + 1, 1)
+        m = 0
+        outer: do j = 2, n + 1
+            testinner: if (j > 3) then
+                exit
+            end if testinner
+            m = m + j
+        end do outer
+        res(2) = real(m, realType)
+        res(3) = real(max(n, 3) - min(n, 3) + mod(-7, 3), realType)
+        res(4) = qq(n, 2, 1) * 0.5_realType
+        deallocate (qq)
+    end subroutine alloc_case
 #ifdef NEVER
     subroutine broken(
 #endif

@@ -30,7 +30,7 @@ def kat():
     os.makedirs(work, exist_ok=True)
     env = f90toc.Env([], {}, [], {})
     code, _tr = f90toc.translate_module(os.path.join(HERE, "golden", "f90toc_kat.F90"),
-                                        only={"scalars", "arrays", "optional_and_shape", "driver_shape"}, env=env,
+                                        only={"scalars", "arrays", "optional_and_shape", "driver_shape", "alloc_case"}, env=env,
                                         rename_modules={}, patches=(), defined=(), tr=None, prefix="kat_")
     assert "broken" not in code                     # the #ifdef NEVER block is dropped
     with open(os.path.join(work, "kat.c"), "w") as f:
@@ -115,3 +115,13 @@ def test_assumed_shape_and_optional(kat):
         for i in range(3):
             s += m[i, j] * wgt[i, j]
     assert res[0] == s and res[1] == -s
+
+
+@pytest.mark.parametrize("n", [3, 6])
+def test_allocatable_named_constructs_and_integer_intrinsics(kat, n):
+    res = (C.c_double * 4)()
+    kat.kat_alloc_case(C.byref(C.c_int(n)), res)
+    q = lambda i, j, k: 100.0 * k + 10 * j + i  # noqa: E731
+    m = sum(j for j in range(2, n + 2) if j <= 3)
+    # Fortran mod(-7, 3) = -1 (sign of the dividend)
+    assert list(res) == [q(2, 2, 0) + q(n, n + 1, 1), float(m), float(max(n, 3) - min(n, 3) - 1), q(n, 2, 1) * 0.5]
