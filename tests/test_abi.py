@@ -65,3 +65,24 @@ def test_integration_doc_binds_every_abi_symbol():
     doc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
     bound = set(re.findall(r'bind\(c,\s*name="(\w+)"\)', doc))
     assert sorted(set(ABI_SYMBOLS) - bound) == []
+
+
+def test_integration_doc_interface_matches_header_arity():
+    """every Fortran interface in INTEGRATION.md has as many dummies as its C prototype has parameters"""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "adflow_b200.h")).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|long long|double)\s+(adfb_\w+)\s*\(([^;{]*?)\)\s*;", h, re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("void", "") else len(re.split(r",(?![^()]*\))", args))
+    doc = re.sub(r"&\s*\n\s*", "", open(os.path.join(root, "INTEGRATION.md")).read())
+    fort = {}
+    for m in re.finditer(r"function\s+(adfb_\w+)\s*\(([^)]*)\)", doc):
+        a = m.group(2).strip()
+        fort[m.group(1)] = 0 if not a else len(a.split(","))
+    assert len(protos) >= 50
+    assert sorted(k for k in protos if k not in fort) == []
+    assert [(k, protos[k], fort[k]) for k in protos if protos[k] != fort[k]] == []
