@@ -86,3 +86,47 @@ def test_integration_doc_interface_matches_header_arity():
     assert len(protos) >= 50
     assert sorted(k for k in protos if k not in fort) == []
     assert [(k, protos[k], fort[k]) for k in protos if protos[k] != fort[k]] == []
+
+
+def test_struct_layouts_match_the_header_field_by_field():
+    """sizeof / offsetof of AdfbParams, AdfbAnkParams and AdfbSubface as gcc sees the header == the ctypes twins the
+    Python layer passes, and the field ORDER of the bind(c) types shown in INTEGRATION.md is the header's"""
+    import subprocess
+
+    from adflow_b200._lib import AdfbSubface
+    from adflow_b200.params import AdfbAnkParams
+
+    work = os.path.join(ROOT, "oracle", "_ref", "_selftest")
+    os.makedirs(work, exist_ok=True)
+    twins = {"AdfbParams": AdfbParams, "AdfbAnkParams": AdfbAnkParams, "AdfbSubface": AdfbSubface}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "adflow_b200.h"', 'int main(void) {']
+    for name, T in twins.items():
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (name, name))
+        for f, _t in T._fields_:
+            cf = {"pad_": "pad_"}.get(f, f)
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (name, f, name, cf))
+    lines += ["return 0; }"]
+    src = os.path.join(work, "layout.c")
+    with open(src, "w") as fh:
+        fh.write("\n".join(lines))
+    exe = os.path.join(work, "layout")
+    subprocess.check_call(["gcc", "-I" + os.path.join(ROOT, "include"), "-o", exe, src])
+    out = subprocess.check_output([exe]).decode().split("\n")
+    got = {}
+    for ln in out:
+        if ln.strip():
+            a, b, c = ln.split()
+            got[(a, b)] = int(c)
+    for name, T in twins.items():
+        assert got[(name, "sizeof")] == C.sizeof(T), name
+        for f, _t in T._fields_:
+            assert got[(name, f)] == getattr(T, f).offset, (name, f)
+    # Fortran types: same field order as the header
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for name, T in (("AdfbParams", AdfbParams), ("AdfbAnkParams", AdfbAnkParams)):
+        body = doc[doc.index("type, bind(c) :: %s" % name):doc.index("end type %s" % name)]
+        body = re.sub(r"&\s*\n\s*", "", body)
+        names = []
+        for decl in re.findall(r"::\s*([^\n]+)", body)[1:]:
+            names += [re.sub(r"\(.*\)", "", x).strip() for x in decl.split(",")]
+        assert [n.lower() for n in names] == [f.lower() for f, _t in T._fields_], name
