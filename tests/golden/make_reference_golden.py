@@ -7,7 +7,9 @@ Per case: checksums (sum, L2 norm) and sampled entries of
   * dw of blocketteResCore (src/NKSolver/blockette.F90:299-753) after the reference's own BC routines,
   * the state after one RungeKuttaSmoother (src/solver/smoothers.F90:4-86),
   * wr / coarse w after transferToCoarseGrid (src/solver/multiGrid.F90:5-324),
-  * the ANK time-step block of one cell (NKSolvers.F90:2116-2329).
+  * the ANK time-step block of one cell (NKSolvers.F90:2116-2329),
+  * the state after executeDADIStep (smoothers.F90:425-693), nuTilde after sa_block (sa.F90:16-86, RANS) and the wall
+    forces of wallIntegrationFace (surfaceIntegrations.F90:406-881).
 
     python tests/golden/make_reference_golden.py
 """
@@ -83,6 +85,26 @@ def compute_reference(name):
         out["mg_fine_w_samples"] = entries(rfine["w"], 5)
     finally:
         mg.close()
+    # one DADI step from the block-path residual; SA solve; wall forces (all on the state after the reference's BCs)
+    hd = hb.copy()
+    r3 = rb.call(hd, prm, "solverutils_timestep_block", 0)
+    for k_, n_ in (("dtl", "dtl"), ("radi", "radI"), ("radj", "radJ"), ("radk", "radK")):
+        getattr(hd, n_)[...] = r3.a[k_]
+    hd.fw[...] = 0
+    hd.dw[...] = 0
+    rb.set_int("smoother", 2)
+    try:
+        r4 = rb.call(hd, prm, "residuals_residual_block", rkstage=0)
+        for k_, n_ in (("dw", "dw"), ("fw", "fw"), ("aa", "aa")):
+            getattr(hd, n_)[...] = r4.a[k_]
+        r5 = rb.call(hd, prm, "smoothers_executedadistep", rkstage=0)
+    finally:
+        rb.set_int("smoother", 1)
+    out["dadi_w"] = [stats(r5.a["w"][ow + (l,)]) for l in range(5)]
+    if prm.equations == 3:
+        r6 = rb.call(hb.copy(), prm, "sa_sa_block", 0)
+        out["sa_nutilde"] = stats(r6.a["w"][ow + (5,)])
+        out["sa_nutilde_samples"] = [float(r6.a["w"][i, j, k, 5]) for (i, j, k) in SAMPLES]
     # ANK time-step block ('None' and 'VLR') of one cell, dtl from the reference's timeStep_block
     r2 = rb.call(hb, prm, "solverutils_timestep_block", 0)
     h3 = hb.copy()
