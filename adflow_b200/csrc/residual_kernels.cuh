@@ -206,6 +206,9 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
 // (allNodalGradients, :5205-5515) on nodes 1:il in gather form.  For node n (= cell index c)
 // the reference's three scatter sweeps add, in this order:  -K(layer k) +K(layer k+1)
 // -J(layer j) +J(layer j+1) -I(layer i) +I(layer i+1), then scale by 1/(8 vol).
+// GAOS (experiment switch ADFB_GRAD_AOS=1, main residual path only): the 12 gradients of a node are stored
+// contiguously (96 B) and read back by k_faces with six 128-bit loads per node instead of twelve 64-bit ones
+template <bool GAOS>
 __global__ void __launch_bounds__(NODAL_TPB, NODAL_MINB) k_nodal(Dims d, BlockDev b, int doGrad, int dissApprox) {
     ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
@@ -273,8 +276,14 @@ __global__ void __launch_bounds__(NODAL_TPB, NODAL_MINB) k_nodal(Dims d, BlockDe
         }
     }
     const double oVol = b.ovol[c];
+    if (GAOS) {
+        double2* o = reinterpret_cast<double2*>(b.grad + (long long)c * 12);
 #pragma unroll
-    for (int m = 0; m < 12; m++) b.grad[m * N + c] = g[m] * oVol;
+        for (int m = 0; m < 6; m++) o[m] = make_double2(g[2 * m] * oVol, g[2 * m + 1] * oVol);
+    } else {
+#pragma unroll
+        for (int m = 0; m < 12; m++) b.grad[m * N + c] = g[m] * oVol;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -294,7 +303,7 @@ __device__ __forceinline__ CellState load_cell(const BlockDev& b, int N, int c) 
 // APPROX bit 0: first-order/lumped dissipation (*Approx routines), bit 1: thin-layer viscous flux,
 // bit 2: first-order coarse-level scalar dissipation (inviscidDissFluxScalarCoarse, fluxes.F90:4977-5203)
 // PART: 0 = everything, 1 = central + dissipation only, 2 = viscous flux only (split launch, ADFB_SPLIT_FACES)
-template <bool VISCOUS, int DISC, int APPROX, int PART = 0>
+template <bool VISCOUS, int DISC, int APPROX, int PART = 0, bool GAOS = false>
 __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int sd, int t1, int t2, int dir,
                                           const double* __restrict__ s, int8_t por, const double* __restrict__ rad,
                                           const double* __restrict__ dss, const CellState& m, double rFil, int doDiss,
@@ -536,10 +545,23 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
         const double heatCoef = mul * (1.0 / (c_prm.prandtl * gm1)) + mue * (1.0 / (c_prm.prandtlTurb * gm1));
         const int n = c, n1 = c - t1 - t2, n2 = c - t2, n3 = c - t1;
         double g[12];
+        if (GAOS) {
+            const double2* p1 = reinterpret_cast<const double2*>(b.grad + (long long)n1 * 12);
+            const double2* p2 = reinterpret_cast<const double2*>(b.grad + (long long)n2 * 12);
+            const double2* p3 = reinterpret_cast<const double2*>(b.grad + (long long)n3 * 12);
+            const double2* p0 = reinterpret_cast<const double2*>(b.grad + (long long)n * 12);
+#pragma unroll
+            for (int l = 0; l < 6; l++) {
+                const double2 a1 = p1[l], a2 = p2[l], a3 = p3[l], a0 = p0[l];
+                g[2 * l] = 0.25 * (a1.x + a2.x + a3.x + a0.x);
+                g[2 * l + 1] = 0.25 * (a1.y + a2.y + a3.y + a0.y);
+            }
+        } else {
 #pragma unroll
         for (int l = 0; l < 12; l++) {
             const double* gm = b.grad + l * N;
             g[l] = 0.25 * (gm[n1] + gm[n2] + gm[n3] + gm[n]);
+        }
         }
         const double* vn = b.vn + (4 * dir) * N;
         const double ssx = vn[c], ssy = vn[N + c], ssz = vn[2 * N + c], snrm = vn[3 * N + c];
@@ -587,7 +609,7 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
 // k_faces: plus faces of cell (i,j,k), i 1:il, j 1:jl, k 1:kl.  MERGED: one array G = fc - fd per
 // face (net outflow of the low cell) -> flux[dir*5 + l]; otherwise fc -> flux[dir*10 + l],
 // fd -> flux[dir*10 + 5 + l] (smoother path: fw persists between RK stages).
-template <bool VISCOUS, bool MERGED, int DISC, int APPROX, bool STOREWALL = false, int PART = 0>
+template <bool VISCOUS, bool MERGED, int DISC, int APPROX, bool STOREWALL = false, int PART = 0, bool GAOS = false>
 __global__ void __launch_bounds__(FACES_TPB, PART == 0 ? FACES_MINB : FACES_MINB_SPLIT) k_faces(Dims d, BlockDev b, double rFil, int doVisc, int doDiss) {
     ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
@@ -608,7 +630,7 @@ __global__ void __launch_bounds__(FACES_TPB, PART == 0 ? FACES_MINB : FACES_MINB
     };
     const bool oi = i >= 2, oj = j >= 2, ok = k >= 2;
     if (oj && ok) {
-        face_flux<VISCOUS, DISC, APPROX, PART>(b, N, c, 1, sJ, sK, 0, b.si, b.porI[c], b.radI, b.dss, m, rFil, doDiss, doVisc, fc, fd, tqp);
+        face_flux<VISCOUS, DISC, APPROX, PART, GAOS>(b, N, c, 1, sJ, sK, 0, b.si, b.porI[c], b.radI, b.dss, m, rFil, doDiss, doVisc, fc, fd, tqp);
         if (STOREWALL && (i == 1 || i == d.il)) store_wall(0, i == 1 ? 0 : 1, j + (long long)d.NJ * k);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
@@ -618,7 +640,7 @@ __global__ void __launch_bounds__(FACES_TPB, PART == 0 ? FACES_MINB : FACES_MINB
         }
     }
     if (oi && ok) {
-        face_flux<VISCOUS, DISC, APPROX, PART>(b, N, c, sJ, 1, sK, 1, b.sj, b.porJ[c], b.radJ, b.dss + N, m, rFil, doDiss, doVisc, fc, fd, tqp);
+        face_flux<VISCOUS, DISC, APPROX, PART, GAOS>(b, N, c, sJ, 1, sK, 1, b.sj, b.porJ[c], b.radJ, b.dss + N, m, rFil, doDiss, doVisc, fc, fd, tqp);
         if (STOREWALL && (j == 1 || j == d.jl)) store_wall(1, j == 1 ? 0 : 1, i + (long long)d.NI * k);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
@@ -628,7 +650,7 @@ __global__ void __launch_bounds__(FACES_TPB, PART == 0 ? FACES_MINB : FACES_MINB
         }
     }
     if (oi && oj) {
-        face_flux<VISCOUS, DISC, APPROX, PART>(b, N, c, sK, 1, sJ, 2, b.sk, b.porK[c], b.radK, b.dss + 2 * N, m, rFil, doDiss, doVisc, fc, fd, tqp);
+        face_flux<VISCOUS, DISC, APPROX, PART, GAOS>(b, N, c, sK, 1, sJ, 2, b.sk, b.porK[c], b.radK, b.dss + 2 * N, m, rFil, doDiss, doVisc, fc, fd, tqp);
         if (STOREWALL && (k == 1 || k == d.kl)) store_wall(2, k == 1 ? 0 : 1, i + (long long)d.NI * j);
 #pragma unroll
         for (int l = 0; l < 5; l++) {
@@ -855,6 +877,11 @@ static int launch_geom(const Dims& d, const BlockDev& b, cudaStream_t stream) {
 }
 
 // doRad: 1 = recompute spectral radii + dtl (blockette order), 0 = keep them (block/smoother path)
+static bool grad_aos() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ADFB_GRAD_AOS"); v = e ? atoi(e) : 0; }
+    return v != 0;
+}
 static bool split_faces() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("ADFB_SPLIT_FACES"); v = e ? atoi(e) : 0; }
@@ -870,6 +897,9 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
     const int doVisc = viscous && doDiss;
     const int dissApprox = (flags & ADFB_RES_DISS_APPROX) ? 1 : 0, viscApprox = (flags & ADFB_RES_VISC_APPROX) ? 1 : 0;
     if ((dissApprox || viscApprox) && persistFw) return 1;  // approximate variants exist on the blockette path only
+    // experiment switch: AoS nodal-gradient store, only for the exact merged viscous scalar-JST residual (the bench path)
+    const bool gradAos = grad_aos() && flowRes && doVisc && !persistFw && !dissApprox && !viscApprox && !b.coarse && !split_faces() &&
+                         !((flags & ADFB_RES_STORE_WALL) != 0) && prm.spaceDiscr == ADFB_DISS_SCALAR;
     dim3 tb(32, 4, 2);
     // The SA row reads only the state and static geometry and writes dw(itu1); the flow rows write dw(1:5).
     // The two chains are independent, so k_sa is forked onto a side stream (also inside graph capture) and
@@ -913,7 +943,8 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         dim3 tn = tune_block("ADFB_NODAL_BLOCK", dim3(32, 4, 2));
         dim3 g((d.ie + tn.x - 1) / tn.x, (d.je + tn.y - 1) / tn.y, (d.ke + tn.z - 1) / tn.z);
         KT_BEGIN(K_NODAL, stream);
-        launch_pdl(k_nodal, g, tn, stream, d, b, (int)(doVisc && !viscApprox), dissApprox);
+        if (gradAos) launch_pdl(k_nodal<true>, g, tn, stream, d, b, (int)(doVisc && !viscApprox), dissApprox);
+        else launch_pdl(k_nodal<false>, g, tn, stream, d, b, (int)(doVisc && !viscApprox), dissApprox);
         KT_END(K_NODAL, stream);
     }
     if (flowRes) {
@@ -957,6 +988,8 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
                 launch_pdl(k_faces<true, true, ADFB_UPWIND, 0, false, 2>, g, tr, stream, d, b, rFil, doVisc, doDiss);
             }
             splitDone = 1;
+        } else if (gradAos) {
+            launch_pdl(k_faces<true, true, ADFB_DISS_SCALAR, 0, false, 0, true>, g, tr, stream, d, b, rFil, doVisc, doDiss);
         } else if (approx == 0) {
             if (viscous) { if (merged) ADFB_FACES_DISC(true, true, 0); else ADFB_FACES_DISC(true, false, 0); }
             else { if (merged) ADFB_FACES_DISC(false, true, 0); else ADFB_FACES_DISC(false, false, 0); }
