@@ -61,6 +61,9 @@ PATCHES = [
 ]
 
 MG_PATCHES = [
+    # executeMGCycle: the iteration-type label is output only
+    (r"^itertype = .*$", "continue"),
+    (r"^call terminate\(\"executemgcycle\".*$", "continue"),
     (r"flowdoms\(nn,\s*finelevel,\s*sps\)%(\w+)", r"fl_\1"),
     (r"flowdoms\(nn,\s*coarselevel,\s*(?:sps|1)\)%bcdata", r"cl_bcdata_unused"),
     (r"flowdoms\(nn,\s*coarselevel,\s*(?:sps|1)\)%(\w+)", r"cl_\1"),
@@ -110,7 +113,7 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  symm symmpolar nswalladiabatic nswallisothermal farfield eulerwall extrap supersonicinflow supersonicoutflow
  subsonicinflow subsonicoutflow massbleedoutflow imin imax jmin jmax kmin kmax
  constantpressure linextrapolpressure quadextrapolpressure normalmomentum
- ank_chartimestepcode ank_nvec sh_ib sh_jb sh_kb fl_ib fl_jb fl_kb cl_il cl_jl cl_kl cl_ie cl_je cl_ke cl_ib cl_jb cl_kb cl_nbocos mgboundcorr bcdirichlet0 bcneumann
+ nstepscycling nlluggs nllusgsline approxtotalits ank_chartimestepcode ank_nvec sh_ib sh_jb sh_kb fl_ib fl_jb fl_kb cl_il cl_jl cl_kl cl_ie cl_je cl_ke cl_ib cl_jb cl_kb cl_nbocos mgboundcorr bcdirichlet0 bcneumann
  slidinginterface oversetouterbound domaininterfaceall domaininterfacerhouvw domaininterfacep domaininterfacerho
  domaininterfacetotal""".split()
 
@@ -201,6 +204,7 @@ def env_arrays():
     # ANK: the PETSc vectors wVec / deltaW as plain arrays (bound by the harness)
     arrs["ank_wvec"] = A("ank_wvec", "double", [("1", "ank_nvec")], pointer=True) if False else A("ank_wvec", "double", [("1", "ank_nvec")])
     arrs["ank_dvec"] = A("ank_dvec", "double", [("1", "ank_nvec")])
+    arrs["cycling"] = A("cycling", "int", [("1", "256")])
     arrs["cl_bctype"] = A("cl_bctype", "int", [("1", "64")])
     arrs["cl_bcfaceid"] = A("cl_bcfaceid", "int", [("1", "64")])
     arrs["bp_bctype"] = A("bp_bctype", "int", [("1", "64")])
@@ -228,6 +232,8 @@ ENV_SUBS = {
     "setpointers": [("nn", "int", False), ("level", "int", False), ("sps", "int", False)],
     "whalo1": [(n, "int", False) for n in ("level", "start", "end", "commpressure", "commgamma", "commviscous")],
     "whalo2": [(n, "int", False) for n in ("level", "start", "end", "commpressure", "commgamma", "commviscous")],
+    "computeutau": [],
+    "turbapi_turbsolveddadi": [],
     "ank_matmul": [("a", "double", True), ("b", "double", True), ("c", "double", True)],
     "ank_matmul_nt": [("a", "double", True), ("b", "double", True), ("c", "double", True)],
 }
@@ -271,7 +277,7 @@ UNITS = [
     # to the blockPointers of the current one) -> fl_x / cl_x env data bound by the harness; the coarse block's
     # BCData -> accessor functions over a second subface table (cbcd)
     ("solver/multiGrid.F90", "multigrid_", ["transfertocoarsegrid", "transfertofinegrid", "setcornerrowhalos",
-                                            "setcorrectionscoarsehalos"], (), None, MG_PATCHES),
+                                            "setcorrectionscoarsehalos", "executemgcycle"], (), None, MG_PATCHES),
     # ANK: time-step block of the matrix-free operator and the physicality check of the update
     ("NKSolver/NKSolvers.F90", "anksolver_", ["computetimestepblock", "physicalitycheckank"], (), "anksolver_ref.c", ANK_PATCHES,
      "anksolver"),

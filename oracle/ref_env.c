@@ -124,3 +124,16 @@ void ank_matmul_nt(double* a, double* b, double* c) {
     }
     for (int q = 0; q < n * n; q++) c[q] = t[q];
 }
+
+/* executeMGCycle environment */
+int nstepscycling = 0, cycling[256], approxtotalits = 0, nsubiterturb = 1;
+void solverutils_computeutau(void) {}
+void sa_sa_block(int* resonly);
+/* turbSolveDDADI, src/turbulence/turbAPI.F90:4-95 (Spalart-Allmaras, steady, one block, no neighbours) */
+void turbsolveddadi(void) {
+    int one = 1, resonly = 0;
+    for (int it = 1; it <= nsubiterturb; it++) {
+        setpointers(&one, &currentlevel, &one);
+        sa_sa_block(&resonly);
+    }
+}

@@ -149,6 +149,12 @@ extern double ank_machinf, *ank_wvec, *ank_dvec;
 void ank_matmul(double* a, double* b, double* c);     /* c = MATMUL(a, b) */
 void ank_matmul_nt(double* a, double* b, double* c);  /* c = MATMUL(a, TRANSPOSE(b)) */
 
+/* executeMGCycle (src/solver/multiGrid.F90:825-955): iteration%cycling / nStepsCycling, the turbulence solve of
+   src/turbulence/turbAPI.F90:4-95 (SA: nSubIterTurb x sa_block) and computeUtau (wall functions: off) */
+extern int nstepscycling, cycling[256], approxtotalits, nsubiterturb;
+void solverutils_computeutau(void);
+void turbsolveddadi(void);
+
 /* driver-level procedures outside the translated set (no-op stubs, see ref_env.c) */
 void setpointers(int* nn, int* level, int* sps);
 void whalo1(int* level, int* start, int* end, int* commpressure, int* commgamma, int* commviscous);

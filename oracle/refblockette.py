@@ -353,14 +353,17 @@ class RefMG:
     the block of `level`; the OTHER level's arrays that the transfer routines reach through flowDoms(nn, level, sps)
     are bound once (fl_* = fine block, cl_* / cbcd = coarse block)."""
 
-    def __init__(self, fine_hb, coarse_hb, prm):
+    def __init__(self, fine_hb, coarse_hb, prm, more_levels=()):
+        """fine_hb / coarse_hb: levels 1 and 2; more_levels: HostBlocks of levels 3, 4, ... (executeMGCycle)"""
         global _BOUND
         self.prm = prm
         set_params(prm, fine_hb.nw)
         _setd("vis2coarse", prm.vis2Coarse); _setd("fcoll", prm.fcoll); _seti("mgboundcorr", prm.mgBoundCorr)
         _seti("spacediscrcoarse", _REF_SPACEDISCR[prm.spaceDiscrCoarse])
         _seti("radiineededcoarse", int(prm.spaceDiscrCoarse == 1))   # inputParamRoutines.F90:2824-2833
-        self.lv = {1: RefBlock(fine_hb, prm), 2: RefBlock(coarse_hb, prm)}
+        _seti("nsubiterturb", prm.nSubiterTurb)
+        hbs = [fine_hb, coarse_hb] + list(more_levels)
+        self.lv = {q + 1: RefBlock(hb, prm) for q, hb in enumerate(hbs)}
         self.keep = {}
         L = lib()
 
@@ -368,19 +371,38 @@ class RefMG:
             rb = self.lv[level]
             rb.bind(shared_from=self.lv[1] if level != 1 else None)
             self.keep[level] = bind_bcs(rb.hb, prm)
+            # the other levels the transfer routines reach through flowDoms(nn, fineLevel / coarseLevel, sps)
+            if level - 1 in self.lv:
+                f = self.lv[level - 1]
+                for n, v in (("ib", f.hb.d.ib), ("jb", f.hb.d.jb), ("kb", f.hb.d.kb)):
+                    _seti("fl_" + n, v)
+                for n in ("w", "p", "vol", "rev", "w1", "p1", "iblank"):
+                    _setp("fl_" + n, f.a[n])
+            if level + 1 in self.lv:
+                c = self.lv[level + 1]
+                for n in ("il", "jl", "kl", "ie", "je", "ke", "ib", "jb", "kb"):
+                    _seti("cl_" + n, getattr(c.hb.d, n))
+                for n in ("w", "p", "vol", "rev", "w1", "p1", "iblank"):
+                    _setp("cl_" + n, c.a[n])
+                self.keep["cl"] = bind_bcs(c.hb, prm, other_level=True)
 
         self._hook = C.CFUNCTYPE(None, C.c_int)(hook)
         C.c_void_p.in_dll(L, "setpointers_hook").value = C.cast(self._hook, C.c_void_p).value
-        f, c = self.lv[1], self.lv[2]
-        for n, v in (("ib", f.hb.d.ib), ("jb", f.hb.d.jb), ("kb", f.hb.d.kb)):
-            _seti("fl_" + n, v)
-        dc = c.hb.d
-        for n in ("il", "jl", "kl", "ie", "je", "ke", "ib", "jb", "kb"):
-            _seti("cl_" + n, getattr(dc, n))
-        for n in ("w", "p", "vol", "rev", "w1", "p1", "iblank"):
-            _setp("fl_" + n, f.a[n]); _setp("cl_" + n, c.a[n])
-        self.keep["cl"] = bind_bcs(c.hb, prm, other_level=True)
+        hook(2)      # the two-level tests call single routines right away: level 2 bound, fl_ = level 1
+        hook(1)      # ... and cl_ = level 2
         _BOUND = self
+
+    def execute_mg_cycle(self, cycling, smoother="RK", n_subiterations=1):
+        """executeMGCycle (multiGrid.F90:825-955) on ground level 1 with iteration%cycling = cycling"""
+        cyc = (C.c_int * 256).in_dll(lib(), "cycling")
+        for q, v in enumerate(cycling):
+            cyc[q] = int(v)
+        _seti("nstepscycling", len(cycling)); _seti("groundlevel", 1); _seti("currentlevel", 1); _seti("rkstage", 0)
+        _seti("smoother", 1 if smoother == "RK" else 2); _seti("nsubiterations", n_subiterations)
+        try:
+            lib().multigrid_executemgcycle()
+        finally:
+            _seti("smoother", 1); _seti("nsubiterations", 1)
 
     def seed_coarse_shared(self):
         """put the coarse block's dw, fw, dtl, radI/J/K, rlv, ... where the reference keeps them: in the finest

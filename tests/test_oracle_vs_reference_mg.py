@@ -203,3 +203,47 @@ def test_coarse_matrix_dissipation():
     ow = coarse.d.owned()
     assert np.abs(coarse.fw[ow] - c2.fw[ow]).max() > 0
     eq(coarse.fw[ow], mg.lv[1].a["fw"][ow], "fw")
+
+
+@pytest.mark.parametrize("shape,options,cycle,dadi_sub", [
+    ((12, 8, 10), {"equationType": "laminar NS"}, "2v", 0),
+    ((16, 12, 8), {"equationType": "Euler", "nRKStages": 3, "resAveraging": "never"}, "3w", 0),
+    ((12, 8, 8), None, "2v", 0),                                   # RANS: turbSolveDDADI at the end of the cycle
+    ((12, 12, 8), None, "3v", 0),
+    ((12, 8, 8), {"equationType": "Euler", "smoother": "DADI", "resAveraging": "never"}, "2v", 2),
+])
+def test_execute_mg_cycle_driven_by_the_reference(shape, options, cycle, dadi_sub):
+    """the reference's own driver executeMGCycle (multiGrid.F90:825-955, translated) runs the whole cycle -- its
+    transferToCoarseGrid / RungeKuttaSmoother or DADISmoother / transferToFineGrid on every level, then turbSolveDDADI,
+    timeStep and the residual -- and the composition of the oracle's pieces that tests/test_mg_gpu.py holds the device to
+    (oracle_mg_cycle) has to reproduce it bit for bit: the ORDER of operations of adfb_mg_cycle is the reference's"""
+    from adflow_b200.solver import ADFLOW_B200
+    from test_mg_gpu import oracle_mg_cycle, prepare_fine
+
+    nlev = int(cycle[0])
+    prm, fine = case(*shape, options)
+    fine.subfaces.sort(key=lambda s_: 0 if s_["bcType"] in (2, 6) else 1)
+    o = Oracle(fine, prm)
+    o.apply_turb_bc(True); o.apply_flow_bc(True)
+    levels = [fine]
+    for _ in range(nlev - 1):
+        levels.append(syn.make_coarse_block(levels[-1], prm))
+    prepare_fine(Oracle(fine, prm))
+    cyc = ADFLOW_B200.cycleStrategy(cycle)
+    ref_levels = [l.copy() for l in levels]
+    mg = rb.RefMG(ref_levels[0], ref_levels[1], prm, more_levels=ref_levels[2:])
+    try:
+        mg.execute_mg_cycle(cyc, smoother="DADI" if dadi_sub else "RK", n_subiterations=max(dadi_sub, 1))
+    finally:
+        mg.close()
+    rf = mg.lv[1].a
+    w0 = fine.w.copy()
+    oracle_mg_cycle(prm, levels, cyc, dadi_subiter=dadi_sub)
+    ow = fine.d.owned()
+    assert np.abs(fine.w[ow] - w0[ow]).max() > 0
+    nv = fine.nw
+    eq(fine.w[..., :nv], rf["w"][..., :nv], "fine state after the cycle (whole box)")
+    eq(fine.p, rf["p"], "fine p")
+    eq(fine.dw[ow][..., :5], rf["dw"][ow][..., :5], "fine residual after the cycle")
+    if prm.equations == 3:
+        eq(fine.rev, rf["rev"], "eddy viscosity")
