@@ -85,6 +85,22 @@ def compute_reference(name):
         out["mg_fine_w_samples"] = entries(rfine["w"], 5)
     finally:
         mg.close()
+    # a whole 2V cycle run by the reference's executeMGCycle (RK smoother), from the block-path residual of the fine level
+    from adflow_b200.solver import ADFLOW_B200
+    hm = hb.copy()
+    rt = rb.call(hm, prm, "solverutils_timestep_block", 0)
+    for k_, n_ in (("dtl", "dtl"), ("radi", "radI"), ("radj", "radJ"), ("radk", "radK")):
+        getattr(hm, n_)[...] = rt.a[k_]
+    hm.fw[...] = 0; hm.dw[...] = 0
+    rr_ = rb.call(hm, prm, "residuals_residual_block", rkstage=0)
+    for k_, n_ in (("dw", "dw"), ("fw", "fw"), ("aa", "aa")):
+        getattr(hm, n_)[...] = rr_.a[k_]
+    mg2 = rb.RefMG(hm, coarse.copy(), prm)
+    try:
+        mg2.execute_mg_cycle(ADFLOW_B200.cycleStrategy("2v"))
+        out["mg_cycle_2v_w"] = [stats(mg2.lv[1].a["w"][ow + (l,)]) for l in range(hb.nw)]
+    finally:
+        mg2.close()
     # one DADI step from the block-path residual; SA solve; wall forces (all on the state after the reference's BCs)
     hd = hb.copy()
     r3 = rb.call(hd, prm, "solverutils_timestep_block", 0)
