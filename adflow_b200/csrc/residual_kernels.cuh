@@ -23,6 +23,9 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+#include "fused_kernels.cuh"
+#include "geom_cell.cuh"
 
 // tunables (see profiles/): threads per block / min resident blocks per SM
 #ifndef FACES_TPB
@@ -64,72 +67,9 @@ static inline dim3 tune_block(const char* env, dim3 dflt) {
 namespace {
 
 // ---------------------------------------------------------------------------
-// k_geom: geometry-derived static arrays, once per mesh (adfb_block_set_geometry).
-//   ssum[dir] = s(c-sd) + s(c)          (timeStep sx/sy/sz, blockette.F90:1976-2006; saAdvection/saViscous xa)
-//   sv[dir]   = 8-face normal sum of the dual face at cell layer c (allNodalGradients, :5247-5258)
-//   ovol      = 1 / (8-cell volume sum) at node c (:5489-5492)
-//   vn[dir]   = unit vector + inverse length between cell centres across face c (viscousFlux, :5638-5657)
+// k_geom: geometry-derived static arrays (geom_cell.cuh), once per mesh (adfb_block_set_geometry)
 __global__ void __launch_bounds__(256) k_geom(Dims d, BlockDev b) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = blockIdx.z * blockDim.z + threadIdx.z;
-    if (i < 1 || i > d.ie || j < 1 || j > d.je || k < 1 || k > d.ke) return;
-    const int N = (int)d.N, sJ = (int)d.sJ, sK = (int)d.sK;
-    const int c = i + sJ * j + sK * k;
-    const double *si = b.si, *sj = b.sj, *sk = b.sk;
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-        b.ssum[m * N + c] = si[m * N + c - 1] + si[m * N + c];
-        b.ssum[(3 + m) * N + c] = sj[m * N + c - sJ] + sj[m * N + c];
-        b.ssum[(6 + m) * N + c] = sk[m * N + c - sK] + sk[m * N + c];
-    }
-    // dual-face sums; reference order: layer c-sd: (0, t1, t2, t1+t2), then layer c
-    if (i <= d.il && j <= d.jl) {  // K sweep: i 1:il, j 1:jl, k 1:ke ; t1 = I, t2 = J
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            const double* s = sk + m * N;
-            b.sv[(6 + m) * N + c] = s[c - sK] + s[c - sK + 1] + s[c - sK + sJ] + s[c - sK + 1 + sJ] + s[c] + s[c + 1] + s[c + sJ] + s[c + 1 + sJ];
-        }
-    }
-    if (i <= d.il && k <= d.kl) {  // J sweep: t1 = I, t2 = K
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            const double* s = sj + m * N;
-            b.sv[(3 + m) * N + c] = s[c - sJ] + s[c - sJ + 1] + s[c - sJ + sK] + s[c - sJ + 1 + sK] + s[c] + s[c + 1] + s[c + sK] + s[c + 1 + sK];
-        }
-    }
-    if (j <= d.jl && k <= d.kl) {  // I sweep: t1 = J, t2 = K
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            const double* s = si + m * N;
-            b.sv[m * N + c] = s[c - 1] + s[c - 1 + sJ] + s[c - 1 + sK] + s[c - 1 + sJ + sK] + s[c] + s[c + sJ] + s[c + sK] + s[c + sJ + sK];
-        }
-    }
-    if (i <= d.il && j <= d.jl && k <= d.kl) {
-        const double* vol = b.vol;
-        b.ovol[c] = 1.0 / (vol[c] + vol[c + sK] + vol[c + 1] + vol[c + 1 + sK] + vol[c + sJ] + vol[c + sJ + sK] + vol[c + 1 + sJ] + vol[c + 1 + sJ + sK]);
-        // face-normal unit vectors for the viscous gradient correction; node n = c
-        const double* x = b.x;
-        const int sd[3] = {1, sJ, sK}, t1[3] = {sJ, 1, 1}, t2[3] = {sK, sK, sJ};
-#pragma unroll
-        for (int dir = 0; dir < 3; dir++) {
-            // faces exist for the two transverse indices >= 2
-            const bool ok = (dir == 0) ? (j >= 2 && k >= 2) : (dir == 1) ? (i >= 2 && k >= 2) : (i >= 2 && j >= 2);
-            if (!ok) continue;
-            const int n = c, n1 = c - t1[dir] - t2[dir], n2 = c - t2[dir], n3 = c - t1[dir], s = sd[dir];
-            double v[3];
-#pragma unroll
-            for (int m = 0; m < 3; m++) {
-                const double* xm = x + m * N;
-                v[m] = 0.125 * (xm[n1 + s] - xm[n1 - s] + xm[n3 + s] - xm[n3 - s] + xm[n2 + s] - xm[n2 - s] + xm[n + s] - xm[n - s]);
-            }
-            const double snrm = 1.0 / sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-            b.vn[(4 * dir + 0) * N + c] = snrm * v[0];
-            b.vn[(4 * dir + 1) * N + c] = snrm * v[1];
-            b.vn[(4 * dir + 2) * N + c] = snrm * v[2];
-            b.vn[(4 * dir + 3) * N + c] = snrm;
-        }
-    }
+    geom_cell(d, b, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y, blockIdx.z * blockDim.z + threadIdx.z);
 }
 
 // ---------------------------------------------------------------------------
@@ -939,7 +879,17 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         launch_pdl(k_prep, g, tb, stream, d, b, updateDt, doRad);
         KT_END(K_PREP, stream);
     }
-    if (flowRes && doDiss) {
+    // tile kernel (fused_kernels.cuh): exact central + scalar-JST (+ viscous) flow rows in one launch
+    bool fusedDone = false;
+    if (flowRes && fused_mode() > 0 && !b.coarse && prm.spaceDiscr == ADFB_DISS_SCALAR && !dissApprox && !viscApprox && !initWr &&
+        !(flags & ADFB_RES_STORE_WALL) && !split_faces()) {
+        KT_BEGIN(K_RESID, stream);
+        const int rc = launch_flowres_tile(d, b, prm, (int)((b.p - b.w) / d.N), rFil, doDiss, !persistFw, persistFw, stream);
+        KT_END(K_RESID, stream);
+        if (rc > 0) return 1;
+        fusedDone = rc == 0;
+    }
+    if (flowRes && doDiss && !fusedDone) {
         dim3 tn = tune_block("ADFB_NODAL_BLOCK", dim3(32, 4, 2));
         dim3 g((d.ie + tn.x - 1) / tn.x, (d.je + tn.y - 1) / tn.y, (d.ke + tn.z - 1) / tn.z);
         KT_BEGIN(K_NODAL, stream);
@@ -947,7 +897,7 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         else launch_pdl(k_nodal<false>, g, tn, stream, d, b, (int)(doVisc && !viscApprox), dissApprox);
         KT_END(K_NODAL, stream);
     }
-    if (flowRes) {
+    if (flowRes && !fusedDone) {
         dim3 tr = tune_block("ADFB_FACES_BLOCK", dim3(32, 4, 1));
         dim3 g((d.il + tr.x - 1) / tr.x, (d.jl + tr.y - 1) / tr.y, (d.kl + tr.z - 1) / tr.z);
         const bool merged = !persistFw;
