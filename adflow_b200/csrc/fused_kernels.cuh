@@ -101,6 +101,14 @@ struct FGeoN { double svKhi[3], svJ[6], svI[6], ovol; };           // nodal grad
 struct FGeoF { double s1, s2, s3, rad0, rad1, vn[4]; int por; };   // an i+ or j+ face
 struct FGeoK { double s1, s2, s3, rad1, vn[4]; int por; FCell qq; double ss2; int iblank; };   // the k+ face, plane k+2 of the column
 
+#ifndef FT_OWNCELL
+#define FT_OWNCELL 0   // 1: the own cell of plane k is read once per step and kept in registers across the three faces
+#endif
+#ifndef FT_PAIRSUM
+#define FT_PAIRSUM 1
+#endif
+struct FOwn { FCell m; double rlv, rev, aa, ss; };   // the thread's own cell of plane k (read once per step)
+
 // read-only global loads through the non-coherent path
 #if defined(__CUDA_ARCH__)
 #define FLDG(p) __ldg(p)
@@ -329,31 +337,52 @@ FHD void ft_nodal(const FTile& t, const FCtx& x, const double* __restrict__ A, c
         const int o = x.o2 + (m & 1) + ((m >> 1) & 1) * PX;
         q[m][0] = S[FV_U * FT_S2 + o]; q[m][1] = S[FV_V * FT_S2 + o]; q[m][2] = S[FV_W * FT_S2 + o]; q[m][3] = S[FV_AA * FT_S2 + o];
     }
+    double bar[6][4];   // [K lo, K hi, J lo, J hi, I lo, I hi]
+#if FT_PAIRSUM
+    // the six dual-face averages of each variable from shared pair sums (14 additions instead of 18; the
+    // reference adds the four cells left to right, the difference is one rounding)
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        const double p01 = q[0][v] + q[1][v], p23 = q[2][v] + q[3][v], p45 = q[4][v] + q[5][v], p67 = q[6][v] + q[7][v];
+        const double p02 = q[0][v] + q[2][v], p13 = q[1][v] + q[3][v], p46 = q[4][v] + q[6][v], p57 = q[5][v] + q[7][v];
+        bar[0][v] = 0.25 * (p01 + p23); bar[1][v] = 0.25 * (p45 + p67);
+        bar[2][v] = 0.25 * (p01 + p45); bar[3][v] = 0.25 * (p23 + p67);
+        bar[4][v] = 0.25 * (p02 + p46); bar[5][v] = 0.25 * (p13 + p57);
+    }
+#else
+    {
+        const int lo[3][4] = {{0, 2, 4, 6}, {0, 1, 4, 5}, {0, 1, 2, 3}};
+        const int hi[3][4] = {{1, 3, 5, 7}, {2, 3, 6, 7}, {4, 5, 6, 7}};
+#pragma unroll
+        for (int dd = 0; dd < 3; dd++)
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                const int* sel = side ? hi[dd] : lo[dd];
+#pragma unroll
+                for (int v = 0; v < 4; v++) bar[2 * (2 - dd) + side][v] = 0.25 * (q[sel[0]][v] + q[sel[1]][v] + q[sel[2]][v] + q[sel[3]][v]);
+            }
+    }
+#endif
     double g[12];
 #pragma unroll
     for (int m = 0; m < 12; m++) g[m] = 0.0;
-    const int lo[3][4] = {{0, 2, 4, 6}, {0, 1, 4, 5}, {0, 1, 2, 3}};
-    const int hi[3][4] = {{1, 3, 5, 7}, {2, 3, 6, 7}, {4, 5, 6, 7}};
 #pragma unroll
     for (int dd = 2; dd >= 0; dd--) {  // K, J, I
 #pragma unroll
         for (int side = 0; side < 2; side++) {
-            const int* sel = side ? hi[dd] : lo[dd];
             const double* sv = dd == 2 ? (side ? gn.svKhi : r.svK) : dd == 1 ? gn.svJ + 3 * side : gn.svI + 3 * side;
             const double s1 = sv[0], s2 = sv[1], s3 = sv[2];
-            double bar[4];
-#pragma unroll
-            for (int v = 0; v < 4; v++) bar[v] = 0.25 * (q[sel[0]][v] + q[sel[1]][v] + q[sel[2]][v] + q[sel[3]][v]);
+            const double* br = bar[2 * (2 - dd) + side];
             const double sg = side ? 1.0 : -1.0;
 #pragma unroll
             for (int v = 0; v < 3; v++) {
-                g[3 * v + 0] += sg * (bar[v] * s1);
-                g[3 * v + 1] += sg * (bar[v] * s2);
-                g[3 * v + 2] += sg * (bar[v] * s3);
+                g[3 * v + 0] += sg * (br[v] * s1);
+                g[3 * v + 1] += sg * (br[v] * s2);
+                g[3 * v + 2] += sg * (br[v] * s3);
             }
-            g[9] -= sg * (bar[3] * s1);
-            g[10] -= sg * (bar[3] * s2);
-            g[11] -= sg * (bar[3] * s3);
+            g[9] -= sg * (br[3] * s1);
+            g[10] -= sg * (br[3] * s2);
+            g[11] -= sg * (br[3] * s3);
         }
     }
 #pragma unroll
@@ -371,11 +400,16 @@ FHD void ft_nodal(const FTile& t, const FCtx& x, const double* __restrict__ A, c
 // phase 2a: the i+ (dir 0) or j+ (dir 1) face of cell (i, j, k): fc (central) and fd (JST + viscous)
 template <bool VISCOUS>
 FHD void ft_face_ij(const AdfbParams& P, const FTile& t, const FCtx& x, int dir, const double* __restrict__ A, const FSmem& sm, const FGeoF& gf,
-                    double rFil, int doDiss, double fc[5], double fd[5]) {
+                    const FOwn& ow, double rFil, int doDiss, double fc[5], double fd[5]) {
     const int so = dir == 0 ? 1 : t.PX;        // state-tile offset of the neighbour across the face
     const int eo = dir == 0 ? t.TX : 1;        // thread-tile offset of the second node column of the face (i face: j-1, j face: i-1)
     const int o = x.o2;
-    const FCell m = ft_cell(A, o), q = ft_cell(A, o + so);
+#if FT_OWNCELL
+    const FCell& m = ow.m;
+#else
+    const FCell m = ft_cell(A, o);
+#endif
+    const FCell q = ft_cell(A, o + so);
     ff_central(m, q, gf.s1, gf.s2, gf.s3, gf.por, fc);
 #pragma unroll
     for (int l = 0; l < 5; l++) fd[l] = 0.0;
@@ -385,31 +419,39 @@ FHD void ft_face_ij(const AdfbParams& P, const FTile& t, const FCtx& x, int dir,
         ff_cons(mm, Qmm); ff_cons(qq, Qqq);
         const double* ss = A + FV_SS * FT_S2;
         const double sslim = ff_sslim(P);
-        const double d0 = ff_dss(ss[o - so], ss[o], ss[o + so], sslim), d1 = ff_dss(ss[o], ss[o + so], ss[o + 2 * so], sslim);
+        const double ssp = ss[o + so];
+        const double ss0 = FT_OWNCELL ? ow.ss : ss[o];
+        const double d0 = ff_dss(ss[o - so], ss0, ssp, sslim), d1 = ff_dss(ss0, ssp, ss[o + 2 * so], sslim);
         ff_jst(P, Qmm, m, q, Qqq, gf.por, gf.rad0 + gf.rad1, dmax_(d0, d1), rFil, fd);
     }
     if (VISCOUS && doDiss) {
         double g[12];
 #pragma unroll
         for (int l = 0; l < 12; l++) g[l] = 0.25 * (sm.EE[l * FT_S0 + x.o0 - eo] + sm.EE[l * FT_S0 + x.o0]);
-        ff_visc(P, m, q, gf.s1, gf.s2, gf.s3, gf.por, rFil, A[FV_RLV * FT_S2 + o] + A[FV_RLV * FT_S2 + o + so],
-                A[FV_REV * FT_S2 + o] + A[FV_REV * FT_S2 + o + so], A[FV_AA * FT_S2 + o + so] - A[FV_AA * FT_S2 + o], gf.vn, g, fd);
+        ff_visc(P, m, q, gf.s1, gf.s2, gf.s3, gf.por, rFil, (FT_OWNCELL ? ow.rlv : A[FV_RLV * FT_S2 + o]) + A[FV_RLV * FT_S2 + o + so],
+                (FT_OWNCELL ? ow.rev : A[FV_REV * FT_S2 + o]) + A[FV_REV * FT_S2 + o + so],
+                A[FV_AA * FT_S2 + o + so] - (FT_OWNCELL ? ow.aa : A[FV_AA * FT_S2 + o]), gf.vn, g, fd);
     }
 }
 
 // phase 2b: the k+ face of the own column (planes k | k+1); updates the carried k-direction registers
 template <bool VISCOUS>
 FHD void ft_face_k(const AdfbParams& P, const FTile& t, const FCtx& x, const double* __restrict__ A, const double* __restrict__ B, const FSmem& sm,
-                   const FGeoK& gk, FRegs& r, double rFil, int doDiss, double fc[5], double fd[5]) {
+                   const FGeoK& gk, const FOwn& ow, FRegs& r, double rFil, int doDiss, double fc[5], double fd[5]) {
     const int o = x.o2, TX = t.TX;
-    const FCell m = ft_cell(A, o), q = ft_cell(B, o);
+#if FT_OWNCELL
+    const FCell& m = ow.m;
+#else
+    const FCell m = ft_cell(A, o);
+#endif
+    const FCell q = ft_cell(B, o);
     ff_central(m, q, gk.s1, gk.s2, gk.s3, gk.por, fc);
 #pragma unroll
     for (int l = 0; l < 5; l++) fd[l] = 0.0;
     if (doDiss) {
         double Qqq[5];
         ff_cons(gk.qq, Qqq);
-        const double d1 = ff_dss(A[FV_SS * FT_S2 + o], B[FV_SS * FT_S2 + o], gk.ss2, ff_sslim(P));
+        const double d1 = ff_dss(FT_OWNCELL ? ow.ss : A[FV_SS * FT_S2 + o], B[FV_SS * FT_S2 + o], gk.ss2, ff_sslim(P));
         ff_jst(P, r.qm1, m, q, Qqq, gk.por, r.radK + gk.rad1, dmax_(r.dssK, d1), rFil, fd);
         r.dssK = d1;
     }
@@ -418,9 +460,10 @@ FHD void ft_face_k(const AdfbParams& P, const FTile& t, const FCtx& x, const dou
         double g[12];
 #pragma unroll
         for (int l = 0; l < 12; l++)
-            g[l] = 0.25 * (sm.G[l * FT_S0 + x.o0 - TX - 1] + sm.G[l * FT_S0 + x.o0 - TX] + sm.G[l * FT_S0 + x.o0 - 1] + sm.G[l * FT_S0 + x.o0]);
-        ff_visc(P, m, q, gk.s1, gk.s2, gk.s3, gk.por, rFil, A[FV_RLV * FT_S2 + o] + B[FV_RLV * FT_S2 + o], A[FV_REV * FT_S2 + o] + B[FV_REV * FT_S2 + o],
-                B[FV_AA * FT_S2 + o] - A[FV_AA * FT_S2 + o], gk.vn, g, fd);
+            g[l] = 0.25 * (sm.G[l * FT_S0 + x.o0 - TX - 1] + sm.G[l * FT_S0 + x.o0 - TX] + sm.G[l * FT_S0 + x.o0 - 1] + r.gprev[l]);   // own node: still in registers
+        ff_visc(P, m, q, gk.s1, gk.s2, gk.s3, gk.por, rFil, (FT_OWNCELL ? ow.rlv : A[FV_RLV * FT_S2 + o]) + B[FV_RLV * FT_S2 + o],
+                (FT_OWNCELL ? ow.rev : A[FV_REV * FT_S2 + o]) + B[FV_REV * FT_S2 + o], B[FV_AA * FT_S2 + o] - (FT_OWNCELL ? ow.aa : A[FV_AA * FT_S2 + o]),
+                gk.vn, g, fd);
     }
     ff_cons(m, r.qm1);
 }
@@ -556,12 +599,23 @@ FHD bool ft_var_used(int v, bool viscous, int doDiss) {
 // The step driver shared by the kernel and the CPU emulation: SYNC is the CTA barrier (a no-op functor on the CPU, where
 // the caller runs every thread up to each cut instead).  Kept as three plain functions so that both drivers call the
 // same per-thread code between the same synchronisation points.
+// FT_EARLY = 1: the global operands of a phase are loaded one phase ahead of their use (needs the registers: FT_MAXT <=
+// 256); 0: right before their use (the L2 prefetch of the previous step covers part of the latency)
+#ifndef FT_EARLY
+#define FT_EARLY (FT_MAXT <= 256)
+#endif
 template <bool VISCOUS, bool MERGED>
 FHD void ft_step_a(const Dims& d, const BlockDev& b, const FTile& t, const FCtx& x, int k, int kb, const double* A, const double* B, FSmem& sm,
                    FRegs& r, FStep& st, int doDiss, bool doIJ) {
     const bool visc = VISCOUS && doDiss;
-    if (visc) {
-        ft_load_nodal(d, b, x, k, k < kb, st.gn);
+    const bool pf = k < kb;
+    if (FT_EARLY) {
+        // face operands of this step: in flight during the nodal phase (gn was loaded during the previous step's k face)
+        if (doIJ) { ft_load_face(d, b, x, k, 0, visc, pf, st.gi); ft_load_face(d, b, x, k, 1, visc, pf, st.gj); }
+        ft_load_face_k(d, b, x, k, visc, doDiss, pf, st.gk);
+        if (visc) ft_nodal(t, x, A, B, st.gn, sm, r, doIJ);
+    } else if (visc) {
+        ft_load_nodal(d, b, x, k, pf, st.gn);
         ft_nodal(t, x, A, B, st.gn, sm, r, doIJ);
     }
 }
@@ -572,22 +626,31 @@ FHD void ft_step_b(const AdfbParams& P, const Dims& d, const BlockDev& b, const 
     const bool visc = VISCOUS && doDiss;
     const bool pf = k < kb;
     double fc[5], fd[5];
+    FOwn ow;
+    if (FT_OWNCELL && (x.fi || x.fj)) {
+        ow.m = ft_cell(A, x.o2);
+        ow.ss = doDiss ? A[FV_SS * FT_S2 + x.o2] : 0.0;
+        ow.rlv = visc ? A[FV_RLV * FT_S2 + x.o2] : 0.0;
+        ow.rev = visc ? A[FV_REV * FT_S2 + x.o2] : 0.0;
+        ow.aa = visc ? A[FV_AA * FT_S2 + x.o2] : 0.0;
+    }
     if (MERGED || part == 0) {
+        if (FT_EARLY && visc && k < kb) ft_load_nodal(d, b, x, k + 1, k + 1 < kb, st.gn);   // for the next step's nodal phase
         if (doIJ && x.fi) {
-            ft_load_face(d, b, x, k, 0, visc, pf, st.gi);
-            ft_face_ij<VISCOUS>(P, t, x, 0, A, sm, st.gi, rFil, doDiss, fc, fd);
+            if (!FT_EARLY) ft_load_face(d, b, x, k, 0, visc, pf, st.gi);
+            ft_face_ij<VISCOUS>(P, t, x, 0, A, sm, st.gi, ow, rFil, doDiss, fc, fd);
             ft_store_flux<MERGED>(x, sm, 0, fc, fd);
         }
     }
     if (MERGED || part == 1) {
         if (doIJ && x.fj) {
-            ft_load_face(d, b, x, k, 1, visc, pf, st.gj);
-            ft_face_ij<VISCOUS>(P, t, x, 1, A, sm, st.gj, rFil, doDiss, fc, fd);
+            if (!FT_EARLY) ft_load_face(d, b, x, k, 1, visc, pf, st.gj);
+            ft_face_ij<VISCOUS>(P, t, x, 1, A, sm, st.gj, ow, rFil, doDiss, fc, fd);
             ft_store_flux<MERGED>(x, sm, 5, fc, fd);
         }
         if (x.own) {
-            ft_load_face_k(d, b, x, k, visc, doDiss, pf, st.gk);
-            ft_face_k<VISCOUS>(P, t, x, A, B, sm, st.gk, r, rFil, doDiss, fc, fd);
+            if (!FT_EARLY) ft_load_face_k(d, b, x, k, visc, doDiss, pf, st.gk);
+            ft_face_k<VISCOUS>(P, t, x, A, B, sm, st.gk, ow, r, rFil, doDiss, fc, fd);
 #pragma unroll
             for (int l = 0; l < 5; l++) {
                 if (MERGED) st.kp[l] = fc[l] - fd[l];
@@ -767,6 +830,7 @@ __global__ void __launch_bounds__(FT_MAXT, FT_MINB) k_flowres(Dims d, BlockDev b
     FRegs r;
     FStep st;
     ft_prologue_regs(c_prm, d, b, x, ka - 1, r, doDiss, VISCOUS);
+    if (FT_EARLY && visc) ft_load_nodal(d, b, x, ka - 1, true, st.gn);
     wait_plane(ka - 1);
     wait_plane(ka);
     __syncthreads();

@@ -456,6 +456,20 @@ __global__ void __launch_bounds__(256) k_bc_frame(Dims d, BlockDev b, const BcLi
     }
 }
 
+// one ordered frame item (subface s of the list, kind 3 = turbulence BC, else the flow phase): the frame cells only
+__global__ void __launch_bounds__(128) k_bc_frame_item(Dims d, BlockDev b, const BcList* __restrict__ Lp, int s, int kind, int secondHalo) {
+    ADFB_PDL_SYNC();
+    const BcList& L = *Lp;
+    const FaceDev& f = L.f[s];
+    const int a0 = f.icBeg > 2 ? f.icBeg : 2, a1 = f.icEnd < L.la[s] ? f.icEnd : L.la[s];
+    const int b0 = f.jcBeg > 2 ? f.jcBeg : 2, b1 = f.jcEnd < L.lb[s] ? f.jcEnd : L.lb[s];
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    int ia, jb;
+    if (!frame_cell(q, f.icBeg, f.icEnd, f.jcBeg, f.jcEnd, a0, a1, b0, b1, &ia, &jb)) return;
+    if (kind == 3) bc_turb_cell(d, b, f, ia, jb, secondHalo);
+    else bc_flow_cell(d, b, f, ia, jb, secondHalo, kind);
+}
+
 // ---------------------------------------------------------------------------
 // executeRkStage part 1: dw *= cfl*etaRK(stage)*dtl, smoothers.F90:196-218
 __global__ void __launch_bounds__(256) k_rk_scale(Dims d, BlockDev b, double tmp) {
@@ -685,15 +699,19 @@ __global__ void __launch_bounds__(256) k_wall_forces(Dims d, BlockDev b, FaceDev
 
 }  // namespace
 
-static bool bc_two_launch() {
+// ADFB_BC_FUSED: 0 (default) = one launch per subface and phase over all of its cells; 1 = one launch for the
+// order-independent cells of all subfaces, then the ordered frame items as small launches (round 2: 14 launches of
+// ~6 us each inside the graph, slower than 13 and not parity-clean: experiment only); 2 = bulk launch + one CTA
+// walking the frame items (measured slower in round 1)
+static int bc_mode() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("ADFB_BC_FUSED"); v = e ? atoi(e) : 0; }   // measured slower: off by default
-    return v != 0;
+    if (v < 0) { const char* e = getenv("ADFB_BC_FUSED"); v = e ? atoi(e) : 0; }
+    return v;
 }
-// all BCs of a block in two launches (k_bc_bulk + k_bc_frame); returns -1 when the general path must be used
+// all BCs of a block: bulk launch + ordered frames; returns -1 when the general path must be used
 static int launch_bc_fused(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, int secondHalo, int withTurb, int withFlow,
                            cudaStream_t s) {
-    if (!bc_two_launch() || subs.empty() || (int)subs.size() > ADFB_BC_MAXSUB || !b.bcList) return -1;
+    if (!bc_mode() || subs.empty() || (int)subs.size() > ADFB_BC_MAXSUB || !b.bcList) return -1;
     int ma = 1, mb = 1;
     for (const AdfbSubface& sf : subs) {
         const int la = (sf.faceId == ADFB_IMIN || sf.faceId == ADFB_IMAX) ? d.jl : d.il;
@@ -707,9 +725,35 @@ static int launch_bc_fused(const Dims& d, const BlockDev& b, const std::vector<A
     KT_BEGIN(K_BC, s);
     launch_pdl(k_bc_bulk, g, tb, s, d, b, L, secondHalo, withTurb, withFlow);
     KT_END(K_BC, s);
-    KT_BEGIN(K_BC, s);
-    launch_pdl(k_bc_frame, dim3(1), dim3(256), s, d, b, L, secondHalo, withTurb, withFlow);
-    KT_END(K_BC, s);
+    if (bc_mode() == 2) {
+        KT_BEGIN(K_BC, s);
+        launch_pdl(k_bc_frame, dim3(1), dim3(256), s, d, b, L, secondHalo, withTurb, withFlow);
+        KT_END(K_BC, s);
+        return (int)cudaGetLastError();
+    }
+    // ordered frame items, the reference's order (applyAllTurbBCThisBlock, then applyAllBC_block: BCRoutines.F90:81-216)
+    auto item = [&](int q, int kind) {
+        const AdfbSubface& sf = subs[q];
+        const int na = sf.icEnd - sf.icBeg + 1, nb = sf.jcEnd - sf.jcBeg + 1;
+        const int nFrame = 2 * (na + nb);   // upper bound of the frame cells of one subface (frame_cell() rejects the rest)
+        KT_BEGIN(K_BC, s);
+        launch_pdl(k_bc_frame_item, dim3((nFrame + 127) / 128), dim3(128), s, d, b, L, q, kind, secondHalo);
+        KT_END(K_BC, s);
+    };
+    const int n = (int)subs.size();
+    if (withTurb) for (int q = 0; q < n; q++) item(q, 3);
+    if (withFlow) {
+        for (int q = 0; q < n; q++) if (subs[q].bcType == ADFB_BC_SYMM) item(q, 1);
+        if (secondHalo) for (int q = 0; q < n; q++) if (subs[q].bcType == ADFB_BC_SYMM) item(q, 2);
+        for (int q = 0; q < n; q++) if (subs[q].bcType == ADFB_BC_SYMMPOLAR) item(q, 1);
+        if (secondHalo) for (int q = 0; q < n; q++) if (subs[q].bcType == ADFB_BC_SYMMPOLAR) item(q, 2);
+        const int order[8][2] = {{ADFB_BC_NSWALL_ADIABATIC, -1}, {ADFB_BC_NSWALL_ISOTHERMAL, -1}, {ADFB_BC_FARFIELD, -1},
+                                 {ADFB_BC_SUBSONIC_OUTFLOW, -1}, {ADFB_BC_SUBSONIC_INFLOW, -1}, {ADFB_BC_EXTRAP, ADFB_BC_SUPERSONIC_OUTFLOW},
+                                 {ADFB_BC_EULERWALL, -1}, {ADFB_BC_SUPERSONIC_INFLOW, -1}};
+        for (int gq = 0; gq < 8; gq++)
+            for (int q = 0; q < n; q++)
+                if (subs[q].bcType == order[gq][0] || subs[q].bcType == order[gq][1]) item(q, 0);
+    }
     return (int)cudaGetLastError();
 }
 // host image of the device-resident subface list of a block (uploaded by adfb_block_set_bc)

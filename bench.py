@@ -43,6 +43,11 @@ sys.path.insert(0, ROOT)
 C2 = (96, 72, 64)
 # DRAM traffic of one residual step on C2 measured by ncu (profiles/r01d_ncu_summary.md: sum over the six residual kernels)
 NCU_TRAFFIC_BYTES = 568.1e6
+NCU_TRAFFIC_NOTE = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the residual kernels of one step, ncu --set full capture "
+                    "(profiles/)")
+# the second roof (SURVEY section 7 'report both'): the path is FP64-issue bound long before it is HBM bound
+FP64_ROOF = {"note": "B200 FP64 pipe: 64 DFMA lanes / SM / clk x 148 SMs x 1.965 GHz = 18.6 T FP64 instructions/s (37 TFLOP/s); "
+                     "percentages from the ncu capture under profiles/", "fp64_pipe_pct": None, "issue_active_pct": None}
 BYTES_PER_CELL = 176.0  # RANS-SA residual, metrics from x, algorithmic
 METRIC = "Mcells/s RANS-SA residual"
 
@@ -163,47 +168,268 @@ def _ref_worker(args):
     return time.perf_counter() - t0, hb.d.ncells, kind
 
 
+def _split_parts(ncores, ny, nz):
+    """(pj, pk): sub-block grid of the C2 block over the host cores, at least 4 cells per sub-block and direction"""
+    best = (1, 1)
+    for pk in range(1, nz // 4 + 1):
+        for pj in range(1, ny // 4 + 1):
+            if pj * pk <= ncores and pj * pk > best[0] * best[1]:
+                best = (pj, pk)
+    return best
+
+
 def run_reference(args):
-    """--impl reference: CPU restatement of the reference algorithm on all host cores."""
+    """--impl reference: the reference's own blocketteResCore (oracle/_ref; else the oracle port) on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import multiprocessing as mp
 
+    from oracle import refblockette as rb
+
+    if rb.available(fast=True):
+        rb.use_fast(True)   # the parent maps the library too: it is what the workers run (driver-side .so record)
     ncores = len(os.sched_getaffinity(0))
     nx, ny, nz = C2
-    # split the C2 block along k (and j if needed) into one sub-block per core, like
-    # the reference's load balancer splits a block over MPI ranks (loadBalance.F90:2790)
-    parts = min(ncores, nz // 4)
-    ks = [nz * q // parts for q in range(parts + 1)]
-    reps = 3
-    jobs = [((nx, ny, ks[q + 1] - ks[q]), (0, 0, ks[q]), C2, reps, q) for q in range(parts)]
+    # the block is split along j and k into one sub-block per core, like the reference's load balancer splits a block
+    # over MPI ranks (loadBalance.F90:2790); an N-GPU job is compared with N such blocks on the same host cores
+    pj, pk = _split_parts(ncores, ny, nz)
+    parts = pj * pk
+    js = [ny * q // pj for q in range(pj + 1)]
+    ks = [nz * q // pk for q in range(pk + 1)]
+    nblocks = max(1, args.gpus)
+    reps = max(1, 3 // nblocks) if nblocks > 1 else 3
+    jobs = [((nx, js[a + 1] - js[a], ks[q + 1] - ks[q]), (0, js[a], ks[q]), C2, reps * nblocks, q * pj + a) for q in range(pk) for a in range(pj)]
     ctx = mp.get_context("spawn")
     step_ms = []
-    with ctx.Pool(parts) as pool:
+    pool = ctx.Pool(parts)
+    try:
         for _ in range(args.warmup):
             pool.map(_ref_worker, jobs)
         for _ in range(args.steps):
-            t0 = time.perf_counter()
             out = pool.map(_ref_worker, jobs)
             wall = max(o[0] for o in out)  # slowest rank, like an MPI barrier
-            step_ms.append(wall * 1e3 / reps)
-            _ = time.perf_counter() - t0
-    cells = nx * ny * nz
+            step_ms.append(wall * 1e3 / reps)   # one step = one residual of all nblocks blocks
+    finally:
+        pool.close()
+        pool.join()
+    cells = nx * ny * nz * nblocks
     ms = sum(step_ms) / len(step_ms)
     val = cells / (ms * 1e-3) / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mcells/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 96x72x64 RANS-SA residual, block split over host cores"},
+        "config": {"workload": workload_name(C2, nblocks), "cells": cells,
+                   "note": "CPU arm: residual core (blocketteResCore) of %d C2 block(s), each split %d x %d (j x k) over the host cores; "
+                           "the host does not grow with --gpus" % (nblocks, pj, pk)},
         "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": parts, "kind": out[0][2],
-                         "sample": "%d residual evaluations (blocketteResCore) of the C2 block per step, %d sub-blocks "
-                                   "(1 per core, one process each), %s" % (reps, parts, KIND_NOTE[out[0][2]])},
+                         "sample": "%d residual evaluations (blocketteResCore) of %d C2 block(s) per step, %d sub-blocks "
+                                   "(1 per core, one process each, %d host cores visible), %s" % (reps, nblocks, parts, ncores, KIND_NOTE[out[0][2]])},
         "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+def workload_name(shape, nblocks):
+    return "C2 %dx%dx%d RANS-SA residual (blocketteRes), %d block(s)" % (tuple(shape) + (nblocks,))
+
+
+def _event_ms(torch, stream, fn, n):
+    """mean device time of fn over n calls: CUDA events on the library stream"""
+    with torch.cuda.stream(stream):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def _gather_ms(torch, dist, world, ms):
+    """per-rank values and their max"""
+    if world == 1:
+        return [ms], ms
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    v = [float(x[0]) for x in out]
+    return v, max(v)
+
+
+def halo_data_check(s, blocks, pat, np, torch=None, dist=None):
+    """Data-plane check of the 1-to-1 exchange (NCCL between ranks, copies inside a rank): every listed halo cell is
+    poisoned on the device, the library exchanges, and each halo cell must then hold exactly the donor cell's value.
+    The expected values travel independently of the library: same-rank donors are read from the host copy, other ranks'
+    donors are sent with torch.distributed point-to-point in the order of the send lists.  Returns (checked, bad)."""
+    saved = []
+    for q, hb in enumerate(blocks):
+        w0, p0 = hb.w.copy(), hb.p.copy()
+        saved.append((w0, p0))
+        ow = hb.d.owned()
+        wp = np.full_like(hb.w, -7.5e3); pp = np.full_like(hb.p, -7.5e3)
+        wp[ow] = w0[ow]; pp[ow] = p0[ow]
+        hb.w[...] = wp; hb.p[...] = pp
+        s.uploadState(q, hb, with_visc=False)
+    s.haloExchange(comm_viscous=False)
+    got = [s.downloadState(q)[:2] for q in range(len(blocks))]
+
+    def values(src, lst):   # (n, nw+1): w(1:nw), p of the listed cells, list order
+        out = np.empty((len(lst), blocks[0].nw + 1))
+        for q in np.unique(lst[:, 0]):
+            sel = lst[:, 0] == q
+            i, j, k = lst[sel, 1], lst[sel, 2], lst[sel, 3]
+            out[sel, :-1] = src[q][0][i, j, k, :]
+            out[sel, -1] = src[q][1][i, j, k]
+        return out
+
+    checked = bad = 0
+    dl, hl = pat["donorList"].reshape(-1, 4), pat["haloList"].reshape(-1, 4)
+    if len(hl):
+        checked += len(hl)
+        bad += int((values(got, hl) != values(saved, dl)).any(axis=1).sum())
+    sl, rl = pat["sendList"].reshape(-1, 4), pat["recvList"].reshape(-1, 4)
+    if len(pat["nbrRank"]):
+        send_all = torch.from_numpy(values(saved, sl)).cuda()
+        recv_all = torch.empty((len(rl), blocks[0].nw + 1), dtype=torch.float64, device="cuda")
+        ops, so, ro = [], 0, 0
+        for m, peer in enumerate(pat["nbrRank"]):
+            ns, nr = int(pat["sendCount"][m]), int(pat["recvCount"][m])
+            if ns:
+                ops.append(dist.P2POp(dist.isend, send_all[so:so + ns].contiguous(), int(peer)))
+            if nr:
+                ops.append(dist.P2POp(dist.irecv, recv_all[ro:ro + nr], int(peer)))
+            so += ns; ro += nr
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        torch.cuda.synchronize()
+        checked += len(rl)
+        bad += int((values(got, rl) != recv_all.cpu().numpy()).any(axis=1).sum())
+    for q, hb in enumerate(blocks):
+        hb.w[...], hb.p[...] = saved[q]
+        s.uploadState(q, hb)
+    return checked, bad
+
+
+# residual norms of the C3 8-block case after one 5-stage RK cycle from the synthetic state, measured at N = 1 (all
+# eight blocks on one GPU): every other distribution of the same blocks must reproduce them (partition independence,
+# the reference's analogue: tests/reg_tests/test_functionals.py:24-58).  None = not recorded yet.
+C3_REF_NORMS = (1233939870.9755895, 26154234242.979332)   # measured at N = 1 (8 blocks on one B200), round 2
+
+
+def strong_scaling_c3(args, torch, dist, rank, world, local, fresh_uid, np):
+    """BASELINE config 3: 8 blocks x 128x128x64 (2x2x2 arrangement, 1-to-1 halos), 8/N blocks per GPU; a step is one
+    5-stage Runge-Kutta cycle (RungeKuttaSmoother, src/solver/smoothers.F90:4-86) incl. the halo exchanges of every stage."""
+    from adflow_b200 import make_params
+    from adflow_b200.halo import BlockGrid, build_cartesian_pattern, make_grid_blocks
+    from adflow_b200.solver import ADFLOW_B200, RES_FLOW, RES_TURB
+
+    shape = (128, 128, 64)
+    if 8 % world:
+        return {"skipped": "8 blocks do not divide over %d ranks" % world}
+    prm = make_params()
+    grid = BlockGrid((2, 2, 2), shape, nranks=world)
+    blocks = make_grid_blocks(grid, rank, prm)
+    pat = build_cartesian_pattern(grid, rank)
+    s = ADFLOW_B200(prm, device=local, rank=rank, nranks=world, unique_id=fresh_uid())
+    out = {}
+    try:
+        for hb in blocks:
+            s.addBlock(hb)
+        s.setCommPattern(pat)
+        stream = torch.cuda.ExternalStream(s.L.adfb_stream(), device=local)
+        checked, bad = halo_data_check(s, blocks, pat, np, torch, dist)
+        if world > 1:
+            t = torch.tensor([checked, bad], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t)
+            checked, bad = int(t[0]), int(t[1])
+        # partition independence of the result: one cycle from the synthetic state, then the residual norms
+        s.applyBCs(True, True)
+        s.haloExchange()
+        s.timeStep(False)
+        s.smootherResidual(0)
+        s.rkCycle()
+        s.residual(RES_FLOW | RES_TURB)
+        norms = [float(x) for x in s.getResNorms()]
+        ok = bad == 0
+        rel = None
+        if C3_REF_NORMS is not None:
+            rel = max(abs(a - b) / b for a, b in zip(norms, C3_REF_NORMS))
+            ok = ok and rel < 1e-10
+        # timing
+        nrep = max(3, min(10, args.steps))
+        for _ in range(3):
+            s.rkCycle()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = _event_ms(torch, stream, lambda: s.rkCycle(), nrep)
+        per_rank, ms_max = _gather_ms(torch, dist, world, ms)
+        msx = _event_ms(torch, stream, lambda: s.haloExchange(), nrep)
+        per_rank_x, msx_max = _gather_ms(torch, dist, world, msx)
+        cells = 8 * shape[0] * shape[1] * shape[2]
+        out = {
+            "workload": "C3: 8 blocks x 128x128x64 RANS-SA (2x2x2), one 5-stage RK cycle per step incl. 5 halo exchanges",
+            "scaling": "strong", "n_gpus": world, "blocks_per_gpu": 8 // world, "cells": cells,
+            "ms_per_cycle": ms_max, "Mcells/s": cells / (ms_max * 1e-3) / 1e6, "ms_per_rank": per_rank,
+            "exchange_only_ms": msx_max, "exchange_only_ms_per_rank": per_rank_x,
+            "exchange_share_of_cycle": 5.0 * msx_max / ms_max,
+            "halo_check": "ok" if ok else "FAILED",
+            "halo_cells_checked": checked, "halo_cells_wrong": bad,
+            "res_norms_after_one_cycle": norms, "norms_rel_diff_vs_n1": rel,
+            "timing": "CUDA events on the library stream, max over ranks; blocks (1.4 GB each) exceed L2",
+        }
+    finally:
+        s.close()
+    return out
+
+
+def nk_matvec_c5(args, torch, dist, rank, world, local, fresh_uid, np, peak):
+    """BASELINE config 5 (per-GPU share): one 160x160x144 block per GPU (N = 8: the 29.5 M-cell case), matrix-free
+    Jacobian-vector products y = (F(U + h a) - F(U)) / h of the NK solver (FormFunction_mf, NKSolvers.F90:437) with
+    device-resident vectors; a sweep of 60 products, halo exchange inside every residual."""
+    from adflow_b200 import make_params
+    from adflow_b200.halo import BlockGrid, build_cartesian_pattern, make_grid_blocks
+    from adflow_b200.solver import ADFLOW_B200
+
+    shape = (160, 160, 144)
+    prm = make_params()
+    nb = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, (world, 1, 1))
+    grid = BlockGrid(nb, shape, nranks=world)
+    blocks = make_grid_blocks(grid, rank, prm)
+    s = ADFLOW_B200(prm, device=local, rank=rank, nranks=world, unique_id=fresh_uid())
+    try:
+        for hb in blocks:
+            s.addBlock(hb)
+        s.setCommPattern(build_cartesian_pattern(grid, rank))
+        stream = torch.cuda.ExternalStream(s.L.adfb_stream(), device=local)
+        U = s.getStates()
+        s.mffdSetBase(U)
+        da = torch.from_numpy(np.random.default_rng(7 + rank).standard_normal(U.size)).cuda()
+        dy = torch.empty_like(da)
+        for _ in range(3):
+            s.mffdApplyDevice(da.data_ptr(), dy.data_ptr(), da.numel(), 1e-7)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        nmv = 60
+        ms = _event_ms(torch, stream, lambda: s.mffdApplyDevice(da.data_ptr(), dy.data_ptr(), da.numel(), 1e-7), nmv)
+        per_rank, ms_max = _gather_ms(torch, dist, world, ms)
+        finite = bool(torch.isfinite(dy).all())
+        cells = shape[0] * shape[1] * shape[2] * world
+        gbs = 464.0 * cells / (ms_max * 1e-3) / 1e9
+        return {
+            "workload": "C5 share: one 160x160x144 RANS-SA block per GPU, sweep of %d matrix-free Jacobian-vector products, vectors on the GPU" % nmv,
+            "scaling": "weak", "n_gpus": world, "cells": cells, "ms_per_matvec": ms_max, "ms_per_rank": per_rank,
+            "Mcells/s": cells / (ms_max * 1e-3) / 1e6, "GB/s": gbs, "algorithmic_bytes_per_cell": 464.0,
+            "frac_of_hbm_peak": gbs / (peak * world),
+            "frac_of_hbm_peak_fused_272B": 272.0 * cells / (ms_max * 1e-3) / 1e9 / (peak * world),
+            "result_finite": finite,
+        }
+    finally:
+        s.close()
 
 
 def main():
@@ -214,6 +440,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shape", type=int, nargs=3, default=list(C2))
+    ap.add_argument("--no-scaling-sections", action="store_true", help="skip the C3 strong-scaling and C5 matvec sections")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -245,8 +472,10 @@ def main():
     # (wall kMin, symmetry jMin, far field) on the outer faces, 1-to-1 halos inside
     nb = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, (world, 1, 1))
     grid = BlockGrid(nb, shape, nranks=world)
-    uid = None
-    if world > 1:
+    def fresh_uid():
+        """NCCL unique id of a new communicator: rank 0 creates it, torch.distributed carries the 128 bytes"""
+        if world == 1:
+            return None
         L0 = __import__("adflow_b200._lib", fromlist=["load"]).load()
         t = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -254,7 +483,9 @@ def main():
             assert L0.adfb_get_unique_id(buf) == 0
             t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
         dist.broadcast(t, 0)
-        uid = bytes(t.cpu().numpy().tobytes())
+        return bytes(t.cpu().numpy().tobytes())
+
+    uid = fresh_uid()
     blocks = make_grid_blocks(grid, rank, prm)
     s = ADFLOW_B200(prm, device=local, rank=rank, nranks=world, unique_id=uid)
     for hb in blocks:
@@ -446,40 +677,73 @@ def main():
     value = cells * world / (ms_step * 1e-3) / 1e6
     e2e_val = cells * world / (e2e_ms * 1e-3) / 1e6
 
+    # ---- self-check of the multi-block data plane of THIS run (N > 1: NCCL) ---------------------------------------
+    pat_main = build_cartesian_pattern(grid, rank)
+    checked, bad = halo_data_check(s, blocks, pat_main, np, torch, dist if world > 1 else None)
+    s.residual(flags_full)
+    norms_main = [float(x) for x in s.getResNorms()]
+    if world > 1:
+        t = torch.tensor([checked, bad], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        checked, bad = int(t[0]), int(t[1])
+    s.close()
+
+    peak, peak_src = peaks()
+    strong = matvec = None
+    if not args.no_scaling_sections:
+        try:
+            strong = strong_scaling_c3(args, torch, dist if world > 1 else None, rank, world, local, fresh_uid, np)
+        except Exception as ex:  # noqa: BLE001
+            strong = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        try:
+            matvec = nk_matvec_c5(args, torch, dist if world > 1 else None, rank, world, local, fresh_uid, np, peak)
+        except Exception as ex:  # noqa: BLE001
+            matvec = {"error": "%s: %s" % (type(ex).__name__, ex)}
+
     if rank == 0:
-        peak, peak_src = peaks()
         achieved = BYTES_PER_CELL * cells / (res_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2 %dx%dx%d RANS-SA full residual = blocketteRes: p/rlv/rev + BCs + halo exchange + "
-                                   "flow+SA rows with exact fluxes; 1 block per GPU, %s block arrangement" % (shape + ("x".join(map(str, nb)),)),
+            "config": {"workload": workload_name(shape, world), "cells": cells * world,
+                       "detail": "full residual = blocketteRes: p/rlv/rev + BCs + halo exchange + flow+SA rows with exact fluxes; "
+                                 "1 block per GPU, %s block arrangement" % "x".join(map(str, nb)),
                        "cells_per_gpu": cells, "l2": "flushed before every timed step (256 MiB memset)",
                        "timing": "CUDA events on the library stream around each step"},
             "e2e": {"value": e2e_val, "unit": "Mcells/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(nvec * 8), "d2h_bytes_per_step": int(nvec * 8),
                     "path": "adfb_set_states(pinned host) -> adfb_residual(p/rlv/rev preamble + core) -> adfb_get_res(pinned host)"},
             "gpu_launches": int(launches),
+            "halo_check": {"status": "ok" if bad == 0 else "FAILED", "halo_cells_checked": checked, "halo_cells_wrong": bad,
+                           "res_norms": norms_main,
+                           "how": "listed halo cells poisoned on the device, exchanged (NCCL between ranks), compared bit for bit with the "
+                                  "synthetic field of the neighbour block"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_from_step_time": BYTES_PER_CELL * cells / (ms_step * 1e-3) / 1e9 / peak,
+                         "frac_note": "frac: 176 B/cell x cells / SUM of the per-kernel event times of one step (separate timing pass, "
+                                      "side-stream overlap counted twice: conservative); frac_from_step_time: same bytes / ms_per_step",
                          "traffic": NCU_TRAFFIC_BYTES if tuple(shape) == tuple(C2) else None,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the six residual kernels of "
-                                         "one step, ncu --set full capture profiles/r01d_ncu_summary.md (k_faces alone: 229 MB)",
+                         "traffic_note": NCU_TRAFFIC_NOTE,
                          "peak_source": peak_src,
-                         "kernel": "whole residual step: all launches (state prep, BCs, halo pack/unpack, k_prep, k_nodal, "
-                                   "k_resid) charged against 176 B/cell",
-                         "algorithmic_bytes_per_cell": BYTES_PER_CELL, "kernels": kernels},
+                         "kernel": "whole residual step: all launches (state prep, BCs, halo pack/unpack, k_prep, k_flowres tile kernel, "
+                                   "k_sa) charged against 176 B/cell",
+                         "algorithmic_bytes_per_cell": BYTES_PER_CELL, "kernels": kernels,
+                         "second_roof": FP64_ROOF},
             "clocks": clocks,
         }
         if others:
             line["other_operators"] = others
+        if strong is not None:
+            line["strong_scaling_c3"] = strong
+        if matvec is not None:
+            line["nk_matvec_c5"] = matvec
         if not args.no_cpu_baseline:
             v, reps, kind = cpu_baseline_single(shape)
             line["cpu_baseline"] = {"value": v, "unit": "Mcells/s", "cores": 1, "kind": kind,
                                     "sample": "%d residual evaluations (blocketteResCore) of the same block, 1 core, %s"
                                               % (reps, KIND_NOTE[kind])}
         print(json.dumps(line))
-    s.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

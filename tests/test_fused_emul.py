@@ -16,7 +16,7 @@ from util import FLOW, TURB, case, oracle_residual, rel_l2
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emul", "fused_emul.cu")
-SO = os.path.join(HERE, "emul", "libfused_emul.so")
+SO = os.path.join(HERE, "emul", "libfused_emul%s.so" % os.environ.get("FT_EMUL_FLAGS", "").replace("-D", "_").replace("=", "").replace(" ", ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 
@@ -26,8 +26,8 @@ def _build():
         return SO
     if not (os.path.exists(NVCC) or shutil.which("nvcc")):
         pytest.skip("nvcc not available")
-    subprocess.check_call([NVCC, "-O1", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
-                           "-o", SO, SRC])
+    subprocess.check_call([NVCC, "-O1", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-gencode", "arch=compute_100a,code=sm_100a"]
+                          + os.environ.get("FT_EMUL_FLAGS", "").split() + ["-o", SO, SRC])
     return SO
 
 
