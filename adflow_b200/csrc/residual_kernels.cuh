@@ -881,7 +881,12 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
     }
     // tile kernel (fused_kernels.cuh): exact central + scalar-JST (+ viscous) flow rows in one launch
     bool fusedDone = false;
-    if (flowRes && fused_mode() > 0 && !b.coarse && prm.spaceDiscr == ADFB_DISS_SCALAR && !dissApprox && !viscApprox && !initWr &&
+    // (smoother path, persistFw: the tile kernel exchanges central and dissipative fluxes separately with two more CTA
+    // barriers per plane and measured slower than k_nodal/k_faces/k_div there: 1.37 vs 1.28 ms per RK cycle; ADFB_FUSED_SMOOTHER=1
+    // selects it anyway)
+    static int fusedSmoother = -1;
+    if (fusedSmoother < 0) { const char* e = getenv("ADFB_FUSED_SMOOTHER"); fusedSmoother = e ? atoi(e) : 0; }
+    if (flowRes && fused_mode() > 0 && (!persistFw || fusedSmoother) && !b.coarse && prm.spaceDiscr == ADFB_DISS_SCALAR && !dissApprox && !viscApprox && !initWr &&
         !(flags & ADFB_RES_STORE_WALL) && !split_faces()) {
         KT_BEGIN(K_RESID, stream);
         const int rc = launch_flowres_tile(d, b, prm, (int)((b.p - b.w) / d.N), rFil, doDiss, !persistFw, persistFw, stream);

@@ -90,7 +90,12 @@ __device__ __forceinline__ void bc_turb_cell(const Dims& d, const BlockDev& b, c
     if (secondHalo) { nt[c0] = v1; b.rev[c0] = r1; }
 }
 
-// phase: 1 = symmetry first halo, 2 = symmetry second halo, 0 = everything else
+// phase: 1 = symmetry first halo, 2 = symmetry second halo, 0 = everything else.
+// Register form: the interior states are read once, the halo states are built in registers (total energy and the
+// second-halo extrapolation included) and stored once -- the reference's routines re-read what they just wrote
+// (computeEtot, extrapolate2ndHalo: BCRoutines.F90:1870-1918), which on the device is a chain of dependent global
+// round trips per subface; the arithmetic and its order are unchanged.
+struct BcCellState { double r, u, v, w, e, p, rlv, rev; };
 __device__ __forceinline__ void bc_flow_cell(const Dims& d, const BlockDev& b, const FaceDev& f, int ia, int jb, int secondHalo, int phase) {
     const long long N = d.N;
     const long long q = ia * f.sa + jb * f.sb;
@@ -102,191 +107,166 @@ __device__ __forceinline__ void bc_flow_cell(const Dims& d, const BlockDev& b, c
     const bool viscous = c_prm.equations != ADFB_EULER, eddy = c_prm.equations == ADFB_RANS;
     const double gam = c_prm.gammaInf;
     double* w = b.w;
-    switch (f.bcType) {
-        case ADFB_BC_SYMM: {  // bcSymm1stHalo / bcSymm2ndHalo, BCRoutines.F90:223-340
-            const long long ch = phase == 1 ? c1 : c0, ci = phase == 1 ? c2 : c3;
-            const double u = w[N + ci], v = w[2 * N + ci], ww = w[3 * N + ci];
-            const double vn = 2.0 * (u * n1 + v * n2 + ww * n3);
-            w[ch] = w[ci];
-            w[N + ch] = u - vn * n1;
-            w[2 * N + ch] = v - vn * n2;
-            w[3 * N + ch] = ww - vn * n3;
-            w[4 * N + ch] = w[4 * N + ci];
-            b.p[ch] = b.p[ci];
-            if (viscous) b.rlv[ch] = b.rlv[ci];
-            if (eddy) b.rev[ch] = b.rev[ci];
-            break;
-        }
-        case ADFB_BC_SYMMPOLAR: {  // bcSymmPolar1stHalo / 2ndHalo, BCRoutines.F90:332-486
-            const long long ch = phase == 1 ? c1 : c0, ci = phase == 1 ? c2 : c3;
+    auto load = [&](long long c) {
+        BcCellState s;
+        s.r = w[c]; s.u = w[N + c]; s.v = w[2 * N + c]; s.w = w[3 * N + c]; s.e = w[4 * N + c]; s.p = b.p[c];
+        s.rlv = viscous ? b.rlv[c] : 0.0;
+        s.rev = eddy ? b.rev[c] : 0.0;
+        return s;
+    };
+    auto store = [&](long long c, const BcCellState& s) {
+        w[c] = s.r; w[N + c] = s.u; w[2 * N + c] = s.v; w[3 * N + c] = s.w; w[4 * N + c] = s.e; b.p[c] = s.p;
+        if (viscous) b.rlv[c] = s.rlv;
+        if (eddy) b.rev[c] = s.rev;
+    };
+    auto etot = [&](BcCellState& s) {   // computeEtot (cpConstant)
+        const double ovgm1 = 1.0 / (c_prm.gammaInf - 1.0);
+        s.e = ovgm1 * s.p + 0.5 * s.r * (s.u * s.u + s.v * s.v + s.w * s.w);
+    };
+    if (f.bcType == ADFB_BC_SYMM || f.bcType == ADFB_BC_SYMMPOLAR) {
+        // bcSymm1stHalo / bcSymm2ndHalo, BCRoutines.F90:223-340; bcSymmPolar1stHalo / 2ndHalo, :332-486
+        const BcCellState si = load(phase == 1 ? c2 : c3);
+        BcCellState sh = si;
+        if (f.bcType == ADFB_BC_SYMM) {
+            const double vn = 2.0 * (si.u * n1 + si.v * n2 + si.w * n3);
+            sh.u = si.u - vn * n1; sh.v = si.v - vn * n2; sh.w = si.w - vn * n3;
+        } else {
             const long long nA = f.xoff + q, nB = f.xoff + (ia - 1) * f.sa + (jb - 1) * f.sb;
             double nnx = b.x[nA] - b.x[nB], nny = b.x[N + nA] - b.x[N + nB], nnz = b.x[2 * N + nA] - b.x[2 * N + nB];
             double tmp = 1.0 / sqrt(nnx * nnx + nny * nny + nnz * nnz);
             nnx = nnx * tmp; nny = nny * tmp; nnz = nnz * tmp;
-            const double u = w[N + ci], v = w[2 * N + ci], ww = w[3 * N + ci];
-            tmp = 2.0 * (u * nnx + v * nny + ww * nnz);
-            w[ch] = w[ci];
-            w[N + ch] = tmp * nnx - u;
-            w[2 * N + ch] = tmp * nny - v;
-            w[3 * N + ch] = tmp * nnz - ww;
-            w[4 * N + ch] = w[4 * N + ci];
-            b.p[ch] = b.p[ci];
-            if (viscous) b.rlv[ch] = b.rlv[ci];
-            if (eddy) b.rev[ch] = b.rev[ci];
-            break;
+            tmp = 2.0 * (si.u * nnx + si.v * nny + si.w * nnz);
+            sh.u = tmp * nnx - si.u; sh.v = tmp * nny - si.v; sh.w = tmp * nnz - si.w;
         }
+        store(phase == 1 ? c1 : c0, sh);
+        return;
+    }
+    const BcCellState s2 = load(c2);
+    BcCellState s1 = s2;   // rlv1 = rlv2, rev1 = rev2 unless changed below
+    switch (f.bcType) {
         case ADFB_BC_NSWALL_ADIABATIC: {  // bcNSWallAdiabatic, BCRoutines.F90:489-578
             double us1 = 0.0, us2 = 0.0, us3 = 0.0;
             if (f.uSlip) { us1 = f.uSlip[o]; us2 = f.uSlip[o + na * nb]; us3 = f.uSlip[o + 2 * na * nb]; }
-            w[c1] = w[c2];
-            w[N + c1] = -w[N + c2] + 2.0 * us1;
-            w[2 * N + c1] = -w[2 * N + c2] + 2.0 * us2;
-            w[3 * N + c1] = -w[3 * N + c2] + 2.0 * us3;
-            b.rlv[c1] = b.rlv[c2];
-            if (eddy) b.rev[c1] = -b.rev[c2];
+            s1.u = -s2.u + 2.0 * us1; s1.v = -s2.v + 2.0 * us2; s1.w = -s2.w + 2.0 * us3;
+            s1.rev = -s2.rev;
             if (c_prm.wallBCConstantPressure || b.coarse) {   // BCRoutines.F90:550,642: coarse levels use constant pressure
-                b.p[c1] = b.p[c2];
+                s1.p = s2.p;
             } else {
-                double p1 = 2.0 * b.p[c2] - b.p[c3];
-                if (p1 <= 0.0) p1 = b.p[c2];
-                b.p[c1] = p1;
+                double p1 = 2.0 * s2.p - b.p[c3];
+                if (p1 <= 0.0) p1 = s2.p;
+                s1.p = p1;
             }
-            bc_etot(b, N, c1);
-            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
             break;
         }
         case ADFB_BC_NSWALL_ISOTHERMAL: {  // bcNSWallIsoThermal, BCRoutines.F90:579-691
             double us1 = 0.0, us2 = 0.0, us3 = 0.0;
             if (f.uSlip) { us1 = f.uSlip[o]; us2 = f.uSlip[o + na * nb]; us3 = f.uSlip[o + 2 * na * nb]; }
             const double tw = f.TNSWall[o];
-            const double t2 = b.p[c2] / (c_prm.RGas * w[c2]);
+            const double t2 = s2.p / (c_prm.RGas * s2.r);
             double t1 = 2.0 * tw - t2;
             t1 = dmax_(0.5 * tw, t1);
             t1 = dmin_(2.0 * tw, t1);
             double p1;
-            if (c_prm.wallBCConstantPressure || b.coarse) {   // BCRoutines.F90:550,642: coarse levels use constant pressure
-                p1 = b.p[c2];
+            if (c_prm.wallBCConstantPressure || b.coarse) {
+                p1 = s2.p;
             } else {
-                p1 = 2.0 * b.p[c2] - b.p[c3];
-                if (p1 <= 0.0) p1 = b.p[c2];
+                p1 = 2.0 * s2.p - b.p[c3];
+                if (p1 <= 0.0) p1 = s2.p;
             }
-            b.p[c1] = p1;
-            w[c1] = p1 / (c_prm.RGas * t1);
-            w[N + c1] = -w[N + c2] + 2.0 * us1;
-            w[2 * N + c1] = -w[2 * N + c2] + 2.0 * us2;
-            w[3 * N + c1] = -w[3 * N + c2] + 2.0 * us3;
-            b.rlv[c1] = b.rlv[c2];
-            if (eddy) b.rev[c1] = -b.rev[c2];
-            bc_etot(b, N, c1);
-            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            s1.p = p1;
+            s1.r = p1 / (c_prm.RGas * t1);
+            s1.u = -s2.u + 2.0 * us1; s1.v = -s2.v + 2.0 * us2; s1.w = -s2.w + 2.0 * us3;
+            s1.rev = -s2.rev;
             break;
         }
         case ADFB_BC_EXTRAP:
         case ADFB_BC_SUPERSONIC_OUTFLOW: {  // bcExtrap, BCRoutines.F90:1479-1570
             double fw2 = 2.0, fw3 = -1.0;   // extrap: linear; supersonic outflow: outflowTreatment
             if (f.bcType == ADFB_BC_SUPERSONIC_OUTFLOW && !c_prm.outflowLinearExtrapol) { fw2 = 1.0; fw3 = 0.0; }
-            double r1 = fw2 * w[c2] + fw3 * w[c3];
-            r1 = dmax_(0.5 * w[c2], r1);
-            w[c1] = r1;
-            w[N + c1] = fw2 * w[N + c2] + fw3 * w[N + c3];
-            w[2 * N + c1] = fw2 * w[2 * N + c2] + fw3 * w[2 * N + c3];
-            w[3 * N + c1] = fw2 * w[3 * N + c2] + fw3 * w[3 * N + c3];
-            double p1 = fw2 * b.p[c2] + fw3 * b.p[c3];
-            p1 = dmax_(0.5 * b.p[c2], p1);
-            b.p[c1] = p1;
-            if (viscous) b.rlv[c1] = b.rlv[c2];
-            if (eddy) b.rev[c1] = b.rev[c2];
-            bc_etot(b, N, c1);
-            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            const double r3 = w[c3], u3 = w[N + c3], v3 = w[2 * N + c3], w3 = w[3 * N + c3], p3 = b.p[c3];
+            double r1 = fw2 * s2.r + fw3 * r3;
+            r1 = dmax_(0.5 * s2.r, r1);
+            s1.r = r1;
+            s1.u = fw2 * s2.u + fw3 * u3;
+            s1.v = fw2 * s2.v + fw3 * v3;
+            s1.w = fw2 * s2.w + fw3 * w3;
+            double p1 = fw2 * s2.p + fw3 * p3;
+            p1 = dmax_(0.5 * s2.p, p1);
+            s1.p = p1;
             break;
         }
         case ADFB_BC_SUBSONIC_OUTFLOW: {  // bcSubsonicOutflow, BCRoutines.F90:693-802
             const double pExit = f.ps[o];
             const double ovg = 1.0 / gam, ovgm1 = 1.0 / (gam - 1.0);
-            const double pInt = b.p[c2];
-            const double r = 1.0 / w[c2];
+            const double pInt = s2.p;
+            const double r = 1.0 / s2.r;
             const double a2 = gam * pInt * r;
             double a = sqrt(a2);
-            const double ue = w[N + c2], ve = w[2 * N + c2], we = w[3 * N + c2];
+            const double ue = s2.u, ve = s2.v, we = s2.w;
             const double qne = ue * n1 + ve * n2 + we * n3;
             const double ss = pInt * pow(r, gam);
             const double ac = qne + 2.0 * a * ovgm1;
             const double r1 = pow(pExit / ss, ovg);
-            w[c1] = r1;
-            b.p[c1] = pExit;
+            s1.r = r1;
+            s1.p = pExit;
             a = sqrt(gam * pExit / r1);
             const double qnh = ac - 2.0 * a * ovgm1;
-            w[N + c1] = ue + (qnh - qne) * n1;
-            w[2 * N + c1] = ve + (qnh - qne) * n2;
-            w[3 * N + c1] = we + (qnh - qne) * n3;
-            if (viscous) b.rlv[c1] = b.rlv[c2];
-            if (eddy) b.rev[c1] = b.rev[c2];
-            bc_etot(b, N, c1);
-            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            s1.u = ue + (qnh - qne) * n1;
+            s1.v = ve + (qnh - qne) * n2;
+            s1.w = we + (qnh - qne) * n3;
             break;
         }
         case ADFB_BC_SUBSONIC_INFLOW: {  // bcSubsonicInflow, BCRoutines.F90:804-1061 (cpConstant)
             const double gm1 = gam - 1.0, ovgm1 = 1.0 / gm1;
-            const double r = 1.0 / w[c2];
-            double a2 = gam * b.p[c2] * r;
-            double beta = w[N + c2] * n1 + w[2 * N + c2] * n2 + w[3 * N + c2] * n3 + 2.0 * ovgm1 * sqrt(a2);
+            const double r = 1.0 / s2.r;
+            double a2 = gam * s2.p * r;
+            double beta = s2.u * n1 + s2.v * n2 + s2.w * n3 + 2.0 * ovgm1 * sqrt(a2);
             if (f.inletTreatment == 1) {   // totalConditions
                 const double govgm1 = gam / (gam - 1.0);
                 const double ptot = f.ptInlet[o], ttot = f.ttInlet[o], htot = f.htInlet[o];
                 const double ssx = f.fxd[o], ssy = f.fyd[o], ssz = f.fzd[o];
                 double scaleFact = 1.0;
-                if (c_prm.hScalingInlet) scaleFact = sqrt(htot / (r * (w[4 * N + c2] + b.p[c2])));
+                if (c_prm.hScalingInlet) scaleFact = sqrt(htot / (r * (s2.e + s2.p)));
                 beta = beta * scaleFact;
-                double q2 = w[N + c2] * w[N + c2] + w[2 * N + c2] * w[2 * N + c2] + w[3 * N + c2] * w[3 * N + c2];
-                const double a2tot = gm1 * (htot - r * (w[4 * N + c2] + b.p[c2]) + 0.5 * q2) + a2;
+                double q2 = s2.u * s2.u + s2.v * s2.v + s2.w * s2.w;
+                const double a2tot = gm1 * (htot - r * (s2.e + s2.p) + 0.5 * q2) + a2;
                 const double alpha = n1 * ssx + n2 * ssy + n3 * ssz;
                 const double aa2 = 0.5 * gm1 * alpha * alpha + 1.0;
                 const double bb = -gm1 * alpha * beta;
                 const double cc = 0.5 * gm1 * beta * beta - 2.0 * ovgm1 * a2tot;
                 double dd = bb * bb - 4.0 * aa2 * cc;
                 dd = sqrt(dmax_(0.0, dd));
-                double q = (-bb + dd) / (2.0 * aa2);
-                q = dmax_(0.0, q);
-                q2 = q * q;
+                double qq = (-bb + dd) / (2.0 * aa2);
+                qq = dmax_(0.0, qq);
+                q2 = qq * qq;
                 a2 = a2tot - 0.5 * gm1 * q2;
                 double m2 = q2 / a2;
                 m2 = dmin_(1.0, m2);
                 q2 = m2 * a2;
-                q = sqrt(q2);
+                qq = sqrt(q2);
                 a2 = a2tot - 0.5 * gm1 * q2;
-                w[N + c1] = q * ssx; w[2 * N + c1] = q * ssy; w[3 * N + c1] = q * ssz;
+                s1.u = qq * ssx; s1.v = qq * ssy; s1.w = qq * ssz;
                 const double ts = a2 / (gam * c_prm.RGas);
                 const double ratio = pow(ts / ttot, govgm1);
-                b.p[c1] = ptot * ratio;
-                w[c1] = (ptot * ratio) / (c_prm.RGas * ts);
+                s1.p = ptot * ratio;
+                s1.r = (ptot * ratio) / (c_prm.RGas * ts);
             } else {                        // massFlow
                 const double rho = f.rho[o], velx = f.velx[o], vely = f.vely[o], velz = f.velz[o];
                 a2 = 0.5 * gm1 * (beta - velx * n1 - vely * n2 - velz * n3);
                 a2 = dmax_(0.0, a2);
                 a2 = a2 * a2;
-                b.p[c1] = rho * a2 / gam;
-                w[c1] = rho; w[N + c1] = velx; w[2 * N + c1] = vely; w[3 * N + c1] = velz;
+                s1.p = rho * a2 / gam;
+                s1.r = rho; s1.u = velx; s1.v = vely; s1.w = velz;
             }
-            if (viscous) b.rlv[c1] = b.rlv[c2];
-            if (eddy) b.rev[c1] = b.rev[c2];
-            bc_etot(b, N, c1);
-            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
             break;
         }
         case ADFB_BC_SUPERSONIC_INFLOW: {  // bcSupersonicInflow, BCRoutines.F90:1411-1477
-            w[c1] = f.rho[o]; w[N + c1] = f.velx[o]; w[2 * N + c1] = f.vely[o]; w[3 * N + c1] = f.velz[o];
-            b.p[c1] = f.ps[o];
-            if (viscous) b.rlv[c1] = b.rlv[c2];
-            if (eddy) b.rev[c1] = b.rev[c2];
-            bc_etot(b, N, c1);
-            if (secondHalo) {
-                w[c0] = f.rho[o]; w[N + c0] = f.velx[o]; w[2 * N + c0] = f.vely[o]; w[3 * N + c0] = f.velz[o];
-                b.p[c0] = f.ps[o];
-                if (viscous) b.rlv[c0] = b.rlv[c1];
-                if (eddy) b.rev[c0] = b.rev[c1];
-                bc_etot(b, N, c0);
-            }
-            break;
+            s1.r = f.rho[o]; s1.u = f.velx[o]; s1.v = f.vely[o]; s1.w = f.velz[o];
+            s1.p = f.ps[o];
+            etot(s1);
+            store(c1, s1);
+            if (secondHalo) store(c0, s1);   // same prescribed state, rlv/rev of the first halo, same total energy
+            return;
         }
         case ADFB_BC_FARFIELD: {  // bcFarfield, BCRoutines.F90:1282-1396
             const double gm1 = gam - 1.0, ovgm1 = 1.0 / gm1;
@@ -295,10 +275,10 @@ __device__ __forceinline__ void bc_flow_cell(const Dims& d, const BlockDev& b, c
             const double s0 = pow(c_prm.wInf[0], gam) / c_prm.pInfCorr;
             const double qn0 = u0 * n1 + v0 * n2 + w0 * n3;
             const double vn0 = qn0 - rface;
-            const double rho2 = w[c2];
-            const double re = 1.0 / rho2, ue = w[N + c2], ve = w[2 * N + c2], we = w[3 * N + c2];
+            const double rho2 = s2.r;
+            const double re = 1.0 / rho2, ue = s2.u, ve = s2.v, we = s2.w;
             const double qne = ue * n1 + ve * n2 + we * n3;
-            const double p2 = b.p[c2];
+            const double p2 = s2.p;
             const double ce = sqrt(gam * p2 * re);
             double ac1, ac2;
             if (vn0 > -c0s) ac1 = qne + 2.0 * ovgm1 * ce; else ac1 = qn0 + 2.0 * ovgm1 * c0s;
@@ -315,28 +295,31 @@ __device__ __forceinline__ void bc_flow_cell(const Dims& d, const BlockDev& b, c
             }
             const double cc = cf * cf / gam;
             const double r1 = pow(sfv * cc, ovgm1);
-            w[c1] = r1; w[N + c1] = uf; w[2 * N + c1] = vf; w[3 * N + c1] = wf;
-            b.p[c1] = r1 * cc;
-            if (viscous) b.rlv[c1] = b.rlv[c2];
-            if (eddy) b.rev[c1] = b.rev[c2];
-            bc_etot(b, N, c1);
-            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            s1.r = r1; s1.u = uf; s1.v = vf; s1.w = wf;
+            s1.p = r1 * cc;
             break;
         }
         case ADFB_BC_EULERWALL: {  // bcEulerWall, BCRoutines.F90:1063-1280 (constant / linear pressure)
-            const double grad = (c_prm.reserved || b.coarse) ? 0.0 : b.p[c3] - b.p[c2];   // BCRoutines.F90:1100
-            b.p[c1] = dmax_(b.p[c2] - grad, 0.0);
-            const double u = w[N + c2], v = w[2 * N + c2], ww = w[3 * N + c2];
-            const double vn = 2.0 * (rface - u * n1 - v * n2 - ww * n3);
-            w[c1] = w[c2];
-            w[N + c1] = u + vn * n1; w[2 * N + c1] = v + vn * n2; w[3 * N + c1] = ww + vn * n3;
-            if (viscous) b.rlv[c1] = b.rlv[c2];
-            if (eddy) b.rev[c1] = b.rev[c2];
-            bc_etot(b, N, c1);
-            if (secondHalo) bc_extrap2(b, N, c0, c1, c2);
+            const double grad = (c_prm.reserved || b.coarse) ? 0.0 : b.p[c3] - s2.p;   // BCRoutines.F90:1100
+            s1.p = dmax_(s2.p - grad, 0.0);
+            const double vn = 2.0 * (rface - s2.u * n1 - s2.v * n2 - s2.w * n3);
+            s1.u = s2.u + vn * n1; s1.v = s2.v + vn * n2; s1.w = s2.w + vn * n3;
             break;
         }
-        default: break;
+        default: return;
+    }
+    etot(s1);
+    store(c1, s1);
+    if (secondHalo) {   // extrapolate2ndHalo, BCRoutines.F90:1870-1918
+        BcCellState s0;
+        s0.r = dmax_(0.5 * s1.r, 2.0 * s1.r - s2.r);
+        s0.u = 2.0 * s1.u - s2.u;
+        s0.v = 2.0 * s1.v - s2.v;
+        s0.w = 2.0 * s1.w - s2.w;
+        s0.p = dmax_(0.5 * s1.p, 2.0 * s1.p - s2.p);
+        s0.rlv = s1.rlv; s0.rev = s1.rev;
+        etot(s0);
+        store(c0, s0);
     }
 }
 
@@ -374,6 +357,15 @@ struct BcList {
     int n;
     int la[ADFB_BC_MAXSUB], lb[ADFB_BC_MAXSUB];   // owned upper index of the two in-plane directions (il/jl/kl)
     FaceDev f[ADFB_BC_MAXSUB];
+    unsigned counters[2];   // k_bc_chain: tickets handed out, CTAs finished (zero between launches)
+};
+// the ordered (subface, kind) items of one BC sweep: kind 3 = turbulence BC, else the flow phase (1 / 2: symmetry first /
+// second halo, 0: everything else); begin[q] = first CTA ticket of item q
+#define ADFB_BC_MAXITEMS (4 * ADFB_BC_MAXSUB + 4)
+struct BcItems {
+    int n, total;
+    short sub[ADFB_BC_MAXITEMS], kind[ADFB_BC_MAXITEMS];
+    int begin[ADFB_BC_MAXITEMS + 1];
 };
 
 __device__ __forceinline__ void bc_all_cell(const Dims& d, const BlockDev& b, const FaceDev& f, int ia, int jb, int secondHalo,
@@ -453,6 +445,54 @@ __global__ void __launch_bounds__(256) k_bc_frame(Dims d, BlockDev b, const BcLi
             else bc_flow_cell(d, b, f, ia, jb, secondHalo, kind);
         }
         __syncthreads();
+    }
+}
+
+// The whole ordered BC sweep of a block in ONE launch.  The reference applies the subfaces one after the other
+// (applyAllTurbBCThisBlock, then applyAllBC_block in its BC-class order, BCRoutines.F90:81-216), and the edge / corner
+// halos depend on that order, so the items stay strictly ordered -- but the hand-over from one item to the next is a
+// device-side counter instead of a kernel boundary (~6 us per dependent launch inside a graph): a CTA draws a ticket,
+// which names its item and its 32 x 4 patch of the subface, waits until every CTA of all earlier items has finished
+// (tickets are handed out in start order, so everything a CTA waits for is already running: no deadlock whatever the
+// dispatch order), applies the BC, and publishes its completion.
+__device__ __forceinline__ unsigned bc_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(128) k_bc_chain(Dims d, BlockDev b, BcList* Lp, BcItems it, int secondHalo) {
+    ADFB_PDL_SYNC();
+    __shared__ int sTicket;
+    BcList& L = *Lp;
+    const bool t0 = threadIdx.x == 0 && threadIdx.y == 0;
+    if (t0) sTicket = (int)atomicAdd(&L.counters[0], 1u);
+    __syncthreads();
+    const int ticket = sTicket;
+    int q = 0;
+    while (q + 1 < it.n && ticket >= it.begin[q + 1]) q++;
+    const int local = ticket - it.begin[q];
+    const FaceDev& f = L.f[it.sub[q]];
+    const int kind = it.kind[q];
+    const int na = f.icEnd - f.icBeg + 1;
+    const int nbx = (na + 31) / 32;
+    const int ia = (local % nbx) * 32 + threadIdx.x + f.icBeg, jb = (local / nbx) * 4 + threadIdx.y + f.jcBeg;
+    if (t0) {
+        while (bc_ld_acquire(&L.counters[1]) < (unsigned)it.begin[q]) __nanosleep(40);
+    }
+    __syncthreads();
+    if (ia <= f.icEnd && jb <= f.jcEnd) {
+        if (kind == 3) bc_turb_cell(d, b, f, ia, jb, secondHalo);
+        else bc_flow_cell(d, b, f, ia, jb, secondHalo, kind);
+    }
+    __threadfence();
+    __syncthreads();
+    if (t0) {
+        const unsigned old = atomicAdd(&L.counters[1], 1u);
+        if ((int)old + 1 == it.total) {   // last CTA of the sweep: every ticket has been drawn, rearm the counters
+            L.counters[0] = 0u;
+            L.counters[1] = 0u;
+            __threadfence();
+        }
     }
 }
 
@@ -699,7 +739,10 @@ __global__ void __launch_bounds__(256) k_wall_forces(Dims d, BlockDev b, FaceDev
 
 }  // namespace
 
-// ADFB_BC_FUSED: 0 (default) = one launch per subface and phase over all of its cells; 1 = one launch for the
+// ADFB_BC_FUSED: 0 (default) = one launch per subface and phase over all of its cells, chained by programmatic dependent
+// launch (13 launches of ~5 us for the bench block); 3 = the whole ordered sweep in one launch, items ordered by a device-side
+// counter (k_bc_chain: parity-clean, but the ticket / fence / counter hand-over costs 5.3 us per item, measured 69 us per sweep
+// against 65 us for the launch chain); 1 = one launch for the
 // order-independent cells of all subfaces, then the ordered frame items as small launches (round 2: 14 launches of
 // ~6 us each inside the graph, slower than 13 and not parity-clean: experiment only); 2 = bulk launch + one CTA
 // walking the frame items (measured slower in round 1)
@@ -712,6 +755,39 @@ static int bc_mode() {
 static int launch_bc_fused(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, int secondHalo, int withTurb, int withFlow,
                            cudaStream_t s) {
     if (!bc_mode() || subs.empty() || (int)subs.size() > ADFB_BC_MAXSUB || !b.bcList) return -1;
+    if (bc_mode() == 3) {
+        BcItems it;
+        memset(&it, 0, sizeof it);
+        int tot = 0;
+        auto item = [&](int q, int kind) {
+            const AdfbSubface& sf = subs[q];
+            const int na = sf.icEnd - sf.icBeg + 1, nb = sf.jcEnd - sf.jcBeg + 1;
+            it.sub[it.n] = (short)q; it.kind[it.n] = (short)kind; it.begin[it.n] = tot;
+            tot += ((na + 31) / 32) * ((nb + 3) / 4);
+            it.n++;
+        };
+        const int n = (int)subs.size();
+        if (withTurb) for (int q = 0; q < n; q++) item(q, 3);
+        if (withFlow) {
+            for (int q = 0; q < n; q++) if (subs[q].bcType == ADFB_BC_SYMM) item(q, 1);
+            if (secondHalo) for (int q = 0; q < n; q++) if (subs[q].bcType == ADFB_BC_SYMM) item(q, 2);
+            for (int q = 0; q < n; q++) if (subs[q].bcType == ADFB_BC_SYMMPOLAR) item(q, 1);
+            if (secondHalo) for (int q = 0; q < n; q++) if (subs[q].bcType == ADFB_BC_SYMMPOLAR) item(q, 2);
+            const int order[8][2] = {{ADFB_BC_NSWALL_ADIABATIC, -1}, {ADFB_BC_NSWALL_ISOTHERMAL, -1}, {ADFB_BC_FARFIELD, -1},
+                                     {ADFB_BC_SUBSONIC_OUTFLOW, -1}, {ADFB_BC_SUBSONIC_INFLOW, -1}, {ADFB_BC_EXTRAP, ADFB_BC_SUPERSONIC_OUTFLOW},
+                                     {ADFB_BC_EULERWALL, -1}, {ADFB_BC_SUPERSONIC_INFLOW, -1}};
+            for (int gq = 0; gq < 8; gq++)
+                for (int q = 0; q < n; q++)
+                    if (subs[q].bcType == order[gq][0] || subs[q].bcType == order[gq][1]) item(q, 0);
+        }
+        if (it.n == 0) return 0;
+        it.begin[it.n] = tot;
+        it.total = tot;
+        KT_BEGIN(K_BC, s);
+        launch_pdl(k_bc_chain, dim3((unsigned)tot), dim3(32, 4), s, d, b, (BcList*)b.bcList, it, secondHalo);
+        KT_END(K_BC, s);
+        return (int)cudaGetLastError();
+    }
     int ma = 1, mb = 1;
     for (const AdfbSubface& sf : subs) {
         const int la = (sf.faceId == ADFB_IMIN || sf.faceId == ADFB_IMAX) ? d.jl : d.il;
