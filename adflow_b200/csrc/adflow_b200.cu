@@ -252,7 +252,14 @@ int run_graphed(unsigned long long key, F body) {
     g_kt.launches += g.graphLaunches[key];
     return 0;
 }
+// the cached per-pattern variable tables hold raw block pointers and the variable selection of the equation set:
+// they go whenever blocks or parameters change (the allocations stay with the pattern until it is reset)
+void drop_comm_tables() {
+    for (auto* m : {&g.pats, &g.ovPats})
+        for (auto& kv : *m) kv.second.tabs.clear();
+}
 void drop_graphs() {
+    drop_comm_tables();
     for (auto& kv : g.graphs) cudaGraphExecDestroy(kv.second);
     g.graphs.clear();
     g.graphLaunches.clear();
@@ -296,17 +303,20 @@ int adfb_init(int device, const void* ncclUniqueId, int rank, int nranks) {
     if (!g.stream) CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     g.device = device; g.rank = rank; g.nranks = nranks;
     if (!g.hRed) CK(cudaMallocHost((void**)&g.hRed, 256 * sizeof(double)));
-    g.ready = true;
     g.err.clear();
+    if (g.comm) { g.nccl.CommDestroy(g.comm); g.comm = nullptr; }   // re-init: the previous communicator goes
     if (nranks > 1) {
+        g.ready = false; g.nranks = 1;   // a failing NCCL set-up must not leave a multi-rank context without a communicator
         if (!ncclUniqueId) return fail("adfb_init: nranks > 1 needs the 128-byte NCCL unique id of rank 0");
         std::string e;
         if (!g.nccl.load(e)) return fail("adfb_init: %s", e.c_str());
         Id128 id;
         memcpy(id.b, ncclUniqueId, 128);
         const int rc = g.nccl.CommInitRank(&g.comm, nranks, id, rank);
-        if (rc != 0) return fail("ncclCommInitRank: %s", g.nccl.GetErrorString(rc));
+        if (rc != 0) { g.comm = nullptr; return fail("ncclCommInitRank: %s", g.nccl.GetErrorString(rc)); }
+        g.nranks = nranks;
     }
+    g.ready = true;
     return 0;
 }
 
@@ -322,7 +332,8 @@ int adfb_finalize(void) {
     if (g.dVec) cudaFree(g.dVec);
     g.dVec = nullptr; g.dVecN = 0;
     for (double** p : {&g.nkA, &g.nkU, &g.nkF0, &g.nkY}) { if (*p) cudaFree(*p); *p = nullptr; }
-    g.nkN = 0; g.nkHaveBase = false;
+    g.nkN = 0;
+    g.nkHaveBase = false; g.ankHaveBase = false;   // the base vectors went with the buffers g.nkHaveBase = false;
     // ANK / Krylov state belongs to the context as well: a later adfb_init starts from scratch
     for (double** p : {&g.ankT, &g.ankPert, &g.kryV, &g.kryRed}) { if (*p) cudaFree(*p); *p = nullptr; }
     g.ankTN = 0; g.ankPertN = 0; g.kryVN = 0;
@@ -870,6 +881,12 @@ int adfb_halo_exchange(int level, int start, int end, int commPressure, int comm
 
 static int residual_body(int level, unsigned flags);
 static void set_l2_window();
+// an overset pattern with entries exists on this level: whalo2 then really changes rhoE of fringe cells
+// (computeEtotBlock after wOverset, haloExchange.F90:174-197), so the owned-cell etot pass is not idempotent
+static bool overset_present(int level) {
+    auto it = g.ovPats.find(level);
+    return it != g.ovPats.end() && it->second.set && (it->second.nSend || it->second.nRecv || it->second.nInt);
+}
 int adfb_residual(int level, unsigned flags) {
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_residual: adfb_set_params has not been called");
@@ -931,7 +948,17 @@ static int residual_body(int level, unsigned flags) {
         const int nwLoc = g.prm.equations == ADFB_RANS ? 6 : 5;
         const bool fr = flags & ADFB_RES_FLOW, tr = (flags & ADFB_RES_TURB) && nwLoc == 6;
         const int lStart = fr ? 1 : 6, lEnd = tr ? 6 : 5;
-        if (halo_exchange_impl(level, lStart, lEnd, 1, 1, false)) return 1;
+        const bool ov = overset_present(level);
+        if (halo_exchange_impl(level, lStart, lEnd, 1, 1, ov)) return 1;
+        if (ov) {
+            // blocketteRes re-applies the turbulence and flow BCs on every block after whalo2 when overset blocks are
+            // present (blockette.F90:252-262): boundary halos next to fringe cells see the interpolated values
+            for (Block& b : g.blocks) {
+                if (!b.alive || b.level != level) continue;
+                if (launch_bc_all(b.d, b.dev, b.subfaces, 1, g.prm.equations == ADFB_RANS && (flags & ADFB_RES_TURB), g.stream))
+                    return fail("BC launch failed");
+            }
+        }
     }
     for (Block& b : g.blocks) {
         if (!b.alive || b.level != level) continue;
@@ -949,6 +976,7 @@ static int nk_buffers(long long need) {
     if (g.nkN >= (size_t)need) return 0;
     for (double** p : {&g.nkA, &g.nkU, &g.nkF0, &g.nkY}) { if (*p) cudaFree(*p); *p = nullptr; }
     g.nkN = 0;
+    g.nkHaveBase = false; g.ankHaveBase = false;   // the base vectors went with the buffers
     for (double** p : {&g.nkA, &g.nkU, &g.nkF0, &g.nkY}) CK(cudaMalloc((void**)p, need * sizeof(double)));
     if (!g.dRed) { CK(cudaMalloc((void**)&g.dRed, (2 * 1024 + 2) * sizeof(double))); g.dRedN = 2 * 1024 + 2; }
     g.nkN = need;
@@ -1019,6 +1047,7 @@ int adfb_mffd_set_base(const double* U, long long n) {
     if (nk_sumsq(g.nkU, need, &uu)) return 1;
     g.nkUnorm = sqrt(uu);
     g.nkHaveBase = true;
+    g.ankHaveBase = false;   // the ANK base shares the buffers
     return 0;
 }
 
@@ -1164,8 +1193,8 @@ static int adfb_rk_stage_body(int level, int rkStage) {
         if (launch_bc_flow(b.d, b.dev, b.subfaces, level > 1 ? 0 : 1, g.stream)) return fail("flow BC launch failed");
     }
     // whalo2(level, 1, nwf, T, T, T) / whalo1 on coarse levels (the pattern of the level holds the matching lists):
-    // the trailing computeEtotBlock is idempotent here
-    if (halo_exchange_impl(level, 1, 5, 1, 1, false)) return 1;
+    // the trailing computeEtotBlock is idempotent here unless an overset pattern interpolates into fringe cells
+    if (halo_exchange_impl(level, 1, 5, 1, 1, overset_present(level))) return 1;
     CK(cudaGetLastError());
     return 0;
 }
@@ -1188,7 +1217,7 @@ static int adfb_dadi_step_body(int level) {
         if (launch_dadi_update(b.d, b.dev, prmL, g.stream, level > 1 ? 5 : 0)) return fail("DADI update launch failed");
         if (launch_bc_flow(b.d, b.dev, b.subfaces, level > 1 ? 0 : 1, g.stream)) return fail("flow BC launch failed");
     }
-    if (halo_exchange_impl(level, 1, 5, 1, 1, false)) return 1;
+    if (halo_exchange_impl(level, 1, 5, 1, 1, overset_present(level))) return 1;
     CK(cudaGetLastError());
     return 0;
 }
@@ -1600,7 +1629,7 @@ static int adfb_mg_prolong_body(int fineLevel) {
         // applyAllBC(secondHalo): second halos on the ground level only
         if (launch_bc_flow(f.d, f.dev, f.subfaces, fineLevel > 1 ? 0 : 1, g.stream)) return fail("flow BC launch failed");
     }
-    if (halo_exchange_impl(fineLevel, 1, 5, 1, 1, false)) return 1;
+    if (halo_exchange_impl(fineLevel, 1, 5, 1, 1, overset_present(fineLevel))) return 1;
     CK(cudaGetLastError());
     return 0;
 }
@@ -1782,7 +1811,8 @@ int adfb_gmres_solve(int op, const double* rhs, double* x, long long n, int rest
             for (int i = 0; i <= j; i++) H[(size_t)i + (size_t)(m + 1) * j] = hcol[i];
             its++;
             rnorm = fabs(gg[j + 1]);
-            if (rnorm <= target || den == 0.0) { j++; break; }
+            if (den == 0.0) break;   // exact breakdown with a zero column: solve with the first j columns only
+            if (rnorm <= target) { j++; break; }
         }
         // y = H^-1 g (upper triangular), x += M^-1 (V y)
         const int k = j;
@@ -1790,7 +1820,9 @@ int adfb_gmres_solve(int op, const double* rhs, double* x, long long n, int rest
         for (int i = k - 1; i >= 0; i--) {
             double t = gg[i];
             for (int l = i + 1; l < k; l++) t -= H[(size_t)i + (size_t)(m + 1) * l] * y[l];
-            y[i] = t / H[(size_t)i + (size_t)(m + 1) * i];
+            const double hii = H[(size_t)i + (size_t)(m + 1) * i];
+            if (hii == 0.0) return fail("adfb_gmres_solve: singular Hessenberg matrix (breakdown at column %d)", i);
+            y[i] = t / hii;
         }
         GmresCoef cy = {};
         for (int i = 0; i < k; i++) cy.c[i] = y[i];

@@ -101,3 +101,45 @@ def test_overset_exchange_two_gpus_nccl(cuda_lib):
         for l in (0, 1, 2, 3, 5):
             assert _close(got[b][0][..., l], ref[b].w[..., l]), (b, l)
         assert _close(got[b][1], ref[b].p)
+
+
+def test_residual_with_overset_pattern_matches_oracle(cuda_lib):
+    """blocketteRes with overset blocks present (src/NKSolver/blockette.F90:213-262): p/rlv/rev, BCs, whalo2 = overset
+    interpolation followed by computeEtotBlock on the owned cells (the fringe rhoE follows the interpolated p, rho, u),
+    then the turbulence and flow BCs AGAIN on every block, then the residual core -- composed from the oracle's pieces
+    and compared with adfb_residual."""
+    import ctypes as C
+
+    from adflow_b200.solver import RES_FLOW, RES_TURB
+    from oracle.pyoracle import Oracle
+
+    from util import rel_l2
+
+    prm = make_params()
+    blocks = two_blocks(prm)
+    pat = build_overset_pattern(overset_entries())
+    ref = [b.copy() for b in blocks]
+    orcs = [Oracle(b, prm) for b in ref]
+    for o in orcs:
+        o.pressure(False); o.lam_viscosity(False); o.eddy_viscosity(False)
+        o.apply_turb_bc(True); o.apply_flow_bc(True)
+    exchange_numpy_overset(ref, pat, VARS)
+    for o, b in zip(orcs, ref):
+        d = b.d
+        o.L.orc_etot(C.byref(o.ob), C.byref(prm), 2, d.il, 2, d.jl, 2, d.kl)
+        o.apply_turb_bc(True); o.apply_flow_bc(True)
+        o.residual_core(RES_FLOW | RES_TURB)
+    s = ADFLOW_B200(prm)
+    try:
+        for hb in blocks:
+            s.addBlock(hb)
+        s.setOversetPattern(pat)
+        s.residual(RES_FLOW | RES_TURB)
+        for q, b in enumerate(ref):
+            dw = s.downloadResidual(q)
+            ow = b.d.owned()
+            for l in range(6):
+                err = rel_l2(dw[ow + (l,)], b.dw[ow + (l,)])
+                assert err < 1e-11, (q, l, err)   # the 8-term interpolation sums differ by FMA contraction (a few ulp)
+    finally:
+        s.close()
