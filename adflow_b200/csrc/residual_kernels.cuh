@@ -75,12 +75,18 @@ __global__ void __launch_bounds__(256) k_geom(Dims d, BlockDev b) {
 // ---------------------------------------------------------------------------
 // k_prep: entropy (inviscidDissFluxScalar, blockette.F90:3055-3089), speed of sound squared
 // (:5168-5203), spectral radii and local time step (timeStep, :1899-2148).
-__global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, int doRad) {
+// part: 0 = every box cell, 1 = owned cells without a halo neighbour (3:nx, ...: the pressure switch of dtl reads the six
+// neighbours), 2 = the rest (the first part does not need the BCs and runs beside them, see residual_body)
+__global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, int doRad, int part) {
     ADFB_PDL_SYNC();  // launched with programmatic stream serialization (launch_pdl)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int k = blockIdx.z * blockDim.z + threadIdx.z;
     if (i > d.ib || j > d.jb || k > d.kb) return;
+    if (part) {
+        const bool inner = i >= 3 && i < d.il && j >= 3 && j < d.jl && k >= 3 && k < d.kl;
+        if (inner != (part == 1)) return;
+    }
     const int N = (int)d.N, sJ = (int)d.sJ, sK = (int)d.sK;
     const int c = i + sJ * j + sK * k;
     const double gam = c_prm.gammaInf;
@@ -723,11 +729,17 @@ __device__ __forceinline__ double sa_source(const BlockDev& b, int N, int sJ, in
 
 // k_sa: SA row of one owned cell: source, advection k/j/i, diffusion k/j/i, scaling
 // (blockette.F90:623-627, :1872-1897)
-__global__ void __launch_bounds__(SA_TPB, SA_MINB) k_sa(Dims d, BlockDev b) {
+// part: 0 = every owned cell, 1 = cells at least two layers away from the block boundary (their stencil holds no halo
+// cell: they do not need the BCs / the exchange), 2 = the boundary shell
+__global__ void __launch_bounds__(SA_TPB, SA_MINB) k_sa(Dims d, BlockDev b, int part) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
     if (i > d.il || j > d.jl || k > d.kl) return;
+    if (part) {
+        const bool inner = i >= 4 && i <= d.il - 2 && j >= 4 && j <= d.jl - 2 && k >= 4 && k <= d.kl - 2;
+        if (inner != (part == 1)) return;
+    }
     const int N = (int)d.N, sJ = (int)d.sJ, sK = (int)d.sK;
     const int c = i + sJ * j + sK * k;
     const double rblank = dmax_((double)b.iblank[c], 0.0);
@@ -827,8 +839,9 @@ static bool split_faces() {
     if (v < 0) { const char* e = getenv("ADFB_SPLIT_FACES"); v = e ? atoi(e) : 0; }
     return v != 0;
 }
+enum { RC_PREP_OWNED = 1, RC_PREP_HALO = 2, RC_SA_INNER = 4, RC_SA_SHELL = 8, RC_FLOW = 16, RC_ALL = 31 };
 static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbParams& prm, unsigned flags, double rFil,
-                                int persistFw, int doRad, cudaStream_t stream, int initWr = 0) {
+                                int persistFw, int doRad, cudaStream_t stream, int initWr = 0, int parts = RC_ALL) {
     const int flowRes = (flags & ADFB_RES_FLOW) != 0;
     const int turbRes = ((flags & ADFB_RES_TURB) != 0) && prm.equations == ADFB_RANS;
     const int updateDt = 1;  // blockette timeStep always computes dtl (blockette.F90:1929-1932)
@@ -851,8 +864,9 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         const char* e = getenv("ADFB_SA_CONCURRENT");
         s_conc = e ? atoi(e) : 1;
     }
-    const bool fork = turbRes && flowRes && s_conc && !g_kt.on;
-    if (turbRes) {
+    const int saPart = ((parts & RC_SA_INNER) && (parts & RC_SA_SHELL)) ? 0 : (parts & RC_SA_INNER) ? 1 : 2;
+    const bool fork = turbRes && flowRes && s_conc && !g_kt.on && (parts & RC_FLOW);
+    if (turbRes && (parts & (RC_SA_INNER | RC_SA_SHELL))) {
         dim3 tr = tune_block("ADFB_SA_BLOCK", dim3(32, 4, 1));
         dim3 g((d.nx + tr.x - 1) / tr.x, (d.ny + tr.y - 1) / tr.y, (d.nz + tr.z - 1) / tr.z);
         if (fork) {
@@ -864,22 +878,24 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
             cudaStreamCopyAttributes(s_side, stream);   // same L2 access-policy window as the main stream
             cudaEventRecord(s_fork, stream);
             cudaStreamWaitEvent(s_side, s_fork, 0);
-            k_sa<<<g, tr, 0, s_side>>>(d, b);
+            k_sa<<<g, tr, 0, s_side>>>(d, b, saPart);
             g_kt.launches++; g_kt.count[K_SA]++;
             cudaEventRecord(s_join, s_side);
         } else {
             KT_BEGIN(K_SA, stream);
-            k_sa<<<g, tr, 0, stream>>>(d, b);
+            k_sa<<<g, tr, 0, stream>>>(d, b, saPart);
             KT_END(K_SA, stream);
         }
     }
-    if (doRad || (flowRes && doDiss)) {
+    if ((doRad || (flowRes && doDiss)) && (parts & (RC_PREP_OWNED | RC_PREP_HALO))) {
+        const int prepPart = ((parts & RC_PREP_OWNED) && (parts & RC_PREP_HALO)) ? 0 : (parts & RC_PREP_OWNED) ? 1 : 2;
         dim3 g((d.NI + tb.x - 1) / tb.x, (d.NJ + tb.y - 1) / tb.y, (d.NK + tb.z - 1) / tb.z);
         KT_BEGIN(K_PREP, stream);
-        launch_pdl(k_prep, g, tb, stream, d, b, updateDt, doRad);
+        launch_pdl(k_prep, g, tb, stream, d, b, updateDt, doRad, prepPart);
         KT_END(K_PREP, stream);
     }
     // tile kernel (fused_kernels.cuh): exact central + scalar-JST (+ viscous) flow rows in one launch
+    if (!(parts & RC_FLOW)) return (int)cudaGetLastError();
     bool fusedDone = false;
     // (smoother path, persistFw: the tile kernel exchanges central and dissipative fluxes separately with two more CTA
     // barriers per plane and measured slower than k_nodal/k_faces/k_div there: 1.37 vs 1.28 ms per RK cycle; ADFB_FUSED_SMOOTHER=1

@@ -677,6 +677,107 @@ __global__ void __launch_bounds__(64) k_resavg_sweep(Dims d, BlockDev b, int dir
     }
 }
 
+// residualAveraging along one direction with the whole solve in shared memory: a CTA takes LPC grid lines and the 5
+// variables (LPC x 5 threads).
+//   A  all threads copy the lines' epz and dw into shared memory, consecutive threads along the direction that is
+//      contiguous in HBM (the line itself for i lines, the line index for j / k lines): every global access coalesced
+//   B  one thread per line factorises: t(i) = 1 / (1 + epz(i) + epz(i-1) - epz(i-1) d(i-1)), d(i) = t(i) epz(i) -- once
+//      per line instead of once per (line, variable), the only chain with a division
+//   C  one thread per (line, variable): forward sweep v(i) = t(i) (dw(i) + epz(i-1) v(i-1)) and back substitution
+//      v(i) += d(i) v(i+1), in place in shared memory (two-FMA chains)
+//   D  coalesced copy back to dw
+// HBM traffic 88 B per cell and direction (epz + dw in, dw out) instead of 192 B with the forward-swept values in
+// global memory, and the serial walks never wait for HBM.  Same operations on the same operands as k_resavg_sweep.
+#define ADFB_RA_THREADS 768   // copy phases: enough loads in flight to fill the SM's share of HBM bandwidth
+// lines are numbered id = (q1 - 2) + n1 (q2 - 2); a CTA takes LPC consecutive ids (LPC is sized on the host so that the
+// grid is one wave of the SMs), LP = padded pitch of the shared arrays (odd: conflict free along and across the lines)
+__global__ void __launch_bounds__(ADFB_RA_THREADS) k_resavg_lines(Dims d, BlockDev b, int dir, long long sd, int n, long long s1, int n1,
+                                                                  long long s2, int n2, int LPC, int LP) {
+    ADFB_PDL_SYNC();
+    extern __shared__ double ra_sm[];
+    double* T = ra_sm;                          // [n][LP]
+    double* D = T + (size_t)n * LP;
+    double* E = D + (size_t)n * LP;
+    double* F = E + (size_t)n * LP;             // [5][n][LP]
+    long long* lineBase = reinterpret_cast<long long*>(F + (size_t)5 * n * LP);   // [LPC] box offset of cell 0 of the line minus 2 sd
+    const int tid = threadIdx.x, nT = blockDim.x;
+    const int lane = tid % LPC, m = tid / LPC;   // solve phases: the first LPC * 5 threads
+    const int id0 = blockIdx.x * LPC;
+    const int nLines = min(LPC, n1 * n2 - id0);
+    if (tid < nLines) {
+        const int id = id0 + tid;
+        lineBase[tid] = (long long)(id % n1 + 2) * s1 + (long long)(id / n1 + 2) * s2 + 2 * sd;
+    }
+    __syncthreads();
+    const long long N = d.N;
+    const double* __restrict__ epzA = b.flux + (1 + dir) * N;
+    const bool alongLine = sd == 1;   // i lines: the cells of a line are contiguous
+    // ---- A: load
+    const int total = n * nLines;
+    for (int e = tid; e < total; e += nT) {
+        const int i = alongLine ? e % n : e / nLines, ln = alongLine ? e / n : e % nLines;
+        const long long c = lineBase[ln] + i * sd;
+        E[i * LP + ln] = epzA[c];
+#pragma unroll
+        for (int v = 0; v < 5; v++) F[((size_t)v * n + i) * LP + ln] = b.dw[v * N + c];
+    }
+    __syncthreads();
+    // ---- B: factorisation, one thread per line
+    if (m == 0 && lane < nLines) {
+        double epzm = 0.0, dm = 0.0;   // epz(1) = d(1) = 0
+#pragma unroll 8
+        for (int i = 0; i < n; i++) {
+            const double epz = E[i * LP + lane];
+            const double t = 1.0 / (1.0 + epz + epzm - epzm * dm);
+            const double dd = t * epz;
+            T[i * LP + lane] = t; D[i * LP + lane] = dd;
+            epzm = epz; dm = dd;
+        }
+    }
+    __syncthreads();
+    // ---- C: forward sweep and back substitution of one (line, variable)
+    if (m < 5 && lane < nLines) {
+        double* f = F + (size_t)m * n * LP + lane;
+        double dwm = 0.0, epzm = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < n; i++) {
+            const double v = T[i * LP + lane] * (f[i * LP] + epzm * dwm);
+            f[i * LP] = v;
+            dwm = v; epzm = E[i * LP + lane];
+        }
+#pragma unroll 8
+        for (int i = n - 2; i >= 0; i--) {
+            const double v = f[i * LP] + D[i * LP + lane] * dwm;
+            f[i * LP] = v;
+            dwm = v;
+        }
+    }
+    __syncthreads();
+    // ---- D: store
+    for (int e = tid; e < total; e += nT) {
+        const int i = alongLine ? e % n : e / nLines, ln = alongLine ? e / n : e % nLines;
+        const long long c = lineBase[ln] + i * sd;
+#pragma unroll
+        for (int v = 0; v < 5; v++) b.dw[v * N + c] = F[((size_t)v * n + i) * LP + ln];
+    }
+}
+
+// lines per CTA of the shared-memory line kernels: one wave of one CTA per SM if the lines fit, else the largest count
+// that fits (nArr arrays of n x LP doubles + the line table)
+static int lines_per_cta(long long nLinesTotal, int n, int nArr, int maxLpc, size_t lim, int* LPout, size_t* bytesOut) {
+    static int nSM = 0;
+    if (!nSM) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev); }
+    auto bytes = [&](int lpc) { const int LP = lpc | 1; return (size_t)nArr * n * LP * sizeof(double) + (size_t)lpc * sizeof(long long); };
+    int lpc = (int)((nLinesTotal + nSM - 1) / nSM);
+    if (lpc < 4) lpc = (int)(nLinesTotal < 4 ? nLinesTotal : 4);
+    if (lpc > maxLpc) lpc = maxLpc;
+    while (lpc > 1 && bytes(lpc) > lim) lpc--;
+    if (bytes(lpc) > lim) return 0;
+    *LPout = lpc | 1;
+    *bytesOut = bytes(lpc);
+    return lpc;
+}
+
 // wallIntegrationFace, force and moment part (src/solver/surfaceIntegrations.F90:406-881): one CTA per wall
 // subface; every thread sums its face cells in index order, then a fixed-order tree reduction, so the result
 // is run-to-run reproducible.  acc = Fp(3), Fv(3), Mp(3), Mv(3).
@@ -916,10 +1017,27 @@ static int launch_residual_averaging(const Dims& d, const BlockDev& b, const Adf
         KT_END(K_RK, s);
     }
     dim3 tb(32, 2);
+    static int smemLines = -1;   // ADFB_RESAVG_SMEM=0: the thread-per-(line, variable) walk through global memory
+    if (smemLines < 0) { const char* e = getenv("ADFB_RESAVG_SMEM"); smemLines = e ? atoi(e) : 1; }
     auto run = [&](int dir, long long sd, int n, long long s1, int n1, long long s2, int n2) {
         if (n <= 1) return;
         KT_BEGIN(K_RK, s);
-        launch_pdl(k_resavg_sweep, dim3((n1 + 31) / 32, (n2 + 1) / 2, 5), tb, s, d, b, dir, sd, n, s1, n1, s2, n2);
+        const size_t lim = 220 * 1024;
+        int LP = 0; size_t smem = 0;
+        const int lpc = !smemLines ? 0 : lines_per_cta((long long)n1 * n2, n, 8, ADFB_RA_THREADS / 5, lim, &LP, &smem);
+        if (lpc) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(((long long)n1 * n2 + lpc - 1) / lpc)); cfg.blockDim = dim3(ADFB_RA_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            static bool once = false;
+            if (!once) { cudaFuncSetAttribute(k_resavg_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim); once = true; }
+            cudaLaunchKernelEx(&cfg, k_resavg_lines, d, b, dir, sd, n, s1, n1, s2, n2, lpc, LP);
+        } else {
+            launch_pdl(k_resavg_sweep, dim3((n1 + 31) / 32, (n2 + 1) / 2, 5), tb, s, d, b, dir, sd, n, s1, n1, s2, n2);
+        }
         KT_END(K_RK, s);
     };
     run(0, 1, d.nx, d.sJ, d.ny, d.sK, d.nz);
