@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler is attached
 #include "../../include/adflow_b200.h"
 
 struct Dims {
@@ -134,8 +135,14 @@ static inline int adfb_part_lanes(int nl) {
     if (nl > 128 && nl <= 256) return 16;
     return 0;
 }
-#define KT_BEGIN(id, stream) g_kt.begin(id, stream)
-#define KT_END(id, stream) g_kt.end(id, stream)
+// every launch site sits in an NVTX range named after its kernel family (tracing)
+#define KT_BEGIN(id, stream) do { nvtxRangePushA(kKernelNames[id]); g_kt.begin(id, stream); } while (0)
+#define KT_END(id, stream) do { g_kt.end(id, stream); nvtxRangePop(); } while (0)
+struct AdfbRange {   // NVTX range of one C-ABI entry point
+    explicit AdfbRange(const char* name) { nvtxRangePushA(name); }
+    ~AdfbRange() { nvtxRangePop(); }
+};
+#define ADFB_RANGE(name) AdfbRange adfb_range_(name)
 
 // ---------------------------------------------------------------------------
 // Launch with the programmatic-dependent-launch attribute (the kernel must call

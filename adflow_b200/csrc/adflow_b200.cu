@@ -771,17 +771,46 @@ int adfb_comm_set_overset(int level, int nNbr, const int* nbrRank, const int* se
 
 // whalo1to1 part of whalo2/whalo1 for the variable selection of setCommPointers
 // (src/utils/haloExchange.F90:356-470)
-static int halo_exchange_impl(int level, int start, int end, int commPressure, int commViscous, bool etotOwned) {
+// phase 0: the whole exchange on the compute stream.  Phases 1 / 2 split it so that the transfer overlaps the boundary
+// conditions (the reference posts its receives and sends, then copies locally, then waits: haloExchange.F90:620-716):
+//   1 "post"   : pack the send lists of the 1-to-1 pattern (owned cells only: the BCs that follow do not touch them) and
+//                run the grouped ncclSend/ncclRecv on the communication stream
+//   2 "finish" : join the communication stream, same-rank copies, unpack, then the overset pattern and the owned-cell
+//                total energy -- after the BCs, like the un-split order (edge halos of the BCs read the OLD interface halos)
+static cudaStream_t g_commStream = nullptr;
+static cudaEvent_t g_evPost = nullptr, g_evDone = nullptr;
+static bool halo_split_ok(int level) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("ADFB_HALO_OVERLAP"); on = e ? atoi(e) : 1; }
+    if (!on || g_kt.on || g.nranks < 2) return false;
+    auto it = g.pats.find(level);
+    return it != g.pats.end() && it->second.set && !it->second.nbrRank.empty();
+}
+static int halo_exchange_impl(int level, int start, int end, int commPressure, int commViscous, bool etotOwned, int phase = 0) {
     const bool viscous = g.prm.equations != ADFB_EULER, eddy = g.prm.equations == ADFB_RANS;
     // whalo1to1 with commPatternCell_2nd / internalCell_2nd, then wOverset with commPatternOverset / internalOverset
     // (whalo2, haloExchange.F90:139-146); orphan averaging is not supported (nOrphans must be 0)
     Context::Pattern* both[2] = {nullptr, nullptr};
     { auto it = g.pats.find(level); if (it != g.pats.end()) both[0] = &it->second; }
     { auto it = g.ovPats.find(level); if (it != g.ovPats.end()) both[1] = &it->second; }
+    if (phase && !g_commStream) {
+        CK(cudaStreamCreateWithFlags(&g_commStream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&g_evPost, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g_evDone, cudaEventDisableTiming));
+    }
     for (Context::Pattern* PP : both) {
         if (!PP) continue;
         Context::Pattern& P = *PP;
         if (!(P.set && (P.nSend || P.nRecv || P.nInt))) continue;
+        const bool oneToOne = PP == both[0];
+        if (phase == 1 && !oneToOne) continue;           // the overset pattern is exchanged in one piece by "finish"
+        const bool doPost = phase == 0 || phase == 1 || !oneToOne;      // pack + send/recv
+        const bool doFinish = phase == 0 || phase == 2;                  // local copies + unpack
+        cudaStream_t cs = (phase == 1) ? g_commStream : g.stream;        // stream of pack + NCCL
+        if (phase == 1) {
+            CK(cudaEventRecord(g_evPost, g.stream));
+            CK(cudaStreamWaitEvent(g_commStream, g_evPost, 0));
+        }
         if ((int)g.blocks.size() != P.tabBlocks) return fail("halo exchange: blocks changed after adfb_comm_set_pattern");
         const int key = start | (end << 4) | ((commPressure ? 1 : 0) << 8) | ((commViscous ? 1 : 0) << 9);
         int nVar = 0;
@@ -818,27 +847,30 @@ static int halo_exchange_impl(int level, int start, int end, int commPressure, i
             dTab = (CommVarTable*)q;
             P.tabs[key] = dTab;
         }
-        if (P.nSend) {
+        if (doPost && P.nSend) {
             const long long n = P.nSend * nVar;
-            KT_BEGIN(K_HALO, g.stream);
+            KT_BEGIN(K_HALO, cs);
             if (P.interp)
-                k_halo_pack_interp<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.sBlk, P.sOff, P.sCum, P.sLocal, P.sCount, P.sSJ, P.sSK,
-                                                                                     P.sW, dTab, nVar, P.nSend, P.sendBuf);
+                k_halo_pack_interp<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(P.sBlk, P.sOff, P.sCum, P.sLocal, P.sCount, P.sSJ, P.sSK,
+                                                                               P.sW, dTab, nVar, P.nSend, P.sendBuf);
             else
-                k_halo_pack<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.sBlk, P.sOff, P.sCum, P.sLocal, P.sCount, dTab, nVar, P.nSend, P.sendBuf);
-            KT_END(K_HALO, g.stream);
+                k_halo_pack<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>(P.sBlk, P.sOff, P.sCum, P.sLocal, P.sCount, dTab, nVar, P.nSend, P.sendBuf);
+            KT_END(K_HALO, cs);
         }
-        if (!P.nbrRank.empty()) {
+        if (doPost && !P.nbrRank.empty()) {
             int rc = g.nccl.GroupStart();
             long long so = 0, ro = 0;
             for (size_t m = 0; m < P.nbrRank.size() && rc == 0; m++) {
-                if (P.sendCount[m]) rc = g.nccl.Send(P.sendBuf + so * nVar, (size_t)P.sendCount[m] * nVar, kNcclDouble, P.nbrRank[m], g.comm, g.stream);
-                if (rc == 0 && P.recvCount[m]) rc = g.nccl.Recv(P.recvBuf + ro * nVar, (size_t)P.recvCount[m] * nVar, kNcclDouble, P.nbrRank[m], g.comm, g.stream);
+                if (P.sendCount[m]) rc = g.nccl.Send(P.sendBuf + so * nVar, (size_t)P.sendCount[m] * nVar, kNcclDouble, P.nbrRank[m], g.comm, cs);
+                if (rc == 0 && P.recvCount[m]) rc = g.nccl.Recv(P.recvBuf + ro * nVar, (size_t)P.recvCount[m] * nVar, kNcclDouble, P.nbrRank[m], g.comm, cs);
                 so += P.sendCount[m]; ro += P.recvCount[m];
             }
             const int rc2 = g.nccl.GroupEnd();
             if (rc != 0 || rc2 != 0) return fail("NCCL halo exchange: %s", g.nccl.GetErrorString(rc ? rc : rc2));
         }
+        if (phase == 1) { CK(cudaEventRecord(g_evDone, g_commStream)); continue; }
+        if (phase == 2 && oneToOne) CK(cudaStreamWaitEvent(g.stream, g_evDone, 0));
+        if (!doFinish) continue;
         if (P.nInt) {
             const long long n = P.nInt * nVar;
             KT_BEGIN(K_HALO, g.stream);
@@ -857,7 +889,7 @@ static int halo_exchange_impl(int level, int start, int end, int commPressure, i
         }
     }
     // bothPAndE: computeEtotBlock(2, il, 2, jl, 2, kl) on every block (haloExchange.F90:174-197)
-    if (etotOwned && commPressure && start <= 5 && end >= 5) {
+    if (phase != 1 && etotOwned && commPressure && start <= 5 && end >= 5) {
         for (Block& b : g.blocks) {
             if (!b.alive || b.level != level) continue;
             dim3 tb(32, 4, 2);
@@ -872,6 +904,7 @@ static int halo_exchange_impl(int level, int start, int end, int commPressure, i
 }
 
 int adfb_halo_exchange(int level, int start, int end, int commPressure, int commGamma, int commViscous) {
+    ADFB_RANGE("adfb_halo_exchange");
     NEED_INIT();
     (void)commGamma;  // gamma is constant (cpConstant): commVarGamma is always false, haloExchange.F90:146
     if (!g.havePrm) return fail("adfb_halo_exchange: adfb_set_params has not been called");
@@ -888,6 +921,7 @@ static bool overset_present(int level) {
     return it != g.ovPats.end() && it->second.set && (it->second.nSend || it->second.nRecv || it->second.nInt);
 }
 int adfb_residual(int level, unsigned flags) {
+    ADFB_RANGE("adfb_residual");
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_residual: adfb_set_params has not been called");
     if (!(flags & (ADFB_RES_FLOW | ADFB_RES_TURB))) return fail("adfb_residual: neither flow nor turbulence residual requested");
@@ -965,18 +999,21 @@ static int residual_body(int level, unsigned flags) {
             }
             CK(cudaEventRecord(eJoin, s2));
         }
+        // whalo2(1, lStart, lEnd, T, T, T), blockette.F90:231-246; the owned-cell
+        // computeEtotBlock of whalo2 is fused into k_state_prep.  Multi-rank: the send lists (owned cells)
+        // are packed and sent while the BC chain runs; the halos are written after it.
+        const int nwLoc = g.prm.equations == ADFB_RANS ? 6 : 5;
+        const bool fr = flags & ADFB_RES_FLOW, tr = (flags & ADFB_RES_TURB) && nwLoc == 6;
+        const int lStart = fr ? 1 : 6, lEnd = tr ? 6 : 5;
+        const bool ov = overset_present(level);
+        const bool split = halo_split_ok(level);
+        if (split && halo_exchange_impl(level, lStart, lEnd, 1, 1, ov, 1)) return 1;
         for (Block& b : g.blocks) {
             if (!b.alive || b.level != level) continue;
             if (launch_bc_all(b.d, b.dev, b.subfaces, 1, g.prm.equations == ADFB_RANS && (flags & ADFB_RES_TURB), g.stream))
                 return fail("BC launch failed");
         }
-        // whalo2(1, lStart, lEnd, T, T, T), blockette.F90:231-246; the owned-cell
-        // computeEtotBlock of whalo2 is fused into k_state_prep
-        const int nwLoc = g.prm.equations == ADFB_RANS ? 6 : 5;
-        const bool fr = flags & ADFB_RES_FLOW, tr = (flags & ADFB_RES_TURB) && nwLoc == 6;
-        const int lStart = fr ? 1 : 6, lEnd = tr ? 6 : 5;
-        const bool ov = overset_present(level);
-        if (halo_exchange_impl(level, lStart, lEnd, 1, 1, ov)) return 1;
+        if (halo_exchange_impl(level, lStart, lEnd, 1, 1, ov, split ? 2 : 0)) return 1;
         if (ov) {
             // blocketteRes re-applies the turbulence and flow BCs on every block after whalo2 when overset blocks are
             // present (blockette.F90:252-262): boundary halos next to fringe cells see the interpolated values
@@ -1047,6 +1084,7 @@ static const unsigned kNkFlags = ADFB_RES_FLOW | ADFB_RES_TURB;
 
 // FormFunction_mf (NKSolvers.F90:437-461): setW(wVec); computeResidualNK; setRVec(rVec)
 int adfb_form_function(const double* wVec, double* rVec, long long n) {
+    ADFB_RANGE("adfb_form_function");
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_form_function: adfb_set_params has not been called");
     const long long need = adfb_state_size();
@@ -1063,6 +1101,7 @@ int adfb_form_function(const double* wVec, double* rVec, long long n) {
 
 // MatMFFDSetBase(dRdw, wVec, baseRes) (NKSolvers.F90:628-630): U <- wVec, F0 <- F(U) on the device
 int adfb_mffd_set_base(const double* U, long long n) {
+    ADFB_RANGE("adfb_mffd_set_base");
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_mffd_set_base: adfb_set_params has not been called");
     const long long need = adfb_state_size();
@@ -1101,6 +1140,7 @@ static int mffd_core(long long need, double h) {
     return 0;
 }
 int adfb_mffd_apply(const double* a, double* y, long long n, double h) {
+    ADFB_RANGE("adfb_mffd_apply");
     NEED_INIT();
     if (!g.nkHaveBase) return fail("adfb_mffd_apply: adfb_mffd_set_base has not been called");
     const long long need = adfb_state_size();
@@ -1120,6 +1160,7 @@ int adfb_mffd_apply(const double* a, double* y, long long n, double h) {
 // the same product for Krylov vectors that already live on THIS device (PETSc VECCUDA: VecCUDAGetArrayRead /
 // VecCUDAGetArrayWrite): no PCIe traffic; the result is complete when the call returns
 int adfb_mffd_apply_device(const double* aDev, double* yDev, long long n, double h) {
+    ADFB_RANGE("adfb_mffd_apply_device");
     NEED_INIT();
     if (!g.nkHaveBase) return fail("adfb_mffd_apply_device: adfb_mffd_set_base has not been called");
     const long long need = adfb_state_size();
@@ -1156,6 +1197,7 @@ int adfb_reference_shock_sensor(int level) {
 
 // applyAllBC (+ turbulence halos), src/solver/BCRoutines.F90:57, turbBCRoutines.F90:49
 int adfb_apply_bcs(int level, int secondHalo, int withTurb) {
+    ADFB_RANGE("adfb_apply_bcs");
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_apply_bcs: adfb_set_params has not been called");
     for (Block& b : g.blocks) {
@@ -1167,6 +1209,7 @@ int adfb_apply_bcs(int level, int secondHalo, int withTurb) {
 
 // timeStep(onlyRadii), src/solver/solverUtils.F90:43-355 (fine level, directional scaling)
 int adfb_timestep(int level, int onlyRadii) {
+    ADFB_RANGE("adfb_timestep");
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_timestep: adfb_set_params has not been called");
     for (Block& b : g.blocks) {
@@ -1202,6 +1245,7 @@ static int adfb_smoother_residual_body(int level, int rkStage) {
     return 0;
 }
 int adfb_smoother_residual(int level, int rkStage) {
+    ADFB_RANGE("adfb_smoother_residual");
     NEED_INIT();
     const unsigned long long key = (3ull << 40) | ((unsigned long long)level << 32) | ((unsigned)g.mgInitWr << 8) | (unsigned)rkStage;
     set_l2_window();
@@ -1219,15 +1263,22 @@ static int adfb_rk_stage_body(int level, int rkStage) {
         AdfbParams prmL = g.prm;
         if (level > 1) prmL.cfl = g.prm.cflCoarse;
         if (launch_rk_update(b.d, b.dev, prmL, rkStage, g.stream, level > 1 ? 5 : 0)) return fail("RK update launch failed");
-        if (launch_bc_flow(b.d, b.dev, b.subfaces, level > 1 ? 0 : 1, g.stream)) return fail("flow BC launch failed");
     }
     // whalo2(level, 1, nwf, T, T, T) / whalo1 on coarse levels (the pattern of the level holds the matching lists):
-    // the trailing computeEtotBlock is idempotent here unless an overset pattern interpolates into fringe cells
-    if (halo_exchange_impl(level, 1, 5, 1, 1, overset_present(level))) return 1;
+    // the trailing computeEtotBlock is idempotent here unless an overset pattern interpolates into fringe cells.
+    // Multi-rank: the updated owned cells travel while the BC chain runs.
+    const bool split = halo_split_ok(level);
+    if (split && halo_exchange_impl(level, 1, 5, 1, 1, overset_present(level), 1)) return 1;
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != level) continue;
+        if (launch_bc_flow(b.d, b.dev, b.subfaces, level > 1 ? 0 : 1, g.stream)) return fail("flow BC launch failed");
+    }
+    if (halo_exchange_impl(level, 1, 5, 1, 1, overset_present(level), split ? 2 : 0)) return 1;
     CK(cudaGetLastError());
     return 0;
 }
 int adfb_rk_stage(int level, int rkStage) {
+    ADFB_RANGE("adfb_rk_stage");
     NEED_INIT();
     const unsigned long long key = (2ull << 40) | ((unsigned long long)level << 32) | (unsigned)rkStage;
     set_l2_window();
@@ -1251,6 +1302,7 @@ static int adfb_dadi_step_body(int level) {
     return 0;
 }
 int adfb_dadi_step(int level) {
+    ADFB_RANGE("adfb_dadi_step");
     NEED_INIT();
     const unsigned long long key = (4ull << 40) | ((unsigned long long)level << 32);
     set_l2_window();
@@ -1268,6 +1320,7 @@ static int adfb_dadi_cycle_body(int level, int nSubiterations) {
     return adfb_dadi_step(level);
 }
 int adfb_dadi_cycle(int level, int nSubiterations) {
+    ADFB_RANGE("adfb_dadi_cycle");
     NEED_INIT();
     const unsigned long long key = (7ull << 40) | ((unsigned long long)level << 32) | (unsigned)nSubiterations;
     set_l2_window();
@@ -1292,6 +1345,7 @@ static int adfb_sa_ddadi_body(int level, int nSubIterTurb) {
     return 0;
 }
 int adfb_sa_ddadi(int level, int nSubIterTurb) {
+    ADFB_RANGE("adfb_sa_ddadi");
     NEED_INIT();
     const unsigned long long key = (5ull << 40) | ((unsigned long long)level << 32) | (unsigned)nSubIterTurb;
     set_l2_window();
@@ -1314,6 +1368,7 @@ static int adfb_rk_cycle_body(int level) {
     return adfb_rk_stage(level, g.prm.nRKStages);
 }
 int adfb_rk_cycle(int level) {
+    ADFB_RANGE("adfb_rk_cycle");
     NEED_INIT();
     const unsigned long long key = (6ull << 40) | ((unsigned long long)level << 32);
     set_l2_window();
@@ -1348,6 +1403,7 @@ int adfb_ank_set_params(const AdfbAnkParams* ank) {
     return 0;
 }
 int adfb_ank_time_step_mat(void) {
+    ADFB_RANGE("adfb_ank_time_step_mat");
     NEED_INIT();
     if (!g.havePrm || !g.haveAnk) return fail("adfb_ank_time_step_mat: adfb_set_params / adfb_ank_set_params have not been called");
     size_t need = 0;
@@ -1408,6 +1464,7 @@ static int ank_ready(const char* who, long long n, long long* need) {
 }
 // FormFunction_mf (:2468-2538)
 int adfb_ank_form_function(const double* inVec, double* rVec, long long n) {
+    ADFB_RANGE("adfb_ank_form_function");
     NEED_INIT();
     long long need = 0;
     if (!inVec || !rVec) return fail("adfb_ank_form_function: null vector");
@@ -1451,6 +1508,7 @@ static int ank_mffd_core(long long need, double h) {
     return 0;
 }
 int adfb_ank_mffd_apply(const double* a, double* y, long long n, double h) {
+    ADFB_RANGE("adfb_ank_mffd_apply");
     NEED_INIT();
     long long need = 0;
     if (!a || !y) return fail("adfb_ank_mffd_apply: null vector");
@@ -1466,6 +1524,7 @@ int adfb_ank_mffd_apply(const double* a, double* y, long long n, double h) {
 }
 // the same product for Krylov vectors resident on this device (PETSc VECCUDA), like adfb_mffd_apply_device
 int adfb_ank_mffd_apply_device(const double* aDev, double* yDev, long long n, double h) {
+    ADFB_RANGE("adfb_ank_mffd_apply_device");
     NEED_INIT();
     long long need = 0;
     if (!aDev || !yDev) return fail("adfb_ank_mffd_apply_device: null vector");
@@ -1486,6 +1545,7 @@ int adfb_ank_mffd_apply_device(const double* aDev, double* yDev, long long n, do
 }
 // physicalityCheckANK (:3013-3210)
 int adfb_ank_physicality_check(const double* wVec, double* deltaW, long long n, double* lambdaP) {
+    ADFB_RANGE("adfb_ank_physicality_check");
     NEED_INIT();
     if (!g.haveAnk) return fail("adfb_ank_physicality_check: adfb_ank_set_params has not been called");
     if (!wVec || !deltaW || !lambdaP) return fail("adfb_ank_physicality_check: null argument");
@@ -1626,6 +1686,7 @@ static int adfb_mg_restrict_body(int fineLevel) {
     return 0;
 }
 int adfb_mg_restrict(int fineLevel) {
+    ADFB_RANGE("adfb_mg_restrict");
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_mg_restrict: adfb_set_params has not been called");
     const unsigned long long key = (8ull << 40) | ((unsigned long long)fineLevel << 32);
@@ -1663,6 +1724,7 @@ static int adfb_mg_prolong_body(int fineLevel) {
     return 0;
 }
 int adfb_mg_prolong(int fineLevel) {
+    ADFB_RANGE("adfb_mg_prolong");
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_mg_prolong: adfb_set_params has not been called");
     const unsigned long long key = (9ull << 40) | ((unsigned long long)fineLevel << 32);
@@ -1704,6 +1766,7 @@ static int adfb_mg_cycle_body(int nSteps, const int* cycling, int smoother) {
     return adfb_smoother_residual(1, 0);
 }
 int adfb_mg_cycle(int nSteps, const int* cycling, int smoother) {
+    ADFB_RANGE("adfb_mg_cycle");
     NEED_INIT();
     if (!g.havePrm) return fail("adfb_mg_cycle: adfb_set_params has not been called");
     if (nSteps < 1 || nSteps > 4096 || !cycling) return fail("adfb_mg_cycle: bad cycling strategy");
@@ -1752,6 +1815,7 @@ static int kry_dots(const double* V, long long ld, int nv, const double* w, long
 }
 int adfb_gmres_solve(int op, const double* rhs, double* x, long long n, int restart, int maxIts, double rtol, double atol,
                      AdfbPrecondFn pc, void* pcCtx, int* itsOut, double* resNormOut) {
+    ADFB_RANGE("adfb_gmres_solve");
     NEED_INIT();
     if (!rhs || !x) return fail("adfb_gmres_solve: null vector");
     if (op < 0 || op > 2) return fail("adfb_gmres_solve: op must be 0 (NK product), 1 (ANK product) or 2 (time-step matrix)");
@@ -1874,6 +1938,7 @@ int adfb_gmres_solve(int op, const double* rhs, double* x, long long n, int rest
 }
 
 int adfb_norms(double out[2]) {
+    ADFB_RANGE("adfb_norms");
     NEED_INIT();
     if (!out) return fail("adfb_norms: null");
     out[0] = out[1] = 0.0;
@@ -1907,6 +1972,7 @@ int adfb_norms(double out[2]) {
 // `level`, all-reduced.  The viscous part uses the wall stresses stored by the last adfb_residual call that had
 // ADFB_RES_STORE_WALL set.
 int adfb_forces(int level, const double refPoint[3], double pRef, double out[12]) {
+    ADFB_RANGE("adfb_forces");
     NEED_INIT();
     if (!refPoint || !out) return fail("adfb_forces: null");
     if (g.dRedN < 16) {
