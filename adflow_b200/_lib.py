@@ -19,12 +19,13 @@ ABI_SYMBOLS = [
     "adfb_set_params", "adfb_upload_state", "adfb_download_state", "adfb_upload_visc",
     "adfb_download_residual", "adfb_download_intermed", "adfb_residual", "adfb_norms", "adfb_synchronize", "adfb_forces",
     "adfb_get_states", "adfb_set_states", "adfb_get_res", "adfb_state_size",
-    "adfb_comm_set_pattern", "adfb_comm_set_overset", "adfb_halo_exchange",
+    "adfb_comm_set_pattern", "adfb_comm_set_overset", "adfb_block_set_orphans", "adfb_halo_exchange",
     "adfb_reference_shock_sensor", "adfb_form_function", "adfb_mffd_set_base", "adfb_mffd_apply", "adfb_mffd_apply_device", "adfb_mffd_last_h",
     "adfb_apply_bcs", "adfb_timestep", "adfb_smoother_residual", "adfb_rk_stage", "adfb_rk_cycle", "adfb_dadi_step", "adfb_dadi_cycle", "adfb_sa_ddadi",
     "adfb_block_set_mg", "adfb_mg_restrict", "adfb_mg_prolong", "adfb_mg_cycle",
     "adfb_ank_set_params", "adfb_ank_time_step_mat", "adfb_ank_form_function", "adfb_ank_mffd_set_base", "adfb_ank_mffd_apply", "adfb_ank_mffd_apply_device",
-    "adfb_ank_physicality_check", "adfb_gmres_solve",
+    "adfb_ank_physicality_check", "adfb_ank_form_function_turb", "adfb_ank_mffd_turb_set_base", "adfb_ank_mffd_turb_apply",
+    "adfb_ank_physicality_check_turb", "adfb_gmres_solve",
 ]
 
 
@@ -87,6 +88,11 @@ def load():
     L.adfb_mffd_last_h.restype = C.c_double
     L.adfb_comm_set_pattern.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, vp, vp]
     L.adfb_comm_set_overset.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp]
+    L.adfb_block_set_orphans.argtypes = [ci, ci, vp, C.c_double, C.c_double]
+    L.adfb_ank_form_function_turb.argtypes = [vp, vp, C.c_longlong]
+    L.adfb_ank_mffd_turb_set_base.argtypes = [vp, C.c_longlong]
+    L.adfb_ank_mffd_turb_apply.argtypes = [vp, vp, C.c_longlong, C.c_double]
+    L.adfb_ank_physicality_check_turb.argtypes = [vp, vp, C.c_longlong, vp]
     L.adfb_halo_exchange.argtypes = [ci] * 6
     L.adfb_apply_bcs.argtypes = [ci, ci, ci]
     L.adfb_timestep.argtypes = [ci, ci]

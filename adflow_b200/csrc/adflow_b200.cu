@@ -42,6 +42,10 @@ struct Block {
     // block: mg?Fine, mg?Weight; the fine block's mg?Coarse are kept with the coarse block as well)
     int fineBlk = -1, coarseBlk = -1;
     MgTables mg = {};
+    // overset orphans (blockPointers nOrphans / orphans) and the free-stream viscosities orphanAverage falls back to
+    int nOrphans = 0;
+    int32_t* dOrphans = nullptr;
+    double muInf = 0.0, eddyVisInfRatio = 0.0;
     std::vector<void*> mgAllocs;
 };
 
@@ -95,7 +99,7 @@ struct Context {
     bool capturing = false;
     // ANK (module ANKSolver): options, per-cell time-step blocks, the perturbed vector of the last product
     AdfbAnkParams ank;
-    bool haveAnk = false, ankHaveT = false, ankHaveBase = false;
+    bool haveAnk = false, ankHaveT = false, ankHaveBase = false, ankTurbHaveBase = false;
     double *ankT = nullptr, *ankPert = nullptr;
     size_t ankTN = 0, ankPertN = 0;
     double ankUnorm = 0.0;
@@ -333,7 +337,7 @@ int adfb_finalize(void) {
     g.dVec = nullptr; g.dVecN = 0;
     for (double** p : {&g.nkA, &g.nkU, &g.nkF0, &g.nkY}) { if (*p) cudaFree(*p); *p = nullptr; }
     g.nkN = 0;
-    g.nkHaveBase = false; g.ankHaveBase = false;   // the base vectors went with the buffers g.nkHaveBase = false;
+    g.nkHaveBase = false; g.ankHaveBase = false; g.ankTurbHaveBase = false;   // the base vectors went with the buffers g.nkHaveBase = false;
     // ANK / Krylov state belongs to the context as well: a later adfb_init starts from scratch
     for (double** p : {&g.ankT, &g.ankPert, &g.kryV, &g.kryRed}) { if (*p) cudaFree(*p); *p = nullptr; }
     g.ankTN = 0; g.ankPertN = 0; g.kryVN = 0;
@@ -456,6 +460,7 @@ int adfb_block_destroy(int blk) {
     for (void* q : b->allocs) cudaFree(q);
     for (void* q : b->bcAllocs) cudaFree(q);
     for (void* q : b->mgAllocs) cudaFree(q);
+    if (b->dOrphans) cudaFree(b->dOrphans);
     *b = Block();
     return 0;
 }
@@ -771,6 +776,28 @@ int adfb_comm_set_overset(int level, int nNbr, const int* nbrRank, const int* se
 
 // whalo1to1 part of whalo2/whalo1 for the variable selection of setCommPointers
 // (src/utils/haloExchange.F90:356-470)
+extern "C" int adfb_block_set_orphans(int blk, int nOrphans, const int32_t* orphans, double muInf, double eddyVisInfRatio) {
+    NEED_INIT();
+    Block* b = get_block(blk);
+    if (!b) return fail("adfb_block_set_orphans: no block %d", blk);
+    if (nOrphans < 0 || (nOrphans > 0 && !orphans)) return fail("adfb_block_set_orphans: bad arguments");
+    drop_graphs();
+    cudaStreamSynchronize(g.stream);
+    if (b->dOrphans) { cudaFree(b->dOrphans); b->dOrphans = nullptr; }
+    b->nOrphans = 0;
+    for (int n = 0; n < nOrphans; n++) {
+        const int i = orphans[3 * n], j = orphans[3 * n + 1], k = orphans[3 * n + 2];
+        if (i < 0 || i > b->d.ib || j < 0 || j > b->d.jb || k < 0 || k > b->d.kb)
+            return fail("adfb_block_set_orphans: orphan %d (%d, %d, %d) outside the block", n, i, j, k);
+    }
+    if (nOrphans > 0) {
+        CK(cudaMalloc((void**)&b->dOrphans, (size_t)3 * nOrphans * sizeof(int32_t)));
+        CK(cudaMemcpy(b->dOrphans, orphans, (size_t)3 * nOrphans * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    b->nOrphans = nOrphans; b->muInf = muInf; b->eddyVisInfRatio = eddyVisInfRatio;
+    return 0;
+}
+
 // phase 0: the whole exchange on the compute stream.  Phases 1 / 2 split it so that the transfer overlaps the boundary
 // conditions (the reference posts its receives and sends, then copies locally, then waits: haloExchange.F90:620-716):
 //   1 "post"   : pack the send lists of the 1-to-1 pattern (owned cells only: the BCs that follow do not touch them) and
@@ -885,6 +912,18 @@ static int halo_exchange_impl(int level, int start, int end, int commPressure, i
             const long long n = P.nRecv * nVar;
             KT_BEGIN(K_HALO, g.stream);
             k_halo_unpack<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(P.rBlk, P.rOff, P.rCum, P.rLocal, P.rCount, dTab, nVar, P.nRecv, P.recvBuf);
+            KT_END(K_HALO, g.stream);
+        }
+    }
+    // orphanAverage on every block that carries an orphan list (haloExchange.F90:56-66, :161-171)
+    if (phase != 1) {
+        for (Block& b : g.blocks) {
+            if (!b.alive || b.level != level || b.nOrphans == 0) continue;
+            const int lEnd = end < b.nw ? end : b.nw;
+            KT_BEGIN(K_HALO, g.stream);
+            k_orphan_average<<<(b.nOrphans + 127) / 128, 128, 0, g.stream>>>(b.d, b.dev, b.nOrphans, b.dOrphans, start, lEnd, commPressure ? 1 : 0,
+                                                                             (viscous && commViscous) ? 1 : 0, (eddy && commViscous) ? 1 : 0,
+                                                                             b.muInf, b.eddyVisInfRatio);
             KT_END(K_HALO, g.stream);
         }
     }
@@ -1042,7 +1081,7 @@ static int nk_buffers(long long need) {
     if (g.nkN >= (size_t)need) return 0;
     for (double** p : {&g.nkA, &g.nkU, &g.nkF0, &g.nkY}) { if (*p) cudaFree(*p); *p = nullptr; }
     g.nkN = 0;
-    g.nkHaveBase = false; g.ankHaveBase = false;   // the base vectors went with the buffers
+    g.nkHaveBase = false; g.ankHaveBase = false; g.ankTurbHaveBase = false;   // the base vectors went with the buffers
     for (double** p : {&g.nkA, &g.nkU, &g.nkF0, &g.nkY}) CK(cudaMalloc((void**)p, need * sizeof(double)));
     if (!g.dRed) { CK(cudaMalloc((void**)&g.dRed, (2 * 1024 + 2) * sizeof(double))); g.dRedN = 2 * 1024 + 2; }
     g.nkN = need;
@@ -1115,7 +1154,7 @@ int adfb_mffd_set_base(const double* U, long long n) {
     if (nk_sumsq(g.nkU, need, &uu)) return 1;
     g.nkUnorm = sqrt(uu);
     g.nkHaveBase = true;
-    g.ankHaveBase = false;   // the ANK base shares the buffers
+    g.ankHaveBase = false; g.ankTurbHaveBase = false;   // the ANK bases share the buffers
     return 0;
 }
 
@@ -1490,7 +1529,7 @@ int adfb_ank_mffd_set_base(const double* U, long long n) {
     if (nk_sumsq(g.nkU, need, &uu)) return 1;
     g.ankUnorm = sqrt(uu);
     g.ankHaveBase = true;
-    g.nkHaveBase = false;   // the NK base shares the buffers
+    g.nkHaveBase = false; g.ankTurbHaveBase = false;   // the NK base shares the buffers
     return 0;
 }
 // y = (F(U + h a) - F(U)) / h with a in g.nkA, y into g.nkY; returns 2 when a == 0
@@ -1544,6 +1583,123 @@ int adfb_ank_mffd_apply_device(const double* aDev, double* yDev, long long n, do
     return 0;
 }
 // physicalityCheckANK (:3013-3210)
+// ---- turbulence KSP of the decoupled ANK (ANKTurbSolveKSP, NKSolvers.F90:3337 ff.): one turbulence variable per owned cell
+static long long ank_turb_vec_size(void) {
+    long long n = 0;
+    for (Block& b : g.blocks)
+        if (b.alive && b.level == 1) n += (long long)b.d.nx * b.d.ny * b.d.nz;
+    return n;
+}
+static int ank_turb_ready(const char* who, long long n) {
+    if (!g.havePrm || !g.haveAnk) return fail("%s: adfb_set_params / adfb_ank_set_params have not been called", who);
+    if (g.prm.equations != ADFB_RANS) return fail("%s: needs the RANS equations (a turbulence variable)", who);
+    const long long need = ank_turb_vec_size();
+    if (n != need) return fail("%s: vector length %lld != %lld (one turbulence variable per owned cell)", who, n, need);
+    if (nk_buffers(adfb_state_size())) return 1;
+    if (g.ankPertN < (size_t)need) {
+        if (g.ankPert) cudaFree(g.ankPert);
+        g.ankPert = nullptr; g.ankPertN = 0;
+        CK(cudaMalloc((void**)&g.ankPert, need * sizeof(double)));
+        g.ankPertN = need;
+    }
+    return 0;
+}
+// blocketteRes without useUpdateIntermed leaves the block's dtl alone (the tile's time step stays local, blockette.F90:1929),
+// the device residual always stores it: the time-stepping term uses the copy taken before the residual (work array 0)
+static int ank_turb_save_dtl(void) {
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != 1) continue;
+        CK(cudaMemcpyAsync(b.dev.scratch, b.dev.dtl, (size_t)b.d.N * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+    }
+    return 0;
+}
+static int ank_turb_vec_kernel(const double* vec, const double* base, double* out, double* pert, double h, int mode) {
+    long long off = 0;
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != 1) continue;
+        const long long nc = (long long)b.d.nx * b.d.ny * b.d.nz;
+        KT_BEGIN(K_MFFD, g.stream);
+        k_ankvec_turb<<<(unsigned)((nc + 255) / 256), 256, 0, g.stream>>>(b.d, b.dev, g.ank, b.dev.scratch, vec ? vec + off : nullptr, base ? base + off : nullptr,
+                                                                         out ? out + off : nullptr, pert ? pert + off : nullptr, h, mode);
+        KT_END(K_MFFD, g.stream);
+        off += nc;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+// FormFunction_mf_turb (:2540-2612): setWANK(inVec, nt1, nt2); blocketteRes(useFlowRes = .false.); setRVecANKTurb; time-stepping term
+int adfb_ank_form_function_turb(const double* inVec, double* rVec, long long n) {
+    ADFB_RANGE("adfb_ank_form_function_turb");
+    NEED_INIT();
+    if (!inVec || !rVec) return fail("adfb_ank_form_function_turb: null vector");
+    if (ank_turb_ready("adfb_ank_form_function_turb", n)) return 1;
+    CK(cudaMemcpyAsync(g.nkA, inVec, n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    if (ank_turb_save_dtl()) return 1;
+    if (ank_turb_vec_kernel(g.nkA, nullptr, nullptr, nullptr, 0.0, 0)) return 1;
+    if (adfb_residual(1, ADFB_RES_TURB)) return 1;
+    if (ank_turb_vec_kernel(g.nkA, nullptr, g.nkY, nullptr, 1.0, 2)) return 1;
+    CK(cudaMemcpyAsync(rVec, g.nkY, n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+// the matrix-free product of the turbulence KSP (MatMFFD shell over FormFunction_mf_turb): base state, then
+// y = (F(U + h a) - F(U)) / h with a given h > 0
+int adfb_ank_mffd_turb_set_base(const double* U, long long n) {
+    ADFB_RANGE("adfb_ank_mffd_turb_set_base");
+    NEED_INIT();
+    if (!U) return fail("adfb_ank_mffd_turb_set_base: null vector");
+    if (ank_turb_ready("adfb_ank_mffd_turb_set_base", n)) return 1;
+    g.nkHaveBase = false; g.ankHaveBase = false;   // the NK / ANK bases share the buffers
+    CK(cudaMemcpyAsync(g.nkU, U, n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    if (ank_turb_save_dtl()) return 1;
+    if (ank_turb_vec_kernel(g.nkU, nullptr, nullptr, nullptr, 0.0, 0)) return 1;
+    if (adfb_residual(1, ADFB_RES_TURB)) return 1;
+    if (ank_turb_vec_kernel(g.nkU, nullptr, g.nkF0, nullptr, 1.0, 2)) return 1;
+    CK(cudaStreamSynchronize(g.stream));
+    g.ankTurbHaveBase = true;
+    return 0;
+}
+int adfb_ank_mffd_turb_apply(const double* a, double* y, long long n, double h) {
+    ADFB_RANGE("adfb_ank_mffd_turb_apply");
+    NEED_INIT();
+    if (!a || !y) return fail("adfb_ank_mffd_turb_apply: null vector");
+    if (!(h > 0.0)) return fail("adfb_ank_mffd_turb_apply: h must be positive");
+    if (ank_turb_ready("adfb_ank_mffd_turb_apply", n)) return 1;
+    if (!g.ankTurbHaveBase || g.nkHaveBase || g.ankHaveBase) return fail("adfb_ank_mffd_turb_apply: adfb_ank_mffd_turb_set_base has not been called");
+    CK(cudaMemcpyAsync(g.nkA, a, n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    if (ank_turb_vec_kernel(g.nkA, g.nkU, nullptr, g.ankPert, h, 1)) return 1;
+    if (adfb_residual(1, ADFB_RES_TURB)) return 1;
+    if (ank_turb_vec_kernel(g.ankPert, g.nkF0, g.nkY, nullptr, h, 3)) return 1;
+    CK(cudaMemcpyAsync(y, g.nkY, n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+// physicalityCheckANKTurb (:3212-3335)
+int adfb_ank_physicality_check_turb(const double* wVec, double* deltaW, long long n, double* lambdaP) {
+    ADFB_RANGE("adfb_ank_physicality_check_turb");
+    NEED_INIT();
+    if (!wVec || !deltaW || !lambdaP) return fail("adfb_ank_physicality_check_turb: null argument");
+    if (ank_turb_ready("adfb_ank_physicality_check_turb", n)) return 1;
+    CK(cudaMemcpyAsync(g.nkA, wVec, n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.nkY, deltaW, n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    const int nPart = 512;
+    KT_BEGIN(K_MFFD, g.stream);
+    k_ank_phys_turb<<<nPart, 256, 0, g.stream>>>(n, g.ank, g.nkA, g.nkY, *lambdaP, g.dRed);
+    KT_END(K_MFFD, g.stream);
+    KT_BEGIN(K_MFFD, g.stream);
+    k_min_final<<<1, 256, 0, g.stream>>>(g.dRed, nPart);
+    KT_END(K_MFFD, g.stream);
+    if (g.nranks > 1) {
+        const int rc = g.nccl.AllReduce(g.dRed + nPart, g.dRed + nPart, 1, kNcclDouble, kNcclMin, g.comm, g.stream);
+        if (rc != 0) return fail("ncclAllReduce: %s", g.nccl.GetErrorString(rc));
+    }
+    CK(cudaMemcpyAsync(g.hRed, g.dRed + nPart, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(deltaW, g.nkY, n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaGetLastError());
+    *lambdaP = g.hRed[0];
+    return 0;
+}
 int adfb_ank_physicality_check(const double* wVec, double* deltaW, long long n, double* lambdaP) {
     ADFB_RANGE("adfb_ank_physicality_check");
     NEED_INIT();

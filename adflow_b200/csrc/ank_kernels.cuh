@@ -207,4 +207,54 @@ __global__ void k_min_final(double* part, int nPart) {
     if (threadIdx.x == 0) part[nPart] = s[0];
 }
 
+
+// turbulence KSP of the decoupled ANK (one turbulence variable per owned cell):
+//   mode 0 : setWANK(inVec, nt1, nt2) (NKSolvers.F90:2975-3011): w(itu1) of the owned cells <- vec
+//   mode 1 : the same with vec = base + h * a (matrix-free product); the perturbed vector is kept in pert
+//   mode 2 : setRVecANKTurb (:2935-2973) + the time-stepping term of FormFunction_mf_turb (:2540-2612):
+//            out = dw(itu1) / volRef * turbResScale + vec / (ANK_CFL dtl volRef) * turbResScale / ANK_turbCFLScale
+//   mode 3 : (that - base) / h
+__global__ void __launch_bounds__(256) k_ankvec_turb(Dims d, BlockDev b, AdfbAnkParams ank, const double* __restrict__ dtl, const double* __restrict__ vec,
+                                                     const double* __restrict__ base, double* __restrict__ out, double* __restrict__ pert,
+                                                     double h, int mode) {
+    const long long nOwned = (long long)d.nx * d.ny * d.nz;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nOwned) return;
+    const int i = (int)(q % d.nx) + 2, j = (int)((q / d.nx) % d.ny) + 2, k = (int)(q / ((long long)d.nx * d.ny)) + 2;
+    const long long c = ADFB_IDX(i, j, k);
+    if (mode <= 1) {
+        const double v = mode == 0 ? vec[q] : base[q] + h * vec[q];
+        if (mode == 1) pert[q] = v;
+        b.w[5 * d.N + c] = v;
+        return;
+    }
+    const double ovv = 1.0 / b.volRef[c];
+    double r = b.dw[5 * d.N + c] * ovv * c_prm.turbResScale;
+    const double dtinv = 1.0 / (ank.cfl * dtl[c] * b.volRef[c]);
+    r = r + vec[q] * dtinv * c_prm.turbResScale / ank.turbCFLScale;
+    out[q] = mode == 2 ? r : (r - base[q]) / h;
+}
+// physicalityCheckANKTurb (:3212-3335): clip of too-limiting updates + MIN over the cells
+__global__ void __launch_bounds__(256) k_ank_phys_turb(long long nCells, AdfbAnkParams ank, const double* __restrict__ wv, double* __restrict__ dv,
+                                                       double lambda0, double* __restrict__ part) {
+    __shared__ double s[256];
+    double lam = lambda0;
+    for (long long ii = (long long)blockIdx.x * blockDim.x + threadIdx.x; ii < nCells; ii += (long long)gridDim.x * blockDim.x) {
+        double ratio = (wv[ii] / (dv[ii] + 1.e-25)) * ank.physLSTolTurb;
+        if (ratio < ank.stepFactor * ank.stepMin) {
+            if (ratio > 0.0) dv[ii] = wv[ii] * ank.physLSTolTurb;
+            ratio = 1.0;
+        }
+        lam = dmin_(lam, ratio);
+        if (lam != lam) lam = 0.0;
+    }
+    s[threadIdx.x] = lam;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st) s[threadIdx.x] = dmin_(s[threadIdx.x], s[threadIdx.x + st]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = s[0];
+}
+
 }  // namespace

@@ -89,6 +89,48 @@ __global__ void __launch_bounds__(256) k_halo_internal(const int* __restrict__ s
     tab[dstBlk[e]].ptr[v][dstOff[e]] = tab[srcBlk[e]].ptr[v][srcOff[e]];
 }
 
+
+// orphanAverage (src/utils/haloExchange.F90:201-354): one thread per orphan.  A neighbour only counts when its iblank
+// is 1 and an orphan's own iblank is not, so the orphans do not feed each other and the reference's sequential loop is
+// order independent; the sums run over -i, +i, -j, +j, -k, +k like the reference's.
+__global__ void __launch_bounds__(128) k_orphan_average(Dims d, BlockDev b, int nOrphans, const int32_t* __restrict__ orphans, int wStart, int wEnd,
+                                                        int calcP, int calcLam, int calcEddy, double muInf, double eddyRatio) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nOrphans) return;
+    const int oi = orphans[3 * n], oj = orphans[3 * n + 1], ok = orphans[3 * n + 2];
+    const long long N = d.N, c = ADFB_IDX(oi, oj, ok);
+    double acc[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) acc[q] = 0.0;
+    int nAvg = 0;
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+        for (int i = -1; i <= 1; i += 2) {
+            const int ni = oi + (m == 0 ? i : 0), nj = oj + (m == 1 ? i : 0), nk = ok + (m == 2 ? i : 0);
+            if (ni < 0 || ni > d.ib || nj < 0 || nj > d.jb || nk < 0 || nk > d.kb) continue;
+            const long long cn = ADFB_IDX(ni, nj, nk);
+            if (b.iblank[cn] != 1) continue;
+            nAvg++;
+            for (int l = wStart; l <= wEnd; l++) acc[l - 1] = acc[l - 1] + b.w[(l - 1) * N + cn];
+            if (calcP) acc[6] = acc[6] + b.p[cn];
+            if (calcLam) acc[7] = acc[7] + b.rlv[cn];
+            if (calcEddy) acc[8] = acc[8] + b.rev[cn];
+        }
+    if (nAvg > 0) {
+        const double r = (double)nAvg;
+        for (int l = wStart; l <= wEnd; l++) b.w[(l - 1) * N + c] = acc[l - 1] / r;
+        if (calcP) b.p[c] = acc[6] / r;
+        if (calcLam) b.rlv[c] = acc[7] / r;
+        if (calcEddy) b.rev[c] = acc[8] / r;
+    } else {
+        for (int l = wStart; l <= wEnd; l++) b.w[(l - 1) * N + c] = c_prm.wInf[l - 1];
+        if (calcP) b.p[c] = c_prm.pInfCorr;
+        if (calcLam) b.rlv[c] = muInf;
+        if (calcEddy) b.rev[c] = eddyRatio * muInf;
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------

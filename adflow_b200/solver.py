@@ -102,6 +102,13 @@ class ADFLOW_B200:
                                            p(a["sendList"]), p(a["sendInterp"]), p(a["recvList"]), len(a["donorList"]),
                                            p(a["donorList"]), p(a["donorInterp"]), p(a["haloList"])), "adfb_comm_set_overset")
 
+    def setOrphans(self, blk, orphans, mu_inf, eddy_vis_inf_ratio):
+        """orphans(3, nOrphans) of one block (cell indices with the reference's bounds) and the free-stream viscosities
+        orphanAverage falls back to; every exchange then ends with orphanAverage on that block."""
+        a = np.ascontiguousarray(np.asarray(orphans, dtype=np.int32).reshape(-1, 3))
+        check(self.L.adfb_block_set_orphans(blk, len(a), a.ctypes.data_as(C.c_void_p) if len(a) else None, C.c_double(mu_inf),
+                                            C.c_double(eddy_vis_inf_ratio)), "adfb_block_set_orphans")
+
     def haloExchange(self, start=1, end=None, comm_pressure=True, comm_gamma=True, comm_viscous=True, level=1):
         """whalo2(level, start, end, commPressure, commGamma, commViscous)."""
         if end is None:
@@ -184,6 +191,32 @@ class ADFLOW_B200:
         dv = np.array(delta_w, dtype=np.float64, order="C", copy=True)
         lam = C.c_double(lambda_p)
         check(self.L.adfb_ank_physicality_check(w.ctypes.data, dv.ctypes.data, w.size, C.byref(lam)), "adfb_ank_physicality_check")
+        return lam.value, dv
+
+    # turbulence KSP of the decoupled ANK: one turbulence variable per owned cell
+    def ankFormFunctionTurb(self, in_vec):
+        """FormFunction_mf_turb (NKSolvers.F90:2540-2612)"""
+        v = np.ascontiguousarray(in_vec, dtype=np.float64)
+        r = np.empty_like(v)
+        check(self.L.adfb_ank_form_function_turb(v.ctypes.data, r.ctypes.data, v.size), "adfb_ank_form_function_turb")
+        return r
+
+    def ankMffdTurbSetBase(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        check(self.L.adfb_ank_mffd_turb_set_base(U.ctypes.data, U.size), "adfb_ank_mffd_turb_set_base")
+
+    def ankMffdTurbApply(self, a, h):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        y = np.empty_like(a)
+        check(self.L.adfb_ank_mffd_turb_apply(a.ctypes.data, y.ctypes.data, a.size, C.c_double(h)), "adfb_ank_mffd_turb_apply")
+        return y
+
+    def ankPhysicalityCheckTurb(self, w_vec, delta_w, lambda_p=1.0):
+        """physicalityCheckANKTurb (NKSolvers.F90:3212-3335): returns (lambdaP, deltaW with the clipped updates)"""
+        w = np.ascontiguousarray(w_vec, dtype=np.float64)
+        dv = np.array(delta_w, dtype=np.float64, order="C", copy=True)
+        lam = C.c_double(lambda_p)
+        check(self.L.adfb_ank_physicality_check_turb(w.ctypes.data, dv.ctypes.data, w.size, C.byref(lam)), "adfb_ank_physicality_check_turb")
         return lam.value, dv
 
     # -- multigrid (src/solver/multiGrid.F90) ----------------------------------------------------------------

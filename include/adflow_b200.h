@@ -261,10 +261,17 @@ int adfb_comm_set_pattern(int level, int nNbr, const int* nbrRank, const int* se
    sendInterp / donorInterp hold its 8 weights per entry in the reference's order (sendList%interp(j,1:8),
    i fastest: (i,j,k), (i+1,j,k), (i,j+1,k), ...), wOversetGeneric src/utils/haloExchange.F90:1471-1654.
    Once set, adfb_halo_exchange (and every call that exchanges halos) runs the overset exchange right after the
-   1-to-1 exchange like whalo2 does; orphan averaging is not supported (nOrphans must be 0). */
+   1-to-1 exchange like whalo2 does, followed by orphanAverage on the blocks that carry an orphan list
+   (adfb_block_set_orphans). */
 int adfb_comm_set_overset(int level, int nNbr, const int* nbrRank, const int* sendCount, const int* recvCount,
                           const int* sendList, const double* sendInterp, const int* recvList, int nInternal,
                           const int* donorList, const double* donorInterp, const int* haloList);
+/* Overset orphans of a block (blockPointers nOrphans / orphans(3, nOrphans), set by the overset connectivity,
+   src/overset/oversetUtilities.F90:1638-1667): cell indices (i, j, k) with the reference's bounds, 3 * nOrphans ints.
+   Every exchange then ends with orphanAverage (src/utils/haloExchange.F90:201-354, called by whalo1 / whalo2 after
+   wOverset): an orphan takes the average of its face neighbours with iblank == 1, or the free stream (wInf, pInfCorr,
+   muInf, eddyVisInfRatio * muInf: flowVarRefState) when it has none.  nOrphans = 0 removes the list. */
+int adfb_block_set_orphans(int blk, int nOrphans, const int32_t* orphans, double muInf, double eddyVisInfRatio);
 /* whalo2(level, start, end, commPressure, commGamma, commViscous)
    (src/utils/haloExchange.F90:109-199): w(start:end) [1-based], p, rlv, rev of all
    listed halo cells; grouped ncclSend/ncclRecv over NVLink; then computeEtotBlock on
@@ -328,6 +335,17 @@ int adfb_ank_form_function(const double* inVec, double* rVec, long long n);
    y = (F(U + h a) - F(U)) / h for host vectors; h <= 0: PETSc's default differencing parameter as in adfb_mffd_apply */
 int adfb_ank_mffd_set_base(const double* U, long long n);
 int adfb_ank_mffd_apply(const double* a, double* y, long long n, double h);
+/* Turbulence KSP of the decoupled ANK (ANKTurbSolveKSP, NKSolvers.F90:3337 ff.); vectors hold the nt1:nt2 = one turbulence
+   variable per owned cell, cell order like getStates.
+   adfb_ank_form_function_turb = FormFunction_mf_turb (:2540-2612): setWANK(inVec, nt1, nt2); blocketteRes(useFlowRes = .false.);
+   setRVecANKTurb (dw(itu1) / volRef * turbResScale); + inVec / (ANK_CFL dtl volRef) * turbResScale / ANK_turbCFLScale.
+   adfb_ank_mffd_turb_set_base / _apply: the MatMFFD shell over it, y = (F(U + h a) - F(U)) / h (h > 0 given by the caller).
+   adfb_ank_physicality_check_turb = physicalityCheckANKTurb (:3212-3335): lambdaP MIN-reduced over all ranks, deltaW returned
+   with the clipped updates. */
+int adfb_ank_form_function_turb(const double* inVec, double* rVec, long long n);
+int adfb_ank_mffd_turb_set_base(const double* U, long long n);
+int adfb_ank_mffd_turb_apply(const double* a, double* y, long long n, double h);
+int adfb_ank_physicality_check_turb(const double* wVec, double* deltaW, long long n, double* lambdaP);
 /* the same product with a and y resident on this GPU (PETSc VECCUDA arrays): no PCIe traffic */
 int adfb_ank_mffd_apply_device(const double* aDev, double* yDev, long long n, double h);
 /* physicalityCheckANK (:3013-3210): largest step lambda <= *lambdaP that changes rho and rhoE by at most physLSTol

@@ -120,6 +120,13 @@ void orc_mg_forcing(const OrcBlock* coarse, const AdfbParams* prm);
 void orc_mg_prolong(const OrcBlock* fine, const OrcBlock* coarse, const AdfbParams* prm, int nSubCoarse, const AdfbSubface* sfCoarse,
                     const int32_t* mgICoarse, const int32_t* mgJCoarse, const int32_t* mgKCoarse);
 /* adflow_oracle_ank.c: ANK pieces (module ANKSolver of src/NKSolver/NKSolvers.F90) */
+/* turbulence KSP of the decoupled ANK: physicalityCheckANKTurb (NKSolvers.F90:3212-3335, pinned bit-exact against the translated
+   routine) and the vector part of FormFunction_mf_turb (:2540-2612) */
+double orc_ank_physicality_check_turb(const AdfbAnkParams* ank, long nCells, const double* wVec, double* dVec, double lambdaP);
+void orc_ank_turb_rvec(const OrcBlock* b, const AdfbParams* prm, const AdfbAnkParams* ank, const double* inVec, double* rVec);
+/* orphanAverage, src/utils/haloExchange.F90:201-354 (pinned bit-exact against the translated routine, tests/test_oracle_vs_reference_orphans.py) */
+void orc_orphan_average(const OrcBlock* b, const AdfbParams* prm, int nOrphans, const int32_t* orphans, int wStart, int wEnd,
+                        int calcPressure, int calcLamVis, int calcEddyVis, double muInf, double eddyVisInfRatio);
 void orc_ank_time_step_block(const OrcBlock* b, const AdfbParams* prm, const AdfbAnkParams* ank, int i, int j, int k, double* blk);
 double orc_ank_physicality_check(const AdfbAnkParams* ank, int nState, long nCells, const double* wVec, double* dVec, double lambdaP);
 #ifdef __cplusplus

@@ -143,3 +143,39 @@ double orc_ank_physicality_check(const AdfbAnkParams* ank, int nState, long nCel
     if (lambdaL != lambdaL) lambdaL = zero;
     return lambdaL;
 }
+
+/* physicalityCheckANKTurb, NKSolvers.F90:3212-3335 (turbulence KSP of the decoupled ANK): vectors of nt2-nt1+1 = 1 entry
+   per owned cell; too-limiting updates are clipped in dVec; returns the new lambdaP */
+double orc_ank_physicality_check_turb(const AdfbAnkParams* ank, long nCells, const double* wVec, double* dVec, double lambdaP) {
+    double lambdaL = lambdaP;
+    for (long ii = 0; ii < nCells; ii++) {
+        double ratio = (wVec[ii] / (dVec[ii] + eps_)) * ank->physLSTolTurb;
+        if (ratio < ank->stepFactor * ank->stepMin) {
+            if (ratio > zero) dVec[ii] = wVec[ii] * ank->physLSTolTurb;
+            ratio = one;
+        }
+        lambdaL = dmin(lambdaL, ratio);
+    }
+    if (lambdaL != lambdaL) lambdaL = zero;
+    return lambdaL;
+}
+
+/* the vector part of FormFunction_mf_turb, NKSolvers.F90:2540-2612, after setWANK(inVec, nt1, nt2) and
+   blocketteRes(useFlowRes = .false.): setRVecANKTurb (:2935-2973: dw(itu1) / volRef * turbResScale(1)) plus the time
+   stepping term inVec / (ANK_CFL dtl volRef) * turbResScale / ANK_turbCFLScale; owned cells, k, j, i order */
+void orc_ank_turb_rvec(const OrcBlock* b, const AdfbParams* prm, const AdfbAnkParams* ank, const double* inVec, double* rVec) {
+    const int il = b->nx + 1, jl = b->ny + 1, kl = b->nz + 1;
+    const long NI = b->nx + 4, NJ = b->ny + 4, N = NI * NJ * (b->nz + 4);
+    const double* dw = (const double*)b->dw; const double* volRef = (const double*)b->volRef; const double* dtl = (const double*)b->dtl;
+    long ii = 0;
+    for (int k = 2; k <= kl; k++)
+        for (int j = 2; j <= jl; j++)
+            for (int i = 2; i <= il; i++) {
+                const long c = i + NI * (j + NJ * (long)k);
+                const double ovv = one / volRef[c];
+                rVec[ii] = dw[5 * N + c] * ovv * prm->turbResScale;
+                const double dtinv = one / (ank->cfl * dtl[c] * volRef[c]);
+                rVec[ii] = rVec[ii] + inVec[ii] * dtinv * prm->turbResScale / ank->turbCFLScale;
+                ii++;
+            }
+}

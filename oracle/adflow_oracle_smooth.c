@@ -814,3 +814,49 @@ void orc_wall_forces(const OrcBlock* b, const AdfbParams* prm, int nSub, const A
         for (int m = 0; m < 3; m++) { out[m] += Fp[m]; out[3 + m] += Fv[m]; out[6 + m] += Mp[m]; out[9 + m] += Mv[m]; }
     }
 }
+
+/* orphanAverage (src/utils/haloExchange.F90:201-354): every overset orphan takes the average of its (up to six)
+ * face neighbours with iblank == 1; with no such neighbour it falls back to the free stream (wInf, pInfCorr, muInf,
+ * eddyVisInfRatio * muInf).  orphans = (3, nOrphans) cell indices (i, j, k); variables w(wStart:wEnd) [1-based],
+ * p / rlv / rev when asked (gamma is constant here). */
+void orc_orphan_average(const OrcBlock* b, const AdfbParams* prm, int nOrphans, const int32_t* orphans, int wStart, int wEnd,
+                        int calcPressure, int calcLamVis, int calcEddyVis, double muInf, double eddyVisInfRatio) {
+    const int ib = b->nx + 3, jb = b->ny + 3, kb = b->nz + 3;
+    const long NI = ib + 1, NJ = jb + 1, N = NI * NJ * (kb + 1);
+    double* w = (double*)b->w; double* p = (double*)b->p; double* rlv = (double*)b->rlv; double* rev = (double*)b->rev;
+    const int32_t* iblank = (const int32_t*)b->iblank;
+    for (int n = 0; n < nOrphans; n++) {
+        const int oi = orphans[3 * n], oj = orphans[3 * n + 1], ok = orphans[3 * n + 2];
+        const long c = oi + NI * (oj + NJ * (long)ok);
+        int nAvg = 0;
+        for (int l = wStart; l <= wEnd; l++) w[(l - 1) * N + c] = 0.0;
+        if (calcPressure) p[c] = 0.0;
+        if (calcLamVis) rlv[c] = 0.0;
+        if (calcEddyVis) rev[c] = 0.0;
+        for (int m = 0; m < 3; m++)
+            for (int i = -1; i <= 1; i += 2) {
+                const int ni = oi + (m == 0 ? i : 0), nj = oj + (m == 1 ? i : 0), nk = ok + (m == 2 ? i : 0);
+                if (ni < 0 || ni > ib || nj < 0 || nj > jb || nk < 0 || nk > kb) continue;
+                const long cn = ni + NI * (nj + NJ * (long)nk);
+                if (iblank[cn] == 1) {
+                    nAvg++;
+                    for (int l = wStart; l <= wEnd; l++) w[(l - 1) * N + c] = w[(l - 1) * N + c] + w[(l - 1) * N + cn];
+                    if (calcPressure) p[c] = p[c] + p[cn];
+                    if (calcLamVis) rlv[c] = rlv[c] + rlv[cn];
+                    if (calcEddyVis) rev[c] = rev[c] + rev[cn];
+                }
+            }
+        if (nAvg > 0) {
+            const double r = (double)nAvg;
+            for (int l = wStart; l <= wEnd; l++) w[(l - 1) * N + c] = w[(l - 1) * N + c] / r;
+            if (calcPressure) p[c] = p[c] / r;
+            if (calcLamVis) rlv[c] = rlv[c] / r;
+            if (calcEddyVis) rev[c] = rev[c] / r;
+        } else {
+            for (int l = wStart; l <= wEnd; l++) w[(l - 1) * N + c] = prm->wInf[l - 1];
+            if (calcPressure) p[c] = prm->pInfCorr;
+            if (calcLamVis) rlv[c] = muInf;
+            if (calcEddyVis) rev[c] = eddyVisInfRatio * muInf;
+        }
+    }
+}

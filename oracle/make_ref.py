@@ -81,6 +81,8 @@ MG_PATCHES = [
 ANK_PATCHES = [
     (r"^call vecgetarrayf90\(wvec, wvec_pointer, ierr\)$", "wvec_pointer => ank_wvec"),
     (r"^call vecgetarrayf90\(deltaw, dvec_pointer, ierr\)$", "dvec_pointer => ank_dvec"),
+    (r"^call vecgetarrayf90\(wvecturb, wvec_pointer, ierr\)$", "wvec_pointer => ank_wvec"),
+    (r"^call vecgetarrayf90\(deltawturb, dvec_pointer, ierr\)$", "dvec_pointer => ank_dvec"),
     (r"^call vecrestorearrayf90\(.*$", "continue"),
     (r"^call echk\(.*$", "continue"),
     (r"^call mpi_allreduce\(lambdal, lambdap_recv,.*$", "lambdap_recv = lambdal"),
@@ -115,7 +117,7 @@ ENV_INTS = """nw nwf nt1 nt2 equations equationmode turbmodel spacediscr ransequ
  constantpressure linextrapolpressure quadextrapolpressure normalmomentum
  nstepscycling nlluggs nllusgsline approxtotalits ank_chartimestepcode ank_nvec sh_ib sh_jb sh_kb fl_ib fl_jb fl_kb cl_il cl_jl cl_kl cl_ie cl_je cl_ke cl_ib cl_jb cl_kb cl_nbocos mgboundcorr bcdirichlet0 bcneumann
  slidinginterface oversetouterbound domaininterfaceall domaininterfacerhouvw domaininterfacep domaininterfacerho
- domaininterfacetotal""".split()
+ domaininterfacetotal bp_norphans""".split()
 
 BOX_STRIDES = ["1", "(bp_ib + 1)", "(bp_ib + 1) * (bp_jb + 1)", "(bp_ib + 1) * (bp_jb + 1) * (bp_kb + 1)"]
 
@@ -173,6 +175,7 @@ def env_arrays():
     arrs["bp_sfacej"] = refarr("sfacej", "double", ("1", "0", "1"), ("bp_ie", "bp_je", "bp_ke"))
     arrs["bp_sfacek"] = refarr("sfacek", "double", ("1", "1", "0"), ("bp_ie", "bp_je", "bp_ke"))
     arrs["bp_iblank"] = refarr("iblank", "int", *c2)
+    arrs["bp_orphans"] = A("bp_orphans", "int", [("1", "3"), ("1", "bp_norphans")])   # blockPointers orphans(3, nOrphans)
     arrs["bp_globalcell"] = refarr("globalcell", "int", *c2)
     arrs["bp_pori"] = refarr("pori", "int", ("1", "2", "2"), ("bp_il", "bp_jl", "bp_kl"))
     arrs["bp_porj"] = refarr("porj", "int", ("2", "1", "2"), ("bp_il", "bp_jl", "bp_kl"))
@@ -279,8 +282,10 @@ UNITS = [
     ("solver/multiGrid.F90", "multigrid_", ["transfertocoarsegrid", "transfertofinegrid", "setcornerrowhalos",
                                             "setcorrectionscoarsehalos", "executemgcycle"], (), None, MG_PATCHES),
     # ANK: time-step block of the matrix-free operator and the physicality check of the update
-    ("NKSolver/NKSolvers.F90", "anksolver_", ["computetimestepblock", "physicalitycheckank"], (), "anksolver_ref.c", ANK_PATCHES,
+    ("NKSolver/NKSolvers.F90", "anksolver_", ["computetimestepblock", "physicalitycheckank", "physicalitycheckankturb"], (), "anksolver_ref.c", ANK_PATCHES,
      "anksolver"),
+    # overset orphans: average of the valid neighbours (called by whalo1 / whalo2 after wOverset)
+    ("utils/haloExchange.F90", "haloexchange_", ["orphanaverage"], (), "haloexchange_ref.c"),
 ]
 RENAME_MODULES = {"blockpointers": "bp_", "flowutils": "flowutils_", "turbutils": "turbutils_",
                   "residuals": "residuals_", "smoothers": "smoothers_", "sa": "sa_",

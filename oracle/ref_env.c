@@ -27,6 +27,8 @@ double *bp_x, *bp_si, *bp_sj, *bp_sk, *bp_sfacei, *bp_sfacej, *bp_sfacek;
 double *bp_dw, *bp_fw, *bp_dtl, *bp_aa, *bp_radi, *bp_radj, *bp_radk;
 double *bp_ux, *bp_uy, *bp_uz, *bp_vx, *bp_vy, *bp_vz, *bp_wx, *bp_wy, *bp_wz, *bp_qx, *bp_qy, *bp_qz;
 int *bp_iblank, *bp_pori, *bp_porj, *bp_pork;
+int bp_norphans, *bp_orphans;
+double muinf, eddyvisinfratio;
 double *bp_rotmatrixi = NULL, *bp_rotmatrixj = NULL, *bp_rotmatrixk = NULL;
 
 int cpmodel = 1 /* cpConstant */, rkstage = 1, resaveraging = 0, bp_ndom = 1, exchangepressureearly = 0;

@@ -53,6 +53,9 @@ extern double *bp_x, *bp_si, *bp_sj, *bp_sk, *bp_sfacei, *bp_sfacej, *bp_sfacek;
 extern double *bp_dw, *bp_fw, *bp_dtl, *bp_aa, *bp_radi, *bp_radj, *bp_radk;
 extern double *bp_ux, *bp_uy, *bp_uz, *bp_vx, *bp_vy, *bp_vz, *bp_wx, *bp_wy, *bp_wz, *bp_qx, *bp_qy, *bp_qz;
 extern int *bp_iblank, *bp_pori, *bp_porj, *bp_pork;
+/* overset orphans of the block (blockPointers nOrphans, orphans(3, nOrphans)) and the free-stream viscosities orphanAverage falls back to */
+extern int bp_norphans, *bp_orphans;
+extern double muinf, eddyvisinfratio;
 extern double *bp_rotmatrixi, *bp_rotmatrixj, *bp_rotmatrixk;
 
 /* utils procedures the translated code calls */

@@ -335,6 +335,25 @@ def wall_forces(hb, prm, ref_point=(0.0, 0.0, 0.0), p_ref=1.0):
     return np.stack([v[cst[k] - 1:cst[k] + 2] for k in ("ifp", "ifv", "imp", "imv")])
 
 
+def orphan_average(hb, prm, orphans, w_start, w_end, calc_p, calc_lam, calc_eddy, mu_inf, eddy_ratio):
+    """orphanAverage (src/utils/haloExchange.F90:201-354) of the translated reference on block hb; orphans = (n, 3) ints"""
+    global _BOUND
+    set_params(prm, hb.nw)
+    rb = RefBlock(hb, prm)
+    rb.bind()
+    orph = np.ascontiguousarray(np.asarray(orphans, dtype=np.int32).reshape(-1, 3))
+    rb.keep = orph
+    _BOUND = rb
+    _seti("bp_norphans", len(orph))
+    _setp("bp_orphans", orph)
+    _setd("muinf", mu_inf); _setd("eddyvisinfratio", eddy_ratio)
+    winf = (C.c_double * 10).in_dll(lib(), "winf")   # flowVarRefState wInf(1:nw)
+    for q in range(6):
+        winf[q] = prm.wInf[q]
+    lib().haloexchange_orphanaverage(*[C.byref(C.c_int(int(v))) for v in (w_start, w_end, calc_p, 0, calc_lam, calc_eddy)])
+    return rb
+
+
 def set_int(name, value):
     """set an integer module variable of the translated reference (e.g. "rkstage") between calls"""
     _seti(name, value)

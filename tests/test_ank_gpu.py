@@ -249,3 +249,64 @@ def test_device_gmres_on_the_matrix_free_operators(cuda_lib, op):
     assert np.isfinite(x).all() and its >= 1 and abs(its - its_h) <= 1
     assert rn <= np.linalg.norm(b) * (1 + 1e-12)
     assert np.linalg.norm(x - xh) < 2e-2 * np.linalg.norm(xh), np.linalg.norm(x - xh) / np.linalg.norm(xh)
+
+
+def test_turbulence_ksp_pieces(cuda_lib):
+    """decoupled ANK, turbulence KSP: FormFunction_mf_turb (NKSolvers.F90:2540-2612), the matrix-free product over it and
+    physicalityCheckANKTurb (:3212-3335) against the oracle (whose check is pinned bit for bit against the reference)."""
+    import ctypes as C
+
+    from util import FLOW, TURB, case, rel_l2
+
+    prm, hb = case(12, 9, 8)
+    ank = make_ank_params(cfl=5.0, coupled=False, physLSTolTurb=0.99, stepMin=0.01, stepFactor=1.0)
+    ow = hb.d.owned()
+    U = np.ascontiguousarray(np.transpose(hb.w[ow][..., 5], (2, 1, 0)).reshape(-1))
+    rng = np.random.default_rng(5)
+    vin = U * (1.0 + 0.01 * rng.standard_normal(U.size))
+
+    def oracle_F(v):
+        h2 = hb.copy()
+        o = Oracle(h2, prm)
+        o.pressure(False); o.lam_viscosity(False); o.eddy_viscosity(False)
+        o.apply_turb_bc(True); o.apply_flow_bc(True)
+        o.time_step(True)                      # dtl of the last time-step evaluation (state of hb)
+        dtl = h2.dtl.copy()
+        h2.w[ow + (5,)] = np.transpose(v.reshape(hb.d.nz, hb.d.ny, hb.d.nx), (2, 1, 0))
+        o.pressure(False); o.lam_viscosity(False); o.eddy_viscosity(False)
+        o.apply_turb_bc(True); o.apply_flow_bc(True)
+        o.L.orc_etot(C.byref(o.ob), C.byref(prm), 2, hb.d.il, 2, hb.d.jl, 2, hb.d.kl)
+        o.residual_core(TURB)
+        h2.dtl[...] = dtl
+        r = np.empty_like(v)
+        o.L.orc_ank_turb_rvec(C.byref(o.ob), C.byref(prm), C.byref(ank), v.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p))
+        return r
+
+    s = ADFLOW_B200(prm)
+    try:
+        s.addBlock(hb)
+        s.ankSetParams(ank)
+        s.residual(FLOW | TURB | 4)            # refreshes dtl like the residual evaluation before the ANK step
+        r = s.ankFormFunctionTurb(vin)
+        want = oracle_F(vin)
+        assert rel_l2(r, want) < 1e-11, rel_l2(r, want)
+        # matrix-free product = difference quotient of two function evaluations
+        a = rng.standard_normal(U.size) * np.abs(U)
+        h = 1e-6
+        s.ankMffdTurbSetBase(U)
+        y = s.ankMffdTurbApply(a, h)
+        yref = (oracle_F(U + h * a) - oracle_F(U)) / h
+        assert rel_l2(y, yref) < 1e-6, rel_l2(y, yref)
+        # physicality check
+        dv = rng.standard_normal(U.size) * np.abs(U) * 0.4
+        dv[:30] = U[:30] * 500.0
+        lam, dclip = s.ankPhysicalityCheckTurb(U, dv, 1.0)
+        f = Oracle(hb, prm).L.orc_ank_physicality_check_turb
+        f.restype = C.c_double
+        dref = dv.copy()
+        lref = f(C.byref(ank), C.c_long(U.size), U.ctypes.data_as(C.c_void_p), dref.ctypes.data_as(C.c_void_p), C.c_double(1.0))
+        assert lam == lref and np.array_equal(dclip, dref) and np.abs(dref - dv).max() > 0
+        with pytest.raises(Exception):
+            s.ankMffdTurbApply(a[:-1], h)
+    finally:
+        s.close()

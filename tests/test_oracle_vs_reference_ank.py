@@ -75,3 +75,32 @@ def test_physicality_check(coupled):
         assert np.array_equal(d_mine, d_ref)
         if coupled:
             assert np.abs(d_ref - dv).max() > 0   # the clip was exercised
+
+
+def test_physicality_check_turb():
+    """physicalityCheckANKTurb (NKSolvers.F90:3212-3335): the oracle against the translated routine, bit for bit"""
+    prm, hb = case(8, 7, 6)
+    ow = hb.d.owned()
+    ank = make_ank_params(coupled=False, physLSTol=0.2, physLSTolTurb=0.99, stepMin=0.01, stepFactor=1.0)
+    wv = np.ascontiguousarray(np.transpose(hb.w[ow][..., 5], (2, 1, 0)).reshape(-1))
+    rng = np.random.default_rng(12)
+    dv = rng.standard_normal(wv.size) * np.abs(wv) * 0.4
+    dv[:40] = wv[:40] * 500.0     # updates more limiting than stepFactor * stepMin: clipped instead
+    for lam0 in (1.0, 0.05):
+        d_ref, d_mine = dv.copy(), dv.copy()
+        rb.set_params(prm, hb.nw)
+        r = rb.RefBlock(hb, prm)
+        r.bind()
+        bind_ank(ank, 1)
+        L = rb.lib()
+        C.c_void_p.in_dll(L, "ank_wvec").value = wv.ctypes.data
+        C.c_void_p.in_dll(L, "ank_dvec").value = d_ref.ctypes.data
+        C.c_int.in_dll(L, "ank_nvec").value = wv.size
+        lam = C.c_double(lam0)
+        L.anksolver_physicalitycheckankturb(C.byref(lam))
+        f = Oracle(hb, prm).L.orc_ank_physicality_check_turb
+        f.restype = C.c_double
+        mine = f(C.byref(ank), C.c_long(wv.size), wv.ctypes.data_as(C.c_void_p), d_mine.ctypes.data_as(C.c_void_p), C.c_double(lam0))
+        assert mine == lam.value and 0.0 < mine <= lam0
+        assert np.array_equal(d_mine, d_ref)
+        assert np.abs(d_ref - dv).max() > 0

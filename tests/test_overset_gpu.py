@@ -143,3 +143,36 @@ def test_residual_with_overset_pattern_matches_oracle(cuda_lib):
                 assert err < 1e-11, (q, l, err)   # the 8-term interpolation sums differ by FMA contraction (a few ulp)
     finally:
         s.close()
+
+
+def test_orphan_average_on_device_matches_oracle(cuda_lib):
+    """whalo2 with an orphan list (adfb_block_set_orphans): the exchange ends with orphanAverage
+    (src/utils/haloExchange.F90:201-354) -- against the oracle's routine, which is pinned bit for bit against the
+    reference's (tests/test_oracle_vs_reference_orphans.py)."""
+    import ctypes as C
+
+    from oracle.pyoracle import Oracle
+
+    from test_oracle_vs_reference_orphans import orphan_case
+
+    prm, hb, orph = orphan_case()
+    mu_inf, ratio = 1.7e-3, 0.009
+    ho = hb.copy()
+    o = Oracle(ho, prm)
+    flat = np.ascontiguousarray(orph.reshape(-1))
+    o.L.orc_orphan_average(C.byref(o.ob), C.byref(prm), len(orph), flat.ctypes.data_as(C.c_void_p), 1, 6, 1, 1, 1, C.c_double(mu_inf),
+                           C.c_double(ratio))
+    d = hb.d
+    o.L.orc_etot(C.byref(o.ob), C.byref(prm), 2, d.il, 2, d.jl, 2, d.kl)   # whalo2 ends with computeEtotBlock on the owned cells
+    s = ADFLOW_B200(prm)
+    try:
+        s.addBlock(hb)
+        s.setOrphans(0, orph, mu_inf, ratio)
+        s.haloExchange(1, 6, True, True, True)
+        w, p, rlv, rev = s.downloadState(0)
+    finally:
+        s.close()
+    assert np.abs(w - hb.w).max() > 0
+    assert np.array_equal(w[..., (0, 1, 2, 3, 5)], ho.w[..., (0, 1, 2, 3, 5)])   # sums of <= 6 terms in the reference's order
+    assert _close(w[..., 4], ho.w[..., 4])
+    assert np.array_equal(p, ho.p) and np.array_equal(rlv, ho.rlv) and np.array_equal(rev, ho.rev)
