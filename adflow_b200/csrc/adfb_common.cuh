@@ -65,6 +65,35 @@ struct BlockDev {
     const void* bcList;   // device-resident BcList (smoother_kernels.cuh) of the block's subfaces, or null
 };
 
+// Matrix-free product fused into the residual (NKSolvers.F90:437-461 with setW :1331 and setRVec :1262): the kernels that
+// write dw also form y = (dw / volRef [* turbResScale] - F0) / h of their rows.  The record lives in device memory (one per
+// context) and is rewritten before every product, so the captured graph of the residual keeps working with a new h.
+struct MffdDev {
+    const double* F0;   // base residual F(U), AoS per owned cell like getStates
+    double* y;          // result
+    double h;
+    int nw;
+};
+struct MffdEpi {        // per block: the record + offset of the block's first owned cell in the vectors
+    const MffdDev* rec; // nullptr: no fused epilogue
+    long long cell0;
+};
+__host__ __device__ inline void mffd_epilogue(const MffdEpi& m, const Dims& d, int i, int j, int k, int l, double dwv, double volRef, double turbScale) {
+    const MffdDev& R = *m.rec;
+    const long long q = (m.cell0 + ((long long)(k - 2) * d.ny + (j - 2)) * d.nx + (i - 2)) * R.nw + l;
+    const double ovv = 1.0 / volRef;
+#if defined(__CUDA_ARCH__)
+    // every step rounded on its own (no contraction), exactly as k_nkvec forms setRVec and the difference quotient
+    double r = __dmul_rn(dwv, ovv);
+    if (l >= 5) r = __dmul_rn(r, turbScale);
+    R.y[q] = __ddiv_rn(__dsub_rn(r, R.F0[q]), R.h);
+#else
+    double r = dwv * ovv;
+    if (l >= 5) r = r * turbScale;
+    R.y[q] = (r - R.F0[q]) / R.h;
+#endif
+}
+
 // single translation unit (adflow_b200.cu includes every *_kernels.cuh)
 __constant__ AdfbParams c_prm;
 // Programmatic dependent launch: every PDL-launched kernel first waits for its predecessor (grid dependency sync: the

@@ -66,6 +66,9 @@ struct Context {
     size_t nkN = 0;
     bool nkHaveBase = false;
     double nkUnorm = 0.0, nkLastH = 0.0;
+    MffdDev* dMffd = nullptr;     // record of the fused matrix-free product (device) and its pinned host image
+    MffdDev* hMffd = nullptr;
+    bool mffdFuse = false;        // adfb_residual: skip k_state_prep (done by k_nkvec_prep) and form y in the kernels that write dw
     std::string err;
     // multi-rank
     NcclApi nccl;
@@ -331,6 +334,8 @@ int adfb_finalize(void) {
     g.blocks.clear();
     if (g.dRed) cudaFree(g.dRed);
     g.dRed = nullptr; g.dRedN = 0;
+    if (g.dMffd) { cudaFree(g.dMffd); g.dMffd = nullptr; }
+    if (g.hMffd) { cudaFreeHost(g.hMffd); g.hMffd = nullptr; }
     if (g.hRed) cudaFreeHost(g.hRed);
     g.hRed = nullptr;
     if (g.dVec) cudaFree(g.dVec);
@@ -966,7 +971,7 @@ int adfb_residual(int level, unsigned flags) {
     if (!(flags & (ADFB_RES_FLOW | ADFB_RES_TURB))) return fail("adfb_residual: neither flow nor turbulence residual requested");
     for (Block& b : g.blocks)
         if (b.alive && b.level == level && !b.haveMetrics) return fail("adfb_residual: geometry of a block was never set");
-    const unsigned long long key = (1ull << 40) | ((unsigned long long)level << 32) | flags;
+    const unsigned long long key = (1ull << 40) | ((unsigned long long)level << 32) | flags | (g.mffdFuse ? (1ull << 31) : 0ull);
     set_l2_window();
     return run_graphed(key, [&]() { return residual_body(level, flags); });
 }
@@ -1026,7 +1031,7 @@ static int residual_body(int level, unsigned flags) {
         for (Block& b : g.blocks) {
             if (!b.alive || b.level != level) continue;
             // blocketteRes :213-226: p, rlv, rev on owned cells, then turbulence and flow BCs
-            if (launch_state_prep(b.d, b.dev, g.prm, false, (flags & ADFB_RES_FLOW) != 0, g.stream)) return fail("state prep launch failed");
+            if (!g.mffdFuse && launch_state_prep(b.d, b.dev, g.prm, false, (flags & ADFB_RES_FLOW) != 0, g.stream)) return fail("state prep launch failed");
         }
         if (overlap) {
             CK(cudaEventRecord(eFork, g.stream));
@@ -1065,10 +1070,13 @@ static int residual_body(int level, unsigned flags) {
         if (overlap) CK(cudaStreamWaitEvent(g.stream, eJoin, 0));
     }
     const int rest = overlap ? (RC_PREP_HALO | RC_SA_SHELL | RC_FLOW) : RC_ALL;
+    long long cell0 = 0;
     for (Block& b : g.blocks) {
         if (!b.alive || b.level != level) continue;
-        if (launch_residual_core(b.d, b.dev, g.prm, flags, 1.0, 0, 1, g.stream, 0, rest))
+        const MffdEpi mf = {g.mffdFuse ? g.dMffd : nullptr, cell0};
+        if (launch_residual_core(b.d, b.dev, g.prm, flags, 1.0, 0, 1, g.stream, 0, rest, mf))
             return fail("residual kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        cell0 += (long long)b.d.nx * b.d.ny * b.d.nz;
     }
     CK(cudaGetLastError());
     return 0;
@@ -1173,6 +1181,42 @@ static int mffd_core(long long need, double h) {
         h = 1.4901161193847656e-08 * sqrt(1.0 + g.nkUnorm) / sqrt(aa);
     }
     g.nkLastH = h;
+    // fused form (NKSolvers.F90:437-461 in one pass each way): the perturbation is formed together with p / rlv / rev of
+    // the owned cells, and the kernels that write dw (tile kernel, k_sa) form y = (R - F0) / h of their rows; bitwise
+    // the unfused product (same operations on the same operands).  ADFB_MFFD_FUSED=0, or a block the tile kernel does not
+    // take (matrix / upwind dissipation, coarse level), selects the three-pass form.
+    // Measured on C2 (round 2): 0.367 ms fused against 0.361 ms in three passes -- the two extra vector passes cost less
+    // than the strided AoS accesses of the epilogue inside the tile kernel, the product is not bandwidth bound.  The
+    // three-pass form therefore stays the default; ADFB_MFFD_FUSED=1 selects the fused one.
+    bool fuse = false;
+    { const char* e = getenv("ADFB_MFFD_FUSED"); if (e && e[0] == '1') fuse = true; }
+    if (g_kt.on) fuse = false;
+    for (Block& b : g.blocks)
+        if (b.alive && b.level == 1 && !tile_kernel_applies(b.d, b.dev, g.prm)) fuse = false;
+    if (overset_present(1)) fuse = false;   // the exchange rewrites owned fringe cells: p, rhoE must follow (k_etot_owned)
+    if (fuse) {
+        if (!g.dMffd) {
+            CK(cudaMalloc((void**)&g.dMffd, sizeof(MffdDev)));
+            CK(cudaMallocHost((void**)&g.hMffd, sizeof(MffdDev)));
+        }
+        int nw0 = 6;
+        for (Block& b : g.blocks) if (b.alive && b.level == 1) { nw0 = b.nw; break; }
+        g.hMffd->F0 = g.nkF0; g.hMffd->y = g.nkY; g.hMffd->h = h; g.hMffd->nw = nw0;
+        CK(cudaMemcpyAsync(g.dMffd, g.hMffd, sizeof(MffdDev), cudaMemcpyHostToDevice, g.stream));
+        long long off = 0;
+        for (Block& b : g.blocks) {
+            if (!b.alive || b.level != 1) continue;
+            const long long nc = (long long)b.d.nx * b.d.ny * b.d.nz;
+            KT_BEGIN(K_MFFD, g.stream);
+            k_nkvec_prep<<<(unsigned)((nc + 255) / 256), 256, 0, g.stream>>>(b.d, b.dev, b.nw, g.nkA + off, g.nkU + off, g.dMffd, 1);
+            KT_END(K_MFFD, g.stream);
+            off += nc * b.nw;
+        }
+        g.mffdFuse = true;
+        const int rc = adfb_residual(1, kNkFlags);
+        g.mffdFuse = false;
+        return rc ? 1 : 0;
+    }
     if (nk_vec_kernel(g.nkA, g.nkU, nullptr, h, 1)) return 1;
     if (adfb_residual(1, kNkFlags)) return 1;
     if (nk_vec_kernel(nullptr, g.nkF0, g.nkY, h, 3)) return 1;

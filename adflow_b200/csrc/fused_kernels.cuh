@@ -40,7 +40,8 @@
 #endif
 
 #ifndef FT_MAXT
-#define FT_MAXT 384   // max threads per CTA of the tile kernel (1 CTA / SM: 65536 / 384 = 170 registers)
+#define FT_MAXT 256   // max threads per CTA of the tile kernel (1 CTA / SM; 246 registers, no spills; 384 threads with 168 registers
+                      // and spills measured 160 us against 155 us on C2)
 #endif
 
 // ring variables (shared-memory state tiles)
@@ -50,10 +51,13 @@ enum { FV_R = 0, FV_U, FV_V, FV_W, FV_E, FV_P, FV_RLV, FV_REV, FV_AA, FV_SS, FV_
 // LDS / STS instruction); the thread tile TX x TY itself is chosen per block at run time within these bounds.
 #define FT_S0 FT_MAXT   // doubles per thread-tile array (one entry per thread)
 #ifndef FT_S2
-#define FT_S2 512       // doubles per state tile: PX * PY <= 512
+#define FT_S2 352       // doubles per state tile: PX * PY <= FT_S2 (512 with FT_MAXT = 384)
 #endif
 #ifndef FT_MINB
 #define FT_MINB 1        // resident CTAs per SM the register allocation is sized for
+#endif
+#ifndef FT_NSLOT
+#define FT_NSLOT 3        // ring slots of the state tiles: planes k, k+1 and (3 slots) the plane k+2 in flight during step k
 #endif
 #define FT_NFLUX 10     // flux exchange arrays: i faces 0..4, j faces 5..9 (smoother path: central 0..4 + dissipative 5..9, i then j)
 
@@ -68,12 +72,12 @@ struct FTile {
 
 // shared-memory carve-up
 struct FSmem {
-    double* ring;   // [3][FV_NUM][FT_S2]
+    double* ring;   // [FT_NSLOT][FV_NUM][FT_S2]
     double* G;      // [12][FT_S0]  nodal gradients of node plane k
     double* EE;     // [12][FT_S0]  k-edge sums  g(k-1) + g(k)
     double* FX;     // [FT_NFLUX][FT_S0] face fluxes
 };
-#define FT_SMEM_DOUBLES ((size_t)3 * FV_NUM * FT_S2 + (size_t)(24 + FT_NFLUX) * FT_S0)
+#define FT_SMEM_DOUBLES ((size_t)FT_NSLOT * FV_NUM * FT_S2 + (size_t)(24 + FT_NFLUX) * FT_S0)
 
 struct FCell { double r, u, v, w, e, p; };
 
@@ -115,9 +119,11 @@ struct FOwn { FCell m; double rlv, rev, aa, ss; };   // the thread's own cell of
 // Next plane of the same operand into L2: the DRAM -> L2 transfer of step k+1's geometry overlaps the arithmetic of
 // step k, so that the loads of the next step are L2 hits (no register, no scoreboard entry).
 #define FPREF(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#define FPREF1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #else
 #define FLDG(p) (*(p))
 #define FPREF(p) ((void)0)
+#define FPREF1(p) ((void)0)
 #endif
 
 // ---------------------------------------------------------------------------
@@ -323,6 +329,42 @@ FHD void ft_load_face_k(const Dims& d, const BlockDev& b, const FCtx& x, int k, 
     }
 }
 
+// FT_PFL1 = 1: at the start of a step every thread asks for the face operands of THIS step in L1 (they are read one to
+// three phases later); pays only when shared memory leaves L1 room for them (FT_MAXT <= 256: ~100 KB of L1)
+#ifndef FT_PFL1
+#define FT_PFL1 0
+#endif
+FHD void ft_prefetch_faces_l1(const Dims& d, const BlockDev& b, const FCtx& x, int k, bool visc, int doDiss, bool doIJ) {
+    if (!(x.fi || x.fj)) return;
+    const int N = (int)d.N, sJ = (int)d.sJ, sK = (int)d.sK;
+    const int c = x.c0 + sK * k;
+    (void)N; (void)sJ; (void)c;
+    if (doIJ) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) { FPREF1(b.si + m * N + c); FPREF1(b.sj + m * N + c); }
+        FPREF1(b.radI + c); FPREF1(b.radJ + c); FPREF1(b.radJ + c + sJ);
+        if (visc) {
+#pragma unroll
+            for (int l = 0; l < 8; l++) FPREF1(b.vn + l * N + c);
+        }
+    }
+    if (x.own) {
+#pragma unroll
+        for (int m = 0; m < 3; m++) FPREF1(b.sk + m * N + c);
+        FPREF1(b.radK + c + sK);
+        if (visc) {
+#pragma unroll
+            for (int l = 8; l < 12; l++) FPREF1(b.vn + l * N + c);
+        }
+        if (doDiss) {
+            const int c2 = c + 2 * sK;
+#pragma unroll
+            for (int l = 0; l < 5; l++) FPREF1(b.w + l * N + c2);
+            FPREF1(b.p + c2); FPREF1(b.ss + c2);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // phase 1: nodal gradients of node (i, j, k) (allNodalGradients, blockette.F90:5205-5515, gather form as k_nodal)
 // from the planes k (A) and k+1 (B); stores g(k) and, when withE, the k-edge sum g(k-1)+g(k); g(k) becomes gprev.
@@ -520,7 +562,7 @@ FHD void ft_store_flux(const FCtx& x, FSmem& sm, int slot, const double fc[5], c
 // divergence of cell (i, j, k): -Fi(c-1) +Fi(c) -Fj(c-sJ) +Fj(c) -Fk(c-sK) +Fk(c) per variable, then the epilogue
 template <bool MERGED>
 FHD void ft_div(const Dims& d, const BlockDev& b, const FTile& t, const FCtx& x, int k, const FSmem& sm, FRegs& r, FStep& st, double rFil,
-                int persistFw) {
+                int persistFw, const MffdEpi& mf, double turbScale) {
     if (!x.own) return;
     const int N = (int)d.N, sK = (int)d.sK, TX = t.TX;
     const int c = x.c0 + sK * k;
@@ -537,7 +579,9 @@ FHD void ft_div(const Dims& d, const BlockDev& b, const FTile& t, const FCtx& x,
             a += F[(5 + l) * FT_S0 + q0];
             a -= r.kprev[l];
             a += st.kp[l];
-            b.dw[l * N + c] = a * rblank;
+            const double dwv = a * rblank;
+            b.dw[l * N + c] = dwv;
+            if (mf.rec) mffd_epilogue(mf, d, x.i, x.j, k, l, dwv, b.volRef[c], turbScale);
         }
     } else {   // second half: the j exchange is in FX, the i part is in st.acc
 #pragma unroll
@@ -602,13 +646,14 @@ FHD bool ft_var_used(int v, bool viscous, int doDiss) {
 // FT_EARLY = 1: the global operands of a phase are loaded one phase ahead of their use (needs the registers: FT_MAXT <=
 // 256); 0: right before their use (the L2 prefetch of the previous step covers part of the latency)
 #ifndef FT_EARLY
-#define FT_EARLY (FT_MAXT <= 256)
+#define FT_EARLY 0
 #endif
 template <bool VISCOUS, bool MERGED>
 FHD void ft_step_a(const Dims& d, const BlockDev& b, const FTile& t, const FCtx& x, int k, int kb, const double* A, const double* B, FSmem& sm,
                    FRegs& r, FStep& st, int doDiss, bool doIJ) {
     const bool visc = VISCOUS && doDiss;
     const bool pf = k < kb;
+    if (FT_PFL1) ft_prefetch_faces_l1(d, b, x, k, visc, doDiss, doIJ);
     if (FT_EARLY) {
         // face operands of this step: in flight during the nodal phase (gn was loaded during the previous step's k face)
         if (doIJ) { ft_load_face(d, b, x, k, 0, visc, pf, st.gi); ft_load_face(d, b, x, k, 1, visc, pf, st.gj); }
@@ -758,11 +803,11 @@ extern __shared__ __align__(128) double ft_smem[];
 
 template <bool VISCOUS, bool MERGED>
 __global__ void __launch_bounds__(FT_MAXT, FT_MINB) k_flowres(Dims d, BlockDev b, FTile t, double rFil, int doDiss, int persistFw, int nw,
-                                                        const __grid_constant__ FTmaMaps maps) {
+                                                        MffdEpi mf, const __grid_constant__ FTmaMaps maps) {
     ADFB_PDL_SYNC();
     FSmem sm;
     sm.ring = ft_smem;
-    sm.G = ft_smem + 3 * FV_NUM * FT_S2;
+    sm.G = ft_smem + FT_NSLOT * FV_NUM * FT_S2;
     sm.EE = sm.G + 12 * FT_S0;
     sm.FX = sm.EE + 12 * FT_S0;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm.FX + FT_NFLUX * FT_S0);   // 3 mbarriers
@@ -779,18 +824,18 @@ __global__ void __launch_bounds__(FT_MAXT, FT_MINB) k_flowres(Dims d, BlockDev b
 
     if (t.useTma) {
         if (tid == 0) {
-            for (int s = 0; s < 3; s++) ft_mbar_init(&bars[s], 1);
+            for (int s = 0; s < FT_NSLOT; s++) ft_mbar_init(&bars[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         }
         __syncthreads();
     }
-    // asynchronous load of state plane kk into ring slot kk % 3
+    // asynchronous load of state plane kk into ring slot kk % FT_NSLOT
     auto load_plane = [&](int kk) {
-        double* slot = sm.ring + (kk % 3) * (FV_NUM * FT_S2);
+        double* slot = sm.ring + (kk % FT_NSLOT) * (FV_NUM * FT_S2);
         if (t.useTma) {
             if (tid == 0) {
-                unsigned long long* bar = &bars[kk % 3];
+                unsigned long long* bar = &bars[kk % FT_NSLOT];
                 ft_mbar_expect_tx(bar, planeBytes);
 #pragma unroll
                 for (int v = 0; v < FV_NUM; v++) {
@@ -820,13 +865,13 @@ __global__ void __launch_bounds__(FT_MAXT, FT_MINB) k_flowres(Dims d, BlockDev b
         }
     };
     auto wait_plane = [&](int kk) {
-        if (t.useTma) ft_mbar_wait(&bars[kk % 3], (unsigned)(((kk - (ka - 1)) / 3) & 1));
+        if (t.useTma) ft_mbar_wait(&bars[kk % FT_NSLOT], (unsigned)(((kk - (ka - 1)) / FT_NSLOT) & 1));
         else ft_cp_async_wait_all();
     };
 
     load_plane(ka - 1);
     load_plane(ka);
-    load_plane(ka + 1);
+    if (FT_NSLOT >= 3) load_plane(ka + 1);
     FRegs r;
     FStep st;
     ft_prologue_regs(c_prm, d, b, x, ka - 1, r, doDiss, VISCOUS);
@@ -836,9 +881,13 @@ __global__ void __launch_bounds__(FT_MAXT, FT_MINB) k_flowres(Dims d, BlockDev b
     __syncthreads();
 
     for (int k = ka - 1; k <= kb; k++) {
-        const double* A = sm.ring + (k % 3) * (FV_NUM * FT_S2);
-        const double* B = sm.ring + ((k + 1) % 3) * (FV_NUM * FT_S2);
+        const double* A = sm.ring + (k % FT_NSLOT) * (FV_NUM * FT_S2);
+        const double* B = sm.ring + ((k + 1) % FT_NSLOT) * (FV_NUM * FT_S2);
         const bool doIJ = k >= ka;
+        if (FT_NSLOT == 2 && k > ka - 1) {   // two slots: plane k+1 was requested when plane k-1 retired, at the end of the previous step
+            wait_plane(k + 1);
+            __syncthreads();
+        }
         ft_step_a<VISCOUS, MERGED>(d, b, t, x, k, kb, A, B, sm, r, st, doDiss, doIJ);
         __syncthreads();   // G / EE of this plane visible; the previous plane's flux exchange is over
         if (MERGED) {
@@ -850,10 +899,11 @@ __global__ void __launch_bounds__(FT_MAXT, FT_MINB) k_flowres(Dims d, BlockDev b
             __syncthreads();   // i exchange consumed: the flux arrays are free for the j exchange
             ft_step_b<VISCOUS, MERGED>(c_prm, d, b, t, x, k, kb, A, B, sm, r, st, rFil, doDiss, doIJ, 1);
         }
-        if (k + 2 <= kb + 1) wait_plane(k + 2);
-        __syncthreads();   // fluxes visible; G / EE and the slot of plane k are free; plane k+2 has landed
-        if (k + 3 <= kb + 1) load_plane(k + 3);
-        if (doIJ) ft_div<MERGED>(d, b, t, x, k, sm, r, st, rFil, persistFw);
+        if (FT_NSLOT >= 3 && k + 2 <= kb + 1) wait_plane(k + 2);
+        __syncthreads();   // fluxes visible; G / EE and the slot of plane k are free; (3 slots) plane k+2 has landed
+        if (FT_NSLOT >= 3) { if (k + 3 <= kb + 1) load_plane(k + 3); }
+        else if (k + 2 <= kb + 1) load_plane(k + 2);
+        if (doIJ) ft_div<MERGED>(d, b, t, x, k, sm, r, st, rFil, persistFw, mf, c_prm.turbResScale);
 #pragma unroll
         for (int l = 0; l < 10; l++) r.kprev[l] = st.kp[l];
     }
@@ -898,7 +948,7 @@ static int fused_mode() {   // ADFB_FUSED: 0 = off (k_nodal/k_faces/k_div), 1 = 
 
 // returns 0 on success, -1 when the tile kernel does not apply (caller uses the general kernels), > 0 on error
 static int launch_flowres_tile(const Dims& d, const BlockDev& b, const AdfbParams& prm, int nw, double rFil, int doDiss, bool merged,
-                               int persistFw, cudaStream_t stream) {
+                               int persistFw, cudaStream_t stream, MffdEpi mf = MffdEpi{nullptr, 0}) {
     static int nSM = 0;
     static size_t smemMax = 0;
     if (!nSM) {
@@ -932,7 +982,7 @@ static int launch_flowres_tile(const Dims& d, const BlockDev& b, const AdfbParam
     do {                                                                                                                        \
         static bool attrSet = false;                                                                                            \
         if (!attrSet) { cudaFuncSetAttribute(k_flowres<V, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax); attrSet = true; } \
-        e = cudaLaunchKernelEx(&cfg, k_flowres<V, M>, d, b, t, rFil, doDiss, persistFw, nw, maps);                               \
+        e = cudaLaunchKernelEx(&cfg, k_flowres<V, M>, d, b, t, rFil, doDiss, persistFw, nw, mf, maps);                               \
     } while (0)
     if (viscous) { if (merged) FT_LAUNCH(true, true); else FT_LAUNCH(true, false); }
     else { if (merged) FT_LAUNCH(false, true); else FT_LAUNCH(false, false); }

@@ -731,7 +731,7 @@ __device__ __forceinline__ double sa_source(const BlockDev& b, int N, int sJ, in
 // (blockette.F90:623-627, :1872-1897)
 // part: 0 = every owned cell, 1 = cells at least two layers away from the block boundary (their stencil holds no halo
 // cell: they do not need the BCs / the exchange), 2 = the boundary shell
-__global__ void __launch_bounds__(SA_TPB, SA_MINB) k_sa(Dims d, BlockDev b, int part) {
+__global__ void __launch_bounds__(SA_TPB, SA_MINB) k_sa(Dims d, BlockDev b, int part, MffdEpi mf) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
     const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
@@ -754,7 +754,9 @@ __global__ void __launch_bounds__(SA_TPB, SA_MINB) k_sa(Dims d, BlockDev b, int 
     r = sa_visc_dir(b, N, c, sK, b.sk, b.ssum + 6 * N, nu, r);
     r = sa_visc_dir(b, N, c, sJ, b.sj, b.ssum + 3 * N, nu, r);
     r = sa_visc_dir(b, N, c, 1, b.si, b.ssum, nu, r);
-    b.dw[ITU1 * N + c] = -b.volRef[c] * r * rblank;
+    const double dwv = -b.volRef[c] * r * rblank;
+    b.dw[ITU1 * N + c] = dwv;
+    if (mf.rec) mffd_epilogue(mf, d, i, j, k, ITU1, dwv, b.volRef[c], c_prm.turbResScale);
 }
 
 // k_div: flux divergence + sumDwandFw epilogue (blockette.F90:6839-6864) for one owned cell.
@@ -839,9 +841,14 @@ static bool split_faces() {
     if (v < 0) { const char* e = getenv("ADFB_SPLIT_FACES"); v = e ? atoi(e) : 0; }
     return v != 0;
 }
+// true when launch_residual_core hands the flow rows of the full exact residual to the tile kernel
+static bool tile_kernel_applies(const Dims& d, const BlockDev& b, const AdfbParams& prm) {
+    return fused_mode() > 0 && !b.coarse && prm.spaceDiscr == ADFB_DISS_SCALAR && !split_faces();
+}
 enum { RC_PREP_OWNED = 1, RC_PREP_HALO = 2, RC_SA_INNER = 4, RC_SA_SHELL = 8, RC_FLOW = 16, RC_ALL = 31 };
 static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbParams& prm, unsigned flags, double rFil,
-                                int persistFw, int doRad, cudaStream_t stream, int initWr = 0, int parts = RC_ALL) {
+                                int persistFw, int doRad, cudaStream_t stream, int initWr = 0, int parts = RC_ALL,
+                                MffdEpi mf = MffdEpi{nullptr, 0}) {
     const int flowRes = (flags & ADFB_RES_FLOW) != 0;
     const int turbRes = ((flags & ADFB_RES_TURB) != 0) && prm.equations == ADFB_RANS;
     const int updateDt = 1;  // blockette timeStep always computes dtl (blockette.F90:1929-1932)
@@ -878,12 +885,12 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
             cudaStreamCopyAttributes(s_side, stream);   // same L2 access-policy window as the main stream
             cudaEventRecord(s_fork, stream);
             cudaStreamWaitEvent(s_side, s_fork, 0);
-            k_sa<<<g, tr, 0, s_side>>>(d, b, saPart);
+            k_sa<<<g, tr, 0, s_side>>>(d, b, saPart, mf);
             g_kt.launches++; g_kt.count[K_SA]++;
             cudaEventRecord(s_join, s_side);
         } else {
             KT_BEGIN(K_SA, stream);
-            k_sa<<<g, tr, 0, stream>>>(d, b, saPart);
+            k_sa<<<g, tr, 0, stream>>>(d, b, saPart, mf);
             KT_END(K_SA, stream);
         }
     }
@@ -905,11 +912,12 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
     if (flowRes && fused_mode() > 0 && (!persistFw || fusedSmoother) && !b.coarse && prm.spaceDiscr == ADFB_DISS_SCALAR && !dissApprox && !viscApprox && !initWr &&
         !(flags & ADFB_RES_STORE_WALL) && !split_faces()) {
         KT_BEGIN(K_RESID, stream);
-        const int rc = launch_flowres_tile(d, b, prm, (int)((b.p - b.w) / d.N), rFil, doDiss, !persistFw, persistFw, stream);
+        const int rc = launch_flowres_tile(d, b, prm, (int)((b.p - b.w) / d.N), rFil, doDiss, !persistFw, persistFw, stream, mf);
         KT_END(K_RESID, stream);
         if (rc > 0) return 1;
         fusedDone = rc == 0;
     }
+    if (mf.rec && flowRes && !fusedDone) return 1;   // the fused matrix-free epilogue lives in the tile kernel
     if (flowRes && doDiss && !fusedDone) {
         dim3 tn = tune_block("ADFB_NODAL_BLOCK", dim3(32, 4, 2));
         dim3 g((d.ie + tn.x - 1) / tn.x, (d.je + tn.y - 1) / tn.y, (d.ke + tn.z - 1) / tn.z);

@@ -175,18 +175,55 @@ __global__ void __launch_bounds__(256) k_nkvec(Dims d, BlockDev b, int nw, const
     const int k = (int)(cell / ((long long)d.nx * d.ny)) + 2;
     const long long c = ADFB_IDX(i, j, k);
     if (mode <= 1) {
-        double v = mode == 0 ? vec[q] : base[q] + h * vec[q];
+        // U + h a as PETSc's VecWAXPY forms it (product rounded, then the sum: no contraction), identically in k_nkvec_prep
+        double v = mode == 0 ? vec[q] : __dadd_rn(base[q], __dmul_rn(h, vec[q]));
         if (l >= 5) v = dmax_(1e-6 * c_prm.wInf[l], v);
         b.w[l * d.N + c] = v;
     } else {
         const double ovv = 1.0 / b.volRef[c];
-        double r = b.dw[l * d.N + c] * ovv;
-        if (l >= 5) r = b.dw[l * d.N + c] * ovv * c_prm.turbResScale;
-        out[q] = mode == 2 ? r : (r - base[q]) / h;
+        double r = __dmul_rn(b.dw[l * d.N + c], ovv);   // setRVec; each step rounded on its own, like mffd_epilogue
+        if (l >= 5) r = __dmul_rn(r, c_prm.turbResScale);
+        out[q] = mode == 2 ? r : __ddiv_rn(__dsub_rn(r, base[q]), h);
     }
 }
 
 // sum of squares of a device vector (two-pass, deterministic): part[0..nPart) then part[nPart]
+// setW(U + h a) fused with the cell-local preamble of blocketteRes: one pass over the owned cells forms the perturbed state
+// (turbulence clip of setW, NKSolvers.F90:1331-1376) and from it p, rhoE, rlv, rev exactly as k_state_prep does
+__global__ void __launch_bounds__(256) k_nkvec_prep(Dims d, BlockDev b, int nw, const double* __restrict__ vec, const double* __restrict__ base,
+                                                    const MffdDev* __restrict__ rec, int etot) {
+    const long long nOwned = (long long)d.nx * d.ny * d.nz;
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= nOwned) return;
+    const int i = (int)(cell % d.nx) + 2, j = (int)((cell / d.nx) % d.ny) + 2, k = (int)(cell / ((long long)d.nx * d.ny)) + 2;
+    const long long N = d.N, c = ADFB_IDX(i, j, k);
+    const double h = rec->h;
+    double wv[6];
+    for (int l = 0; l < nw; l++) {
+        const long long q = cell * nw + l;
+        double v = __dadd_rn(base[q], __dmul_rn(h, vec[q]));
+        if (l >= 5) v = dmax_(1e-6 * c_prm.wInf[l], v);
+        wv[l] = v;
+        b.w[l * N + c] = v;
+    }
+    const double rho = wv[0], u = wv[1], v = wv[2], w = wv[3];
+    const double v2 = u * u + v * v + w * w;
+    double p = (c_prm.gammaInf - 1.0) * (wv[4] - 0.5 * rho * v2);
+    p = dmax_(p, 1.e-4 * c_prm.pInfCorr);
+    b.p[c] = p;
+    if (etot) b.w[4 * N + c] = (1.0 / (c_prm.gammaInf - 1.0)) * p + 0.5 * rho * v2;
+    if (c_prm.equations == ADFB_EULER) return;
+    const double T = p / (c_prm.RGas * rho);
+    const double rlv = c_prm.muSuth * ((c_prm.TSuth + c_prm.SSuth) / (T + c_prm.SSuth)) * pow(T / c_prm.TSuth, 1.5);
+    b.rlv[c] = rlv;
+    if (c_prm.equations != ADFB_RANS || nw < 6 || b.coarse) return;
+    const double rnuSA = wv[5] * rho;
+    const double chi = rnuSA / rlv;
+    const double chi3 = chi * chi * chi;
+    const double cv13 = c_prm.rsaCv1 * c_prm.rsaCv1 * c_prm.rsaCv1;
+    b.rev[c] = chi3 / (chi3 + cv13) * rnuSA;
+}
+
 __global__ void __launch_bounds__(256) k_sumsq_partial(const double* __restrict__ v, long long n, double* part) {
     __shared__ double s[256];
     double a = 0.0;

@@ -40,7 +40,7 @@ int emul_flowres(int nx, int ny, int nz, const AdfbParams* prm, const EmulArrays
     std::vector<double> smem(FT_SMEM_DOUBLES);
     FSmem sm;
     sm.ring = smem.data();
-    sm.G = sm.ring + (size_t)3 * FV_NUM * FT_S2;
+    sm.G = sm.ring + (size_t)FT_NSLOT * FV_NUM * FT_S2;
     sm.EE = sm.G + (size_t)12 * FT_S0;
     sm.FX = sm.EE + (size_t)12 * FT_S0;
     const bool visc = viscous && doDiss;
@@ -63,7 +63,7 @@ int emul_flowres(int nx, int ny, int nz, const AdfbParams* prm, const EmulArrays
                 const int kb = (ka + t.kChunk - 1 < d.kl) ? ka + t.kChunk - 1 : d.kl;
                 const int gi0 = bx * (t.TX - 1), gj0 = by * (t.TY - 1);
                 auto load_plane = [&](int kk) {
-                    double* slot = sm.ring + (size_t)(kk % 3) * FV_NUM * FT_S2;
+                    double* slot = sm.ring + (size_t)(kk % FT_NSLOT) * FV_NUM * FT_S2;
                     for (int e = 0; e < t.PX * t.PY; e++) {
                         const int py = e / t.PX, px = e - py * t.PX;
                         const int gi = gi0 + px, gj = gj0 + py;
@@ -81,10 +81,11 @@ int emul_flowres(int nx, int ny, int nz, const AdfbParams* prm, const EmulArrays
                     ft_prologue_regs(P, d, b, ctx[tid], ka - 1, regs[tid], doDiss, viscous);
                     if (FT_EARLY && visc) ft_load_nodal(d, b, ctx[tid], ka - 1, true, steps[tid].gn);
                 }
-                load_plane(ka - 1); load_plane(ka); load_plane(ka + 1);
+                load_plane(ka - 1); load_plane(ka);
+                if (FT_NSLOT >= 3) load_plane(ka + 1);
                 for (int k = ka - 1; k <= kb; k++) {
-                    const double* A = sm.ring + (size_t)(k % 3) * FV_NUM * FT_S2;
-                    const double* B = sm.ring + (size_t)((k + 1) % 3) * FV_NUM * FT_S2;
+                    const double* A = sm.ring + (size_t)(k % FT_NSLOT) * FV_NUM * FT_S2;
+                    const double* B = sm.ring + (size_t)((k + 1) % FT_NSLOT) * FV_NUM * FT_S2;
                     const bool doIJ = k >= ka;
                     ALL_THREADS(DISPATCH(ft_step_a, d, b, t, x, k, kb, A, B, sm, r, st, doDiss, doIJ));
                     if (merged) {
@@ -95,13 +96,13 @@ int emul_flowres(int nx, int ny, int nz, const AdfbParams* prm, const EmulArrays
                         ALL_THREADS(DISPATCH(ft_step_b, P, d, b, t, x, k, kb, A, B, sm, r, st, rFil, doDiss, doIJ, 1));
                     }
                     // (barrier) the slot of plane k is free now
-                    if (k + 3 <= kb + 1) {
-                        double* slot = sm.ring + (size_t)(k % 3) * FV_NUM * FT_S2;
+                    if (k + FT_NSLOT <= kb + 1) {
+                        double* slot = sm.ring + (size_t)(k % FT_NSLOT) * FV_NUM * FT_S2;
                         for (int q = 0; q < FV_NUM * FT_S2; q++) slot[q] = nan("");
-                        load_plane(k + 3);
+                        load_plane(k + FT_NSLOT);
                     }
-                    ALL_THREADS(if (doIJ) { if (merged) ft_div<true>(d, b, t, x, k, sm, r, st, rFil, persistFw);
-                                            else ft_div<false>(d, b, t, x, k, sm, r, st, rFil, persistFw); }
+                    ALL_THREADS(if (doIJ) { if (merged) ft_div<true>(d, b, t, x, k, sm, r, st, rFil, persistFw, MffdEpi{nullptr, 0}, 1.0);
+                                            else ft_div<false>(d, b, t, x, k, sm, r, st, rFil, persistFw, MffdEpi{nullptr, 0}, 1.0); }
                                 for (int l = 0; l < 10; l++) r.kprev[l] = st.kp[l]);
                 }
             }

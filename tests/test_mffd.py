@@ -100,3 +100,30 @@ def test_mffd_device_vectors_equal_host_vectors(cuda_lib):
         assert s.L.adfb_mffd_apply_device(a.ctypes.data, a.ctypes.data, a.size, 1e-7) != 0
     finally:
         s.close()
+
+
+def test_fused_product_is_bitwise_the_three_pass_product(cuda_lib):
+    """The matrix-free product with the perturbation formed inside the state preparation and the difference quotient
+    formed by the kernels that write dw (ADFB_MFFD_FUSED=1) against the default three-pass form: same bits."""
+    import os
+
+    prm, hb = case(14, 11, 9)
+    U = state_vec(hb)
+    a = np.random.default_rng(2).standard_normal(U.size) * np.abs(U).clip(1e-6)
+    s = ADFLOW_B200(prm)
+    try:
+        s.addBlock(hb)
+        s.mffdSetBase(U)
+        y0 = s.mffdApply(a, 1e-7).copy()
+        os.environ["ADFB_MFFD_FUSED"] = "1"
+        try:
+            y1 = s.mffdApply(a, 1e-7).copy()
+            y2 = s.mffdApply(a, 3e-7).copy()      # the captured graph follows a new h
+        finally:
+            del os.environ["ADFB_MFFD_FUSED"]
+        y3 = s.mffdApply(a, 3e-7).copy()
+    finally:
+        s.close()
+    assert np.isfinite(y1).all() and np.abs(y1).max() > 0
+    assert np.array_equal(y1, y0)
+    assert np.array_equal(y2, y3) and not np.array_equal(y1, y2)
