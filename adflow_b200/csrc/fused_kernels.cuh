@@ -73,11 +73,14 @@ struct FTile {
 // shared-memory carve-up
 struct FSmem {
     double* ring;   // [FT_NSLOT][FV_NUM][FT_S2]
-    double* G;      // [12][FT_S0]  nodal gradients of node plane k
-    double* EE;     // [12][FT_S0]  k-edge sums  g(k-1) + g(k)
+    double* G;      // [FT_S0][FT_GP]  nodal gradients of node plane k (12 used)
+    double* EE;     // [FT_S0][FT_GP]  k-edge sums  g(k-1) + g(k)
     double* FX;     // [FT_NFLUX][FT_S0] face fluxes
 };
-#define FT_SMEM_DOUBLES ((size_t)FT_NSLOT * FV_NUM * FT_S2 + (size_t)(24 + FT_NFLUX) * FT_S0)
+// nodal gradients and k-edge sums: the 12 values of a node are contiguous (pitch 14 doubles = 112 bytes: 16-byte aligned, and
+// the eight lanes of a 128-bit access hit 32 distinct banks), written and read with 128-bit shared-memory accesses
+#define FT_GP 14
+#define FT_SMEM_DOUBLES ((size_t)FT_NSLOT * FV_NUM * FT_S2 + (size_t)(2 * FT_GP + FT_NFLUX) * FT_S0)
 
 struct FCell { double r, u, v, w, e, p; };
 
@@ -430,12 +433,14 @@ FHD void ft_nodal(const FTile& t, const FCtx& x, const double* __restrict__ A, c
 #pragma unroll
     for (int m = 0; m < 3; m++) r.svK[m] = gn.svKhi[m];
     const double oVol = gn.ovol;
+    double2* Gd = reinterpret_cast<double2*>(sm.G + (size_t)x.o0 * FT_GP);
+    double2* Ed = reinterpret_cast<double2*>(sm.EE + (size_t)x.o0 * FT_GP);
 #pragma unroll
-    for (int m = 0; m < 12; m++) {
-        const double gm = g[m] * oVol;
-        sm.G[m * FT_S0 + x.o0] = gm;
-        if (withE) sm.EE[m * FT_S0 + x.o0] = r.gprev[m] + gm;
-        r.gprev[m] = gm;
+    for (int m = 0; m < 6; m++) {
+        const double g0 = g[2 * m] * oVol, g1 = g[2 * m + 1] * oVol;
+        Gd[m] = make_double2(g0, g1);
+        if (withE) Ed[m] = make_double2(r.gprev[2 * m] + g0, r.gprev[2 * m + 1] + g1);
+        r.gprev[2 * m] = g0; r.gprev[2 * m + 1] = g1;
     }
 }
 
@@ -469,7 +474,15 @@ FHD void ft_face_ij(const AdfbParams& P, const FTile& t, const FCtx& x, int dir,
     if (VISCOUS && doDiss) {
         double g[12];
 #pragma unroll
-        for (int l = 0; l < 12; l++) g[l] = 0.25 * (sm.EE[l * FT_S0 + x.o0 - eo] + sm.EE[l * FT_S0 + x.o0]);
+        {
+            const double2* Ea = reinterpret_cast<const double2*>(sm.EE + (size_t)(x.o0 - eo) * FT_GP);
+            const double2* Eb = reinterpret_cast<const double2*>(sm.EE + (size_t)x.o0 * FT_GP);
+#pragma unroll
+            for (int l = 0; l < 6; l++) {
+                const double2 a = Ea[l], c = Eb[l];
+                g[2 * l] = 0.25 * (a.x + c.x); g[2 * l + 1] = 0.25 * (a.y + c.y);
+            }
+        }
         ff_visc(P, m, q, gf.s1, gf.s2, gf.s3, gf.por, rFil, (FT_OWNCELL ? ow.rlv : A[FV_RLV * FT_S2 + o]) + A[FV_RLV * FT_S2 + o + so],
                 (FT_OWNCELL ? ow.rev : A[FV_REV * FT_S2 + o]) + A[FV_REV * FT_S2 + o + so],
                 A[FV_AA * FT_S2 + o + so] - (FT_OWNCELL ? ow.aa : A[FV_AA * FT_S2 + o]), gf.vn, g, fd);
@@ -500,9 +513,16 @@ FHD void ft_face_k(const AdfbParams& P, const FTile& t, const FCtx& x, const dou
     r.radK = gk.rad1;
     if (VISCOUS && doDiss) {
         double g[12];
+        {
+            const double2* G1 = reinterpret_cast<const double2*>(sm.G + (size_t)(x.o0 - TX - 1) * FT_GP);
+            const double2* G2 = reinterpret_cast<const double2*>(sm.G + (size_t)(x.o0 - TX) * FT_GP);
+            const double2* G3 = reinterpret_cast<const double2*>(sm.G + (size_t)(x.o0 - 1) * FT_GP);
 #pragma unroll
-        for (int l = 0; l < 12; l++)
-            g[l] = 0.25 * (sm.G[l * FT_S0 + x.o0 - TX - 1] + sm.G[l * FT_S0 + x.o0 - TX] + sm.G[l * FT_S0 + x.o0 - 1] + r.gprev[l]);   // own node: still in registers
+            for (int l = 0; l < 6; l++) {   // own node: still in registers
+                const double2 a = G1[l], c = G2[l], e = G3[l];
+                g[2 * l] = 0.25 * (a.x + c.x + e.x + r.gprev[2 * l]); g[2 * l + 1] = 0.25 * (a.y + c.y + e.y + r.gprev[2 * l + 1]);
+            }
+        }
         ff_visc(P, m, q, gk.s1, gk.s2, gk.s3, gk.por, rFil, (FT_OWNCELL ? ow.rlv : A[FV_RLV * FT_S2 + o]) + B[FV_RLV * FT_S2 + o],
                 (FT_OWNCELL ? ow.rev : A[FV_REV * FT_S2 + o]) + B[FV_REV * FT_S2 + o], B[FV_AA * FT_S2 + o] - (FT_OWNCELL ? ow.aa : A[FV_AA * FT_S2 + o]),
                 gk.vn, g, fd);
@@ -801,15 +821,23 @@ struct FTmaMaps { CUtensorMap slab, aa, ss; };
 // Flow rows of the residual for one (i, j) tile and one chunk of k planes.
 extern __shared__ __align__(128) double ft_smem[];
 
+#ifndef FT_LB
+#define FT_LB FT_MAXT   // launch bound: FT_LB > FT_MAXT caps the registers below 65536 / FT_MAXT and leaves room for a co-resident kernel
+#endif
 template <bool VISCOUS, bool MERGED>
-__global__ void __launch_bounds__(FT_MAXT, FT_MINB) k_flowres(Dims d, BlockDev b, FTile t, double rFil, int doDiss, int persistFw, int nw,
+#ifdef FT_MAXNREG
+__global__ void __maxnreg__(FT_MAXNREG) k_flowres
+#else
+__global__ void __launch_bounds__(FT_LB, FT_MINB) k_flowres
+#endif
+(Dims d, BlockDev b, FTile t, double rFil, int doDiss, int persistFw, int nw,
                                                         MffdEpi mf, const __grid_constant__ FTmaMaps maps) {
     ADFB_PDL_SYNC();
     FSmem sm;
     sm.ring = ft_smem;
     sm.G = ft_smem + FT_NSLOT * FV_NUM * FT_S2;
-    sm.EE = sm.G + 12 * FT_S0;
-    sm.FX = sm.EE + 12 * FT_S0;
+    sm.EE = sm.G + FT_GP * FT_S0;
+    sm.FX = sm.EE + FT_GP * FT_S0;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm.FX + FT_NFLUX * FT_S0);   // 3 mbarriers
     const int tid = threadIdx.x;
     const FCtx x = ft_ctx(d, t, tid, blockIdx.x, blockIdx.y);

@@ -878,7 +878,10 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         dim3 g((d.nx + tr.x - 1) / tr.x, (d.ny + tr.y - 1) / tr.y, (d.nz + tr.z - 1) / tr.z);
         if (fork) {
             if (!s_side) {
-                if (cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking) != cudaSuccess) return 1;
+                // lowest priority: the SA row fills the issue slots the tile kernel leaves, it must not take SMs from it
+                int prLo = 0, prHi = 0;
+                cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+                if (cudaStreamCreateWithPriority(&s_side, cudaStreamNonBlocking, prLo) != cudaSuccess) return 1;
                 if (cudaEventCreateWithFlags(&s_fork, cudaEventDisableTiming) != cudaSuccess) return 1;
                 if (cudaEventCreateWithFlags(&s_join, cudaEventDisableTiming) != cudaSuccess) return 1;
             }

@@ -41,13 +41,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C2 = (96, 72, 64)
-# DRAM traffic of one residual step on C2 measured by ncu (profiles/r01d_ncu_summary.md: sum over the six residual kernels)
-NCU_TRAFFIC_BYTES = 568.1e6
+# DRAM traffic of one residual step on C2 measured by ncu (profiles/r02_ncu_summary.md: sum over the four residual kernels
+# k_state_prep + k_sa + k_prep + k_flowres; round 1 had 568.1e6 over six kernels)
+NCU_TRAFFIC_BYTES = 404.0e6
 NCU_TRAFFIC_NOTE = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the residual kernels of one step, ncu --set full capture "
                     "(profiles/)")
 # the second roof (SURVEY section 7 'report both'): the path is FP64-issue bound long before it is HBM bound
 FP64_ROOF = {"note": "B200 FP64 pipe: 64 DFMA lanes / SM / clk x 148 SMs x 1.965 GHz = 18.6 T FP64 instructions/s (37 TFLOP/s); "
-                     "percentages from the ncu capture under profiles/", "fp64_pipe_pct": None, "issue_active_pct": None}
+                     "percentages of the dominant kernel k_flowres from the ncu --set full capture profiles/r02_ncu_summary.md", "fp64_pipe_pct": 26.7, "issue_active_pct": 31.9}
 BYTES_PER_CELL = 176.0  # RANS-SA residual, metrics from x, algorithmic
 METRIC = "Mcells/s RANS-SA residual"
 
@@ -193,14 +194,36 @@ def run_reference(args):
     nx, ny, nz = C2
     # the block is split along j and k into one sub-block per core, like the reference's load balancer splits a block
     # over MPI ranks (loadBalance.F90:2790); an N-GPU job is compared with N such blocks on the same host cores
-    pj, pk = _split_parts(ncores, ny, nz)
-    parts = pj * pk
-    js = [ny * q // pj for q in range(pj + 1)]
-    ks = [nz * q // pk for q in range(pk + 1)]
     nblocks = max(1, args.gpus)
     reps = max(1, 3 // nblocks) if nblocks > 1 else 3
-    jobs = [((nx, js[a + 1] - js[a], ks[q + 1] - ks[q]), (0, js[a], ks[q]), C2, reps * nblocks, q * pj + a) for q in range(pk) for a in range(pj)]
     ctx = mp.get_context("spawn")
+
+    def jobs_for(pj, pk, r):
+        js = [ny * q // pj for q in range(pj + 1)]
+        ks = [nz * q // pk for q in range(pk + 1)]
+        return [((nx, js[a + 1] - js[a], ks[q + 1] - ks[q]), (0, js[a], ks[q]), C2, r, q * pj + a) for q in range(pk) for a in range(pj)]
+
+    # one process per sub-block; more sub-blocks use more cores but carry more halo cells (2 layers per cut) and more
+    # memory traffic per owned cell, so the split is calibrated on this host: candidates up to one process per core, one
+    # step each, the fastest is measured
+    cands = []
+    for want in (16, 32, 64, ncores):
+        c = _split_parts(min(want, ncores), ny, nz)
+        if c not in cands:
+            cands.append(c)
+    calib = {}
+    for (pj, pk) in cands:
+        pool = ctx.Pool(pj * pk)
+        try:
+            pool.map(_ref_worker, jobs_for(pj, pk, 1))          # start-up + warm-up
+            out = pool.map(_ref_worker, jobs_for(pj, pk, 1))
+            calib[(pj, pk)] = max(o[0] for o in out)
+        finally:
+            pool.close()
+            pool.join()
+    pj, pk = min(calib, key=calib.get)
+    parts = pj * pk
+    jobs = jobs_for(pj, pk, reps * nblocks)
     step_ms = []
     pool = ctx.Pool(parts)
     try:
@@ -222,7 +245,7 @@ def run_reference(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(C2, nblocks), "cells": cells,
                    "note": "CPU arm: residual core (blocketteResCore) of %d C2 block(s), each split %d x %d (j x k) over the host cores; "
-                           "the host does not grow with --gpus" % (nblocks, pj, pk)},
+                           "the host does not grow with --gpus; split calibrated over %s (s per step)" % (nblocks, pj, pk, {"%dx%d" % k: round(v, 3) for k, v in calib.items()})},
         "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": parts, "kind": out[0][2],
                          "sample": "%d residual evaluations (blocketteResCore) of %d C2 block(s) per step, %d sub-blocks "
                                    "(1 per core, one process each, %d host cores visible), %s" % (reps, nblocks, parts, ncores, KIND_NOTE[out[0][2]])},
@@ -718,7 +741,7 @@ def main():
             "halo_check": {"status": "ok" if bad == 0 else "FAILED", "halo_cells_checked": checked, "halo_cells_wrong": bad,
                            "res_norms": norms_main,
                            "how": "listed halo cells poisoned on the device, exchanged (NCCL between ranks), compared bit for bit with the "
-                                  "synthetic field of the neighbour block"},
+                                  "donor cells' values, which travel to the checking rank independently (torch point-to-point)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "frac_from_step_time": BYTES_PER_CELL * cells / (ms_step * 1e-3) / 1e9 / peak,
                          "frac_note": "frac: 176 B/cell x cells / SUM of the per-kernel event times of one step (separate timing pass, "

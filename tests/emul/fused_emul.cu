@@ -41,8 +41,8 @@ int emul_flowres(int nx, int ny, int nz, const AdfbParams* prm, const EmulArrays
     FSmem sm;
     sm.ring = smem.data();
     sm.G = sm.ring + (size_t)FT_NSLOT * FV_NUM * FT_S2;
-    sm.EE = sm.G + (size_t)12 * FT_S0;
-    sm.FX = sm.EE + (size_t)12 * FT_S0;
+    sm.EE = sm.G + (size_t)FT_GP * FT_S0;
+    sm.FX = sm.EE + (size_t)FT_GP * FT_S0;
     const bool visc = viscous && doDiss;
     std::vector<FRegs> regs(t.nT);
     std::vector<FCtx> ctx(t.nT);
