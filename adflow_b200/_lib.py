@@ -23,6 +23,7 @@ ABI_SYMBOLS = [
     "adfb_reference_shock_sensor", "adfb_form_function", "adfb_mffd_set_base", "adfb_mffd_apply", "adfb_mffd_apply_device", "adfb_mffd_last_h",
     "adfb_apply_bcs", "adfb_timestep", "adfb_smoother_residual", "adfb_rk_stage", "adfb_rk_cycle", "adfb_dadi_step", "adfb_dadi_cycle", "adfb_sa_ddadi",
     "adfb_block_set_mg", "adfb_mg_restrict", "adfb_mg_prolong", "adfb_mg_cycle",
+    "adfb_set_ground_level", "adfb_get_ground_level", "adfb_mg_prolong_solution",
     "adfb_ank_set_params", "adfb_ank_time_step_mat", "adfb_ank_form_function", "adfb_ank_mffd_set_base", "adfb_ank_mffd_apply", "adfb_ank_mffd_apply_device",
     "adfb_ank_physicality_check", "adfb_ank_form_function_turb", "adfb_ank_mffd_turb_set_base", "adfb_ank_mffd_turb_apply",
     "adfb_ank_physicality_check_turb", "adfb_gmres_solve",
@@ -105,6 +106,9 @@ def load():
     L.adfb_block_set_mg.argtypes = [ci, ci] + [vp] * 9
     L.adfb_mg_restrict.argtypes = [ci]
     L.adfb_mg_prolong.argtypes = [ci]
+    L.adfb_set_ground_level.argtypes = [ci]
+    L.adfb_get_ground_level.argtypes = []
+    L.adfb_mg_prolong_solution.argtypes = [ci]
     L.adfb_mg_cycle.argtypes = [ci, vp, ci]
     L.adfb_ank_set_params.argtypes = [vp]
     L.adfb_ank_form_function.argtypes = [vp, vp, C.c_longlong]

@@ -110,9 +110,14 @@ struct Context {
     double *kryV = nullptr, *kryRed = nullptr;
     size_t kryVN = 0;
     int mgInitWr = 1;   // coarse-level smoother residual starts from wr (0 inside transferToCoarseGrid: from zero)
+    int groundLevel = 1;   // iteration%groundLevel: the finest level of the current multigrid cycle (> 1 during the full-multigrid start-up)
 };
 
 Context g;
+
+// currentLevel > groundLevel: the coarse-level branches of the smoother path (dw = wr start, first-order dissipation, first
+// halos only, frozen eddy viscosity, constant-pressure walls); levels <= groundLevel run the fine-grid routines.
+static inline bool above_ground(int level) { return level > g.groundLevel; }
 
 int fail(const char* fmt, ...) {
     char buf[1024];
@@ -1318,11 +1323,11 @@ static int adfb_smoother_residual_body(int level, int rkStage) {
     for (Block& b : g.blocks) {
         if (!b.alive || b.level != level) continue;
         // coarse level: initRes starts from the residual forcing term (dw = wr)
-        if (launch_residual_core(b.d, b.dev, g.prm, ADFB_RES_FLOW, rFil, 1, 0, g.stream, level > 1 ? g.mgInitWr : 0))
-            return fail("residual launch failed%s", level > 1 && g.prm.spaceDiscrCoarse == ADFB_UPWIND
+        if (launch_residual_core(b.d, b.dev, g.prm, ADFB_RES_FLOW, rFil, 1, 0, g.stream, above_ground(level) ? g.mgInitWr : 0))
+            return fail("residual launch failed%s", above_ground(level) && g.prm.spaceDiscrCoarse == ADFB_UPWIND
                                                         ? ": upwind dissipation is not supported on coarse levels" : "");
         // the primitive <-> conservative round trip that inviscidDissFluxScalarCoarse leaves on w (the matrix form does not convert)
-        if (level > 1 && fabs(rFil) >= 1.e-10 && g.prm.spaceDiscrCoarse == ADFB_DISS_SCALAR) launch_mg_cells1(b.d, b.dev, 2, g.stream);
+        if (above_ground(level) && fabs(rFil) >= 1.e-10 && g.prm.spaceDiscrCoarse == ADFB_DISS_SCALAR) launch_mg_cells1(b.d, b.dev, 2, g.stream);
     }
     CK(cudaGetLastError());
     return 0;
@@ -1345,7 +1350,7 @@ static int adfb_rk_stage_body(int level, int rkStage) {
         // currentCfl = cflCoarse unless currentLevel == 1; second halos only on the ground level (smoothers.F90:131-140)
         AdfbParams prmL = g.prm;
         if (level > 1) prmL.cfl = g.prm.cflCoarse;
-        if (launch_rk_update(b.d, b.dev, prmL, rkStage, g.stream, level > 1 ? 5 : 0)) return fail("RK update launch failed");
+        if (launch_rk_update(b.d, b.dev, prmL, rkStage, g.stream, above_ground(level) ? 5 : 0)) return fail("RK update launch failed");
     }
     // whalo2(level, 1, nwf, T, T, T) / whalo1 on coarse levels (the pattern of the level holds the matching lists):
     // the trailing computeEtotBlock is idempotent here unless an overset pattern interpolates into fringe cells.
@@ -1354,7 +1359,7 @@ static int adfb_rk_stage_body(int level, int rkStage) {
     if (split && halo_exchange_impl(level, 1, 5, 1, 1, overset_present(level), 1)) return 1;
     for (Block& b : g.blocks) {
         if (!b.alive || b.level != level) continue;
-        if (launch_bc_flow(b.d, b.dev, b.subfaces, level > 1 ? 0 : 1, g.stream)) return fail("flow BC launch failed");
+        if (launch_bc_flow(b.d, b.dev, b.subfaces, above_ground(level) ? 0 : 1, g.stream)) return fail("flow BC launch failed");
     }
     if (halo_exchange_impl(level, 1, 5, 1, 1, overset_present(level), split ? 2 : 0)) return 1;
     CK(cudaGetLastError());
@@ -1377,8 +1382,8 @@ static int adfb_dadi_step_body(int level) {
         AdfbParams prmL = g.prm;   // coarse levels: cflCoarse, first halos only, frozen eddy viscosity (smoothers.F90:463-472)
         if (level > 1) prmL.cfl = g.prm.cflCoarse;
         if (launch_dadi(b.d, b.dev, prmL, g.stream)) return fail("DADI launch failed");
-        if (launch_dadi_update(b.d, b.dev, prmL, g.stream, level > 1 ? 5 : 0)) return fail("DADI update launch failed");
-        if (launch_bc_flow(b.d, b.dev, b.subfaces, level > 1 ? 0 : 1, g.stream)) return fail("flow BC launch failed");
+        if (launch_dadi_update(b.d, b.dev, prmL, g.stream, above_ground(level) ? 5 : 0)) return fail("DADI update launch failed");
+        if (launch_bc_flow(b.d, b.dev, b.subfaces, above_ground(level) ? 0 : 1, g.stream)) return fail("flow BC launch failed");
     }
     if (halo_exchange_impl(level, 1, 5, 1, 1, overset_present(level))) return 1;
     CK(cudaGetLastError());
@@ -1908,7 +1913,7 @@ static int adfb_mg_prolong_body(int fineLevel) {
             dim3 tb(32, 4);
             dim3 gr((fd.icEnd - fd.icBeg + 1 + 31) / 32, (fd.jcEnd - fd.jcBeg + 1 + 3) / 4);
             KT_BEGIN(K_BC, g.stream);
-            launch_pdl(k_mg_corr_halos, gr, tb, g.stream, c.d, c.dev, fd, fact);
+            launch_pdl(k_mg_corr_halos, gr, tb, g.stream, c.d, c.dev, fd, fact, 5);
             KT_END(K_BC, g.stream);
         }
         dim3 tb(32, 4, 1);
@@ -1917,7 +1922,7 @@ static int adfb_mg_prolong_body(int fineLevel) {
         launch_pdl(k_mg_prolong, gr, tb, g.stream, f.d, f.dev, c.d, c.dev, c.mg, f.nw);
         KT_END(K_MISC, g.stream);
         // applyAllBC(secondHalo): second halos on the ground level only
-        if (launch_bc_flow(f.d, f.dev, f.subfaces, fineLevel > 1 ? 0 : 1, g.stream)) return fail("flow BC launch failed");
+        if (launch_bc_flow(f.d, f.dev, f.subfaces, above_ground(fineLevel) ? 0 : 1, g.stream)) return fail("flow BC launch failed");
     }
     if (halo_exchange_impl(fineLevel, 1, 5, 1, 1, overset_present(fineLevel))) return 1;
     CK(cudaGetLastError());
@@ -1932,16 +1937,99 @@ int adfb_mg_prolong(int fineLevel) {
     return run_graphed(key, [&]() { return adfb_mg_prolong_body(fineLevel); });
 }
 
+// iteration%groundLevel of the solver loop `do groundLevel = mgStartlevel, 1, -1` (solvers.F90:63): the finest level of the
+// multigrid cycles that follow.  Levels above it take the coarse-level branches; the ground level itself runs the fine-grid
+// routines with cflCoarse (currentLevel /= 1) and the coarse discretisation, which must be the fine one here.
+int adfb_set_ground_level(int level) {
+    ADFB_RANGE("adfb_set_ground_level");
+    NEED_INIT();
+    if (level < 1) return fail("adfb_set_ground_level: level %d", level);
+    bool have = false;
+    for (Block& b : g.blocks) if (b.alive && b.level == level) have = true;
+    if (!have) return fail("adfb_set_ground_level: no block of level %d", level);
+    if (level > 1 && g.havePrm && g.prm.spaceDiscrCoarse != g.prm.spaceDiscr)
+        return fail("adfb_set_ground_level: a coarse ground level needs spaceDiscrCoarse == spaceDiscr (the kernels read one discretisation)");
+    CK(cudaStreamSynchronize(g.stream));
+    g.groundLevel = level;
+    for (Block& b : g.blocks) if (b.alive) b.dev.coarse = b.level > level ? 1 : 0;
+    drop_graphs();
+    return 0;
+}
+int adfb_get_ground_level(void) { return g.groundLevel; }
+
+// transferToFineGrid(corrections = .false.), multiGrid.F90:326-654, the step of the full-multigrid start-up that follows the
+// cycles on ground level fineLevel + 1 (solvers.F90:83-95): the coarse SOLUTION (all nw variables, pressure in place of
+// rho*E, boundary halos by setCorrectionsCoarseHalos with fact = 1) interpolated to the owned cells of `fineLevel`, halos
+// by constant extrapolation (extrapolateSolution / extrapolateViscosities), turbulence BCs, flow BCs twice, exchange, flow
+// BCs, exchange -- all with second halos (currentLevel < groundLevel).  The caller lowers the ground level afterwards.
+static int adfb_mg_prolong_solution_body(int fineLevel) {
+    const int cl = fineLevel + 1;
+    for (Block& c : g.blocks) {
+        if (!c.alive || c.level != cl) continue;
+        if (c.fineBlk < 0) return fail("adfb_mg_prolong_solution: block of level %d without adfb_block_set_mg", cl);
+        Block& f = g.blocks[c.fineBlk];
+        if (c.nw != f.nw) return fail("adfb_mg_prolong_solution: coarse and fine block carry %d / %d variables", c.nw, f.nw);
+        launch_mg_cells1(c.d, c.dev, 3, g.stream);
+        for (const AdfbSubface& sf : c.subfaces) {   // setCorrectionsCoarseHalos: BCData order
+            FaceDev fd = make_face(c.d, sf);
+            dim3 tb(32, 4);
+            dim3 gr((fd.icEnd - fd.icBeg + 1 + 31) / 32, (fd.jcEnd - fd.jcBeg + 1 + 3) / 4);
+            KT_BEGIN(K_BC, g.stream);
+            launch_pdl(k_mg_corr_halos, gr, tb, g.stream, c.d, c.dev, fd, 1.0, f.nw);
+            KT_END(K_BC, g.stream);
+        }
+        {
+            dim3 tb(32, 4, 1);
+            dim3 gr((f.d.nx + 31) / 32, (f.d.ny + 3) / 4, f.d.nz);
+            KT_BEGIN(K_MISC, g.stream);
+            launch_pdl(k_mg_prolong_solution, gr, tb, g.stream, f.d, f.dev, c.d, c.dev, c.mg, f.nw);
+            KT_END(K_MISC, g.stream);
+        }
+        {
+            dim3 tb(32, 4, 2);
+            dim3 gr((f.d.NI + 31) / 32, (f.d.NJ + 3) / 4, (f.d.NK + 1) / 2);
+            KT_BEGIN(K_MISC, g.stream);
+            launch_pdl(k_mg_extrapolate, gr, tb, g.stream, f.d, f.dev, f.nw);
+            KT_END(K_MISC, g.stream);
+        }
+        const bool rans = g.prm.equations == ADFB_RANS;
+        if (rans && launch_bc_turb(f.d, f.dev, f.subfaces, 1, g.stream)) return fail("turbulence BC launch failed");
+        if (launch_bc_flow(f.d, f.dev, f.subfaces, 1, g.stream)) return fail("flow BC launch failed");
+        if (launch_bc_flow(f.d, f.dev, f.subfaces, 1, g.stream)) return fail("flow BC launch failed");
+    }
+    int nwAll = 5;
+    for (Block& f : g.blocks) if (f.alive && f.level == fineLevel) nwAll = f.nw;
+    if (halo_exchange_impl(fineLevel, 1, nwAll, 1, 1, overset_present(fineLevel))) return 1;
+    for (Block& f : g.blocks) {
+        if (!f.alive || f.level != fineLevel) continue;
+        if (launch_bc_flow(f.d, f.dev, f.subfaces, 1, g.stream)) return fail("flow BC launch failed");
+    }
+    if (halo_exchange_impl(fineLevel, 1, nwAll, 1, 1, overset_present(fineLevel))) return 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+int adfb_mg_prolong_solution(int fineLevel) {
+    ADFB_RANGE("adfb_mg_prolong_solution");
+    NEED_INIT();
+    if (!g.havePrm) return fail("adfb_mg_prolong_solution: adfb_set_params has not been called");
+    if (fineLevel < 1 || g.groundLevel != fineLevel + 1)
+        return fail("adfb_mg_prolong_solution: the ground level must be %d (adfb_set_ground_level), it is %d", fineLevel + 1, g.groundLevel);
+    const unsigned long long key = (11ull << 40) | ((unsigned long long)fineLevel << 32);
+    set_l2_window();
+    return run_graphed(key, [&]() { return adfb_mg_prolong_solution_body(fineLevel); });
+}
+
 // executeMGCycle, multiGrid.F90:825-955, for the cycling strategy of setCycleStrategy (:957-1030): entries
 // -1 = prolongate to the next finer level, 0 = smoothing step, +1 = restrict to the next coarser level.
 // Ground level 1.  The turbulence solve and the final residual of the cycle are included (:933-951).
 static int adfb_mg_cycle_body(int nSteps, const int* cycling, int smoother) {
-    int level = 1;
+    const int ground = g.groundLevel;
+    int level = ground;
     for (int n = 0; n < nSteps; n++) {
         switch (cycling[n]) {
             case -1:
                 level -= 1;
-                if (level < 1) return fail("adfb_mg_cycle: cycling strategy leaves the grid hierarchy");
+                if (level < ground) return fail("adfb_mg_cycle: cycling strategy leaves the grid hierarchy");
                 if (adfb_mg_prolong(level)) return 1;
                 break;
             case 0:
@@ -1950,7 +2038,7 @@ static int adfb_mg_cycle_body(int nSteps, const int* cycling, int smoother) {
                     if (adfb_smoother_residual(level, 0)) return 1;
                 }
                 if (smoother == 0) { if (adfb_rk_cycle(level)) return 1; }
-                else if (adfb_dadi_cycle(level, smoother)) return 1;   // DADISmoother: nSubiterations steps on every level (groundLevel == 1)
+                else if (adfb_dadi_cycle(level, ground == 1 ? smoother : 1)) return 1;   // DADISmoother: nSubiterations steps on every level if groundLevel == 1, else one (smoothers.F90:400)
                 break;
             case 1:
                 if (adfb_mg_restrict(level)) return 1;
@@ -1959,11 +2047,11 @@ static int adfb_mg_cycle_body(int nSteps, const int* cycling, int smoother) {
             default: return fail("adfb_mg_cycle: cycling entry %d", cycling[n]);
         }
     }
-    if (level != 1) return fail("adfb_mg_cycle: the strategy does not end on the ground level");
+    if (level != ground) return fail("adfb_mg_cycle: the strategy does not end on the ground level");
     if (g.prm.equations == ADFB_RANS)
-        if (adfb_sa_ddadi(1, g.prm.nSubiterTurb)) return 1;
-    if (adfb_timestep(1, 0)) return 1;
-    return adfb_smoother_residual(1, 0);
+        if (adfb_sa_ddadi(ground, g.prm.nSubiterTurb)) return 1;
+    if (adfb_timestep(ground, 0)) return 1;
+    return adfb_smoother_residual(ground, 0);
 }
 int adfb_mg_cycle(int nSteps, const int* cycling, int smoother) {
     ADFB_RANGE("adfb_mg_cycle");

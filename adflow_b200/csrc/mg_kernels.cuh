@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(256) k_mg_corner_rows(Dims d, BlockDev b) {
 }
 
 // mode 0: w1 = w, p1 = p (1:ie);  mode 1: corrections w -= w1, w(irhoE) = p - p1 (1:ie);
-// mode 2: the w round trip of inviscidDissFluxScalarCoarse (1:ie)
+// mode 2: the w round trip of inviscidDissFluxScalarCoarse (1:ie);  mode 3: w(irhoE) = p (1:ie), the solution
+// transfer of the full-multigrid start-up (transferToFineGrid(.false.), multiGrid.F90:455-470)
 __global__ void __launch_bounds__(256) k_mg_cells1(Dims d, BlockDev b, int mode) {
     ADFB_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
@@ -149,6 +150,8 @@ __global__ void __launch_bounds__(256) k_mg_cells1(Dims d, BlockDev b, int mode)
 #pragma unroll
         for (int l = 0; l < 4; l++) b.w[l * N + c] = b.w[l * N + c] - b.w1[l * N + c];
         b.w[4 * N + c] = b.p[c] - b.p1[c];
+    } else if (mode == 3) {
+        b.w[4 * N + c] = b.p[c];
     } else {
         const double rho = b.w[c];
         const double rhoi = 1.0 / rho;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(256) k_mg_forcing(Dims d, BlockDev b, double f
     }
 }
 
-__global__ void __launch_bounds__(128) k_mg_corr_halos(Dims d, BlockDev b, FaceDev f, double fact) {
+__global__ void __launch_bounds__(128) k_mg_corr_halos(Dims d, BlockDev b, FaceDev f, double fact, int nVarInt) {
     ADFB_PDL_SYNC();
     const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
     const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
@@ -199,9 +202,9 @@ __global__ void __launch_bounds__(128) k_mg_corr_halos(Dims d, BlockDev b, FaceD
         w[2 * N + c1] = v - vn * nny;
         w[3 * N + c1] = ww - vn * nnz;
         w[4 * N + c1] = w[4 * N + c2];
+        for (int l = 5; l < nVarInt; l++) w[l * N + c1] = w[l * N + c2];
     } else {
-#pragma unroll
-        for (int l = 0; l < 5; l++) w[l * N + c1] = fact * w[l * N + c2];
+        for (int l = 0; l < nVarInt; l++) w[l * N + c1] = fact * w[l * N + c2];
     }
 }
 
@@ -245,6 +248,63 @@ __global__ void __launch_bounds__(128) k_mg_prolong(Dims d, BlockDev b, Dims dc,
     const double chi3 = chi * chi * chi;
     const double cv13 = c_prm.rsaCv1 * c_prm.rsaCv1 * c_prm.rsaCv1;
     b.rev[c] = chi3 / (chi3 + cv13) * rnuSA;
+}
+
+// transferToFineGrid(corrections = .false.), multiGrid.F90:468-552: the SOLUTION of the coarse block (all nw variables, the
+// pressure in the place of rho*E) interpolated to the owned cells of the fine block; p, then computeEtotBlock /
+// computeLamViscosity / computeEddyViscosity of the owned cells fused in
+__global__ void __launch_bounds__(128) k_mg_prolong_solution(Dims d, BlockDev b, Dims dc, BlockDev cb, MgTables t, int nw) {
+    ADFB_PDL_SYNC();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
+    if (i > d.il || j > d.jl || k > d.kl) return;
+    const long long N = d.N, NC = dc.N, c = ADFB_IDX(i, j, k);
+    const int ii = t.cI[i], ii1 = t.cI[i + d.ie + 1], jj = t.cJ[j], jj1 = t.cJ[j + d.je + 1], kk = t.cK[k], kk1 = t.cK[k + d.ke + 1];
+#define CI_(a, b_, c_) ((long long)(a) + dc.sJ * (long long)(b_) + dc.sK * (long long)(c_))
+    const long long a000 = CI_(ii, jj, kk), a100 = CI_(ii1, jj, kk), a010 = CI_(ii, jj1, kk), a001 = CI_(ii, jj, kk1);
+    const long long a110 = CI_(ii1, jj1, kk), a101 = CI_(ii1, jj, kk1), a011 = CI_(ii, jj1, kk1), a111 = CI_(ii1, jj1, kk1);
+#undef CI_
+    double v[6];
+    for (int l = 0; l < nw && l < 6; l++) {
+        const double* ww = cb.w + l * NC;
+        const double t0 = __dmul_rn(0.421875, ww[a000]);
+        const double t1 = __dmul_rn(0.140625, (ww[a100] + ww[a010]) + ww[a001]);
+        const double t2 = __dmul_rn(0.046875, (ww[a110] + ww[a101]) + ww[a011]);
+        const double t3 = __dmul_rn(0.015625, ww[a111]);
+        v[l] = __dadd_rn(__dadd_rn(__dadd_rn(t0, t1), t2), t3);
+    }
+    const double rho = v[0], u = v[1], vv = v[2], w = v[3], p = v[4];
+    b.w[c] = rho; b.w[N + c] = u; b.w[2 * N + c] = vv; b.w[3 * N + c] = w; b.p[c] = p;
+    b.w[4 * N + c] = (1.0 / (c_prm.gammaInf - 1.0)) * p + 0.5 * rho * (u * u + vv * vv + w * w);
+    if (nw >= 6) b.w[5 * N + c] = v[5];
+    if (c_prm.equations == ADFB_EULER) return;
+    const double rlv = lam_visc(p, rho);
+    b.rlv[c] = rlv;
+    if (c_prm.equations != ADFB_RANS || nw < 6 || b.coarse) return;
+    const double rnuSA = v[5] * rho;
+    const double chi = rnuSA / rlv;
+    const double chi3 = chi * chi * chi;
+    const double cv13 = c_prm.rsaCv1 * c_prm.rsaCv1 * c_prm.rsaCv1;
+    b.rev[c] = chi3 / (chi3 + cv13) * rnuSA;
+}
+
+// extrapolateSolution + extrapolateViscosities, multiGrid.F90:656-823: constant extrapolation into the halos, i then j then k
+// with the earlier directions' halos taken along -- every halo cell receives the owned cell with the clamped indices
+__global__ void __launch_bounds__(256) k_mg_extrapolate(Dims d, BlockDev b, int nw) {
+    ADFB_PDL_SYNC();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z;
+    if (i > d.ib || j > d.jb || k > d.kb) return;
+    const int ic = i < 2 ? 2 : (i > d.il ? d.il : i), jc = j < 2 ? 2 : (j > d.jl ? d.jl : j), kc = k < 2 ? 2 : (k > d.kl ? d.kl : k);
+    if (ic == i && jc == j && kc == k) return;
+    const long long N = d.N, c = ADFB_IDX(i, j, k), s = ADFB_IDX(ic, jc, kc);
+    for (int l = 0; l < nw; l++) b.w[l * N + c] = b.w[l * N + s];
+    b.p[c] = b.p[s];
+    if (c_prm.equations == ADFB_EULER) return;
+    b.rlv[c] = b.rlv[s];
+    if (c_prm.equations == ADFB_RANS) b.rev[c] = b.rev[s];
 }
 
 }  // namespace

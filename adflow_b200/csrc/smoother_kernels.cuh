@@ -510,6 +510,84 @@ __global__ void __launch_bounds__(128) k_bc_frame_item(Dims d, BlockDev b, const
     else bc_flow_cell(d, b, f, ia, jb, secondHalo, kind);
 }
 
+// One LEVEL of the ordered BC sweep.  Two items of the reference's ordered list (subface, kind) can only influence each other
+// when they touch common cells: subfaces on faces of different index directions (they share the edge / corner halos of
+// the block), or the same cells of one face (turbulence BC and flow BC of one subface both write the eddy-viscosity halo).
+// Subfaces on opposite faces, disjoint subfaces of one face and the two symmetry phases of one subface read and write
+// disjoint cells.  Items are given the level 1 + max(level of the earlier items they conflict with); the items of one level
+// run in one launch (blockIdx.z = item), the levels in the reference's order -- every conflicting pair keeps its order,
+// so the halos are the reference's bit for bit, in about half the launches.
+struct BcLevel {
+    int n;
+    short sub[ADFB_BC_MAXITEMS], kind[ADFB_BC_MAXITEMS];
+};
+__global__ void __launch_bounds__(128) k_bc_level(Dims d, BlockDev b, const BcList* __restrict__ Lp, BcLevel lv, int secondHalo) {
+    ADFB_PDL_SYNC();
+    const FaceDev& f = Lp->f[lv.sub[blockIdx.z]];
+    const int kind = lv.kind[blockIdx.z];
+    const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
+    const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
+    if (ia > f.icEnd || jb > f.jcEnd) return;
+    if (kind == 3) bc_turb_cell(d, b, f, ia, jb, secondHalo);
+    else bc_flow_cell(d, b, f, ia, jb, secondHalo, kind);
+}
+
+// The whole ordered BC sweep of a block in ONE launch, exact.  A face cell (a, b) of a subface reads the two owned cells
+// and writes the two halo cells of its own grid line; it can only meet cells of a subface of an ADJACENT face when one of its
+// in-plane indices lies within three cells of that face (indices 0..3 or l-1..l+1: the neighbour's halos 0, 1 and the owned
+// cells 2, 3 its BC reads -- and vice versa).  So
+//   bulk  = in-plane indices 4 .. l-2 in both directions: conflict-free with every other subface, any order;
+//   frame = the rest of the subface (three layers along each block edge): applied in the reference's order.
+// CTA 0 walks the LEVELS of the ordered item list (bc_items_conflict) over the frames with a barrier between levels --
+// a frame level is ~1000 cells, one pass of the CTA -- while the other CTAs apply turbulence + flow BCs to the bulk cells.
+struct BcSweep {
+    int nLevels, nItems;
+    short sub[ADFB_BC_MAXITEMS], kind[ADFB_BC_MAXITEMS];   // items sorted by level (stable)
+    short levelBegin[ADFB_BC_MAXITEMS + 1];
+    int bulkBegin[ADFB_BC_MAXSUB + 1];                      // first bulk CTA of every subface (32 x 16 patches)
+};
+__device__ __forceinline__ void bc_bulk_box(const FaceDev& f, int la, int lb, int* a0, int* a1, int* b0, int* b1) {
+    *a0 = f.icBeg > 4 ? f.icBeg : 4; *a1 = f.icEnd < la - 2 ? f.icEnd : la - 2;
+    *b0 = f.jcBeg > 4 ? f.jcBeg : 4; *b1 = f.jcEnd < lb - 2 ? f.jcEnd : lb - 2;
+    if (*a1 < *a0 || *b1 < *b0) { *a0 = f.icBeg; *a1 = f.icEnd; *b0 = f.jcEnd + 1; *b1 = f.jcEnd; }   // no bulk: all rows are frame
+}
+__global__ void __launch_bounds__(512) k_bc_sweep(Dims d, BlockDev b, const BcList* __restrict__ Lp, BcSweep sw, int secondHalo, int withTurb,
+                                                  int withFlow) {
+    ADFB_PDL_SYNC();
+    const BcList& L = *Lp;
+    if (blockIdx.x == 0) {
+        const int tid = threadIdx.y * 32 + threadIdx.x;
+        for (int l = 0; l < sw.nLevels; l++) {
+            for (int it = sw.levelBegin[l]; it < sw.levelBegin[l + 1]; it++) {
+                const int s = sw.sub[it], kind = sw.kind[it];
+                const FaceDev& f = L.f[s];
+                int a0, a1, b0, b1;
+                bc_bulk_box(f, L.la[s], L.lb[s], &a0, &a1, &b0, &b1);
+                for (int q = tid;; q += 512) {
+                    int ia, jb;
+                    if (!frame_cell(q, f.icBeg, f.icEnd, f.jcBeg, f.jcEnd, a0, a1, b0, b1, &ia, &jb)) break;
+                    if (kind == 3) bc_turb_cell(d, b, f, ia, jb, secondHalo);
+                    else bc_flow_cell(d, b, f, ia, jb, secondHalo, kind);
+                }
+            }
+            __syncthreads();
+        }
+        return;
+    }
+    const int cta = blockIdx.x - 1;
+    int s = 0;
+    while (s + 1 < L.n && cta >= sw.bulkBegin[s + 1]) s++;
+    const FaceDev& f = L.f[s];
+    int a0, a1, b0, b1;
+    bc_bulk_box(f, L.la[s], L.lb[s], &a0, &a1, &b0, &b1);
+    if (b1 < b0) return;
+    const int local = cta - sw.bulkBegin[s];
+    const int nbx = (a1 - a0 + 1 + 31) / 32;
+    const int ia = (local % nbx) * 32 + threadIdx.x + a0, jb = (local / nbx) * 16 + threadIdx.y + b0;
+    if (ia > a1 || jb > b1) return;
+    bc_all_cell(d, b, f, ia, jb, secondHalo, withTurb, withFlow);
+}
+
 // ---------------------------------------------------------------------------
 // executeRkStage part 1: dw *= cfl*etaRK(stage)*dtl, smoothers.F90:196-218
 __global__ void __launch_bounds__(256) k_rk_scale(Dims d, BlockDev b, double tmp) {
@@ -840,7 +918,8 @@ __global__ void __launch_bounds__(256) k_wall_forces(Dims d, BlockDev b, FaceDev
 
 }  // namespace
 
-// ADFB_BC_FUSED: 0 (default) = one launch per subface and phase over all of its cells, chained by programmatic dependent
+// ADFB_BC_FUSED: 5 = the whole sweep in one launch, exact (k_bc_sweep: bulk cells by all CTAs, the ordered frames by CTA 0);
+// 4 = one launch per LEVEL of mutually independent items (k_bc_level); 0 = one launch per subface and phase over all of its cells, chained by programmatic dependent
 // launch (13 launches of ~5 us for the bench block); 3 = the whole ordered sweep in one launch, items ordered by a device-side
 // counter (k_bc_chain: parity-clean, but the ticket / fence / counter hand-over costs 5.3 us per item, measured 69 us per sweep
 // against 65 us for the launch chain); 1 = one launch for the
@@ -852,10 +931,106 @@ static int bc_mode() {
     if (v < 0) { const char* e = getenv("ADFB_BC_FUSED"); v = e ? atoi(e) : 0; }
     return v;
 }
+// the reference's ordered list of (subface, kind) items of one BC sweep (applyAllTurbBCThisBlock, then applyAllBC_block in its
+// BC-class order: BCRoutines.F90:81-216); kind 3 = turbulence BC, 1 / 2 = symmetry first / second halo, 0 = the other classes
+static std::vector<std::pair<int, int>> bc_ordered_items(const std::vector<AdfbSubface>& subs, int secondHalo, int withTurb, int withFlow) {
+    std::vector<std::pair<int, int>> it;
+    const int n = (int)subs.size();
+    if (withTurb) for (int q = 0; q < n; q++) it.emplace_back(q, 3);
+    if (withFlow) {
+        for (int q = 0; q < n; q++) if (subs[q].bcType == ADFB_BC_SYMM) it.emplace_back(q, 1);
+        if (secondHalo) for (int q = 0; q < n; q++) if (subs[q].bcType == ADFB_BC_SYMM) it.emplace_back(q, 2);
+        for (int q = 0; q < n; q++) if (subs[q].bcType == ADFB_BC_SYMMPOLAR) it.emplace_back(q, 1);
+        if (secondHalo) for (int q = 0; q < n; q++) if (subs[q].bcType == ADFB_BC_SYMMPOLAR) it.emplace_back(q, 2);
+        const int order[8][2] = {{ADFB_BC_NSWALL_ADIABATIC, -1}, {ADFB_BC_NSWALL_ISOTHERMAL, -1}, {ADFB_BC_FARFIELD, -1},
+                                 {ADFB_BC_SUBSONIC_OUTFLOW, -1}, {ADFB_BC_SUBSONIC_INFLOW, -1}, {ADFB_BC_EXTRAP, ADFB_BC_SUPERSONIC_OUTFLOW},
+                                 {ADFB_BC_EULERWALL, -1}, {ADFB_BC_SUPERSONIC_INFLOW, -1}};
+        for (int gq = 0; gq < 8; gq++)
+            for (int q = 0; q < n; q++)
+                if (subs[q].bcType == order[gq][0] || subs[q].bcType == order[gq][1]) it.emplace_back(q, 0);
+    }
+    return it;
+}
+// can two items of the ordered list touch common cells?
+static bool bc_items_conflict(const std::vector<AdfbSubface>& subs, std::pair<int, int> a, std::pair<int, int> c) {
+    const AdfbSubface& A = subs[a.first];
+    const AdfbSubface& C = subs[c.first];
+    if ((A.faceId - 1) / 2 != (C.faceId - 1) / 2) return true;    // faces of different directions share edge / corner halos
+    if (A.faceId != C.faceId) return false;                       // opposite faces
+    if (a.first == c.first) {                                     // one subface: the symmetry phases are disjoint, the rest is not
+        const bool symPhases = (a.second == 1 && c.second == 2) || (a.second == 2 && c.second == 1);
+        return !symPhases;
+    }
+    const bool apart = A.icEnd < C.icBeg || C.icEnd < A.icBeg || A.jcEnd < C.jcBeg || C.jcEnd < A.jcBeg;
+    return !apart;                                                // subfaces of one face: disjoint unless their ranges overlap
+}
 // all BCs of a block: bulk launch + ordered frames; returns -1 when the general path must be used
 static int launch_bc_fused(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, int secondHalo, int withTurb, int withFlow,
                            cudaStream_t s) {
     if (!bc_mode() || subs.empty() || (int)subs.size() > ADFB_BC_MAXSUB || !b.bcList) return -1;
+    if (bc_mode() == 5) {
+        const std::vector<std::pair<int, int>> items = bc_ordered_items(subs, secondHalo, withTurb, withFlow);
+        if (items.empty()) return 0;
+        if ((int)items.size() > ADFB_BC_MAXITEMS) return -1;
+        std::vector<int> level(items.size(), 1);
+        int nLevels = 1;
+        for (size_t q = 0; q < items.size(); q++) {
+            for (size_t r = 0; r < q; r++)
+                if (level[r] >= level[q] && bc_items_conflict(subs, items[r], items[q])) level[q] = level[r] + 1;
+            if (level[q] > nLevels) nLevels = level[q];
+        }
+        BcSweep sw;
+        memset(&sw, 0, sizeof sw);
+        sw.nLevels = nLevels;
+        for (int l = 1; l <= nLevels; l++) {
+            sw.levelBegin[l - 1] = (short)sw.nItems;
+            for (size_t q = 0; q < items.size(); q++)
+                if (level[q] == l) { sw.sub[sw.nItems] = (short)items[q].first; sw.kind[sw.nItems] = (short)items[q].second; sw.nItems++; }
+        }
+        sw.levelBegin[nLevels] = (short)sw.nItems;
+        int nBulk = 0;
+        for (size_t q = 0; q < subs.size(); q++) {
+            const AdfbSubface& sf = subs[q];
+            const int la = (sf.faceId == ADFB_IMIN || sf.faceId == ADFB_IMAX) ? d.jl : d.il;
+            const int lb = (sf.faceId == ADFB_KMIN || sf.faceId == ADFB_KMAX) ? d.jl : d.kl;
+            const int a0 = std::max(sf.icBeg, 4), a1 = std::min(sf.icEnd, la - 2), b0 = std::max(sf.jcBeg, 4), b1 = std::min(sf.jcEnd, lb - 2);
+            sw.bulkBegin[q] = nBulk;
+            if (a1 >= a0 && b1 >= b0) nBulk += ((a1 - a0 + 1 + 31) / 32) * ((b1 - b0 + 1 + 15) / 16);
+        }
+        sw.bulkBegin[subs.size()] = nBulk;
+        KT_BEGIN(K_BC, s);
+        launch_pdl(k_bc_sweep, dim3((unsigned)(1 + nBulk)), dim3(32, 16), s, d, b, (const BcList*)b.bcList, sw, secondHalo, withTurb, withFlow);
+        KT_END(K_BC, s);
+        return (int)cudaGetLastError();
+    }
+    if (bc_mode() == 4) {
+        const std::vector<std::pair<int, int>> items = bc_ordered_items(subs, secondHalo, withTurb, withFlow);
+        if (items.empty()) return 0;
+        if ((int)items.size() > ADFB_BC_MAXITEMS) return -1;
+        std::vector<int> level(items.size(), 1);
+        int nLevels = 1;
+        for (size_t q = 0; q < items.size(); q++) {
+            for (size_t r = 0; r < q; r++)
+                if (level[r] >= level[q] && bc_items_conflict(subs, items[r], items[q])) level[q] = level[r] + 1;
+            if (level[q] > nLevels) nLevels = level[q];
+        }
+        for (int l = 1; l <= nLevels; l++) {
+            BcLevel lv;
+            lv.n = 0;
+            int ma = 1, mb = 1;
+            for (size_t q = 0; q < items.size(); q++) {
+                if (level[q] != l) continue;
+                const AdfbSubface& sf = subs[items[q].first];
+                lv.sub[lv.n] = (short)items[q].first; lv.kind[lv.n] = (short)items[q].second; lv.n++;
+                ma = std::max(ma, sf.icEnd - sf.icBeg + 1);
+                mb = std::max(mb, sf.jcEnd - sf.jcBeg + 1);
+            }
+            KT_BEGIN(K_BC, s);
+            launch_pdl(k_bc_level, dim3((ma + 31) / 32, (mb + 3) / 4, (unsigned)lv.n), dim3(32, 4), s, d, b, (const BcList*)b.bcList, lv, secondHalo);
+            KT_END(K_BC, s);
+        }
+        return (int)cudaGetLastError();
+    }
     if (bc_mode() == 3) {
         BcItems it;
         memset(&it, 0, sizeof it);

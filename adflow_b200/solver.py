@@ -246,6 +246,29 @@ class ADFLOW_B200:
         """transferToFineGrid(corrections=.true.) from fine_level + 1 to fine_level"""
         check(self.L.adfb_mg_prolong(fine_level), "adfb_mg_prolong")
 
+    def setGroundLevel(self, level):
+        """iteration%groundLevel (solvers.F90:63): the finest level of the multigrid cycles that follow"""
+        check(self.L.adfb_set_ground_level(level), "adfb_set_ground_level")
+
+    def mgProlongSolution(self, fine_level=1):
+        """transferToFineGrid(corrections=.false.): the solution of ground level fine_level + 1 -> fine_level"""
+        check(self.L.adfb_mg_prolong_solution(fine_level), "adfb_mg_prolong_solution")
+
+    def fullMultigridStartUp(self, mg_start_level, n_cycles_coarse, cycle="sg", smoother="RK", n_subiterations=1):
+        """The full-multigrid start-up of `solver` (src/solver/solvers.F90:63-117): nCyclesCoarse cycles of executeMGCycle on
+        every ground level mgStartlevel, ..., 2 (the strategy of `cycle` shortened to the levels below the ground level),
+        each followed by transferToFineGrid(.false.); leaves the ground level at 1."""
+        n_lev = 1 if cycle.lower() == "sg" else int(cycle[:-1])
+        for ground in range(mg_start_level, 1, -1):
+            self.setGroundLevel(ground)
+            left = n_lev - ground + 1          # levels ground .. n_lev take part
+            spec = "sg" if left < 2 else "%d%s" % (left, cycle[-1])
+            cyc = self.cycleStrategy(spec)
+            for _ in range(n_cycles_coarse):
+                self.mgCycle(cyc, smoother, n_subiterations)
+            self.mgProlongSolution(ground - 1)
+        self.setGroundLevel(1)
+
     @staticmethod
     def cycleStrategy(spec):
         """inputIteration%cycleStrategy of the pyADflow option MGCycle ('sg', '2v', '3w', ...), extractMgInfo /

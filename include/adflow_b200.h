@@ -385,7 +385,18 @@ int adfb_mg_restrict(int fineLevel);
 /* transferToFineGrid(corrections = .true.) (multiGrid.F90:326-654) from fineLevel + 1 to fineLevel: corrections
    w - w1 / p - p1, setCorrectionsCoarseHalos (mgBoundCorr), trilinear interpolation, state update, BCs, exchange */
 int adfb_mg_prolong(int fineLevel);
-/* executeMGCycle (multiGrid.F90:825-955) on ground level 1 with the strategy of setCycleStrategy (:957-1030):
+/* Full-multigrid start-up, the solver loop `do groundLevel = mgStartlevel, 1, -1` (src/solver/solvers.F90:63-117):
+   adfb_set_ground_level = iteration%groundLevel, the finest level of the cycles that follow (levels above it take the
+   coarse-level branches; a coarse ground level runs the fine-grid routines with cflCoarse and second halos, and needs
+   spaceDiscrCoarse == spaceDiscr and second-level halo lists for that level);
+   adfb_mg_prolong_solution = transferToFineGrid(corrections = .false.) (multiGrid.F90:326-654) with extrapolateSolution
+   (:656-737) and extrapolateViscosities (:739-823): the solution of ground level fineLevel + 1 interpolated to fineLevel,
+   halos extrapolated, turbulence + flow BCs and the exchanges as the reference orders them.  Lower the ground level
+   afterwards. */
+int adfb_set_ground_level(int level);
+int adfb_get_ground_level(void);
+int adfb_mg_prolong_solution(int fineLevel);
+/* executeMGCycle (multiGrid.F90:825-955) on the ground level (adfb_set_ground_level, default 1) with the strategy of setCycleStrategy (:957-1030):
    cycling(1:nSteps) in {-1 prolongate, 0 smooth, +1 restrict}; smoother 0 = RungeKuttaSmoother, n >= 1 = DADISmoother
    with nSubiterations = n (smoothers.F90:400-420).  Ends like the reference
    with turbSolveDDADI (RANS), timeStep and the ground-level residual. */

@@ -119,6 +119,9 @@ void orc_mg_store_w1(const OrcBlock* coarse);
 void orc_mg_forcing(const OrcBlock* coarse, const AdfbParams* prm);
 void orc_mg_prolong(const OrcBlock* fine, const OrcBlock* coarse, const AdfbParams* prm, int nSubCoarse, const AdfbSubface* sfCoarse,
                     const int32_t* mgICoarse, const int32_t* mgJCoarse, const int32_t* mgKCoarse);
+/* full-multigrid start-up: transferToFineGrid(corrections = .false.) with extrapolateSolution / extrapolateViscosities */
+void orc_mg_prolong_solution(const OrcBlock* fine, const OrcBlock* coarse, const AdfbParams* prm, int nSubCoarse,
+                             const AdfbSubface* sfCoarse, const int32_t* mgICoarse, const int32_t* mgJCoarse, const int32_t* mgKCoarse);
 /* adflow_oracle_ank.c: ANK pieces (module ANKSolver of src/NKSolver/NKSolvers.F90) */
 /* turbulence KSP of the decoupled ANK: physicalityCheckANKTurb (NKSolvers.F90:3212-3335, pinned bit-exact against the translated
    routine) and the vector part of FormFunction_mf_turb (:2540-2612) */

@@ -300,3 +300,72 @@ void orc_mg_prolong(const OrcBlock* b, const OrcBlock* cb, const AdfbParams* prm
     orc_lam_viscosity(b, prm, 0);
     orc_eddy_viscosity(b, prm, 0);
 }
+
+/* extrapolateSolution / extrapolateViscosities, multiGrid.F90:656-737 / 739-823: constant extrapolation into the halos,
+   i, then j (taking the i halos along), then k */
+static void extrapolate_halos(Dims d, double* a) {
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) {
+        a[IDX(0, j, k)] = a[IDX(2, j, k)]; a[IDX(1, j, k)] = a[IDX(2, j, k)];
+        a[IDX(d.ie, j, k)] = a[IDX(d.il, j, k)]; a[IDX(d.ib, j, k)] = a[IDX(d.il, j, k)];
+    }
+    for (int k = 2; k <= d.kl; k++) for (int i = 0; i <= d.ib; i++) {
+        a[IDX(i, 0, k)] = a[IDX(i, 2, k)]; a[IDX(i, 1, k)] = a[IDX(i, 2, k)];
+        a[IDX(i, d.je, k)] = a[IDX(i, d.jl, k)]; a[IDX(i, d.jb, k)] = a[IDX(i, d.jl, k)];
+    }
+    for (int j = 0; j <= d.jb; j++) for (int i = 0; i <= d.ib; i++) {
+        a[IDX(i, j, 0)] = a[IDX(i, j, 2)]; a[IDX(i, j, 1)] = a[IDX(i, j, 2)];
+        a[IDX(i, j, d.ke)] = a[IDX(i, j, d.kl)]; a[IDX(i, j, d.kb)] = a[IDX(i, j, d.kl)];
+    }
+}
+
+/* transferToFineGrid(corrections = .false.), multiGrid.F90:326-590: the full-multigrid start-up step that interpolates
+   the SOLUTION of the coarse block `cb` to the fine block `b` (all nw variables, the pressure in the place of the total
+   energy), up to (not including) the boundary conditions and the exchanges.  Like the reference, the coarse block's
+   rho*E is overwritten by its pressure and its boundary halos by setCorrectionsCoarseHalos(fact = 1). */
+void orc_mg_prolong_solution(const OrcBlock* b, const OrcBlock* cb, const AdfbParams* prm, int nSubC, const AdfbSubface* sfs,
+                             const int32_t* mgICoarse, const int32_t* mgJCoarse, const int32_t* mgKCoarse) {
+    Dims d = dims_of(b);
+    Dims dc = dims_of(cb);
+    const int nVarInt = b->nw;
+    {
+        Dims d = dc;  /* shadow: W() on the coarse block */
+        const OrcBlock* b = cb;
+        for (int k = 1; k <= d.ke; k++) for (int j = 1; j <= d.je; j++) for (int i = 1; i <= d.ie; i++) {
+            long c = IDX(i, j, k);
+            W(c, IRHOE) = b->p[c];
+        }
+        corr_halos(b, d, nSubC, sfs, one, nVarInt);
+    }
+#define CIDX(i, j, k) ((long)(i) + dc.NI * ((long)(j) + dc.NJ * (long)(k)))
+    for (int k = 2; k <= d.kl; k++) {
+        int kk = mgKCoarse[k], kk1 = mgKCoarse[k + (d.ke + 1)];
+        for (int j = 2; j <= d.jl; j++) {
+            int jj = mgJCoarse[j], jj1 = mgJCoarse[j + (d.je + 1)];
+            for (int i = 2; i <= d.il; i++) {
+                int ii = mgICoarse[i], ii1 = mgICoarse[i + (d.ie + 1)];
+                long c = IDX(i, j, k);
+                for (int l = 0; l < nVarInt; l++) {
+                    const double* ww = cb->w + (long)l * dc.N;
+                    W(c, l) = 0.421875 * ww[CIDX(ii, jj, kk)] +
+                              0.140625 * (ww[CIDX(ii1, jj, kk)] + ww[CIDX(ii, jj1, kk)] + ww[CIDX(ii, jj, kk1)]) +
+                              0.046875 * (ww[CIDX(ii1, jj1, kk)] + ww[CIDX(ii1, jj, kk1)] + ww[CIDX(ii, jj1, kk1)]) +
+                              0.015625 * ww[CIDX(ii1, jj1, kk1)];
+                }
+            }
+        }
+    }
+#undef CIDX
+    for (int k = 2; k <= d.kl; k++) for (int j = 2; j <= d.jl; j++) for (int i = 2; i <= d.il; i++) {
+        long c = IDX(i, j, k);
+        b->p[c] = W(c, IRHOE);
+    }
+    orc_etot(b, prm, 2, d.il, 2, d.jl, 2, d.kl);
+    for (int l = 0; l < b->nw; l++) extrapolate_halos(d, b->w + (long)l * d.N);
+    extrapolate_halos(d, b->p);
+    orc_lam_viscosity(b, prm, 0);
+    orc_eddy_viscosity(b, prm, 0);
+    if (prm->equations != ADFB_EULER) {
+        extrapolate_halos(d, b->rlv);
+        if (prm->equations == ADFB_RANS) extrapolate_halos(d, b->rev);
+    }
+}

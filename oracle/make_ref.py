@@ -71,9 +71,6 @@ MG_PATCHES = [
     (r"^bcdata => cl_bcdata_unused$", "continue"),
     (r"bcdata\((\w+)\)%(\w+)\(", r"cbcd_\2(\1, "),
     (r"bcdata\((\w+)\)%(\w+)", r"cbcd_\2(\1)"),
-    # full-multigrid start-up only (corrections = .false.): outside the path
-    (r"^if \(\.not\. corrections\) call extrapolatesolution$", "continue"),
-    (r"^if \(\.not\. corrections\) call extrapolateviscosities$", "continue"),
 ]
 
 # ANK pieces of NKSolvers.F90 (module ANKSolver): PETSc vectors -> harness arrays, MPI reduction -> copy (one rank),
@@ -261,7 +258,7 @@ UNITS = [
     ("adjoint/adjointExtra.F90", "adjointextra_", ["volume_block", "metric_block"], ()),
     ("solver/surfaceIntegrations.F90", "surfaceintegrations_", ["wallintegrationface", "ksaggregationfunction"], ()),
     ("turbulence/turbBCRoutines.F90", "turbbcroutines_",
-     ["applyallturbbcthisblock", "bceddynowall", "bceddywall", "bcturbfarfield", "bcturbinflow", "bcturbinterface",
+     ["applyallturbbc", "applyallturbbcthisblock", "bceddynowall", "bceddywall", "bcturbfarfield", "bcturbinflow", "bcturbinterface",
       "bcturboutflow", "bcturbsymm", "bcturbtreatment", "bcturbwall", "turb2ndhalo"], ()),
     ("turbulence/sa.F90", "sa_", ["sa_block", "sasource", "saviscous", "saresscale", "sasolve"], ()),
     ("solver/residuals.F90", "residuals_", ["residualaveraging", "computedwdadi", "tridiagsolve", "initres", "residual"], ()),
@@ -280,7 +277,8 @@ UNITS = [
     # to the blockPointers of the current one) -> fl_x / cl_x env data bound by the harness; the coarse block's
     # BCData -> accessor functions over a second subface table (cbcd)
     ("solver/multiGrid.F90", "multigrid_", ["transfertocoarsegrid", "transfertofinegrid", "setcornerrowhalos",
-                                            "setcorrectionscoarsehalos", "executemgcycle"], (), None, MG_PATCHES),
+                                            "setcorrectionscoarsehalos", "executemgcycle", "extrapolatesolution",
+                                            "extrapolateviscosities"], (), None, MG_PATCHES),
     # ANK: time-step block of the matrix-free operator and the physicality check of the update
     ("NKSolver/NKSolvers.F90", "anksolver_", ["computetimestepblock", "physicalitycheckank", "physicalitycheckankturb"], (), "anksolver_ref.c", ANK_PATCHES,
      "anksolver"),

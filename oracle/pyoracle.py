@@ -208,6 +208,13 @@ class Oracle:
         n, arr = coarse._subfaces()
         self.L.orc_mg_prolong(_p(self.ob), _p(coarse.ob), _p(self.prm), C.c_int(n), arr, *[k[1] for k in keep])
 
+    def mg_prolong_solution(self, coarse):
+        """FINE block: transferToFineGrid(.false.) -- interpolate the SOLUTION of `coarse` (an Oracle), extrapolate into the halos"""
+        mg = self.hb.mg
+        keep = [self._tab(mg[n], np.int32) for n in ("mgICoarse", "mgJCoarse", "mgKCoarse")]
+        n, arr = coarse._subfaces()
+        self.L.orc_mg_prolong_solution(_p(self.ob), _p(coarse.ob), _p(self.prm), C.c_int(n), arr, *[k[1] for k in keep])
+
     # -- ANK pieces (adflow_oracle_ank.c) ---------------------------------------------------------------------------
     def ank_time_step_block(self, ank, i, j, k):
         n = self.hb.nw if ank.coupled else 5

@@ -89,8 +89,6 @@ UNREACHABLE(turbutils_kweddyviscosity)
 UNREACHABLE(turbutils_ssteddyviscosity)
 UNREACHABLE(turbutils_kteddyviscosity)
 UNREACHABLE(turbutils_vfeddyviscosity)
-/* full-multigrid start-up (transferToFineGrid(corrections = .false.)) is outside the path */
-void turbbcroutines_applyallturbbc(int* secondhalo) { (void)secondhalo; terminate("applyAllTurbBC", "full-multigrid start-up is outside the translated hot path"); }
 
 
 /* src/utils/utils.F90:486-500 */

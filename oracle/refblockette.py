@@ -435,13 +435,16 @@ class RefMG:
         C.c_void_p.in_dll(lib(), "setpointers_hook").value = None
         _seti("currentlevel", 1)
 
-    def call(self, level, routine, *int_args, rkstage=None):
-        """setPointers(1, level, 1), currentLevel = level, then one translated procedure"""
-        _seti("currentlevel", level); _seti("groundlevel", 1)
+    def call(self, level, routine, *int_args, rkstage=None, ground=1):
+        """setPointers(1, level, 1), currentLevel = level (ground level `ground`), then one translated procedure"""
+        _seti("currentlevel", level); _seti("groundlevel", ground)
         if rkstage is not None:
             _seti("rkstage", rkstage)
         self._hook(level)
-        getattr(lib(), routine)(*[C.byref(C.c_int(int(v))) for v in int_args])
+        try:
+            getattr(lib(), routine)(*[C.byref(C.c_int(int(v))) for v in int_args])
+        finally:
+            _seti("groundlevel", 1)
         return self.lv[level]
 
     def transfer_to_coarse(self):
@@ -450,7 +453,11 @@ class RefMG:
         lib().multigrid_transfertocoarsegrid()
         assert C.c_int.in_dll(lib(), "currentlevel").value == 2
 
-    def transfer_to_fine(self):
-        """currentLevel = 1; transferToFineGrid(.true.)"""
-        _seti("currentlevel", 1); _seti("groundlevel", 1)
-        lib().multigrid_transfertofinegrid(C.byref(C.c_int(1)))
+    def transfer_to_fine(self, corrections=True):
+        """currentLevel = 1; transferToFineGrid(.true.), or with corrections = False the full-multigrid start-up step
+        (ground level 2 -> currentLevel 1 < groundLevel: solution interpolated, halos extrapolated, BCs with second halos)"""
+        _seti("currentlevel", 1); _seti("groundlevel", 1 if corrections else 2)
+        try:
+            lib().multigrid_transfertofinegrid(C.byref(C.c_int(1 if corrections else 0)))
+        finally:
+            _seti("groundlevel", 1)

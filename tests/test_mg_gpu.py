@@ -198,6 +198,79 @@ def test_mg_cycle_with_dadi_smoother(cuda_lib):
     assert rel_max(w[..., :5], fine.w[..., :5]) < 1e-9
 
 
+@pytest.mark.parametrize("shape,options", [((16, 12, 8), None), ((12, 8, 8), {"equationType": "Euler"})])
+def test_full_multigrid_start_up(cuda_lib, shape, options):
+    """solver loop of src/solver/solvers.F90:63-117 with mgStartlevel = 2: single-grid cycles on ground level 2 (fine-grid
+    routines on the coarse block, cflCoarse, second halos, turbulence solve), then transferToFineGrid(.false.).  The oracle
+    composition is pinned bit for bit against the reference in tests/test_oracle_vs_reference_mg.py
+    (test_rk_smoother_on_a_coarse_ground_level, test_full_multigrid_start_up_transfer)."""
+    prm, levels = make_levels(shape, options, 2)
+    fine, coarse = levels
+    # a coarse start solution with halos; the fine state is whatever the start-up finds there (it is overwritten)
+    oracle_transfer_to_coarse(prm, fine, coarse)
+    dev_levels = [l.copy() for l in levels]
+    n_cycles = 2
+    cfl = prm.cfl
+    try:                                     # oracle: the coarse block as a ground level = level-1 semantics with cflCoarse
+        prm.cfl = prm.cflCoarse
+        coarse.level = 1
+        og = Oracle(coarse, prm)
+        if prm.equations == 3:
+            og.apply_turb_bc(True)
+        og.apply_flow_bc(True)
+        og.time_step(True)
+        coarse.fw[...] = 0
+        og.residual_block(prm.cdisRK[0])
+        c0 = coarse.w.copy()
+        for _ in range(n_cycles):
+            oracle_mg_cycle(prm, [coarse], [0])
+    finally:
+        prm.cfl = cfl
+        coarse.level = 2
+    cs = coarse.copy()                       # the transfer overwrites the coarse rho*E and boundary halos
+    of, oc = Oracle(fine, prm), Oracle(coarse, prm)
+    of.mg_prolong_solution(oc)
+    if prm.equations == 3:
+        of.apply_turb_bc(True)
+    of.apply_flow_bc(True); of.apply_flow_bc(True); of.apply_flow_bc(True)
+    s = device(prm, dev_levels)
+    try:
+        s.setGroundLevel(2)
+        s.applyBCs(True, True, level=2)
+        s.timeStep(False, level=2)
+        s.smootherResidual(0, level=2)
+        for _ in range(n_cycles):
+            s.mgCycle([0])
+        wc, pc, _, revc = s.downloadState(1)
+        from adflow_b200._lib import AdflowB200Error
+        with pytest.raises(AdflowB200Error):
+            s.mgProlongSolution(2)           # no level 3 / wrong ground level
+        s.mgProlongSolution(1)
+        s.setGroundLevel(1)
+        w, p, rlv, rev = s.downloadState(0)
+        # the fine level is usable right away: one residual on it
+        s.timeStep(False); s.smootherResidual(0)
+        dw = s.downloadResidual(0)
+    finally:
+        s.close()
+    ow = coarse.d.owned()
+    # coarse ground level after the cycles
+    assert rel_max(wc[..., :5], cs.w[..., :5]) < 1e-9
+    assert rel_max(pc, cs.p) < 1e-9
+    assert np.abs(cs.w[ow][..., :5] - c0[ow][..., :5]).max() > 0
+    assert rel_max(w, fine.w) < 1e-9, rel_max(w, fine.w)
+    assert rel_max(p, fine.p) < 1e-9
+    if prm.equations != 1:
+        assert rel_max(rlv, fine.rlv) < 1e-9
+    if prm.equations == 3:
+        assert rel_max(rev, fine.rev) < 1e-8
+    o = Oracle(fine, prm)
+    o.time_step(True); fine.fw[...] = 0; o.residual_block(prm.cdisRK[0])
+    owf = fine.d.owned()
+    for l in range(5):
+        assert rel_l2(dw[owf + (l,)], fine.dw[owf + (l,)]) < 1e-7, ("fine residual after the start-up", l)
+
+
 def test_cycle_strategy_and_errors(cuda_lib):
     assert ADFLOW_B200.cycleStrategy("sg") == [0]
     assert ADFLOW_B200.cycleStrategy("2v") == [0, 1, 0, -1]

@@ -133,6 +133,82 @@ def test_transfer_to_fine_grid(shape, options, neumann):
         eq(fine.rev, rf["rev"], "fine rev")
 
 
+@pytest.mark.parametrize("shape,options", CASES[:4])
+def test_full_multigrid_start_up_transfer(shape, options):
+    """transferToFineGrid(corrections = .false.), multiGrid.F90:326-654 with extrapolateSolution / extrapolateViscosities:
+    the solution of the coarse ground level interpolated to the next finer level, halos extrapolated, turbulence + flow
+    BCs (the flow BCs three times, as the reference does)"""
+    prm, fine, coarse = two_levels(shape, options)
+    oracle_transfer_to_coarse(prm, fine, coarse)
+    Oracle(coarse, prm).rk_smoother()        # a coarse solution that differs from the restricted one
+    rng = np.random.default_rng(5)
+    fine.w[...] = fine.w * (1.0 + 0.05 * rng.standard_normal(fine.w.shape))   # the fine state is overwritten entirely
+    f2, c2 = fine.copy(), coarse.copy()
+    mg = rb.RefMG(f2, c2, prm)
+    try:
+        mg.transfer_to_fine(corrections=False)
+    finally:
+        mg.close()
+    rf, rc = mg.lv[1].a, mg.lv[2].a
+    of, oc = Oracle(fine, prm), Oracle(coarse, prm)
+    of.mg_prolong_solution(oc)
+    if prm.equations == 3:
+        of.apply_turb_bc(True)
+    of.apply_flow_bc(True); of.apply_flow_bc(True); of.apply_flow_bc(True)
+    d, dc = fine.d, coarse.d
+    c1c = (slice(1, dc.ie + 1), slice(1, dc.je + 1), slice(1, dc.ke + 1))
+    eq(coarse.w[c1c], rc["w"][c1c], "coarse w with the pressure in place of rho*E (incl. boundary halos)")
+    eq(fine.w, rf["w"], "fine w (whole box)")
+    eq(fine.p, rf["p"], "fine p")
+    if prm.equations != 1:
+        eq(fine.rlv, rf["rlv"], "fine rlv")
+    if prm.equations == 3:
+        eq(fine.rev, rf["rev"], "fine rev")
+
+
+@pytest.mark.parametrize("shape,options", CASES[:4])
+def test_rk_smoother_on_a_coarse_ground_level(shape, options):
+    """Full-multigrid start-up: RungeKuttaSmoother with currentLevel = groundLevel = 2.  The reference then runs the
+    FINE-grid routines on the coarse block (second-order dissipation, dw = 0 start, second halos, eddy viscosity updated) with
+    cflCoarse; the oracle does the same when the block carries level 1 and the parameters cfl = cflCoarse."""
+    prm, fine, coarse = two_levels(shape, options)
+    oracle_transfer_to_coarse(prm, fine, coarse)
+    cfl = prm.cfl
+    try:
+        prm.cfl = prm.cflCoarse
+        coarse.level = 1
+        og = Oracle(coarse, prm)
+        if prm.equations == 3:
+            og.apply_turb_bc(True)
+        og.apply_flow_bc(True)
+        og.time_step(True)
+        coarse.fw[...] = 0
+        og.residual_block(prm.cdisRK[0])
+        f2, c2 = fine.copy(), coarse.copy()
+        c2.level = 2
+        prm.cfl = cfl
+        mg = rb.RefMG(f2, c2, prm)
+        try:
+            mg.seed_coarse_shared()
+            mg.call(2, "smoothers_rungekuttasmoother", ground=2)
+        finally:
+            mg.close()
+        rc, rf = mg.lv[2].a, mg.lv[1].a
+        prm.cfl = prm.cflCoarse
+        w0 = coarse.w.copy()
+        og.rk_smoother()
+    finally:
+        prm.cfl = cfl
+        coarse.level = 2
+    d = coarse.d
+    assert np.abs(coarse.w[d.owned()][..., :5] - w0[d.owned()][..., :5]).max() > 0
+    eq(coarse.w[..., :5], rc["w"][..., :5], "coarse-ground-level w after the RK cycle (whole box, second halos)")
+    eq(coarse.p, rc["p"], "p")
+    eq(coarse.dw[d.owned()][..., :5], rf["dw"][d.owned()][..., :5], "dw")
+    if prm.equations == 3:
+        eq(coarse.rev, rc["rev"], "rev")
+
+
 def test_coarse_dissipation_and_corner_row_halos():
     prm, fine, coarse = two_levels((10, 8, 6), None)
     oracle_transfer_to_coarse(prm, fine, coarse)
