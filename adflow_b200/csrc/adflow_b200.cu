@@ -1324,8 +1324,7 @@ static int adfb_smoother_residual_body(int level, int rkStage) {
         if (!b.alive || b.level != level) continue;
         // coarse level: initRes starts from the residual forcing term (dw = wr)
         if (launch_residual_core(b.d, b.dev, g.prm, ADFB_RES_FLOW, rFil, 1, 0, g.stream, above_ground(level) ? g.mgInitWr : 0))
-            return fail("residual launch failed%s", above_ground(level) && g.prm.spaceDiscrCoarse == ADFB_UPWIND
-                                                        ? ": upwind dissipation is not supported on coarse levels" : "");
+            return fail("residual launch failed");
         // the primitive <-> conservative round trip that inviscidDissFluxScalarCoarse leaves on w (the matrix form does not convert)
         if (above_ground(level) && fabs(rFil) >= 1.e-10 && g.prm.spaceDiscrCoarse == ADFB_DISS_SCALAR) launch_mg_cells1(b.d, b.dev, 2, g.stream);
     }

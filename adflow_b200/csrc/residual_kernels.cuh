@@ -945,8 +945,11 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         int splitDone = 0;
         const bool storeWall = (flags & ADFB_RES_STORE_WALL) && viscous && doVisc && merged && approx == 0;
         if (b.coarse) {   // coarse multigrid level: first-order scalar dissipation, block path only
-            if (merged || approx || (prm.spaceDiscrCoarse != ADFB_DISS_SCALAR && prm.spaceDiscrCoarse != ADFB_DISS_MATRIX)) return 1;
-            if (prm.spaceDiscrCoarse == ADFB_DISS_SCALAR) {
+            if (merged || approx) return 1;
+            if (prm.spaceDiscrCoarse == ADFB_UPWIND) {   // inviscidUpwindFlux(fineGrid = .false.): first-order states, fluxes.F90:1532
+                if (viscous) launch_pdl(k_faces<true, false, ADFB_UPWIND, 1>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+                else launch_pdl(k_faces<false, false, ADFB_UPWIND, 1>, g, tr, stream, d, b, rFil, doVisc, doDiss);
+            } else if (prm.spaceDiscrCoarse == ADFB_DISS_SCALAR) {
                 if (viscous) launch_pdl(k_faces<true, false, ADFB_DISS_SCALAR, 4>, g, tr, stream, d, b, rFil, doVisc, doDiss);
                 else launch_pdl(k_faces<false, false, ADFB_DISS_SCALAR, 4>, g, tr, stream, d, b, rFil, doVisc, doDiss);
             } else {

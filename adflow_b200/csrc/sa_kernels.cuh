@@ -38,6 +38,34 @@ __global__ void __launch_bounds__(128) k_sa_bmt(Dims d, BlockDev b, FaceDev f) {
     b.scratch[2 * N + c1] = bmt;
 }
 
+// the same for all subfaces of the device-resident list in one launch (blockIdx.z = subface).  The values are read at the
+// first-halo cells next to OWNED cells only (k_sa_rhs, k_sa_coef), so each subface is clipped to its owned in-plane range:
+// no cell is written by two subfaces and the launch order of the reference's loop does not matter.
+__global__ void __launch_bounds__(128) k_sa_bmt_all(Dims d, BlockDev b, const BcList* __restrict__ Lp) {
+    ADFB_PDL_SYNC();
+    const BcList& L = *Lp;
+    const int q = blockIdx.z;
+    const FaceDev& f = L.f[q];
+    const int a0 = f.icBeg > 2 ? f.icBeg : 2, a1 = f.icEnd < L.la[q] ? f.icEnd : L.la[q];
+    const int b0 = f.jcBeg > 2 ? f.jcBeg : 2, b1 = f.jcEnd < L.lb[q] ? f.jcEnd : L.lb[q];
+    const int ia = blockIdx.x * blockDim.x + threadIdx.x + a0;
+    const int jb = blockIdx.y * blockDim.y + threadIdx.y + b0;
+    if (ia > a1 || jb > b1) return;
+    const long long N = d.N;
+    const long long c1 = f.off[1] + ia * f.sa + jb * f.sb;
+    const long long na = f.icEnd - f.icBeg + 1, nb = f.jcEnd - f.jcBeg + 1;
+    const long long o = (ia - f.icBeg) + na * (jb - f.jcBeg);
+    double bmt = -1.0;
+    if (f.bcType == ADFB_BC_NSWALL_ADIABATIC || f.bcType == ADFB_BC_NSWALL_ISOTHERMAL || f.bcType == ADFB_BC_SUBSONIC_INFLOW ||
+        f.bcType == ADFB_BC_SUPERSONIC_INFLOW) bmt = 1.0;
+    else if (f.bcType == ADFB_BC_FARFIELD) {
+        const double dot = f.norm[o] * c_prm.wInf[1] + f.norm[o + na * nb] * c_prm.wInf[2] + f.norm[o + 2 * na * nb] * c_prm.wInf[3] -
+                           (f.rface ? f.rface[o] : 0.0);
+        bmt = dot > 0.0 ? -1.0 : 0.0;
+    }
+    b.scratch[2 * N + c1] = bmt;
+}
+
 // diffusion coefficients of cell c along sd (shared by the residual and the line solve)
 __device__ __forceinline__ void sa_diff_coef(const BlockDev& b, int N, int c, int sd, const double* __restrict__ s,
                                              const double* __restrict__ ssum, double nu, double& c1m, double& c1p,
@@ -346,7 +374,18 @@ __global__ void __launch_bounds__(256) k_sa_update(Dims d, BlockDev b) {
 static int launch_sa_block(const Dims& d, const BlockDev& b, const AdfbParams& prm, const std::vector<AdfbSubface>& subs, cudaStream_t s) {
     const int sJ = (int)d.sJ, sK = (int)d.sK;
     cudaMemsetAsync(b.scratch + 2 * d.N, 0, sizeof(double) * d.N, s);
+    static int bmtOne = -1;
+    if (bmtOne < 0) { const char* e = getenv("ADFB_SA_BMT_ONE"); bmtOne = e ? atoi(e) : 1; }
+    const bool oneLaunch = bmtOne && b.bcList && !subs.empty() && (int)subs.size() <= ADFB_BC_MAXSUB;
+    if (oneLaunch) {
+        int ma = 1, mb = 1;
+        for (const AdfbSubface& sf : subs) { ma = std::max(ma, sf.icEnd - sf.icBeg + 1); mb = std::max(mb, sf.jcEnd - sf.jcBeg + 1); }
+        KT_BEGIN(K_SASOLVE, s);
+        launch_pdl(k_sa_bmt_all, dim3((ma + 31) / 32, (mb + 3) / 4, (unsigned)subs.size()), dim3(32, 4), s, d, b, (const BcList*)b.bcList);
+        KT_END(K_SASOLVE, s);
+    }
     for (const AdfbSubface& sf : subs) {
+        if (oneLaunch) break;
         FaceDev f = make_face(d, sf);
         dim3 tb(32, 4);
         dim3 g((f.icEnd - f.icBeg + 1 + 31) / 32, (f.jcEnd - f.jcBeg + 1 + 3) / 4);

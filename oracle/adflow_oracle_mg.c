@@ -76,7 +76,11 @@ void orc_residual_block_coarse(const OrcBlock* b, const AdfbParams* prm, double 
     }
     orc_central_flux(b, prm);
     if (prm->spaceDiscrCoarse == ADFB_DISS_MATRIX) orc_diss_matrix_coarse(b, prm, rFil);
-    else orc_diss_scalar_coarse(b, prm, rFil);
+    else if (prm->spaceDiscrCoarse == ADFB_UPWIND) {   /* inviscidUpwindFlux(fineGrid = .false.): first order, fluxes.F90:1532 */
+        AdfbParams p1 = *prm;
+        p1.limiter = ADFB_LIM_FIRSTORDER;
+        orc_upwind_flux(b, &p1, rFil);
+    } else orc_diss_scalar_coarse(b, prm, rFil);
     if (viscous && fabs(rFil) > thresholdReal) {
         orc_speed_of_sound(b, prm);
         orc_nodal_gradients(b);

@@ -16,7 +16,9 @@ pytestmark = pytest.mark.skipif(not rb.available(), reason="oracle/_ref not buil
 
 CASES = [((12, 8, 10), None), ((9, 7, 6), None), ((8, 6, 6), {"equationType": "Euler"}),
          ((6, 9, 5), {"equationType": "laminar NS"}),
-         ((10, 8, 6), {"coarseDiscretization": "central plus matrix dissipation"})]
+         ((10, 8, 6), {"coarseDiscretization": "central plus matrix dissipation"}),
+         ((10, 8, 6), {"coarseDiscretization": "upwind"}),
+         ((8, 6, 6), {"equationType": "Euler", "discretization": "upwind", "coarseDiscretization": "upwind"})]
 
 
 def two_levels(shape, options, seed=314):
@@ -81,7 +83,7 @@ def test_transfer_to_coarse_grid(shape, options):
         eq(coarse.rev[c1], rc["rev"][c1], "coarse rev")
 
 
-@pytest.mark.parametrize("shape,options", CASES[:3])
+@pytest.mark.parametrize("shape,options", CASES[:3] + CASES[5:])
 def test_coarse_level_rk_smoother(shape, options):
     """RungeKuttaSmoother on level 2: dw = wr start, cflCoarse, first-order dissipation, no second halos"""
     prm, fine, coarse = two_levels(shape, options)
