@@ -299,6 +299,147 @@ __global__ void __launch_bounds__(64) k_dadi_thomas(Dims d, BlockDev b, int sd, 
     }
 }
 
+// Tiled variant of k_dadi_thomas: one WARP = 32 neighbouring lines of one variable.  The recurrence is walked in chunks of
+// ADFB_DT_CH cells; the operands of a chunk (tridiagonal rows, right-hand side) are staged as a [line][cell] tile in shared
+// memory with cp.async, the next chunk's tile in flight while the current one is eliminated, and the results leave through a
+// tile as well.  Two things are gained over the per-thread walk: (1) the load latency of a chunk is no longer serialised
+// with the arithmetic of the previous one (12 dependent round trips per sweep on a 96-cell line), (2) for lines along i
+// (sd == 1), where neighbouring THREADS own lines a whole row apart, the lanes copy along the line (8 consecutive cells =
+// one 64-byte segment per 8 lanes) instead of touching 32 cache lines per load instruction -- that sweep was bound by L1
+// wavefronts (79 us against 28 us for the other two directions on C2).  Same operations on the same operands.
+#define ADFB_DT_CH 8
+#define ADFB_DT_WARPS 4
+struct DtSmem {
+    double in[2][4][32][ADFB_DT_CH + 1];   // [stage][array][line][cell]; odd pitch: conflict-free 64-bit accesses down a column
+    double out[2][32][ADFB_DT_CH + 1];
+};
+__device__ __forceinline__ void dt_cp8(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void dt_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NPEND>
+__device__ __forceinline__ void dt_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND) : "memory"); }
+
+__global__ void __launch_bounds__(32 * ADFB_DT_WARPS) k_dadi_thomas_tile(Dims d, BlockDev b, int sd, int nl, int s1, int n1, int s2, int n2) {
+    ADFB_PDL_SYNC();
+    constexpr int CH = ADFB_DT_CH;
+    extern __shared__ __align__(16) unsigned char dt_raw[];
+    DtSmem& S = reinterpret_cast<DtSmem*>(dt_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int groups = (n1 + 31) / 32;
+    long long item = (long long)blockIdx.x * ADFB_DT_WARPS + (threadIdx.x >> 5);
+    if (item >= (long long)groups * n2 * 5 || nl <= 1) return;   // whole warps leave; only __syncwarp below
+    const int n = (int)(item % 5);
+    item /= 5;
+    const int grp = (int)(item % groups), q2 = (int)(item / groups) + 2;
+    const int t = n < 3 ? 0 : n - 2;   // coefficient set: (u), (u+c), (u-c)
+    const int N = (int)d.N;
+    const int q10 = grp * 32 + 2;
+    const int nLines = (n1 + 2 - q10) < 32 ? (n1 + 2 - q10) : 32;
+    const int base0 = q10 * s1 + q2 * s2;
+    const int l = nl + 1;
+    const double* __restrict__ ccA = b.flux + (19 + t) * N;
+    const double* __restrict__ bbA = b.flux + (22 + t) * N;
+    const double* __restrict__ dsA = b.flux + (25 + t) * N;
+    double* dd = b.flux + (9 + n) * N;
+    double* fo = b.flux + (14 + n) * N;
+    double* f = b.dw + n * N;
+    const bool alongLine = sd == 1;
+    const int nChunks = (nl + CH - 1) / CH;
+    // tile element e -> (line, cell of the chunk)
+#define DT_ELEM(e, ln, u) const int ln = alongLine ? (e) / CH : (e) % 32, u = alongLine ? (e) % CH : (e) / 32
+    auto issueF = [&](int chunk, int stage) {
+        const int m0 = 2 + chunk * CH;
+        for (int e = lane; e < 32 * CH; e += 32) {
+            DT_ELEM(e, ln, u);
+            const int m = m0 + u;
+            if (ln < nLines && m <= l) {
+                const int c = base0 + ln * s1 + m * sd;
+                dt_cp8(&S.in[stage][0][ln][u], ccA + c);
+                dt_cp8(&S.in[stage][1][ln][u], bbA + c);
+                dt_cp8(&S.in[stage][2][ln][u], dsA + c);
+                dt_cp8(&S.in[stage][3][ln][u], f + c);
+            }
+        }
+        dt_commit();
+    };
+    double ddp = 0.0, ffp = 0.0;
+    issueF(0, 0);
+    for (int ch = 0; ch < nChunks; ch++) {
+        const int st = ch & 1;
+        if (ch + 1 < nChunks) { issueF(ch + 1, st ^ 1); dt_wait<1>(); } else dt_wait<0>();
+        __syncwarp();
+        const int m0 = 2 + ch * CH;
+        if (lane < nLines) {
+#pragma unroll
+            for (int u = 0; u < CH; u++) {
+                const int m = m0 + u;
+                if (m <= l) {
+                    const double cc = S.in[st][0][lane][u], bb = S.in[st][1][lane][u], ds = S.in[st][2][lane][u], fv = S.in[st][3][lane][u];
+                    const double d0 = (m == 2) ? 1.0 / cc : 1.0 / (cc - bb * ddp);
+                    const double ddm = ds * d0;
+                    S.out[0][lane][u] = ddm;
+                    const double v = (m == 2) ? fv * d0 : (fv - bb * ffp) * d0;
+                    S.out[1][lane][u] = v;
+                    ffp = v; ddp = ddm;
+                }
+            }
+        }
+        __syncwarp();
+        for (int e = lane; e < 32 * CH; e += 32) {
+            DT_ELEM(e, ln, u);
+            const int m = m0 + u;
+            if (ln < nLines && m <= l) {
+                const int c = base0 + ln * s1 + m * sd;
+                dd[c] = S.out[0][ln][u];
+                fo[c] = S.out[1][ln][u];
+            }
+        }
+        __syncwarp();
+    }
+    // back substitution, chunks in reverse; ffp holds ff(l) = the value stored at m = l
+    auto issueB = [&](int chunk, int stage) {
+        const int m0 = 2 + chunk * CH;
+        for (int e = lane; e < 32 * CH; e += 32) {
+            DT_ELEM(e, ln, u);
+            const int m = m0 + u;
+            if (ln < nLines && m <= l) {
+                const int c = base0 + ln * s1 + m * sd;
+                dt_cp8(&S.in[stage][0][ln][u], fo + c);
+                dt_cp8(&S.in[stage][1][ln][u], dd + c);
+            }
+        }
+        dt_commit();
+    };
+    issueB(nChunks - 1, 0);
+    for (int ch = nChunks - 1, it = 0; ch >= 0; ch--, it++) {
+        const int st = it & 1;
+        if (ch > 0) { issueB(ch - 1, st ^ 1); dt_wait<1>(); } else dt_wait<0>();
+        __syncwarp();
+        const int m0 = 2 + ch * CH;
+        if (lane < nLines) {
+#pragma unroll
+            for (int u = CH - 1; u >= 0; u--) {
+                const int m = m0 + u;
+                if (m <= l) {
+                    const double fr = S.in[st][0][lane][u], dr = S.in[st][1][lane][u];
+                    const double v = (m == l) ? fr : fr - dr * ffp;
+                    S.out[0][lane][u] = v;
+                    ffp = v;
+                }
+            }
+        }
+        __syncwarp();
+        for (int e = lane; e < 32 * CH; e += 32) {
+            DT_ELEM(e, ln, u);
+            const int m = m0 + u;
+            if (ln < nLines && m <= l) f[base0 + ln * s1 + m * sd] = S.out[0][ln][u];
+        }
+        __syncwarp();
+    }
+#undef DT_ELEM
+}
+
 // The three coefficient sets and the five right-hand sides of LPC grid lines solved in shared memory: replaces
 // k_dadi_tri + k_dadi_thomas (tridiagonal rows residuals.F90:1374-1391, tridiagsolve :1750-1783).
 //   A  all threads copy the cell coefficients of k_dadi_coef (dP, dM of the three sets, viscTerm1/3, dual_dt) and
@@ -434,7 +575,26 @@ static int launch_dadi(const Dims& d, const BlockDev& b, const AdfbParams& prm, 
 #undef ADFB_DL_LAUNCH
         return true;
     };
+    // ADFB_DADI_TILE: 1 (default) = the tiled walk for the i sweep (lines along the contiguous index), 2 = for all three
+    // sweeps, 0 = per-thread walks everywhere
+    static int tileMode = -1;
+    if (tileMode < 0) { const char* e = getenv("ADFB_DADI_TILE"); tileMode = e ? atoi(e) : 1; }
     auto thomas = [&](int sd, int nl, int s1, int n1, int s2, int n2) {
+        if (tileMode == 2 || (tileMode == 1 && sd == 1)) {
+            static bool once = false;
+            const size_t smem = sizeof(DtSmem) * ADFB_DT_WARPS;
+            if (!once) { cudaFuncSetAttribute(k_dadi_thomas_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }
+            const long long items = (long long)((n1 + 31) / 32) * n2 * 5;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)((items + ADFB_DT_WARPS - 1) / ADFB_DT_WARPS)); cfg.blockDim = dim3(32 * ADFB_DT_WARPS);
+            cfg.dynamicSmemBytes = smem; cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, k_dadi_thomas_tile, d, b, sd, nl, s1, n1, s2, n2);
+            return;
+        }
         launch_pdl(k_dadi_thomas, dim3((n1 + 31) / 32, n2, 5), tb, s, d, b, sd, nl, s1, n1, s2, n2);
     };
     // rows + solve of one direction: shared-memory kernel, else k_dadi_tri + k_dadi_thomas

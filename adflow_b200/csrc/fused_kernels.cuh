@@ -59,7 +59,8 @@ enum { FV_R = 0, FV_U, FV_V, FV_W, FV_E, FV_P, FV_RLV, FV_REV, FV_AA, FV_SS, FV_
 #ifndef FT_NSLOT
 #define FT_NSLOT 3        // ring slots of the state tiles: planes k, k+1 and (3 slots) the plane k+2 in flight during step k
 #endif
-#define FT_NFLUX 10     // flux exchange arrays: i faces 0..4, j faces 5..9 (smoother path: central 0..4 + dissipative 5..9, i then j)
+#define FT_NFLUX 10     // flux exchange arrays: i faces 0..4, j faces 5..9
+#define FT_NFLUX_SPLIT 20   // smoother path (central and dissipative parts apart): i central 0..4, i diss 5..9, j central 10..14, j diss 15..19
 
 struct FTile {
     int TX, TY;        // thread tile
@@ -567,7 +568,6 @@ struct FStep {
     FGeoF gi, gj;
     FGeoK gk;
     double kp[10];
-    double acc[10];   // smoother path: partial sums between the two exchanges
 };
 
 template <bool MERGED>
@@ -575,7 +575,7 @@ FHD void ft_store_flux(const FCtx& x, FSmem& sm, int slot, const double fc[5], c
 #pragma unroll
     for (int l = 0; l < 5; l++) {
         if (MERGED) sm.FX[(slot + l) * FT_S0 + x.o0] = fc[l] - fd[l];
-        else { sm.FX[l * FT_S0 + x.o0] = fc[l]; sm.FX[(5 + l) * FT_S0 + x.o0] = fd[l]; }
+        else { sm.FX[(2 * slot + l) * FT_S0 + x.o0] = fc[l]; sm.FX[(2 * slot + 5 + l) * FT_S0 + x.o0] = fd[l]; }
     }
 }
 
@@ -603,17 +603,22 @@ FHD void ft_div(const Dims& d, const BlockDev& b, const FTile& t, const FCtx& x,
             b.dw[l * N + c] = dwv;
             if (mf.rec) mffd_epilogue(mf, d, x.i, x.j, k, l, dwv, b.volRef[c], turbScale);
         }
-    } else {   // second half: the j exchange is in FX, the i part is in st.acc
+    } else {   // smoother path: central part -> dw, dissipative + viscous part blended into the persistent fw
+        const double sfil = 1.0 - rFil;
 #pragma unroll
         for (int l = 0; l < 5; l++) {
-            double a = st.acc[l];
-            a -= F[l * FT_S0 + q0 - TX];
+            double a = 0.0;
+            a -= F[l * FT_S0 + q0 - 1];
             a += F[l * FT_S0 + q0];
+            a -= F[(10 + l) * FT_S0 + q0 - TX];
+            a += F[(10 + l) * FT_S0 + q0];
             a -= r.kprev[l];
             a += st.kp[l];
-            double fw = st.acc[5 + l];
-            fw += F[(5 + l) * FT_S0 + q0 - TX];
+            double fw = persistFw ? sfil * b.fw[l * N + c] : 0.0;
+            fw += F[(5 + l) * FT_S0 + q0 - 1];
             fw -= F[(5 + l) * FT_S0 + q0];
+            fw += F[(15 + l) * FT_S0 + q0 - TX];
+            fw -= F[(15 + l) * FT_S0 + q0];
             fw += r.kprev[5 + l];
             fw -= st.kp[5 + l];
             if (persistFw) b.fw[l * N + c] = fw;
@@ -621,27 +626,6 @@ FHD void ft_div(const Dims& d, const BlockDev& b, const FTile& t, const FCtx& x,
         }
     }
 }
-// smoother path, first half: i part of the divergence from the i exchange
-FHD void ft_div_i(const Dims& d, const BlockDev& b, const FCtx& x, int k, const FSmem& sm, FStep& st, double rFil, int persistFw) {
-    if (!x.own) return;
-    const int N = (int)d.N, sK = (int)d.sK;
-    const int c = x.c0 + sK * k;
-    const double* F = sm.FX;
-    const int q0 = x.o0;
-    const double sfil = 1.0 - rFil;
-#pragma unroll
-    for (int l = 0; l < 5; l++) {
-        double a = 0.0;
-        a -= F[l * FT_S0 + q0 - 1];
-        a += F[l * FT_S0 + q0];
-        st.acc[l] = a;
-        double fw = persistFw ? sfil * b.fw[l * N + c] : 0.0;
-        fw += F[(5 + l) * FT_S0 + q0 - 1];
-        fw -= F[(5 + l) * FT_S0 + q0];
-        st.acc[5 + l] = fw;
-    }
-}
-
 // global source of ring variable v
 FHD const double* ft_var_ptr(const Dims& d, const BlockDev& b, int v) {
     switch (v) {
@@ -684,7 +668,7 @@ FHD void ft_step_a(const Dims& d, const BlockDev& b, const FTile& t, const FCtx&
         ft_nodal(t, x, A, B, st.gn, sm, r, doIJ);
     }
 }
-// merged path: i, j and k faces between the two barriers.  smoother path: call with part = 0 (i face), 1 (j face + k face)
+// i, j and k faces between the two barriers (`part` is kept for experiments: 0 = i face only, 1 = j + k faces only, 2 = all)
 template <bool VISCOUS, bool MERGED>
 FHD void ft_step_b(const AdfbParams& P, const Dims& d, const BlockDev& b, const FTile& t, const FCtx& x, int k, int kb, const double* A,
                    const double* B, FSmem& sm, FRegs& r, FStep& st, double rFil, int doDiss, bool doIJ, int part) {
@@ -699,7 +683,7 @@ FHD void ft_step_b(const AdfbParams& P, const Dims& d, const BlockDev& b, const 
         ow.rev = visc ? A[FV_REV * FT_S2 + x.o2] : 0.0;
         ow.aa = visc ? A[FV_AA * FT_S2 + x.o2] : 0.0;
     }
-    if (MERGED || part == 0) {
+    if (part != 1) {
         if (FT_EARLY && visc && k < kb) ft_load_nodal(d, b, x, k + 1, k + 1 < kb, st.gn);   // for the next step's nodal phase
         if (doIJ && x.fi) {
             if (!FT_EARLY) ft_load_face(d, b, x, k, 0, visc, pf, st.gi);
@@ -707,7 +691,7 @@ FHD void ft_step_b(const AdfbParams& P, const Dims& d, const BlockDev& b, const 
             ft_store_flux<MERGED>(x, sm, 0, fc, fd);
         }
     }
-    if (MERGED || part == 1) {
+    if (part != 0) {
         if (doIJ && x.fj) {
             if (!FT_EARLY) ft_load_face(d, b, x, k, 1, visc, pf, st.gj);
             ft_face_ij<VISCOUS>(P, t, x, 1, A, sm, st.gj, ow, rFil, doDiss, fc, fd);
@@ -838,7 +822,7 @@ __global__ void __launch_bounds__(FT_LB, FT_MINB) k_flowres
     sm.G = ft_smem + FT_NSLOT * FV_NUM * FT_S2;
     sm.EE = sm.G + FT_GP * FT_S0;
     sm.FX = sm.EE + FT_GP * FT_S0;
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm.FX + FT_NFLUX * FT_S0);   // 3 mbarriers
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm.FX + (MERGED ? FT_NFLUX : FT_NFLUX_SPLIT) * FT_S0);   // 3 mbarriers
     const int tid = threadIdx.x;
     const FCtx x = ft_ctx(d, t, tid, blockIdx.x, blockIdx.y);
     const int ka = 2 + blockIdx.z * t.kChunk;
@@ -918,15 +902,7 @@ __global__ void __launch_bounds__(FT_LB, FT_MINB) k_flowres
         }
         ft_step_a<VISCOUS, MERGED>(d, b, t, x, k, kb, A, B, sm, r, st, doDiss, doIJ);
         __syncthreads();   // G / EE of this plane visible; the previous plane's flux exchange is over
-        if (MERGED) {
-            ft_step_b<VISCOUS, MERGED>(c_prm, d, b, t, x, k, kb, A, B, sm, r, st, rFil, doDiss, doIJ, 0);
-        } else {
-            ft_step_b<VISCOUS, MERGED>(c_prm, d, b, t, x, k, kb, A, B, sm, r, st, rFil, doDiss, doIJ, 0);
-            __syncthreads();   // i exchange visible
-            if (doIJ) ft_div_i(d, b, x, k, sm, st, rFil, persistFw);
-            __syncthreads();   // i exchange consumed: the flux arrays are free for the j exchange
-            ft_step_b<VISCOUS, MERGED>(c_prm, d, b, t, x, k, kb, A, B, sm, r, st, rFil, doDiss, doIJ, 1);
-        }
+        ft_step_b<VISCOUS, MERGED>(c_prm, d, b, t, x, k, kb, A, B, sm, r, st, rFil, doDiss, doIJ, 2);
         if (FT_NSLOT >= 3 && k + 2 <= kb + 1) wait_plane(k + 2);
         __syncthreads();   // fluxes visible; G / EE and the slot of plane k are free; (3 slots) plane k+2 has landed
         if (FT_NSLOT >= 3) { if (k + 3 <= kb + 1) load_plane(k + 3); }
@@ -989,6 +965,7 @@ static int launch_flowres_tile(const Dims& d, const BlockDev& b, const AdfbParam
     const bool viscous = prm.equations != ADFB_EULER;
     bool tma = fused_mode() >= 2 && !(d.NI & 1);
     FTile t = ftile_choose(d, tma, nSM);
+    if (!merged) t.smemBytes += (size_t)(FT_NFLUX_SPLIT - FT_NFLUX) * FT_S0 * sizeof(double);   // central and dissipative fluxes exchanged apart
     if (!ftile_fits(t) || t.smemBytes > smemMax) return -1;
     FTmaMaps maps;
     memset(&maps, 0, sizeof maps);

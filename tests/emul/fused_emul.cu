@@ -37,7 +37,7 @@ int emul_flowres(int nx, int ny, int nz, const AdfbParams* prm, const EmulArrays
     FTile t = ftile_make(TX, TY, kChunk, false);
     if (!ftile_fits(t)) return 2;
     const int nti = (d.nx + t.TX - 2) / (t.TX - 1), ntj = (d.ny + t.TY - 2) / (t.TY - 1), nkc = (d.nz + t.kChunk - 1) / t.kChunk;
-    std::vector<double> smem(FT_SMEM_DOUBLES);
+    std::vector<double> smem(FT_SMEM_DOUBLES + (size_t)(FT_NFLUX_SPLIT - FT_NFLUX) * FT_S0);
     FSmem sm;
     sm.ring = smem.data();
     sm.G = sm.ring + (size_t)FT_NSLOT * FV_NUM * FT_S2;
@@ -88,13 +88,7 @@ int emul_flowres(int nx, int ny, int nz, const AdfbParams* prm, const EmulArrays
                     const double* B = sm.ring + (size_t)((k + 1) % FT_NSLOT) * FV_NUM * FT_S2;
                     const bool doIJ = k >= ka;
                     ALL_THREADS(DISPATCH(ft_step_a, d, b, t, x, k, kb, A, B, sm, r, st, doDiss, doIJ));
-                    if (merged) {
-                        ALL_THREADS(DISPATCH(ft_step_b, P, d, b, t, x, k, kb, A, B, sm, r, st, rFil, doDiss, doIJ, 0));
-                    } else {
-                        ALL_THREADS(DISPATCH(ft_step_b, P, d, b, t, x, k, kb, A, B, sm, r, st, rFil, doDiss, doIJ, 0));
-                        ALL_THREADS(if (doIJ) ft_div_i(d, b, x, k, sm, st, rFil, persistFw));
-                        ALL_THREADS(DISPATCH(ft_step_b, P, d, b, t, x, k, kb, A, B, sm, r, st, rFil, doDiss, doIJ, 1));
-                    }
+                    ALL_THREADS(DISPATCH(ft_step_b, P, d, b, t, x, k, kb, A, B, sm, r, st, rFil, doDiss, doIJ, 2));
                     // (barrier) the slot of plane k is free now
                     if (k + FT_NSLOT <= kb + 1) {
                         double* slot = sm.ring + (size_t)(k % FT_NSLOT) * FV_NUM * FT_S2;
