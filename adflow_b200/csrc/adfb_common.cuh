@@ -96,6 +96,8 @@ __host__ __device__ inline void mffd_epilogue(const MffdEpi& m, const Dims& d, i
 
 // single translation unit (adflow_b200.cu includes every *_kernels.cuh)
 __constant__ AdfbParams c_prm;
+// heat-flux coefficients 1/(Pr (gamma-1)), 1/(Pr_t (gamma-1)) of viscousFlux: two divisions per face and thread otherwise
+__constant__ double c_fheat[2];
 // Programmatic dependent launch: every PDL-launched kernel first waits for its predecessor (grid dependency sync: the
 // predecessor has completed and its writes are visible), then -- with ADFB_PDL_TRIGGER=1 -- signals at once that ITS
 // dependent may be launched, so that the dependent's blocks are scheduled while this kernel's last wave drains; the

@@ -406,6 +406,13 @@ int adfb_set_params(const AdfbParams* prm) {
     g.havePrm = true;
     CK(cudaMemcpyToSymbolAsync(c_prm, &g.prm, sizeof(AdfbParams), 0, cudaMemcpyHostToDevice, g.stream));
     {
+        static double fheat[2];
+        const double gm1 = g.prm.gammaInf - 1.0;
+        fheat[0] = 1.0 / (g.prm.prandtl * gm1); fheat[1] = 1.0 / (g.prm.prandtlTurb * gm1);
+        CK(cudaMemcpyToSymbolAsync(c_fheat, fheat, sizeof fheat, 0, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+    }
+    {
         static int trig = -1;
         if (trig < 0) { const char* e = getenv("ADFB_PDL_TRIGGER"); trig = e ? atoi(e) : 0; }
         CK(cudaMemcpyToSymbolAsync(c_pdlTrigger, &trig, sizeof(int), 0, cudaMemcpyHostToDevice, g.stream));
@@ -1107,7 +1114,7 @@ static int nk_vec_kernel(const double* vec, const double* base, double* out, dou
         const long long n = (long long)b.d.nx * b.d.ny * b.d.nz * b.nw;
         KT_BEGIN(K_MFFD, g.stream);
         k_nkvec<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(b.d, b.dev, b.nw, vec ? vec + off : nullptr, base ? base + off : nullptr,
-                                                                   out ? out + off : nullptr, h, mode);
+                                                                   out ? out + off : nullptr, h, mode, 0LL, LLONG_MAX);
         KT_END(K_MFFD, g.stream);
         off += n;
     }
@@ -1134,6 +1141,148 @@ static int nk_sumsq(const double* v, long long n, double* out) {
 }
 static const unsigned kNkFlags = ADFB_RES_FLOW | ADFB_RES_TURB;
 
+// FormFunction_mf as a slab pipeline.  The state vector is ordered with k slowest, so a range of k planes is a contiguous piece of
+// wVec / rVec.  Every stage of blocketteRes is local in k up to +-2 planes -- setW and the p / rlv / rev preamble are cell local,
+// an i- or j-face boundary cell touches its own plane only (launch_bc_levels), the time-step / sensor preparation is cell
+// local, the SA row and the tile kernel read two planes either side -- so the residual of the planes of slab s can be formed
+// as soon as slab s+1 has arrived, while later slabs are still on the bus, and its rows leave while the next ones are computed:
+// the host-to-device copy, the kernels and the device-to-host copy of one call overlap (three streams, full-duplex PCIe).
+// Same kernels, same operands as the one-shot path: the result is identical.  Used when both vectors are page-locked, the
+// blocks have no exchange partners (no 1-to-1 / overset pattern on level 1) and the tile kernel applies; ADFB_FF_PIPE=0 disables it.
+static cudaStream_t g_ffIn = nullptr, g_ffOut = nullptr;
+static cudaEvent_t g_ffEv[3][32];
+static bool ff_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+static int form_function_pipe_slabs() {   // read at every call: tests switch it
+    const char* e = getenv("ADFB_FF_PIPE");
+    return e ? atoi(e) : 6;
+}
+// returns -1 when the pipeline does not apply (caller takes the one-shot path)
+static int form_function_pipelined(const double* wVec, double* rVec, long long need) {
+    const int wantSlabs = form_function_pipe_slabs();
+    if (wantSlabs < 2 || g.nranks > 1 || g_kt.on || g.mffdFuse) return -1;
+    {   // exchange partners (entries in a 1-to-1 or overset pattern of level 1) tie planes of different slabs together
+        auto busy = [](const std::map<int, Context::Pattern>& m) {
+            auto it = m.find(1);
+            return it != m.end() && it->second.set && (it->second.nSend || it->second.nRecv || it->second.nInt);
+        };
+        if (busy(g.pats) || busy(g.ovPats)) return -1;
+    }
+    if (!ff_pinned(wVec) || !ff_pinned(rVec)) return -1;
+    const int kc = 4;   // planes per CTA of the tile kernel inside the pipeline
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != 1) continue;
+        if (!b.haveMetrics || b.nOrphans || !tile_kernel_applies(b.d, b.dev, g.prm) || b.d.nz < 4 * kc) return -1;
+    }
+    if (!g_ffIn) {
+        CK(cudaStreamCreateWithFlags(&g_ffIn, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&g_ffOut, cudaStreamNonBlocking));
+        for (int a = 0; a < 3; a++) for (int q = 0; q < 32; q++) CK(cudaEventCreateWithFlags(&g_ffEv[a][q], cudaEventDisableTiming));
+    }
+    set_l2_window();
+    const bool rans = g.prm.equations == ADFB_RANS;
+    // the copy streams start after whatever the library stream still has in flight, and the first kernels after them
+    CK(cudaEventRecord(g_ffEv[2][0], g.stream));
+    CK(cudaStreamWaitEvent(g_ffIn, g_ffEv[2][0], 0));
+    CK(cudaStreamWaitEvent(g_ffOut, g_ffEv[2][0], 0));
+    long long off = 0;
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != 1) continue;
+        const Dims& d = b.d;
+        const long long plane = (long long)d.nx * d.ny * b.nw;   // vector entries per k plane
+        const int nChunks = (d.nz + kc - 1) / kc;
+        const int S = std::min(std::min(wantSlabs, 32), nChunks / 2);
+        // slab boundaries in chunks: small slabs at both ends (the pipeline fills and drains faster), larger ones in the middle
+        std::vector<int> cb(S + 1, 0);
+        {
+            std::vector<double> wgt(S);
+            double tot = 0.0;
+            for (int q = 0; q < S; q++) { const double x = (q + 0.5) / S; wgt[q] = 0.6 + 1.6 * x * (1.0 - x) * 2.0; tot += wgt[q]; }
+            double acc = 0.0;
+            for (int q = 0; q < S; q++) {
+                acc += wgt[q];
+                int e = (int)(acc / tot * nChunks + 0.5);
+                if (e <= cb[q]) e = cb[q] + 1;
+                if (e > nChunks - (S - 1 - q)) e = nChunks - (S - 1 - q);
+                cb[q + 1] = e;
+            }
+            cb[S] = nChunks;
+        }
+        auto ownedEnd = [&](int chunkEnd) { return std::min(chunkEnd * kc, d.nz); };   // owned plane index (0-based), exclusive
+        for (int q = 0; q < S; q++) {   // all host-to-device copies are queued at once; they run back to back on their stream
+            const long long q0 = (long long)ownedEnd(cb[q]) * plane, q1 = (long long)ownedEnd(cb[q + 1]) * plane;
+            CK(cudaMemcpyAsync(g.nkA + off + q0, wVec + off + q0, (size_t)(q1 - q0) * sizeof(double), cudaMemcpyHostToDevice, g_ffIn));
+            CK(cudaEventRecord(g_ffEv[0][q], g_ffIn));
+        }
+        int cNext = 0;   // first k chunk whose residual has not been formed
+        for (int q = 0; q < S; q++) {
+            const bool first = q == 0, last = q == S - 1;
+            const int o0 = ownedEnd(cb[q]), o1 = ownedEnd(cb[q + 1]);   // owned planes o0 .. o1-1 (0-based) = absolute 2+o0 .. 1+o1
+            CK(cudaStreamWaitEvent(g.stream, g_ffEv[0][q], 0));
+            // setW + p / rlv / rev of the slab's owned cells
+            {
+                const long long q0 = (long long)o0 * plane, q1 = (long long)o1 * plane;
+                KT_BEGIN(K_MFFD, g.stream);
+                k_nkvec<<<(unsigned)((q1 - q0 + 255) / 256), 256, 0, g.stream>>>(d, b.dev, b.nw, g.nkA + off, nullptr, nullptr, 0.0, 0, q0, q1);
+                KT_END(K_MFFD, g.stream);
+                dim3 tb(32, 4, 2);
+                dim3 gr((d.nx + 31) / 32, (d.ny + 3) / 4, (o1 - o0 + 1) / 2);
+                KT_BEGIN(K_STATE, g.stream);
+                launch_pdl(k_state_prep, gr, tb, g.stream, d, b.dev, 0, rans ? 6 : 5, 1, o0, 1 + o1);
+                KT_END(K_STATE, g.stream);
+            }
+            // boundary conditions of the slab's planes (+ the k-face subfaces with the first / last slab)
+            const int pLo = first ? 0 : 2 + o0, pHi = last ? d.kb : 1 + o1;
+            if (launch_bc_levels(d, b.dev, b.subfaces, 1, rans ? 1 : 0, 1, g.stream, first ? -(1 << 30) : pLo, last ? (1 << 30) : pHi,
+                                 (first ? 1 : 0) | (last ? 2 : 0)))
+                return fail("BC launch failed");
+            // time step / radii / sensor of the slab's planes (halo planes with the first and the last slab)
+            {
+                dim3 tb(32, 4, 2);
+                dim3 gr((d.NI + 31) / 32, (d.NJ + 3) / 4, (pHi - pLo + 2) / 2);
+                KT_BEGIN(K_PREP, g.stream);
+                launch_pdl(k_prep, gr, tb, g.stream, d, b.dev, 1, 1, 0, pLo, pHi);
+                KT_END(K_PREP, g.stream);
+            }
+            // residual rows of the k chunks whose +-2 plane stencil is complete
+            int cEnd = cNext;
+            while (cEnd < nChunks && (last || 2 + ownedEnd(cEnd + 1) - 1 + 2 <= pHi)) cEnd++;
+            if (cEnd > cNext) {
+                const int r0 = ownedEnd(cNext), r1 = ownedEnd(cEnd);
+                if (rans) {
+                    dim3 tr(32, 4, 1);
+                    dim3 gr((d.nx + 31) / 32, (d.ny + 3) / 4, r1 - r0);
+                    KT_BEGIN(K_SA, g.stream);
+                    k_sa<<<gr, tr, 0, g.stream>>>(d, b.dev, 0, MffdEpi{nullptr, 0}, r0, 1 + r1);
+                    KT_END(K_SA, g.stream);
+                }
+                KT_BEGIN(K_RESID, g.stream);
+                const int rc = launch_flowres_tile(d, b.dev, g.prm, (int)((b.dev.p - b.dev.w) / d.N), 1.0, 1, true, 0, g.stream, MffdEpi{nullptr, 0}, kc,
+                                                   cNext, cEnd - cNext);
+                KT_END(K_RESID, g.stream);
+                if (rc) return fail("tile kernel launch failed inside the form-function pipeline");
+                const long long q0 = (long long)r0 * plane, q1 = (long long)r1 * plane;
+                KT_BEGIN(K_MFFD, g.stream);
+                k_nkvec<<<(unsigned)((q1 - q0 + 255) / 256), 256, 0, g.stream>>>(d, b.dev, b.nw, nullptr, nullptr, g.nkY + off, 1.0, 2, q0, q1);
+                KT_END(K_MFFD, g.stream);
+                CK(cudaEventRecord(g_ffEv[1][q], g.stream));
+                CK(cudaStreamWaitEvent(g_ffOut, g_ffEv[1][q], 0));
+                CK(cudaMemcpyAsync(rVec + off + q0, g.nkY + off + q0, (size_t)(q1 - q0) * sizeof(double), cudaMemcpyDeviceToHost, g_ffOut));
+                cNext = cEnd;
+            }
+        }
+        off += (long long)d.nz * plane;
+    }
+    (void)need;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(g_ffOut));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
 // FormFunction_mf (NKSolvers.F90:437-461): setW(wVec); computeResidualNK; setRVec(rVec)
 int adfb_form_function(const double* wVec, double* rVec, long long n) {
     ADFB_RANGE("adfb_form_function");
@@ -1142,6 +1291,12 @@ int adfb_form_function(const double* wVec, double* rVec, long long n) {
     const long long need = adfb_state_size();
     if (!wVec || !rVec || n != need) return fail("adfb_form_function: vector length %lld != local state size %lld", n, need);
     if (nk_buffers(need)) return 1;
+    for (Block& b : g.blocks)
+        if (b.alive && b.level == 1 && !b.haveMetrics) return fail("adfb_form_function: geometry of a block was never set");
+    {
+        const int rc = form_function_pipelined(wVec, rVec, need);
+        if (rc >= 0) return rc;
+    }
     CK(cudaMemcpyAsync(g.nkA, wVec, need * sizeof(double), cudaMemcpyHostToDevice, g.stream));
     if (nk_vec_kernel(g.nkA, nullptr, nullptr, 0.0, 0)) return 1;
     if (adfb_residual(1, kNkFlags)) return 1;
@@ -1305,7 +1460,7 @@ int adfb_timestep(int level, int onlyRadii) {
         dim3 tb(32, 4, 2);
         dim3 gr((b.d.NI + 31) / 32, (b.d.NJ + 3) / 4, (b.d.NK + 1) / 2);
         KT_BEGIN(K_PREP, g.stream);
-        launch_pdl(k_prep, gr, tb, g.stream, b.d, b.dev, onlyRadii ? 0 : 1, 1, 0);
+        launch_pdl(k_prep, gr, tb, g.stream, b.d, b.dev, onlyRadii ? 0 : 1, 1, 0, 0, INT_MAX);
         KT_END(K_PREP, g.stream);
     }
     CK(cudaGetLastError());

@@ -183,7 +183,12 @@ FHD void ff_visc(const AdfbParams& P, const FCell& m, const FCell& q, double s1,
     const double mue = porv * revSum;
     const double mut = mul + mue;
     const double gm1 = P.gammaInf - 1.0;
+#if defined(__CUDA_ARCH__)
+    const double heatCoef = mul * c_fheat[0] + mue * c_fheat[1];   // the same two quotients, formed once on the host (adfb_set_params)
+    (void)gm1;
+#else
     const double heatCoef = mul * (1.0 / (P.prandtl * gm1)) + mue * (1.0 / (P.prandtlTurb * gm1));
+#endif
     const double ssx = vn[0], ssy = vn[1], ssz = vn[2], snrm = vn[3];
     double corr;
     corr = g[0] * ssx + g[1] * ssy + g[2] * ssz - (q.u - m.u) * snrm;
@@ -815,7 +820,7 @@ __global__ void __maxnreg__(FT_MAXNREG) k_flowres
 __global__ void __launch_bounds__(FT_LB, FT_MINB) k_flowres
 #endif
 (Dims d, BlockDev b, FTile t, double rFil, int doDiss, int persistFw, int nw,
-                                                        MffdEpi mf, const __grid_constant__ FTmaMaps maps) {
+                                                        MffdEpi mf, const __grid_constant__ FTmaMaps maps, int zOff) {
     ADFB_PDL_SYNC();
     FSmem sm;
     sm.ring = ft_smem;
@@ -825,7 +830,7 @@ __global__ void __launch_bounds__(FT_LB, FT_MINB) k_flowres
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm.FX + (MERGED ? FT_NFLUX : FT_NFLUX_SPLIT) * FT_S0);   // 3 mbarriers
     const int tid = threadIdx.x;
     const FCtx x = ft_ctx(d, t, tid, blockIdx.x, blockIdx.y);
-    const int ka = 2 + blockIdx.z * t.kChunk;
+    const int ka = 2 + (blockIdx.z + zOff) * t.kChunk;   // zOff: the k chunks zOff .. of the slab pipeline; 0 otherwise
     const int kb = min(ka + t.kChunk - 1, d.kl);
     const int gi0 = blockIdx.x * (t.TX - 1), gj0 = blockIdx.y * (t.TY - 1);   // box index of the tile origin (i0-2, j0-2)
     const bool visc = VISCOUS && doDiss;
@@ -951,8 +956,10 @@ static int fused_mode() {   // ADFB_FUSED: 0 = off (k_nodal/k_faces/k_div), 1 = 
 }
 
 // returns 0 on success, -1 when the tile kernel does not apply (caller uses the general kernels), > 0 on error
+// kChunkForce > 0: that many planes per CTA instead of the wave-fitted chunk; zOff / zCount: only the k chunks zOff .. zOff+zCount-1
 static int launch_flowres_tile(const Dims& d, const BlockDev& b, const AdfbParams& prm, int nw, double rFil, int doDiss, bool merged,
-                               int persistFw, cudaStream_t stream, MffdEpi mf = MffdEpi{nullptr, 0}) {
+                               int persistFw, cudaStream_t stream, MffdEpi mf = MffdEpi{nullptr, 0}, int kChunkForce = 0, int zOff = 0,
+                               int zCount = -1) {
     static int nSM = 0;
     static size_t smemMax = 0;
     if (!nSM) {
@@ -965,6 +972,7 @@ static int launch_flowres_tile(const Dims& d, const BlockDev& b, const AdfbParam
     const bool viscous = prm.equations != ADFB_EULER;
     bool tma = fused_mode() >= 2 && !(d.NI & 1);
     FTile t = ftile_choose(d, tma, nSM);
+    if (kChunkForce > 0) t.kChunk = kChunkForce;
     if (!merged) t.smemBytes += (size_t)(FT_NFLUX_SPLIT - FT_NFLUX) * FT_S0 * sizeof(double);   // central and dissipative fluxes exchanged apart
     if (!ftile_fits(t) || t.smemBytes > smemMax) return -1;
     FTmaMaps maps;
@@ -975,7 +983,9 @@ static int launch_flowres_tile(const Dims& d, const BlockDev& b, const AdfbParam
         if (!tma) { t.useTma = 0; memset(&maps, 0, sizeof maps); }
     }
     const int nti = (d.nx + t.TX - 2) / (t.TX - 1), ntj = (d.ny + t.TY - 2) / (t.TY - 1), nkc = (d.nz + t.kChunk - 1) / t.kChunk;
-    dim3 grid(nti, ntj, nkc), block(t.nT);
+    if (zCount < 0) zCount = nkc - zOff;
+    if (zOff < 0 || zCount < 1 || zOff + zCount > nkc) return 1;
+    dim3 grid(nti, ntj, zCount), block(t.nT);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = t.smemBytes; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -987,7 +997,7 @@ static int launch_flowres_tile(const Dims& d, const BlockDev& b, const AdfbParam
     do {                                                                                                                        \
         static bool attrSet = false;                                                                                            \
         if (!attrSet) { cudaFuncSetAttribute(k_flowres<V, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax); attrSet = true; } \
-        e = cudaLaunchKernelEx(&cfg, k_flowres<V, M>, d, b, t, rFil, doDiss, persistFw, nw, mf, maps);                               \
+        e = cudaLaunchKernelEx(&cfg, k_flowres<V, M>, d, b, t, rFil, doDiss, persistFw, nw, mf, maps, zOff);                               \
     } while (0)
     if (viscous) { if (merged) FT_LAUNCH(true, true); else FT_LAUNCH(true, false); }
     else { if (merged) FT_LAUNCH(false, true); else FT_LAUNCH(false, false); }

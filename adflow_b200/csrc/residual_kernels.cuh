@@ -77,12 +77,13 @@ __global__ void __launch_bounds__(256) k_geom(Dims d, BlockDev b) {
 // (:5168-5203), spectral radii and local time step (timeStep, :1899-2148).
 // part: 0 = every box cell, 1 = owned cells without a halo neighbour (3:nx, ...: the pressure switch of dtl reads the six
 // neighbours), 2 = the rest (the first part does not need the BCs and runs beside them, see residual_body)
-__global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, int doRad, int part) {
+// kOff / kTop: the planes kOff .. kTop only (slab pipeline of adfb_form_function); 0 / INT_MAX: all of them
+__global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, int doRad, int part, int kOff, int kTop) {
     ADFB_PDL_SYNC();  // launched with programmatic stream serialization (launch_pdl)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = blockIdx.z * blockDim.z + threadIdx.z;
-    if (i > d.ib || j > d.jb || k > d.kb) return;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + kOff;
+    if (i > d.ib || j > d.jb || k > d.kb || k > kTop) return;
     if (part) {
         const bool inner = i >= 3 && i < d.il && j >= 3 && j < d.jl && k >= 3 && k < d.kl;
         if (inner != (part == 1)) return;
@@ -731,11 +732,12 @@ __device__ __forceinline__ double sa_source(const BlockDev& b, int N, int sJ, in
 // (blockette.F90:623-627, :1872-1897)
 // part: 0 = every owned cell, 1 = cells at least two layers away from the block boundary (their stencil holds no halo
 // cell: they do not need the BCs / the exchange), 2 = the boundary shell
-__global__ void __launch_bounds__(SA_TPB, SA_MINB) k_sa(Dims d, BlockDev b, int part, MffdEpi mf) {
+// kOff / kTop: the owned planes 2 + kOff .. kTop only (slab pipeline); 0 / INT_MAX: all of them
+__global__ void __launch_bounds__(SA_TPB, SA_MINB) k_sa(Dims d, BlockDev b, int part, MffdEpi mf, int kOff, int kTop) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 2;
-    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2;
-    if (i > d.il || j > d.jl || k > d.kl) return;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + 2 + kOff;
+    if (i > d.il || j > d.jl || k > d.kl || k > kTop) return;
     if (part) {
         const bool inner = i >= 4 && i <= d.il - 2 && j >= 4 && j <= d.jl - 2 && k >= 4 && k <= d.kl - 2;
         if (inner != (part == 1)) return;
@@ -888,12 +890,12 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
             cudaStreamCopyAttributes(s_side, stream);   // same L2 access-policy window as the main stream
             cudaEventRecord(s_fork, stream);
             cudaStreamWaitEvent(s_side, s_fork, 0);
-            k_sa<<<g, tr, 0, s_side>>>(d, b, saPart, mf);
+            k_sa<<<g, tr, 0, s_side>>>(d, b, saPart, mf, 0, INT_MAX);
             g_kt.launches++; g_kt.count[K_SA]++;
             cudaEventRecord(s_join, s_side);
         } else {
             KT_BEGIN(K_SA, stream);
-            k_sa<<<g, tr, 0, stream>>>(d, b, saPart, mf);
+            k_sa<<<g, tr, 0, stream>>>(d, b, saPart, mf, 0, INT_MAX);
             KT_END(K_SA, stream);
         }
     }
@@ -901,7 +903,7 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
         const int prepPart = ((parts & RC_PREP_OWNED) && (parts & RC_PREP_HALO)) ? 0 : (parts & RC_PREP_OWNED) ? 1 : 2;
         dim3 g((d.NI + tb.x - 1) / tb.x, (d.NJ + tb.y - 1) / tb.y, (d.NK + tb.z - 1) / tb.z);
         KT_BEGIN(K_PREP, stream);
-        launch_pdl(k_prep, g, tb, stream, d, b, updateDt, doRad, prepPart);
+        launch_pdl(k_prep, g, tb, stream, d, b, updateDt, doRad, prepPart, 0, INT_MAX);
         KT_END(K_PREP, stream);
     }
     // tile kernel (fused_kernels.cuh): exact central + scalar-JST (+ viscous) flow rows in one launch

@@ -10,6 +10,7 @@
 #pragma once
 #include "adfb_common.cuh"
 #include <math.h>
+#include <cooperative_groups.h>
 
 struct FaceDev {
     long long off[4];  // plane 0 (2nd halo) .. 3 (2nd interior), setBCPointers utils.F90:881
@@ -20,6 +21,7 @@ struct FaceDev {
     const double *ps, *rho, *velx, *vely, *velz, *ptInlet, *ttInlet, *htInlet, *fxd, *fyd, *fzd, *turbInlet;
     int inletTreatment;
     long long xoff;   // node plane of the boundary face (polar symmetry reads the mesh)
+    int bLo, bHi;     // clip of the second in-plane index (the slab pipeline applies the i / j faces plane range by plane range)
 };
 
 static FaceDev make_face(const Dims& d, const AdfbSubface& sf) {
@@ -33,6 +35,7 @@ static FaceDev make_face(const Dims& d, const AdfbSubface& sf) {
         default: f.off[0] = d.kb * d.sK; f.off[1] = d.ke * d.sK; f.off[2] = d.kl * d.sK; f.off[3] = d.nz * d.sK; f.sa = 1; f.sb = d.sJ; break;
     }
     f.icBeg = sf.icBeg; f.icEnd = sf.icEnd; f.jcBeg = sf.jcBeg; f.jcEnd = sf.jcEnd;
+    f.bLo = -(1 << 30); f.bHi = 1 << 30;
     f.bcType = sf.bcType;
     f.norm = sf.norm; f.rface = sf.rface; f.uSlip = sf.uSlip; f.TNSWall = sf.TNSWall;
     f.ps = sf.ps; f.rho = sf.rho; f.velx = sf.velx; f.vely = sf.vely; f.velz = sf.velz;
@@ -517,17 +520,19 @@ __global__ void __launch_bounds__(128) k_bc_frame_item(Dims d, BlockDev b, const
 // disjoint cells.  Items are given the level 1 + max(level of the earlier items they conflict with); the items of one level
 // run in one launch (blockIdx.z = item), the levels in the reference's order -- every conflicting pair keeps its order,
 // so the halos are the reference's bit for bit, in about half the launches.
-struct BcLevel {
+#define ADFB_BC_LEVEL_MAX 8
+struct BcLevel {   // passed by value: the face descriptors sit in the constant bank, no dependent global load before the state loads
     int n;
-    short sub[ADFB_BC_MAXITEMS], kind[ADFB_BC_MAXITEMS];
+    int kind[ADFB_BC_LEVEL_MAX];
+    FaceDev f[ADFB_BC_LEVEL_MAX];
 };
-__global__ void __launch_bounds__(128) k_bc_level(Dims d, BlockDev b, const BcList* __restrict__ Lp, BcLevel lv, int secondHalo) {
+__global__ void __launch_bounds__(128) k_bc_level(Dims d, BlockDev b, const __grid_constant__ BcLevel lv, int secondHalo) {
     ADFB_PDL_SYNC();
-    const FaceDev& f = Lp->f[lv.sub[blockIdx.z]];
+    const FaceDev& f = lv.f[blockIdx.z];
     const int kind = lv.kind[blockIdx.z];
     const int ia = blockIdx.x * blockDim.x + threadIdx.x + f.icBeg;
     const int jb = blockIdx.y * blockDim.y + threadIdx.y + f.jcBeg;
-    if (ia > f.icEnd || jb > f.jcEnd) return;
+    if (ia > f.icEnd || jb > f.jcEnd || jb < f.bLo || jb > f.bHi) return;
     if (kind == 3) bc_turb_cell(d, b, f, ia, jb, secondHalo);
     else bc_flow_cell(d, b, f, ia, jb, secondHalo, kind);
 }
@@ -545,24 +550,26 @@ struct BcSweep {
     short sub[ADFB_BC_MAXITEMS], kind[ADFB_BC_MAXITEMS];   // items sorted by level (stable)
     short levelBegin[ADFB_BC_MAXITEMS + 1];
     int bulkBegin[ADFB_BC_MAXSUB + 1];                      // first bulk CTA of every subface (32 x 16 patches)
+    int nSub, la[ADFB_BC_MAXSUB], lb[ADFB_BC_MAXSUB];       // by value (constant bank): no dependent global load before the state loads
+    FaceDev f[ADFB_BC_MAXSUB];
 };
 __device__ __forceinline__ void bc_bulk_box(const FaceDev& f, int la, int lb, int* a0, int* a1, int* b0, int* b1) {
     *a0 = f.icBeg > 4 ? f.icBeg : 4; *a1 = f.icEnd < la - 2 ? f.icEnd : la - 2;
     *b0 = f.jcBeg > 4 ? f.jcBeg : 4; *b1 = f.jcEnd < lb - 2 ? f.jcEnd : lb - 2;
     if (*a1 < *a0 || *b1 < *b0) { *a0 = f.icBeg; *a1 = f.icEnd; *b0 = f.jcEnd + 1; *b1 = f.jcEnd; }   // no bulk: all rows are frame
 }
-__global__ void __launch_bounds__(512) k_bc_sweep(Dims d, BlockDev b, const BcList* __restrict__ Lp, BcSweep sw, int secondHalo, int withTurb,
+__global__ void __launch_bounds__(512) k_bc_sweep(Dims d, BlockDev b, const BcList* __restrict__ Lp, const __grid_constant__ BcSweep sw, int secondHalo, int withTurb,
                                                   int withFlow) {
     ADFB_PDL_SYNC();
-    const BcList& L = *Lp;
+    (void)Lp;
     if (blockIdx.x == 0) {
         const int tid = threadIdx.y * 32 + threadIdx.x;
         for (int l = 0; l < sw.nLevels; l++) {
             for (int it = sw.levelBegin[l]; it < sw.levelBegin[l + 1]; it++) {
                 const int s = sw.sub[it], kind = sw.kind[it];
-                const FaceDev& f = L.f[s];
+                const FaceDev& f = sw.f[s];
                 int a0, a1, b0, b1;
-                bc_bulk_box(f, L.la[s], L.lb[s], &a0, &a1, &b0, &b1);
+                bc_bulk_box(f, sw.la[s], sw.lb[s], &a0, &a1, &b0, &b1);
                 for (int q = tid;; q += 512) {
                     int ia, jb;
                     if (!frame_cell(q, f.icBeg, f.icEnd, f.jcBeg, f.jcEnd, a0, a1, b0, b1, &ia, &jb)) break;
@@ -576,10 +583,53 @@ __global__ void __launch_bounds__(512) k_bc_sweep(Dims d, BlockDev b, const BcLi
     }
     const int cta = blockIdx.x - 1;
     int s = 0;
-    while (s + 1 < L.n && cta >= sw.bulkBegin[s + 1]) s++;
-    const FaceDev& f = L.f[s];
+    while (s + 1 < sw.nSub && cta >= sw.bulkBegin[s + 1]) s++;
+    const FaceDev& f = sw.f[s];
     int a0, a1, b0, b1;
-    bc_bulk_box(f, L.la[s], L.lb[s], &a0, &a1, &b0, &b1);
+    bc_bulk_box(f, sw.la[s], sw.lb[s], &a0, &a1, &b0, &b1);
+    if (b1 < b0) return;
+    const int local = cta - sw.bulkBegin[s];
+    const int nbx = (a1 - a0 + 1 + 31) / 32;
+    const int ia = (local % nbx) * 32 + threadIdx.x + a0, jb = (local / nbx) * 16 + threadIdx.y + b0;
+    if (ia > a1 || jb > b1) return;
+    bc_all_cell(d, b, f, ia, jb, secondHalo, withTurb, withFlow);
+}
+
+// k_bc_sweep with the ordered frames walked by a CLUSTER of 8 CTAs (4096 threads: a whole frame level in one pass) that meet
+// at the hardware cluster barrier between levels (release / acquire at cluster scope: the halo cells written by one CTA are
+// visible to the next level's reads of another).  Cluster 0 walks the frames, the other clusters apply the bulk cells.
+#define ADFB_BC_CLUSTER 8
+__global__ void __cluster_dims__(ADFB_BC_CLUSTER, 1, 1) __launch_bounds__(512)
+k_bc_sweep_cluster(Dims d, BlockDev b, const BcList* __restrict__ Lp, const __grid_constant__ BcSweep sw, int secondHalo, int withTurb, int withFlow, int nBulk) {
+    ADFB_PDL_SYNC();
+    (void)Lp;
+    if (blockIdx.x < ADFB_BC_CLUSTER) {
+        cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+        const int tid = (int)cl.block_rank() * 512 + threadIdx.y * 32 + threadIdx.x;
+        for (int l = 0; l < sw.nLevels; l++) {
+            for (int it = sw.levelBegin[l]; it < sw.levelBegin[l + 1]; it++) {
+                const int s = sw.sub[it], kind = sw.kind[it];
+                const FaceDev& f = sw.f[s];
+                int a0, a1, b0, b1;
+                bc_bulk_box(f, sw.la[s], sw.lb[s], &a0, &a1, &b0, &b1);
+                for (int q = tid;; q += 512 * ADFB_BC_CLUSTER) {
+                    int ia, jb;
+                    if (!frame_cell(q, f.icBeg, f.icEnd, f.jcBeg, f.jcEnd, a0, a1, b0, b1, &ia, &jb)) break;
+                    if (kind == 3) bc_turb_cell(d, b, f, ia, jb, secondHalo);
+                    else bc_flow_cell(d, b, f, ia, jb, secondHalo, kind);
+                }
+            }
+            if (l + 1 < sw.nLevels) cl.sync();
+        }
+        return;
+    }
+    const int cta = blockIdx.x - ADFB_BC_CLUSTER;
+    if (cta >= nBulk) return;
+    int s = 0;
+    while (s + 1 < sw.nSub && cta >= sw.bulkBegin[s + 1]) s++;
+    const FaceDev& f = sw.f[s];
+    int a0, a1, b0, b1;
+    bc_bulk_box(f, sw.la[s], sw.lb[s], &a0, &a1, &b0, &b1);
     if (b1 < b0) return;
     const int local = cta - sw.bulkBegin[s];
     const int nbx = (a1 - a0 + 1 + 31) / 32;
@@ -919,6 +969,7 @@ __global__ void __launch_bounds__(256) k_wall_forces(Dims d, BlockDev b, FaceDev
 }  // namespace
 
 // ADFB_BC_FUSED: 5 = the whole sweep in one launch, exact (k_bc_sweep: bulk cells by all CTAs, the ordered frames by CTA 0);
+// 6 = the same with the frames walked by a cluster of 8 CTAs (k_bc_sweep_cluster);
 // 4 = one launch per LEVEL of mutually independent items (k_bc_level); 0 = one launch per subface and phase over all of its cells, chained by programmatic dependent
 // launch (13 launches of ~5 us for the bench block); 3 = the whole ordered sweep in one launch, items ordered by a device-side
 // counter (k_bc_chain: parity-clean, but the ticket / fence / counter hand-over costs 5.3 us per item, measured 69 us per sweep
@@ -928,7 +979,7 @@ __global__ void __launch_bounds__(256) k_wall_forces(Dims d, BlockDev b, FaceDev
 // walking the frame items (measured slower in round 1)
 static int bc_mode() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("ADFB_BC_FUSED"); v = e ? atoi(e) : 0; }
+    if (v < 0) { const char* e = getenv("ADFB_BC_FUSED"); v = e ? atoi(e) : 4; }
     return v;
 }
 // the reference's ordered list of (subface, kind) items of one BC sweep (applyAllTurbBCThisBlock, then applyAllBC_block in its
@@ -964,11 +1015,57 @@ static bool bc_items_conflict(const std::vector<AdfbSubface>& subs, std::pair<in
     const bool apart = A.icEnd < C.icBeg || C.icEnd < A.icBeg || A.jcEnd < C.jcBeg || C.jcEnd < A.jcBeg;
     return !apart;                                                // subfaces of one face: disjoint unless their ranges overlap
 }
+// The ordered BC sweep as levels of mutually independent items (k_bc_level).  bLo / bHi clip the k index of the i- and j-face
+// subfaces, kFaces selects the k-face subfaces (1 = kMin, 2 = kMax): the slab pipeline of adfb_form_function applies the
+// sweep plane range by plane range -- an i/j-face cell touches its own k plane only, a k-face cell the planes 0..3 or
+// kl-1..kb, so every conflicting pair of items still meets inside one slab, in the reference's order.
+static int launch_bc_levels(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, int secondHalo, int withTurb, int withFlow,
+                            cudaStream_t s, int bLo = -(1 << 30), int bHi = 1 << 30, int kFaces = 3) {
+    const std::vector<std::pair<int, int>> items = bc_ordered_items(subs, secondHalo, withTurb, withFlow);
+    if (items.empty()) return 0;
+    std::vector<int> level(items.size(), 1);
+    int nLevels = 1;
+    for (size_t q = 0; q < items.size(); q++) {
+        for (size_t r = 0; r < q; r++)
+            if (level[r] >= level[q] && bc_items_conflict(subs, items[r], items[q])) level[q] = level[r] + 1;
+        if (level[q] > nLevels) nLevels = level[q];
+    }
+    for (int l = 1; l <= nLevels; l++) {
+        BcLevel lv;
+        lv.n = 0;
+        int ma = 1, mb = 1;
+        auto flush = [&]() {
+            if (!lv.n) return;
+            KT_BEGIN(K_BC, s);
+            launch_pdl(k_bc_level, dim3((ma + 31) / 32, (mb + 3) / 4, (unsigned)lv.n), dim3(32, 4), s, d, b, lv, secondHalo);
+            KT_END(K_BC, s);
+            lv.n = 0; ma = 1; mb = 1;
+        };
+        for (size_t q = 0; q < items.size(); q++) {
+            if (level[q] != l) continue;
+            const AdfbSubface& sf = subs[items[q].first];
+            const bool kFace = sf.faceId == ADFB_KMIN || sf.faceId == ADFB_KMAX;
+            if (kFace && !(kFaces & (sf.faceId == ADFB_KMIN ? 1 : 2))) continue;
+            FaceDev f = make_face(d, sf);
+            if (!kFace) {
+                f.bLo = bLo; f.bHi = bHi;
+                if (sf.jcEnd < bLo || sf.jcBeg > bHi) continue;   // nothing of this subface in the plane range
+            }
+            lv.f[lv.n] = f; lv.kind[lv.n] = items[q].second; lv.n++;
+            ma = std::max(ma, sf.icEnd - sf.icBeg + 1);
+            mb = std::max(mb, sf.jcEnd - sf.jcBeg + 1);
+            if (lv.n == ADFB_BC_LEVEL_MAX) flush();   // more independent items than one launch carries: any order
+        }
+        flush();
+    }
+    return (int)cudaGetLastError();
+}
 // all BCs of a block: bulk launch + ordered frames; returns -1 when the general path must be used
 static int launch_bc_fused(const Dims& d, const BlockDev& b, const std::vector<AdfbSubface>& subs, int secondHalo, int withTurb, int withFlow,
                            cudaStream_t s) {
-    if (!bc_mode() || subs.empty() || (int)subs.size() > ADFB_BC_MAXSUB || !b.bcList) return -1;
-    if (bc_mode() == 5) {
+    if (!bc_mode() || subs.empty()) return -1;
+    if (bc_mode() != 4 && ((int)subs.size() > ADFB_BC_MAXSUB || !b.bcList)) return -1;
+    if (bc_mode() == 5 || bc_mode() == 6) {
         const std::vector<std::pair<int, int>> items = bc_ordered_items(subs, secondHalo, withTurb, withFlow);
         if (items.empty()) return 0;
         if ((int)items.size() > ADFB_BC_MAXITEMS) return -1;
@@ -995,42 +1092,22 @@ static int launch_bc_fused(const Dims& d, const BlockDev& b, const std::vector<A
             const int lb = (sf.faceId == ADFB_KMIN || sf.faceId == ADFB_KMAX) ? d.jl : d.kl;
             const int a0 = std::max(sf.icBeg, 4), a1 = std::min(sf.icEnd, la - 2), b0 = std::max(sf.jcBeg, 4), b1 = std::min(sf.jcEnd, lb - 2);
             sw.bulkBegin[q] = nBulk;
+            sw.f[q] = make_face(d, sf); sw.la[q] = la; sw.lb[q] = lb;
             if (a1 >= a0 && b1 >= b0) nBulk += ((a1 - a0 + 1 + 31) / 32) * ((b1 - b0 + 1 + 15) / 16);
         }
         sw.bulkBegin[subs.size()] = nBulk;
+        sw.nSub = (int)subs.size();
         KT_BEGIN(K_BC, s);
-        launch_pdl(k_bc_sweep, dim3((unsigned)(1 + nBulk)), dim3(32, 16), s, d, b, (const BcList*)b.bcList, sw, secondHalo, withTurb, withFlow);
+        if (bc_mode() == 6) {
+            const unsigned nCta = (unsigned)(ADFB_BC_CLUSTER + (nBulk + ADFB_BC_CLUSTER - 1) / ADFB_BC_CLUSTER * ADFB_BC_CLUSTER);
+            launch_pdl(k_bc_sweep_cluster, dim3(nCta), dim3(32, 16), s, d, b, (const BcList*)b.bcList, sw, secondHalo, withTurb, withFlow, nBulk);
+        } else {
+            launch_pdl(k_bc_sweep, dim3((unsigned)(1 + nBulk)), dim3(32, 16), s, d, b, (const BcList*)b.bcList, sw, secondHalo, withTurb, withFlow);
+        }
         KT_END(K_BC, s);
         return (int)cudaGetLastError();
     }
-    if (bc_mode() == 4) {
-        const std::vector<std::pair<int, int>> items = bc_ordered_items(subs, secondHalo, withTurb, withFlow);
-        if (items.empty()) return 0;
-        if ((int)items.size() > ADFB_BC_MAXITEMS) return -1;
-        std::vector<int> level(items.size(), 1);
-        int nLevels = 1;
-        for (size_t q = 0; q < items.size(); q++) {
-            for (size_t r = 0; r < q; r++)
-                if (level[r] >= level[q] && bc_items_conflict(subs, items[r], items[q])) level[q] = level[r] + 1;
-            if (level[q] > nLevels) nLevels = level[q];
-        }
-        for (int l = 1; l <= nLevels; l++) {
-            BcLevel lv;
-            lv.n = 0;
-            int ma = 1, mb = 1;
-            for (size_t q = 0; q < items.size(); q++) {
-                if (level[q] != l) continue;
-                const AdfbSubface& sf = subs[items[q].first];
-                lv.sub[lv.n] = (short)items[q].first; lv.kind[lv.n] = (short)items[q].second; lv.n++;
-                ma = std::max(ma, sf.icEnd - sf.icBeg + 1);
-                mb = std::max(mb, sf.jcEnd - sf.jcBeg + 1);
-            }
-            KT_BEGIN(K_BC, s);
-            launch_pdl(k_bc_level, dim3((ma + 31) / 32, (mb + 3) / 4, (unsigned)lv.n), dim3(32, 4), s, d, b, (const BcList*)b.bcList, lv, secondHalo);
-            KT_END(K_BC, s);
-        }
-        return (int)cudaGetLastError();
-    }
+    if (bc_mode() == 4) return launch_bc_levels(d, b, subs, secondHalo, withTurb, withFlow, s);
     if (bc_mode() == 3) {
         BcItems it;
         memset(&it, 0, sizeof it);

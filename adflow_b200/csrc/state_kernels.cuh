@@ -7,6 +7,7 @@
 //                  (src/turbulence/turbUtils.F90:657-712) fused in one pass
 //   k_norms      : sumResiduals / sumAllResiduals (src/utils/utils.F90:6364-6459)
 #pragma once
+#include <limits.h>
 #include "adfb_common.cuh"
 #include <math.h>
 
@@ -51,14 +52,15 @@ __global__ void __launch_bounds__(256) k_metrics(Dims d, BlockDev b, double fact
 }
 
 // p on [pLo,pHi] (owned, or 0:ib with halos), rlv/rev on [vLo,vHi] (owned, or 1:ie with halos)
-__global__ void __launch_bounds__(256) k_state_prep(Dims d, BlockDev b, int includeHalos, int nw, int etot) {
+// kOff / kTop: the planes lo + kOff .. kTop only (slab pipeline of adfb_form_function); 0 / INT_MAX: all of them
+__global__ void __launch_bounds__(256) k_state_prep(Dims d, BlockDev b, int includeHalos, int nw, int etot, int kOff, int kTop) {
     ADFB_PDL_SYNC();  // launched with programmatic stream serialization (launch_pdl)
     const int lo = includeHalos ? 0 : 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x + lo;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + lo;
-    const int k = blockIdx.z * blockDim.z + threadIdx.z + lo;
+    const int k = blockIdx.z * blockDim.z + threadIdx.z + lo + kOff;
     const int iHi = includeHalos ? d.ib : d.il, jHi = includeHalos ? d.jb : d.jl, kHi = includeHalos ? d.kb : d.kl;
-    if (i > iHi || j > jHi || k > kHi) return;
+    if (i > iHi || j > jHi || k > kHi || k > kTop) return;
     const long long N = d.N;
     const long long c = ADFB_IDX(i, j, k);
     const double rho = b.w[c], u = b.w[N + c], v = b.w[2 * N + c], w = b.w[3 * N + c];
@@ -163,11 +165,13 @@ __global__ void __launch_bounds__(256) k_vec(Dims d, BlockDev b, int nw, double*
 //  mode 1: perturbed setW               w <- max-clip(base + h*vec)   (MFFD: F(U + h a))
 //  mode 2: setRVec (:1262-1329)         out <- dw/volRef (* turbResScale on turbulence rows)
 //  mode 3: MFFD difference              out <- (dw/volRef*scale - base) / h
+// q0 / qEnd: the entries q0 .. qEnd-1 of the block's vector only (slab pipeline); 0 / LLONG_MAX: all
 __global__ void __launch_bounds__(256) k_nkvec(Dims d, BlockDev b, int nw, const double* __restrict__ vec,
-                                               const double* __restrict__ base, double* __restrict__ out, double h, int mode) {
+                                               const double* __restrict__ base, double* __restrict__ out, double h, int mode, long long q0,
+                                               long long qEnd) {
     const long long nOwned = (long long)d.nx * d.ny * d.nz;
-    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nOwned * nw) return;
+    const long long q = q0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nOwned * nw || q >= qEnd) return;
     const int l = (int)(q % nw);
     const long long cell = q / nw;
     const int i = (int)(cell % d.nx) + 2;
@@ -274,7 +278,7 @@ static int launch_state_prep(const Dims& d, const BlockDev& b, const AdfbParams&
     const int ni = includeHalos ? d.NI : d.nx, nj = includeHalos ? d.NJ : d.ny, nk = includeHalos ? d.NK : d.nz;
     dim3 g((ni + tb.x - 1) / tb.x, (nj + tb.y - 1) / tb.y, (nk + tb.z - 1) / tb.z);
     KT_BEGIN(K_STATE, stream);
-    launch_pdl(k_state_prep, g, tb, stream, d, b, includeHalos ? 1 : 0, prm.equations == ADFB_RANS ? 6 : 5, etot ? 1 : 0);
+    launch_pdl(k_state_prep, g, tb, stream, d, b, includeHalos ? 1 : 0, prm.equations == ADFB_RANS ? 6 : 5, etot ? 1 : 0, 0, INT_MAX);
     KT_END(K_STATE, stream);
     return (int)cudaGetLastError();
 }

@@ -403,6 +403,11 @@ class ADFLOW_B200:
         check(self.L.adfb_form_function(wvec.ctypes.data, r.ctypes.data, wvec.size), "adfb_form_function")
         return r
 
+    def formFunctionPtr(self, w_ptr, r_ptr, n):
+        """FormFunction_mf for host vectors given by address (e.g. page-locked torch tensors: with page-locked vectors and
+        blocks without exchange partners the call runs as a slab pipeline -- copy in, kernels and copy out overlap)"""
+        check(self.L.adfb_form_function(int(w_ptr), int(r_ptr), int(n)), "adfb_form_function")
+
     def mffdSetBase(self, U):
         U = np.ascontiguousarray(U, dtype=np.float64)
         check(self.L.adfb_mffd_set_base(U.ctypes.data, U.size), "adfb_mffd_set_base")
