@@ -14,6 +14,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "adfb_common.cuh"
 #include "state_kernels.cuh"
@@ -1149,8 +1150,8 @@ static const unsigned kNkFlags = ADFB_RES_FLOW | ADFB_RES_TURB;
 // the host-to-device copy, the kernels and the device-to-host copy of one call overlap (three streams, full-duplex PCIe).
 // Same kernels, same operands as the one-shot path: the result is identical.  Used when both vectors are page-locked, the
 // blocks have no exchange partners (no 1-to-1 / overset pattern on level 1) and the tile kernel applies; ADFB_FF_PIPE=0 disables it.
-static cudaStream_t g_ffIn = nullptr, g_ffOut = nullptr;
-static cudaEvent_t g_ffEv[3][32];
+static cudaStream_t g_ffIn = nullptr, g_ffOut = nullptr, g_ffBack = nullptr;
+static cudaEvent_t g_ffEv[4][34];
 static bool ff_pinned(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -1158,36 +1159,26 @@ static bool ff_pinned(const void* p) {
 }
 static int form_function_pipe_slabs() {   // read at every call: tests switch it
     const char* e = getenv("ADFB_FF_PIPE");
-    return e ? atoi(e) : 6;
+    return e ? atoi(e) : 8;
 }
-// returns -1 when the pipeline does not apply (caller takes the one-shot path)
-static int form_function_pipelined(const double* wVec, double* rVec, long long need) {
-    const int wantSlabs = form_function_pipe_slabs();
-    if (wantSlabs < 2 || g.nranks > 1 || g_kt.on || g.mffdFuse) return -1;
-    {   // exchange partners (entries in a 1-to-1 or overset pattern of level 1) tie planes of different slabs together
-        auto busy = [](const std::map<int, Context::Pattern>& m) {
-            auto it = m.find(1);
-            return it != m.end() && it->second.set && (it->second.nSend || it->second.nRecv || it->second.nInt);
-        };
-        if (busy(g.pats) || busy(g.ovPats)) return -1;
-    }
-    if (!ff_pinned(wVec) || !ff_pinned(rVec)) return -1;
-    const int kc = 4;   // planes per CTA of the tile kernel inside the pipeline
-    for (Block& b : g.blocks) {
-        if (!b.alive || b.level != 1) continue;
-        if (!b.haveMetrics || b.nOrphans || !tile_kernel_applies(b.d, b.dev, g.prm) || b.d.nz < 4 * kc) return -1;
-    }
-    if (!g_ffIn) {
-        CK(cudaStreamCreateWithFlags(&g_ffIn, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&g_ffOut, cudaStreamNonBlocking));
-        for (int a = 0; a < 3; a++) for (int q = 0; q < 32; q++) CK(cudaEventCreateWithFlags(&g_ffEv[a][q], cudaEventDisableTiming));
-    }
-    set_l2_window();
+// the stream work of one pipelined call (captured into a CUDA graph per (wVec, rVec) pair: ~15 launches per slab otherwise
+// cost more host time than the GPU needs for them).  Front end of a slab (setW, p / rlv / rev, BCs, time step / sensor) on the
+// library stream, back end (SA row, tile kernel, setRVec) on a second one: the front end of slab s+1 touches planes above the
+// ones the back end of slab s reads, so the two run side by side.
+static int form_function_pipe_kc() {   // planes per CTA of the tile kernel inside the pipeline
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ADFB_FF_KC"); v = e ? atoi(e) : 4; if (v < 1) v = 4; }
+    return v;
+}
+static int form_function_pipe_body(const double* wVec, double* rVec, int wantSlabs, int twoStreams) {
+    const int kc = form_function_pipe_kc();
     const bool rans = g.prm.equations == ADFB_RANS;
-    // the copy streams start after whatever the library stream still has in flight, and the first kernels after them
-    CK(cudaEventRecord(g_ffEv[2][0], g.stream));
-    CK(cudaStreamWaitEvent(g_ffIn, g_ffEv[2][0], 0));
-    CK(cudaStreamWaitEvent(g_ffOut, g_ffEv[2][0], 0));
+    cudaStream_t sF = g.stream, sB = twoStreams ? g_ffBack : g.stream;
+    // fork: the other streams start after whatever the library stream still has in flight
+    CK(cudaEventRecord(g_ffEv[3][0], sF));
+    CK(cudaStreamWaitEvent(g_ffIn, g_ffEv[3][0], 0));
+    CK(cudaStreamWaitEvent(g_ffOut, g_ffEv[3][0], 0));
+    if (twoStreams) CK(cudaStreamWaitEvent(sB, g_ffEv[3][0], 0));
     long long off = 0;
     for (Block& b : g.blocks) {
         if (!b.alive || b.level != 1) continue;
@@ -1200,7 +1191,7 @@ static int form_function_pipelined(const double* wVec, double* rVec, long long n
         {
             std::vector<double> wgt(S);
             double tot = 0.0;
-            for (int q = 0; q < S; q++) { const double x = (q + 0.5) / S; wgt[q] = 0.6 + 1.6 * x * (1.0 - x) * 2.0; tot += wgt[q]; }
+            for (int q = 0; q < S; q++) { const double x = (q + 0.5) / S; wgt[q] = 0.6 + 3.2 * x * (1.0 - x); tot += wgt[q]; }
             double acc = 0.0;
             for (int q = 0; q < S; q++) {
                 acc += wgt[q];
@@ -1221,54 +1212,58 @@ static int form_function_pipelined(const double* wVec, double* rVec, long long n
         for (int q = 0; q < S; q++) {
             const bool first = q == 0, last = q == S - 1;
             const int o0 = ownedEnd(cb[q]), o1 = ownedEnd(cb[q + 1]);   // owned planes o0 .. o1-1 (0-based) = absolute 2+o0 .. 1+o1
-            CK(cudaStreamWaitEvent(g.stream, g_ffEv[0][q], 0));
+            CK(cudaStreamWaitEvent(sF, g_ffEv[0][q], 0));
             // setW + p / rlv / rev of the slab's owned cells
             {
                 const long long q0 = (long long)o0 * plane, q1 = (long long)o1 * plane;
-                KT_BEGIN(K_MFFD, g.stream);
-                k_nkvec<<<(unsigned)((q1 - q0 + 255) / 256), 256, 0, g.stream>>>(d, b.dev, b.nw, g.nkA + off, nullptr, nullptr, 0.0, 0, q0, q1);
-                KT_END(K_MFFD, g.stream);
+                KT_BEGIN(K_MFFD, sF);
+                k_nkvec<<<(unsigned)((q1 - q0 + 255) / 256), 256, 0, sF>>>(d, b.dev, b.nw, g.nkA + off, nullptr, nullptr, 0.0, 0, q0, q1);
+                KT_END(K_MFFD, sF);
                 dim3 tb(32, 4, 2);
                 dim3 gr((d.nx + 31) / 32, (d.ny + 3) / 4, (o1 - o0 + 1) / 2);
-                KT_BEGIN(K_STATE, g.stream);
-                launch_pdl(k_state_prep, gr, tb, g.stream, d, b.dev, 0, rans ? 6 : 5, 1, o0, 1 + o1);
-                KT_END(K_STATE, g.stream);
+                KT_BEGIN(K_STATE, sF);
+                launch_pdl(k_state_prep, gr, tb, sF, d, b.dev, 0, rans ? 6 : 5, 1, o0, 1 + o1);
+                KT_END(K_STATE, sF);
             }
             // boundary conditions of the slab's planes (+ the k-face subfaces with the first / last slab)
             const int pLo = first ? 0 : 2 + o0, pHi = last ? d.kb : 1 + o1;
-            if (launch_bc_levels(d, b.dev, b.subfaces, 1, rans ? 1 : 0, 1, g.stream, first ? -(1 << 30) : pLo, last ? (1 << 30) : pHi,
+            if (launch_bc_levels(d, b.dev, b.subfaces, 1, rans ? 1 : 0, 1, sF, first ? -(1 << 30) : pLo, last ? (1 << 30) : pHi,
                                  (first ? 1 : 0) | (last ? 2 : 0)))
                 return fail("BC launch failed");
             // time step / radii / sensor of the slab's planes (halo planes with the first and the last slab)
             {
                 dim3 tb(32, 4, 2);
                 dim3 gr((d.NI + 31) / 32, (d.NJ + 3) / 4, (pHi - pLo + 2) / 2);
-                KT_BEGIN(K_PREP, g.stream);
-                launch_pdl(k_prep, gr, tb, g.stream, d, b.dev, 1, 1, 0, pLo, pHi);
-                KT_END(K_PREP, g.stream);
+                KT_BEGIN(K_PREP, sF);
+                launch_pdl(k_prep, gr, tb, sF, d, b.dev, 1, 1, 0, pLo, pHi);
+                KT_END(K_PREP, sF);
             }
             // residual rows of the k chunks whose +-2 plane stencil is complete
             int cEnd = cNext;
             while (cEnd < nChunks && (last || 2 + ownedEnd(cEnd + 1) - 1 + 2 <= pHi)) cEnd++;
             if (cEnd > cNext) {
+                if (twoStreams) {
+                    CK(cudaEventRecord(g_ffEv[2][q], sF));
+                    CK(cudaStreamWaitEvent(sB, g_ffEv[2][q], 0));
+                }
                 const int r0 = ownedEnd(cNext), r1 = ownedEnd(cEnd);
                 if (rans) {
                     dim3 tr(32, 4, 1);
                     dim3 gr((d.nx + 31) / 32, (d.ny + 3) / 4, r1 - r0);
-                    KT_BEGIN(K_SA, g.stream);
-                    k_sa<<<gr, tr, 0, g.stream>>>(d, b.dev, 0, MffdEpi{nullptr, 0}, r0, 1 + r1);
-                    KT_END(K_SA, g.stream);
+                    KT_BEGIN(K_SA, sB);
+                    k_sa<<<gr, tr, 0, sB>>>(d, b.dev, 0, MffdEpi{nullptr, 0}, r0, 1 + r1);
+                    KT_END(K_SA, sB);
                 }
-                KT_BEGIN(K_RESID, g.stream);
-                const int rc = launch_flowres_tile(d, b.dev, g.prm, (int)((b.dev.p - b.dev.w) / d.N), 1.0, 1, true, 0, g.stream, MffdEpi{nullptr, 0}, kc,
+                KT_BEGIN(K_RESID, sB);
+                const int rc = launch_flowres_tile(d, b.dev, g.prm, (int)((b.dev.p - b.dev.w) / d.N), 1.0, 1, true, 0, sB, MffdEpi{nullptr, 0}, kc,
                                                    cNext, cEnd - cNext);
-                KT_END(K_RESID, g.stream);
+                KT_END(K_RESID, sB);
                 if (rc) return fail("tile kernel launch failed inside the form-function pipeline");
                 const long long q0 = (long long)r0 * plane, q1 = (long long)r1 * plane;
-                KT_BEGIN(K_MFFD, g.stream);
-                k_nkvec<<<(unsigned)((q1 - q0 + 255) / 256), 256, 0, g.stream>>>(d, b.dev, b.nw, nullptr, nullptr, g.nkY + off, 1.0, 2, q0, q1);
-                KT_END(K_MFFD, g.stream);
-                CK(cudaEventRecord(g_ffEv[1][q], g.stream));
+                KT_BEGIN(K_MFFD, sB);
+                k_nkvec<<<(unsigned)((q1 - q0 + 255) / 256), 256, 0, sB>>>(d, b.dev, b.nw, nullptr, nullptr, g.nkY + off, 1.0, 2, q0, q1);
+                KT_END(K_MFFD, sB);
+                CK(cudaEventRecord(g_ffEv[1][q], sB));
                 CK(cudaStreamWaitEvent(g_ffOut, g_ffEv[1][q], 0));
                 CK(cudaMemcpyAsync(rVec + off + q0, g.nkY + off + q0, (size_t)(q1 - q0) * sizeof(double), cudaMemcpyDeviceToHost, g_ffOut));
                 cNext = cEnd;
@@ -1276,9 +1271,63 @@ static int form_function_pipelined(const double* wVec, double* rVec, long long n
         }
         off += (long long)d.nz * plane;
     }
-    (void)need;
+    // join: everything meets on the library stream again
+    CK(cudaEventRecord(g_ffEv[3][1], g_ffIn));
+    CK(cudaStreamWaitEvent(sF, g_ffEv[3][1], 0));
+    CK(cudaEventRecord(g_ffEv[3][2], g_ffOut));
+    CK(cudaStreamWaitEvent(sF, g_ffEv[3][2], 0));
+    if (twoStreams) {
+        CK(cudaEventRecord(g_ffEv[3][3], sB));
+        CK(cudaStreamWaitEvent(sF, g_ffEv[3][3], 0));
+    }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(g_ffOut));
+    return 0;
+}
+// returns -1 when the pipeline does not apply (caller takes the one-shot path)
+static int form_function_pipelined(const double* wVec, double* rVec, long long need) {
+    (void)need;
+    const int wantSlabs = form_function_pipe_slabs();
+    if (wantSlabs < 2 || g.nranks > 1 || g_kt.on || g.mffdFuse) return -1;
+    {   // exchange partners (entries in a 1-to-1 or overset pattern of level 1) tie planes of different slabs together
+        auto busy = [](const std::map<int, Context::Pattern>& m) {
+            auto it = m.find(1);
+            return it != m.end() && it->second.set && (it->second.nSend || it->second.nRecv || it->second.nInt);
+        };
+        if (busy(g.pats) || busy(g.ovPats)) return -1;
+    }
+    if (!ff_pinned(wVec) || !ff_pinned(rVec)) return -1;
+    for (Block& b : g.blocks) {
+        if (!b.alive || b.level != 1) continue;
+        if (!b.haveMetrics || b.nOrphans || !tile_kernel_applies(b.d, b.dev, g.prm) || b.d.nz < 16) return -1;
+    }
+    if (!g_ffIn) {
+        CK(cudaStreamCreateWithFlags(&g_ffIn, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&g_ffOut, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&g_ffBack, cudaStreamNonBlocking));
+        for (int a = 0; a < 4; a++) for (int q = 0; q < 34; q++) CK(cudaEventCreateWithFlags(&g_ffEv[a][q], cudaEventDisableTiming));
+    }
+    set_l2_window();
+    int twoStreams = 1;
+    if (const char* e = getenv("ADFB_FF_STREAMS")) twoStreams = atoi(e) >= 2 ? 1 : 0;
+    // one graph per (wVec, rVec, slabs, streams): an NK solve calls with the same PETSc vectors over and over
+    unsigned long long h = 1469598103934665603ull;
+    for (unsigned long long v : {(unsigned long long)(uintptr_t)wVec, (unsigned long long)(uintptr_t)rVec, (unsigned long long)wantSlabs,
+                                 (unsigned long long)twoStreams})
+        h = (h ^ v) * 1099511628211ull;
+    const unsigned long long key = (12ull << 40) | (h & 0xffffffffffull);
+    {   // a handful of vector pairs at most: forget the oldest graph beyond that
+        static std::vector<unsigned long long> keys;
+        if (std::find(keys.begin(), keys.end(), key) == keys.end()) {
+            keys.push_back(key);
+            if (keys.size() > 8) {
+                auto it = g.graphs.find(keys.front());
+                if (it != g.graphs.end()) { cudaGraphExecDestroy(it->second); g.graphLaunches.erase(it->first); g.graphs.erase(it); }
+                keys.erase(keys.begin());
+            }
+        }
+    }
+    const int rc = run_graphed(key, [&]() { return form_function_pipe_body(wVec, rVec, wantSlabs, twoStreams); });
+    if (rc) return rc;
     CK(cudaStreamSynchronize(g.stream));
     return 0;
 }
