@@ -346,19 +346,35 @@ __global__ void __launch_bounds__(32 * ADFB_DT_WARPS) k_dadi_thomas_tile(Dims d,
     double* f = b.dw + n * N;
     const bool alongLine = sd == 1;
     const int nChunks = (nl + CH - 1) / CH;
-    // tile element e -> (line, cell of the chunk)
-#define DT_ELEM(e, ln, u) const int ln = alongLine ? (e) / CH : (e) % 32, u = alongLine ? (e) % CH : (e) / 32
+    // The 32 x CH tile is copied by the warp in CH passes of 32 elements.  Lines along i (sd == 1): lane -> cell u = lane % CH of
+    // line lane / CH + (32 / CH) * pass (8 lanes = one 64-byte segment of a line); otherwise lane -> line, pass -> cell (32 lanes =
+    // 256 contiguous bytes across the lines).  Global and shared offsets of the passes are fixed per lane; a chunk adds m0 * sd.
+    int gOff[CH], sOff[CH];
+    unsigned okLine = 0;   // bit r: the line of pass r exists
+#pragma unroll
+    for (int r = 0; r < CH; r++) {
+        const int ln = alongLine ? (lane / CH) + (32 / CH) * r : lane;
+        const int u = alongLine ? lane % CH : r;
+        gOff[r] = base0 + ln * s1 + u * sd;
+        sOff[r] = ln * (CH + 1) + u;
+        if (ln < nLines) okLine |= 1u << r;
+    }
+    const int uLane = alongLine ? lane % CH : 0;   // cell of the lane's elements (alongLine); pass index otherwise
+    double* const in0 = &S.in[0][0][0][0];
+    double* const out0 = &S.out[0][0][0];
+    constexpr int TILE = 32 * (CH + 1);
     auto issueF = [&](int chunk, int stage) {
         const int m0 = 2 + chunk * CH;
-        for (int e = lane; e < 32 * CH; e += 32) {
-            DT_ELEM(e, ln, u);
-            const int m = m0 + u;
-            if (ln < nLines && m <= l) {
-                const int c = base0 + ln * s1 + m * sd;
-                dt_cp8(&S.in[stage][0][ln][u], ccA + c);
-                dt_cp8(&S.in[stage][1][ln][u], bbA + c);
-                dt_cp8(&S.in[stage][2][ln][u], dsA + c);
-                dt_cp8(&S.in[stage][3][ln][u], f + c);
+        double* t0 = in0 + stage * 4 * TILE;
+#pragma unroll
+        for (int r = 0; r < CH; r++) {
+            const int m = m0 + (alongLine ? uLane : r);
+            if (((okLine >> r) & 1u) && m <= l) {
+                const int c = gOff[r] + m0 * sd;
+                dt_cp8(t0 + sOff[r], ccA + c);
+                dt_cp8(t0 + TILE + sOff[r], bbA + c);
+                dt_cp8(t0 + 2 * TILE + sOff[r], dsA + c);
+                dt_cp8(t0 + 3 * TILE + sOff[r], f + c);
             }
         }
         dt_commit();
@@ -386,13 +402,13 @@ __global__ void __launch_bounds__(32 * ADFB_DT_WARPS) k_dadi_thomas_tile(Dims d,
             }
         }
         __syncwarp();
-        for (int e = lane; e < 32 * CH; e += 32) {
-            DT_ELEM(e, ln, u);
-            const int m = m0 + u;
-            if (ln < nLines && m <= l) {
-                const int c = base0 + ln * s1 + m * sd;
-                dd[c] = S.out[0][ln][u];
-                fo[c] = S.out[1][ln][u];
+#pragma unroll
+        for (int r = 0; r < CH; r++) {
+            const int m = m0 + (alongLine ? uLane : r);
+            if (((okLine >> r) & 1u) && m <= l) {
+                const int c = gOff[r] + m0 * sd;
+                dd[c] = out0[sOff[r]];
+                fo[c] = out0[TILE + sOff[r]];
             }
         }
         __syncwarp();
@@ -400,13 +416,14 @@ __global__ void __launch_bounds__(32 * ADFB_DT_WARPS) k_dadi_thomas_tile(Dims d,
     // back substitution, chunks in reverse; ffp holds ff(l) = the value stored at m = l
     auto issueB = [&](int chunk, int stage) {
         const int m0 = 2 + chunk * CH;
-        for (int e = lane; e < 32 * CH; e += 32) {
-            DT_ELEM(e, ln, u);
-            const int m = m0 + u;
-            if (ln < nLines && m <= l) {
-                const int c = base0 + ln * s1 + m * sd;
-                dt_cp8(&S.in[stage][0][ln][u], fo + c);
-                dt_cp8(&S.in[stage][1][ln][u], dd + c);
+        double* t0 = in0 + stage * 4 * TILE;
+#pragma unroll
+        for (int r = 0; r < CH; r++) {
+            const int m = m0 + (alongLine ? uLane : r);
+            if (((okLine >> r) & 1u) && m <= l) {
+                const int c = gOff[r] + m0 * sd;
+                dt_cp8(t0 + sOff[r], fo + c);
+                dt_cp8(t0 + TILE + sOff[r], dd + c);
             }
         }
         dt_commit();
@@ -430,14 +447,13 @@ __global__ void __launch_bounds__(32 * ADFB_DT_WARPS) k_dadi_thomas_tile(Dims d,
             }
         }
         __syncwarp();
-        for (int e = lane; e < 32 * CH; e += 32) {
-            DT_ELEM(e, ln, u);
-            const int m = m0 + u;
-            if (ln < nLines && m <= l) f[base0 + ln * s1 + m * sd] = S.out[0][ln][u];
+#pragma unroll
+        for (int r = 0; r < CH; r++) {
+            const int m = m0 + (alongLine ? uLane : r);
+            if (((okLine >> r) & 1u) && m <= l) f[gOff[r] + m0 * sd] = out0[sOff[r]];
         }
         __syncwarp();
     }
-#undef DT_ELEM
 }
 
 // The three coefficient sets and the five right-hand sides of LPC grid lines solved in shared memory: replaces

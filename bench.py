@@ -584,6 +584,14 @@ def main():
     res_three = h_res.numpy().copy()
     e2e_ms = wall_ms(e2e_step)
     e2e_maxdiff = float(np.abs(h_res.numpy() - res_three).max() / max(np.abs(res_three).max(), 1e-300))
+    # nvidia-smi answers every 100 ms and needs a few hundred ms for its first line; a short timed region (K steps of 0.3 ms) can end
+    # before it.  The same step keeps running, untimed, for a fixed number of launches on every rank (the step holds a collective
+    # at N > 1), so that the clocks and throttle reasons reported are those of this workload under load.
+    for _ in range(60):
+        for _ in range(25):
+            step()
+        torch.cuda.synchronize()
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel timing pass (roofline) --------------------------------------
