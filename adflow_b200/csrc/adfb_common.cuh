@@ -118,7 +118,7 @@ __host__ __device__ static inline double dmin_(double a, double b) { return a < 
 // launch accounting + optional per-kernel CUDA-event timing (bench.py roofline)
 #include <vector>
 enum KernelId { K_PREP = 0, K_NODAL, K_RESID, K_DIV, K_SA, K_STATE, K_METRICS, K_NORMS, K_VEC, K_BC, K_RK, K_HALO, K_DADI, K_SASOLVE, K_MFFD, K_MISC, K_NUM };
-static const char* const kKernelNames[K_NUM] = {"k_prep", "k_nodal", "k_faces", "k_div", "k_sa", "k_state_prep", "k_metrics", "k_norms",
+static const char* const kKernelNames[K_NUM] = {"k_prep", "k_nodal", "k_flowres|k_faces", "k_div", "k_sa", "k_state_prep", "k_metrics", "k_norms",
                                                 "k_vec", "k_bc", "k_rk", "k_halo", "k_dadi", "k_sa_solve", "k_mffd", "k_misc"};
 struct KTimer {
     bool on = false;

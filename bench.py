@@ -608,6 +608,7 @@ def main():
     kernels = {s.L.adfb_kernel_name(i).decode(): {"ms_per_launch": ms_k[i] / cnt_k[i], "launches": int(cnt_k[i])}
                for i in range(nk) if cnt_k[i] > 0}
     res_ms = sum(ms_k[i] for i in range(nk)) / args.steps  # every kernel of the step (preamble, BCs, halo, core)
+    dom = max(kernels.items(), key=lambda kv: kv[1]["ms_per_launch"] * kv[1]["launches"]) if kernels else None
     _ = flags_core
 
     # ---- the other operators of the metric (smoothers, SA solve, matrix-free matvec): N = 1 only --------
@@ -778,6 +779,11 @@ def main():
                          "kernel": "whole residual step: all launches (state prep, BCs, halo pack/unpack, k_prep, k_flowres tile kernel, "
                                    "k_sa) charged against 176 B/cell",
                          "algorithmic_bytes_per_cell": BYTES_PER_CELL, "kernels": kernels,
+                         "dominant_kernel": None if dom is None else {
+                             "name": dom[0], "ms_per_launch": dom[1]["ms_per_launch"],
+                             "share_of_summed_kernel_time": dom[1]["ms_per_launch"] * dom[1]["launches"] / (res_ms * args.steps),
+                             "GB/s_if_charged_the_whole_176_B_per_cell": BYTES_PER_CELL * cells / (dom[1]["ms_per_launch"] * 1e-3) / 1e9,
+                             "note": "the tile kernel k_flowres (flow rows of the residual); its own ncu numbers are in profiles/r02_ncu_summary.md"},
                          "second_roof": FP64_ROOF},
             "clocks": clocks,
         }
