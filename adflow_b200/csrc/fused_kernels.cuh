@@ -230,8 +230,16 @@ FHD void ff_visc(const AdfbParams& P, const FCell& m, const FCell& q, double s1,
 FHD double ff_dss(double sm, double s0, double sp, double sslim) {
     return fabs((sp - 2.0 * s0 + sm) / (sp + 2.0 * s0 + sm + sslim));
 }
-FHD double ff_sslim(const AdfbParams& P) {
+FHD double ff_sslim_eval(const AdfbParams& P) {
     return (P.equations == ADFB_EULER) ? 0.001 * P.pInfCorr : 0.001 * P.pInfCorr / pow(P.rhoInf, P.gammaInf);
+}
+FHD double ff_sslim(const AdfbParams& P) {
+#if defined(__CUDA_ARCH__)
+    (void)P;
+    return c_fheat[2];   // ff_sslim_eval(c_prm), evaluated once per parameter set on the device (k_param_consts)
+#else
+    return ff_sslim_eval(P);
+#endif
 }
 
 FHD FCell ft_cell(const double* __restrict__ S, int o) {

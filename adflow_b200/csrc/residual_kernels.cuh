@@ -148,6 +148,11 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
     b.dtl[c] = rfl / dt;
 }
 
+// parameter-only constants evaluated once per adfb_set_params with the device's own arithmetic (c_fheat[2])
+__global__ void k_param_consts(double* out) {
+    out[0] = ff_sslim_eval(c_prm);
+}
+
 // ---------------------------------------------------------------------------
 // k_nodal: shock sensor dss (blockette.F90:3091-3105) on cells 1:ie and the nodal gradients
 // (allNodalGradients, :5205-5515) on nodes 1:il in gather form.  For node n (= cell index c)
@@ -165,8 +170,7 @@ __global__ void __launch_bounds__(NODAL_TPB, NODAL_MINB) k_nodal(Dims d, BlockDe
     const int N = (int)d.N, sJ = (int)d.sJ, sK = (int)d.sK;
     const int c = i + sJ * j + sK * k;
     if (c_prm.spaceDiscr == ADFB_DISS_SCALAR) {
-        const double sslim = (c_prm.equations == ADFB_EULER) ? 0.001 * c_prm.pInfCorr
-                                                            : 0.001 * c_prm.pInfCorr / pow(c_prm.rhoInf, c_prm.gammaInf);
+        const double sslim = c_fheat[2];   // 0.001 pInfCorr / rhoInf**gamma (pInfCorr for Euler), k_param_consts
         const double* ss = dissApprox ? b.shock : b.ss;  // *Approx: frozen sensor field (blockette.F90:4385-4396)
         const double s0 = ss[c];
         b.dss[c] = fabs((ss[c + 1] - 2.0 * s0 + ss[c - 1]) / (ss[c + 1] + 2.0 * s0 + ss[c - 1] + sslim));
@@ -649,7 +653,7 @@ __device__ __forceinline__ double sa_visc_dir(const BlockDev& b, int N, int c, i
     const double* w = b.w;
     const double* vol = b.vol;
     const int cm = c - sd, cp = c + sd;
-    const double cb3Inv = 1.0 / c_prm.rsaCb3, cb2 = c_prm.rsaCb2;
+    const double cb3Inv = c_fheat[3] /* 1 / rsaCb3 */, cb2 = c_prm.rsaCb2;
     const double vc = vol[c];
     const double voli = 1.0 / vc;
     const double volmi = 2.0 / (vc + vol[cm]);
@@ -702,7 +706,7 @@ __device__ __forceinline__ double sa_source(const BlockDev& b, int N, int sJ, in
         sqrtProd = sqrt(vortx * vortx + vorty * vorty + vortz * vortz);
     }
     const double cv13 = c_prm.rsaCv1 * c_prm.rsaCv1 * c_prm.rsaCv1;
-    const double kar2Inv = 1.0 / (c_prm.rsaK * c_prm.rsaK);
+    const double kar2Inv = c_fheat[4];   // 1 / rsaK**2
     const double cw3 = c_prm.rsaCw3;
     const double cw36 = (cw3 * cw3 * cw3) * (cw3 * cw3 * cw3);
     const double nt = w[ITU1 * N + c];

@@ -73,7 +73,7 @@ __device__ __forceinline__ void sa_diff_coef(const BlockDev& b, int N, int c, in
     const double* w = b.w;
     const double* vol = b.vol;
     const int cm = c - sd, cp = c + sd;
-    const double cb3Inv = 1.0 / c_prm.rsaCb3, cb2 = c_prm.rsaCb2;
+    const double cb3Inv = c_fheat[3] /* 1 / rsaCb3 */, cb2 = c_prm.rsaCb2;
     const double vc = vol[c];
     const double voli = 1.0 / vc;
     const double volmi = 2.0 / (vc + vol[cm]);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128, 4) k_sa_rhs(Dims d, BlockDev b, double fa
         ss = sqrt(vortx * vortx + vorty * vorty + vortz * vortz);
     }
     const double cv13 = c_prm.rsaCv1 * c_prm.rsaCv1 * c_prm.rsaCv1;
-    const double kar2Inv = 1.0 / (c_prm.rsaK * c_prm.rsaK);
+    const double kar2Inv = c_fheat[4];   // 1 / rsaK**2
     const double cw3 = c_prm.rsaCw3;
     const double cw36 = (cw3 * cw3 * cw3) * (cw3 * cw3 * cw3);
     const double nut = w[5 * N + c];
