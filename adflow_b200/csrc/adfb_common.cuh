@@ -100,8 +100,9 @@ __constant__ AdfbParams c_prm;
 // viscousFlux (formed on the host), [2] the shock-sensor floor sslim = 0.001 pInfCorr / rhoInf**gamma (blockette.F90:3060-3070;
 // formed ON THE DEVICE by k_param_consts, so that it is bit for bit the value the kernels used to recompute with pow() per
 // face and thread -- one 190-instruction pow chain per face otherwise: 21 % of the tile kernel's instructions)
-// [3] = 1/rsaCb3, [4] = 1/rsaK**2 of the SA model (host quotients: correctly rounded on both sides)
-__constant__ double c_fheat[8];
+// [3] = 1/rsaCb3, [4] = 1/rsaK**2 of the SA model, [7] = 1/(gamma-1), [8] = 1e-6 gamma pInfCorr / rhoInf (host quotients: correctly
+// rounded on both sides); [5] = rhoInf**gamma / pInfCorr, [6] = sqrt(gamma pInfCorr / rhoInf) of the far-field BC (device)
+__constant__ double c_fheat[16];
 // Programmatic dependent launch: every PDL-launched kernel first waits for its predecessor (grid dependency sync: the
 // predecessor has completed and its writes are visible), then -- with ADFB_PDL_TRIGGER=1 -- signals at once that ITS
 // dependent may be launched, so that the dependent's blocks are scheduled while this kernel's last wave drains; the

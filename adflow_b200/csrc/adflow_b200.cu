@@ -407,15 +407,17 @@ int adfb_set_params(const AdfbParams* prm) {
     g.havePrm = true;
     CK(cudaMemcpyToSymbolAsync(c_prm, &g.prm, sizeof(AdfbParams), 0, cudaMemcpyHostToDevice, g.stream));
     {
-        static double fheat[8];
+        static double fheat[16];
         const double gm1 = g.prm.gammaInf - 1.0;
         fheat[0] = 1.0 / (g.prm.prandtl * gm1); fheat[1] = 1.0 / (g.prm.prandtlTurb * gm1);
         fheat[3] = 1.0 / g.prm.rsaCb3; fheat[4] = 1.0 / (g.prm.rsaK * g.prm.rsaK);
+        fheat[7] = 1.0 / gm1; fheat[8] = 0.000001 * g.prm.gammaInf * g.prm.pInfCorr / g.prm.rhoInf;
         CK(cudaMemcpyToSymbolAsync(c_fheat, fheat, sizeof fheat, 0, cudaMemcpyHostToDevice, g.stream));
         static double* dConst = nullptr;
         if (!dConst) CK(cudaMalloc((void**)&dConst, 8 * sizeof(double)));
         k_param_consts<<<1, 1, 0, g.stream>>>(dConst);   // reads the c_prm uploaded above (stream order)
         CK(cudaMemcpyToSymbolAsync(c_fheat, dConst, sizeof(double), 2 * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+        CK(cudaMemcpyToSymbolAsync(c_fheat, dConst + 1, 2 * sizeof(double), 5 * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
         CK(cudaStreamSynchronize(g.stream));
     }
     {

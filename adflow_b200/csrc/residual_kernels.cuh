@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
     if (viscous) b.aa[c] = gam * p / rho;
     if (!doRad) return;  // smoother path: radii/dtl are frozen between timeStep calls
 
-    const double clim2 = 0.000001 * gam * c_prm.pInfCorr / c_prm.rhoInf;
+    const double clim2 = c_fheat[8];   // 0.000001 * gam * pInfCorr / rhoInf
     const double adis = c_prm.adis, asf = c_prm.acousticScaleFactor;
     const double ux = b.w[N + c], uy = b.w[2 * N + c], uz = b.w[3 * N + c];
     double cc2 = gam * p / rho;
@@ -151,6 +151,11 @@ __global__ void __launch_bounds__(256) k_prep(Dims d, BlockDev b, int updateDt, 
 // parameter-only constants evaluated once per adfb_set_params with the device's own arithmetic (c_fheat[2])
 __global__ void k_param_consts(double* out) {
     out[0] = ff_sslim_eval(c_prm);
+    // bcFarfield (BCRoutines.F90:1282-1396): free-stream entropy measure and speed of sound
+    const double gam = c_prm.gammaInf;
+    const double r0 = 1.0 / c_prm.wInf[0];
+    out[1] = pow(c_prm.wInf[0], gam) / c_prm.pInfCorr;
+    out[2] = sqrt(gam * c_prm.pInfCorr * r0);
 }
 
 // ---------------------------------------------------------------------------
@@ -474,7 +479,7 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
         const double mue = porv * (b.rev[c] + b.rev[cp]);
         const double mut = mul + mue;
         const double gm1 = c_prm.gammaInf - 1.0;
-        const double heatCoef = mul * (1.0 / (c_prm.prandtl * gm1)) + mue * (1.0 / (c_prm.prandtlTurb * gm1));
+        const double heatCoef = mul * c_fheat[0] + mue * c_fheat[1];   // 1/(Pr gm1), 1/(Pr_t gm1)
         const double fracDiv = (2.0 * (1.0 / 3.0)) * (u_x + v_y + w_z);
         const double tauxx = mut * (2.0 * u_x - fracDiv), tauyy = mut * (2.0 * v_y - fracDiv), tauzz = mut * (2.0 * w_z - fracDiv);
         const double tauxy = mut * (u_y + v_x), tauxz = mut * (u_z + w_x), tauyz = mut * (v_z + w_y);
@@ -493,7 +498,7 @@ __device__ __forceinline__ void face_flux(const BlockDev& b, int N, int c, int s
         const double mue = porv * (b.rev[c] + b.rev[cp]);
         const double mut = mul + mue;
         const double gm1 = c_prm.gammaInf - 1.0;
-        const double heatCoef = mul * (1.0 / (c_prm.prandtl * gm1)) + mue * (1.0 / (c_prm.prandtlTurb * gm1));
+        const double heatCoef = mul * c_fheat[0] + mue * c_fheat[1];   // 1/(Pr gm1), 1/(Pr_t gm1)
         const int n = c, n1 = c - t1 - t2, n2 = c - t2, n3 = c - t1;
         double g[12];
         if (GAOS) {

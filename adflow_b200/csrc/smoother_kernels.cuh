@@ -274,8 +274,8 @@ __device__ __forceinline__ void bc_flow_cell(const Dims& d, const BlockDev& b, c
         case ADFB_BC_FARFIELD: {  // bcFarfield, BCRoutines.F90:1282-1396
             const double gm1 = gam - 1.0, ovgm1 = 1.0 / gm1;
             const double r0 = 1.0 / c_prm.wInf[0], u0 = c_prm.wInf[1], v0 = c_prm.wInf[2], w0 = c_prm.wInf[3];
-            const double c0s = sqrt(gam * c_prm.pInfCorr * r0);
-            const double s0 = pow(c_prm.wInf[0], gam) / c_prm.pInfCorr;
+            const double c0s = c_fheat[6];   // sqrt(gam * pInfCorr * r0)           } evaluated once per parameter set on the
+            const double s0 = c_fheat[5];    // pow(wInf[0], gam) / pInfCorr        } device (k_param_consts): same bits
             const double qn0 = u0 * n1 + v0 * n2 + w0 * n3;
             const double vn0 = qn0 - rface;
             const double rho2 = s2.r;

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) k_state_prep(Dims d, BlockDev b, int incl
     p = dmax_(p, 1.e-4 * c_prm.pInfCorr);
     b.p[c] = p;
     // whalo2's computeEtotBlock on owned cells (haloExchange.F90:174-197), fused here
-    if (etot) b.w[4 * N + c] = (1.0 / (c_prm.gammaInf - 1.0)) * p + 0.5 * rho * v2;
+    if (etot) b.w[4 * N + c] = c_fheat[7] /* 1/(gamma-1) */ * p + 0.5 * rho * v2;
     if (c_prm.equations == ADFB_EULER) return;
     if (includeHalos && (i < 1 || i > d.ie || j < 1 || j > d.je || k < 1 || k > d.ke)) return;
     const double T = p / (c_prm.RGas * rho);
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k_etot_owned(Dims d, BlockDev b) {
     if (i > d.il || j > d.jl || k > d.kl) return;
     const long long N = d.N, c = ADFB_IDX(i, j, k);
     const double r = b.w[c], u = b.w[N + c], v = b.w[2 * N + c], w = b.w[3 * N + c];
-    b.w[4 * N + c] = (1.0 / (c_prm.gammaInf - 1.0)) * b.p[c] + 0.5 * r * (u * u + v * v + w * w);
+    b.w[4 * N + c] = c_fheat[7] /* 1/(gamma-1) */ * b.p[c] + 0.5 * r * (u * u + v * v + w * w);
 }
 
 // two-pass deterministic reduction: pass 1 -> nPart partial pairs, pass 2 -> final pair
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) k_nkvec_prep(Dims d, BlockDev b, int nw, 
     double p = (c_prm.gammaInf - 1.0) * (wv[4] - 0.5 * rho * v2);
     p = dmax_(p, 1.e-4 * c_prm.pInfCorr);
     b.p[c] = p;
-    if (etot) b.w[4 * N + c] = (1.0 / (c_prm.gammaInf - 1.0)) * p + 0.5 * rho * v2;
+    if (etot) b.w[4 * N + c] = c_fheat[7] /* 1/(gamma-1) */ * p + 0.5 * rho * v2;
     if (c_prm.equations == ADFB_EULER) return;
     const double T = p / (c_prm.RGas * rho);
     const double rlv = c_prm.muSuth * ((c_prm.TSuth + c_prm.SSuth) / (T + c_prm.SSuth)) * pow(T / c_prm.TSuth, 1.5);
