@@ -43,12 +43,12 @@ sys.path.insert(0, ROOT)
 C2 = (96, 72, 64)
 # DRAM traffic of one residual step on C2 measured by ncu (profiles/r02_ncu_summary.md: sum over the four residual kernels
 # k_state_prep + k_sa + k_prep + k_flowres; round 1 had 568.1e6 over six kernels)
-NCU_TRAFFIC_BYTES = 404.0e6
+NCU_TRAFFIC_BYTES = 403.6e6
 NCU_TRAFFIC_NOTE = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the residual kernels of one step, ncu --set full capture "
                     "(profiles/)")
 # the second roof (SURVEY section 7 'report both'): the path is FP64-issue bound long before it is HBM bound
 FP64_ROOF = {"note": "B200 FP64 pipe: 64 DFMA lanes / SM / clk x 148 SMs x 1.965 GHz = 18.6 T FP64 instructions/s (37 TFLOP/s); "
-                     "percentages of the dominant kernel k_flowres from the ncu --set full capture profiles/r02_ncu_summary.md", "fp64_pipe_pct": 26.7, "issue_active_pct": 31.9}
+                     "percentages of the dominant kernel k_flowres from the ncu --set full capture profiles/r02_ncu_summary.md", "fp64_pipe_pct": 23.9, "issue_active_pct": 27.9}
 BYTES_PER_CELL = 176.0  # RANS-SA residual, metrics from x, algorithmic
 METRIC = "Mcells/s RANS-SA residual"
 
