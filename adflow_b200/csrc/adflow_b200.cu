@@ -313,7 +313,15 @@ int adfb_init(int device, const void* ncclUniqueId, int rank, int nranks) {
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     if (device < 0 || device >= n) return fail("adfb_init: device %d out of range (0..%d)", device, n - 1);
     CK(cudaSetDevice(device));
-    if (!g.stream) CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    if (!g.stream) {
+        // the library stream carries the latency-bound chains (BC levels, line solves): highest priority, so that work forked onto
+        // side streams (SA row, overlap experiments: default = lowest priority) never delays them (ADFB_STREAM_PRIO=0: default priority)
+        int prLo = 0, prHi = 0;
+        cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+        const char* e = getenv("ADFB_STREAM_PRIO");
+        const int pr = (e && e[0] == '0') ? prLo : prHi;
+        CK(cudaStreamCreateWithPriority(&g.stream, cudaStreamNonBlocking, pr));
+    }
     g.device = device; g.rank = rank; g.nranks = nranks;
     if (!g.hRed) CK(cudaMallocHost((void**)&g.hRed, 256 * sizeof(double)));
     g.err.clear();
