@@ -665,6 +665,13 @@ FHD bool ft_var_used(int v, bool viscous, int doDiss) {
 #ifndef FT_EARLY
 #define FT_EARLY 0
 #endif
+// FT_AHEAD (bits): 1 / 2 = the operands of the j / k face are requested before the i face is formed (their L2 latency hides
+// behind its arithmetic; 242-254 registers, no spills: 134 -> 128 us on C2, default 3); 4 = the nodal operands of the next plane at
+// the end of the step (spills 60 bytes: 138 us, off); 8 = the i-face operands before the barrier that follows the nodal phase
+// (129.5 us with 3: no gain, off)
+#ifndef FT_AHEAD
+#define FT_AHEAD 3
+#endif
 template <bool VISCOUS, bool MERGED>
 FHD void ft_step_a(const Dims& d, const BlockDev& b, const FTile& t, const FCtx& x, int k, int kb, const double* A, const double* B, FSmem& sm,
                    FRegs& r, FStep& st, int doDiss, bool doIJ) {
@@ -677,9 +684,11 @@ FHD void ft_step_a(const Dims& d, const BlockDev& b, const FTile& t, const FCtx&
         ft_load_face_k(d, b, x, k, visc, doDiss, pf, st.gk);
         if (visc) ft_nodal(t, x, A, B, st.gn, sm, r, doIJ);
     } else if (visc) {
-        ft_load_nodal(d, b, x, k, pf, st.gn);
+        if (!(FT_AHEAD & 4)) ft_load_nodal(d, b, x, k, pf, st.gn);   // bit 4: requested at the end of the previous step (and in the prologue)
         ft_nodal(t, x, A, B, st.gn, sm, r, doIJ);
     }
+    // bit 8: the i-face operands are requested here, before the barrier that follows the nodal phase
+    if (!FT_EARLY && (FT_AHEAD & 8) && doIJ && x.fi) ft_load_face(d, b, x, k, 0, visc, pf, st.gi);
 }
 // i, j and k faces between the two barriers (`part` is kept for experiments: 0 = i face only, 1 = j + k faces only, 2 = all)
 template <bool VISCOUS, bool MERGED>
@@ -696,22 +705,27 @@ FHD void ft_step_b(const AdfbParams& P, const Dims& d, const BlockDev& b, const 
         ow.rev = visc ? A[FV_REV * FT_S2 + x.o2] : 0.0;
         ow.aa = visc ? A[FV_AA * FT_S2 + x.o2] : 0.0;
     }
+    // FT_AHEAD bits 1 / 2: the face operands of the j and k faces are requested BEFORE the i face is formed
+    if (!FT_EARLY && part == 2) {
+        if ((FT_AHEAD & 1) && doIJ && x.fj) ft_load_face(d, b, x, k, 1, visc, pf, st.gj);
+        if ((FT_AHEAD & 2) && x.own) ft_load_face_k(d, b, x, k, visc, doDiss, pf, st.gk);
+    }
     if (part != 1) {
         if (FT_EARLY && visc && k < kb) ft_load_nodal(d, b, x, k + 1, k + 1 < kb, st.gn);   // for the next step's nodal phase
         if (doIJ && x.fi) {
-            if (!FT_EARLY) ft_load_face(d, b, x, k, 0, visc, pf, st.gi);
+            if (!FT_EARLY && !(FT_AHEAD & 8)) ft_load_face(d, b, x, k, 0, visc, pf, st.gi);
             ft_face_ij<VISCOUS>(P, t, x, 0, A, sm, st.gi, ow, rFil, doDiss, fc, fd);
             ft_store_flux<MERGED>(x, sm, 0, fc, fd);
         }
     }
     if (part != 0) {
         if (doIJ && x.fj) {
-            if (!FT_EARLY) ft_load_face(d, b, x, k, 1, visc, pf, st.gj);
+            if (!FT_EARLY && !((FT_AHEAD & 1) && part == 2)) ft_load_face(d, b, x, k, 1, visc, pf, st.gj);
             ft_face_ij<VISCOUS>(P, t, x, 1, A, sm, st.gj, ow, rFil, doDiss, fc, fd);
             ft_store_flux<MERGED>(x, sm, 5, fc, fd);
         }
         if (x.own) {
-            if (!FT_EARLY) ft_load_face_k(d, b, x, k, visc, doDiss, pf, st.gk);
+            if (!FT_EARLY && !((FT_AHEAD & 2) && part == 2)) ft_load_face_k(d, b, x, k, visc, doDiss, pf, st.gk);
             ft_face_k<VISCOUS>(P, t, x, A, B, sm, st.gk, ow, r, rFil, doDiss, fc, fd);
 #pragma unroll
             for (int l = 0; l < 5; l++) {
@@ -720,6 +734,7 @@ FHD void ft_step_b(const AdfbParams& P, const Dims& d, const BlockDev& b, const 
             }
         }
     }
+    if (!FT_EARLY && (FT_AHEAD & 4) && visc && k < kb && part != 0) ft_load_nodal(d, b, x, k + 1, k + 1 < kb, st.gn);
 }
 
 // ---------------------------------------------------------------------------
@@ -900,7 +915,7 @@ __global__ void __launch_bounds__(FT_LB, FT_MINB) k_flowres
     FRegs r;
     FStep st;
     ft_prologue_regs(c_prm, d, b, x, ka - 1, r, doDiss, VISCOUS);
-    if (FT_EARLY && visc) ft_load_nodal(d, b, x, ka - 1, true, st.gn);
+    if ((FT_EARLY || (FT_AHEAD & 4)) && visc) ft_load_nodal(d, b, x, ka - 1, true, st.gn);
     wait_plane(ka - 1);
     wait_plane(ka);
     __syncthreads();
