@@ -684,7 +684,7 @@ FHD void ft_step_a(const Dims& d, const BlockDev& b, const FTile& t, const FCtx&
         ft_load_face_k(d, b, x, k, visc, doDiss, pf, st.gk);
         if (visc) ft_nodal(t, x, A, B, st.gn, sm, r, doIJ);
     } else if (visc) {
-        if (!(FT_AHEAD & 4)) ft_load_nodal(d, b, x, k, pf, st.gn);   // bit 4: requested at the end of the previous step (and in the prologue)
+        if (!(FT_AHEAD & (4 | 16))) ft_load_nodal(d, b, x, k, pf, st.gn);   // bits 4 / 16: requested during the previous step (and in the prologue)
         ft_nodal(t, x, A, B, st.gn, sm, r, doIJ);
     }
     // bit 8: the i-face operands are requested here, before the barrier that follows the nodal phase
@@ -915,7 +915,7 @@ __global__ void __launch_bounds__(FT_LB, FT_MINB) k_flowres
     FRegs r;
     FStep st;
     ft_prologue_regs(c_prm, d, b, x, ka - 1, r, doDiss, VISCOUS);
-    if ((FT_EARLY || (FT_AHEAD & 4)) && visc) ft_load_nodal(d, b, x, ka - 1, true, st.gn);
+    if ((FT_EARLY || (FT_AHEAD & (4 | 16))) && visc) ft_load_nodal(d, b, x, ka - 1, true, st.gn);
     wait_plane(ka - 1);
     wait_plane(ka);
     __syncthreads();
@@ -935,6 +935,8 @@ __global__ void __launch_bounds__(FT_LB, FT_MINB) k_flowres
         __syncthreads();   // fluxes visible; G / EE and the slot of plane k are free; (3 slots) plane k+2 has landed
         if (FT_NSLOT >= 3) { if (k + 3 <= kb + 1) load_plane(k + 3); }
         else if (k + 2 <= kb + 1) load_plane(k + 2);
+        // bit 16: the nodal operands of the next plane are requested before the divergence of this one is formed
+        if (!FT_EARLY && (FT_AHEAD & 16) && visc && k < kb) ft_load_nodal(d, b, x, k + 1, k + 1 < kb, st.gn);
         if (doIJ) ft_div<MERGED>(d, b, t, x, k, sm, r, st, rFil, persistFw, mf, c_prm.turbResScale);
 #pragma unroll
         for (int l = 0; l < 10; l++) r.kprev[l] = st.kp[l];

@@ -79,7 +79,7 @@ int emul_flowres(int nx, int ny, int nz, const AdfbParams* prm, const EmulArrays
                     ctx[tid] = ft_ctx(d, t, tid, bx, by);
                     memset(&steps[tid], 0, sizeof(FStep));
                     ft_prologue_regs(P, d, b, ctx[tid], ka - 1, regs[tid], doDiss, viscous);
-                    if ((FT_EARLY || (FT_AHEAD & 4)) && visc) ft_load_nodal(d, b, ctx[tid], ka - 1, true, steps[tid].gn);
+                    if ((FT_EARLY || (FT_AHEAD & (4 | 16))) && visc) ft_load_nodal(d, b, ctx[tid], ka - 1, true, steps[tid].gn);
                 }
                 load_plane(ka - 1); load_plane(ka);
                 if (FT_NSLOT >= 3) load_plane(ka + 1);
