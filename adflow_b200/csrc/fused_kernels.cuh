@@ -756,35 +756,35 @@ static inline bool ftile_fits(const FTile& t) { return t.nT <= FT_MAXT && t.PX *
 static inline FTile ftile_choose(const Dims& d, bool tma, int nSM) {
     int ox = 0, oy = 0, okc = 0;
     if (const char* e = getenv("ADFB_TILE")) sscanf(e, "%d,%d,%d", &ox, &oy, &okc);
-    FTile best = ftile_make(8, 4, d.nz, tma);
-    double bestScore = -1.0;
-    for (int TX = 4; TX <= 128; TX++) {
-        for (int TY = 3; TY <= 64; TY++) {
-            if (ox > 0 && (TX != ox || TY != oy)) continue;
-            FTile t = ftile_make(TX, TY, d.nz, tma);
-            if (!ftile_fits(t) || (tma && !(TX & 1))) continue;   // TMA: the tile origin bx*(TX-1) must be 16-byte aligned
-            const int nti = (d.nx + TX - 2) / (TX - 1), ntj = (d.ny + TY - 2) / (TY - 1);
-            const double useful = (double)d.nx * d.ny / ((double)nti * ntj * t.nT);   // owned cells per thread slot
-            // rows that are whole half-warps keep the 64-bit shared-memory accesses conflict free
-            const double bank = (TX % 16 == 0) ? 1.0 : 0.93;
-            const double score = useful * bank * (0.55 + 0.45 * t.nT / (double)FT_MAXT);
-            if (score > bestScore) { bestScore = score; best = t; }
+    // One CTA per SM, and the time of a k plane grows with the warps of the CTA (the kernel is issue bound inside the CTA): measured
+    // 2.3 + 0.69 x warps [us] per plane.  The cost of a choice is waves x (planes per chunk + the prologue step, ~0.45 of a plane) x that
+    // time; on C2: 13 x 19 threads, 5-plane chunks (3 waves of 8 warps) model 127.9 / measured 128.1 us; 17 x 13 threads, 16-plane chunks
+    // (1 wave of 7 warps) 117.3 / 117.5 us; the same tile with 8-plane chunks (2 waves) 120.5 / 122.4 us.
+    FTile best = ftile_make(tma ? 9 : 8, 4, d.nz, tma);
+    double bestCost = 1e300;
+    for (int pass = 0; pass < 2 && bestCost >= 1e300; pass++) {   // pass 0 honours ADFB_TILE, pass 1 (override does not fit) searches freely
+        for (int TX = 4; TX <= 128; TX++) {
+            for (int TY = 3; TY <= 64; TY++) {
+                if (pass == 0 && ox > 0 && (TX != ox || TY != oy)) continue;
+                FTile t = ftile_make(TX, TY, d.nz, tma);
+                if (!ftile_fits(t) || (tma && !(TX & 1))) continue;   // TMA: the tile origin bx*(TX-1) must be 16-byte aligned
+                const int nti = (d.nx + TX - 2) / (TX - 1), ntj = (d.ny + TY - 2) / (TY - 1);
+                const long long cols = (long long)nti * ntj;
+                // rows that are whole half-warps keep the 64-bit shared-memory accesses conflict free
+                const double bank = (TX % 16 == 0) ? 1.0 : 0.93;
+                for (int n = 1; n <= d.nz; n++) {
+                    int kc = (d.nz + n - 1) / n;
+                    if (pass == 0 && okc > 0) kc = okc;
+                    if (kc < 2 && n > 1) break;
+                    const long long ctas = cols * ((d.nz + kc - 1) / kc);
+                    const long long waves = (ctas + nSM - 1) / nSM;
+                    const double cost = (double)waves * (kc + 0.45) * (2.3 + 0.69 * (t.nT / 32)) / bank;
+                    if (cost < bestCost - 1e-9) { bestCost = cost; best = t; best.kChunk = kc; }
+                    if (pass == 0 && okc > 0) break;
+                }
+            }
         }
     }
-    const int nti = (d.nx + best.TX - 2) / (best.TX - 1), ntj = (d.ny + best.TY - 2) / (best.TY - 1);
-    const int cols = nti * ntj;
-    int nkc = 1;
-    double bestEff = -1.0;
-    for (int n = 1; n <= d.nz; n++) {
-        const int kc = (d.nz + n - 1) / n;
-        if (kc < 4 && n > 1) break;
-        const long long ctas = (long long)cols * ((d.nz + kc - 1) / kc);
-        const long long waves = (ctas + nSM - 1) / nSM;
-        const double eff = (double)ctas / (double)(waves * nSM) * ((double)kc / (kc + 0.45));   // prologue step ~ 0.45 of a plane
-        if (eff > bestEff + 1e-9) { bestEff = eff; nkc = n; }
-    }
-    best.kChunk = (d.nz + nkc - 1) / nkc;
-    if (okc > 0) best.kChunk = okc;
     return best;
 }
 
