@@ -1174,7 +1174,7 @@ static bool ff_pinned(const void* p) {
 }
 static int form_function_pipe_slabs() {   // read at every call: tests switch it
     const char* e = getenv("ADFB_FF_PIPE");
-    return e ? atoi(e) : 8;
+    return e ? atoi(e) : 6;   // C2, final tile kernel: 6 slabs 0.660 ms, 8 slabs 0.694 ms, 10 slabs 0.696 ms per call
 }
 // the stream work of one pipelined call (captured into a CUDA graph per (wVec, rVec) pair: ~15 launches per slab otherwise
 // cost more host time than the GPU needs for them).  Front end of a slab (setW, p / rlv / rev, BCs, time step / sensor) on the
