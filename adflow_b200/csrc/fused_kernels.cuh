@@ -40,8 +40,9 @@
 #endif
 
 #ifndef FT_MAXT
-#define FT_MAXT 256   // max threads per CTA of the tile kernel (1 CTA / SM; 246 registers, no spills; 384 threads with 168 registers
-                      // and spills measured 160 us against 155 us on C2)
+#define FT_MAXT 256   // max threads per CTA of the tile kernel (1 CTA / SM; 252 registers, no spills; final tree on C2: 117 us with the
+                      // 17 x 13 tile ftile_choose picks; 320 / 384 threads at 168 registers spill: 171 / 161 us; two CTAs of 128
+                      // threads per SM (-DFT_MAXT=128 -DFT_S2=224 -DFT_MINB=2) 111 us)
 #endif
 
 // ring variables (shared-memory state tiles)
