@@ -923,7 +923,9 @@ static int launch_residual_core(const Dims& d, const BlockDev& b, const AdfbPara
     // selects it anyway)
     static int fusedSmoother = -1;
     if (fusedSmoother < 0) { const char* e = getenv("ADFB_FUSED_SMOOTHER"); fusedSmoother = e ? atoi(e) : 0; }
-    if (flowRes && fused_mode() > 0 && (!persistFw || fusedSmoother) && !b.coarse && prm.spaceDiscr == ADFB_DISS_SCALAR && !dissApprox && !viscApprox && !initWr &&
+    // ADFB_FUSED_SMOOTHER: 1 = the tile kernel for every smoother residual, 2 = only for the stages that form the dissipative and viscous
+    // fluxes (rFil /= 0); the central-only stages keep k_faces + k_div, which are cheaper there
+    if (flowRes && fused_mode() > 0 && (!persistFw || fusedSmoother == 1 || (fusedSmoother == 2 && doDiss)) && !b.coarse && prm.spaceDiscr == ADFB_DISS_SCALAR && !dissApprox && !viscApprox && !initWr &&
         !(flags & ADFB_RES_STORE_WALL) && !split_faces()) {
         KT_BEGIN(K_RESID, stream);
         const int rc = launch_flowres_tile(d, b, prm, (int)((b.p - b.w) / d.N), rFil, doDiss, !persistFw, persistFw, stream, mf);
