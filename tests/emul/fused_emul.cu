@@ -20,6 +20,14 @@ struct EmulArrays {
     int32_t* iblank;
 };
 
+// the tile of the host chooser for a block (for the tests): out = TX, TY, kChunk, nT
+int emul_choose(int nx, int ny, int nz, int tma, int nSM, int* out) {
+    const Dims d = make_dims(nx, ny, nz);
+    const FTile t = ftile_choose(d, tma != 0, nSM);
+    out[0] = t.TX; out[1] = t.TY; out[2] = t.kChunk; out[3] = t.nT;
+    return ftile_fits(t) ? 0 : 1;
+}
+
 int emul_flowres(int nx, int ny, int nz, const AdfbParams* prm, const EmulArrays* a, int TX, int TY, int kChunk, double rFil, int doDiss,
                  int merged, int persistFw) {
     const Dims d = make_dims(nx, ny, nz);
@@ -34,8 +42,11 @@ int emul_flowres(int nx, int ny, int nz, const AdfbParams* prm, const EmulArrays
             for (int i = 0; i <= d.ib; i++) geom_cell(d, b, i, j, k);
     const AdfbParams& P = *prm;
     const bool viscous = P.equations != ADFB_EULER;
-    FTile t = ftile_make(TX, TY, kChunk, false);
+    // TX == 0: the tile the library's host chooser picks for this block (ftile_choose with the TMA constraint: odd TX), on kChunk SMs
+    FTile t = TX > 0 ? ftile_make(TX, TY, kChunk, false) : ftile_choose(d, true, kChunk > 0 ? kChunk : 148);
+    t.useTma = 0;
     if (!ftile_fits(t)) return 2;
+    if (TX == 0 && (!(t.TX & 1) || t.kChunk < 1)) return 3;
     const int nti = (d.nx + t.TX - 2) / (t.TX - 1), ntj = (d.ny + t.TY - 2) / (t.TY - 1), nkc = (d.nz + t.kChunk - 1) / t.kChunk;
     std::vector<double> smem(FT_SMEM_DOUBLES + (size_t)(FT_NFLUX_SPLIT - FT_NFLUX) * FT_S0);
     FSmem sm;

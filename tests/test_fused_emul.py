@@ -77,6 +77,23 @@ def test_emulated_tile_kernel_matches_oracle_rans(shape, tile):
         assert rel_l2(dw[ow + (l,)], ho.dw[ow + (l,)]) < 1e-12, l
 
 
+@pytest.mark.parametrize("shape,n_sm", [((24, 16, 12), 148), ((20, 14, 9), 148), ((33, 17, 8), 16), ((12, 10, 8), 4)])
+def test_tiles_of_the_host_chooser(shape, n_sm):
+    """ftile_choose (tile shape and k chunk from the cost model, TMA constraint: odd TX) picks small tiles for small blocks and for
+    few SMs; whatever it picks must fit the compile-time arrays, cover the block, and give the oracle's residual."""
+    prm, hb = case(*shape)
+    L = C.CDLL(_build())
+    out = (C.c_int * 4)()
+    assert L.emul_choose(shape[0], shape[1], shape[2], 1, n_sm, out) == 0
+    TX, TY, kc, nT = list(out)
+    assert TX % 2 == 1 and TX >= 3 and TY >= 3 and 1 <= kc <= shape[2] and nT % 32 == 0 and nT <= 256
+    ho = oracle_residual(prm, hb, FLOW | TURB)
+    dw, _ = run_emul(prm, hb, ho, 0, 0, n_sm)          # TX = 0: the chooser's tile on n_sm SMs
+    ow = hb.d.owned()
+    for l in range(5):
+        assert rel_l2(dw[ow + (l,)], ho.dw[ow + (l,)]) < 1e-12, l
+
+
 def test_emulated_tile_kernel_euler():
     prm, hb = case(12, 8, 10, {"equationType": "Euler"})
     ho = oracle_residual(prm, hb, FLOW)
