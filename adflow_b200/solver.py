@@ -254,15 +254,26 @@ class ADFLOW_B200:
         """transferToFineGrid(corrections=.false.): the solution of ground level fine_level + 1 -> fine_level"""
         check(self.L.adfb_mg_prolong_solution(fine_level), "adfb_mg_prolong_solution")
 
+    @staticmethod
+    def fmgSchedule(mg_start_level, cycle="sg"):
+        """Ground levels of the full-multigrid start-up with the cycle each of them runs: the strategy of `cycle` ('sg', '<n>v',
+        '<n>w') shortened to the levels at and below the ground level (setCycleStrategy works on nMGLevels - groundLevel + 1
+        levels, src/solver/multiGrid.F90:957-1030).  Returns [(groundLevel, spec), ...] for groundLevel = mgStartlevel .. 2."""
+        n_lev = 1 if cycle.lower() == "sg" else int(cycle[:-1])
+        if mg_start_level < 1 or mg_start_level > max(n_lev, 1):
+            raise ValueError("mgStartlevel %d outside 1..%d" % (mg_start_level, max(n_lev, 1)))
+        out = []
+        for ground in range(mg_start_level, 1, -1):
+            left = n_lev - ground + 1          # levels ground .. n_lev take part
+            out.append((ground, "sg" if left < 2 else "%d%s" % (left, cycle[-1].lower())))
+        return out
+
     def fullMultigridStartUp(self, mg_start_level, n_cycles_coarse, cycle="sg", smoother="RK", n_subiterations=1):
         """The full-multigrid start-up of `solver` (src/solver/solvers.F90:63-117): nCyclesCoarse cycles of executeMGCycle on
-        every ground level mgStartlevel, ..., 2 (the strategy of `cycle` shortened to the levels below the ground level),
-        each followed by transferToFineGrid(.false.); leaves the ground level at 1."""
-        n_lev = 1 if cycle.lower() == "sg" else int(cycle[:-1])
-        for ground in range(mg_start_level, 1, -1):
+        every ground level mgStartlevel, ..., 2 (fmgSchedule), each followed by transferToFineGrid(.false.); leaves the ground
+        level at 1."""
+        for ground, spec in self.fmgSchedule(mg_start_level, cycle):
             self.setGroundLevel(ground)
-            left = n_lev - ground + 1          # levels ground .. n_lev take part
-            spec = "sg" if left < 2 else "%d%s" % (left, cycle[-1])
             cyc = self.cycleStrategy(spec)
             for _ in range(n_cycles_coarse):
                 self.mgCycle(cyc, smoother, n_subiterations)

@@ -28,6 +28,21 @@ def test_cycle_strategies(n):
         ADFLOW_B200.cycleStrategy("1v")
 
 
+def test_full_multigrid_schedule():
+    """ground levels of the start-up (solver loop, src/solver/solvers.F90:63) and the cycle each of them runs"""
+    assert ADFLOW_B200.fmgSchedule(1, "3w") == []                       # mgStartlevel = 1: nothing to do
+    assert ADFLOW_B200.fmgSchedule(3, "3w") == [(3, "sg"), (2, "2w")]   # coarsest level single grid, then a 2-level W cycle
+    assert ADFLOW_B200.fmgSchedule(2, "4v") == [(2, "3v")]
+    assert ADFLOW_B200.fmgSchedule(4, "4V") == [(4, "sg"), (3, "2v"), (2, "3v")]
+    for _, spec in ADFLOW_B200.fmgSchedule(4, "4w"):
+        cyc = ADFLOW_B200.cycleStrategy(spec)
+        assert cyc[0] == 0 and np.cumsum(cyc)[-1] == 0
+    with pytest.raises(ValueError):
+        ADFLOW_B200.fmgSchedule(3, "2v")                                 # start level beyond the cycle's levels
+    with pytest.raises(ValueError):
+        ADFLOW_B200.fmgSchedule(2, "sg")
+
+
 @pytest.mark.parametrize("nx", [2, 5, 8, 9])
 def test_transfer_tables(nx):
     keep = syn.mg_kept_nodes(nx)
